@@ -1,0 +1,224 @@
+"""ctypes/numpy front end of the CPU oracle (oracle/pyro_oracle.c).  TEST INFRASTRUCTURE ONLY:
+importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs -- never from pyro2_b200/.
+
+Arrays cross this interface in the reference's own layout ``[i, j, n]`` (x slowest, variable
+fastest -- pyro/mesh/patch.py:450-452) and are transposed to the oracle's SoA planes here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
+            "periodic": 3}
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "pyro_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class CompParams(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double),
+                ("delta", C.c_double), ("cvisc", C.c_double), ("limiter", C.c_int),
+                ("use_flattening", C.c_int), ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int)]
+
+
+_STAGE_NAMES = ["q", "xi", "ldx", "ldy", "Uxl_hat", "Uxr_hat", "Uyl_hat", "Uyr_hat", "Fx_t", "Fy_t",
+                "Uxl", "Uxr", "Uyl", "Uyr", "Fx", "Fy"]
+
+
+class CompStages(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _STAGE_NAMES]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        dp = C.c_void_p
+        for name in ("orc_fill_ghost_f64", "orc_fill_ghost_i64"):
+            f = getattr(L, name)
+            f.argtypes = [dp] + [C.c_int] * 7 + [dp] * 4 + [C.c_double] * 2
+            f.restype = None
+        L.orc_cfl_dt.argtypes = [dp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4
+        L.orc_cfl_dt.restype = C.c_double
+        L.orc_compressible_step.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                            C.c_double, C.POINTER(CompParams), C.POINTER(CompStages)]
+        L.orc_compressible_step.restype = C.c_int
+        L.orc_mg_create.argtypes = [C.c_int, C.POINTER(C.c_int * 4)] + [C.c_double] * 6 + [C.c_int] * 2
+        L.orc_mg_create.restype = C.c_void_p
+        L.orc_mg_destroy.argtypes = [C.c_void_p]
+        L.orc_mg_nlevels.argtypes = [C.c_void_p]
+        L.orc_mg_nlevels.restype = C.c_int
+        L.orc_mg_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_mg_plane.restype = C.POINTER(C.c_double)
+        L.orc_mg_set_bc_values.argtypes = [C.c_void_p, C.c_int, dp]
+        for name in ("orc_mg_residual", "orc_mg_restrict", "orc_mg_prolong_correct", "orc_mg_vcycle"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+            getattr(L, name).restype = None
+        L.orc_mg_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_mg_smooth.restype = None
+        L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
+        L.orc_norm.restype = C.c_double
+        L.orc_mg_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp]
+        L.orc_mg_solve.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _bc4(bc):
+    """bc: 4 names (xlb, xrb, ylb, yrb) or an object with those attributes"""
+    if hasattr(bc, "xlb"):
+        bc = (bc.xlb, bc.xrb, bc.ylb, bc.yrb)
+    return [BC_CODES[b] for b in bc]
+
+
+def fill_ghost(a, ng, bc, values=(None, None, None, None), dx=1.0, dy=1.0):
+    """in-place ghost fill of one 2-d plane ``a[qx, qy]`` (float64 or int64);
+    pyro/mesh/array_indexer.py:150-274"""
+    assert a.ndim == 2 and a.flags.c_contiguous
+    qx, qy = a.shape
+    codes = _bc4(bc)
+    vals = [None if v is None else np.ascontiguousarray(v, dtype=a.dtype) for v in values]
+    if a.dtype == np.float64:
+        f = lib().orc_fill_ghost_f64
+    elif a.dtype == np.int64:
+        f = lib().orc_fill_ghost_i64
+    else:
+        raise TypeError(a.dtype)
+    f(_ptr(a), qx - 2 * ng, qy - 2 * ng, ng, *codes, *[_ptr(v) for v in vals], dx, dy)
+    return a
+
+
+def to_planes(U_ijn):
+    return np.ascontiguousarray(np.moveaxis(np.asarray(U_ijn, dtype=np.float64), 2, 0))
+
+
+def from_planes(P):
+    return np.ascontiguousarray(np.moveaxis(P, 0, 2))
+
+
+def cfl_dt(U_ijn, ng, dx, dy, gamma, cfl):
+    P = to_planes(U_ijn)
+    _, qx, qy = P.shape
+    return lib().orc_cfl_dt(_ptr(P), qx - 2 * ng, qy - 2 * ng, ng, dx, dy, gamma, cfl)
+
+
+def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
+                no_avisc_xhi=1, no_avisc_yhi=1):
+    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi)
+
+
+def compressible_step(U_ijn, ng, dx, dy, dt, params=None, stages=False, planes=False):
+    """one evolve() on a ghost-filled state; returns the new state (and the per-stage arrays).
+    ``planes=True``: U is already SoA ``[n, i, j]`` and is updated in place (no transposes)."""
+    params = params or comp_params()
+    P = U_ijn if planes else to_planes(U_ijn)
+    assert P.flags.c_contiguous and P.dtype == np.float64
+    _, qx, qy = P.shape
+    st = CompStages()
+    out = {}
+    if stages:
+        for name in _STAGE_NAMES:
+            nvar = 1 if name == "xi" else 4
+            out[name] = np.zeros((nvar, qx, qy))
+            setattr(st, name, out[name].ctypes.data)
+    rc = lib().orc_compressible_step(_ptr(P), qx - 2 * ng, qy - 2 * ng, ng, dx, dy, dt,
+                                     C.byref(params), C.byref(st) if stages else None)
+    if rc:
+        raise AssertionError("invalid state (rho <= 0 or e <= 0)")
+    res = P if planes else from_planes(P)
+    if stages:
+        return res, {k: (v[0] if k == "xi" else from_planes(v)) for k, v in out.items()}
+    return res
+
+
+class MG:
+    """oracle multigrid hierarchy; mirrors the call surface the tests need from
+    pyro/multigrid/MG.py (init_zeros/init_solution/init_RHS/solve/v_cycle/get_solution)"""
+
+    def __init__(self, nx, bc=("dirichlet",) * 4, alpha=0.0, beta=-1.0, xmin=0.0, xmax=1.0,
+                 ymin=0.0, ymax=1.0, nsmooth=10, nsmooth_bottom=50):
+        self.nx = nx
+        codes = (C.c_int * 4)(*_bc4(bc))
+        self._h = lib().orc_mg_create(nx, C.byref(codes), alpha, beta, xmin, xmax, ymin, ymax,
+                                      nsmooth, nsmooth_bottom)
+        self.nlevels = lib().orc_mg_nlevels(self._h)
+        assert 2 ** self.nlevels == nx, "nx must be a power of two"
+        self.dx = (xmax - xmin) / nx
+        self.dy = (ymax - ymin) / nx
+        self.source_norm = 0.0
+        self.max_cycles = 100
+        self.num_cycles = 0
+        self.residuals = []
+        self.relative_errors = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_mg_destroy(self._h)
+            self._h = None
+
+    def plane(self, level, which):
+        n = 2 ** (level + 1) + 2
+        idx = {"v": 0, "f": 1, "r": 2}[which]
+        return np.ctypeslib.as_array(lib().orc_mg_plane(self._h, level, idx), shape=(n, n))
+
+    def set_bc_values(self, side, vals):
+        v = None if vals is None else np.ascontiguousarray(vals, dtype=np.float64)
+        lib().orc_mg_set_bc_values(self._h, {"xl": 0, "xr": 1, "yl": 2, "yr": 3}[side], _ptr(v))
+
+    def init_zeros(self):
+        self.plane(self.nlevels - 1, "v")[:] = 0.0
+
+    def init_solution(self, data):
+        self.plane(self.nlevels - 1, "v")[:] = data
+
+    def init_RHS(self, data):
+        f = self.plane(self.nlevels - 1, "f")
+        f[:] = data
+        self.source_norm = self.norm(f)
+
+    def norm(self, a):
+        a = np.ascontiguousarray(a)
+        return lib().orc_norm(_ptr(a), a.shape[0] - 2, self.dx, self.dy)
+
+    def smooth(self, level, n):
+        lib().orc_mg_smooth(self._h, level, n)
+
+    def residual(self, level):
+        lib().orc_mg_residual(self._h, level)
+
+    def restrict(self, level):
+        lib().orc_mg_restrict(self._h, level)
+
+    def prolong_correct(self, level):
+        lib().orc_mg_prolong_correct(self._h, level)
+
+    def v_cycle(self, level=None):
+        lib().orc_mg_vcycle(self._h, self.nlevels - 1 if level is None else level)
+
+    def solve(self, rtol=1.e-11):
+        res = np.zeros(self.max_cycles)
+        rel = np.zeros(self.max_cycles)
+        self.num_cycles = lib().orc_mg_solve(self._h, rtol, self.source_norm, self.max_cycles,
+                                             _ptr(res), _ptr(rel))
+        self.residuals = list(res[:self.num_cycles])
+        self.relative_errors = list(rel[:self.num_cycles])
+        self.residual_error = self.residuals[-1] if self.residuals else 1.e33
+        self.relative_error = self.relative_errors[-1] if self.relative_errors else 1.e33
+
+    def get_solution(self):
+        return self.plane(self.nlevels - 1, "v").copy()
