@@ -1,0 +1,108 @@
+/*
+ * pyro2b200.h -- C ABI of libpyro2b200.so: the B200 (sm_100a) implementation of pyro2's two
+ * data-parallel hot paths.  Plain C, plain pointers and sizes, no torch / C++ types.
+ *
+ * pyro2 is pure Python: it has no FFI or plugin registry to bind against, so each
+ * entry point below names the reference *Python* interface it replaces (file:line relative to the
+ * pyro2 tree).  The Python host side (pyro2_b200/) mirrors those interfaces signature for
+ * signature and calls these functions through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocations); the library never
+ *     frees caller memory.  Exceptions: p2b_last_error() returns a host string.
+ *   - every call is asynchronous on the given cudaStream_t (passed as void*).
+ *   - return 0 on success, P2B_EINVAL (-1) for a bad argument, P2B_ECUDA (-2) for a CUDA error
+ *     (text via p2b_last_error()).  Invalid-state detection (the reference's assert at
+ *     compressible/simulation.py:71) is reported through a device-side status word, see below.
+ *   - state layout: structure of arrays.  A "state" is nvar planes; plane n starts at
+ *     base + n*plane_stride; element (i, j) of a plane is at i*pitch + j, x = i is the slow axis,
+ *     y = j is contiguous (the reference indexes [i, j, n]; pyro/mesh/patch.py:450-452).
+ *     pitch must be even (rows 16-byte aligned for the TMA bulk copies), base 16-byte aligned.
+ *   - boundary-condition codes: pyro/mesh/boundary.py names mapped as
+ *       outflow / neumann -> P2B_BC_OUTFLOW, reflect-even -> P2B_BC_REFLECT_EVEN,
+ *       reflect-odd / dirichlet -> P2B_BC_REFLECT_ODD, periodic -> P2B_BC_PERIODIC,
+ *       P2B_BC_NONE leaves that side untouched (interior slab boundary in a decomposed run).
+ */
+#ifndef PYRO2B200_H
+#define PYRO2B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2B_OK 0
+#define P2B_EINVAL (-1)
+#define P2B_ECUDA (-2)
+
+enum { P2B_BC_OUTFLOW = 0, P2B_BC_REFLECT_EVEN = 1, P2B_BC_REFLECT_ODD = 2, P2B_BC_PERIODIC = 3,
+       P2B_BC_NONE = 4 };
+
+typedef struct {
+    int nx, ny, ng;          /* interior zones and ghost width (pyro/mesh/patch.py:62-117) */
+    int pitch;               /* elements between consecutive i rows (>= ny + 2 ng) */
+    long long plane_stride;  /* elements between consecutive variables */
+    double dx, dy;
+} p2b_grid;
+
+/* compressible/_defaults + eos.gamma: the runtime parameters the sweep consumes */
+typedef struct {
+    double gamma;
+    double z0, z1, delta;    /* flattening */
+    double cvisc;
+    int limiter;             /* 0 none, 1 MC 2nd order, 2 MC 4th order */
+    int use_flattening;
+    int no_avisc_xhi;        /* 1 on the global +x face: reference leaves avisco_x unset there */
+    int no_avisc_yhi;        /*   (pyro/compressible/interface.py:366-367); 0 on interior slab faces */
+} p2b_comp_params;
+
+/* device scratch the sweep needs, 8 x 64-bit words owned by the caller:
+ *   [0] bits of max(|u|+cs) over the cells written, [1] bits of max(|v|+cs)   (for the next dt)
+ *   [2] task counter (work distribution), [3] status: nonzero = invalid state seen
+ *   [4..7] reserved */
+#define P2B_SCRATCH_WORDS 8
+
+const char* p2b_last_error(void);
+int p2b_version(void);
+
+/* number of SMs / resident sweep warps on the current device (diagnostics for bench.py) */
+int p2b_device_sms(void);
+
+/* ---- ghost fill: ArrayIndexer.fill_ghost (pyro/mesh/array_indexer.py:150-274) applied to nvar
+ * planes, as CellCenterData2d.fill_BC_all does (pyro/mesh/patch.py:575-624).  bc = nvar x 4 codes
+ * (xlb, xrb, ylb, yrb per variable), host array.  x faces first, then y faces over the full x
+ * range, exactly as the reference orders them.  Bit-exact for float64 and int64. */
+int p2b_fill_ghost_f64(double* base, const p2b_grid* g, int nvar, const int* bc, void* stream);
+int p2b_fill_ghost_i64(int64_t* base, const p2b_grid* g, int nvar, const int* bc, void* stream);
+
+/* single plane with inhomogeneous Dirichlet / Neumann boundary values (array_indexer.py:166-183,
+ * used by the finest multigrid level, pyro/multigrid/MG.py:231-242).  xl/xr have qy entries,
+ * yl/yr have qx entries (device pointers) or NULL for homogeneous. */
+int p2b_fill_ghost_values_f64(double* plane, const p2b_grid* g, const int bc[4], const double* xl,
+                              const double* xr, const double* yl, const double* yr, void* stream);
+
+/* ---- CFL wave speeds: Simulation.method_compute_timestep (pyro/compressible/simulation.py:267-288)
+ * over the FULL array including ghosts.  Accumulates (atomic max) the bit patterns of
+ * max(|u|+cs), max(|v|+cs) into scratch[0], scratch[1]; the caller zeroes them first and forms
+ * dt = cfl * min(dx / a, dy / b), which is bit-identical to the reference's min over cells. */
+int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* scratch, void* stream);
+
+/* ---- the fused compressible sweep: Simulation.evolve (pyro/compressible/simulation.py:290-450)
+ * with interface_states / apply_transverse_flux / apply_artificial_viscosity
+ * (pyro/compressible/unsplit_fluxes.py:134-549), interface.states (interface.py:6-236),
+ * riemann_hllc (riemann.py:682-860) folded into one kernel.  Uin must have its ghost cells filled;
+ * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
+ * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
+ * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, grav = 0,
+ * Cartesian geometry, HLLC. */
+int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
+                           const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
+
+/* launch geometry chosen for the last sweep (bench diagnostics): tasks, resident warps, seglen */
+int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

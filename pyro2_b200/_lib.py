@@ -1,0 +1,129 @@
+"""Build + ctypes binding of libpyro2b200.so (the C ABI declared in include/pyro2b200.h).
+
+The library is built IN-TREE (pyro2_b200/csrc/libpyro2b200.so) with
+``nvcc -gencode arch=compute_100a,code=sm_100a`` -- sm_100a only, no fallbacks.  There is no CPU
+path: if the shared object is missing or CUDA is unavailable the product raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libpyro2b200.so")
+SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "../../include/pyro2b200.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--shared"]
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """compile every CUDA source for sm_100a into the in-tree shared object"""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+class Grid(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("ng", C.c_int), ("pitch", C.c_int),
+                ("plane_stride", C.c_longlong), ("dx", C.c_double), ("dy", C.c_double)]
+
+
+class CompParams(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double), ("delta", C.c_double),
+                ("cvisc", C.c_double), ("limiter", C.c_int), ("use_flattening", C.c_int),
+                ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int)]
+
+
+BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
+            "periodic": 3, None: 4, "none": 4}
+
+_lib = None
+
+# every symbol include/pyro2b200.h declares: (name, restype, argtypes)
+_vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+_PG = C.POINTER(Grid)
+SIGNATURES = {
+    "p2b_last_error": (C.c_char_p, []),
+    "p2b_version": (_i, []),
+    "p2b_device_sms": (_i, []),
+    "p2b_fill_ghost_f64": (_i, [_vp, _PG, _i, C.POINTER(_i), _vp]),
+    "p2b_fill_ghost_i64": (_i, [_vp, _PG, _i, C.POINTER(_i), _vp]),
+    "p2b_fill_ghost_values_f64": (_i, [_vp, _PG, C.POINTER(_i), _vp, _vp, _vp, _vp, _vp]),
+    "p2b_cfl_wavemax": (_i, [_vp, _PG, _d, _vp, _vp]),
+    "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
+    "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "p2b_mg_create": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i]),
+    "p2b_mg_destroy": (_i, [_vp]),
+    "p2b_mg_nlevels": (_i, [_vp]),
+    "p2b_mg_workspace_bytes": (_ll, [_vp]),
+    "p2b_mg_bind": (_i, [_vp, _vp, _ll]),
+    "p2b_mg_level_ptr": (_vp, [_vp, _i, _i]),
+    "p2b_mg_level_pitch": (_i, [_vp, _i]),
+    "p2b_mg_set_bc_values": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "p2b_mg_smooth": (_i, [_vp, _i, _i, _vp]),
+    "p2b_mg_residual": (_i, [_vp, _i, _vp]),
+    "p2b_mg_restrict": (_i, [_vp, _i, _vp]),
+    "p2b_mg_prolong_correct": (_i, [_vp, _i, _vp]),
+    "p2b_mg_fill_bc": (_i, [_vp, _i, _vp]),
+    "p2b_mg_zero_coarse": (_i, [_vp, _vp]),
+    "p2b_mg_vcycle": (_i, [_vp, _vp]),
+    "p2b_mg_norm2": (_i, [_vp, _i, _i, _vp, _vp]),
+    "p2b_mg_cycle_diagnostics": (_i, [_vp, _vp, _vp, _vp]),
+}
+
+
+def lib():
+    """the loaded C-ABI library; raises (never falls back) when it cannot be loaded"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "pyro2_b200 has no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)   # AttributeError here = header/library mismatch
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class P2BError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().p2b_last_error().decode()
+        if rc == -1:
+            raise ValueError(msg)
+        raise P2BError(f"libpyro2b200 error {rc}: {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def bc_array(rows):
+    """rows: iterable of 4-tuples of BC names -> flat ctypes int array"""
+    flat = [BC_CODES[b] for r in rows for b in r]
+    return (C.c_int * len(flat))(*flat)

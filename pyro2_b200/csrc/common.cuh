@@ -1,0 +1,46 @@
+// common.cuh -- error plumbing shared by the .cu translation units of libpyro2b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pyro2b200.h"
+
+namespace pyro {
+
+// thread-local last-error text (no global mutable state except this string)
+char* last_error_buf();
+void set_error(const char* fmt, ...);
+
+#define P2B_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            pyro::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,              \
+                            cudaGetErrorString(e__));                                         \
+            return P2B_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+#define P2B_REQUIRE(cond, msg)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            pyro::set_error("invalid argument: %s (%s:%d)", msg, __FILE__, __LINE__);         \
+            return P2B_EINVAL;                                                                \
+        }                                                                                     \
+    } while (0)
+
+inline int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace pyro

@@ -1,0 +1,522 @@
+// mg.cu -- cell-centred constant-coefficient multigrid V-cycle (HP-2) for (alpha - beta L) phi = f.
+//
+// Reference behaviour (pyro2, file:line):
+//   CellCenterMG2d.smooth            pyro/multigrid/MG.py:544-599   red-black Gauss-Seidel, ghost fill
+//                                                                   after each colour
+//   CellCenterMG2d._compute_residual pyro/multigrid/MG.py:529-542
+//   CellCenterData2d.restrict        pyro/mesh/patch.py:640-676     4-cell average
+//   CellCenterData2d.prolong         pyro/mesh/patch.py:678-736     centred (unlimited) slopes
+//   CellCenterMG2d.v_cycle / solve   pyro/multigrid/MG.py:699-778 / 623-697
+//   ArrayIndexer.norm                pyro/mesh/array_indexer.py:98-111
+//
+// All arithmetic here is written with explicitly rounded, unfused operations in the reference's
+// evaluation order: the path is HBM-bound, so the FP64 pipe has slack, and the payoff is that the
+// device solution is BIT-IDENTICAL to the reference's (red-black ordering makes every point update
+// independent of the traversal order).  Only the norms (a reduction) differ at the 1e-16 level.
+//
+// Ghost cells (ng = 1) are kept consistent by the thread that updates the interior source cell of
+// each ghost ("fused fill_BC"), so a half-sweep is one launch.
+#include "common.cuh"
+#include "hydro_core.cuh"
+
+namespace pyro {
+
+struct MgLevel {
+    int n, pitch;
+    double *v, *f, *r;
+    double dx, dy;
+};
+
+struct MgBC {
+    int xl, xr, yl, yr;                       // P2B_BC_* codes
+    const double *xlv, *xrv, *ylv, *yrv;      // inhomogeneous values (finest level) or NULL
+};
+
+constexpr int MG_MAX_LEVELS = 24;
+constexpr int MG_NPART = 1024;                // partial sums of the deterministic norm
+
+}  // namespace pyro
+
+struct p2b_mg {
+    int nlevels;
+    int bc[4];
+    double alpha, beta, xmin, xmax, ymin, ymax;
+    int nsmooth, nsmooth_bottom;
+    pyro::MgLevel lev[pyro::MG_MAX_LEVELS];
+    long long bytes, coarse_v_bytes;
+    double* base;
+    double* partials;                         // MG_NPART doubles x 2
+    const double *xlv, *xrv, *ylv, *yrv;
+};
+
+namespace pyro {
+
+// ---- ghost update fused into the writers --------------------------------------------------------
+// value of the ghost cell generated from interior source value `val` (array_indexer.py:164-274)
+__device__ __forceinline__ double ghost_lo(double val, int code, const double* vals, int idx, double h)
+{
+    if (vals) {
+        if (code == P2B_BC_OUTFLOW) return exact_sub(val, exact_mul(h, vals[idx]));
+        if (code == P2B_BC_REFLECT_ODD) return exact_sub(exact_mul(2.0, vals[idx]), val);
+    }
+    return code == P2B_BC_REFLECT_ODD ? -val : val;
+}
+
+__device__ __forceinline__ double ghost_hi(double val, int code, const double* vals, int idx, double h)
+{
+    if (vals) {
+        if (code == P2B_BC_OUTFLOW) return exact_add(val, exact_mul(h, vals[idx]));
+        if (code == P2B_BC_REFLECT_ODD) return exact_sub(exact_mul(2.0, vals[idx]), val);
+    }
+    return code == P2B_BC_REFLECT_ODD ? -val : val;
+}
+
+// store v(i,j) = val and every ghost cell whose source is (i,j).  x ghosts are functions of the
+// interior value; y ghosts (filled second in the reference, over the full x range) are functions of
+// the already x-filled column, which gives the corner values.
+__device__ __forceinline__ void store_with_ghosts(double* v, int n, int pitch, int i, int j, double val,
+                                                  const MgBC& b, double dx, double dy)
+{
+    v[(long long)i * pitch + j] = val;
+    if (b.xl == P2B_BC_NONE) return;   // (not used by the single-GPU path)
+    const int sxl = (b.xl == P2B_BC_PERIODIC) ? n : 1;    // source row of ghost row 0
+    const int sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : n;    // source row of ghost row n+1
+    const int syl = (b.yl == P2B_BC_PERIODIC) ? n : 1;
+    const int syh = (b.yr == P2B_BC_PERIODIC) ? 1 : n;
+    // the up-to-three rows this value lives in after the x fill: (row index, value)
+    int rows[3]; double rv[3]; int nr = 0;
+    rows[nr] = i; rv[nr] = val; ++nr;
+    if (i == sxl) { rows[nr] = 0; rv[nr] = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = rv[nr]; ++nr; }
+    if (i == sxh) { rows[nr] = n + 1; rv[nr] = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(n + 1) * pitch + j] = rv[nr]; ++nr; }
+    if (j == syl)
+        for (int k = 0; k < nr; ++k)
+            v[(long long)rows[k] * pitch] = ghost_lo(rv[k], b.yl, b.ylv, rows[k], dy);
+    if (j == syh)
+        for (int k = 0; k < nr; ++k)
+            v[(long long)rows[k] * pitch + n + 1] = ghost_hi(rv[k], b.yr, b.yrv, rows[k], dy);
+}
+
+struct SmoothCoef { double alpha, xc, yc, denom; };
+
+__device__ __forceinline__ double gs_update(const double* v, const double* f, int pitch, int i, int j,
+                                            const SmoothCoef& c)
+{
+    // MG.py:593-596:  (f + xcoeff*(v[i+1]+v[i-1]) + ycoeff*(v[j+1]+v[j-1])) / (alpha + 2xc + 2yc)
+    const long long k = (long long)i * pitch + j;
+    double sx = exact_add(v[k + pitch], v[k - pitch]);
+    double sy = exact_add(v[k + 1], v[k - 1]);
+    double num = exact_add(exact_add(f[k], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+    return exact_div(num, c.denom);
+}
+
+// one colour of one red-black iteration; colour 0 = (i+j) even = the reference's groups (0,0),(1,1)
+__global__ void mg_halfsweep_kernel(MgLevel L, MgBC b, SmoothCoef c, int colour)
+{
+    const int half = L.n >> 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (k >= half || i > L.n) return;
+    const int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+    double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+    store_with_ghosts(L.v, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+}
+
+// whole smooth() for a small level in one CTA (global memory, __syncthreads between colours)
+__global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmooth)
+{
+    const int half = L.n >> 1;
+    const int npts = L.n * half;
+    for (int it = 0; it < 2 * nsmooth; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int i = t / half + 1, k = t % half;
+            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+            double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            store_with_ghosts(L.v, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+        }
+        __syncthreads();
+    }
+}
+
+// full ghost fill of v from the interior (used once per smooth() like MG.py:565)
+__global__ void mg_fill_kernel(MgLevel L, MgBC b)
+{
+    // every interior edge cell re-stores itself with its ghosts
+    const int n = L.n;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 4 * n; t += gridDim.x * blockDim.x) {
+        int side = t / n, s = t % n + 1;
+        int i, j;
+        if (side == 0) { i = 1; j = s; } else if (side == 1) { i = n; j = s; }
+        else if (side == 2) { i = s; j = 1; } else { i = s; j = n; }
+        // corners are visited twice with identical results
+        store_with_ghosts(L.v, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+    }
+}
+
+__global__ void mg_residual_kernel(MgLevel L, double alpha, double beta)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > L.n || j > L.n) return;
+    const long long k = (long long)i * L.pitch + j;
+    const double* v = L.v;
+    // MG.py:540-542
+    double v2 = exact_mul(2.0, v[k]);
+    double lx = exact_div(exact_sub(exact_add(v[k - L.pitch], v[k + L.pitch]), v2), exact_mul(L.dx, L.dx));
+    double ly = exact_div(exact_sub(exact_add(v[k - 1], v[k + 1]), v2), exact_mul(L.dy, L.dy));
+    L.r[k] = exact_add(exact_sub(L.f[k], exact_mul(alpha, v[k])), exact_mul(beta, exact_add(lx, ly)));
+}
+
+// fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732)
+__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs)
+{
+    const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (ic > Cs.n || jc > Cs.n) return;
+    const long long k = (long long)(2 * ic - 1) * F.pitch + (2 * jc - 1);
+    const double* r = F.r;
+    double s = exact_add(exact_add(exact_add(r[k], r[k + F.pitch]), r[k + 1]), r[k + F.pitch + 1]);
+    Cs.f[(long long)ic * Cs.pitch + jc] = exact_mul(0.25, s);
+}
+
+// v_fine += prolong(v_coarse), ghosts refreshed (patch.py:716-734, MG.py:745-751)
+__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b)
+{
+    const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (ic > Cs.n || jc > Cs.n) return;
+    const double* c = Cs.v;
+    const long long kc = (long long)ic * Cs.pitch + jc;
+    double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
+    double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+    double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my);
+    double c0 = c[kc];
+    const int i = 2 * ic - 1, j = 2 * jc - 1;
+    double e00 = exact_sub(exact_sub(c0, qx), qy);
+    double e10 = exact_sub(exact_add(c0, qx), qy);
+    double e01 = exact_add(exact_sub(c0, qx), qy);
+    double e11 = exact_add(exact_add(c0, qx), qy);
+    double* v = F.v;
+    const int P = F.pitch;
+    store_with_ghosts(v, F.n, P, i, j, exact_add(v[(long long)i * P + j], e00), b, F.dx, F.dy);
+    store_with_ghosts(v, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], e10), b, F.dx, F.dy);
+    store_with_ghosts(v, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], e01), b, F.dx, F.dy);
+    store_with_ghosts(v, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], e11), b, F.dx, F.dy);
+}
+
+// deterministic sum of squares over the valid region: fixed partition into MG_NPART partials,
+// then one block sums the partials in a fixed order.  mode 0: a^2;  mode 1: ((a-b)/(a+small))^2 and
+// b <- a (the relative-change diagnostic of MG.py:673-676)
+__global__ void mg_sumsq_partial_kernel(const double* a, double* bprev, int n, int pitch, int mode, double* part)
+{
+    double s = 0.0;
+    const long long total = (long long)n * n;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / n) + 1, j = (int)(t % n) + 1;
+        long long k = (long long)i * pitch + j;
+        double x = a[k];
+        if (mode == 1) {
+            double o = bprev[k];
+            bprev[k] = x;
+            x = (x - o) / (x + 1.e-16);
+        }
+        s += x * x;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
+__global__ void mg_sumsq_final_kernel(const double* part, int npart, double* out)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int t = threadIdx.x; t < npart; t += 256) s += part[t];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+static MgBC level_bc(const p2b_mg* m, int level)
+{
+    MgBC b;
+    b.xl = m->bc[0]; b.xr = m->bc[1]; b.yl = m->bc[2]; b.yr = m->bc[3];
+    const bool fin = (level == m->nlevels - 1);
+    // inhomogeneous values apply on the finest level only (MG.py:231-242) and only to
+    // Dirichlet / Neumann sides (array_indexer.py:165-183)
+    auto ok = [](int code) { return code == P2B_BC_OUTFLOW || code == P2B_BC_REFLECT_ODD; };
+    b.xlv = (fin && ok(b.xl)) ? m->xlv : nullptr;
+    b.xrv = (fin && ok(b.xr)) ? m->xrv : nullptr;
+    b.ylv = (fin && ok(b.yl)) ? m->ylv : nullptr;
+    b.yrv = (fin && ok(b.yr)) ? m->yrv : nullptr;
+    return b;
+}
+
+static SmoothCoef level_coef(const p2b_mg* m, const MgLevel& L)
+{
+    SmoothCoef c;
+    c.alpha = m->alpha;
+    c.xc = m->beta / (L.dx * L.dx);
+    c.yc = m->beta / (L.dy * L.dy);
+    c.denom = m->alpha + 2.0 * c.xc + 2.0 * c.yc;
+    return c;
+}
+
+constexpr int MG_SMALL_N = 32;   // levels up to 32^2 are smoothed by one CTA in one launch
+
+static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaStream_t st)
+{
+    const MgLevel& L = m->lev[level];
+    MgBC b = level_bc(m, level);
+    SmoothCoef c = level_coef(m, L);
+    if (fill_first) mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, st>>>(L, b);
+    if (L.n <= MG_SMALL_N) {
+        int threads = L.n * (L.n / 2);
+        threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
+        mg_smooth_small_kernel<<<1, threads, 0, st>>>(L, b, c, nsmooth);
+    } else {
+        dim3 blk(64, 4);
+        dim3 grd((L.n / 2 + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
+        for (int it = 0; it < nsmooth; ++it) {
+            mg_halfsweep_kernel<<<grd, blk, 0, st>>>(L, b, c, 0);
+            mg_halfsweep_kernel<<<grd, blk, 0, st>>>(L, b, c, 1);
+        }
+    }
+    return P2B_OK;
+}
+
+static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
+{
+    const MgLevel& L = m->lev[level];
+    dim3 blk(64, 4);
+    dim3 grd((L.n + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
+    mg_residual_kernel<<<grd, blk, 0, st>>>(L, m->alpha, m->beta);
+}
+
+static void restrict_impl(p2b_mg* m, int level, cudaStream_t st)
+{
+    const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
+    dim3 blk(64, 4);
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (Cs.n + blk.y - 1) / blk.y);
+    mg_restrict_kernel<<<grd, blk, 0, st>>>(F, Cs);
+}
+
+static void prolong_impl(p2b_mg* m, int level, cudaStream_t st)
+{
+    const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
+    dim3 blk(64, 4);
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (Cs.n + blk.y - 1) / blk.y);
+    mg_prolong_kernel<<<grd, blk, 0, st>>>(F, Cs, level_bc(m, level));
+}
+
+static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
+{
+    // MG.py:699-778
+    if (level > 0) {
+        smooth_impl(m, level, m->nsmooth, true, st);
+        residual_impl(m, level, st);
+        restrict_impl(m, level, st);
+        vcycle_impl(m, level - 1, st);
+        prolong_impl(m, level, st);
+        smooth_impl(m, level, m->nsmooth, true, st);
+    } else {
+        smooth_impl(m, 0, m->nsmooth_bottom, true, st);
+    }
+}
+
+static int sumsq_impl(p2b_mg* m, const double* a, double* prev, int level, int mode, double* out, cudaStream_t st)
+{
+    const MgLevel& L = m->lev[level];
+    long long total = (long long)L.n * L.n;
+    int blocks = (int)((total + 255) / 256 < MG_NPART ? (total + 255) / 256 : MG_NPART);
+    mg_sumsq_partial_kernel<<<blocks, 256, 0, st>>>(a, prev, L.n, L.pitch, mode, m->partials);
+    mg_sumsq_final_kernel<<<1, 256, 0, st>>>(m->partials, blocks, out);
+    return P2B_OK;
+}
+
+}  // namespace pyro
+
+using namespace pyro;
+
+extern "C" {
+
+// CellCenterMG2d.__init__ (MG.py:85-295): level l has 2^(l+1) cells per side, ng = 1, vars v, f, r
+p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                      double ymin, double ymax, int nsmooth, int nsmooth_bottom)
+{
+    if (nx < 2 || (nx & (nx - 1)) != 0) { set_error("multigrid requires nx = ny = power of two (got %d)", nx); return nullptr; }
+    if (!bc) { set_error("null bc"); return nullptr; }
+    p2b_mg* m = new p2b_mg();
+    memset(m, 0, sizeof *m);
+    int nl = 0;
+    while ((2 << nl) < nx) ++nl;
+    m->nlevels = nl + 1;
+    for (int s = 0; s < 4; ++s) m->bc[s] = bc[s];
+    m->alpha = alpha; m->beta = beta;
+    m->xmin = xmin; m->xmax = xmax; m->ymin = ymin; m->ymax = ymax;
+    m->nsmooth = nsmooth; m->nsmooth_bottom = nsmooth_bottom;
+    // layout: [v of levels 0..L-2] [f, r of levels 0..L-2] [v, f, r of the finest] [partials]
+    long long off = 0;
+    for (int l = 0; l < m->nlevels; ++l) {
+        MgLevel& L = m->lev[l];
+        L.n = 2 << l;
+        int q = L.n + 2;
+        L.pitch = (q >= 16) ? (q + 15) / 16 * 16 : (q + 1) / 2 * 2;
+        L.dx = (xmax - xmin) / L.n;
+        L.dy = (ymax - ymin) / L.n;
+    }
+    auto plane = [](const MgLevel& L) { return (long long)(L.n + 2) * L.pitch; };
+    // offsets are stored as fake pointers (element counts) until p2b_mg_bind
+    for (int l = 0; l < m->nlevels - 1; ++l) { m->lev[l].v = (double*)off; off += plane(m->lev[l]); }
+    m->coarse_v_bytes = off * 8;
+    for (int l = 0; l < m->nlevels - 1; ++l) {
+        m->lev[l].f = (double*)off; off += plane(m->lev[l]);
+        m->lev[l].r = (double*)off; off += plane(m->lev[l]);
+    }
+    MgLevel& Lf = m->lev[m->nlevels - 1];
+    Lf.v = (double*)off; off += plane(Lf);
+    Lf.f = (double*)off; off += plane(Lf);
+    Lf.r = (double*)off; off += plane(Lf);
+    m->partials = (double*)off; off += 2 * MG_NPART;
+    m->bytes = off * 8;
+    return m;
+}
+
+int p2b_mg_destroy(p2b_mg* m) { delete m; return P2B_OK; }
+int p2b_mg_nlevels(p2b_mg* m) { return m ? m->nlevels : 0; }
+long long p2b_mg_workspace_bytes(p2b_mg* m) { return m ? m->bytes : 0; }
+
+// hand the hierarchy its (caller-owned, zero-initialised) device memory
+int p2b_mg_bind(p2b_mg* m, void* mem, long long bytes)
+{
+    P2B_REQUIRE(m && mem, "null pointer");
+    P2B_REQUIRE(bytes >= m->bytes, "workspace too small");
+    P2B_REQUIRE(m->base == nullptr, "already bound");
+    P2B_REQUIRE(((uintptr_t)mem % 16) == 0, "workspace must be 16-byte aligned");
+    m->base = (double*)mem;
+    for (int l = 0; l < m->nlevels; ++l) {
+        m->lev[l].v = m->base + (long long)m->lev[l].v;
+        m->lev[l].f = m->base + (long long)m->lev[l].f;
+        m->lev[l].r = m->base + (long long)m->lev[l].r;
+    }
+    m->partials = m->base + (long long)m->partials;
+    return P2B_OK;
+}
+
+void* p2b_mg_level_ptr(p2b_mg* m, int level, int which)
+{
+    if (!m || level < 0 || level >= m->nlevels) return nullptr;
+    return which == 0 ? m->lev[level].v : which == 1 ? m->lev[level].f : m->lev[level].r;
+}
+
+int p2b_mg_level_pitch(p2b_mg* m, int level) { return (m && level >= 0 && level < m->nlevels) ? m->lev[level].pitch : 0; }
+
+// inhomogeneous boundary values for the finest level: device arrays of n+2 doubles or NULL
+int p2b_mg_set_bc_values(p2b_mg* m, const double* xl, const double* xr, const double* yl, const double* yr)
+{
+    P2B_REQUIRE(m, "null handle");
+    m->xlv = xl; m->xrv = xr; m->ylv = yl; m->yrv = yr;
+    return P2B_OK;
+}
+
+#define MG_CHECK_LEVEL(m, level) \
+    P2B_REQUIRE((m) && (m)->base, "hierarchy not bound"); \
+    P2B_REQUIRE((level) >= 0 && (level) < (m)->nlevels, "bad level")
+
+int p2b_mg_smooth(p2b_mg* m, int level, int nsmooth, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    smooth_impl(m, level, nsmooth, true, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_mg_residual(p2b_mg* m, int level, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    residual_impl(m, level, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_mg_restrict(p2b_mg* m, int level, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(level >= 1, "no coarser level");
+    restrict_impl(m, level, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(level >= 1, "no coarser level");
+    prolong_impl(m, level, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    const MgLevel& L = m->lev[level];
+    mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(L, level_bc(m, level));
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+// zero v on every level but the finest (MG.py:658-659); the coarse v planes are contiguous
+int p2b_mg_zero_coarse(p2b_mg* m, void* stream)
+{
+    P2B_REQUIRE(m && m->base, "hierarchy not bound");
+    if (m->coarse_v_bytes) P2B_CUDA_CHECK(cudaMemsetAsync(m->base, 0, m->coarse_v_bytes, (cudaStream_t)stream));
+    return P2B_OK;
+}
+
+int p2b_mg_vcycle(p2b_mg* m, void* stream)
+{
+    P2B_REQUIRE(m && m->base, "hierarchy not bound");
+    vcycle_impl(m, m->nlevels - 1, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+// sum of squares of plane `which` (0 v, 1 f, 2 r) over the valid region -> *out (device double);
+// ArrayIndexer.norm = sqrt(dx*dy*sum) (array_indexer.py:98-111)
+int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(out, "null out");
+    const MgLevel& L = m->lev[level];
+    const double* a = which == 0 ? L.v : which == 1 ? L.f : L.r;
+    sumsq_impl(m, a, nullptr, level, 0, out, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+// per-cycle bookkeeping of solve() (MG.py:668-686) on the finest level:
+//   out[0] = sum(((v - old_phi)/(v + 1e-16))^2), old_phi <- v, r <- residual, out[1] = sum(r^2)
+int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stream)
+{
+    P2B_REQUIRE(m && m->base && old_phi && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lf = m->nlevels - 1;
+    sumsq_impl(m, m->lev[lf].v, old_phi, lf, 1, out, st);
+    residual_impl(m, lf, st);
+    sumsq_impl(m, m->lev[lf].r, nullptr, lf, 0, out + 1, st);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+}  // extern "C"

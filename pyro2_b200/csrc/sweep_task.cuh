@@ -1,0 +1,353 @@
+// sweep_task.cuh -- one warp's share of the fused compressible CTU sweep (HP-1).
+//
+// Replaces, in a single pass over the state, everything the reference does in
+// pyro/compressible/simulation.py:290-450 (evolve) for Cartesian/HLLC/grav=0:
+//   cons_to_prim -> flatten/flatten_multid -> limit -> interface.states (x, y) -> prim_to_cons ->
+//   transverse riemann_hllc (x, y) -> transverse correction -> final riemann_hllc (x, y) ->
+//   artificial viscosity -> conservative update, plus the wave-speed maxima the next
+//   method_compute_timestep() needs (simulation.py:267-288).
+//
+// Decomposition ("marching strips"): a warp owns a strip of 30 output columns (y, the contiguous
+// axis; lanes 0 and 31 are the +-1 halo columns whose interface states the neighbours need) and
+// marches along x over a segment of rows.  Everything that couples rows (x-direction stencils,
+// the x Riemann problems, the row-lagged update) lives in the lane's own registers, carried from
+// one iteration to the next; everything that couples columns goes through warp shuffles or the
+// warp's shared-memory row ring.  No block-level barrier exists anywhere: warps are independent.
+//
+//   iteration i (i0-1 <= i <= i1) does
+//     ready row i+3 (TMA bulk copy landed -> convert cons->prim in place in the ring)
+//     xi(i), limited slopes(i), traced states of row i                     [hat states]
+//     transverse F_x at face i-1/2 (needs row i-1 from regs)  -> dF_x of row i-1
+//     corrected y-states of row i-1 -> final F_y of row i-1 (+ viscosity)
+//     transverse F_y of row i (lane shuffles) -> dF_y of row i -> corrected x-states of row i
+//     final F_x at face i-1/2 (+ viscosity)
+//     conservative update of row i-1, store, wave-speed maxima
+//
+// HBM traffic per updated cell: one read of U (the 38/30 column overlap and the 8-row segment
+// overlap are absorbed by L2) and one write: 64 B.  Dependency radius is exactly ng = 4
+// (SURVEY.md 9.3), which is why rows i0-4 .. i1+3 and columns j0-4 .. j0+33 are staged.
+//
+// The code is written against a small "warp services" policy W so the identical source can be
+// compiled for a host-side lane-per-thread emulator (tests/emu) -- test infrastructure only.
+#pragma once
+#include "hydro_core.cuh"
+
+namespace pyro {
+
+constexpr int SW_OUT = 30;     // output columns per warp
+constexpr int SW_QW = 38;      // staged columns: 32 lanes + 3 each side
+constexpr int SW_RING = 8;     // row ring depth (rows i-2 .. i+5)
+constexpr int SW_XW = 34;      // exchange width: 32 lanes + 1 each side
+
+struct SweepArgs {
+    const double* Uin;         // 4 planes [n][i][j], ghosts filled
+    double* Uout;              // 4 planes, valid region written
+    long long plane_stride;    // elements between planes
+    int pitch;                 // elements between rows (>= qy, even)
+    int nx, ny, ng;            // ng >= 4
+    double dx, dy, dt, gamma;
+    double z0, z1, delta, cvisc;
+    int limiter, use_flattening;
+    int no_avisc_xhi, no_avisc_yhi;   // reference quirk 9.2-13 on the global +x / +y faces
+    int nstrips, nsegs, seglen;
+    unsigned long long* wavemax;      // [0] = bits of max(|u|+cs), [1] = bits of max(|v|+cs)
+    int* status;                      // set to 1 when a valid cell has rho <= 0 or e <= 0
+#ifdef SWEEP_DEBUG
+    double* dbg;                      // host emulator only: [k][i][j] planes of intermediates
+#endif
+};
+
+struct alignas(16) SweepSmem {
+    double q[4][SW_RING][SW_QW];      // raw U on arrival, primitives after ready()
+    double xch[5][SW_XW];             // [0] xi_y, [1..4] limit2_y of the 4 primitives
+    unsigned long long mbar[SW_RING];
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class W>
+struct SweepTask {
+    W& w;
+    const SweepArgs& A;
+    SweepSmem& S;
+    unsigned phase_bits;       // one mbarrier parity bit per ring slot (warp-uniform)
+
+    HD SweepTask(W& w_, const SweepArgs& a, SweepSmem& s, unsigned ph) : w(w_), A(a), S(s), phase_bits(ph) {}
+
+    HD double& Q(int n, int r, int c) { return S.q[n][r & (SW_RING - 1)][c]; }
+
+    // wait for the bulk copy of row r, convert cons -> prim in place, publish to the warp
+    HD void ready(int r, int col0, int jvalid_lo, int jvalid_hi, bool row_valid)
+    {
+        const int slot = r & (SW_RING - 1);
+        w.load_wait(S.mbar[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= (1u << slot);
+        bool anybad = false;
+        for (int c = w.lane(); c < SW_QW; c += 32) {
+            Cons U;
+            U.dens = S.q[IDENS][slot][c]; U.ener = S.q[IENER][slot][c];
+            U.xmom = S.q[IXMOM][slot][c]; U.ymom = S.q[IYMOM][slot][c];
+            bool bad;
+            Prim p = cons_to_prim(U, A.gamma, &bad);
+            S.q[IRHO][slot][c] = p.rho; S.q[IU][slot][c] = p.u;
+            S.q[IV][slot][c] = p.v;     S.q[IP][slot][c] = p.p;
+            int j = col0 + c;
+            if (bad && row_valid && j >= jvalid_lo && j < jvalid_hi) anybad = true;
+        }
+        if (anybad) *A.status = 1;
+        w.sync();
+    }
+
+    HD void issue(int r, int col0, int ncols)
+    {
+        const int slot = r & (SW_RING - 1);
+        const double* src = A.Uin + (long long)r * A.pitch + col0;
+        w.load_issue(S.mbar[slot], &S.q[0][slot][0], &S.q[1][slot][0], &S.q[2][slot][0],
+                     &S.q[3][slot][0], src, A.plane_stride, ncols);
+    }
+
+    HD double flat_x(int r, int c, const FlatPar& fp)
+    {
+        return flatten_1d(Q(IP, r - 2, c), Q(IP, r - 1, c), Q(IP, r + 1, c), Q(IP, r + 2, c),
+                          Q(IU, r - 1, c), Q(IU, r + 1, c), fp);
+    }
+
+    HD void run(int strip, int seg)
+    {
+        const int lane = w.lane();
+        const int ng = A.ng;
+        const int i0 = ng + seg * A.seglen;
+        const int i1 = (i0 + A.seglen < ng + A.nx) ? i0 + A.seglen : ng + A.nx;   // exclusive
+        const int jout0 = ng + SW_OUT * strip;          // first output column
+        const int col0 = jout0 - 4;                     // global column of ring column 0
+        const int ncols = (A.pitch - col0 < SW_QW) ? A.pitch - col0 : SW_QW;
+        const int j = jout0 - 1 + lane;                 // this lane's global column
+        const int cc = lane + 3;                        // ... and its ring column
+        const int jhi = ng + A.ny;                      // one past the last valid column
+        const int ihi = ng + A.nx;
+        const int rlast = i1 + 3;
+        const bool out_lane = (lane >= 1 && lane <= SW_OUT && j < jhi);
+
+        const double gamma = A.gamma;
+        const double ginv1 = 1.0 / (gamma - 1.0);
+        const HllcPar hp = hllc_par(gamma);
+        FlatPar fp; fp.z0 = A.z0; fp.inv_dz = 1.0 / (A.z1 - A.z0); fp.delta = A.delta;
+        const double dtdx = A.dt / A.dx, dtdy = A.dt / A.dy;
+        const double hdtdx = 0.5 * dtdx, hdtdy = 0.5 * dtdy;
+        const double dxinv = 1.0 / A.dx, dyinv = 1.0 / A.dy;
+        const int lim = A.limiter;
+        const bool flat = A.use_flattening != 0;
+
+        // raw U of the lane's own column is re-read from global (L2 hit: the bulk copy just
+        // streamed it) so that the update adds the flux divergence to the unmodified state
+        const long long jj = (j < A.pitch) ? j : A.pitch - 1;
+        const double* Ucol = A.Uin + jj;
+        double* Ocol = A.Uout + jj;
+
+        // ---- prologue: rows i0-4 .. i0+3 in flight, i0-4 .. i0+1 ready ---------------------
+        for (int r = i0 - 4; r <= i0 + 3 && r <= rlast; ++r) issue(r, col0, ncols);
+        for (int r = i0 - 4; r <= i0 + 1; ++r) ready(r, col0, ng, jhi, r >= ng && r < ihi);
+
+        double xix_m1 = 1.0, xix_0 = 1.0;               // xi_x of rows i-1, i
+        if (flat) { xix_m1 = flat_x(i0 - 2, cc, fp); xix_0 = flat_x(i0 - 1, cc, fp); }
+        double l2x_m1[4], l2x_0[4];                     // limit2_x of rows i-1, i
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            l2x_m1[n] = slope2(Q(n, i0 - 3, cc), Q(n, i0 - 2, cc), Q(n, i0 - 1, cc), lim);
+            l2x_0[n] = slope2(Q(n, i0 - 2, cc), Q(n, i0 - 1, cc), Q(n, i0, cc), lim);
+        }
+        w.sync();
+        if (i0 + 4 <= rlast) issue(i0 + 4, col0, ncols);
+
+        // ---- state carried from row i-1 to row i (all column-local) -------------------------
+        Cons XPc = {0, 0, 0, 0};      // traced state on the +x face of cell (i-1)   [ref: U_xl[i]]
+        Cons XPpc = {0, 0, 0, 0};     // ... after the transverse correction
+        Cons YMc = {0, 0, 0, 0}, YPc = {0, 0, 0, 0};    // traced y-face states of cell (i-1)
+        Cons FxT_prev = {0, 0, 0, 0};                   // transverse x-flux at face (i-1)-1/2
+        Cons Fx_prev = {0, 0, 0, 0};                    // final x-flux at face (i-1)-1/2
+        Cons U_prev = {0, 0, 0, 0};                     // raw U(i-1, j)
+        double divU_prev = 0.0;                         // vertex divergence at (i-1 -1/2, j-1/2)
+        double wmax_x = 0.0, wmax_y = 0.0;
+
+        for (int i = i0 - 1; i <= i1; ++i) {
+            ready(i + 3, col0, ng, jhi, (i + 3) >= ng && (i + 3) < ihi);
+
+            // raw state of this row (latency hidden behind the hat-state arithmetic)
+            Cons Uc;
+            {
+                const double* p = Ucol + (long long)i * A.pitch;
+                Uc.dens = p[0]; Uc.ener = p[A.plane_stride];
+                Uc.xmom = p[2 * A.plane_stride]; Uc.ymom = p[3 * A.plane_stride];
+            }
+
+            // ---- B. y-direction helpers on the 34-column exchange row ------------------------
+            // exchange column ee <-> global column jout0-2+ee <-> ring column ee+2; a lane's own
+            // column is ee = lane+1.  Second trip: lanes 0 and 1 do the two outer columns 0 and 33.
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1 && lane >= 2) break;
+                const int ee = (pass == 0) ? lane + 1 : (lane == 0 ? 0 : SW_XW - 1);
+                const int c = ee + 2;
+                double xiy = 1.0;
+                if (flat)
+                    xiy = flatten_1d(Q(IP, i, c - 2), Q(IP, i, c - 1), Q(IP, i, c + 1), Q(IP, i, c + 2),
+                                     Q(IV, i, c - 1), Q(IV, i, c + 1), fp);
+                S.xch[0][ee] = xiy;
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+                    S.xch[1 + n][ee] = slope2(Q(n, i, c - 1), Q(n, i, c), Q(n, i, c + 1), lim);
+            }
+            w.sync();
+
+            // ---- C. xi(i, j) (flatten_multid, reconstruction.py:167-183) ----------------------
+            double xix_p1 = flat ? flat_x(i + 1, cc, fp) : 1.0;
+            double xi = 1.0;
+            if (flat) {
+                double px = (Q(IP, i + 1, cc) - Q(IP, i - 1, cc) > 0.0) ? xix_m1 : xix_p1;
+                double py = (Q(IP, i, cc + 1) - Q(IP, i, cc - 1) > 0.0) ? S.xch[0][lane] : S.xch[0][lane + 2];
+                xi = dmin(dmin(xix_0, px), dmin(S.xch[0][lane + 1], py));
+            }
+
+#ifdef SWEEP_DEBUG
+            if (A.dbg && j < A.pitch) {
+                long long np_ = (long long)(A.nx + 2 * A.ng) * A.pitch;
+                A.dbg[0 * np_ + (long long)i * A.pitch + j] = xi;
+                A.dbg[1 * np_ + (long long)i * A.pitch + j] = xix_0;
+                A.dbg[2 * np_ + (long long)i * A.pitch + j] = S.xch[0][lane + 1];
+            }
+#endif
+            // ---- D. limited slopes (unsplit_fluxes.py:192-197) -------------------------------
+            Prim q0;
+            q0.rho = Q(IRHO, i, cc); q0.u = Q(IU, i, cc); q0.v = Q(IV, i, cc); q0.p = Q(IP, i, cc);
+            double ldx[4], ldy[4], l2x_p1[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                double am = Q(n, i - 1, cc), a0 = Q(n, i, cc), ap = Q(n, i + 1, cc);
+                l2x_p1[n] = slope2(a0, ap, Q(n, i + 2, cc), lim);
+                double sx = (lim == 2) ? slope4(am, a0, ap, l2x_m1[n], l2x_p1[n]) : l2x_0[n];
+                ldx[n] = xi * sx;
+                double bm = Q(n, i, cc - 1), bp = Q(n, i, cc + 1);
+                double sy = (lim == 2) ? slope4(bm, a0, bp, S.xch[1 + n][lane], S.xch[1 + n][lane + 2])
+                                       : S.xch[1 + n][lane + 1];
+                ldy[n] = xi * sy;
+            }
+
+            // ---- E. characteristic tracing, both directions -> conserved face states ---------
+            Cons XM, XP, YM, YP;
+            {
+                TraceGeom g = trace_geom(q0, gamma);
+                Prim m, p;
+                trace_1d(q0.rho, q0.u, q0.v, q0.p, ldx[IRHO], ldx[IU], ldx[IV], ldx[IP], g, dtdx,
+                         m.rho, m.u, m.v, m.p, p.rho, p.u, p.v, p.p);
+                XM = prim_to_cons(m, ginv1); XP = prim_to_cons(p, ginv1);
+                trace_1d(q0.rho, q0.v, q0.u, q0.p, ldy[IRHO], ldy[IV], ldy[IU], ldy[IP], g, dtdy,
+                         m.rho, m.v, m.u, m.p, p.rho, p.v, p.u, p.p);
+                YM = prim_to_cons(m, ginv1); YP = prim_to_cons(p, ginv1);
+            }
+
+            // ---- H. vertex divergence for the artificial viscosity ---------------------------
+            double divU = vertex_divU(Q(IU, i, cc), Q(IU, i, cc - 1), Q(IU, i - 1, cc), Q(IU, i - 1, cc - 1),
+                                      Q(IV, i, cc), Q(IV, i, cc - 1), Q(IV, i - 1, cc), Q(IV, i - 1, cc - 1),
+                                      dxinv, dyinv);
+            double divU_jp1 = w.down(divU);
+
+            Cons Fy = {0, 0, 0, 0};
+            if (i >= i0) {
+                // ---- F. transverse x-flux at face i-1/2; dF_x of cell (i-1) -------------------
+                Flux f = hllc(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp);
+                Cons FxT = {f.dens, f.ener, f.mn, f.mt};
+                // ---- G. transverse correction of the y-face states of cell (i-1)
+                //         (unsplit_fluxes.py:463-471: U_yl[i,j+1], U_yr[i,j] -= dt/2dx * dF_x)
+                Cons YMp, YPp;
+                YMp.dens = YMc.dens - hdtdx * (FxT.dens - FxT_prev.dens);
+                YMp.ener = YMc.ener - hdtdx * (FxT.ener - FxT_prev.ener);
+                YMp.xmom = YMc.xmom - hdtdx * (FxT.xmom - FxT_prev.xmom);
+                YMp.ymom = YMc.ymom - hdtdx * (FxT.ymom - FxT_prev.ymom);
+                YPp.dens = YPc.dens - hdtdx * (FxT.dens - FxT_prev.dens);
+                YPp.ener = YPc.ener - hdtdx * (FxT.ener - FxT_prev.ener);
+                YPp.xmom = YPc.xmom - hdtdx * (FxT.xmom - FxT_prev.xmom);
+                YPp.ymom = YPc.ymom - hdtdx * (FxT.ymom - FxT_prev.ymom);
+                FxT_prev = FxT;
+
+                if (i > i0) {
+                    // ---- I. final y-flux of row i-1 at face j-1/2 (left state from lane-1) ----
+                    double ld = w.up(YPp.dens), le = w.up(YPp.ener), lx = w.up(YPp.xmom), ly = w.up(YPp.ymom);
+                    Flux g = hllc(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp);
+                    Fy.dens = g.dens; Fy.ener = g.ener; Fy.ymom = g.mn; Fy.xmom = g.mt;
+                    // viscosity (unsplit_fluxes.py:545-547); zero on the global +y face
+                    double avy = avisc_coeff(divU_prev, divU, A.dy, A.cvisc);
+                    if (A.no_avisc_yhi && j == jhi) avy = 0.0;
+                    double bd = w.up(U_prev.dens), be = w.up(U_prev.ener), bx = w.up(U_prev.xmom), by = w.up(U_prev.ymom);
+                    Fy.dens += avy * (bd - U_prev.dens);
+                    Fy.ener += avy * (be - U_prev.ener);
+                    Fy.xmom += avy * (bx - U_prev.xmom);
+                    Fy.ymom += avy * (by - U_prev.ymom);
+                }
+            }
+
+            // ---- J. transverse y-flux of row i at face j-1/2; dF_y of cell (i, j) -------------
+            Cons XMp, XPp;
+            {
+                double ld = w.up(YP.dens), le = w.up(YP.ener), lx = w.up(YP.xmom), ly = w.up(YP.ymom);
+                Flux g = hllc(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp);
+                // g.mn is the y-momentum flux, g.mt the x-momentum flux
+                double dd = w.down(g.dens) - g.dens, de = w.down(g.ener) - g.ener;
+                double dmy = w.down(g.mn) - g.mn, dmx = w.down(g.mt) - g.mt;
+                // ---- K. (unsplit_fluxes.py:453-461: U_xl[i+1,j], U_xr[i,j] -= dt/2dy * dF_y)
+                XMp.dens = XM.dens - hdtdy * dd; XMp.ener = XM.ener - hdtdy * de;
+                XMp.xmom = XM.xmom - hdtdy * dmx; XMp.ymom = XM.ymom - hdtdy * dmy;
+                XPp.dens = XP.dens - hdtdy * dd; XPp.ener = XP.ener - hdtdy * de;
+                XPp.xmom = XP.xmom - hdtdy * dmx; XPp.ymom = XP.ymom - hdtdy * dmy;
+            }
+
+            if (i >= i0) {
+                // ---- L. final x-flux at face i-1/2 ------------------------------------------
+                Flux f = hllc(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
+                              XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp);
+                Cons Fx = {f.dens, f.ener, f.mn, f.mt};
+                double avx = avisc_coeff(divU, divU_jp1, A.dx, A.cvisc);
+                if (A.no_avisc_xhi && i == ihi) avx = 0.0;
+                Fx.dens += avx * (U_prev.dens - Uc.dens);
+                Fx.ener += avx * (U_prev.ener - Uc.ener);
+                Fx.xmom += avx * (U_prev.xmom - Uc.xmom);
+                Fx.ymom += avx * (U_prev.ymom - Uc.ymom);
+
+                if (i > i0) {
+                    // ---- M. conservative update of cell (i-1, j) (simulation.py:377-384) ------
+                    double fd = w.down(Fy.dens), fe = w.down(Fy.ener), fx = w.down(Fy.xmom), fy = w.down(Fy.ymom);
+                    Cons Un;
+                    Un.dens = U_prev.dens + dtdx * (Fx_prev.dens - Fx.dens) + dtdy * (Fy.dens - fd);
+                    Un.ener = U_prev.ener + dtdx * (Fx_prev.ener - Fx.ener) + dtdy * (Fy.ener - fe);
+                    Un.xmom = U_prev.xmom + dtdx * (Fx_prev.xmom - Fx.xmom) + dtdy * (Fy.xmom - fx);
+                    Un.ymom = U_prev.ymom + dtdx * (Fx_prev.ymom - Fx.ymom) + dtdy * (Fy.ymom - fy);
+                    if (out_lane) {
+                        double* o = Ocol + (long long)(i - 1) * A.pitch;
+                        o[0] = Un.dens; o[A.plane_stride] = Un.ener;
+                        o[2 * A.plane_stride] = Un.xmom; o[3 * A.plane_stride] = Un.ymom;
+                        double ax, ay;
+                        cfl_speeds(Un.dens, Un.ener, Un.xmom, Un.ymom, gamma, ax, ay);
+                        wmax_x = dmax(wmax_x, ax); wmax_y = dmax(wmax_y, ay);
+                    }
+                }
+                Fx_prev = Fx;
+            }
+
+            // ---- N. carry ---------------------------------------------------------------------
+            XPc = XP; XPpc = XPp; YMc = YM; YPc = YP; U_prev = Uc; divU_prev = divU;
+            xix_m1 = xix_0; xix_0 = xix_p1;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { l2x_m1[n] = l2x_0[n]; l2x_0[n] = l2x_p1[n]; }
+
+            // ---- O. row i-2 is dead: recycle its slot for row i+6 -----------------------------
+            w.sync();
+            if (i + 6 <= rlast) issue(i + 6, col0, ncols);
+        }
+
+        // wave-speed maxima of this strip (positive doubles order like their bit patterns)
+        wmax_x = w.reduce_max(wmax_x); wmax_y = w.reduce_max(wmax_y);
+        if (lane == 0) {
+            w.atomic_max_bits(&A.wavemax[0], wmax_x);
+            w.atomic_max_bits(&A.wavemax[1], wmax_y);
+        }
+    }
+};
+
+}  // namespace pyro

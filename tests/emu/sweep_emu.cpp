@@ -1,0 +1,132 @@
+// sweep_emu.cpp -- host-side emulation of one CUDA warp running pyro2_b200/csrc/sweep_task.cuh.
+//
+// TEST INFRASTRUCTURE ONLY (built by tests/conftest.py into tests/emu/libsweep_emu.so, loaded only
+// by tests/test_sweep_emulated.py).  It compiles the *same* SweepTask source as the device build,
+// with the warp services (shuffles, __syncwarp, TMA bulk copy + mbarrier) replaced by 32 host
+// threads in lock step.  This lets the kernel's indexing, halo logic and row pipeline be checked
+// against the oracle on the CPU-only build box; it is not a fallback and the product never loads it.
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "../../pyro2_b200/csrc/sweep_task.cuh"
+
+namespace {
+
+struct WarpShared {
+    pthread_barrier_t bar;
+    double slot[2][32];
+    int flip[32];
+};
+
+struct EmuWarp {
+    WarpShared* ws;
+    int lane_;
+
+    int lane() const { return lane_; }
+    void sync() const { pthread_barrier_wait(&ws->bar); }
+
+    // two alternating exchange buffers: one barrier per exchange is enough (see sweep_emu notes)
+    double exchange(double v, int from) const
+    {
+        int b = ws->flip[lane_];
+        ws->flip[lane_] ^= 1;
+        ws->slot[b][lane_] = v;
+        pthread_barrier_wait(&ws->bar);
+        return (from < 0 || from > 31) ? v : ws->slot[b][from];
+    }
+    double up(double v) const { return exchange(v, lane_ - 1); }
+    double down(double v) const { return exchange(v, lane_ + 1); }
+
+    void load_issue(unsigned long long&, double* d0, double* d1, double* d2, double* d3, const double* src,
+                    long long plane_stride, int ncols) const
+    {
+        if (lane_ == 0) {
+            double* dst[4] = {d0, d1, d2, d3};
+            for (int n = 0; n < 4; ++n) memcpy(dst[n], src + n * plane_stride, (size_t)ncols * 8);
+        }
+    }
+    void load_wait(unsigned long long&, unsigned) const { pthread_barrier_wait(&ws->bar); }
+
+    double reduce_max(double v) const
+    {
+        int b = ws->flip[lane_];
+        ws->flip[lane_] ^= 1;
+        ws->slot[b][lane_] = v;
+        pthread_barrier_wait(&ws->bar);
+        double m = v;
+        for (int l = 0; l < 32; ++l) m = std::max(m, ws->slot[b][l]);
+        return m;
+    }
+    void atomic_max_bits(unsigned long long* addr, double v) const
+    {
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        if (bits > *addr) *addr = bits;
+    }
+};
+
+struct LaneCtx {
+    WarpShared* ws;
+    pyro::SweepSmem* smem;
+    const pyro::SweepArgs* A;
+    int lane;
+    int ntasks;
+};
+
+void* lane_main(void* p)
+{
+    LaneCtx* c = (LaneCtx*)p;
+    EmuWarp w{c->ws, c->lane};
+    pyro::SweepTask<EmuWarp> T(w, *c->A, *c->smem, 0u);
+    for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, int ny, int ng, int pitch,
+                                      long long plane_stride, double dx, double dy, double dt,
+                                      double gamma, double z0, double z1, double delta, double cvisc,
+                                      int limiter, int use_flattening, int no_avisc_xhi, int no_avisc_yhi,
+                                      int seglen, uint64_t* scratch, double* dbg)
+{
+    pyro::SweepArgs A;
+    A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
+    A.nx = nx; A.ny = ny; A.ng = ng; A.dx = dx; A.dy = dy; A.dt = dt; A.gamma = gamma;
+    A.z0 = z0; A.z1 = z1; A.delta = delta; A.cvisc = cvisc;
+    A.limiter = limiter; A.use_flattening = use_flattening;
+    A.no_avisc_xhi = no_avisc_xhi; A.no_avisc_yhi = no_avisc_yhi;
+    A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
+    A.seglen = seglen;
+    A.nsegs = (nx + seglen - 1) / seglen;
+    memset(scratch, 0, 4 * sizeof(uint64_t));
+    A.wavemax = (unsigned long long*)scratch;
+    A.status = (int*)(scratch + 3);
+#ifdef SWEEP_DEBUG
+    A.dbg = dbg;
+#else
+    (void)dbg;
+#endif
+
+    WarpShared ws;
+    pthread_barrier_init(&ws.bar, nullptr, 32);
+    memset(ws.flip, 0, sizeof ws.flip);
+    pyro::SweepSmem* smem = new pyro::SweepSmem;
+    // poison the ring so that stale-slot reads show up as NaNs in the comparison
+    memset(smem, 0xff, sizeof *smem);
+    LaneCtx ctx[32];
+    pthread_t th[32];
+    for (int l = 0; l < 32; ++l) {
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs};
+        pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
+    }
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&ws.bar);
+    delete smem;
+    return 0;
+}
