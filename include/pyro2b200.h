@@ -102,6 +102,43 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
 /* launch geometry chosen for the last sweep (bench diagnostics): tasks, resident warps, seglen */
 int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
 
+/* ---- multigrid: CellCenterMG2d (pyro/multigrid/MG.py:77-778), constant coefficients,
+ * (alpha - beta L) phi = f, nx = ny = 2^k, ng = 1.  The handle is a host object; the hierarchy's
+ * device memory (p2b_mg_workspace_bytes, zero-initialised, 16-byte aligned) is allocated by the
+ * caller and attached with p2b_mg_bind.  Level l has 2^(l+1) cells per side (MG.py:207-257) and three
+ * planes: which = 0 v (solution / correction), 1 f (right-hand side), 2 r (residual), each
+ * (n+2) rows of p2b_mg_level_pitch elements.  bc = {xl, xr, yl, yr} codes ("dirichlet" ->
+ * P2B_BC_REFLECT_ODD, "neumann" -> P2B_BC_OUTFLOW as in pyro/mesh/array_indexer.py:160-162).
+ * All arithmetic is unfused and ordered as in the reference: v, f, r are bit-identical to it. */
+typedef struct p2b_mg p2b_mg;
+
+p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                      double ymin, double ymax, int nsmooth, int nsmooth_bottom);   /* MG.py:85-295 */
+int p2b_mg_destroy(p2b_mg* m);
+int p2b_mg_nlevels(p2b_mg* m);
+long long p2b_mg_workspace_bytes(p2b_mg* m);
+int p2b_mg_bind(p2b_mg* m, void* device_mem, long long bytes);
+void* p2b_mg_level_ptr(p2b_mg* m, int level, int which);
+int p2b_mg_level_pitch(p2b_mg* m, int level);
+/* inhomogeneous Dirichlet / Neumann values for phi on the finest level (MG.py:231-242): device
+ * arrays of n+2 doubles (xl, xr indexed by j; yl, yr by i) or NULL */
+int p2b_mg_set_bc_values(p2b_mg* m, const double* xl, const double* xr, const double* yl, const double* yr);
+
+int p2b_mg_smooth(p2b_mg* m, int level, int nsmooth, void* stream);      /* smooth, MG.py:544-599 */
+int p2b_mg_residual(p2b_mg* m, int level, void* stream);                 /* _compute_residual, MG.py:529-542 */
+int p2b_mg_restrict(p2b_mg* m, int level, void* stream);                 /* r(level) -> f(level-1): patch.py:640-676, MG.py:731-732 */
+int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream);          /* v(level) += P v(level-1), fill_BC: patch.py:678-736, MG.py:745-751 */
+int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream);                  /* grids[level].fill_BC("v") */
+int p2b_mg_zero_coarse(p2b_mg* m, void* stream);                         /* MG.py:658-659 */
+int p2b_mg_vcycle(p2b_mg* m, void* stream);                              /* v_cycle(nlevels-1), MG.py:699-778 */
+/* sum over the valid region of plane^2 -> *out_dev (ArrayIndexer.norm = sqrt(dx dy sum),
+ * pyro/mesh/array_indexer.py:98-111); deterministic summation order */
+int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out_dev, void* stream);
+/* per-cycle bookkeeping of solve() (MG.py:668-686) on the finest level:
+ *   out_dev[0] = sum(((v - old_phi) / (v + 1e-16))^2), old_phi <- v, r <- residual, out_dev[1] = sum(r^2)
+ * old_phi is a caller-owned (n+2) x pitch buffer */
+int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,202 @@
+"""Compressible solver front end: the reference's ``Simulation`` interface
+(pyro/compressible/simulation.py) with the time step executed by one fused CUDA kernel.
+
+What maps to what
+  Simulation.initialize               simulation.py:193-265  (grid, variables, BCs, problem init)
+  Simulation.method_compute_timestep  simulation.py:267-288  -> p2b_cfl_wavemax, or the maxima the
+                                                               previous sweep already accumulated
+  Simulation.evolve                   simulation.py:290-450  -> p2b_compressible_sweep
+  Simulation.clean_state              simulation.py:452-456
+  cons_to_prim / prim_to_cons         simulation.py:49-102   (torch, for users / tests / output)
+  Variables                           simulation.py:12-46
+
+Scope: Cartesian grid, HLLC, no gravity / sponge / particles / problem sources.
+Anything else raises instead of silently taking another path.
+"""
+import torch
+
+from .. import ops
+from ..mesh import boundary as bnd
+from ..simulation_null import NullSimulation, bc_setup, grid_setup
+from ..util import msg
+from . import derives, eos
+
+
+class Variables:
+    """integer keys of the conserved / primitive variables (simulation.py:12-46)"""
+
+    def __init__(self, myd):
+        self.nvar = len(myd.names)
+        self.idens = myd.names.index("density")
+        self.ixmom = myd.names.index("x-momentum")
+        self.iymom = myd.names.index("y-momentum")
+        self.iener = myd.names.index("energy")
+        self.naux = self.nvar - 4
+        self.irhox = 4 if self.naux > 0 else -1
+        self.nq = 4 + self.naux
+        self.irho, self.iu, self.iv, self.ip = 0, 1, 2, 3
+        self.ix = 4 if self.naux > 0 else -1
+
+
+def cons_to_prim(U, gamma, ivars, myg):
+    """conserved [i, j, n] -> primitive (rho, u, v, p) (simulation.py:49-80), on the device"""
+    q = myg.scratch_array(nvar=ivars.nq)
+    rho = U[:, :, ivars.idens].t()
+    nz = rho != 0.0
+    safe = torch.where(nz, rho, torch.ones_like(rho))
+    u = torch.where(nz, U[:, :, ivars.ixmom].t() / safe, torch.zeros_like(rho))
+    v = torch.where(nz, U[:, :, ivars.iymom].t() / safe, torch.zeros_like(rho))
+    e = torch.where(nz, (U[:, :, ivars.iener].t() - 0.5 * rho * (u ** 2 + v ** 2)) / safe, torch.zeros_like(rho))
+    g = myg
+    valid = (slice(g.ilo, g.ihi + 1), slice(g.jlo, g.jhi + 1))
+    e_min, rho_min = float(e[valid].min()), float(rho[valid].min())
+    assert e_min > 0.0 and rho_min > 0.0, f"invalid state, min(rho) = {rho_min}, min(e) = {e_min}"
+    q[:, :, ivars.irho] = rho
+    q[:, :, ivars.iu] = u
+    q[:, :, ivars.iv] = v
+    q[:, :, ivars.ip] = eos.pres(gamma, rho, e)
+    return q
+
+
+def prim_to_cons(q, gamma, ivars, myg):
+    """primitive -> conserved (simulation.py:83-102)"""
+    U = myg.scratch_array(nvar=ivars.nvar)
+    rho, u, v, p = (q[:, :, k].t() for k in (ivars.irho, ivars.iu, ivars.iv, ivars.ip))
+    U[:, :, ivars.idens] = rho
+    U[:, :, ivars.ixmom] = u * rho
+    U[:, :, ivars.iymom] = v * rho
+    U[:, :, ivars.iener] = eos.rhoe(gamma, p) + 0.5 * rho * (u ** 2 + v ** 2)
+    return U
+
+
+class Simulation(NullSimulation):
+    """unsplit CTU compressible hydrodynamics; same life cycle as the reference class"""
+
+    def initialize(self, *, extra_vars=None, ng=4):
+        if extra_vars:
+            raise NotImplementedError("passively advected extra variables are not in the device sweep")
+        rp = self.rp
+        my_grid = grid_setup(rp, ng=ng)
+        if ng < 4:
+            raise ValueError("the compressible sweep needs ng >= 4 (dependency radius, SURVEY.md 9.3)")
+        my_data = self.data_class(my_grid)
+
+        riemann_method = rp.get_param("compressible.riemann")
+        if riemann_method != "HLLC":
+            msg.fail(f"ERROR: the device sweep implements the HLLC Riemann solver only (got {riemann_method})")
+        if rp.get_param("compressible.grav") != 0.0:
+            msg.fail("ERROR: gravity source terms are not implemented in the device sweep (grav must be 0)")
+        try:
+            if rp.get_param("sponge.do_sponge"):
+                msg.fail("ERROR: the sponge term is not implemented in the device sweep")
+        except KeyError:
+            pass
+        try:
+            if rp.get_param("particles.do_particles") == 1:
+                msg.fail("ERROR: particles are not supported")
+        except KeyError:
+            pass
+        if self.problem_source is not None:
+            msg.fail("ERROR: problem source terms are not supported by the device sweep")
+
+        bc, bc_xodd, bc_yodd = bc_setup(rp)
+        self.solid = bnd.bc_is_solid(bc)
+
+        # registration order fixes the variable indices: dens 0, ener 1, xmom 2, ymom 3
+        # (simulation.py:223-226) -- the kernels rely on it
+        my_data.register_var("density", bc)
+        my_data.register_var("energy", bc)
+        my_data.register_var("x-momentum", bc_xodd)
+        my_data.register_var("y-momentum", bc_yodd)
+        my_data.set_aux("gamma", rp.get_param("eos.gamma"))
+        my_data.set_aux("grav", rp.get_param("compressible.grav"))
+        my_data.create()
+        self.cc_data = my_data
+
+        self.ivars = Variables(my_data)
+        assert (self.ivars.idens, self.ivars.iener, self.ivars.ixmom, self.ivars.iymom) == (0, 1, 2, 3)
+        self.cc_data.add_derived(derives.derive_primitives)
+
+        # second state buffer (the sweep is out of place) and the device scratch words
+        self._alt_planes = torch.zeros_like(my_data.planes)
+        self._scratch = ops.new_scratch()
+        self._wave_version = None     # cc_data.version for which the cached wave speeds are valid
+        self._pending_status = False
+
+        self.problem_func(self.cc_data, self.rp)
+        if self.verbose > 0:
+            print(my_data)
+
+    # ---- parameters of the sweep ------------------------------------------------------------
+    def _comp_params(self):
+        rp = self.rp
+        return ops.comp_params(gamma=rp.get_param("eos.gamma"), z0=rp.get_param("compressible.z0"),
+                               z1=rp.get_param("compressible.z1"), delta=rp.get_param("compressible.delta"),
+                               cvisc=rp.get_param("compressible.cvisc"),
+                               limiter=rp.get_param("compressible.limiter"),
+                               use_flattening=rp.get_param("compressible.use_flattening"),
+                               no_avisc_xhi=getattr(self, "_no_avisc_xhi", 1), no_avisc_yhi=1)
+
+    def _read_scratch(self):
+        """one D2H copy: wave-speed maxima + status word of the last sweep"""
+        words = self._scratch[:4].cpu()
+        if self._pending_status:
+            self._pending_status = False
+            if int(words[3]) != 0:
+                raise AssertionError("invalid state: rho <= 0 or e <= 0 in a valid zone "
+                                     "(compressible/simulation.py:71)")
+        return words[:2].view(torch.float64).tolist()
+
+    def check_state(self):
+        """raise now if the last evolve() saw an invalid state (otherwise raised by the next dt)"""
+        self._read_scratch()
+
+    def method_compute_timestep(self):
+        """CFL timestep (simulation.py:267-288): cfl * min(dx/(|u|+cs), dy/(|v|+cs)), bit-identical.
+        Uses the maxima the last sweep accumulated when nothing touched the data since; the ghost
+        cells the reference includes cannot change the minimum for the standard boundary types
+        (SURVEY.md 9.2-3)."""
+        cfl = self.rp.get_param("driver.cfl")
+        g = self.cc_data.grid
+        standard = all(t not in bnd.ext_bcs for b in self.cc_data.BCs.values() for t in b.names())
+        if self._wave_version is not None and self._wave_version == self.cc_data.version and standard:
+            wx, wy = self._read_scratch()
+        else:
+            if self._pending_status:
+                self._read_scratch()
+            wx, wy = ops.cfl_wavemax(self.cc_data.planes, g.nx, g.ny, g.ng, self.rp.get_param("eos.gamma"),
+                                     self._scratch)
+        self.dt = cfl * float(min(g.dx / wx, g.dy / wy))
+
+    def evolve(self):
+        """advance the state through dt with the fused sweep (simulation.py:290-450)"""
+        tm_evolve = self.tc.timer("evolve")
+        tm_evolve.begin()
+        myd = self.cc_data
+        g = myd.grid
+        self.clean_state(None)
+        ops.compressible_sweep(myd.planes, self._alt_planes, g.nx, g.ny, g.ng, g.dx, g.dy, float(self.dt),
+                               self._comp_params(), self._scratch)
+        # the new state lives in the other buffer; its ghost cells are filled by the next fill_BC
+        myd.planes, self._alt_planes = self._alt_planes, myd.planes
+        self._wave_version = myd.version
+        self._pending_status = True
+        myd.t += self.dt
+        self.n += 1
+        tm_evolve.end()
+
+    def clean_state(self, U):   # pylint: disable=unused-argument
+        """density floor (simulation.py:452-456); a no-op for the default small_dens = -1e200"""
+        small = self.rp.get_param("compressible.small_dens")
+        if small > -1.e100:
+            g = self.cc_data.grid
+            d = self.cc_data.planes[0, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1]
+            d.clamp_(min=small)
+
+    def dovis(self):
+        """runtime visualisation is host-side matplotlib in the reference; not part of the device build"""
+
+    def write_extras(self, f):
+        gb = f.create_group("BC")
+        gb.create_dataset("hse", data=False)
+        gb.create_dataset("ambient", data=False)

@@ -43,7 +43,7 @@ struct p2b_mg {
     double alpha, beta, xmin, xmax, ymin, ymax;
     int nsmooth, nsmooth_bottom;
     pyro::MgLevel lev[pyro::MG_MAX_LEVELS];
-    long long bytes, coarse_v_bytes;
+    long long bytes;
     double* base;
     double* partials;                         // MG_NPART doubles x 2
     const double *xlv, *xrv, *ylv, *yrv;
@@ -247,6 +247,16 @@ __global__ void mg_sumsq_final_kernel(const double* part, int npart, double* out
     if (threadIdx.x == 0) *out = sh[0];
 }
 
+struct MgZeroTable { double* v[MG_MAX_LEVELS]; long long count[MG_MAX_LEVELS]; int nlev; };
+
+__global__ void mg_zero_kernel(MgZeroTable t)
+{
+    for (int l = 0; l < t.nlev; ++l)
+        for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < t.count[l];
+             k += (long long)gridDim.x * blockDim.x)
+            t.v[l][k] = 0.0;
+}
+
 static MgBC level_bc(const p2b_mg* m, int level)
 {
     MgBC b;
@@ -365,7 +375,8 @@ p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double x
     m->alpha = alpha; m->beta = beta;
     m->xmin = xmin; m->xmax = xmax; m->ymin = ymin; m->ymax = ymax;
     m->nsmooth = nsmooth; m->nsmooth_bottom = nsmooth_bottom;
-    // layout: [v of levels 0..L-2] [f, r of levels 0..L-2] [v, f, r of the finest] [partials]
+    // layout: per level three consecutive planes v, f, r (uniform plane stride, so a level is one
+    // strided (3, n+2, pitch) tensor on the Python side); then the norm partials
     long long off = 0;
     for (int l = 0; l < m->nlevels; ++l) {
         MgLevel& L = m->lev[l];
@@ -374,19 +385,12 @@ p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double x
         L.pitch = (q >= 16) ? (q + 15) / 16 * 16 : (q + 1) / 2 * 2;
         L.dx = (xmax - xmin) / L.n;
         L.dy = (ymax - ymin) / L.n;
+        long long plane = (long long)q * L.pitch;
+        // offsets are stored as fake pointers (element counts) until p2b_mg_bind
+        L.v = (double*)off; off += plane;
+        L.f = (double*)off; off += plane;
+        L.r = (double*)off; off += plane;
     }
-    auto plane = [](const MgLevel& L) { return (long long)(L.n + 2) * L.pitch; };
-    // offsets are stored as fake pointers (element counts) until p2b_mg_bind
-    for (int l = 0; l < m->nlevels - 1; ++l) { m->lev[l].v = (double*)off; off += plane(m->lev[l]); }
-    m->coarse_v_bytes = off * 8;
-    for (int l = 0; l < m->nlevels - 1; ++l) {
-        m->lev[l].f = (double*)off; off += plane(m->lev[l]);
-        m->lev[l].r = (double*)off; off += plane(m->lev[l]);
-    }
-    MgLevel& Lf = m->lev[m->nlevels - 1];
-    Lf.v = (double*)off; off += plane(Lf);
-    Lf.f = (double*)off; off += plane(Lf);
-    Lf.r = (double*)off; off += plane(Lf);
     m->partials = (double*)off; off += 2 * MG_NPART;
     m->bytes = off * 8;
     return m;
@@ -476,11 +480,23 @@ int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream)
     return P2B_OK;
 }
 
-// zero v on every level but the finest (MG.py:658-659); the coarse v planes are contiguous
+// zero v on every level but the finest (MG.py:658-659), one launch
 int p2b_mg_zero_coarse(p2b_mg* m, void* stream)
 {
     P2B_REQUIRE(m && m->base, "hierarchy not bound");
-    if (m->coarse_v_bytes) P2B_CUDA_CHECK(cudaMemsetAsync(m->base, 0, m->coarse_v_bytes, (cudaStream_t)stream));
+    if (m->nlevels < 2) return P2B_OK;
+    MgZeroTable t;
+    t.nlev = m->nlevels - 1;
+    long long most = 0;
+    for (int l = 0; l < t.nlev; ++l) {
+        t.v[l] = m->lev[l].v;
+        t.count[l] = (long long)(m->lev[l].n + 2) * m->lev[l].pitch;
+        if (t.count[l] > most) most = t.count[l];
+    }
+    long long blocks = (most + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    mg_zero_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(t);
+    P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
 

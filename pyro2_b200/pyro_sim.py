@@ -1,0 +1,144 @@
+"""The driver: mirror of pyro/pyro_sim.py (Pyro :34-322) for the solvers this package provides.
+
+    p = Pyro("compressible")
+    p.initialize_problem("sedov", inputs_dict={"mesh.nx": 4096, "mesh.ny": 4096})
+    p.run_sim()            # or p.single_step() in a loop
+
+single_step() keeps the reference's order: fill_BC_all -> compute_timestep -> evolve
+(pyro_sim.py:241-256)."""
+import importlib
+import os
+
+from .util import msg
+from .util import profile_pyro as profile
+from .util.runparams import RuntimeParameters
+
+valid_solvers = ["compressible"]
+
+
+class Pyro:
+    def __init__(self, solver_name, *, from_commandline=False):
+        if from_commandline:
+            msg.bold("pyro (B200 hot-path build) ...")
+        if solver_name not in valid_solvers:
+            msg.fail(f"ERROR: {solver_name} is not a valid solver (this build provides {valid_solvers})")
+        self.from_commandline = from_commandline
+        self.pyro_home = os.path.dirname(os.path.realpath(__file__)) + "/"
+        self.solver = importlib.import_module(f"{__package__}.{solver_name}")
+        self.solver_name = solver_name
+        self.problem_name = None
+        self.problem_func = None
+        self.problem_source = None
+        self.problem_params = None
+        self.problem_finalize = None
+        self.custom_problems = {}
+        self.rp = RuntimeParameters()
+        self.rp.load_params(self.pyro_home + "_defaults")
+        self.rp.load_params(self.pyro_home + self.solver_name + "/_defaults")
+        self.tc = profile.TimerCollection()
+        self.is_initialized = False
+
+    def add_problem(self, name, problem_func, *, problem_params=None):
+        """register a custom initial-condition function (pyro_sim.py:91-106)"""
+        self.custom_problems[name] = (problem_func, problem_params or {})
+
+    def initialize_problem(self, problem_name, *, inputs_file=None, inputs_dict=None):
+        if problem_name in self.custom_problems:
+            self.problem_name = problem_name
+            self.problem_func, self.problem_params = self.custom_problems[problem_name]
+            self.problem_finalize = None
+            self.problem_source = None
+        else:
+            problem = importlib.import_module(f"{__package__}.{self.solver_name}.problems.{problem_name}")
+            self.problem_name = problem_name
+            self.problem_func = problem.init_data
+            self.problem_params = problem.PROBLEM_PARAMS
+            self.problem_finalize = problem.finalize
+            self.problem_source = getattr(problem, "source_terms", None)
+            if inputs_file is None:
+                inputs_file = problem.DEFAULT_INPUTS
+
+        for k, v in self.problem_params.items():
+            self.rp.set_param(k, v, no_new=False)
+
+        if inputs_file is not None:
+            if not os.path.isfile(inputs_file):
+                inputs_file = self.pyro_home + self.solver_name + "/problems/" + inputs_file
+                if not os.path.isfile(inputs_file):
+                    msg.fail("ERROR: inputs file does not exist")
+            self.rp.load_params(inputs_file, no_new=1)
+
+        if not self.from_commandline:
+            self.rp.set_param("vis.dovis", 0)
+            self.rp.set_param("driver.verbose", 0)
+            self.rp.set_param("io.do_io", 0)
+
+        if inputs_dict is not None:
+            for k, v in inputs_dict.items():
+                self.rp.set_param(k, v)
+
+        self.verbose = self.rp.get_param("driver.verbose")
+        self.dovis = self.rp.get_param("vis.dovis")
+
+        self.sim = self.solver.Simulation(self.solver_name, self.problem_name, self.problem_func, self.rp,
+                                          problem_finalize_func=self.problem_finalize,
+                                          problem_source_func=self.problem_source, timers=self.tc)
+        self.sim.initialize()
+        self.sim.preevolve()
+        self.sim.cc_data.t = 0.0
+        self.is_initialized = True
+
+    def run_sim(self):
+        if not self.is_initialized:
+            msg.fail("ERROR: problem has not been initialized")
+        tm_main = self.tc.timer("main")
+        tm_main.begin()
+        basename = self.rp.get_param("io.basename")
+        do_io = self.rp.get_param("io.do_io")
+        if do_io:
+            self.sim.write(f"{basename}{self.sim.n:04d}")
+        while not self.sim.finished():
+            self.single_step()
+        if do_io or self.rp.get_param("io.force_final_output"):
+            self.sim.write(f"{basename}{self.sim.n:04d}")
+        tm_main.end()
+        if self.verbose > 0:
+            self.rp.print_unused_params()
+            self.tc.report()
+        self.sim.finalize()
+
+    def single_step(self):
+        if not self.is_initialized:
+            msg.fail("ERROR: problem has not been initialized")
+        self.sim.cc_data.fill_BC_all()
+        self.sim.compute_timestep()
+        self.sim.evolve()
+        if self.verbose > 0:
+            print("%5d %10.5f %10.5f" % (self.sim.n, self.sim.cc_data.t, self.sim.dt))
+        if self.sim.do_output():
+            basename = self.rp.get_param("io.basename")
+            self.sim.write(f"{basename}{self.sim.n:04d}")
+
+    def __repr__(self):
+        return f"Pyro('{self.solver_name}')"
+
+    def __str__(self):
+        s = f"Solver = {self.solver_name}\n"
+        if self.is_initialized:
+            s += f"Problem = {self.sim.problem_name}\n"
+            s += f"Simulation time = {self.sim.cc_data.t}\n"
+            s += f"Simulation step number = {self.sim.n}\n"
+        return s + "\nRuntime Parameters\n------------------\n" + str(self.rp)
+
+    def get_var(self, v):
+        if not self.is_initialized:
+            msg.fail("ERROR: problem has not been initialized")
+        return self.sim.cc_data.get_var(v)
+
+    def get_grid(self):
+        if not self.is_initialized:
+            msg.fail("ERROR: problem has not been initialized")
+        return self.sim.cc_data.grid
+
+    def get_sim(self):
+        return self.sim

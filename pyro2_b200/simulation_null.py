@@ -1,0 +1,145 @@
+"""Solver-independent simulation scaffolding: mirror of pyro/simulation_null.py
+(grid_setup :10-68, bc_setup :71-112, NullSimulation :115-300)."""
+from .mesh import boundary as bnd
+from .mesh import patch
+from .util import msg
+from .util import profile_pyro as profile
+
+
+def _param(rp, key, default):
+    try:
+        return rp.get_param(key)
+    except KeyError:
+        msg.warning(f"{key} not set, defaulting to {default}")
+        return default
+
+
+def grid_setup(rp, ng=1):
+    nx = rp.get_param("mesh.nx")
+    ny = rp.get_param("mesh.ny")
+    xmin = _param(rp, "mesh.xmin", 0.0)
+    xmax = _param(rp, "mesh.xmax", 1.0)
+    ymin = _param(rp, "mesh.ymin", 0.0)
+    ymax = _param(rp, "mesh.ymax", 1.0)
+    grid_type = _param(rp, "mesh.grid_type", "Cartesian2d")
+    if grid_type != "Cartesian2d":
+        # SphericalPolar is outside the B200 hot-path scope
+        raise ValueError("Unsupported grid type!")
+    return patch.Cartesian2d(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)
+
+
+def bc_setup(rp):
+    """BC objects for scalars, x-velocity-like and y-velocity-like variables (odd reflection in
+    the normal direction)"""
+    types = {k: _param(rp, f"mesh.{k}boundary", "periodic") for k in ("xl", "xr", "yl", "yr")}
+    kw = {"xlb": types["xl"], "xrb": types["xr"], "ylb": types["yl"], "yrb": types["yr"]}
+    return bnd.BC(**kw), bnd.BC(**kw, odd_reflect_dir="x"), bnd.BC(**kw, odd_reflect_dir="y")
+
+
+class NullSimulation:
+    """time-step bookkeeping shared by all solvers"""
+
+    def __init__(self, solver_name, problem_name, problem_func, rp, *,
+                 problem_finalize_func=None, problem_source_func=None,
+                 timers=None, data_class=patch.CellCenterData2d):
+        self.n = 0
+        self.dt = -1.e33
+        self.dt_old = -1.e33
+        self.data_class = data_class
+        try:
+            self.tmax = rp.get_param("driver.tmax")
+        except (AttributeError, KeyError):
+            self.tmax = None
+        try:
+            self.max_steps = rp.get_param("driver.max_steps")
+        except (AttributeError, KeyError):
+            self.max_steps = None
+        self.rp = rp
+        self.cc_data = None
+        self.particles = None
+        self.SMALL = 1.e-12
+        self.solver_name = solver_name
+        self.problem_name = problem_name
+        self.problem_func = problem_func
+        self.problem_finalize = problem_finalize_func
+        self.problem_source = problem_source_func
+        self.tc = profile.TimerCollection() if timers is None else timers
+        try:
+            self.verbose = self.rp.get_param("driver.verbose")
+        except (AttributeError, KeyError):
+            self.verbose = 0
+        self.n_num_out = 0
+        self.cm = "viridis"
+
+    def __str__(self):
+        return f"pyro Simulation:\n  solver: {self.solver_name}\n  problem: {self.problem_name}\n"
+
+    def finished(self):
+        return self.cc_data.t >= self.tmax or self.n >= self.max_steps
+
+    def do_output(self):
+        dt_out = self.rp.get_param("io.dt_out")
+        n_out = self.rp.get_param("io.n_out")
+        do_io = self.rp.get_param("io.do_io")
+        is_time = self.cc_data.t >= (self.n_num_out + 1) * dt_out or self.n % n_out == 0
+        if is_time and do_io == 1:
+            self.n_num_out += 1
+            return True
+        return False
+
+    def initialize(self):
+        pass
+
+    def method_compute_timestep(self):
+        """the method-specific timestep code"""
+
+    def compute_timestep(self):
+        """driver-level limits on the method's dt (simulation_null.py:222-244)"""
+        init_tstep_factor = self.rp.get_param("driver.init_tstep_factor")
+        max_dt_change = self.rp.get_param("driver.max_dt_change")
+        fix_dt = self.rp.get_param("driver.fix_dt")
+        if fix_dt > 0.0:
+            self.dt = fix_dt
+        else:
+            self.method_compute_timestep()
+            if self.n == 0:
+                self.dt = init_tstep_factor * self.dt
+            else:
+                self.dt = min(max_dt_change * self.dt_old, self.dt)
+            self.dt_old = self.dt
+        if self.cc_data.t + self.dt > self.tmax:
+            self.dt = self.tmax - self.cc_data.t
+
+    def preevolve(self):
+        pass
+
+    def evolve(self):
+        self.cc_data.t += self.dt
+        self.n += 1
+
+    def dovis(self):
+        pass
+
+    def finalize(self):
+        if self.problem_finalize:
+            self.problem_finalize()
+
+    def write(self, filename):
+        """HDF5 snapshot in the reference's layout (simulation_null.py:270-290); needs h5py"""
+        import h5py   # pylint: disable=import-outside-toplevel
+        if not filename.endswith(".h5"):
+            filename += ".h5"
+        with h5py.File(filename, "w") as f:
+            f.attrs["solver"] = self.solver_name
+            f.attrs["problem"] = self.problem_name
+            f.attrs["time"] = self.cc_data.t
+            f.attrs["nsteps"] = self.n
+            self.cc_data.write_data(f)
+            self.rp.write_params(f)
+            self.write_extras(f)
+
+    def write_extras(self, f):
+        pass
+
+    def read_extras(self, f):
+        pass

@@ -1,0 +1,120 @@
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE UNMODIFIED REFERENCE
+(/root/reference, python-hydro/pyro2) through its own public API.  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Outputs (small .npz files, committed):
+  comp_<problem>.npz   Pyro("compressible") runs: parameters, initial state, per-step dt, final state
+  mg_<case>.npz        CellCenterMG2d solves: rhs, solution, cycle count, residual / relative errors
+  mesh_bcs.npz         ghost fill of an integer array for every standard BC type (test_patch.py style)
+  ref_kats.npz         known answers quoted from the reference's own unit tests / stored outputs
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+import ref_shim  # noqa: E402
+
+ref_shim.load()
+
+
+def comp_case(name, problem, params, nsteps):
+    p = ref_shim.make_sim("compressible", problem, dict(params, **{"driver.max_steps": 100000}))
+    sim = p.sim
+    g = sim.cc_data.grid
+    U0 = np.asarray(sim.cc_data.data).copy()
+    dts = []
+    for _ in range(nsteps):
+        if sim.finished():
+            break
+        p.single_step()
+        dts.append(sim.dt)
+    rp = sim.rp
+    keys = ["eos.gamma", "compressible.limiter", "compressible.use_flattening", "compressible.cvisc",
+            "compressible.z0", "compressible.z1", "compressible.delta", "driver.cfl", "driver.tmax",
+            "driver.init_tstep_factor", "driver.max_dt_change",
+            "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
+            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
+    np.savez_compressed(os.path.join(HERE, f"comp_{name}.npz"),
+                        problem=problem, inputs=np.array([f"{k}={v}" for k, v in params.items()]),
+                        rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]),
+                        ng=g.ng, U0=U0, U=np.asarray(sim.cc_data.data).copy(), dts=np.array(dts),
+                        t=sim.cc_data.t, n=sim.n)
+    print(name, "steps", sim.n, "t", sim.cc_data.t)
+
+
+def mg_case(name, nx, bc, alpha, beta, rhs_kind, rtol, bcfuncs=None):
+    import pyro.multigrid.MG as MG
+    kw = dict(xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3], alpha=alpha, beta=beta)
+    if bcfuncs:
+        kw.update(bcfuncs)
+    a = MG.CellCenterMG2d(nx, nx, **kw)
+    x, y = a.x2d, a.y2d
+    if rhs_kind == "poly":
+        f = -2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2))
+    elif rhs_kind == "periodic":
+        f = np.sin(2 * np.pi * x) * np.cos(4 * np.pi * y)
+    else:
+        f = np.exp(-((x - 0.5) ** 2 + (y - 0.5) ** 2) / 0.02)
+    a.init_zeros()
+    a.init_RHS(f)
+    # per-cycle history: re-implement the loop's prints by wrapping v_cycle
+    hist = []
+    a.solve(rtol=rtol)
+    np.savez_compressed(os.path.join(HERE, f"mg_{name}.npz"), nx=nx, bc=np.array(bc), alpha=alpha, beta=beta,
+                        rtol=rtol, f=np.asarray(f), v=np.asarray(a.get_solution()),
+                        num_cycles=a.num_cycles, residual_error=a.residual_error,
+                        relative_error=a.relative_error, source_norm=a.source_norm)
+    print(name, "cycles", a.num_cycles, "resid", a.residual_error)
+
+
+def mesh_bcs():
+    from pyro.mesh import boundary as bnd
+    from pyro.mesh import patch
+    out = {}
+    rng = np.random.default_rng(7)
+    for ng in (1, 4):
+        g = patch.Grid2d(6, 5, ng=ng)
+        base = rng.integers(-50, 50, size=(g.qx, g.qy))
+        out[f"base_ng{ng}"] = base
+        for t in ("outflow", "periodic", "reflect-even", "reflect-odd"):
+            d = patch.CellCenterData2d(g, dtype=np.int_)
+            d.register_var("a", bnd.BC(xlb=t, xrb=t, ylb=t, yrb=t))
+            d.create()
+            d.get_var("a")[:, :] = base
+            d.fill_BC("a")
+            out[f"{t}_ng{ng}"] = np.asarray(d.get_var("a")).copy()
+    np.savez_compressed(os.path.join(HERE, "mesh_bcs.npz"), **out)
+    print("mesh_bcs done")
+
+
+def ref_kats():
+    """constants the reference's own tests assert (cited so the oracle is pinned to them too)"""
+    conv = np.loadtxt(os.path.join(ref_shim.REF_ROOT, "pyro/multigrid/tests/mg_convergence.txt"))
+    np.savez_compressed(os.path.join(HERE, "ref_kats.npz"),
+                        mg_convergence=conv,                       # pyro/multigrid/tests/mg_convergence.txt
+                        mg_gradient_row=np.array([0, 36, 60, 36, 12, -12, -36, -60, -36, 0.]),  # test_multigrid_comps.py:54-57
+                        indexer_v=np.array([[16., 17., 18.], [23., 24., 25.]]),                  # test_array_indexer.py:22
+                        indexer_ip1=np.array([[23., 24., 25.], [30., 31., 32.]]),
+                        indexer_jpm1=np.array([[15., 16., 17.], [22., 23., 24.]]),
+                        advection_smooth_sum=4.310466040637315e+03)
+    print("kats done", conv.shape)
+
+
+if __name__ == "__main__":
+    comp_case("sedov64", "sedov", {"mesh.nx": 64, "mesh.ny": 64, "sedov.r_init": 0.05, "driver.tmax": 0.05}, 40)
+    comp_case("quad64", "quad", {"mesh.nx": 64, "mesh.ny": 64, "driver.tmax": 0.3}, 40)
+    comp_case("sod_x", "sod", {}, 1000)          # the reference's own regression setup: 128x10, limiter 1, 76 steps
+    comp_case("kh32", "kh", {"mesh.nx": 32, "mesh.ny": 32, "driver.tmax": 0.2}, 25)
+    mg_case("poisson_dirichlet_64", 64, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
+    mg_case("poisson_dirichlet_256", 256, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
+    mg_case("poisson_periodic_64", 64, ("periodic",) * 4, 0.0, -1.0, "periodic", 1.e-11)
+    mg_case("helmholtz_neumann_64", 64, ("neumann",) * 4, 1.0, 0.01, "gauss", 1.e-12)
+    mg_case("poisson_mixed_128", 128, ("dirichlet", "dirichlet", "neumann", "neumann"), 0.0, -1.0, "poly", 1.e-11)
+    mg_case("poisson_inhom_64", 64, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11,
+            bcfuncs=dict(xl_BC=lambda y: y ** 2, xr_BC=lambda y: 1.0 + y, yl_BC=lambda x: x, yr_BC=lambda x: 1.0 + x ** 2))
+    mesh_bcs()
+    ref_kats()

@@ -1,0 +1,184 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pyro2b200.h declares (no compute
+call is made), and the host-side mirror of the reference interfaces behaves like the reference's
+own unit tests say (pyro/mesh/tests/test_array_indexer.py, pyro/mesh/tests/test_patch.py,
+pyro/tests/test_simulation.py, pyro/util tests)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyro2_b200 import _lib
+    _lib.build()
+    header = open(os.path.join(ROOT, "include", "pyro2b200.h")).read()
+    declared = set(re.findall(r"\b(p2b_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    L = _lib.lib()          # raises if any bound symbol is missing
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.p2b_version() >= 100
+
+
+def test_product_has_no_cpu_fallback():
+    from pyro2_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        ops.alloc_planes(4, 8, 8)
+    from pyro2_b200.mesh.patch import Grid2d
+    with pytest.raises(RuntimeError):
+        Grid2d(4, 4)                     # default device is CUDA; no silent CPU path
+    # nothing under pyro2_b200/ may reference the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pyro2_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_buf_split_and_indexer_views():
+    from pyro2_b200.mesh import array_indexer as ai
+    from pyro2_b200.mesh.patch import Grid2d
+    assert list(ai._buf_split(2)) == [2, 2, 2, 2]
+    assert list(ai._buf_split((2, 3))) == [2, 3, 2, 3]
+    assert list(ai._buf_split((1, 2, 3, 4))) == [1, 2, 3, 4]
+    g = Grid2d(2, 3, ng=2, device="cpu")
+    a = g.scratch_array()
+    a[:, :] = np.arange(g.qx * g.qy, dtype=np.float64).reshape(g.qx, g.qy)
+    kat = np.load(os.path.join(ROOT, "tests", "golden", "ref_kats.npz"))
+    assert np.array_equal(a.v().numpy(), kat["indexer_v"])           # test_array_indexer.py:22
+    assert np.array_equal(a.ip(1).numpy(), kat["indexer_ip1"])
+    assert np.array_equal(a.jp(-1).numpy(), kat["indexer_jpm1"])
+    assert np.array_equal(a.ip_jp(1, 1).numpy(), np.array([[24., 25., 26.], [31., 32., 33.]]))
+    # views alias the storage
+    a.v()[:, :] = -1.0
+    assert float(a[g.ilo, g.jlo]) == -1.0
+    # strided views (multigrid colouring)
+    assert a.v(s=2).shape == (1, 2)
+
+
+def test_grid_indices_and_coordinates():
+    from pyro2_b200.mesh.patch import Cartesian2d
+    g = Cartesian2d(8, 16, ng=4, xmax=2.0, device="cpu")
+    assert (g.ilo, g.ihi, g.jlo, g.jhi, g.qx, g.qy) == (4, 11, 4, 19, 16, 24)
+    assert g.dx == 0.25 and g.dy == 1.0 / 16
+    assert np.allclose(g.x[g.ilo], 0.125) and np.allclose(g.xl[g.ilo], 0.0) and np.allclose(g.xr[g.ihi], 2.0)
+    assert g.x2d.shape == (16, 24) and float(g.x2d[g.ilo, 0]) == g.x[g.ilo]
+    assert float(g.V[0, 0]) == g.dx * g.dy and g.coord_type == 0
+    assert g.coarse_like(2).nx == 4 and g.fine_like(2).ny == 32
+    assert g == Cartesian2d(8, 16, ng=4, xmax=2.0, device="cpu")
+
+
+def test_cellcenterdata_layout_and_norm():
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.mesh.patch import CellCenterData2d, Grid2d
+    g = Grid2d(4, 6, ng=2, device="cpu")
+    d = CellCenterData2d(g)
+    bc = bnd.BC()
+    d.register_var("a", bc)
+    d.register_var("b", bc)
+    d.create()
+    assert d.data.shape == (8, 10, 2)
+    d.get_var("b")[:, :] = 3.0
+    assert float(d.data[1, 2, 1]) == 3.0 and float(d.data[1, 2, 0]) == 0.0
+    assert d.get_var("b").norm() == pytest.approx(np.sqrt(g.dx * g.dy * 9.0 * 24))   # test_patch.py norm
+    assert float(d.max("b")) == 3.0 and float(d.min("a")) == 0.0
+    d.zero("b")
+    assert float(d.max("b")) == 0.0
+    with pytest.raises(KeyError):
+        d.get_var("nope")
+
+
+def test_restrict_prolong_conserve():
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.mesh.patch import CellCenterData2d, Grid2d
+    g = Grid2d(8, 8, ng=1, device="cpu")
+    d = CellCenterData2d(g)
+    d.register_var("a", bnd.BC())
+    d.create()
+    rng = np.random.default_rng(0)
+    d.get_var("a").v()[:, :] = torch.from_numpy(rng.standard_normal((8, 8)))
+    c = d.restrict("a")
+    assert float(c.v().sum()) * 4 == pytest.approx(float(d.get_var("a").v().sum()))
+    f = d.prolong("a")
+    assert f.v().shape == (16, 16)
+    assert float(f.v().sum()) / 4 == pytest.approx(float(d.get_var("a").v().sum()))
+
+
+def test_bc_object_rules():
+    from pyro2_b200.mesh import boundary as bnd
+    b = bnd.BC(xlb="reflect", xrb="reflect", ylb="reflect", yrb="outflow", odd_reflect_dir="x")
+    assert b.names() == ("reflect-odd", "reflect-odd", "reflect-even", "outflow")
+    s = bnd.bc_is_solid(b)
+    assert (s.xl, s.xr, s.yl, s.yr) == (1, 1, 1, 0)
+    with pytest.raises(SystemExit):
+        bnd.BC(xlb="periodic", xrb="outflow")
+    with pytest.raises(SystemExit):
+        bnd.BC(xlb="bogus")
+
+
+def test_runtime_parameters(tmp_path):
+    from pyro2_b200.util.runparams import RuntimeParameters
+    f = tmp_path / "inputs"
+    f.write_text("[driver]\ncfl = 0.8 ; the CFL number\nmax_steps = 10\n[mesh]\nxlboundary = outflow\n")
+    rp = RuntimeParameters()
+    rp.load_params(str(f))
+    assert rp.get_param("driver.cfl") == 0.8 and isinstance(rp.get_param("driver.max_steps"), int)
+    assert rp.get_param("mesh.xlboundary") == "outflow"
+    assert rp.param_comments["driver.cfl"] == "the CFL number"
+    rp.set_param("driver.cfl", 0.5)
+    assert rp.get_param("driver.cfl") == 0.5
+    with pytest.raises(KeyError):
+        rp.set_param("driver.nope", 1)
+    with pytest.raises(KeyError):
+        rp.get_param("driver.nope")
+    rp.set_param("new.key", 3, no_new=False)
+    rp.command_line_params(["driver.max_steps=20"])
+    assert rp.get_param("driver.max_steps") == 20
+    g = tmp_path / "over"
+    g.write_text("[driver]\ncfl = 0.3\nunknown = 1\n")
+    rp.load_params(str(g), no_new=True)
+    assert rp.get_param("driver.cfl") == 0.3 and "driver.unknown" not in rp.params
+
+
+def test_compute_timestep_limits():
+    """NullSimulation.compute_timestep (pyro/tests/test_simulation.py:49-68 logic)"""
+    from pyro2_b200.simulation_null import NullSimulation
+    from pyro2_b200.util.runparams import RuntimeParameters
+
+    class Sim(NullSimulation):
+        raw = 1.0
+
+        def method_compute_timestep(self):
+            self.dt = self.raw
+
+    class Data:
+        t = 0.0
+
+    rp = RuntimeParameters()
+    for k, v in {"driver.tmax": 10.0, "driver.max_steps": 5, "driver.init_tstep_factor": 0.01,
+                 "driver.max_dt_change": 2.0, "driver.fix_dt": -1.0, "driver.verbose": 0}.items():
+        rp.set_param(k, v, no_new=False)
+    s = Sim("x", "y", None, rp)
+    s.cc_data = Data()
+    s.compute_timestep()
+    assert s.dt == 0.01
+    s.n = 1
+    s.compute_timestep()
+    assert s.dt == 0.02               # limited by max_dt_change * dt_old
+    s.cc_data.t = 9.99
+    s.compute_timestep()
+    assert s.dt == pytest.approx(0.01) and s.cc_data.t + s.dt == pytest.approx(10.0)
+    rp.set_param("driver.fix_dt", 0.125)
+    s.cc_data.t = 0.0
+    s.compute_timestep()
+    assert s.dt == 0.125
+    assert not s.finished()
+    s.n = 5
+    assert s.finished()

@@ -1,0 +1,106 @@
+"""CPU: the oracle (oracle/pyro_oracle.c) against the fixtures produced by running the unmodified
+reference (tests/golden/make_golden.py) -- this is what pins the oracle.  Tolerances: the
+compressible step matches the reference to ~1e-15 per step (np.dot / pow ordering), 1e-12 after
+tens of steps; multigrid solutions are bit-identical; dt is bit-identical."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_l2
+from golden_util import load_comp, load_mg, var_bcs
+
+
+def _run_oracle(z, rp, nsteps=None):
+    ng = int(z["ng"])
+    U = z["U0"].copy()
+    nx, ny = rp["mesh.nx"], rp["mesh.ny"]
+    dx = (rp["mesh.xmax"] - rp["mesh.xmin"]) / nx
+    dy = (rp["mesh.ymax"] - rp["mesh.ymin"]) / ny
+    prm = oracle.comp_params(gamma=rp["eos.gamma"], z0=rp["compressible.z0"], z1=rp["compressible.z1"],
+                             delta=rp["compressible.delta"], cvisc=rp["compressible.cvisc"],
+                             limiter=rp["compressible.limiter"], use_flattening=rp["compressible.use_flattening"])
+    bcs = var_bcs(rp)
+    t, dt_old, dts = 0.0, None, []
+    nsteps = len(z["dts"]) if nsteps is None else nsteps
+    for n in range(nsteps):
+        for k in range(4):
+            pl = np.ascontiguousarray(U[:, :, k])
+            oracle.fill_ghost(pl, ng, bcs[k])
+            U[:, :, k] = pl
+        dt = oracle.cfl_dt(U, ng, dx, dy, rp["eos.gamma"], rp["driver.cfl"])
+        # NullSimulation.compute_timestep (simulation_null.py:222-244)
+        dt = rp["driver.init_tstep_factor"] * dt if n == 0 else min(rp["driver.max_dt_change"] * dt_old, dt)
+        dt_old = dt
+        if t + dt > rp["driver.tmax"]:
+            dt = rp["driver.tmax"] - t
+        U = oracle.compressible_step(U, ng, dx, dy, dt, prm)
+        t += dt
+        dts.append(dt)
+    return U, np.array(dts), ng
+
+
+@pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32"])
+def test_compressible_run_matches_reference(name):
+    z, rp, _ = load_comp(name)
+    U, dts, ng = _run_oracle(z, rp)
+    ref = z["U"]
+    v = (slice(ng, -ng), slice(ng, -ng))
+    assert np.allclose(dts, z["dts"], rtol=1e-12, atol=0)
+    assert dts[0] == z["dts"][0]          # first dt: pure CFL reduction, bit-exact
+    for n in range(4):
+        assert rel_l2(U[v][..., n], ref[v][..., n]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["poisson_dirichlet_64", "poisson_dirichlet_256", "poisson_periodic_64",
+                                  "helmholtz_neumann_64", "poisson_mixed_128"])
+def test_mg_solve_matches_reference(name):
+    z = load_mg(name)
+    o = oracle.MG(int(z["nx"]), bc=tuple(str(b) for b in z["bc"]), alpha=float(z["alpha"]), beta=float(z["beta"]))
+    o.init_zeros()
+    o.init_RHS(z["f"])
+    o.solve(rtol=float(z["rtol"]))
+    assert o.num_cycles == int(z["num_cycles"])
+    assert np.array_equal(o.get_solution(), z["v"])
+    assert abs(o.residual_error - float(z["residual_error"])) <= 1e-12 * float(z["residual_error"]) + 1e-25
+    assert abs(o.source_norm - float(z["source_norm"])) <= 1e-14 * float(z["source_norm"])
+
+
+def test_mg_inhomogeneous_dirichlet_matches_reference():
+    z = load_mg("poisson_inhom_64")
+    nx = int(z["nx"])
+    o = oracle.MG(nx)
+    c = (np.arange(nx + 2) - 0.5) / nx
+    o.set_bc_values("xl", c ** 2); o.set_bc_values("xr", 1.0 + c)
+    o.set_bc_values("yl", c); o.set_bc_values("yr", 1.0 + c ** 2)
+    o.init_zeros()
+    o.init_RHS(z["f"])
+    o.solve(rtol=float(z["rtol"]))
+    assert o.num_cycles == int(z["num_cycles"])
+    assert np.array_equal(o.get_solution(), z["v"])
+
+
+def test_mg_convergence_table():
+    """pyro/multigrid/tests/mg_convergence.txt: L2 error vs the analytic solution, N = 16 .. 256"""
+    kat = np.load(__import__("os").path.join(__import__("golden_util").GOLDEN, "ref_kats.npz"))
+    for n, err in kat["mg_convergence"]:
+        n = int(n)
+        o = oracle.MG(n)
+        x = (np.arange(n + 2) - 0.5) / n
+        X, Y = np.meshgrid(x, x, indexing="ij")
+        o.init_zeros()
+        o.init_RHS(-2.0 * ((1.0 - 6.0 * X ** 2) * Y ** 2 * (1.0 - Y ** 2) + (1.0 - 6.0 * Y ** 2) * X ** 2 * (1.0 - X ** 2)))
+        o.solve(rtol=1.e-11)
+        e = o.get_solution() - (X ** 2 - X ** 4) * (Y ** 4 - Y ** 2)
+        assert abs(o.norm(e) - err) <= 1e-5 * err     # table is printed with 6 significant digits
+
+
+def test_ghost_fill_matches_reference_int_and_all_types():
+    z = np.load(__import__("os").path.join(__import__("golden_util").GOLDEN, "mesh_bcs.npz"))
+    for ng in (1, 4):
+        for t in ("outflow", "periodic", "reflect-even", "reflect-odd"):
+            a = z[f"base_ng{ng}"].astype(np.int64).copy()
+            oracle.fill_ghost(a, ng, (t,) * 4)
+            assert np.array_equal(a, z[f"{t}_ng{ng}"])
+            b = z[f"base_ng{ng}"].astype(np.float64).copy()
+            oracle.fill_ghost(b, ng, (t,) * 4)
+            assert np.array_equal(b, z[f"{t}_ng{ng}"].astype(np.float64))

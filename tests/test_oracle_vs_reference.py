@@ -1,0 +1,45 @@
+"""CPU, build container only: the oracle against the LIVE reference imported from /root/reference
+(skipped on the GPU box, where the reference tree does not exist)."""
+import numpy as np
+import pytest
+
+import oracle
+import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+def test_compressible_stages_bit_identical():
+    p = ref_shim.make_sim("compressible", "sedov", {"mesh.nx": 40, "mesh.ny": 32, "sedov.r_init": 0.1,
+                                                    "driver.tmax": 10.0})
+    import pyro.compressible.unsplit_fluxes as flx
+    sim = p.sim
+    g = sim.cc_data.grid
+    for _ in range(3):
+        sim.cc_data.fill_BC_all()
+        sim.compute_timestep()
+        U0 = np.asarray(sim.cc_data.data).copy()
+        raw_dt = sim.dt
+        sim.method_compute_timestep()
+        assert sim.dt == oracle.cfl_dt(U0, g.ng, g.dx, g.dy, 1.4, 0.8)
+        sim.dt = raw_dt
+        hat = [np.asarray(x).copy() for x in flx.interface_states(sim.cc_data, sim.rp, sim.ivars, sim.tc, sim.dt)]
+        Unew, st = oracle.compressible_step(U0, g.ng, g.dx, g.dy, sim.dt, stages=True)
+        for nm, a in zip(["Uxl_hat", "Uxr_hat", "Uyl_hat", "Uyr_hat"], hat):
+            assert np.array_equal(st[nm], a), nm
+        sim.evolve()
+        v = (slice(g.ilo, g.ihi + 1), slice(g.jlo, g.jhi + 1))
+        assert np.abs(Unew[v] - np.asarray(sim.cc_data.data)[v]).max() < 1e-14
+
+
+def test_mg_bit_identical():
+    ref_shim.load()
+    import pyro.multigrid.MG as MG
+    a = MG.CellCenterMG2d(32, 32, xl_BC_type="neumann", xr_BC_type="neumann", yl_BC_type="dirichlet",
+                          yr_BC_type="dirichlet", alpha=0.5, beta=0.02)
+    f = np.cos(3 * a.x2d) * a.y2d
+    a.init_zeros(); a.init_RHS(f); a.solve(rtol=1e-12)
+    o = oracle.MG(32, bc=("neumann", "neumann", "dirichlet", "dirichlet"), alpha=0.5, beta=0.02)
+    o.init_zeros(); o.init_RHS(np.asarray(f)); o.solve(rtol=1e-12)
+    assert o.num_cycles == a.num_cycles
+    assert np.array_equal(o.get_solution(), np.asarray(a.get_solution()))
