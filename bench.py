@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two hot paths on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nx 4096] [--skip-cpu]
+
+Workload (BASELINE.json): compressible Sedov HLLC 4096^2 fp64 -- metric ``cell-updates/s`` -- with
+the multigrid constant-coefficient Poisson 4096^2 V-cycle rate reported beside it in ``"mg"``.
+A "step" is one pass of the driver loop over the whole grid through the public API
+(``Pyro.single_step()``: fill_BC_all -> compute_timestep -> evolve, pyro/pyro_sim.py:241-256).
+
+One JSON line on stdout (rank 0).  ``value``: state resident in HBM.  ``e2e``: the same step with
+the state pushed from pinned host memory before and pulled back after every step.  ``roofline``:
+algorithmic bytes (64 B per cell update) / CUDA-event time of the sweep kernel alone,
+against the measured copy bandwidth in MEASURED_PEAKS.json.  ``cpu_baseline``: the oracle port
+(oracle/pyro_oracle.c, OpenMP) on this box's host cores on a bounded sample.
+
+N > 1 (torchrun, one rank per GPU): the domain is split into x-slabs with a 4-row halo exchanged
+over NCCL each step (weak scaling: every rank owns an nx x ny block).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=4096, help="zones per side (per GPU)")
+    ap.add_argument("--mg-cycles", type=int, default=10)
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-mg", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.lines = []
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle port).  The only places bench.py touches oracle/.
+# --------------------------------------------------------------------------------------------
+def sedov_planes_numpy(n, ng=4, gamma=1.4):
+    import numpy as np
+    q = n + 2 * ng
+    x = (np.arange(q) + 0.5 - ng) / n
+    r2 = (x[:, None] - 0.5) ** 2 + (x[None, :] - 0.5) ** 2
+    P = np.zeros((4, q, q))
+    P[0] = 1.0
+    P[1] = np.where(r2 < 0.01 ** 2 + (1.0 / n) ** 2, 1.0 / (np.pi * 0.01 ** 2), 1.e-5) / (gamma - 1.0)
+    return P
+
+
+def cpu_compressible(n, steps):
+    """oracle port of the compressible step on the host cores: cell-updates/s"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle
+    ng = 4
+    P = sedov_planes_numpy(n)
+    dx = 1.0 / n
+    bc = ("outflow",) * 4
+    prm = oracle.comp_params()
+
+    def step(first):
+        for k in range(4):
+            oracle.fill_ghost(P[k], ng, bc)
+        dt = oracle.lib().orc_cfl_dt(P.ctypes.data, n, n, ng, dx, dx, 1.4, 0.8) * (0.01 if first else 1.0)
+        oracle.compressible_step(P, ng, dx, dx, dt, prm, planes=True)
+    step(True)                     # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(False)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(P).all()
+    return n * n * steps / dt, dt
+
+
+def cpu_mg(n, cycles):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle
+    o = oracle.MG(n)
+    x = (np.arange(n + 2) - 0.5) / n
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    o.init_zeros()
+    o.init_RHS(-2.0 * ((1.0 - 6.0 * X ** 2) * Y ** 2 * (1.0 - Y ** 2) + (1.0 - 6.0 * Y ** 2) * X ** 2 * (1.0 - X ** 2)))
+    o.v_cycle()
+    t0 = time.perf_counter()
+    for _ in range(cycles):
+        o.v_cycle()
+    dt = time.perf_counter() - t0
+    return cycles / dt, dt
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path.  pyro2 is Python and cannot
+    travel to the GPU box, so this is the oracle port (oracle/pyro_oracle.c, bit-identical to the
+    reference per stage, OpenMP over all host threads) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    n = min(args.nx, 2048)
+    steps = max(1, min(args.steps, 2))
+    rate, secs = cpu_compressible(n, steps)
+    line = {
+        "impl": "reference", "metric": "cell-updates/s", "value": rate, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": secs / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"compressible Sedov HLLC {args.nx}^2 fp64 (CPU sample: {n}^2 zones)",
+                   "note": "oracle port of the reference path (pyro2 itself is Python; not present on this box)"},
+        "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": host_threads(), "kind": "port",
+                         "sample": f"{steps} step(s) of the {n}^2 Sedov state after 1 warm-up step"},
+        "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; pyro2_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__
+    __graft_entry__.build()
+    from pyro2_b200 import ops
+    from pyro2_b200.parallel import SlabDecomposition
+    from pyro2_b200.pyro_sim import Pyro
+
+    n = args.nx
+    K, W = args.steps, max(args.warmup, 3)
+    peaks, peak_kind = measured_peaks()
+
+    # ---- the compressible Sedov problem through the public API --------------------------------
+    p = Pyro("compressible")
+    inputs = {"mesh.nx": n * world, "mesh.ny": n, "mesh.xmax": float(world), "driver.max_steps": 10 ** 9,
+              "driver.tmax": 1.e9}
+    slab = SlabDecomposition(rank, world) if world > 1 else None
+    p.initialize_problem("sedov", inputs_dict=inputs, **({"decomposition": slab} if slab else {}))
+    sim = p.sim
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        p.single_step()
+    sim.check_state()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        p.single_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    sim.check_state()
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms)
+    value = n * n * world * K / (ms * 1e-3)
+    launches_per_step = 3 + (2 if world > 1 else 0)     # fill_x, fill_y, sweep (+ halo pack/unpack)
+
+    # ---- the sweep kernel alone (roofline numerator's denominator) ----------------------------
+    g = sim.cc_data.grid
+    prm = sim._comp_params()
+    A, B = sim.cc_data.planes, sim._alt_planes
+    ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = 0.0
+    for _ in range(K):
+        sim.cc_data.fill_BC_all()
+        ks.record()
+        ops.compressible_sweep(A, B, g.nx, g.ny, g.ng, g.dx, g.dy, float(sim.dt), prm, sim._scratch)
+        ke.record()
+        ke.synchronize()
+        kms += ks.elapsed_time(ke)
+        A, B = B, A
+    kms /= K
+    alg_bytes = 64.0 * g.nx * g.ny
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except OSError:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"of {peak_kind}",
+                "kernel": "pyro::sweep_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "the fused sweep is FP64-pipe bound (~1.3 k DP instructions per cell update, DESIGN.md); "
+                        "this is its algorithmic-byte rate against the HBM copy peak"}
+
+    # ---- e2e: host buffers, H2D before and D2H after every step --------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        planes = sim.cc_data.planes
+        host_in = torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True)
+        host_out = torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True)
+        host_in.copy_(planes)
+        nbytes = planes.numel() * 8
+        ke2 = min(K, 5)
+        barrier()
+        e0.record()
+        for _ in range(ke2):
+            sim.cc_data.planes.copy_(host_in, non_blocking=True)
+            sim.cc_data.version += 1          # the state was replaced: forces the stand-alone CFL kernel
+            p.single_step()
+            host_out.copy_(sim.cc_data.planes, non_blocking=True)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ems], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ems = float(tms)
+        e2e = {"value": n * n * world * ke2 / (ems * 1e-3), "unit": "cell-updates/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": ke2,
+               "note": "Pyro.single_step() with the full state copied from/to pinned host memory every step"}
+        del host_in, host_out
+
+    # ---- multigrid V-cycles (single GPU) --------------------------------------------------------
+    mg = None
+    if not args.skip_mg and world == 1:
+        del p, sim, A, B
+        torch.cuda.empty_cache()
+        from pyro2_b200.multigrid import MG
+        a = MG.CellCenterMG2d(n, n)
+        x = a.x2d.t()
+        y = a.y2d.t()
+        a.init_zeros()
+        a.init_RHS(-2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2)))
+        a.max_cycles = 3
+        a.solve(rtol=0.0)                       # warm-up cycles
+        a.max_cycles = args.mg_cycles
+        torch.cuda.synchronize()
+        e0.record()
+        a.solve(rtol=0.0)                       # exactly mg_cycles V-cycles through the public API
+        e1.record()
+        torch.cuda.synchronize()
+        mms = e0.elapsed_time(e1) / a.num_cycles
+        mg_bytes = 776.0 * n * n                # one-pass-per-operator model
+        mg = {"metric": "V-cycles/s", "value": 1e3 / mms, "unit": "V-cycles/s", "ms_per_cycle": mms,
+              "cycles": a.num_cycles, "residual_error": a.residual_error,
+              "config": {"workload": f"multigrid constant-coefficient Poisson {n}^2 fp64, dirichlet, nsmooth 10/50"},
+              "roofline": {"bound": "hbm", "achieved": mg_bytes / (mms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                           "unit": "GB/s", "frac": mg_bytes / (mms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                           "traffic": None, "algorithmic_bytes_per_cycle": mg_bytes}}
+        del a
+
+    # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        ncpu = min(n, 2048)
+        rate, secs = cpu_compressible(ncpu, 2)
+        cpu = {"value": rate, "unit": "cell-updates/s", "cores": host_threads(), "kind": "port",
+               "sample": f"2 steps of the {ncpu}^2 Sedov state after 1 warm-up step ({secs:.1f} s)"}
+        if mg is not None:
+            mrate, msecs = cpu_mg(ncpu, 3)
+            mg["cpu_baseline"] = {"value": mrate, "unit": "V-cycles/s", "cores": host_threads(), "kind": "port",
+                                  "sample": f"3 V-cycles at {ncpu}^2 ({msecs:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"compressible Sedov HLLC {n}^2 fp64 per GPU (limiter 2, flattening, cvisc 0.1, outflow)",
+                       "global_zones": [n * world, n], "parallelism": f"x-slabs x{world}" if world > 1 else "single GPU",
+                       "l2": "state (2 x 539 MB at 4096^2) is larger than L2; no flush needed",
+                       "sweep": ops.sweep_info()},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
+            "roofline": roofline, "cpu_baseline": cpu, "mg": mg,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

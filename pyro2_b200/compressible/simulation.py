@@ -76,7 +76,7 @@ class Simulation(NullSimulation):
         if extra_vars:
             raise NotImplementedError("passively advected extra variables are not in the device sweep")
         rp = self.rp
-        my_grid = grid_setup(rp, ng=ng)
+        my_grid = grid_setup(rp, ng=ng, decomposition=self.decomposition)
         if ng < 4:
             raise ValueError("the compressible sweep needs ng >= 4 (dependency radius, SURVEY.md 9.3)")
         my_data = self.data_class(my_grid)
@@ -111,7 +111,10 @@ class Simulation(NullSimulation):
         my_data.set_aux("gamma", rp.get_param("eos.gamma"))
         my_data.set_aux("grav", rp.get_param("compressible.grav"))
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
+        # artificial viscosity is left unset on the GLOBAL +x face only
+        self._no_avisc_xhi = 1 if (self.decomposition is None or self.decomposition.is_last) else 0
 
         self.ivars = Variables(my_data)
         assert (self.ivars.idens, self.ivars.iener, self.ivars.ixmom, self.ivars.iymom) == (0, 1, 2, 3)
@@ -139,6 +142,10 @@ class Simulation(NullSimulation):
 
     def _read_scratch(self):
         """one D2H copy: wave-speed maxima + status word of the last sweep"""
+        if self.decomposition is not None and self.decomposition.size > 1:
+            # global maxima: the wave speeds are positive doubles, the status word a small integer
+            self.decomposition.allreduce_max_(self._scratch[:2].view(torch.float64))
+            self.decomposition.allreduce_max_(self._scratch[3:4])
         words = self._scratch[:4].cpu()
         if self._pending_status:
             self._pending_status = False
@@ -166,6 +173,10 @@ class Simulation(NullSimulation):
                 self._read_scratch()
             wx, wy = ops.cfl_wavemax(self.cc_data.planes, g.nx, g.ny, g.ng, self.rp.get_param("eos.gamma"),
                                      self._scratch)
+            if self.decomposition is not None and self.decomposition.size > 1:
+                w = self.decomposition.allreduce_max_(torch.tensor([wx, wy], dtype=torch.float64,
+                                                                   device=self.cc_data.planes.device))
+                wx, wy = w.tolist()
         self.dt = cfl * float(min(g.dx / wx, g.dy / wy))
 
     def evolve(self):

@@ -39,8 +39,14 @@ def _default_device():
 class Grid2d:
     """the 2-d grid: index space, coordinates, scratch allocation (patch.py:42-190)"""
 
-    def __init__(self, nx, ny, *, ng=1, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, device=None):
+    def __init__(self, nx, ny, *, ng=1, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, device=None,
+                 nx_global=None, ioffset=0):
+        """nx_global / ioffset (extension): this grid is the x-slab [ioffset, ioffset + nx) of a global
+        grid of nx_global zones spanning [xmin, xmax]; dx and the coordinates are then computed with
+        the global formulas so they are bit-identical to the single-domain grid's."""
         self.nx, self.ny, self.ng = int(nx), int(ny), int(ng)
+        self.nx_global = int(nx_global) if nx_global is not None else self.nx
+        self.ioffset = int(ioffset)
         self.qx = int(2 * ng + nx)
         self.qy = int(2 * ng + ny)
         self.xmin, self.xmax, self.ymin, self.ymax = xmin, xmax, ymin, ymax
@@ -51,9 +57,9 @@ class Grid2d:
         self.device = torch.device(device) if device is not None else _default_device()
 
         # 1-d coordinates stay on the host (problem setups and BC callbacks index them)
-        self.dx = (xmax - xmin) / nx
-        self.xl = (np.arange(self.qx) - ng) * self.dx + xmin
-        self.xr = (np.arange(self.qx) + 1.0 - ng) * self.dx + xmin
+        self.dx = (xmax - xmin) / self.nx_global
+        self.xl = (np.arange(self.qx) + self.ioffset - ng) * self.dx + xmin
+        self.xr = (np.arange(self.qx) + self.ioffset + 1.0 - ng) * self.dx + xmin
         self.x = 0.5 * (self.xl + self.xr)
         self.dy = (ymax - ymin) / ny
         self.yl = (np.arange(self.qy) - ng) * self.dy + ymin
@@ -113,8 +119,10 @@ class Grid2d:
 class Cartesian2d(Grid2d):
     """Cartesian geometry (patch.py:192-239): coord_type 0, constant face lengths / areas / volume"""
 
-    def __init__(self, nx, ny, *, ng=1, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, device=None):
-        super().__init__(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device=device)
+    def __init__(self, nx, ny, *, ng=1, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, device=None,
+                 nx_global=None, ioffset=0):
+        super().__init__(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device=device,
+                         nx_global=nx_global, ioffset=ioffset)
         self.coord_type = 0
 
     def _full(self, name, value):
@@ -154,6 +162,7 @@ class CellCenterData2d:
         self.t = -1.0
         self.initialized = 0
         self.version = 0            # bumped whenever user code may have modified the data
+        self.decomposition = None   # parallel.SlabDecomposition when the grid is one x-slab of many
 
     def register_var(self, name, bc):
         if self.initialized == 1:
@@ -236,6 +245,9 @@ class CellCenterData2d:
         """all variables in one pair of launches (patch.py:575-580)"""
         g = self.grid
         bcs = [self.BCs[name] for name in self.names]
+        if self.decomposition is not None and self.decomposition.size > 1:
+            self._fill_BC_all_slab(bcs)
+            return
         has_values = any(v is not None for b in bcs for v in (b.xl_value, b.xr_value, b.yl_value, b.yr_value))
         has_ext = any(t in bnd.ext_bcs for b in bcs for t in b.names())
         if has_values or has_ext or g.device.type != "cuda":
@@ -243,6 +255,24 @@ class CellCenterData2d:
                 self.fill_BC(name)
             return
         ops.fill_ghost(self.planes, g.nx, g.ny, g.ng, [b.names() for b in bcs])
+
+    def _fill_BC_all_slab(self, bcs):
+        """x-slab of a decomposed domain: neighbour rows first (they are the "x fill" of interior
+        sides), then the physical x sides and the y sides over the full x range -- the same order as
+        the single-domain fill (array_indexer.py:164-274), so corners come out identical."""
+        g = self.grid
+        periodic = bcs[0].xlb == "periodic"
+        self.decomposition.exchange(self.planes, g.nx, g.ng, periodic=periodic)
+        lo_int, hi_int = self.decomposition.interior_sides(periodic)
+        names = []
+        for b in bcs:
+            n = list(b.names())
+            if lo_int:
+                n[0] = None
+            if hi_int:
+                n[1] = None
+            names.append(tuple(n))
+        ops.fill_ghost(self.planes, g.nx, g.ny, g.ng, names)
 
     def fill_BC(self, name):
         """one variable: standard types on the device, then any user-registered callbacks

@@ -1,0 +1,82 @@
+"""Domain decomposition across the GPUs of one box: 1-d slabs along x.
+
+The reference is single-process (pyro/mesh/array_indexer.py:157-158: "there is only a single
+grid"); this is the B200-side extension SURVEY.md 8(e) describes.  x is the slow storage axis, so a
+slab's ghost rows are contiguous in every plane and can be sent / received in place, without
+packing.  One process per GPU (torchrun); the exchange is torch.distributed point-to-point over
+NCCL / NVLink (gloo on CPU tensors for the host-logic tests).
+
+Why 4 rows: the dependency radius of one compressible cell update is exactly ng = 4
+(SURVEY.md 9.3), so one exchange per time step reproduces the single-domain step bit for bit,
+provided the artificial viscosity is applied on inter-slab faces but not on the global +x face
+(SURVEY.md 9.2-13).
+"""
+import torch
+import torch.distributed as dist
+
+
+class SlabDecomposition:
+    """rank r of `size` owns global rows [r * nx_local, (r + 1) * nx_local)"""
+
+    def __init__(self, rank=None, size=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.size = dist.get_world_size(group) if size is None else size
+
+    @property
+    def is_first(self):
+        return self.rank == 0
+
+    @property
+    def is_last(self):
+        return self.rank == self.size - 1
+
+    def local_nx(self, nx_global):
+        if nx_global % self.size:
+            raise ValueError(f"mesh.nx = {nx_global} is not divisible by the {self.size} slabs")
+        return nx_global // self.size
+
+    def ioffset(self, nx_global):
+        return self.rank * self.local_nx(nx_global)
+
+    def neighbours(self, periodic):
+        """(low, high) ranks or None at a physical (non-periodic) boundary"""
+        lo = self.rank - 1 if self.rank > 0 else (self.size - 1 if periodic else None)
+        hi = self.rank + 1 if self.rank < self.size - 1 else (0 if periodic else None)
+        if self.size == 1:
+            lo = hi = None   # single slab: periodic wrap is the ordinary local ghost fill
+        return lo, hi
+
+    def exchange(self, planes, nx, ng, periodic=False):
+        """fill the x ghost rows that face another slab with that slab's boundary rows.
+        planes: (nvar, qx, pitch); rows of a plane are contiguous, so each plane's ng-row block is
+        sent / received in place."""
+        lo, hi = self.neighbours(periodic)
+        ops = []
+        # Posting order matters when both neighbours are the same rank (2 slabs, periodic): messages
+        # between a pair of ranks match in posting order, so every rank posts, per plane,
+        # send(top -> hi), send(bottom -> lo), recv(low ghost <- lo), recv(high ghost <- hi):
+        # the peer's first send (its top rows) then lands in my low ghost rows, as it must.
+        for n in range(planes.shape[0]):
+            p = planes[n]
+            if hi is not None:
+                ops.append(dist.P2POp(dist.isend, p[nx:nx + ng], hi, self.group))            # my top valid rows
+            if lo is not None:
+                ops.append(dist.P2POp(dist.isend, p[ng:2 * ng], lo, self.group))             # my bottom valid rows
+            if lo is not None:
+                ops.append(dist.P2POp(dist.irecv, p[0:ng], lo, self.group))                  # low ghost rows
+            if hi is not None:
+                ops.append(dist.P2POp(dist.irecv, p[ng + nx:ng + nx + ng], hi, self.group))  # high ghost rows
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allreduce_max_(self, t):
+        if self.size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def interior_sides(self, periodic):
+        """(low_is_interior, high_is_interior)"""
+        lo, hi = self.neighbours(periodic)
+        return lo is not None, hi is not None

@@ -42,7 +42,9 @@ class Pyro:
         """register a custom initial-condition function (pyro_sim.py:91-106)"""
         self.custom_problems[name] = (problem_func, problem_params or {})
 
-    def initialize_problem(self, problem_name, *, inputs_file=None, inputs_dict=None):
+    def initialize_problem(self, problem_name, *, inputs_file=None, inputs_dict=None, decomposition=None):
+        """decomposition (extension): a parallel.SlabDecomposition; this process then owns one
+        x-slab of the mesh.nx x mesh.ny domain"""
         if problem_name in self.custom_problems:
             self.problem_name = problem_name
             self.problem_func, self.problem_params = self.custom_problems[problem_name]
@@ -83,6 +85,7 @@ class Pyro:
         self.sim = self.solver.Simulation(self.solver_name, self.problem_name, self.problem_func, self.rp,
                                           problem_finalize_func=self.problem_finalize,
                                           problem_source_func=self.problem_source, timers=self.tc)
+        self.sim.decomposition = decomposition
         self.sim.initialize()
         self.sim.preevolve()
         self.sim.cc_data.t = 0.0

@@ -14,7 +14,8 @@ def _param(rp, key, default):
         return default
 
 
-def grid_setup(rp, ng=1):
+def grid_setup(rp, ng=1, decomposition=None):
+    """decomposition (extension): build only this rank's x-slab of the mesh.nx x mesh.ny grid"""
     nx = rp.get_param("mesh.nx")
     ny = rp.get_param("mesh.ny")
     xmin = _param(rp, "mesh.xmin", 0.0)
@@ -25,6 +26,9 @@ def grid_setup(rp, ng=1):
     if grid_type != "Cartesian2d":
         # SphericalPolar is outside the B200 hot-path scope
         raise ValueError("Unsupported grid type!")
+    if decomposition is not None and decomposition.size > 1:
+        return patch.Cartesian2d(decomposition.local_nx(nx), ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax,
+                                 ng=ng, nx_global=nx, ioffset=decomposition.ioffset(nx))
     return patch.Cartesian2d(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)
 
 
@@ -70,6 +74,7 @@ class NullSimulation:
             self.verbose = 0
         self.n_num_out = 0
         self.cm = "viridis"
+        self.decomposition = None   # set by Pyro.initialize_problem(decomposition=...)
 
     def __str__(self):
         return f"pyro Simulation:\n  solver: {self.solver_name}\n  problem: {self.problem_name}\n"
