@@ -249,8 +249,12 @@ struct SweepTask {
                                       dxinv, dyinv);
             double divU_jp1 = w.down(divU);
 
-            Cons Fy = {0, 0, 0, 0};
-            if (i >= i0) {
+            // The first one / two iterations of a segment run F..M on not-yet-meaningful carried state
+            // (zeros -> NaNs); nothing of it is stored and every carried value is overwritten before
+            // it is used for real.  Keeping the body branch-free lets the scheduler interleave the
+            // independent Riemann problems (F with J, I with L).
+            Cons Fy;
+            {
                 // ---- F. transverse x-flux at face i-1/2; dF_x of cell (i-1) -------------------
                 Flux f = hllc(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp);
                 Cons FxT = {f.dens, f.ener, f.mn, f.mt};
@@ -267,7 +271,7 @@ struct SweepTask {
                 YPp.ymom = YPc.ymom - hdtdx * (FxT.ymom - FxT_prev.ymom);
                 FxT_prev = FxT;
 
-                if (i > i0) {
+                {
                     // ---- I. final y-flux of row i-1 at face j-1/2 (left state from lane-1) ----
                     double ld = w.up(YPp.dens), le = w.up(YPp.ener), lx = w.up(YPp.xmom), ly = w.up(YPp.ymom);
                     Flux g = hllc(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp);
@@ -298,7 +302,7 @@ struct SweepTask {
                 XPp.xmom = XP.xmom - hdtdy * dmx; XPp.ymom = XP.ymom - hdtdy * dmy;
             }
 
-            if (i >= i0) {
+            {
                 // ---- L. final x-flux at face i-1/2 ------------------------------------------
                 Flux f = hllc(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
                               XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp);
@@ -310,7 +314,7 @@ struct SweepTask {
                 Fx.xmom += avx * (U_prev.xmom - Uc.xmom);
                 Fx.ymom += avx * (U_prev.ymom - Uc.ymom);
 
-                if (i > i0) {
+                {
                     // ---- M. conservative update of cell (i-1, j) (simulation.py:377-384) ------
                     double fd = w.down(Fy.dens), fe = w.down(Fy.ener), fx = w.down(Fy.xmom), fy = w.down(Fy.ymom);
                     Cons Un;
@@ -318,7 +322,7 @@ struct SweepTask {
                     Un.ener = U_prev.ener + dtdx * (Fx_prev.ener - Fx.ener) + dtdy * (Fy.ener - fe);
                     Un.xmom = U_prev.xmom + dtdx * (Fx_prev.xmom - Fx.xmom) + dtdy * (Fy.xmom - fx);
                     Un.ymom = U_prev.ymom + dtdx * (Fx_prev.ymom - Fx.ymom) + dtdy * (Fy.ymom - fy);
-                    if (out_lane) {
+                    if (out_lane && i > i0) {
                         double* o = Ocol + (long long)(i - 1) * A.pitch;
                         o[0] = Un.dens; o[A.plane_stride] = Un.ener;
                         o[2 * A.plane_stride] = Un.xmom; o[3 * A.plane_stride] = Un.ymom;

@@ -38,7 +38,23 @@ def _as_tensor(value, like):
     return value
 
 
-class ArrayIndexer(torch.Tensor):
+class DeviceView(torch.Tensor):
+    """what the stencil accessors return: a torch view that, like the numpy views of the reference,
+    accepts numpy arrays / lists on assignment and converts to numpy on request"""
+
+    def __setitem__(self, key, value):
+        torch.Tensor.__setitem__(self.as_subclass(torch.Tensor), key, _as_tensor(value, self))
+
+    def numpy(self):   # pylint: disable=arguments-differ
+        """host copy (device -> host), mostly for tests and output"""
+        return self.as_subclass(torch.Tensor).detach().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class ArrayIndexer(DeviceView):
     """a tensor that knows its grid; ``d`` may be a torch tensor (aliased, not copied) or array-like"""
 
     @staticmethod
@@ -66,17 +82,6 @@ class ArrayIndexer(torch.Tensor):
     def t(self):
         return self.as_subclass(torch.Tensor)
 
-    def __setitem__(self, key, value):
-        torch.Tensor.__setitem__(self.t(), key, _as_tensor(value, self))
-
-    def numpy(self):   # pylint: disable=arguments-differ
-        """host copy (device -> host), mostly for tests and output"""
-        return self.t().detach().cpu().numpy()
-
-    def __array__(self, dtype=None, copy=None):
-        a = self.numpy()
-        return a.astype(dtype) if dtype is not None else a
-
     # ---- stencil views (array_indexer.py:49-90) -------------------------------------------------
     def v(self, buf=0, n=0, s=1):
         return self.ip_jp(0, 0, buf=buf, n=n, s=s)
@@ -94,8 +99,8 @@ class ArrayIndexer(torch.Tensor):
         si = slice(g.ilo - bxlo + ishift, g.ihi + 1 + bxhi + ishift, s)
         sj = slice(g.jlo - bylo + jshift, g.jhi + 1 + byhi + jshift, s)
         if t.dim() == 2:
-            return t[si, sj]
-        return t[si, sj, n]
+            return t[si, sj].as_subclass(DeviceView)
+        return t[si, sj, n].as_subclass(DeviceView)
 
     def lap(self, n=0, buf=0):
         """5-point Laplacian (array_indexer.py:92-96)"""
