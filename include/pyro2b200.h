@@ -115,6 +115,9 @@ typedef struct p2b_mg p2b_mg;
 p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
                       double ymin, double ymax, int nsmooth, int nsmooth_bottom);   /* MG.py:85-295 */
 int p2b_mg_destroy(p2b_mg* m);
+/* A/B switch (default on): temporally blocked smoother (5 red-black iterations per HBM pass) vs one
+ * launch per colour; both produce identical bits */
+int p2b_mg_set_blocking(p2b_mg* m, int enable);
 int p2b_mg_nlevels(p2b_mg* m);
 long long p2b_mg_workspace_bytes(p2b_mg* m);
 int p2b_mg_bind(p2b_mg* m, void* device_mem, long long bytes);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "p2b_mg_create": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i]),
     "p2b_mg_destroy": (_i, [_vp]),
+    "p2b_mg_set_blocking": (_i, [_vp, _i]),
     "p2b_mg_nlevels": (_i, [_vp]),
     "p2b_mg_workspace_bytes": (_ll, [_vp]),
     "p2b_mg_bind": (_i, [_vp, _vp, _ll]),

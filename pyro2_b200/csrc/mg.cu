@@ -16,6 +16,8 @@
 //
 // Ghost cells (ng = 1) are kept consistent by the thread that updates the interior source cell of
 // each ghost ("fused fill_BC"), so a half-sweep is one launch.
+#include <type_traits>
+
 #include "common.cuh"
 #include "hydro_core.cuh"
 
@@ -24,6 +26,7 @@ namespace pyro {
 struct MgLevel {
     int n, pitch;
     double *v, *f, *r;
+    double *w;          // scratch plane: ping-pong target of the temporally blocked smoother
     double dx, dy;
 };
 
@@ -47,6 +50,7 @@ struct p2b_mg {
     double* base;
     double* partials;                         // MG_NPART doubles x 2
     const double *xlv, *xrv, *ylv, *yrv;
+    int no_blocking;                          // debugging / A-B switch: 1 = plain half-sweep kernels
 };
 
 namespace pyro {
@@ -96,7 +100,19 @@ __device__ __forceinline__ void store_with_ghosts(double* v, int n, int pitch, i
             v[(long long)rows[k] * pitch + n + 1] = ghost_hi(rv[k], b.yr, b.yrv, rows[k], dy);
 }
 
-struct SmoothCoef { double alpha, xc, yc, denom; };
+// rden = RN(1/denom), fast = 1 when q = RN(a*rden); r = fma(-denom, q, a); RN(q + r*rden) is the
+// correctly rounded a/denom (Markstein's theorem: holds unless denom's significand is all ones) --
+// three DP instructions and no branch instead of the ~10 + slow path of a true division, with the
+// SAME bits as the reference's division.
+struct SmoothCoef { double alpha, xc, yc, denom, rden; int fast; };
+
+__device__ __forceinline__ double div_by_denom(double a, const SmoothCoef& c)
+{
+    if (!c.fast) return exact_div(a, c.denom);
+    double q = exact_mul(a, c.rden);
+    double r = __fma_rn(-c.denom, q, a);
+    return __fma_rn(r, c.rden, q);
+}
 
 __device__ __forceinline__ double gs_update(const double* v, const double* f, int pitch, int i, int j,
                                             const SmoothCoef& c)
@@ -106,7 +122,7 @@ __device__ __forceinline__ double gs_update(const double* v, const double* f, in
     double sx = exact_add(v[k + pitch], v[k - pitch]);
     double sy = exact_add(v[k + 1], v[k - 1]);
     double num = exact_add(exact_add(f[k], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
-    return exact_div(num, c.denom);
+    return div_by_denom(num, c);
 }
 
 // one colour of one red-black iteration; colour 0 = (i+j) even = the reference's groups (0,0),(1,1)
@@ -136,6 +152,163 @@ __global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmo
         }
         __syncthreads();
     }
+}
+
+
+// ---- temporally blocked smoother -------------------------------------------------------------------
+// One CTA owns a TI x TJ tile and loads it with a halo of H = 2*TB_K cells into REGISTERS: a thread
+// holds a 2-column x TB_R-row patch of v and f (lane t <-> columns 2t, 2t+1 of the 64-column
+// region; warp w <-> rows w*TB_R ...).  It then runs up to TB_K full red-black iterations without
+// touching global memory: x-neighbours (rows) come from the thread's own registers or, across
+// warps, from a small double-buffered shared row exchange; y-neighbours from the pair partner or
+// the adjacent lane (shuffle).  Halo cells are updated redundantly; the error of not knowing what is
+// outside the region advances one cell per half-sweep and never reaches the tile.  Ghost cells are
+// not stored at all while blocking: at a domain edge the neighbour is computed from the cell's own
+// value with the same formula fill_BC uses (ghost = g(inner)), which is exactly the value the
+// reference's fill_BC-after-every-colour keeps there; periodic sides wrap on load.  Every point update
+// executes the reference's operations in the reference's order, so the result is bit-identical to
+// nsmooth separate half-sweeps; HBM traffic per pass is ~42 B per cell for 5 iterations instead of
+// 5 x 48 B.  Reads vin, writes vout (another plane): neighbouring CTAs read each other's tiles.
+constexpr int TB_K = 5;                 // iterations per pass
+constexpr int TB_H = 2 * TB_K;          // halo
+constexpr int TB_R = 8;                 // rows per thread
+constexpr int TB_NW = 8;                // warps per CTA
+constexpr int TB_RH = TB_R * TB_NW;     // region rows  (64)
+constexpr int TB_RW = 64;               // region columns
+constexpr int TB_TI = TB_RH - 2 * TB_H; // tile rows    (44)
+constexpr int TB_TJ = TB_RW - 2 * TB_H; // tile columns (44)
+static_assert(TB_TI % 2 == 0 && TB_TJ % 2 == 0 && TB_R % 2 == 0, "parity bookkeeping needs even tile sizes");
+
+__device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [1, n]
+{
+    int k = (i - 1) % n;
+    return (k < 0 ? k + n : k) + 1;
+}
+
+// EDGE = false: the whole 64 x 64 region lies strictly inside the domain (the case for all but the
+// outermost ring of CTAs): no wrap, no ghost logic, no per-cell predicates.  EDGE = true: the general
+// path.  The choice is block-uniform, so a CTA executes exactly one of the two instruction streams.
+template <bool EDGE>
+__device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
+                                               double* __restrict__ vout, const MgBC& b, const SmoothCoef& c,
+                                               int niter, double (*edge)[TB_NW][2][TB_RW])
+{
+    const int n = L.n, P = L.pitch;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd)
+    const int gj0 = J0 - TB_H + 2 * lane;          // first of its two columns (odd)
+    const bool xper = EDGE && (b.xl == P2B_BC_PERIODIC), yper = EDGE && (b.yl == P2B_BC_PERIODIC);
+
+    double v[TB_R][2], f[TB_R][2];
+    // EDGE only: bit r*2+a set = (r, a) is a real interior cell; per-row / per-column edge flags
+    unsigned inmask = 0xffffffffu;
+    unsigned row_lo = 0, row_hi = 0;               // bit r: global row is 1 / n (non-periodic x)
+    bool col_lo[2] = {false, false}, col_hi[2] = {false, false};
+#pragma unroll
+    for (int r = 0; r < TB_R; ++r) {
+        int gi = gi0 + r;
+        int si = xper ? wrap1(gi, n) : gi;
+        if (EDGE && !xper) { if (gi == 1) row_lo |= 1u << r; if (gi == n) row_hi |= 1u << r; }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int gj = gj0 + a;
+            int sj = yper ? wrap1(gj, n) : gj;
+            bool ok = !EDGE || (si >= 1 && si <= n && sj >= 1 && sj <= n);
+            if (!ok) inmask &= ~(1u << (2 * r + a));
+            long long k = (long long)si * P + sj;
+            v[r][a] = ok ? vin[k] : 0.0;
+            f[r][a] = ok ? L.f[k] : 0.0;
+        }
+    }
+    if (EDGE && !yper) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { col_lo[a] = (gj0 + a == 1); col_hi[a] = (gj0 + a == n); }
+    }
+
+    double uph[2] = {0.0, 0.0}, dnh[2] = {0.0, 0.0};   // rows just above / below this thread's strip
+    auto publish = [&](int buf) {
+        *reinterpret_cast<double2*>(&edge[buf][w][0][2 * lane]) = make_double2(v[0][0], v[0][1]);
+        *reinterpret_cast<double2*>(&edge[buf][w][1][2 * lane]) = make_double2(v[TB_R - 1][0], v[TB_R - 1][1]);
+        __syncthreads();
+        if (w > 0) {
+            double2 t = *reinterpret_cast<const double2*>(&edge[buf][w - 1][1][2 * lane]);
+            uph[0] = t.x; uph[1] = t.y;
+        }
+        if (w < TB_NW - 1) {
+            double2 t = *reinterpret_cast<const double2*>(&edge[buf][w + 1][0][2 * lane]);
+            dnh[0] = t.x; dnh[1] = t.y;
+        }
+    };
+    publish(0);
+
+    // one colour of one iteration; the colour is a compile-time constant so that every register
+    // array index is static.  colour 0 = (i + j) even; gi0 and gj0 are both odd (tile origins are
+    // 1 + even multiples, H even, strip offsets even), so cell (r, a) has colour (r + a) & 1.
+    auto half_sweep = [&](auto colour_tag, int buf) {
+        constexpr int colour = decltype(colour_tag)::value;
+        double nv[TB_R];
+#pragma unroll
+        for (int r = 0; r < TB_R; ++r) {
+            constexpr int dummy = 0; (void)dummy;
+            const int a = (r + colour) & 1;          // active column of the pair in this row (static)
+            const double self = v[r][a];
+            double up = (r == 0) ? uph[a] : v[r == 0 ? 0 : r - 1][a];
+            double dn = (r == TB_R - 1) ? dnh[a] : v[r == TB_R - 1 ? r : r + 1][a];
+            // y-neighbours: the pair partner, or the adjacent lane's facing column
+            double lf = (a == 0) ? __shfl_up_sync(0xffffffffu, v[r][1], 1) : v[r][0];
+            double rt = (a == 0) ? v[r][1] : __shfl_down_sync(0xffffffffu, v[r][0], 1);
+            if (EDGE) {
+                // domain edges: the ghost value fill_BC would hold, from the cell's own current value
+                const int gi = gi0 + r, gj = gj0 + a;
+                if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
+                if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
+                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, gi, L.dy);
+                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, gi, L.dy);
+            }
+            double sx = exact_add(dn, up);
+            double sy = exact_add(rt, lf);
+            double num = exact_add(exact_add(f[r][a], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+            nv[r] = div_by_denom(num, c);
+        }
+#pragma unroll
+        for (int r = 0; r < TB_R; ++r) {
+            const int a = (r + colour) & 1;
+            if (!EDGE || ((inmask >> (2 * r + a)) & 1u)) v[r][a] = nv[r];
+        }
+        publish(buf);
+    };
+
+    for (int it = 0; it < niter; ++it) {
+        half_sweep(std::integral_constant<int, 0>{}, 1);
+        half_sweep(std::integral_constant<int, 1>{}, 0);
+    }
+
+    // store the tile (and, on the EDGE path, the ghost cells its boundary cells generate)
+#pragma unroll
+    for (int r = 0; r < TB_R; ++r) {
+        int gi = gi0 + r;
+        if (gi < I0 || gi >= I0 + TB_TI || gi > n) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int gj = gj0 + a;
+            if (gj < J0 || gj >= J0 + TB_TJ || gj > n) continue;
+            if (EDGE) store_with_ghosts(vout, n, P, gi, gj, v[r][a], b, L.dx, L.dy);
+            else vout[(long long)gi * P + gj] = v[r][a];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * TB_NW, 2)
+mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
+                    SmoothCoef c, int niter)
+{
+    __shared__ __align__(16) double edge[2][TB_NW][2][TB_RW];   // [buffer][warp][first/last row][column]
+    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + TB_RH - 1 <= L.n) &&
+                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
+    if (interior) smooth_tb_body<false>(L, vin, vout, b, c, niter, edge);
+    else smooth_tb_body<true>(L, vin, vout, b, c, niter, edge);
 }
 
 // full ghost fill of v from the interior (used once per smooth() like MG.py:565)
@@ -279,22 +452,46 @@ static SmoothCoef level_coef(const p2b_mg* m, const MgLevel& L)
     c.xc = m->beta / (L.dx * L.dx);
     c.yc = m->beta / (L.dy * L.dy);
     c.denom = m->alpha + 2.0 * c.xc + 2.0 * c.yc;
+    c.rden = 1.0 / c.denom;
+    unsigned long long bits;
+    memcpy(&bits, &c.denom, 8);
+    const unsigned long long mant = bits & 0xFFFFFFFFFFFFFULL;
+    c.fast = (mant != 0xFFFFFFFFFFFFFULL) && isfinite(c.rden) && c.denom != 0.0 &&
+             fabs(c.denom) > 1e-290 && fabs(c.denom) < 1e290;
     return c;
 }
 
-constexpr int MG_SMALL_N = 32;   // levels up to 32^2 are smoothed by one CTA in one launch
+constexpr int MG_SMALL_N = 64;   // levels up to 64^2 are smoothed by one CTA in one launch
+constexpr int MG_TB_MIN_N = 128;  // from here up the temporally blocked kernel is used
 
 static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaStream_t st)
 {
     const MgLevel& L = m->lev[level];
     MgBC b = level_bc(m, level);
     SmoothCoef c = level_coef(m, L);
-    if (fill_first) mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, st>>>(L, b);
     if (L.n <= MG_SMALL_N) {
+        if (fill_first) mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, st>>>(L, b);
         int threads = L.n * (L.n / 2);
-        threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
+        threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
         mg_smooth_small_kernel<<<1, threads, 0, st>>>(L, b, c, nsmooth);
+    } else if (L.n >= MG_TB_MIN_N && !m->no_blocking) {
+        // passes of up to TB_K iterations, ping-ponging v <-> w; the blocked kernel derives ghost
+        // values from interior cells itself, so no separate fill_BC is needed before it
+        dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.n + TB_TI - 1) / TB_TI);
+        const double* src = L.v;
+        double* dst = L.w;
+        int left = nsmooth;
+        if (left == 0 && fill_first) mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, st>>>(L, b);
+        while (left > 0) {
+            int it = left < TB_K ? left : TB_K;
+            mg_smooth_tb_kernel<<<grd, 32 * TB_NW, 0, st>>>(L, src, dst, b, c, it);
+            left -= it;
+            const double* t = src; src = dst; dst = const_cast<double*>(t);
+        }
+        if (src != L.v)   // odd number of passes: the result sits in w
+            cudaMemcpyAsync(L.v, L.w, (size_t)(L.n + 2) * L.pitch * sizeof(double), cudaMemcpyDeviceToDevice, st);
     } else {
+        if (fill_first) mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, st>>>(L, b);
         dim3 blk(64, 4);
         dim3 grd((L.n / 2 + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
         for (int it = 0; it < nsmooth; ++it) {
@@ -390,6 +587,7 @@ p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double x
         L.v = (double*)off; off += plane;
         L.f = (double*)off; off += plane;
         L.r = (double*)off; off += plane;
+        L.w = (double*)off; off += plane;
     }
     m->partials = (double*)off; off += 2 * MG_NPART;
     m->bytes = off * 8;
@@ -397,6 +595,7 @@ p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double x
 }
 
 int p2b_mg_destroy(p2b_mg* m) { delete m; return P2B_OK; }
+int p2b_mg_set_blocking(p2b_mg* m, int enable) { if (!m) return P2B_EINVAL; m->no_blocking = !enable; return P2B_OK; }
 int p2b_mg_nlevels(p2b_mg* m) { return m ? m->nlevels : 0; }
 long long p2b_mg_workspace_bytes(p2b_mg* m) { return m ? m->bytes : 0; }
 
@@ -412,6 +611,7 @@ int p2b_mg_bind(p2b_mg* m, void* mem, long long bytes)
         m->lev[l].v = m->base + (long long)m->lev[l].v;
         m->lev[l].f = m->base + (long long)m->lev[l].f;
         m->lev[l].r = m->base + (long long)m->lev[l].r;
+        m->lev[l].w = m->base + (long long)m->lev[l].w;
     }
     m->partials = m->base + (long long)m->partials;
     return P2B_OK;

@@ -55,6 +55,9 @@ class MGHandle:
         self._bc_vals = vals   # keep alive
         _lib.check(_lib.lib().p2b_mg_set_bc_values(self._h, *[None if v is None else v.data_ptr() for v in vals]))
 
+    def set_blocking(self, enable):
+        _lib.check(_lib.lib().p2b_mg_set_blocking(self._h, int(bool(enable))))
+
     def _s(self):
         return _lib.stream_ptr()
 
