@@ -53,7 +53,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from the warm-up through the timed region;
+    the median is taken over samples drawing > 300 W (i.e. under load)"""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -66,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -87,9 +88,13 @@ class ClockSampler:
             if len(p) < 7:
                 continue
             try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
+                clk, cmax, power = float(p[0]), float(p[1]), float(p[2])
             except ValueError:
                 continue
+            mx.append(cmax)
+            if power < 300.0:
+                continue          # idle sample (before / after the loop)
+            sm.append(clk)
             for nm, val in zip(names, p[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
@@ -220,13 +225,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        p.single_step()
-    sim.check_state()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        p.single_step()
+    sim.check_state()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -242,7 +246,7 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms)
     value = n * n * world * K / (ms * 1e-3)
-    launches_per_step = 3 + (2 if world > 1 else 0)     # fill_x, fill_y, sweep (+ halo pack/unpack)
+    launches_per_step = 3     # fill_x_kernel, fill_y_kernel, sweep_kernel (the halo exchange is NCCL's)
 
     # ---- the sweep kernel alone (roofline numerator's denominator) ----------------------------
     g = sim.cc_data.grid

@@ -87,17 +87,22 @@ __device__ __forceinline__ void store_with_ghosts(double* v, int n, int pitch, i
     const int sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : n;    // source row of ghost row n+1
     const int syl = (b.yl == P2B_BC_PERIODIC) ? n : 1;
     const int syh = (b.yr == P2B_BC_PERIODIC) ? 1 : n;
-    // the up-to-three rows this value lives in after the x fill: (row index, value)
-    int rows[3]; double rv[3]; int nr = 0;
-    rows[nr] = i; rv[nr] = val; ++nr;
-    if (i == sxl) { rows[nr] = 0; rv[nr] = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = rv[nr]; ++nr; }
-    if (i == sxh) { rows[nr] = n + 1; rv[nr] = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(n + 1) * pitch + j] = rv[nr]; ++nr; }
-    if (j == syl)
-        for (int k = 0; k < nr; ++k)
-            v[(long long)rows[k] * pitch] = ghost_lo(rv[k], b.yl, b.ylv, rows[k], dy);
-    if (j == syh)
-        for (int k = 0; k < nr; ++k)
-            v[(long long)rows[k] * pitch + n + 1] = ghost_hi(rv[k], b.yr, b.yrv, rows[k], dy);
+    const bool lo = (i == sxl), hi = (i == sxh);
+    if (!(lo || hi || j == syl || j == syh)) return;       // interior cell: nothing else to write
+    // after the x fill this value lives in up to three rows: i, 0 (if lo), n+1 (if hi)
+    double glo = 0.0, ghi = 0.0;
+    if (lo) { glo = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = glo; }
+    if (hi) { ghi = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(n + 1) * pitch + j] = ghi; }
+    if (j == syl) {
+        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, i, dy);
+        if (lo) v[0] = ghost_lo(glo, b.yl, b.ylv, 0, dy);
+        if (hi) v[(long long)(n + 1) * pitch] = ghost_lo(ghi, b.yl, b.ylv, n + 1, dy);
+    }
+    if (j == syh) {
+        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, i, dy);
+        if (lo) v[n + 1] = ghost_hi(glo, b.yr, b.yrv, 0, dy);
+        if (hi) v[(long long)(n + 1) * pitch + n + 1] = ghost_hi(ghi, b.yr, b.yrv, n + 1, dy);
+    }
 }
 
 // rden = RN(1/denom), fast = 1 when q = RN(a*rden); r = fma(-denom, q, a); RN(q + r*rden) is the
@@ -105,6 +110,26 @@ __device__ __forceinline__ void store_with_ghosts(double* v, int n, int pitch, i
 // three DP instructions and no branch instead of the ~10 + slow path of a true division, with the
 // SAME bits as the reference's division.
 struct SmoothCoef { double alpha, xc, yc, denom, rden; int fast; };
+struct DivConst { double d, rd; int fast; };     // exact a / d for a loop-invariant d (same trick)
+
+__device__ __forceinline__ double div_const(double a, const DivConst& k)
+{
+    if (!k.fast) return exact_div(a, k.d);
+    double q = exact_mul(a, k.rd);
+    double r = __fma_rn(-k.d, q, a);
+    return __fma_rn(r, k.rd, q);
+}
+
+static DivConst make_div_const(double d)
+{
+    DivConst k;
+    k.d = d; k.rd = 1.0 / d;
+    unsigned long long bits;
+    memcpy(&bits, &d, 8);
+    k.fast = ((bits & 0xFFFFFFFFFFFFFULL) != 0xFFFFFFFFFFFFFULL) && isfinite(k.rd) && d != 0.0 &&
+             fabs(d) > 1e-290 && fabs(d) < 1e290;
+    return k;
+}
 
 __device__ __forceinline__ double div_by_denom(double a, const SmoothCoef& c)
 {
@@ -311,6 +336,146 @@ mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restric
     else smooth_tb_body<true>(L, vin, vout, b, c, niter, edge);
 }
 
+
+struct ResidCoef { double alpha, beta; DivConst dx2, dy2; };
+
+__device__ __forceinline__ double residual_at(const MgLevel& L, long long k, const ResidCoef& rc)
+{
+    // MG.py:540-542:  f - alpha v + beta ((v[i-1] + v[i+1] - 2 v)/dx**2 + (v[j-1] + v[j+1] - 2 v)/dy**2)
+    const double* v = L.v;
+    double v2 = exact_mul(2.0, v[k]);
+    double lx = div_const(exact_sub(exact_add(v[k - L.pitch], v[k + L.pitch]), v2), rc.dx2);
+    double ly = div_const(exact_sub(exact_add(v[k - 1], v[k + 1]), v2), rc.dy2);
+    return exact_add(exact_sub(L.f[k], exact_mul(rc.alpha, v[k])), exact_mul(rc.beta, exact_add(lx, ly)));
+}
+
+// ---- the coarse part of the V-cycle in ONE launch ---------------------------------------------------
+// Levels up to 64^2 do not have enough points to fill the chip and every kernel on them is pure
+// launch + memory latency (ncu r1: 26 us per smooth(), ~0.35 ms per V-cycle in total).  One CTA
+// keeps v, f, r of all levels 0..top (<= 64^2: 140 KB) in shared memory and runs the whole
+// sub-V-cycle there: smooth / residual / restrict on the way down, the bottom solve, prolong +
+// correct + smooth on the way up -- same device functions, same operation order, same bits.
+constexpr int MG_COARSE_TOP_N = 64;
+constexpr int MG_COARSE_LEVELS = 6;     // 2, 4, 8, 16, 32, 64
+
+struct CoarseTable {
+    MgLevel g[MG_COARSE_LEVELS];        // the levels' global planes
+    int top;                            // highest level handled here
+    int nsmooth, nsmooth_bottom;
+    ResidCoef rcoef[MG_COARSE_LEVELS];
+    SmoothCoef coef[MG_COARSE_LEVELS];
+    MgBC bc_top, bc_coarse;             // bc_top carries the inhomogeneous values when top is the finest
+};
+
+__device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, const SmoothCoef& c, int nsmooth)
+{
+    const int n = L.n, half = n >> 1, npts = n * half;
+    // fill_BC("v") at the start of smooth() (MG.py:565)
+    for (int t = threadIdx.x; t < 4 * n; t += blockDim.x) {
+        int side = t / n, q = t % n + 1;
+        int i = side == 0 ? 1 : side == 1 ? n : q;
+        int j = side == 2 ? 1 : side == 3 ? n : q;
+        store_with_ghosts(L.v, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+    }
+    __syncthreads();
+    for (int it = 0; it < 2 * nsmooth; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int i = t / half + 1, k = t % half;
+            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+            double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            store_with_ghosts(L.v, n, L.pitch, i, j, val, b, L.dx, L.dy);
+        }
+        __syncthreads();
+    }
+}
+
+
+__global__ void __launch_bounds__(1024, 1) mg_coarse_vcycle_kernel(CoarseTable T)
+{
+    extern __shared__ __align__(16) double sm[];
+    MgLevel S[MG_COARSE_LEVELS];
+    {
+        double* p = sm;
+        for (int l = 0; l <= T.top; ++l) {
+            S[l] = T.g[l];
+            const int q = S[l].n + 2;
+            S[l].pitch = (q + 1) & ~1;
+            const long long plane = (long long)q * S[l].pitch;
+            S[l].v = p; p += plane;
+            S[l].f = p; p += plane;
+            S[l].r = p; p += plane;
+        }
+    }
+    // load: v and f of the top level come from global (v is the current iterate there: zero on a
+    // coarse top level, the solution when the top level is the finest); everything below starts at 0
+    for (int l = 0; l <= T.top; ++l) {
+        const int q = S[l].n + 2;
+        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
+            int i = t / q, j = t % q;
+            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
+            S[l].v[ks] = (l == T.top) ? T.g[l].v[kg] : 0.0;
+            S[l].f[ks] = (l == T.top) ? T.g[l].f[kg] : 0.0;
+            S[l].r[ks] = T.g[l].r[kg];
+        }
+    }
+    __syncthreads();
+
+    for (int l = T.top; l >= 1; --l) {
+        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
+        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+        const int n = S[l].n;
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+            long long k = (long long)(t / n + 1) * S[l].pitch + (t % n + 1);
+            S[l].r[k] = residual_at(S[l], k, T.rcoef[l]);
+        }
+        __syncthreads();
+        const int nc = S[l - 1].n;
+        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
+            int ic = t / nc + 1, jc = t % nc + 1;
+            const double* r = S[l].r;
+            long long k = (long long)(2 * ic - 1) * S[l].pitch + (2 * jc - 1);
+            double sum = exact_add(exact_add(exact_add(r[k], r[k + S[l].pitch]), r[k + 1]), r[k + S[l].pitch + 1]);
+            S[l - 1].f[(long long)ic * S[l - 1].pitch + jc] = exact_mul(0.25, sum);
+        }
+        __syncthreads();
+    }
+    cta_smooth(S[0], (T.top == 0) ? T.bc_top : T.bc_coarse, T.coef[0], T.nsmooth_bottom);
+    for (int l = 1; l <= T.top; ++l) {
+        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
+        const MgLevel &F = S[l], &Cs = S[l - 1];
+        const int nc = Cs.n;
+        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
+            int ic = t / nc + 1, jc = t % nc + 1;
+            const double* c = Cs.v;
+            const long long kc = (long long)ic * Cs.pitch + jc;
+            double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
+            double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+            double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my), c0 = c[kc];
+            const int i = 2 * ic - 1, j = 2 * jc - 1, P = F.pitch;
+            double* v = F.v;
+            store_with_ghosts(v, F.n, P, i, j, exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+        }
+        __syncthreads();
+        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+    }
+
+    // store everything back (coarse planes stay observable through grids[level], like the reference's)
+    for (int l = 0; l <= T.top; ++l) {
+        const int q = S[l].n + 2;
+        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
+            int i = t / q, j = t % q;
+            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
+            T.g[l].v[kg] = S[l].v[ks];
+            T.g[l].f[kg] = S[l].f[ks];
+            T.g[l].r[kg] = S[l].r[ks];
+        }
+    }
+}
+
 // full ghost fill of v from the interior (used once per smooth() like MG.py:565)
 __global__ void mg_fill_kernel(MgLevel L, MgBC b)
 {
@@ -326,18 +491,13 @@ __global__ void mg_fill_kernel(MgLevel L, MgBC b)
     }
 }
 
-__global__ void mg_residual_kernel(MgLevel L, double alpha, double beta)
+__global__ void mg_residual_kernel(MgLevel L, ResidCoef rc)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
     if (i > L.n || j > L.n) return;
     const long long k = (long long)i * L.pitch + j;
-    const double* v = L.v;
-    // MG.py:540-542
-    double v2 = exact_mul(2.0, v[k]);
-    double lx = exact_div(exact_sub(exact_add(v[k - L.pitch], v[k + L.pitch]), v2), exact_mul(L.dx, L.dx));
-    double ly = exact_div(exact_sub(exact_add(v[k - 1], v[k + 1]), v2), exact_mul(L.dy, L.dy));
-    L.r[k] = exact_add(exact_sub(L.f[k], exact_mul(alpha, v[k])), exact_mul(beta, exact_add(lx, ly)));
+    L.r[k] = residual_at(L, k, rc);
 }
 
 // fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732)
@@ -430,6 +590,50 @@ __global__ void mg_zero_kernel(MgZeroTable t)
             t.v[l][k] = 0.0;
 }
 
+// solve()'s per-cycle bookkeeping in one pass over the finest level (MG.py:668-686): relative change
+// against old_phi (old_phi <- v), residual r (stored), partial sums of both squares.  Same fixed
+// two-stage summation as mg_sumsq_*; part[0..nb) relative change, part[MG_NPART..) residual.
+__global__ void mg_diag_partial_kernel(MgLevel L, double* old_phi, ResidCoef rc, double* part)
+{
+    double s_rel = 0.0, s_res = 0.0;
+    const int n = L.n;
+    // block b owns rows b, b + gridDim.x, ...; threads stride along the contiguous axis
+    for (int i = 1 + blockIdx.x; i <= n; i += gridDim.x) {
+        for (int j = 1 + threadIdx.x; j <= n; j += blockDim.x) {
+            long long k = (long long)i * L.pitch + j;
+            double x = L.v[k], o = old_phi[k];
+            old_phi[k] = x;
+            double d = (x - o) / (x + 1.e-16);
+            s_rel += d * d;
+            double r = residual_at(L, k, rc);
+            L.r[k] = r;
+            s_res += r * r;
+        }
+    }
+    __shared__ double sh[2][256];
+    sh[0][threadIdx.x] = s_rel; sh[1][threadIdx.x] = s_res;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[blockIdx.x] = sh[0][0]; part[MG_NPART + blockIdx.x] = sh[1][0]; }
+}
+
+__global__ void mg_diag_final_kernel(const double* part, int npart, double* out)
+{
+    __shared__ double sh[2][256];
+    double a = 0.0, b = 0.0;
+    for (int t = threadIdx.x; t < npart; t += 256) { a += part[t]; b += part[MG_NPART + t]; }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; }
+}
+
 static MgBC level_bc(const p2b_mg* m, int level)
 {
     MgBC b;
@@ -443,6 +647,15 @@ static MgBC level_bc(const p2b_mg* m, int level)
     b.ylv = (fin && ok(b.yl)) ? m->ylv : nullptr;
     b.yrv = (fin && ok(b.yr)) ? m->yrv : nullptr;
     return b;
+}
+
+static ResidCoef level_rcoef(const p2b_mg* m, const MgLevel& L)
+{
+    ResidCoef rc;
+    rc.alpha = m->alpha; rc.beta = m->beta;
+    rc.dx2 = make_div_const(L.dx * L.dx);
+    rc.dy2 = make_div_const(L.dy * L.dy);
+    return rc;
 }
 
 static SmoothCoef level_coef(const p2b_mg* m, const MgLevel& L)
@@ -507,7 +720,7 @@ static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
     const MgLevel& L = m->lev[level];
     dim3 blk(64, 4);
     dim3 grd((L.n + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
-    mg_residual_kernel<<<grd, blk, 0, st>>>(L, m->alpha, m->beta);
+    mg_residual_kernel<<<grd, blk, 0, st>>>(L, level_rcoef(m, L));
 }
 
 static void restrict_impl(p2b_mg* m, int level, cudaStream_t st)
@@ -526,9 +739,45 @@ static void prolong_impl(p2b_mg* m, int level, cudaStream_t st)
     mg_prolong_kernel<<<grd, blk, 0, st>>>(F, Cs, level_bc(m, level));
 }
 
+static int coarse_top(const p2b_mg* m)
+{
+    int top = -1;
+    for (int l = 0; l < m->nlevels && l < MG_COARSE_LEVELS; ++l)
+        if (m->lev[l].n <= MG_COARSE_TOP_N) top = l;
+    return top;
+}
+
+static void coarse_vcycle_impl(p2b_mg* m, int top, cudaStream_t st)
+{
+    CoarseTable T;
+    memset(&T, 0, sizeof T);
+    size_t bytes = 0;
+    for (int l = 0; l <= top; ++l) {
+        T.g[l] = m->lev[l];
+        T.coef[l] = level_coef(m, m->lev[l]);
+        int q = m->lev[l].n + 2;
+        bytes += 3 * (size_t)q * ((q + 1) & ~1) * sizeof(double);
+    }
+    T.top = top;
+    T.nsmooth = m->nsmooth; T.nsmooth_bottom = m->nsmooth_bottom;
+    for (int l = 0; l <= top; ++l) T.rcoef[l] = level_rcoef(m, m->lev[l]);
+    T.bc_top = level_bc(m, top);
+    T.bc_coarse = level_bc(m, top == m->nlevels - 1 ? -1 : 0);   // homogeneous
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(mg_coarse_vcycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    mg_coarse_vcycle_kernel<<<1, 1024, bytes, st>>>(T);
+}
+
 static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     // MG.py:699-778
+    if (!m->no_blocking && level <= coarse_top(m)) {
+        coarse_vcycle_impl(m, level, st);
+        return;
+    }
     if (level > 0) {
         smooth_impl(m, level, m->nsmooth, true, st);
         residual_impl(m, level, st);
@@ -728,9 +977,10 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stre
     P2B_REQUIRE(m && m->base && old_phi && out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int lf = m->nlevels - 1;
-    sumsq_impl(m, m->lev[lf].v, old_phi, lf, 1, out, st);
-    residual_impl(m, lf, st);
-    sumsq_impl(m, m->lev[lf].r, nullptr, lf, 0, out + 1, st);
+    const MgLevel& L = m->lev[lf];
+    int blocks = L.n < MG_NPART ? L.n : MG_NPART;
+    mg_diag_partial_kernel<<<blocks, 256, 0, st>>>(L, old_phi, level_rcoef(m, L), m->partials);
+    mg_diag_final_kernel<<<1, 256, 0, st>>>(m->partials, blocks, out);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
