@@ -82,6 +82,7 @@ struct SweepTask {
         w.load_wait(S.mbar[slot], (phase_bits >> slot) & 1u);
         phase_bits ^= (1u << slot);
         bool anybad = false;
+#pragma unroll 1
         for (int c = w.lane(); c < SW_QW; c += 32) {
             Cons U;
             U.dens = S.q[IDENS][slot][c]; U.ener = S.q[IENER][slot][c];
