@@ -106,7 +106,7 @@ int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
  * (alpha - beta L) phi = f, nx = ny = 2^k, ng = 1.  The handle is a host object; the hierarchy's
  * device memory (p2b_mg_workspace_bytes, zero-initialised, 16-byte aligned) is allocated by the
  * caller and attached with p2b_mg_bind.  Level l has 2^(l+1) cells per side (MG.py:207-257) and three
- * planes: which = 0 v (solution / correction), 1 f (right-hand side), 2 r (residual), each
+ * planes: which = 0 v (solution / correction), 1 f (right-hand side), 2 r (residual), 3 w (scratch), each
  * (n+2) rows of p2b_mg_level_pitch elements.  bc = {xl, xr, yl, yr} codes ("dirichlet" ->
  * P2B_BC_REFLECT_ODD, "neumann" -> P2B_BC_OUTFLOW as in pyro/mesh/array_indexer.py:160-162).
  * All arithmetic is unfused and ordered as in the reference: v, f, r are bit-identical to it. */
@@ -114,6 +114,17 @@ typedef struct p2b_mg p2b_mg;
 
 p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
                       double ymin, double ymax, int nsmooth, int nsmooth_bottom);   /* MG.py:85-295 */
+/* multi-GPU (extension): this process owns x-slab `rank` of `size` (power of two) on every
+ * level with at least split_n columns; coarser levels are replicated on all ranks.  Slab levels store
+ * p2b_mg_tb_halo() halo rows beyond each end of the owned rows; the caller exchanges them (NCCL) before
+ * each p2b_mg_tb_pass / residual / prolong and all-gathers the restricted RHS at the slab -> replicated
+ * transition (pyro2_b200/multigrid/MG.py does). */
+p2b_mg* p2b_mg_create_slab(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                           double ymin, double ymax, int nsmooth, int nsmooth_bottom, int rank, int size,
+                           int split_n);
+/* out[8] = {owned rows ni, columns n, pitch, halo rows gx, global row offset, is_slab, plane stride
+ * (elements), first slab level} */
+int p2b_mg_level_info(p2b_mg* m, int level, long long* out);
 int p2b_mg_destroy(p2b_mg* m);
 /* A/B switch (default on): temporally blocked smoother (5 red-black iterations per HBM pass) vs one
  * launch per colour; both produce identical bits */
@@ -134,6 +145,12 @@ int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream);          /* v(le
 int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream);                  /* grids[level].fill_BC("v") */
 int p2b_mg_zero_coarse(p2b_mg* m, void* stream);                         /* MG.py:658-659 */
 int p2b_mg_vcycle(p2b_mg* m, void* stream);                              /* v_cycle(nlevels-1), MG.py:699-778 */
+int p2b_mg_vcycle_level(p2b_mg* m, int level, void* stream);             /* v_cycle(level) on non-decomposed levels */
+/* one pass (1..p2b_mg_tb_iters() red-black iterations) of the temporally blocked smoother, plane src ->
+ * plane dst (0 = v, 3 = scratch w; v->w or w->v) */
+int p2b_mg_tb_pass(p2b_mg* m, int level, int src, int dst, int niter, void* stream);
+int p2b_mg_tb_halo(void);
+int p2b_mg_tb_iters(void);
 /* sum over the valid region of plane^2 -> *out_dev (ArrayIndexer.norm = sqrt(dx dy sum),
  * pyro/mesh/array_indexer.py:98-111); deterministic summation order */
 int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out_dev, void* stream);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "p2b_mg_create": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i]),
+    "p2b_mg_create_slab": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i]),
+    "p2b_mg_level_info": (_i, [_vp, _i, C.POINTER(_ll)]),
     "p2b_mg_destroy": (_i, [_vp]),
     "p2b_mg_set_blocking": (_i, [_vp, _i]),
     "p2b_mg_nlevels": (_i, [_vp]),
@@ -86,6 +88,10 @@ SIGNATURES = {
     "p2b_mg_fill_bc": (_i, [_vp, _i, _vp]),
     "p2b_mg_zero_coarse": (_i, [_vp, _vp]),
     "p2b_mg_vcycle": (_i, [_vp, _vp]),
+    "p2b_mg_vcycle_level": (_i, [_vp, _i, _vp]),
+    "p2b_mg_tb_pass": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "p2b_mg_tb_halo": (_i, []),
+    "p2b_mg_tb_iters": (_i, []),
     "p2b_mg_norm2": (_i, [_vp, _i, _i, _vp, _vp]),
     "p2b_mg_cycle_diagnostics": (_i, [_vp, _vp, _vp, _vp]),
 }

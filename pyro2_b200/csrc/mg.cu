@@ -24,10 +24,15 @@
 namespace pyro {
 
 struct MgLevel {
-    int n, pitch;
+    int n, pitch;       // columns (y) of the level and the row pitch
     double *v, *f, *r;
     double *w;          // scratch plane: ping-pong target of the temporally blocked smoother
     double dx, dy;
+    // x-slab decomposition (multi-GPU): this rank owns global rows ioff+1 .. ioff+ni; gx halo rows
+    // are stored beyond each end (row index 1-gx .. ni+gx).  Single GPU / replicated level:
+    // ni = n, ioff = 0, gx = 1, both x sides physical.
+    int ni, ioff, gx;
+    int xlo_phys, xhi_phys;
 };
 
 struct MgBC {
@@ -51,6 +56,8 @@ struct p2b_mg {
     double* partials;                         // MG_NPART doubles x 2
     const double *xlv, *xrv, *ylv, *yrv;
     int no_blocking;                          // debugging / A-B switch: 1 = plain half-sweep kernels
+    int rank, size;                           // x-slab decomposition (size 1 = single GPU)
+    int split_level;                          // levels >= split_level are slabs when size > 1
 };
 
 namespace pyro {
@@ -78,30 +85,30 @@ __device__ __forceinline__ double ghost_hi(double val, int code, const double* v
 // store v(i,j) = val and every ghost cell whose source is (i,j).  x ghosts are functions of the
 // interior value; y ghosts (filled second in the reference, over the full x range) are functions of
 // the already x-filled column, which gives the corner values.
-__device__ __forceinline__ void store_with_ghosts(double* v, int n, int pitch, int i, int j, double val,
-                                                  const MgBC& b, double dx, double dy)
+__device__ __forceinline__ void store_with_ghosts(double* v, int ni, int n, int pitch, int i, int j, double val,
+                                                  const MgBC& b, double dx, double dy, int ioff = 0)
 {
     v[(long long)i * pitch + j] = val;
-    if (b.xl == P2B_BC_NONE) return;   // (not used by the single-GPU path)
-    const int sxl = (b.xl == P2B_BC_PERIODIC) ? n : 1;    // source row of ghost row 0
-    const int sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : n;    // source row of ghost row n+1
+    // x sides with P2B_BC_NONE face another slab: their halo rows come from the neighbour
+    const int sxl = (b.xl == P2B_BC_PERIODIC) ? ni : 1;   // source row of ghost row 0
+    const int sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : ni;   // source row of ghost row ni+1
     const int syl = (b.yl == P2B_BC_PERIODIC) ? n : 1;
     const int syh = (b.yr == P2B_BC_PERIODIC) ? 1 : n;
-    const bool lo = (i == sxl), hi = (i == sxh);
+    const bool lo = (b.xl != P2B_BC_NONE) && (i == sxl), hi = (b.xr != P2B_BC_NONE) && (i == sxh);
     if (!(lo || hi || j == syl || j == syh)) return;       // interior cell: nothing else to write
-    // after the x fill this value lives in up to three rows: i, 0 (if lo), n+1 (if hi)
+    // after the x fill this value lives in up to three rows: i, 0 (if lo), ni+1 (if hi)
     double glo = 0.0, ghi = 0.0;
     if (lo) { glo = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = glo; }
-    if (hi) { ghi = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(n + 1) * pitch + j] = ghi; }
+    if (hi) { ghi = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(ni + 1) * pitch + j] = ghi; }
     if (j == syl) {
-        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, i, dy);
-        if (lo) v[0] = ghost_lo(glo, b.yl, b.ylv, 0, dy);
-        if (hi) v[(long long)(n + 1) * pitch] = ghost_lo(ghi, b.yl, b.ylv, n + 1, dy);
+        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, ioff + i, dy);
+        if (lo) v[0] = ghost_lo(glo, b.yl, b.ylv, ioff, dy);
+        if (hi) v[(long long)(ni + 1) * pitch] = ghost_lo(ghi, b.yl, b.ylv, ioff + ni + 1, dy);
     }
     if (j == syh) {
-        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, i, dy);
-        if (lo) v[n + 1] = ghost_hi(glo, b.yr, b.yrv, 0, dy);
-        if (hi) v[(long long)(n + 1) * pitch + n + 1] = ghost_hi(ghi, b.yr, b.yrv, n + 1, dy);
+        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, ioff + i, dy);
+        if (lo) v[n + 1] = ghost_hi(glo, b.yr, b.yrv, ioff, dy);
+        if (hi) v[(long long)(ni + 1) * pitch + n + 1] = ghost_hi(ghi, b.yr, b.yrv, ioff + ni + 1, dy);
     }
 }
 
@@ -159,7 +166,7 @@ __global__ void mg_halfsweep_kernel(MgLevel L, MgBC b, SmoothCoef c, int colour)
     if (k >= half || i > L.n) return;
     const int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
     double val = gs_update(L.v, L.f, L.pitch, i, j, c);
-    store_with_ghosts(L.v, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+    store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
 }
 
 // whole smooth() for a small level in one CTA (global memory, __syncthreads between colours)
@@ -173,7 +180,7 @@ __global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmo
             int i = t / half + 1, k = t % half;
             int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
             double val = gs_update(L.v, L.f, L.pitch, i, j, c);
-            store_with_ghosts(L.v, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+            store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
         }
         __syncthreads();
     }
@@ -218,12 +225,15 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                                                double* __restrict__ vout, const MgBC& b, const SmoothCoef& c,
                                                int niter, double (*edge)[TB_NW][2][TB_RW])
 {
-    const int n = L.n, P = L.pitch;
+    const int n = L.n, ni = L.ni, P = L.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
-    const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd)
+    const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd; local index)
     const int gj0 = J0 - TB_H + 2 * lane;          // first of its two columns (odd)
     const bool xper = EDGE && (b.xl == P2B_BC_PERIODIC), yper = EDGE && (b.yl == P2B_BC_PERIODIC);
+    // rows that hold real cells: the owned rows plus, on a side facing another slab, the TB_H halo
+    // rows received from it (they are updated redundantly, exactly like the periodic wrap)
+    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? ni : ni + TB_H;
 
     double v[TB_R][2], f[TB_R][2];
     // EDGE only: bit r*2+a set = (r, a) is a real interior cell; per-row / per-column edge flags
@@ -233,13 +243,16 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
 #pragma unroll
     for (int r = 0; r < TB_R; ++r) {
         int gi = gi0 + r;
-        int si = xper ? wrap1(gi, n) : gi;
-        if (EDGE && !xper) { if (gi == 1) row_lo |= 1u << r; if (gi == n) row_hi |= 1u << r; }
+        int si = xper ? wrap1(gi, ni) : gi;
+        if (EDGE && !xper) {
+            if (L.xlo_phys && gi == 1) row_lo |= 1u << r;
+            if (L.xhi_phys && gi == ni) row_hi |= 1u << r;
+        }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             int gj = gj0 + a;
             int sj = yper ? wrap1(gj, n) : gj;
-            bool ok = !EDGE || (si >= 1 && si <= n && sj >= 1 && sj <= n);
+            bool ok = !EDGE || (si >= rlo && si <= rhi && sj >= 1 && sj <= n);
             if (!ok) inmask &= ~(1u << (2 * r + a));
             long long k = (long long)si * P + sj;
             v[r][a] = ok ? vin[k] : 0.0;
@@ -288,8 +301,8 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                 const int gi = gi0 + r, gj = gj0 + a;
                 if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
                 if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
-                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, gi, L.dy);
-                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, gi, L.dy);
+                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, L.ioff + gi, L.dy);
+                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, L.ioff + gi, L.dy);
             }
             double sx = exact_add(dn, up);
             double sy = exact_add(rt, lf);
@@ -313,12 +326,12 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
 #pragma unroll
     for (int r = 0; r < TB_R; ++r) {
         int gi = gi0 + r;
-        if (gi < I0 || gi >= I0 + TB_TI || gi > n) continue;
+        if (gi < I0 || gi >= I0 + TB_TI || gi > ni) continue;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             int gj = gj0 + a;
             if (gj < J0 || gj >= J0 + TB_TJ || gj > n) continue;
-            if (EDGE) store_with_ghosts(vout, n, P, gi, gj, v[r][a], b, L.dx, L.dy);
+            if (EDGE) store_with_ghosts(vout, ni, n, P, gi, gj, v[r][a], b, L.dx, L.dy, L.ioff);
             else vout[(long long)gi * P + gj] = v[r][a];
         }
     }
@@ -330,7 +343,8 @@ mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restric
 {
     __shared__ __align__(16) double edge[2][TB_NW][2][TB_RW];   // [buffer][warp][first/last row][column]
     const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
-    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + TB_RH - 1 <= L.n) &&
+    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? L.ni : L.ni + TB_H;
+    const bool interior = (I0 - TB_H >= rlo) && (I0 - TB_H + TB_RH - 1 <= rhi) &&
                           (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
     if (interior) smooth_tb_body<false>(L, vin, vout, b, c, niter, edge);
     else smooth_tb_body<true>(L, vin, vout, b, c, niter, edge);
@@ -376,7 +390,7 @@ __device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, cons
         int side = t >> ls, q = (t & (n - 1)) + 1;
         int i = side == 0 ? 1 : side == 1 ? n : q;
         int j = side == 2 ? 1 : side == 3 ? n : q;
-        store_with_ghosts(L.v, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+        store_with_ghosts(L.v, n, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
     }
     __syncthreads();
     for (int it = 0; it < 2 * nsmooth; ++it) {
@@ -385,7 +399,7 @@ __device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, cons
             int i = (t >> hs) + 1, k = t & (half - 1);
             int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
             double val = gs_update(L.v, L.f, L.pitch, i, j, c);
-            store_with_ghosts(L.v, n, L.pitch, i, j, val, b, L.dx, L.dy);
+            store_with_ghosts(L.v, n, n, L.pitch, i, j, val, b, L.dx, L.dy);
         }
         __syncthreads();
     }
@@ -455,10 +469,10 @@ __global__ void __launch_bounds__(1024, 1) mg_coarse_vcycle_kernel(CoarseTable T
             double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my), c0 = c[kc];
             const int i = 2 * ic - 1, j = 2 * jc - 1, P = F.pitch;
             double* v = F.v;
-            store_with_ghosts(v, F.n, P, i, j, exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i, j, exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
         }
         __syncthreads();
         cta_smooth(S[l], b, T.coef[l], T.nsmooth);
@@ -488,7 +502,7 @@ __global__ void mg_fill_kernel(MgLevel L, MgBC b)
         if (side == 0) { i = 1; j = s; } else if (side == 1) { i = n; j = s; }
         else if (side == 2) { i = s; j = 1; } else { i = s; j = n; }
         // corners are visited twice with identical results
-        store_with_ghosts(L.v, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+        store_with_ghosts(L.v, n, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
     }
 }
 
@@ -496,31 +510,32 @@ __global__ void mg_residual_kernel(MgLevel L, ResidCoef rc)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (i > L.n || j > L.n) return;
+    if (i > L.ni || j > L.n) return;
     const long long k = (long long)i * L.pitch + j;
     L.r[k] = residual_at(L, k, rc);
 }
 
-// fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732)
-__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs)
+// fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732).  crow: row offset of this
+// rank's rows inside the coarse array (non-zero when a slab level restricts into a replicated one)
+__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs, int crow)
 {
     const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (ic > Cs.n || jc > Cs.n) return;
+    if (ic > F.ni / 2 || jc > Cs.n) return;
     const long long k = (long long)(2 * ic - 1) * F.pitch + (2 * jc - 1);
     const double* r = F.r;
     double s = exact_add(exact_add(exact_add(r[k], r[k + F.pitch]), r[k + 1]), r[k + F.pitch + 1]);
-    Cs.f[(long long)ic * Cs.pitch + jc] = exact_mul(0.25, s);
+    Cs.f[(long long)(ic + crow) * Cs.pitch + jc] = exact_mul(0.25, s);
 }
 
 // v_fine += prolong(v_coarse), ghosts refreshed (patch.py:716-734, MG.py:745-751)
-__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b)
+__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b, int crow)
 {
     const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (ic > Cs.n || jc > Cs.n) return;
+    if (ic > F.ni / 2 || jc > Cs.n) return;
     const double* c = Cs.v;
-    const long long kc = (long long)ic * Cs.pitch + jc;
+    const long long kc = (long long)(ic + crow) * Cs.pitch + jc;
     double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
     double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
     double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my);
@@ -532,10 +547,10 @@ __global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b)
     double e11 = exact_add(exact_add(c0, qx), qy);
     double* v = F.v;
     const int P = F.pitch;
-    store_with_ghosts(v, F.n, P, i, j, exact_add(v[(long long)i * P + j], e00), b, F.dx, F.dy);
-    store_with_ghosts(v, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], e10), b, F.dx, F.dy);
-    store_with_ghosts(v, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], e01), b, F.dx, F.dy);
-    store_with_ghosts(v, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], e11), b, F.dx, F.dy);
+    store_with_ghosts(v, F.ni, F.n, P, i, j, exact_add(v[(long long)i * P + j], e00), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], e10), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], e01), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], e11), b, F.dx, F.dy, F.ioff);
 }
 
 // ---- deterministic reductions over the valid region ------------------------------------------------
@@ -560,12 +575,12 @@ __device__ __forceinline__ double block_sum(double s, double* sh)
 }
 
 // mode 0: sum a^2
-__global__ void __launch_bounds__(RED_THREADS) mg_sumsq_partial_kernel(const double* __restrict__ a, int n, int pitch,
+__global__ void __launch_bounds__(RED_THREADS) mg_sumsq_partial_kernel(const double* __restrict__ a, int ni, int n, int pitch,
                                                                        double* __restrict__ part)
 {
     __shared__ double sh[RED_THREADS];
     double s = 0.0;
-    for (int i = 1 + blockIdx.x; i <= n; i += gridDim.x) {
+    for (int i = 1 + blockIdx.x; i <= ni; i += gridDim.x) {
         const double* row = a + (long long)i * pitch;
         for (int j0 = 1 + threadIdx.x; j0 <= n; j0 += RED_THREADS * RED_PER_THREAD) {
             double x[RED_PER_THREAD];
@@ -613,7 +628,7 @@ mg_diag_partial_kernel(MgLevel L, double* __restrict__ old_phi, ResidCoef rc, do
     const double* __restrict__ v = L.v;
     const double* __restrict__ f = L.f;
     double* __restrict__ r = L.r;
-    for (int i = 1 + blockIdx.x; i <= n; i += gridDim.x) {
+    for (int i = 1 + blockIdx.x; i <= L.ni; i += gridDim.x) {
         const long long base = (long long)i * P;
         for (int j0 = 1 + threadIdx.x; j0 <= n; j0 += RED_THREADS * RED_PER_THREAD) {
             double c[RED_PER_THREAD], up[RED_PER_THREAD], dn[RED_PER_THREAD], lf[RED_PER_THREAD],
@@ -663,6 +678,11 @@ static MgBC level_bc(const p2b_mg* m, int level)
 {
     MgBC b;
     b.xl = m->bc[0]; b.xr = m->bc[1]; b.yl = m->bc[2]; b.yr = m->bc[3];
+    if (level >= 0 && level < m->nlevels) {
+        // a slab's x side that faces another slab (or, for periodic x, wraps onto one) has no BC
+        if (!m->lev[level].xlo_phys) b.xl = P2B_BC_NONE;
+        if (!m->lev[level].xhi_phys) b.xr = P2B_BC_NONE;
+    }
     const bool fin = (level == m->nlevels - 1);
     // inhomogeneous values apply on the finest level only (MG.py:231-242) and only to
     // Dirichlet / Neumann sides (array_indexer.py:165-183)
@@ -740,11 +760,24 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
     return P2B_OK;
 }
 
+// rows of the coarse level that correspond to this rank's fine rows start at ioff_fine / 2; that is
+// a non-zero offset into the coarse array only when the coarse level is replicated (ioff = 0 there)
+static int coarse_row_offset(const MgLevel& F, const MgLevel& Cs) { return F.ioff / 2 - Cs.ioff; }
+
+static bool is_slab(const p2b_mg* m, int level) { return m->size > 1 && level >= m->split_level; }
+
+static void tb_pass_impl(p2b_mg* m, int level, const double* src, double* dst, int niter, cudaStream_t st)
+{
+    const MgLevel& L = m->lev[level];
+    dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.ni + TB_TI - 1) / TB_TI);
+    mg_smooth_tb_kernel<<<grd, 32 * TB_NW, 0, st>>>(L, src, dst, level_bc(m, level), level_coef(m, L), niter);
+}
+
 static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     const MgLevel& L = m->lev[level];
     dim3 blk(64, 4);
-    dim3 grd((L.n + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
+    dim3 grd((L.n + blk.x - 1) / blk.x, (L.ni + blk.y - 1) / blk.y);
     mg_residual_kernel<<<grd, blk, 0, st>>>(L, level_rcoef(m, L));
 }
 
@@ -752,16 +785,16 @@ static void restrict_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
     dim3 blk(64, 4);
-    dim3 grd((Cs.n + blk.x - 1) / blk.x, (Cs.n + blk.y - 1) / blk.y);
-    mg_restrict_kernel<<<grd, blk, 0, st>>>(F, Cs);
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (F.ni / 2 + blk.y - 1) / blk.y);
+    mg_restrict_kernel<<<grd, blk, 0, st>>>(F, Cs, coarse_row_offset(F, Cs));
 }
 
 static void prolong_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
     dim3 blk(64, 4);
-    dim3 grd((Cs.n + blk.x - 1) / blk.x, (Cs.n + blk.y - 1) / blk.y);
-    mg_prolong_kernel<<<grd, blk, 0, st>>>(F, Cs, level_bc(m, level));
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (F.ni / 2 + blk.y - 1) / blk.y);
+    mg_prolong_kernel<<<grd, blk, 0, st>>>(F, Cs, level_bc(m, level), coarse_row_offset(F, Cs));
 }
 
 static int coarse_top(const p2b_mg* m)
@@ -818,8 +851,8 @@ static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
 static int sumsq_impl(p2b_mg* m, const double* a, int level, double* out, cudaStream_t st)
 {
     const MgLevel& L = m->lev[level];
-    int blocks = L.n < MG_NPART ? L.n : MG_NPART;
-    mg_sumsq_partial_kernel<<<blocks, RED_THREADS, 0, st>>>(a, L.n, L.pitch, m->partials);
+    int blocks = L.ni < MG_NPART ? L.ni : MG_NPART;
+    mg_sumsq_partial_kernel<<<blocks, RED_THREADS, 0, st>>>(a, L.ni, L.n, L.pitch, m->partials);
     mg_sumsq_final_kernel<<<1, RED_THREADS, 0, st>>>(m->partials, blocks, out);
     return P2B_OK;
 }
@@ -830,12 +863,13 @@ using namespace pyro;
 
 extern "C" {
 
-// CellCenterMG2d.__init__ (MG.py:85-295): level l has 2^(l+1) cells per side, ng = 1, vars v, f, r
-p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
-                      double ymin, double ymax, int nsmooth, int nsmooth_bottom)
+static p2b_mg* mg_create_impl(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                              double ymin, double ymax, int nsmooth, int nsmooth_bottom, int rank, int size,
+                              int split_n)
 {
     if (nx < 2 || (nx & (nx - 1)) != 0) { set_error("multigrid requires nx = ny = power of two (got %d)", nx); return nullptr; }
     if (!bc) { set_error("null bc"); return nullptr; }
+    if (size < 1 || (size & (size - 1)) != 0 || rank < 0 || rank >= size) { set_error("slab count must be a power of two"); return nullptr; }
     p2b_mg* m = new p2b_mg();
     memset(m, 0, sizeof *m);
     int nl = 0;
@@ -845,26 +879,74 @@ p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double x
     m->alpha = alpha; m->beta = beta;
     m->xmin = xmin; m->xmax = xmax; m->ymin = ymin; m->ymax = ymax;
     m->nsmooth = nsmooth; m->nsmooth_bottom = nsmooth_bottom;
-    // layout: per level three consecutive planes v, f, r (uniform plane stride, so a level is one
-    // strided (3, n+2, pitch) tensor on the Python side); then the norm partials
+    m->rank = rank; m->size = size;
+    // levels with at least split_n columns are x-slabs; each slab must keep >= 2*TB_H rows so a halo
+    // never reaches past the neighbour's owned rows
+    m->split_level = m->nlevels;
+    if (size > 1) {
+        for (int l = m->nlevels - 1; l >= 0; --l) {
+            int n = 2 << l;
+            if (n >= split_n && n / size >= 2 * TB_H && n >= MG_TB_MIN_N) m->split_level = l; else break;
+        }
+        if (m->split_level >= m->nlevels) { set_error("grid too small for %d slabs", size); delete m; return nullptr; }
+    }
+    const bool xper = (bc[0] == P2B_BC_PERIODIC);
+    // layout: per level four consecutive planes v, f, r, w (uniform plane stride, so a level is one
+    // strided tensor on the Python side); then the norm partials
     long long off = 0;
     for (int l = 0; l < m->nlevels; ++l) {
         MgLevel& L = m->lev[l];
         L.n = 2 << l;
+        const bool slab = (size > 1 && l >= m->split_level);
+        L.ni = slab ? L.n / size : L.n;
+        L.ioff = slab ? rank * L.ni : 0;
+        L.gx = slab ? TB_H : 1;
+        L.xlo_phys = !slab || (rank == 0 && !xper);
+        L.xhi_phys = !slab || (rank == size - 1 && !xper);
         int q = L.n + 2;
         L.pitch = (q >= 16) ? (q + 15) / 16 * 16 : (q + 1) / 2 * 2;
         L.dx = (xmax - xmin) / L.n;
         L.dy = (ymax - ymin) / L.n;
-        long long plane = (long long)q * L.pitch;
+        const long long rows = L.ni + 2 * L.gx;
+        const long long plane = rows * L.pitch;
+        const long long row0 = (long long)(L.gx - 1) * L.pitch;    // pointer = address of row index 0
         // offsets are stored as fake pointers (element counts) until p2b_mg_bind
-        L.v = (double*)off; off += plane;
-        L.f = (double*)off; off += plane;
-        L.r = (double*)off; off += plane;
-        L.w = (double*)off; off += plane;
+        L.v = (double*)(off + row0); off += plane;
+        L.f = (double*)(off + row0); off += plane;
+        L.r = (double*)(off + row0); off += plane;
+        L.w = (double*)(off + row0); off += plane;
     }
     m->partials = (double*)off; off += 2 * MG_NPART;
     m->bytes = off * 8;
     return m;
+}
+
+// CellCenterMG2d.__init__ (MG.py:85-295): level l has 2^(l+1) cells per side, ng = 1, vars v, f, r
+p2b_mg* p2b_mg_create(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                      double ymin, double ymax, int nsmooth, int nsmooth_bottom)
+{
+    return mg_create_impl(nx, bc, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom, 0, 1, 0);
+}
+
+// multi-GPU: this process owns x-slab `rank` of `size` on every level with >= split_n columns;
+// coarser levels are replicated on all ranks
+p2b_mg* p2b_mg_create_slab(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
+                           double ymin, double ymax, int nsmooth, int nsmooth_bottom, int rank, int size,
+                           int split_n)
+{
+    return mg_create_impl(nx, bc, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom, rank, size, split_n);
+}
+
+// geometry of a level: out = {ni, n, pitch, gx, ioff, is_slab, plane_stride_lo, plane_stride_hi}
+int p2b_mg_level_info(p2b_mg* m, int level, long long* out)
+{
+    P2B_REQUIRE(m && out && level >= 0 && level < m->nlevels, "bad level");
+    const MgLevel& L = m->lev[level];
+    out[0] = L.ni; out[1] = L.n; out[2] = L.pitch; out[3] = L.gx; out[4] = L.ioff;
+    out[5] = (m->size > 1 && level >= m->split_level) ? 1 : 0;
+    out[6] = (long long)(L.ni + 2 * L.gx) * L.pitch;
+    out[7] = m->split_level;
+    return P2B_OK;
 }
 
 int p2b_mg_destroy(p2b_mg* m) { delete m; return P2B_OK; }
@@ -893,7 +975,7 @@ int p2b_mg_bind(p2b_mg* m, void* mem, long long bytes)
 void* p2b_mg_level_ptr(p2b_mg* m, int level, int which)
 {
     if (!m || level < 0 || level >= m->nlevels) return nullptr;
-    return which == 0 ? m->lev[level].v : which == 1 ? m->lev[level].f : m->lev[level].r;
+    return which == 0 ? m->lev[level].v : which == 1 ? m->lev[level].f : which == 2 ? m->lev[level].r : m->lev[level].w;
 }
 
 int p2b_mg_level_pitch(p2b_mg* m, int level) { return (m && level >= 0 && level < m->nlevels) ? m->lev[level].pitch : 0; }
@@ -913,6 +995,7 @@ int p2b_mg_set_bc_values(p2b_mg* m, const double* xl, const double* xr, const do
 int p2b_mg_smooth(p2b_mg* m, int level, int nsmooth, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(!is_slab(m, level), "smooth() on a slab level needs halo exchanges: drive it with p2b_mg_tb_pass");
     smooth_impl(m, level, nsmooth, true, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -947,6 +1030,7 @@ int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream)
 int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(!is_slab(m, level), "fill_bc on a slab level: exchange the halo rows instead");
     const MgLevel& L = m->lev[level];
     mg_fill_kernel<<<(4 * L.n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(L, level_bc(m, level));
     P2B_CUDA_CHECK(cudaGetLastError());
@@ -962,8 +1046,8 @@ int p2b_mg_zero_coarse(p2b_mg* m, void* stream)
     t.nlev = m->nlevels - 1;
     long long most = 0;
     for (int l = 0; l < t.nlev; ++l) {
-        t.v[l] = m->lev[l].v;
-        t.count[l] = (long long)(m->lev[l].n + 2) * m->lev[l].pitch;
+        t.v[l] = m->lev[l].v - (long long)(m->lev[l].gx - 1) * m->lev[l].pitch;
+        t.count[l] = (long long)(m->lev[l].ni + 2 * m->lev[l].gx) * m->lev[l].pitch;
         if (t.count[l] > most) most = t.count[l];
     }
     long long blocks = (most + 255) / 256;
@@ -973,9 +1057,39 @@ int p2b_mg_zero_coarse(p2b_mg* m, void* stream)
     return P2B_OK;
 }
 
+// one pass (<= 5 red-black iterations) of the temporally blocked smoother on `level`, reading plane
+// src (0 = v, 3 = w) and writing dst (3 = w, 0 = v).  On slab levels the caller exchanges TB_H halo
+// rows of the source plane first (p2b_mg_tb_halo()).
+int p2b_mg_tb_pass(p2b_mg* m, int level, int src, int dst, int niter, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE((src == 0 && dst == 3) || (src == 3 && dst == 0), "src/dst must be v->w or w->v");
+    P2B_REQUIRE(niter >= 1 && niter <= TB_K, "niter out of range");
+    P2B_REQUIRE(m->lev[level].n >= MG_TB_MIN_N, "level too small for the blocked smoother");
+    const MgLevel& L = m->lev[level];
+    tb_pass_impl(m, level, src == 0 ? L.v : L.w, dst == 0 ? L.v : L.w, niter, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_mg_tb_halo(void) { return TB_H; }
+int p2b_mg_tb_iters(void) { return TB_K; }
+
+// the sub-V-cycle from `level` down and back up (v_cycle(level), MG.py:699-778); used for the
+// replicated coarse levels of a decomposed hierarchy
+int p2b_mg_vcycle_level(p2b_mg* m, int level, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(!is_slab(m, level), "level is decomposed");
+    vcycle_impl(m, level, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
 int p2b_mg_vcycle(p2b_mg* m, void* stream)
 {
     P2B_REQUIRE(m && m->base, "hierarchy not bound");
+    P2B_REQUIRE(m->size == 1, "decomposed hierarchy: the V-cycle is driven level by level (halo exchanges)");
     vcycle_impl(m, m->nlevels - 1, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -1002,7 +1116,7 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     const int lf = m->nlevels - 1;
     const MgLevel& L = m->lev[lf];
-    int blocks = L.n < MG_NPART ? L.n : MG_NPART;
+    int blocks = L.ni < MG_NPART ? L.ni : MG_NPART;
     mg_diag_partial_kernel<<<blocks, RED_THREADS, 0, st>>>(L, old_phi, level_rcoef(m, L), m->partials);
     mg_diag_final_kernel<<<1, RED_THREADS, 0, st>>>(m->partials, blocks, out);
     P2B_CUDA_CHECK(cudaGetLastError());

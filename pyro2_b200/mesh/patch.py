@@ -256,13 +256,14 @@ class CellCenterData2d:
             return
         ops.fill_ghost(self.planes, g.nx, g.ny, g.ng, [b.names() for b in bcs])
 
-    def _fill_BC_all_slab(self, bcs):
+    def _fill_BC_all_slab(self, bcs, planes=None):
         """x-slab of a decomposed domain: neighbour rows first (they are the "x fill" of interior
         sides), then the physical x sides and the y sides over the full x range -- the same order as
         the single-domain fill (array_indexer.py:164-274), so corners come out identical."""
         g = self.grid
+        planes = self.planes if planes is None else planes
         periodic = bcs[0].xlb == "periodic"
-        self.decomposition.exchange(self.planes, g.nx, g.ng, periodic=periodic)
+        self.decomposition.exchange(planes, g.nx, g.ng, periodic=periodic)
         lo_int, hi_int = self.decomposition.interior_sides(periodic)
         names = []
         for b in bcs:
@@ -272,13 +273,16 @@ class CellCenterData2d:
             if hi_int:
                 n[1] = None
             names.append(tuple(n))
-        ops.fill_ghost(self.planes, g.nx, g.ny, g.ng, names)
+        ops.fill_ghost(planes, g.nx, g.ny, g.ng, names)
 
     def fill_BC(self, name):
         """one variable: standard types on the device, then any user-registered callbacks
         (patch.py:582-624)"""
         n = self.names.index(name)
         bc = self.BCs[name]
+        if self.decomposition is not None and self.decomposition.size > 1:
+            self._fill_BC_all_slab([bc], planes=self.planes[n:n + 1])
+            return
         self.get_var_by_index(n).fill_ghost(bc=_StandardOnly(bc))
         for side, btype in zip(("xlb", "xrb", "ylb", "yrb"), bc.names()):
             if btype in bnd.ext_bcs:

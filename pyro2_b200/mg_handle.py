@@ -10,14 +10,26 @@ from .ops import require_cuda
 
 
 class MGHandle:
-    def __init__(self, nx, bc, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom):
+    def __init__(self, nx, bc, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom,
+                 decomposition=None, split_n=1024):
+        """decomposition: parallel.SlabDecomposition -- this process then holds x-slab `rank` of every
+        level with >= split_n columns and a full copy of the coarser ones"""
         require_cuda()
         L = _lib.lib()
         codes = (C.c_int * 4)(*[_lib.BC_CODES[b] for b in bc])
-        self._h = L.p2b_mg_create(nx, codes, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom)
+        self.decomp = decomposition if (decomposition is not None and decomposition.size > 1) else None
+        if self.decomp is None:
+            self._h = L.p2b_mg_create(nx, codes, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom)
+        else:
+            self._h = L.p2b_mg_create_slab(nx, codes, alpha, beta, xmin, xmax, ymin, ymax, nsmooth,
+                                           nsmooth_bottom, self.decomp.rank, self.decomp.size, split_n)
         if not self._h:
             raise ValueError(L.p2b_last_error().decode())
         self.nlevels = L.p2b_mg_nlevels(self._h)
+        self.tb_halo = L.p2b_mg_tb_halo()
+        self.tb_iters = L.p2b_mg_tb_iters()
+        self.xperiodic = bc[0] == "periodic"
+        self._info = {}
         nbytes = L.p2b_mg_workspace_bytes(self._h)
         self.workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
         _lib.check(L.p2b_mg_bind(self._h, self.workspace.data_ptr(), nbytes))
@@ -36,17 +48,52 @@ class MGHandle:
         except Exception:
             pass
 
+    _WHICH = {"v": 0, "f": 1, "r": 2, "w": 3}
+
+    def info(self, level):
+        """geometry of a level: owned rows ni, columns n, pitch, halo rows gx, global row offset ioff,
+        slab flag, plane stride (elements), first slab level"""
+        if level not in self._info:
+            out = (C.c_longlong * 8)()
+            _lib.check(_lib.lib().p2b_mg_level_info(self._h, level, out))
+            keys = ("ni", "n", "pitch", "gx", "ioff", "slab", "plane_stride", "split_level")
+            self._info[level] = dict(zip(keys, [int(x) for x in out]))
+        return self._info[level]
+
+    def _row0_offset(self, level, which):
+        ptr = _lib.lib().p2b_mg_level_ptr(self._h, level, self._WHICH[which])
+        return (ptr - self.workspace.data_ptr()) // 8
+
     def plane(self, level, which):
-        """(n+2, n+2) strided view of plane which in {'v','f','r'} on `level`"""
+        """(ni+2, n+2) strided view (one ghost row / column all round) of plane which in
+        {'v','f','r','w'} on `level`; ni = n unless the level is a slab"""
         key = (level, which)
         if key not in self._planes:
-            idx = {"v": 0, "f": 1, "r": 2}[which]
-            n = 2 ** (level + 1)
-            ptr = _lib.lib().p2b_mg_level_ptr(self._h, level, idx)
-            pitch = _lib.lib().p2b_mg_level_pitch(self._h, level)
-            off = (ptr - self.workspace.data_ptr()) // 8
-            self._planes[key] = self.workspace.as_strided((n + 2, n + 2), (pitch, 1), off)
+            g = self.info(level)
+            self._planes[key] = self.workspace.as_strided((g["ni"] + 2, g["n"] + 2), (g["pitch"], 1),
+                                                          self._row0_offset(level, which))
         return self._planes[key]
+
+    def halo_rows(self, level, which, depth):
+        """contiguous (ni + 2*depth, pitch) view: `depth` halo rows, the owned rows, `depth` halo rows"""
+        g = self.info(level)
+        assert depth <= g["gx"]
+        off = self._row0_offset(level, which) + (1 - depth) * g["pitch"]
+        return self.workspace.as_strided((g["ni"] + 2 * depth, g["pitch"]), (g["pitch"], 1), off)
+
+    def exchange(self, level, which, depth):
+        """halo exchange of `depth` rows with the neighbouring slabs (no-op on replicated levels)"""
+        g = self.info(level)
+        if self.decomp is None or not g["slab"]:
+            return
+        self.decomp.exchange(self.halo_rows(level, which, depth).unsqueeze(0), g["ni"], depth,
+                             periodic=self.xperiodic)
+
+    def tb_pass(self, level, src, dst, niter):
+        _lib.check(_lib.lib().p2b_mg_tb_pass(self._h, level, self._WHICH[src], self._WHICH[dst], niter, self._s()))
+
+    def vcycle_level(self, level):
+        _lib.check(_lib.lib().p2b_mg_vcycle_level(self._h, level, self._s()))
 
     def set_bc_values(self, xl=None, xr=None, yl=None, yr=None):
         vals = []
@@ -85,10 +132,16 @@ class MGHandle:
     def sumsq(self, level, which):
         idx = {"v": 0, "f": 1, "r": 2}[which]
         _lib.check(_lib.lib().p2b_mg_norm2(self._h, level, idx, self._out.data_ptr(), self._s()))
+        if self.decomp is not None and self.info(level)["slab"]:
+            import torch.distributed as dist
+            dist.all_reduce(self._out[:1], group=self.decomp.group)
         return float(self._out[0])
 
     def cycle_diagnostics(self, old_phi):
         """returns (sum rel-change^2, sum r^2); updates old_phi <- v and the r plane"""
         _lib.check(_lib.lib().p2b_mg_cycle_diagnostics(self._h, old_phi.data_ptr(), self._out.data_ptr(), self._s()))
+        if self.decomp is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._out, group=self.decomp.group)
         a, b = self._out.tolist()
         return a, b

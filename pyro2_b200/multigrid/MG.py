@@ -45,7 +45,11 @@ class CellCenterMG2d:
                  nsmooth=10, nsmooth_bottom=50,
                  verbose=0,
                  aux_field=None, aux_bc=None,
-                 true_function=None, vis=0, vis_title=""):
+                 true_function=None, vis=0, vis_title="",
+                 decomposition=None, split_n=1024):
+        """decomposition / split_n (extension, multi-GPU): a parallel.SlabDecomposition; every level
+        with at least split_n columns is then split into x-slabs (this process owns one), coarser
+        levels are replicated.  x2d / y2d / init_RHS / get_solution refer to the local slab."""
         if nx != ny:
             raise ValueError("ERROR: multigrid currently requires nx = ny")
         if (xmax - xmin) != (ymax - ymin):
@@ -72,30 +76,44 @@ class CellCenterMG2d:
             self.nlevels = nx.bit_length() - 1
 
         bc_names = (xl_BC_type, xr_BC_type, yl_BC_type, yr_BC_type)
-        self._h = MGHandle(nx, bc_names, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom)
+        self._h = MGHandle(nx, bc_names, alpha, beta, xmin, xmax, ymin, ymax, nsmooth, nsmooth_bottom,
+                           decomposition=decomposition, split_n=split_n)
         assert self._h.nlevels == self.nlevels
+        self._decomp = self._h.decomp
+        self._split = self._h.info(self.nlevels - 1)["split_level"] if self._decomp is not None else 0
 
         # grids[0] is the coarsest (2x2), grids[nlevels-1] the finest (MG.py:207-257)
         self.grids = []
         bc = bnd.BC(xlb=xl_BC_type, xrb=xr_BC_type, ylb=yl_BC_type, yrb=yr_BC_type)
         n_t = 2
         for i in range(self.nlevels):
-            my_grid = patch.Grid2d(n_t, n_t, ng=self.ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax)
+            info = self._h.info(i)
+            if info["slab"]:
+                my_grid = patch.Grid2d(info["ni"], n_t, ng=self.ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax,
+                                       nx_global=n_t, ioffset=info["ioff"])
+            else:
+                my_grid = patch.Grid2d(n_t, n_t, ng=self.ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax)
             lev = patch.CellCenterData2d(my_grid, dtype=np.float64)
+            if info["slab"]:
+                lev.decomposition = self._decomp
             if i == self.nlevels - 1:
                 # inhomogeneous boundary values apply to phi on the finest level only
                 bc_p = bnd.BC(xlb=xl_BC_type, xrb=xr_BC_type, ylb=yl_BC_type, yrb=yr_BC_type,
                               xl_func=xl_BC, xr_func=xr_BC, yl_func=yl_BC, yr_func=yr_BC, grid=my_grid)
                 lev.register_var("v", bc_p)
+                # the library indexes the y-side values with GLOBAL row indices
+                full = patch.Grid2d(n_t, n_t, ng=self.ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax,
+                                    device=my_grid.device) if info["slab"] else my_grid
                 self._h.set_bc_values(_to_host_1d(bc_p.xl_value), _to_host_1d(bc_p.xr_value),
-                                      _to_host_1d(bc_p.yl_value), _to_host_1d(bc_p.yr_value))
+                                      _to_host_1d(yl_BC(full.x)) if yl_BC is not None else None,
+                                      _to_host_1d(yr_BC(full.x)) if yr_BC is not None else None)
             else:
                 lev.register_var("v", bc)
             lev.register_var("f", bc)
             lev.register_var("r", bc)
             v = self._h.plane(i, "v")
             pitch = v.stride(0)
-            planes = self._h.workspace.as_strided((3, n_t + 2, pitch), ((n_t + 2) * pitch, pitch, 1),
+            planes = self._h.workspace.as_strided((3, info["ni"] + 2, pitch), (info["plane_stride"], pitch, 1),
                                                   v.storage_offset())
             lev.create(planes=planes)
             self.grids.append(lev)
@@ -168,6 +186,8 @@ class CellCenterMG2d:
         f = self.grids[self.nlevels - 1].get_var("f")
         self._assign(f, data)
         self.source_norm = self._norm(self.nlevels - 1, "f")
+        if self._decomp is not None:
+            self._h.exchange(self.nlevels - 1, "f", self._h.tb_halo)   # halo cells need f too
         if self.verbose:
             print("Source norm = ", self.source_norm)
         self.initialized_rhs = 1
@@ -191,6 +211,9 @@ class CellCenterMG2d:
         """one V-cycle from `level` down and back (MG.py:699-778).  With the stock smoother and
         residual the whole hierarchy is traversed inside the library; subclasses that override the
         hooks get the reference's recursion with their hooks called per level."""
+        if self._decomp is not None:
+            self._v_cycle_slabs(level)
+            return
         if self._stock() and level == self.nlevels - 1 and not self.verbose:
             self.current_level = level
             self._h.vcycle()
@@ -226,6 +249,51 @@ class CellCenterMG2d:
             self.smooth(level, self.nsmooth_bottom)
             self._h.fill_bc(level)
 
+    # ---- multi-GPU V-cycle: slab levels with NCCL halo exchange, replicated coarse levels ----------
+    def _smooth_slabs(self, level, nsmooth):
+        """nsmooth red-black iterations on a slab level: passes of <= 5 iterations of the temporally
+        blocked kernel, each preceded by one exchange of its 10-row halo (communication-avoiding:
+        one message per 5 iterations instead of one per colour)"""
+        h = self._h
+        src, dst = "v", "w"
+        left = nsmooth
+        while left > 0:
+            it = min(left, h.tb_iters)
+            h.exchange(level, src, h.tb_halo)
+            h.tb_pass(level, src, dst, it)
+            left -= it
+            src, dst = dst, src
+        if src != "v":
+            g = h.info(level)
+            h.halo_rows(level, "v", g["gx"]).copy_(h.halo_rows(level, "w", g["gx"]))
+
+    def _v_cycle_slabs(self, level):
+        import torch.distributed as dist
+        h = self._h
+        if level < self._split:
+            # replicated levels: every rank runs the identical sub-V-cycle, no communication
+            h.vcycle_level(level)
+            return
+        self.current_level = level
+        self._smooth_slabs(level, self.nsmooth)
+        h.exchange(level, "v", 1)
+        h.residual(level)
+        h.restrict(level)
+        if level - 1 < self._split:
+            # slab -> replicated: everyone needs the whole coarse right-hand side
+            g = h.info(level - 1)
+            f = h.halo_rows(level - 1, "f", 0)                  # owned rows = the whole level, contiguous
+            mine = f[self._decomp.rank * (g["ni"] // self._decomp.size):][:g["ni"] // self._decomp.size]
+            dist.all_gather_into_tensor(f.view(-1), mine.reshape(-1), group=self._decomp.group)
+        else:
+            # the blocked smoother updates the halo cells redundantly, so it needs their right-hand side
+            h.exchange(level - 1, "f", h.tb_halo)
+        self._v_cycle_slabs(level - 1)
+        if level - 1 >= self._split:
+            h.exchange(level - 1, "v", 1)
+        h.prolong_correct(level)
+        self._smooth_slabs(level, self.nsmooth)
+
     def solve(self, rtol=1.e-11):
         """V-cycles until ||r|| / ||f|| <= rtol or max_cycles (MG.py:623-697); one host read-back of
         two scalars per cycle"""
@@ -250,6 +318,8 @@ class CellCenterMG2d:
                 print(f"<<< beginning V-cycle (cycle {cycle}) >>>\n")
             self.v_cycle(fine)
             # relative change, old_phi <- v, residual and its norm, all on the device
+            if self._decomp is not None:
+                self._h.exchange(fine, "v", 1)      # the residual stencil reads the neighbours' rows
             if self._stock():
                 relsq, rsq = self._h.cycle_diagnostics(old_phi)
             else:
@@ -266,4 +336,7 @@ class CellCenterMG2d:
         self.num_cycles = cycle - 1
         self.relative_error = relative_error
         self.residual_error = residual_error
-        self._h.fill_bc(fine)
+        if self._decomp is not None:
+            self._h.exchange(fine, "v", 1)      # the slab's x "ghost" rows are the neighbours' rows
+        else:
+            self._h.fill_bc(fine)
