@@ -137,6 +137,13 @@ class MGHandle:
             dist.all_reduce(self._out[:1], group=self.decomp.group)
         return float(self._out[0])
 
+    def cycle_diagnostics_enqueue(self, old_phi):
+        """device part of cycle_diagnostics (capturable in a CUDA graph): results land in self._out"""
+        _lib.check(_lib.lib().p2b_mg_cycle_diagnostics(self._h, old_phi.data_ptr(), self._out.data_ptr(), self._s()))
+        if self.decomp is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._out, group=self.decomp.group)
+
     def cycle_diagnostics(self, old_phi):
         """returns (sum rel-change^2, sum r^2); updates old_phi <- v and the r plane"""
         _lib.check(_lib.lib().p2b_mg_cycle_diagnostics(self._h, old_phi.data_ptr(), self._out.data_ptr(), self._s()))

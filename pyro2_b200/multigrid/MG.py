@@ -138,6 +138,9 @@ class CellCenterMG2d:
         self.vis_title = vis_title
         self.frame = 0
         self._old_phi = None
+        self.use_graph = True       # replay the V-cycle as a CUDA graph after one eager cycle
+        self._graph = None
+        self._graph_error = None
 
     x2d = property(lambda self: self.soln_grid.x2d)
     y2d = property(lambda self: self.soln_grid.y2d)
@@ -305,27 +308,69 @@ class CellCenterMG2d:
         g = self.soln_grid
         v = self.grids[fine].get_var("v").t()
         pitch = v.stride(0)
-        old_phi = torch.empty((g.qx, pitch), dtype=torch.float64, device=v.device)
+        if self._old_phi is None:       # persistent: the captured graph holds its address
+            self._old_phi = torch.empty((g.qx, pitch), dtype=torch.float64, device=v.device)
+        old_phi = self._old_phi
         old_phi[:, :g.qy].copy_(v)
 
         residual_error = 1.e33
         relative_error = 1.e33
         cycle = 1
-        while residual_error > rtol and cycle <= self.max_cycles:
-            self.current_cycle = cycle
+        graph = self._graph             # captured by an earlier solve() on this object
+        eager_done = 0
+        # The cycle body (zero coarse v, V-cycle, diagnostics) is ~60 small launches (plus the NCCL
+        # exchanges when decomposed): after one eager cycle it is captured into a CUDA graph and
+        # replayed, so a cycle costs one launch on the host.  Verbose mode and subclasses that
+        # override the hooks stay eager (their hooks may synchronise).
+        # (not when decomposed: a captured graph holding NCCL work kept the process from shutting
+        # down cleanly in testing, and only bought 6%)
+        use_graph = self.use_graph and self._stock() and not self.verbose and self._decomp is None
+
+        def body():
             self._h.zero_coarse()
-            if self.verbose:
-                print(f"<<< beginning V-cycle (cycle {cycle}) >>>\n")
             self.v_cycle(fine)
-            # relative change, old_phi <- v, residual and its norm, all on the device
             if self._decomp is not None:
                 self._h.exchange(fine, "v", 1)      # the residual stencil reads the neighbours' rows
-            if self._stock():
-                relsq, rsq = self._h.cycle_diagnostics(old_phi)
+            self._h.cycle_diagnostics_enqueue(old_phi)
+
+        while residual_error > rtol and cycle <= self.max_cycles:
+            self.current_cycle = cycle
+            if self.verbose:
+                print(f"<<< beginning V-cycle (cycle {cycle}) >>>\n")
+            if use_graph:
+                if graph is not None:
+                    graph.replay()
+                elif eager_done >= 1:
+                    try:
+                        torch.cuda.synchronize()
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            body()
+                        self._graph = graph
+                        graph.replay()
+                    except Exception as exc:   # pylint: disable=broad-except
+                        # capture is an optimisation only: fall back to eager launches
+                        graph, use_graph = None, False
+                        self.use_graph = False
+                        self._graph_error = repr(exc)
+                        torch.cuda.synchronize()
+                        body()
+                else:
+                    body()
+                    eager_done += 1
+                relsq, rsq = self._h._out.tolist()
             else:
-                relsq, _ = self._h.cycle_diagnostics(old_phi)
-                self._compute_residual(fine)
-                rsq = self._h.sumsq(fine, "r")
+                self._h.zero_coarse()
+                self.v_cycle(fine)
+                # relative change, old_phi <- v, residual and its norm, all on the device
+                if self._decomp is not None:
+                    self._h.exchange(fine, "v", 1)
+                if self._stock():
+                    relsq, rsq = self._h.cycle_diagnostics(old_phi)
+                else:
+                    relsq, _ = self._h.cycle_diagnostics(old_phi)
+                    self._compute_residual(fine)
+                    rsq = self._h.sumsq(fine, "r")
             relative_error = math.sqrt(g.dx * g.dy * relsq)
             rnorm = math.sqrt(g.dx * g.dy * rsq)
             residual_error = rnorm / self.source_norm if self.source_norm != 0.0 else rnorm

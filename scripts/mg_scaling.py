@@ -22,5 +22,5 @@ e0.record(); a.solve(rtol=0.0); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.num_cycles
 if world > 1:
     t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
-if rank == 0: print(f"MG_SCALING world={world} n={n} split={split} ms_per_cycle={ms:.3f} resid={a.residual_error:.3e}", flush=True)
+if rank == 0: print(f"MG_SCALING world={world} n={n} split={split} ms_per_cycle={ms:.3f} resid={a.residual_error:.3e} graph={a._graph is not None} err={a._graph_error}", flush=True)
 if world > 1: dist.destroy_process_group()
