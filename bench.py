@@ -53,8 +53,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms from the warm-up through the timed region;
-    the median is taken over samples drawing > 300 W (i.e. under load)"""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; the median is taken over the samples
+    that arrived between mark_start() and mark_end() (the timed region)"""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -63,6 +63,13 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.index = index
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -75,7 +82,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -83,23 +90,27 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t0 or 0.0
+        t1 = (self.t1 or time.time()) + 0.03
+        power = []
+        for stamp, ln in self.lines:
             p = [s.strip() for s in ln.split(",")]
             if len(p) < 7:
                 continue
             try:
-                clk, cmax, power = float(p[0]), float(p[1]), float(p[2])
+                clk, cmax, pw = float(p[0]), float(p[1]), float(p[2])
             except ValueError:
                 continue
             mx.append(cmax)
-            if power < 300.0:
-                continue          # idle sample (before / after the loop)
+            if stamp < t0 or stamp > t1:
+                continue          # outside the timed region
             sm.append(clk)
+            power.append(pw)
             for nm, val in zip(names, p[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -233,11 +244,13 @@ def main():
     sim.check_state()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
     e0.record()
     for _ in range(K):
         p.single_step()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     sim.check_state()
