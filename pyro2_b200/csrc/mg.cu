@@ -204,7 +204,10 @@ __global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmo
 constexpr int TB_K = 5;                 // iterations per pass
 constexpr int TB_H = 2 * TB_K;          // halo
 constexpr int TB_R = 8;                 // rows per thread
-constexpr int TB_NW = 8;                // warps per CTA
+#ifndef TB_NW_CFG
+#define TB_NW_CFG 16       // 16 warps = 128 x 64 region, 108 x 44 tile (measured 7% faster than 8 warps / 44 x 44)
+#endif
+constexpr int TB_NW = TB_NW_CFG;        // warps per CTA
 constexpr int TB_RH = TB_R * TB_NW;     // region rows  (64)
 constexpr int TB_RW = 64;               // region columns
 constexpr int TB_TI = TB_RH - 2 * TB_H; // tile rows    (44)
@@ -337,7 +340,7 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     }
 }
 
-__global__ void __launch_bounds__(32 * TB_NW, 2)
+__global__ void __launch_bounds__(32 * TB_NW, (TB_NW <= 8 ? 2 : 1))
 mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
                     SmoothCoef c, int niter)
 {
