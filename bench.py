@@ -206,6 +206,8 @@ def main():
         run_reference(args, rank)
         return
 
+    # keep stdout to the single JSON line: NCCL prints its version banner there at INFO/VERSION level
+    os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
