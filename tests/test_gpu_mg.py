@@ -110,3 +110,42 @@ def test_inhomogeneous_dirichlet_bit_exact():
         d.zero_coarse()
         o.v_cycle(); d.vcycle()
         assert _same(o, d, L, "v")
+
+
+def test_unreachable_tolerance_runs_max_cycles_like_the_reference():
+    """SURVEY.md 7 "solve() tolerance floor": when rtol is below the fp64 residual floor the reference
+    loops to max_cycles = 100 (MG.py:190,653); the drop-in must reproduce that control flow -- same
+    cycle count, same bits after 100 cycles (periodic, singular Poisson as in the incompressible
+    projection)."""
+    import torch
+    import oracle
+    from pyro2_b200.multigrid import MG
+    nx = 128
+    bc = ("periodic",) * 4
+    a = MG.CellCenterMG2d(nx, nx, xl_BC_type="periodic", xr_BC_type="periodic", yl_BC_type="periodic",
+                          yr_BC_type="periodic")
+    x, y = a.x2d.numpy(), a.y2d.numpy()
+    f = np.sin(2 * np.pi * x) * np.cos(6 * np.pi * y) + 0.3 * np.cos(4 * np.pi * x)
+    a.init_zeros()
+    a.init_RHS(f)
+    a.solve(rtol=1.e-30)
+    o = oracle.MG(nx, bc=bc)
+    o.init_zeros()
+    o.init_RHS(f)
+    o.solve(rtol=1.e-30)
+    assert a.num_cycles == o.num_cycles == 100
+    assert np.array_equal(a.get_solution().numpy(), o.get_solution())
+    assert a.residual_error == pytest.approx(o.residual_error, rel=1e-6)
+
+
+@pytest.mark.parametrize("nsmooth", [1, 5, 7, 12])
+def test_blocked_and_per_colour_smoothers_agree_bitwise(nsmooth):
+    """the temporally blocked smoother (odd / even pass counts, partial last pass) against the
+    one-launch-per-colour kernels and the oracle"""
+    o, d = _pair(256, ("dirichlet", "neumann", "periodic", "periodic"), alpha=0.3, beta=0.02, seed=11)
+    o2, e = _pair(256, ("dirichlet", "neumann", "periodic", "periodic"), alpha=0.3, beta=0.02, seed=11)
+    L = o.nlevels - 1
+    e.set_blocking(False)
+    o.smooth(L, nsmooth); d.smooth(L, nsmooth); e.smooth(L, nsmooth)
+    assert _same(o, d, L, "v")
+    assert np.array_equal(d.plane(L, "v").cpu().numpy(), e.plane(L, "v").cpu().numpy())
