@@ -143,9 +143,9 @@ class Simulation(NullSimulation):
     def _read_scratch(self):
         """one D2H copy: wave-speed maxima + status word of the last sweep"""
         if self.decomposition is not None and self.decomposition.size > 1:
-            # global maxima: the wave speeds are positive doubles, the status word a small integer
-            self.decomposition.allreduce_max_(self._scratch[:2].view(torch.float64))
-            self.decomposition.allreduce_max_(self._scratch[3:4])
+            # one all-reduce for everything: positive doubles order like their bit patterns (the same
+            # trick the kernel's atomicMax uses), the status word is a small integer
+            self.decomposition.allreduce_max_(self._scratch[:4])
         words = self._scratch[:4].cpu()
         if self._pending_status:
             self._pending_status = False
