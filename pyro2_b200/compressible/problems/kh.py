@@ -6,6 +6,13 @@ from ...util import msg
 
 DEFAULT_INPUTS = "inputs.kh"
 
+# stock run: 64^2 doubly periodic box (the reference's inputs.kh)
+INPUTS = {"driver.max_steps": 5000, "driver.tmax": 2.0, "compressible.limiter": 2, "compressible.cvisc": 0.1,
+          "io.basename": "kh_", "eos.gamma": 1.4, "mesh.nx": 64, "mesh.ny": 64, "mesh.xmax": 1.0, "mesh.ymax": 1.0,
+          "mesh.xlboundary": "periodic", "mesh.xrboundary": "periodic",
+          "mesh.ylboundary": "periodic", "mesh.yrboundary": "periodic",
+          "kh.rho_1": 1, "kh.u_1": -0.5, "kh.rho_2": 2, "kh.u_2": 0.5}
+
 PROBLEM_PARAMS = {"kh.rho_1": 1.0, "kh.u_1": -1.0, "kh.rho_2": 2.0, "kh.u_2": 1.0,
                   "kh.bulk_velocity": 0.0}
 

@@ -6,6 +6,18 @@ from ...util import msg
 
 DEFAULT_INPUTS = "inputs.quad"
 
+# stock run: 256^2, corner at (0.8, 0.8) (the reference's inputs.quad)
+INPUTS = {"driver.max_steps": 1000, "driver.tmax": 0.8, "compressible.limiter": 2, "compressible.cvisc": 0.1,
+          "io.basename": "quad_unsplit_", "io.dt_out": 0.1, "mesh.nx": 256, "mesh.ny": 256,
+          "mesh.xmax": 1.0, "mesh.ymax": 1.0, "mesh.xlboundary": "outflow", "mesh.xrboundary": "outflow",
+          "mesh.ylboundary": "outflow", "mesh.yrboundary": "outflow",
+          "quadrant.rho1": 1.4, "quadrant.u1": 0.0, "quadrant.v1": 0.0, "quadrant.p1": 1.5,
+          "quadrant.rho2": 0.532258064516129, "quadrant.u2": 1.206045378311055, "quadrant.v2": 0.0, "quadrant.p2": 0.3,
+          "quadrant.rho3": 0.137992831541219, "quadrant.u3": 1.206045378311055, "quadrant.v3": 1.206045378311055,
+          "quadrant.p3": 0.029032258064516,
+          "quadrant.rho4": 0.532258064516129, "quadrant.u4": 0.0, "quadrant.v4": 1.206045378311055, "quadrant.p4": 0.3,
+          "quadrant.cx": 0.8, "quadrant.cy": 0.8}
+
 PROBLEM_PARAMS = {"quadrant.rho1": 1.5, "quadrant.u1": 0.0, "quadrant.v1": 0.0, "quadrant.p1": 1.5,
                   "quadrant.rho2": 0.532258064516129, "quadrant.u2": 1.206045378311055,
                   "quadrant.v2": 0.0, "quadrant.p2": 0.3,

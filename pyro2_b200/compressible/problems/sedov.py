@@ -9,6 +9,13 @@ from ...util import msg
 
 DEFAULT_INPUTS = "inputs.sedov"
 
+# stock run: 128^2 outflow box, blast radius 0.01 (what the reference's inputs.sedov sets)
+INPUTS = {"driver.max_steps": 5000, "driver.tmax": 0.1, "compressible.limiter": 2, "compressible.cvisc": 0.1,
+          "io.basename": "sedov_unsplit_", "io.dt_out": 0.0125, "eos.gamma": 1.4,
+          "mesh.nx": 128, "mesh.ny": 128, "mesh.xmax": 1.0, "mesh.ymax": 1.0,
+          "mesh.xlboundary": "outflow", "mesh.xrboundary": "outflow",
+          "mesh.ylboundary": "outflow", "mesh.yrboundary": "outflow", "sedov.r_init": 0.01}
+
 PROBLEM_PARAMS = {"sedov.r_init": 0.1,   # radius of the initial energy deposit
                   "sedov.nsub": 4}       # sub-samples per direction in partially covered zones
 

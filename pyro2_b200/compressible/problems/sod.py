@@ -6,6 +6,13 @@ from ...util import msg
 
 DEFAULT_INPUTS = "inputs.sod.x"
 
+# stock run: the 128 x 10 tube along x used by the reference's regression suite (inputs.sod.x)
+INPUTS = {"driver.max_steps": 200, "driver.tmax": 0.2, "compressible.limiter": 1,
+          "io.basename": "sod_x_", "io.dt_out": 0.05, "mesh.nx": 128, "mesh.ny": 10,
+          "mesh.xmax": 1.0, "mesh.ymax": 0.05, "mesh.xlboundary": "outflow", "mesh.xrboundary": "outflow",
+          "sod.direction": "x", "sod.dens_left": 1.0, "sod.dens_right": 0.125,
+          "sod.u_left": 0.0, "sod.u_right": 0.0, "sod.p_left": 1.0, "sod.p_right": 0.1}
+
 PROBLEM_PARAMS = {"sod.direction": "x", "sod.dens_left": 1.0, "sod.dens_right": 0.125,
                   "sod.u_left": 0.0, "sod.u_right": 0.0, "sod.p_left": 1.0, "sod.p_right": 0.1}
 

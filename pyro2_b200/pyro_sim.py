@@ -9,6 +9,7 @@ single_step() keeps the reference's order: fill_BC_all -> compute_timestep -> ev
 import importlib
 import os
 
+from . import defaults
 from .util import msg
 from .util import profile_pyro as profile
 from .util.runparams import RuntimeParameters
@@ -33,8 +34,8 @@ class Pyro:
         self.problem_finalize = None
         self.custom_problems = {}
         self.rp = RuntimeParameters()
-        self.rp.load_params(self.pyro_home + "_defaults")
-        self.rp.load_params(self.pyro_home + self.solver_name + "/_defaults")
+        self.rp.load_dict(defaults.GLOBAL)
+        self.rp.load_dict(defaults.SOLVER[self.solver_name])
         self.tc = profile.TimerCollection()
         self.is_initialized = False
 
@@ -57,17 +58,19 @@ class Pyro:
             self.problem_params = problem.PROBLEM_PARAMS
             self.problem_finalize = problem.finalize
             self.problem_source = getattr(problem, "source_terms", None)
-            if inputs_file is None:
-                inputs_file = problem.DEFAULT_INPUTS
+            stock = getattr(problem, "INPUTS", {}) if inputs_file is None else None
 
         for k, v in self.problem_params.items():
             self.rp.set_param(k, v, no_new=False)
 
+        if problem_name not in self.custom_problems and stock is not None:
+            # the problem's stock parameter set (the reference ships these as inputs.* files), applied
+            # like an inputs file: after the problem's own parameters, existing keys only
+            self.rp.load_dict(stock, no_new=True)
+
         if inputs_file is not None:
             if not os.path.isfile(inputs_file):
-                inputs_file = self.pyro_home + self.solver_name + "/problems/" + inputs_file
-                if not os.path.isfile(inputs_file):
-                    msg.fail("ERROR: inputs file does not exist")
+                msg.fail(f"ERROR: inputs file {inputs_file} does not exist")
             self.rp.load_params(inputs_file, no_new=1)
 
         if not self.from_commandline:

@@ -40,39 +40,39 @@ def bc_setup(rp):
     return bnd.BC(**kw), bnd.BC(**kw, odd_reflect_dir="x"), bnd.BC(**kw, odd_reflect_dir="y")
 
 
+def _optional(rp, key, default=None):
+    """a driver parameter that may be absent (or rp itself may be a stub without parameters)"""
+    try:
+        return rp.get_param(key)
+    except (AttributeError, KeyError):
+        return default
+
+
 class NullSimulation:
-    """time-step bookkeeping shared by all solvers"""
+    """time-step bookkeeping shared by all solvers (constructor contract: simulation_null.py:117-191)"""
 
     def __init__(self, solver_name, problem_name, problem_func, rp, *,
                  problem_finalize_func=None, problem_source_func=None,
                  timers=None, data_class=patch.CellCenterData2d):
-        self.n = 0
-        self.dt = -1.e33
-        self.dt_old = -1.e33
-        self.data_class = data_class
-        try:
-            self.tmax = rp.get_param("driver.tmax")
-        except (AttributeError, KeyError):
-            self.tmax = None
-        try:
-            self.max_steps = rp.get_param("driver.max_steps")
-        except (AttributeError, KeyError):
-            self.max_steps = None
-        self.rp = rp
-        self.cc_data = None
-        self.particles = None
-        self.SMALL = 1.e-12
-        self.solver_name = solver_name
-        self.problem_name = problem_name
+        # identity of the run
+        self.solver_name, self.problem_name = solver_name, problem_name
         self.problem_func = problem_func
         self.problem_finalize = problem_finalize_func
         self.problem_source = problem_source_func
-        self.tc = profile.TimerCollection() if timers is None else timers
-        try:
-            self.verbose = self.rp.get_param("driver.verbose")
-        except (AttributeError, KeyError):
-            self.verbose = 0
+        self.rp = rp
+        self.data_class = data_class
+        self.tc = timers if timers is not None else profile.TimerCollection()
+        # step counters and limits
+        self.n = 0
+        self.dt = self.dt_old = -1.e33
+        self.tmax = _optional(rp, "driver.tmax")
+        self.max_steps = _optional(rp, "driver.max_steps")
+        self.verbose = _optional(rp, "driver.verbose", 0)
         self.n_num_out = 0
+        self.SMALL = 1.e-12
+        # state filled in by initialize()
+        self.cc_data = None
+        self.particles = None
         self.cm = "viridis"
         self.decomposition = None   # set by Pyro.initialize_problem(decomposition=...)
 

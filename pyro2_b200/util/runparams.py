@@ -56,6 +56,17 @@ class RuntimeParameters:
                 comment = self.param_comments.get(key, "")
             self.param_comments[key] = comment
 
+    def load_dict(self, table, *, no_new=False):
+        """table: {"section.key": value} or {"section.key": (value, comment)}"""
+        for key, item in table.items():
+            value, comment = item if isinstance(item, tuple) else (item, "")
+            if no_new and key not in self.params:
+                msg.warning(f"warning, key: {key} not defined")
+                continue
+            self.params[key] = value
+            if comment or key not in self.param_comments:
+                self.param_comments[key] = comment
+
     def command_line_params(self, cmd_strings):
         """``section.key=value`` strings override existing parameters (runparams.py:166-187)"""
         for item in cmd_strings:
