@@ -206,8 +206,9 @@ def main():
         run_reference(args, rank)
         return
 
-    # keep stdout to the single JSON line: NCCL prints its version banner there at INFO/VERSION level
-    os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the single JSON line: with NCCL_DEBUG set (VERSION, WARN, INFO ...) NCCL prints its
+    # version banner on stdout
+    os.environ.pop("NCCL_DEBUG", None)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
