@@ -206,9 +206,10 @@ def main():
         run_reference(args, rank)
         return
 
-    # keep stdout to the single JSON line: with NCCL_DEBUG set (VERSION, WARN, INFO ...) NCCL prints its
-    # version banner on stdout
-    os.environ.pop("NCCL_DEBUG", None)
+    # keep stdout to the single JSON line: at NCCL_DEBUG=VERSION or WARN (from the environment or an
+    # nccl.conf) NCCL printf()s its version banner to stdout; an unrecognised level silences it and,
+    # being an environment variable, takes precedence over a conf file
+    os.environ["NCCL_DEBUG"] = "NONE"
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
