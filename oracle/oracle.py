@@ -67,6 +67,10 @@ def lib():
             getattr(L, name).restype = None
         L.orc_mg_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_mg_smooth.restype = None
+        L.orc_mg_set_coeffs.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int * 4)]
+        L.orc_mg_set_coeffs.restype = None
+        L.orc_mg_coef_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_mg_coef_plane.restype = C.POINTER(C.c_double)
         L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
         L.orc_norm.restype = C.c_double
         L.orc_mg_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp]
@@ -179,6 +183,18 @@ class MG:
     def set_bc_values(self, side, vals):
         v = None if vals is None else np.ascontiguousarray(vals, dtype=np.float64)
         lib().orc_mg_set_bc_values(self._h, {"xl": 0, "xr": 1, "yl": 2, "yr": 3}[side], _ptr(v))
+
+    def set_coeffs(self, coeffs, coeffs_bc):
+        """variable-coefficient mode (pyro/multigrid/variable_coeff_MG.py): div(eta grad phi) = f with
+        eta given at the finest level's cell centres, (n+2)^2, and its boundary types"""
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        codes = (C.c_int * 4)(*_bc4(coeffs_bc))
+        lib().orc_mg_set_coeffs(self._h, _ptr(c), C.byref(codes))
+
+    def coef_plane(self, level, which):
+        n = 2 ** (level + 1) + 2
+        idx = {"c": 0, "ex": 1, "ey": 2}[which]
+        return np.ctypeslib.as_array(lib().orc_mg_coef_plane(self._h, level, idx), shape=(n, n))
 
     def init_zeros(self):
         self.plane(self.nlevels - 1, "v")[:] = 0.0

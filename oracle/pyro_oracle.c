@@ -617,6 +617,9 @@ typedef struct {
     double **v, **f, **r; /* per level planes, owned */
     /* inhomogeneous values on the finest level only (MG.py:231-242); NULL = homogeneous */
     double *xl_val, *xr_val, *yl_val, *yr_val;
+    /* variable-coefficient variant (variable_coeff_MG.py): per level the cell-centred coefficient and
+       the edge coefficients eta_x, eta_y (already divided by dx^2, dy^2); NULL = constant coefficients */
+    double **cc, **ex, **ey;
 } orc_mg;
 
 orc_mg *orc_mg_create(int nx, const int bc[4], double alpha, double beta, double xmin, double xmax,
@@ -644,6 +647,10 @@ void orc_mg_destroy(orc_mg *m)
     for (int l = 0; l < m->nlevels; l++) { free(m->v[l]); free(m->f[l]); free(m->r[l]); }
     free(m->v); free(m->f); free(m->r);
     free(m->xl_val); free(m->xr_val); free(m->yl_val); free(m->yr_val);
+    if (m->cc) {
+        for (int l = 0; l < m->nlevels; l++) { free(m->cc[l]); free(m->ex[l]); free(m->ey[l]); }
+        free(m->cc); free(m->ex); free(m->ey);
+    }
     free(m);
 }
 
@@ -666,6 +673,78 @@ void orc_mg_set_bc_values(orc_mg *m, int side, const double *vals)
 static int level_n(int l) { return 2 << l; }
 static double level_dx(const orc_mg *m, int l) { return (m->xmax - m->xmin) / level_n(l); }
 
+/* VarCoeffCCMG2d.__init__ (variable_coeff_MG.py:40-109) + EdgeCoeffs (edge_coeffs.py:1-54):
+ * coeffs = finest-level cell-centred coefficient (n+2)^2 (valid cells used), cbc = its BC codes */
+void orc_mg_set_coeffs(orc_mg *m, const double *coeffs, const int cbc[4])
+{
+    const int L = m->nlevels - 1;
+    if (!m->cc) {
+        m->cc = (double **)calloc(m->nlevels, sizeof(double *));
+        m->ex = (double **)calloc(m->nlevels, sizeof(double *));
+        m->ey = (double **)calloc(m->nlevels, sizeof(double *));
+        for (int l = 0; l < m->nlevels; l++) {
+            size_t np = (size_t)(level_n(l) + 2) * (level_n(l) + 2);
+            m->cc[l] = zalloc(np); m->ex[l] = zalloc(np); m->ey[l] = zalloc(np);
+        }
+    }
+    for (int l = L; l >= 0; l--) {
+        const int n = level_n(l), qy = n + 2;
+        const size_t np = (size_t)qy * qy;
+        double *c = m->cc[l], *ex = m->ex[l], *ey = m->ey[l];
+        const double dx = level_dx(m, l), dy = (m->ymax - m->ymin) / n;
+        memset(c, 0, np * sizeof(double)); memset(ex, 0, np * sizeof(double)); memset(ey, 0, np * sizeof(double));
+        if (l == L) {
+            for (int i = 1; i <= n; i++)
+                for (int j = 1; j <= n; j++) c[IDX(i, j)] = coeffs[IDX(i, j)];
+        } else {
+            /* coeffs_c.v() = f_patch.restrict("coeffs").v()  (patch.py:659-662) */
+            const double *cf = m->cc[l + 1];
+            const int qyf = level_n(l + 1) + 2;
+            for (int i = 1; i <= n; i++)
+                for (int j = 1; j <= n; j++) {
+                    size_t k = (size_t)(2 * i - 1) * qyf + (2 * j - 1);
+                    c[IDX(i, j)] = 0.25 * (cf[k] + cf[k + qyf] + cf[k + 1] + cf[k + qyf + 1]);
+                }
+        }
+        orc_fill_ghost_f64(c, n, n, 1, cbc[0], cbc[1], cbc[2], cbc[3], NULL, NULL, NULL, NULL, dx, dy);
+        if (l == L) {
+            /* EdgeCoeffs(g, eta): region buf = (0, 1) */
+            for (int i = 1; i <= n + 1; i++)
+                for (int j = 1; j <= n + 1; j++) {
+                    ex[IDX(i, j)] = 0.5 * (c[IDX(i - 1, j)] + c[IDX(i, j)]);
+                    ey[IDX(i, j)] = 0.5 * (c[IDX(i, j - 1)] + c[IDX(i, j)]);
+                }
+            for (size_t k = 0; k < np; k++) { ex[k] /= dx * dx; ey[k] /= dy * dy; }
+        } else {
+            /* EdgeCoeffs.restrict() of the finer level's edge coefficients */
+            const double *xf = m->ex[l + 1], *yf = m->ey[l + 1];
+            const int qyf = level_n(l + 1) + 2;
+            const double fdx = level_dx(m, l + 1), fdy = (m->ymax - m->ymin) / level_n(l + 1);
+            for (int i = 1; i <= n + 1; i++)
+                for (int j = 1; j <= n; j++) {
+                    size_t k = (size_t)(2 * i - 1) * qyf + (2 * j - 1);
+                    ex[IDX(i, j)] = 0.5 * (xf[k] + xf[k + 1]);
+                }
+            for (int i = 1; i <= n; i++)
+                for (int j = 1; j <= n + 1; j++) {
+                    size_t k = (size_t)(2 * i - 1) * qyf + (2 * j - 1);
+                    ey[IDX(i, j)] = 0.5 * (yf[k] + yf[k + qyf]);
+                }
+            for (size_t k = 0; k < np; k++) {
+                ex[k] = ex[k] * (fdx * fdx) / (dx * dx);
+                ey[k] = ey[k] * (fdy * fdy) / (dy * dy);
+            }
+        }
+    }
+}
+
+double *orc_mg_coef_plane(orc_mg *m, int level, int which)
+{
+    return which == 0 ? m->cc[level] : which == 1 ? m->ex[level] : m->ey[level];
+}
+
+
+
 static void mg_fill_bc_v(orc_mg *m, int l)
 {
     int n = level_n(l), fin = (l == m->nlevels - 1);
@@ -685,6 +764,23 @@ void orc_mg_smooth(orc_mg *m, int l, int nsmooth)
     const double xcoeff = m->beta / (dx * dx), ycoeff = m->beta / (dy * dy);
     static const int off[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
     mg_fill_bc_v(m, l);
+    if (m->ex) {
+        /* variable_coeff_MG.py:137-171 */
+        const double *ex = m->ex[l], *ey = m->ey[l];
+        for (int it = 0; it < nsmooth; it++)
+            for (int g = 0; g < 4; g++) {
+                int ix = off[g][0], iy = off[g][1];
+                for (int i = 1 + ix; i <= n; i += 2)
+                    for (int j = 1 + iy; j <= n; j += 2) {
+                        double denom = ex[IDX(i + 1, j)] + ex[IDX(i, j)] + ey[IDX(i, j + 1)] + ey[IDX(i, j)];
+                        v[IDX(i, j)] = (-f[IDX(i, j)] + ex[IDX(i + 1, j)] * v[IDX(i + 1, j)] +
+                                        ex[IDX(i, j)] * v[IDX(i - 1, j)] + ey[IDX(i, j + 1)] * v[IDX(i, j + 1)] +
+                                        ey[IDX(i, j)] * v[IDX(i, j - 1)]) / denom;
+                    }
+                if (g == 1 || g == 3) mg_fill_bc_v(m, l);
+            }
+        return;
+    }
     for (int it = 0; it < nsmooth; it++)
         for (int g = 0; g < 4; g++) {
             int ix = off[g][0], iy = off[g][1];
@@ -705,6 +801,19 @@ void orc_mg_residual(orc_mg *m, int l)
     const double *v = m->v[l], *f = m->f[l];
     double *r = m->r[l];
     const double dx = level_dx(m, l), dy = (m->ymax - m->ymin) / n;
+    if (m->ex) {
+        /* variable_coeff_MG.py:199-212: r = f - L_eta phi */
+        const double *ex = m->ex[l], *ey = m->ey[l];
+        for (int i = 1; i <= n; i++)
+            for (int j = 1; j <= n; j++) {
+                double L = ex[IDX(i + 1, j)] * (v[IDX(i + 1, j)] - v[IDX(i, j)]) -
+                           ex[IDX(i, j)] * (v[IDX(i, j)] - v[IDX(i - 1, j)]) +
+                           ey[IDX(i, j + 1)] * (v[IDX(i, j + 1)] - v[IDX(i, j)]) -
+                           ey[IDX(i, j)] * (v[IDX(i, j)] - v[IDX(i, j - 1)]);
+                r[IDX(i, j)] = f[IDX(i, j)] - L;
+            }
+        return;
+    }
 #pragma omp parallel for if (n >= 256)
     for (int i = 1; i <= n; i++)
         for (int j = 1; j <= n; j++)

@@ -6,6 +6,7 @@
 Outputs (small .npz files, committed):
   comp_<problem>.npz   Pyro("compressible") runs: parameters, initial state, per-step dt, final state
   mg_<case>.npz        CellCenterMG2d solves: rhs, solution, cycle count, residual / relative errors
+  mgvc_<case>.npz      VarCoeffCCMG2d solves (the reference's mg_test_vc_* setups): coefficients, rhs, solution
   mesh_bcs.npz         ghost fill of an integer array for every standard BC type (test_patch.py style)
   ref_kats.npz         known answers quoted from the reference's own unit tests / stored outputs
 """
@@ -71,6 +72,43 @@ def mg_case(name, nx, bc, alpha, beta, rhs_kind, rtol, bcfuncs=None):
     print(name, "cycles", a.num_cycles, "resid", a.residual_error)
 
 
+def mgvc_case(name, nx, phibc, cbc, kind, rtol=1.e-11):
+    """the setups of pyro/multigrid/examples/mg_test_vc_{dirichlet,periodic,constant}.py"""
+    import pyro.mesh.boundary as bnd
+    import pyro.multigrid.variable_coeff_MG as VMG
+    from pyro.mesh import patch
+    g = patch.Grid2d(nx, nx, ng=1)
+    d = patch.CellCenterData2d(g)
+    bc_c = bnd.BC(xlb=cbc, xrb=cbc, ylb=cbc, yrb=cbc)
+    d.register_var("c", bc_c)
+    d.create()
+    c = d.get_var("c")
+    x, y = g.x2d, g.y2d
+    pi = np.pi
+    if kind == "dirichlet":        # mg_test_vc_dirichlet.py:40-52
+        c[:, :] = 2.0 + np.cos(2.0 * pi * x) * np.cos(2.0 * pi * y)
+        rhs = -16.0 * pi ** 2 * (np.cos(2 * pi * x) * np.cos(2 * pi * y) + 1) * np.sin(2 * pi * x) * np.sin(2 * pi * y)
+    elif kind == "periodic":       # mg_test_vc_periodic.py:41-54
+        c[:, :] = 2.0 + np.cos(2.0 * pi * x) * np.cos(2.0 * pi * y)
+        rhs = -16.0 * pi ** 2 * (np.cos(2 * pi * x) * np.cos(2 * pi * y) + 1) * np.sin(2 * pi * x) * np.sin(2 * pi * y)
+    else:                          # mg_test_vc_constant.py:33-45: alpha = 1, the constant-coefficient problem
+        c[:, :] = 1.0
+        rhs = -2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2))
+    a = VMG.VarCoeffCCMG2d(nx, nx, xl_BC_type=phibc, yl_BC_type=phibc, xr_BC_type=phibc, yr_BC_type=phibc,
+                           coeffs=c, coeffs_bc=bc_c, verbose=0)
+    a.init_zeros()
+    a.init_RHS(rhs)
+    a.solve(rtol=rtol)
+    r = a.grids[a.nlevels - 1].get_var("r")
+    np.savez_compressed(os.path.join(HERE, f"mgvc_{name}.npz"), nx=nx, bc=np.array((phibc,) * 4),
+                        coeffs_bc=np.array((cbc,) * 4), rtol=rtol, coeffs=np.asarray(c), f=np.asarray(rhs),
+                        v=np.asarray(a.get_solution()), r=np.asarray(r), num_cycles=a.num_cycles,
+                        residual_error=a.residual_error, relative_error=a.relative_error,
+                        source_norm=a.source_norm,
+                        ex_coarse=np.asarray(a.edge_coeffs[2].x), ey_coarse=np.asarray(a.edge_coeffs[2].y))
+    print(name, "cycles", a.num_cycles, "resid", a.residual_error)
+
+
 def mesh_bcs():
     from pyro.mesh import boundary as bnd
     from pyro.mesh import patch
@@ -116,5 +154,9 @@ if __name__ == "__main__":
     mg_case("poisson_mixed_128", 128, ("dirichlet", "dirichlet", "neumann", "neumann"), 0.0, -1.0, "poly", 1.e-11)
     mg_case("poisson_inhom_64", 64, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11,
             bcfuncs=dict(xl_BC=lambda y: y ** 2, xr_BC=lambda y: 1.0 + y, yl_BC=lambda x: x, yr_BC=lambda x: 1.0 + x ** 2))
+    mgvc_case("dirichlet_64", 64, "dirichlet", "neumann", "dirichlet")
+    mgvc_case("periodic_64", 64, "periodic", "periodic", "periodic")
+    mgvc_case("constant_32", 32, "dirichlet", "neumann", "constant")
+    mgvc_case("dirichlet_128", 128, "dirichlet", "neumann", "dirichlet")
     mesh_bcs()
     ref_kats()

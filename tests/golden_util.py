@@ -26,6 +26,10 @@ def load_mg(name):
     return np.load(os.path.join(GOLDEN, f"mg_{name}.npz"))
 
 
+def load_mgvc(name):
+    return np.load(os.path.join(GOLDEN, f"mgvc_{name}.npz"))
+
+
 def var_bcs(rp):
     """BC names per conserved variable (density, energy, x-momentum, y-momentum) following
     pyro/simulation_null.py:71-112: 'reflect' is even, except odd for the momentum normal to it"""

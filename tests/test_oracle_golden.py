@@ -7,7 +7,7 @@ import pytest
 
 import oracle
 from conftest import rel_l2
-from golden_util import load_comp, load_mg, var_bcs
+from golden_util import load_comp, load_mg, load_mgvc, var_bcs
 
 
 def _run_oracle(z, rp, nsteps=None):
@@ -77,6 +77,24 @@ def test_mg_inhomogeneous_dirichlet_matches_reference():
     o.solve(rtol=float(z["rtol"]))
     assert o.num_cycles == int(z["num_cycles"])
     assert np.array_equal(o.get_solution(), z["v"])
+
+
+@pytest.mark.parametrize("name", ["dirichlet_64", "periodic_64", "constant_32", "dirichlet_128"])
+def test_mg_variable_coeff_solve_matches_reference(name):
+    """VarCoeffCCMG2d (variable_coeff_MG.py:24-213) run by the reference on its mg_test_vc_* setups"""
+    z = load_mgvc(name)
+    o = oracle.MG(int(z["nx"]), bc=tuple(str(b) for b in z["bc"]), alpha=0.0, beta=0.0)
+    o.set_coeffs(z["coeffs"], tuple(str(b) for b in z["coeffs_bc"]))
+    assert np.array_equal(o.coef_plane(2, "ex"), z["ex_coarse"])
+    assert np.array_equal(o.coef_plane(2, "ey"), z["ey_coarse"])
+    o.init_zeros()
+    o.init_RHS(z["f"])
+    o.solve(rtol=float(z["rtol"]))
+    assert o.num_cycles == int(z["num_cycles"])
+    assert np.array_equal(o.get_solution(), z["v"])
+    n = int(z["nx"])
+    assert np.array_equal(o.plane(o.nlevels - 1, "r")[1:n + 1, 1:n + 1], z["r"][1:n + 1, 1:n + 1])
+    assert abs(o.residual_error - float(z["residual_error"])) <= 1e-12 * float(z["residual_error"]) + 1e-25
 
 
 def test_mg_convergence_table():

@@ -43,3 +43,32 @@ def test_mg_bit_identical():
     o.init_zeros(); o.init_RHS(np.asarray(f)); o.solve(rtol=1e-12)
     assert o.num_cycles == a.num_cycles
     assert np.array_equal(o.get_solution(), np.asarray(a.get_solution()))
+
+
+def test_mg_variable_coeff_bit_identical():
+    """every level's edge coefficients and the solve of a random-coefficient problem"""
+    ref_shim.load()
+    import pyro.mesh.boundary as bnd
+    import pyro.multigrid.variable_coeff_MG as VMG
+    from pyro.mesh import patch
+    rng = np.random.default_rng(5)
+    nx = 32
+    g = patch.Grid2d(nx, nx, ng=1)
+    d = patch.CellCenterData2d(g)
+    bc_c = bnd.BC(xlb="neumann", xrb="neumann", ylb="periodic", yrb="periodic")
+    d.register_var("c", bc_c)
+    d.create()
+    c = d.get_var("c")
+    c[:, :] = 0.5 + rng.random((nx + 2, nx + 2))
+    a = VMG.VarCoeffCCMG2d(nx, nx, xl_BC_type="dirichlet", xr_BC_type="neumann", yl_BC_type="periodic",
+                           yr_BC_type="periodic", coeffs=c, coeffs_bc=bc_c, verbose=0)
+    f = np.sin(2 * np.pi * a.y2d) * (a.x2d + 0.3)
+    a.init_zeros(); a.init_RHS(f); a.solve(rtol=1e-11)
+    o = oracle.MG(nx, bc=("dirichlet", "neumann", "periodic", "periodic"), alpha=0.0, beta=0.0)
+    o.set_coeffs(np.asarray(c), ("neumann", "neumann", "periodic", "periodic"))
+    for lev in range(o.nlevels):
+        assert np.array_equal(o.coef_plane(lev, "ex"), np.asarray(a.edge_coeffs[lev].x))
+        assert np.array_equal(o.coef_plane(lev, "ey"), np.asarray(a.edge_coeffs[lev].y))
+    o.init_zeros(); o.init_RHS(np.asarray(f)); o.solve(rtol=1e-11)
+    assert o.num_cycles == a.num_cycles
+    assert np.array_equal(o.get_solution(), np.asarray(a.get_solution()))
