@@ -193,12 +193,35 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line.  Libraries loaded below (NCCL's version banner, nvcc
+    during a first build) write to file descriptor 1 behind Python's back, so point fd 1 at stderr for
+    the whole run and keep a private duplicate of the real stdout for the result line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 # --------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -384,7 +407,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
             "roofline": roofline, "cpu_baseline": cpu, "mg": mg,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
