@@ -1,6 +1,12 @@
 // common.cuh -- error plumbing shared by the .cu translation units of libpyro2b200.so
 #pragma once
+#ifdef P2B_EMU_HEADER
+#include P2B_EMU_HEADER   // tests/emu only: the host emulation of the CUDA execution model
+#else
 #include <cuda_runtime.h>
+#define P2B_LAUNCH(kernel, grid, block, smem, stream) kernel<<<grid, block, smem, stream>>>
+#define P2B_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>

@@ -1,0 +1,668 @@
+// mg_kernels.cuh -- device code of the multigrid V-cycle (HP-2): kernels and the per-point arithmetic,
+// no runtime-API calls.  Included by mg.cu (nvcc) and by tests/emu/mg_emu.cpp, which compiles the very
+// same kernels for the host through tests/emu/cuda_emu.h (threads = pthreads, __syncthreads = barrier,
+// shuffles = warp slots) so that they can be checked against the oracle without a GPU.
+//
+// Reference behaviour (pyro2, file:line):
+//   CellCenterMG2d.smooth            pyro/multigrid/MG.py:544-599   red-black Gauss-Seidel, ghost fill
+//                                                                   after each colour
+//   CellCenterMG2d._compute_residual pyro/multigrid/MG.py:529-542
+//   CellCenterData2d.restrict        pyro/mesh/patch.py:640-676     4-cell average
+//   CellCenterData2d.prolong         pyro/mesh/patch.py:678-736     centred (unlimited) slopes
+//   ArrayIndexer.norm                pyro/mesh/array_indexer.py:98-111
+//   VarCoeffCCMG2d.smooth/_compute_residual   pyro/multigrid/variable_coeff_MG.py:112-213
+//   EdgeCoeffs                       pyro/multigrid/edge_coeffs.py:1-54
+#pragma once
+#include <math.h>
+#include <string.h>
+#include <type_traits>
+
+#include "../../include/pyro2b200.h"
+#include "hydro_core.cuh"
+
+namespace pyro {
+
+struct MgLevel {
+    int n, pitch;       // columns (y) of the level and the row pitch
+    double *v, *f, *r;
+    double *w;          // scratch plane: ping-pong target of the temporally blocked smoother
+    double dx, dy;
+    // x-slab decomposition (multi-GPU): this rank owns global rows ioff+1 .. ioff+ni; gx halo rows
+    // are stored beyond each end (row index 1-gx .. ni+gx).  Single GPU / replicated level:
+    // ni = n, ioff = 0, gx = 1, both x sides physical.
+    int ni, ioff, gx;
+    int xlo_phys, xhi_phys;
+};
+
+struct MgBC {
+    int xl, xr, yl, yr;                       // P2B_BC_* codes
+    const double *xlv, *xrv, *ylv, *yrv;      // inhomogeneous values (finest level) or NULL
+};
+
+constexpr int MG_MAX_LEVELS = 24;
+constexpr int MG_NPART = 16384;               // partial sums of the deterministic norms (one per row)
+
+}  // namespace pyro
+
+namespace pyro {
+
+// ---- ghost update fused into the writers --------------------------------------------------------
+// value of the ghost cell generated from interior source value `val` (array_indexer.py:164-274)
+__device__ __forceinline__ double ghost_lo(double val, int code, const double* vals, int idx, double h)
+{
+    if (vals) {
+        if (code == P2B_BC_OUTFLOW) return exact_sub(val, exact_mul(h, vals[idx]));
+        if (code == P2B_BC_REFLECT_ODD) return exact_sub(exact_mul(2.0, vals[idx]), val);
+    }
+    return code == P2B_BC_REFLECT_ODD ? -val : val;
+}
+
+__device__ __forceinline__ double ghost_hi(double val, int code, const double* vals, int idx, double h)
+{
+    if (vals) {
+        if (code == P2B_BC_OUTFLOW) return exact_add(val, exact_mul(h, vals[idx]));
+        if (code == P2B_BC_REFLECT_ODD) return exact_sub(exact_mul(2.0, vals[idx]), val);
+    }
+    return code == P2B_BC_REFLECT_ODD ? -val : val;
+}
+
+// store v(i,j) = val and every ghost cell whose source is (i,j).  x ghosts are functions of the
+// interior value; y ghosts (filled second in the reference, over the full x range) are functions of
+// the already x-filled column, which gives the corner values.
+__device__ __forceinline__ void store_with_ghosts(double* v, int ni, int n, int pitch, int i, int j, double val,
+                                                  const MgBC& b, double dx, double dy, int ioff = 0)
+{
+    v[(long long)i * pitch + j] = val;
+    // x sides with P2B_BC_NONE face another slab: their halo rows come from the neighbour
+    const int sxl = (b.xl == P2B_BC_PERIODIC) ? ni : 1;   // source row of ghost row 0
+    const int sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : ni;   // source row of ghost row ni+1
+    const int syl = (b.yl == P2B_BC_PERIODIC) ? n : 1;
+    const int syh = (b.yr == P2B_BC_PERIODIC) ? 1 : n;
+    const bool lo = (b.xl != P2B_BC_NONE) && (i == sxl), hi = (b.xr != P2B_BC_NONE) && (i == sxh);
+    if (!(lo || hi || j == syl || j == syh)) return;       // interior cell: nothing else to write
+    // after the x fill this value lives in up to three rows: i, 0 (if lo), ni+1 (if hi)
+    double glo = 0.0, ghi = 0.0;
+    if (lo) { glo = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = glo; }
+    if (hi) { ghi = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(ni + 1) * pitch + j] = ghi; }
+    if (j == syl) {
+        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, ioff + i, dy);
+        if (lo) v[0] = ghost_lo(glo, b.yl, b.ylv, ioff, dy);
+        if (hi) v[(long long)(ni + 1) * pitch] = ghost_lo(ghi, b.yl, b.ylv, ioff + ni + 1, dy);
+    }
+    if (j == syh) {
+        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, ioff + i, dy);
+        if (lo) v[n + 1] = ghost_hi(glo, b.yr, b.yrv, ioff, dy);
+        if (hi) v[(long long)(ni + 1) * pitch + n + 1] = ghost_hi(ghi, b.yr, b.yrv, ioff + ni + 1, dy);
+    }
+}
+
+// rden = RN(1/denom), fast = 1 when q = RN(a*rden); r = fma(-denom, q, a); RN(q + r*rden) is the
+// correctly rounded a/denom (Markstein's theorem: holds unless denom's significand is all ones) --
+// three DP instructions and no branch instead of the ~10 + slow path of a true division, with the
+// SAME bits as the reference's division.
+struct SmoothCoef { double alpha, xc, yc, denom, rden; int fast; };
+struct DivConst { double d, rd; int fast; };     // exact a / d for a loop-invariant d (same trick)
+
+__device__ __forceinline__ double div_const(double a, const DivConst& k)
+{
+    if (!k.fast) return exact_div(a, k.d);
+    double q = exact_mul(a, k.rd);
+    double r = __fma_rn(-k.d, q, a);
+    return __fma_rn(r, k.rd, q);
+}
+
+static DivConst make_div_const(double d)
+{
+    DivConst k;
+    k.d = d; k.rd = 1.0 / d;
+    unsigned long long bits;
+    memcpy(&bits, &d, 8);
+    k.fast = ((bits & 0xFFFFFFFFFFFFFULL) != 0xFFFFFFFFFFFFFULL) && isfinite(k.rd) && d != 0.0 &&
+             fabs(d) > 1e-290 && fabs(d) < 1e290;
+    return k;
+}
+
+__device__ __forceinline__ double div_by_denom(double a, const SmoothCoef& c)
+{
+    if (!c.fast) return exact_div(a, c.denom);
+    double q = exact_mul(a, c.rden);
+    double r = __fma_rn(-c.denom, q, a);
+    return __fma_rn(r, c.rden, q);
+}
+
+__device__ __forceinline__ double gs_update(const double* v, const double* f, int pitch, int i, int j,
+                                            const SmoothCoef& c)
+{
+    // MG.py:593-596:  (f + xcoeff*(v[i+1]+v[i-1]) + ycoeff*(v[j+1]+v[j-1])) / (alpha + 2xc + 2yc)
+    const long long k = (long long)i * pitch + j;
+    double sx = exact_add(v[k + pitch], v[k - pitch]);
+    double sy = exact_add(v[k + 1], v[k - 1]);
+    double num = exact_add(exact_add(f[k], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+    return div_by_denom(num, c);
+}
+
+// one colour of one red-black iteration; colour 0 = (i+j) even = the reference's groups (0,0),(1,1)
+__global__ void mg_halfsweep_kernel(MgLevel L, MgBC b, SmoothCoef c, int colour)
+{
+    const int half = L.n >> 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (k >= half || i > L.n) return;
+    const int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+    double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+    store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+}
+
+// whole smooth() for a small level in one CTA (global memory, __syncthreads between colours)
+__global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmooth)
+{
+    const int half = L.n >> 1;
+    const int npts = L.n * half;
+    for (int it = 0; it < 2 * nsmooth; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int i = t / half + 1, k = t % half;
+            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+            double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+        }
+        __syncthreads();
+    }
+}
+
+
+// ---- temporally blocked smoother -------------------------------------------------------------------
+// One CTA owns a TI x TJ tile and loads it with a halo of H = 2*TB_K cells into REGISTERS: a thread
+// holds a 2-column x TB_R-row patch of v and f (lane t <-> columns 2t, 2t+1 of the 64-column
+// region; warp w <-> rows w*TB_R ...).  It then runs up to TB_K full red-black iterations without
+// touching global memory: x-neighbours (rows) come from the thread's own registers or, across
+// warps, from a small double-buffered shared row exchange; y-neighbours from the pair partner or
+// the adjacent lane (shuffle).  Halo cells are updated redundantly; the error of not knowing what is
+// outside the region advances one cell per half-sweep and never reaches the tile.  Ghost cells are
+// not stored at all while blocking: at a domain edge the neighbour is computed from the cell's own
+// value with the same formula fill_BC uses (ghost = g(inner)), which is exactly the value the
+// reference's fill_BC-after-every-colour keeps there; periodic sides wrap on load.  Every point update
+// executes the reference's operations in the reference's order, so the result is bit-identical to
+// nsmooth separate half-sweeps; HBM traffic per pass is ~42 B per cell for 5 iterations instead of
+// 5 x 48 B.  Reads vin, writes vout (another plane): neighbouring CTAs read each other's tiles.
+constexpr int TB_K = 5;                 // iterations per pass
+constexpr int TB_H = 2 * TB_K;          // halo
+constexpr int TB_R = 8;                 // rows per thread
+#ifndef TB_NW_CFG
+#define TB_NW_CFG 16       // 16 warps = 128 x 64 region, 108 x 44 tile (measured 7% faster than 8 warps / 44 x 44)
+#endif
+constexpr int TB_NW = TB_NW_CFG;        // warps per CTA
+constexpr int TB_RH = TB_R * TB_NW;     // region rows  (64)
+constexpr int TB_RW = 64;               // region columns
+constexpr int TB_TI = TB_RH - 2 * TB_H; // tile rows    (44)
+constexpr int TB_TJ = TB_RW - 2 * TB_H; // tile columns (44)
+static_assert(TB_TI % 2 == 0 && TB_TJ % 2 == 0 && TB_R % 2 == 0, "parity bookkeeping needs even tile sizes");
+
+__device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [1, n]
+{
+    int k = (i - 1) % n;
+    return (k < 0 ? k + n : k) + 1;
+}
+
+// EDGE = false: the whole 64 x 64 region lies strictly inside the domain (the case for all but the
+// outermost ring of CTAs): no wrap, no ghost logic, no per-cell predicates.  EDGE = true: the general
+// path.  The choice is block-uniform, so a CTA executes exactly one of the two instruction streams.
+template <bool EDGE>
+__device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
+                                               double* __restrict__ vout, const MgBC& b, const SmoothCoef& c,
+                                               int niter, double (*edge)[TB_NW][2][TB_RW])
+{
+    const int n = L.n, ni = L.ni, P = L.pitch;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd; local index)
+    const int gj0 = J0 - TB_H + 2 * lane;          // first of its two columns (odd)
+    const bool xper = EDGE && (b.xl == P2B_BC_PERIODIC), yper = EDGE && (b.yl == P2B_BC_PERIODIC);
+    // rows that hold real cells: the owned rows plus, on a side facing another slab, the TB_H halo
+    // rows received from it (they are updated redundantly, exactly like the periodic wrap)
+    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? ni : ni + TB_H;
+
+    double v[TB_R][2], f[TB_R][2];
+    // EDGE only: bit r*2+a set = (r, a) is a real interior cell; per-row / per-column edge flags
+    unsigned inmask = 0xffffffffu;
+    unsigned row_lo = 0, row_hi = 0;               // bit r: global row is 1 / n (non-periodic x)
+    bool col_lo[2] = {false, false}, col_hi[2] = {false, false};
+#pragma unroll
+    for (int r = 0; r < TB_R; ++r) {
+        int gi = gi0 + r;
+        int si = xper ? wrap1(gi, ni) : gi;
+        if (EDGE && !xper) {
+            if (L.xlo_phys && gi == 1) row_lo |= 1u << r;
+            if (L.xhi_phys && gi == ni) row_hi |= 1u << r;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int gj = gj0 + a;
+            int sj = yper ? wrap1(gj, n) : gj;
+            bool ok = !EDGE || (si >= rlo && si <= rhi && sj >= 1 && sj <= n);
+            if (!ok) inmask &= ~(1u << (2 * r + a));
+            long long k = (long long)si * P + sj;
+            v[r][a] = ok ? vin[k] : 0.0;
+            f[r][a] = ok ? L.f[k] : 0.0;
+        }
+    }
+    if (EDGE && !yper) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { col_lo[a] = (gj0 + a == 1); col_hi[a] = (gj0 + a == n); }
+    }
+
+    double uph[2] = {0.0, 0.0}, dnh[2] = {0.0, 0.0};   // rows just above / below this thread's strip
+    auto publish = [&](int buf) {
+        *reinterpret_cast<double2*>(&edge[buf][w][0][2 * lane]) = make_double2(v[0][0], v[0][1]);
+        *reinterpret_cast<double2*>(&edge[buf][w][1][2 * lane]) = make_double2(v[TB_R - 1][0], v[TB_R - 1][1]);
+        __syncthreads();
+        if (w > 0) {
+            double2 t = *reinterpret_cast<const double2*>(&edge[buf][w - 1][1][2 * lane]);
+            uph[0] = t.x; uph[1] = t.y;
+        }
+        if (w < TB_NW - 1) {
+            double2 t = *reinterpret_cast<const double2*>(&edge[buf][w + 1][0][2 * lane]);
+            dnh[0] = t.x; dnh[1] = t.y;
+        }
+    };
+    publish(0);
+
+    // one colour of one iteration; the colour is a compile-time constant so that every register
+    // array index is static.  colour 0 = (i + j) even; gi0 and gj0 are both odd (tile origins are
+    // 1 + even multiples, H even, strip offsets even), so cell (r, a) has colour (r + a) & 1.
+    auto half_sweep = [&](auto colour_tag, int buf) {
+        constexpr int colour = decltype(colour_tag)::value;
+        double nv[TB_R];
+#pragma unroll
+        for (int r = 0; r < TB_R; ++r) {
+            constexpr int dummy = 0; (void)dummy;
+            const int a = (r + colour) & 1;          // active column of the pair in this row (static)
+            const double self = v[r][a];
+            double up = (r == 0) ? uph[a] : v[r == 0 ? 0 : r - 1][a];
+            double dn = (r == TB_R - 1) ? dnh[a] : v[r == TB_R - 1 ? r : r + 1][a];
+            // y-neighbours: the pair partner, or the adjacent lane's facing column
+            double lf = (a == 0) ? __shfl_up_sync(0xffffffffu, v[r][1], 1) : v[r][0];
+            double rt = (a == 0) ? v[r][1] : __shfl_down_sync(0xffffffffu, v[r][0], 1);
+            if (EDGE) {
+                // domain edges: the ghost value fill_BC would hold, from the cell's own current value
+                const int gi = gi0 + r, gj = gj0 + a;
+                if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
+                if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
+                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, L.ioff + gi, L.dy);
+                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, L.ioff + gi, L.dy);
+            }
+            double sx = exact_add(dn, up);
+            double sy = exact_add(rt, lf);
+            double num = exact_add(exact_add(f[r][a], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+            nv[r] = div_by_denom(num, c);
+        }
+#pragma unroll
+        for (int r = 0; r < TB_R; ++r) {
+            const int a = (r + colour) & 1;
+            if (!EDGE || ((inmask >> (2 * r + a)) & 1u)) v[r][a] = nv[r];
+        }
+        publish(buf);
+    };
+
+    for (int it = 0; it < niter; ++it) {
+        half_sweep(std::integral_constant<int, 0>{}, 1);
+        half_sweep(std::integral_constant<int, 1>{}, 0);
+    }
+
+    // store the tile (and, on the EDGE path, the ghost cells its boundary cells generate)
+#pragma unroll
+    for (int r = 0; r < TB_R; ++r) {
+        int gi = gi0 + r;
+        if (gi < I0 || gi >= I0 + TB_TI || gi > ni) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int gj = gj0 + a;
+            if (gj < J0 || gj >= J0 + TB_TJ || gj > n) continue;
+            if (EDGE) store_with_ghosts(vout, ni, n, P, gi, gj, v[r][a], b, L.dx, L.dy, L.ioff);
+            else vout[(long long)gi * P + gj] = v[r][a];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * TB_NW, (TB_NW <= 8 ? 2 : 1))
+mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
+                    SmoothCoef c, int niter)
+{
+    __shared__ __align__(16) double edge[2][TB_NW][2][TB_RW];   // [buffer][warp][first/last row][column]
+    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? L.ni : L.ni + TB_H;
+    const bool interior = (I0 - TB_H >= rlo) && (I0 - TB_H + TB_RH - 1 <= rhi) &&
+                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
+    if (interior) smooth_tb_body<false>(L, vin, vout, b, c, niter, edge);
+    else smooth_tb_body<true>(L, vin, vout, b, c, niter, edge);
+}
+
+
+struct ResidCoef { double alpha, beta; DivConst dx2, dy2; };
+
+__device__ __forceinline__ double residual_at(const MgLevel& L, long long k, const ResidCoef& rc)
+{
+    // MG.py:540-542:  f - alpha v + beta ((v[i-1] + v[i+1] - 2 v)/dx**2 + (v[j-1] + v[j+1] - 2 v)/dy**2)
+    const double* v = L.v;
+    double v2 = exact_mul(2.0, v[k]);
+    double lx = div_const(exact_sub(exact_add(v[k - L.pitch], v[k + L.pitch]), v2), rc.dx2);
+    double ly = div_const(exact_sub(exact_add(v[k - 1], v[k + 1]), v2), rc.dy2);
+    return exact_add(exact_sub(L.f[k], exact_mul(rc.alpha, v[k])), exact_mul(rc.beta, exact_add(lx, ly)));
+}
+
+// ---- the coarse part of the V-cycle in ONE launch ---------------------------------------------------
+// Levels up to 64^2 do not have enough points to fill the chip and every kernel on them is pure
+// launch + memory latency (ncu r1: 26 us per smooth(), ~0.35 ms per V-cycle in total).  One CTA
+// keeps v, f, r of all levels 0..top (<= 64^2: 140 KB) in shared memory and runs the whole
+// sub-V-cycle there: smooth / residual / restrict on the way down, the bottom solve, prolong +
+// correct + smooth on the way up -- same device functions, same operation order, same bits.
+constexpr int MG_COARSE_TOP_N = 64;
+constexpr int MG_COARSE_LEVELS = 6;     // 2, 4, 8, 16, 32, 64
+
+struct CoarseTable {
+    MgLevel g[MG_COARSE_LEVELS];        // the levels' global planes
+    int top;                            // highest level handled here
+    int nsmooth, nsmooth_bottom;
+    ResidCoef rcoef[MG_COARSE_LEVELS];
+    SmoothCoef coef[MG_COARSE_LEVELS];
+    MgBC bc_top, bc_coarse;             // bc_top carries the inhomogeneous values when top is the finest
+};
+
+__device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, const SmoothCoef& c, int nsmooth)
+{
+    const int n = L.n, half = n >> 1, npts = n * half;
+    const int ls = __ffs(n) - 1, hs = ls - 1;   // n and half are powers of two: shifts instead of divisions
+    // fill_BC("v") at the start of smooth() (MG.py:565)
+    for (int t = threadIdx.x; t < 4 * n; t += blockDim.x) {
+        int side = t >> ls, q = (t & (n - 1)) + 1;
+        int i = side == 0 ? 1 : side == 1 ? n : q;
+        int j = side == 2 ? 1 : side == 3 ? n : q;
+        store_with_ghosts(L.v, n, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+    }
+    __syncthreads();
+    for (int it = 0; it < 2 * nsmooth; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int i = (t >> hs) + 1, k = t & (half - 1);
+            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+            double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            store_with_ghosts(L.v, n, n, L.pitch, i, j, val, b, L.dx, L.dy);
+        }
+        __syncthreads();
+    }
+}
+
+
+#ifndef MG_COARSE_THREADS
+#define MG_COARSE_THREADS 1024
+#endif
+
+__global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(CoarseTable T)
+{
+    P2B_DYN_SMEM(double, sm);
+    MgLevel S[MG_COARSE_LEVELS];
+    {
+        double* p = sm;
+        for (int l = 0; l <= T.top; ++l) {
+            S[l] = T.g[l];
+            const int q = S[l].n + 2;
+            S[l].pitch = (q + 1) & ~1;
+            const long long plane = (long long)q * S[l].pitch;
+            S[l].v = p; p += plane;
+            S[l].f = p; p += plane;
+            S[l].r = p; p += plane;
+        }
+    }
+    // load: v and f of the top level come from global (v is the current iterate there: zero on a
+    // coarse top level, the solution when the top level is the finest); everything below starts at 0
+    for (int l = 0; l <= T.top; ++l) {
+        const int q = S[l].n + 2;
+        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
+            int i = t / q, j = t % q;
+            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
+            S[l].v[ks] = (l == T.top) ? T.g[l].v[kg] : 0.0;
+            S[l].f[ks] = (l == T.top) ? T.g[l].f[kg] : 0.0;
+            S[l].r[ks] = T.g[l].r[kg];
+        }
+    }
+    __syncthreads();
+
+    for (int l = T.top; l >= 1; --l) {
+        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
+        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+        const int n = S[l].n;
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+            long long k = (long long)(t / n + 1) * S[l].pitch + (t % n + 1);
+            S[l].r[k] = residual_at(S[l], k, T.rcoef[l]);
+        }
+        __syncthreads();
+        const int nc = S[l - 1].n;
+        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
+            int ic = t / nc + 1, jc = t % nc + 1;
+            const double* r = S[l].r;
+            long long k = (long long)(2 * ic - 1) * S[l].pitch + (2 * jc - 1);
+            double sum = exact_add(exact_add(exact_add(r[k], r[k + S[l].pitch]), r[k + 1]), r[k + S[l].pitch + 1]);
+            S[l - 1].f[(long long)ic * S[l - 1].pitch + jc] = exact_mul(0.25, sum);
+        }
+        __syncthreads();
+    }
+    cta_smooth(S[0], (T.top == 0) ? T.bc_top : T.bc_coarse, T.coef[0], T.nsmooth_bottom);
+    for (int l = 1; l <= T.top; ++l) {
+        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
+        const MgLevel &F = S[l], &Cs = S[l - 1];
+        const int nc = Cs.n;
+        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
+            int ic = t / nc + 1, jc = t % nc + 1;
+            const double* c = Cs.v;
+            const long long kc = (long long)ic * Cs.pitch + jc;
+            double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
+            double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+            double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my), c0 = c[kc];
+            const int i = 2 * ic - 1, j = 2 * jc - 1, P = F.pitch;
+            double* v = F.v;
+            store_with_ghosts(v, F.n, F.n, P, i, j, exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
+            store_with_ghosts(v, F.n, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
+        }
+        __syncthreads();
+        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+    }
+
+    // store everything back (coarse planes stay observable through grids[level], like the reference's)
+    for (int l = 0; l <= T.top; ++l) {
+        const int q = S[l].n + 2;
+        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
+            int i = t / q, j = t % q;
+            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
+            T.g[l].v[kg] = S[l].v[ks];
+            T.g[l].f[kg] = S[l].f[ks];
+            T.g[l].r[kg] = S[l].r[ks];
+        }
+    }
+}
+
+// full ghost fill of v from the interior (used once per smooth() like MG.py:565)
+__global__ void mg_fill_kernel(MgLevel L, MgBC b)
+{
+    // every interior edge cell re-stores itself with its ghosts
+    const int n = L.n;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 4 * n; t += gridDim.x * blockDim.x) {
+        int side = t / n, s = t % n + 1;
+        int i, j;
+        if (side == 0) { i = 1; j = s; } else if (side == 1) { i = n; j = s; }
+        else if (side == 2) { i = s; j = 1; } else { i = s; j = n; }
+        // corners are visited twice with identical results
+        store_with_ghosts(L.v, n, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
+    }
+}
+
+__global__ void mg_residual_kernel(MgLevel L, ResidCoef rc)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > L.ni || j > L.n) return;
+    const long long k = (long long)i * L.pitch + j;
+    L.r[k] = residual_at(L, k, rc);
+}
+
+// fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732).  crow: row offset of this
+// rank's rows inside the coarse array (non-zero when a slab level restricts into a replicated one)
+__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs, int crow)
+{
+    const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (ic > F.ni / 2 || jc > Cs.n) return;
+    const long long k = (long long)(2 * ic - 1) * F.pitch + (2 * jc - 1);
+    const double* r = F.r;
+    double s = exact_add(exact_add(exact_add(r[k], r[k + F.pitch]), r[k + 1]), r[k + F.pitch + 1]);
+    Cs.f[(long long)(ic + crow) * Cs.pitch + jc] = exact_mul(0.25, s);
+}
+
+// v_fine += prolong(v_coarse), ghosts refreshed (patch.py:716-734, MG.py:745-751)
+__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b, int crow)
+{
+    const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (ic > F.ni / 2 || jc > Cs.n) return;
+    const double* c = Cs.v;
+    const long long kc = (long long)(ic + crow) * Cs.pitch + jc;
+    double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
+    double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+    double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my);
+    double c0 = c[kc];
+    const int i = 2 * ic - 1, j = 2 * jc - 1;
+    double e00 = exact_sub(exact_sub(c0, qx), qy);
+    double e10 = exact_sub(exact_add(c0, qx), qy);
+    double e01 = exact_add(exact_sub(c0, qx), qy);
+    double e11 = exact_add(exact_add(c0, qx), qy);
+    double* v = F.v;
+    const int P = F.pitch;
+    store_with_ghosts(v, F.ni, F.n, P, i, j, exact_add(v[(long long)i * P + j], e00), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], e10), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], e01), b, F.dx, F.dy, F.ioff);
+    store_with_ghosts(v, F.ni, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], e11), b, F.dx, F.dy, F.ioff);
+}
+
+// ---- deterministic reductions over the valid region ------------------------------------------------
+// One CTA per row (>= one CTA per MG_NPART-th of the rows), a thread owns up to RED_PER_THREAD cells
+// of the row and issues all of its loads before any arithmetic (memory-level parallelism: the first
+// version looped cell by cell and ran at 23% of HBM bandwidth, ncu r1).  Fixed summation order:
+// per-thread sequential, block tree, then one CTA sums the per-row partials in index order.
+constexpr int RED_THREADS = 256;
+constexpr int RED_PER_THREAD = 4;           // cells a thread keeps in flight per trip
+
+__device__ __forceinline__ double block_sum(double s, double* sh)
+{
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// mode 0: sum a^2
+__global__ void __launch_bounds__(RED_THREADS) mg_sumsq_partial_kernel(const double* __restrict__ a, int ni, int n, int pitch,
+                                                                       double* __restrict__ part)
+{
+    __shared__ double sh[RED_THREADS];
+    double s = 0.0;
+    for (int i = 1 + blockIdx.x; i <= ni; i += gridDim.x) {
+        const double* row = a + (long long)i * pitch;
+        for (int j0 = 1 + threadIdx.x; j0 <= n; j0 += RED_THREADS * RED_PER_THREAD) {
+            double x[RED_PER_THREAD];
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) {
+                int j = j0 + u * RED_THREADS;
+                x[u] = (j <= n) ? row[j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) s += x[u] * x[u];
+        }
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+__global__ void mg_sumsq_final_kernel(const double* part, int npart, double* out)
+{
+    __shared__ double sh[RED_THREADS];
+    double s = 0.0;
+    for (int t = threadIdx.x; t < npart; t += RED_THREADS) s += part[t];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) *out = s;
+}
+
+struct MgZeroTable { double* v[MG_MAX_LEVELS]; long long count[MG_MAX_LEVELS]; int nlev; };
+
+__global__ void mg_zero_kernel(MgZeroTable t)
+{
+    for (int l = 0; l < t.nlev; ++l)
+        for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < t.count[l];
+             k += (long long)gridDim.x * blockDim.x)
+            t.v[l][k] = 0.0;
+}
+
+// solve()'s per-cycle bookkeeping in one pass over the finest level (MG.py:668-686): relative change
+// against old_phi (old_phi <- v), residual r (stored), partial sums of both squares.  Same fixed
+// two-stage summation as mg_sumsq_*; part[0..nb) relative change, part[MG_NPART..) residual.
+__global__ void __launch_bounds__(RED_THREADS)
+mg_diag_partial_kernel(MgLevel L, double* __restrict__ old_phi, ResidCoef rc, double* __restrict__ part)
+{
+    __shared__ double sh[RED_THREADS];
+    double s_rel = 0.0, s_res = 0.0;
+    const int n = L.n, P = L.pitch;
+    const double* __restrict__ v = L.v;
+    const double* __restrict__ f = L.f;
+    double* __restrict__ r = L.r;
+    for (int i = 1 + blockIdx.x; i <= L.ni; i += gridDim.x) {
+        const long long base = (long long)i * P;
+        for (int j0 = 1 + threadIdx.x; j0 <= n; j0 += RED_THREADS * RED_PER_THREAD) {
+            double c[RED_PER_THREAD], up[RED_PER_THREAD], dn[RED_PER_THREAD], lf[RED_PER_THREAD],
+                rt[RED_PER_THREAD], ff[RED_PER_THREAD], oo[RED_PER_THREAD];
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) {
+                int j = j0 + u * RED_THREADS;
+                bool ok = j <= n;
+                long long k = base + (ok ? j : 1);
+                c[u] = v[k]; up[u] = v[k - P]; dn[u] = v[k + P]; lf[u] = v[k - 1]; rt[u] = v[k + 1];
+                ff[u] = f[k]; oo[u] = old_phi[k];
+            }
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) {
+                int j = j0 + u * RED_THREADS;
+                if (j > n) continue;
+                long long k = base + j;
+                old_phi[k] = c[u];
+                double d = (c[u] - oo[u]) / (c[u] + 1.e-16);
+                s_rel += d * d;
+                // MG.py:540-542
+                double v2 = exact_mul(2.0, c[u]);
+                double lx = div_const(exact_sub(exact_add(up[u], dn[u]), v2), rc.dx2);
+                double ly = div_const(exact_sub(exact_add(lf[u], rt[u]), v2), rc.dy2);
+                double res = exact_add(exact_sub(ff[u], exact_mul(rc.alpha, c[u])), exact_mul(rc.beta, exact_add(lx, ly)));
+                r[k] = res;
+                s_res += res * res;
+            }
+        }
+    }
+    s_rel = block_sum(s_rel, sh);
+    s_res = block_sum(s_res, sh);
+    if (threadIdx.x == 0) { part[blockIdx.x] = s_rel; part[MG_NPART + blockIdx.x] = s_res; }
+}
+
+__global__ void mg_diag_final_kernel(const double* part, int npart, double* out)
+{
+    __shared__ double sh[RED_THREADS];
+    double a = 0.0, b = 0.0;
+    for (int t = threadIdx.x; t < npart; t += RED_THREADS) { a += part[t]; b += part[MG_NPART + t]; }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+}  // namespace pyro

@@ -1,0 +1,141 @@
+// cuda_emu.h -- a small host emulation of the CUDA execution model.  TEST INFRASTRUCTURE ONLY.
+//
+// tests/emu/mg_emu.cpp compiles pyro2_b200/csrc/mg.cu (kernels AND host orchestration, unchanged) with
+// g++ and -DP2B_EMU_HEADER=<this file>: common.cuh then includes this header instead of
+// <cuda_runtime.h>.  "Device" memory is host memory; a launch runs the CTAs one after the other;
+// kernels that synchronise (registered with emu::threaded) get one FIBER (ucontext) per CUDA thread,
+// scheduled round-robin inside the calling OS thread: __syncthreads and the warp shuffles are yield
+// points that a fiber leaves only when its whole CTA / warp has arrived; every other kernel simply
+// runs its threads one after the other.  The point is to check indexing, halo / ghost logic and bit-exactness of
+// the multigrid kernels against the oracle on the GPU-less build box.  The product never loads it.
+#pragma once
+#include <math.h>
+#include <ucontext.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <set>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct emu_uint3 { unsigned x, y, z; };
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+extern emu_uint3 threadIdx, blockIdx;   // of the running fiber (saved / restored by the scheduler)
+extern dim3 blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static            // CTAs run one at a time, so one static copy is the CTA's copy
+#define __align__(n) __attribute__((aligned(n)))
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum { cudaMemcpyDeviceToDevice = 3 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int, cudaStream_t)
+{
+    for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+template <class K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+
+namespace emu {
+
+struct Cta {
+    int nthreads = 0;
+    int live = 0;                      // fibers that have not returned yet
+    int all_count = 0;                 // arrivals at the current __syncthreads
+    unsigned all_gen = 0;
+    std::vector<int> warp_count;       // arrivals at the current exchange, per warp
+    std::vector<unsigned> warp_gen;
+    std::vector<double> slot;          // [warp][2][32]
+    std::vector<int> flip;             // exchange-buffer parity per thread
+};
+
+extern Cta* cta;                       // null in sequential mode
+extern int lin_tid;                    // linear thread index of the running fiber
+extern void* dyn_smem;                 // dynamic shared memory of the running CTA
+void yield();                          // switch to the next fiber of the CTA
+
+std::set<const void*>& threaded_set();
+inline void threaded(const void* k) { threaded_set().insert(k); }
+
+void run(const void* kernel, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+
+[[noreturn]] inline void need_threads(const char* what)
+{
+    fprintf(stderr, "cuda_emu: %s used by a kernel that was not registered with emu::threaded()\n", what);
+    abort();
+}
+
+// warp-wide exchange: every lane deposits its value, waits until the whole warp has, then reads.  Two
+// alternating buffers: a lane can be at most one exchange ahead of the slowest lane of its warp.
+inline double exchange(double v, int from_lane)
+{
+    if (!cta) need_threads("warp shuffle");
+    Cta* c = cta;
+    const int tid = lin_tid, w = tid >> 5, lane = tid & 31;
+    const int width = (c->nthreads - w * 32) < 32 ? (c->nthreads - w * 32) : 32;
+    const int b = c->flip[tid];
+    c->flip[tid] ^= 1;
+    double* s = &c->slot[(size_t)(w * 2 + b) * 32];
+    s[lane] = v;
+    const unsigned gen = c->warp_gen[w];
+    if (++c->warp_count[w] == width) { c->warp_count[w] = 0; ++c->warp_gen[w]; }
+    while (c->warp_gen[w] == gen) yield();
+    return (from_lane < 0 || from_lane >= width) ? v : s[from_lane];
+}
+
+template <class... P>
+struct Bound {
+    void (*k)(P...);
+    dim3 g, b;
+    size_t s;
+    template <class... A>
+    void operator()(A&&... a) const
+    {
+        auto kk = k;
+        run((const void*)k, g, b, s, [&] { kk(a...); });
+    }
+};
+
+template <class... P>
+Bound<P...> bind_launch(void (*k)(P...), dim3 g, dim3 b, size_t s) { return Bound<P...>{k, g, b, s}; }
+
+}  // namespace emu
+
+inline void __syncthreads()
+{
+    emu::Cta* c = emu::cta;
+    if (!c) emu::need_threads("__syncthreads");
+    const unsigned gen = c->all_gen;
+    if (++c->all_count == c->live) { c->all_count = 0; ++c->all_gen; }
+    while (c->all_gen == gen) emu::yield();
+}
+inline double __shfl_up_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) - d); }
+inline double __shfl_down_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) + d); }
+
+#define P2B_LAUNCH(kernel, grid, block, smem, stream) ::emu::bind_launch(kernel, grid, block, smem)
+#define P2B_DYN_SMEM(type, name) type* name = (type*)::emu::dyn_smem
