@@ -159,6 +159,20 @@ int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out_dev, void* stream)
  * old_phi is a caller-owned (n+2) x pitch buffer */
 int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out_dev, void* stream);
 
+/* ---- variable coefficients: VarCoeffCCMG2d (pyro/multigrid/variable_coeff_MG.py:24-213) with EdgeCoeffs
+ * (pyro/multigrid/edge_coeffs.py:1-54): div(eta grad phi) = f.  p2b_mg_set_coeffs does what the
+ * reference's constructor does (:57-109), on the device: eta (finest level, (n+2) rows of coeffs_pitch
+ * doubles, valid cells read; coeffs_bc = its boundary codes) is restricted level by level and ghost
+ * filled, the finest level's edge coefficients eta_x[i,j] = eta_{i-1/2,j}/dx^2, eta_y[i,j] =
+ * eta_{i,j-1/2}/dy^2 are formed and restricted down.  The planes live in caller-owned memory of
+ * p2b_mg_coeff_workspace_bytes (16-byte aligned).  Afterwards smooth / residual / vcycle /
+ * cycle_diagnostics apply the variable-coefficient operator (:112-213), bit-identical to the reference.
+ * Single-GPU hierarchies only.  p2b_mg_coeff_ptr: which = 0 eta, 1 eta_x, 2 eta_y (level pitch). */
+long long p2b_mg_coeff_workspace_bytes(p2b_mg* m);
+int p2b_mg_set_coeffs(p2b_mg* m, void* device_mem, long long bytes, const double* coeffs, int coeffs_pitch,
+                      const int* coeffs_bc, void* stream);
+void* p2b_mg_coeff_ptr(p2b_mg* m, int level, int which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,9 @@ struct p2b_mg {
     int no_blocking;                          // debugging / A-B switch: 1 = plain half-sweep kernels
     int rank, size;                           // x-slab decomposition (size 1 = single GPU)
     int split_level;                          // levels >= split_level are slabs when size > 1
+    // variable-coefficient mode (VarCoeffCCMG2d): per level the cell-centred eta and the two edge planes
+    int varcoef;
+    double *cc[pyro::MG_MAX_LEVELS], *ex[pyro::MG_MAX_LEVELS], *ey[pyro::MG_MAX_LEVELS];
 };
 
 namespace pyro {
@@ -81,6 +84,13 @@ static SmoothCoef level_coef(const p2b_mg* m, const MgLevel& L)
     return c;
 }
 
+static VcEdges level_edges(const p2b_mg* m, int level)
+{
+    VcEdges E;
+    E.ex = m->ex[level]; E.ey = m->ey[level];
+    return E;
+}
+
 constexpr int MG_SMALL_N = 64;   // levels up to 64^2 are smoothed by one CTA in one launch
 constexpr int MG_TB_MIN_N = 128;  // from here up the temporally blocked kernel is used
 
@@ -89,6 +99,24 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
     const MgLevel& L = m->lev[level];
     MgBC b = level_bc(m, level);
     SmoothCoef c = level_coef(m, L);
+    if (m->varcoef) {
+        // variable_coeff_MG.py:112-171
+        const VcEdges E = level_edges(m, level);
+        if (fill_first) P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, st)(L, b);
+        if (L.n <= MG_SMALL_N) {
+            int threads = L.n * (L.n / 2);
+            threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+            P2B_LAUNCH(mg_vc_smooth_small_kernel, 1, threads, 0, st)(L, b, E, nsmooth);
+        } else {
+            dim3 blk(64, 4);
+            dim3 grd((L.n / 2 + blk.x - 1) / blk.x, (L.n + blk.y - 1) / blk.y);
+            for (int it = 0; it < nsmooth; ++it) {
+                P2B_LAUNCH(mg_vc_halfsweep_kernel, grd, blk, 0, st)(L, b, E, 0);
+                P2B_LAUNCH(mg_vc_halfsweep_kernel, grd, blk, 0, st)(L, b, E, 1);
+            }
+        }
+        return P2B_OK;
+    }
     if (L.n <= MG_SMALL_N) {
         if (fill_first) P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, st)(L, b);
         int threads = L.n * (L.n / 2);
@@ -140,6 +168,10 @@ static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
     const MgLevel& L = m->lev[level];
     dim3 blk(64, 4);
     dim3 grd((L.n + blk.x - 1) / blk.x, (L.ni + blk.y - 1) / blk.y);
+    if (m->varcoef) {
+        P2B_LAUNCH(mg_vc_residual_kernel, grd, blk, 0, st)(L, level_edges(m, level));
+        return;
+    }
     P2B_LAUNCH(mg_residual_kernel, grd, blk, 0, st)(L, level_rcoef(m, L));
 }
 
@@ -194,7 +226,7 @@ static void coarse_vcycle_impl(p2b_mg* m, int top, cudaStream_t st)
 static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     // MG.py:699-778
-    if (!m->no_blocking && level <= coarse_top(m)) {
+    if (!m->no_blocking && !m->varcoef && level <= coarse_top(m)) {
         coarse_vcycle_impl(m, level, st);
         return;
     }
@@ -428,6 +460,7 @@ int p2b_mg_tb_pass(p2b_mg* m, int level, int src, int dst, int niter, void* stre
     P2B_REQUIRE((src == 0 && dst == 3) || (src == 3 && dst == 0), "src/dst must be v->w or w->v");
     P2B_REQUIRE(niter >= 1 && niter <= TB_K, "niter out of range");
     P2B_REQUIRE(m->lev[level].n >= MG_TB_MIN_N, "level too small for the blocked smoother");
+    P2B_REQUIRE(!m->varcoef, "the blocked smoother is constant-coefficient only");
     const MgLevel& L = m->lev[level];
     tb_pass_impl(m, level, src == 0 ? L.v : L.w, dst == 0 ? L.v : L.w, niter, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
@@ -479,10 +512,92 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stre
     const int lf = m->nlevels - 1;
     const MgLevel& L = m->lev[lf];
     int blocks = L.ni < MG_NPART ? L.ni : MG_NPART;
-    P2B_LAUNCH(mg_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, old_phi, level_rcoef(m, L), m->partials);
+    if (m->varcoef)
+        P2B_LAUNCH(mg_vc_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, level_edges(m, lf), old_phi, m->partials);
+    else
+        P2B_LAUNCH(mg_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, old_phi, level_rcoef(m, L), m->partials);
     P2B_LAUNCH(mg_diag_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
+}
+
+// ---- variable coefficients: VarCoeffCCMG2d.__init__ (variable_coeff_MG.py:40-109) --------------------
+// three planes (eta at cell centres, eta_x, eta_y) per level, each the size of one of the level's planes
+long long p2b_mg_coeff_workspace_bytes(p2b_mg* m)
+{
+    if (!m) return 0;
+    long long n = 0;
+    for (int l = 0; l < m->nlevels; ++l) n += 3LL * (m->lev[l].n + 2) * m->lev[l].pitch;
+    return n * 8;
+}
+
+// coeffs: eta on the finest level, (n+2) rows of coeffs_pitch doubles (valid cells are read);
+// coeffs_bc: its four boundary types.  Builds, on the device, what the reference's constructor builds:
+// the ghost-filled eta of every level (restricted level by level), the finest level's edge
+// coefficients and their restrictions.  From here on smooth / residual / V-cycle / diagnostics use
+// the variable-coefficient operator (alpha and beta are ignored, as in the reference).
+int p2b_mg_set_coeffs(p2b_mg* m, void* mem, long long bytes, const double* coeffs, int coeffs_pitch,
+                      const int* coeffs_bc, void* stream)
+{
+    P2B_REQUIRE(m && m->base, "hierarchy not bound");
+    P2B_REQUIRE(mem && coeffs && coeffs_bc, "null pointer");
+    P2B_REQUIRE(m->size == 1, "variable coefficients are not available on a decomposed hierarchy");
+    P2B_REQUIRE(bytes >= p2b_mg_coeff_workspace_bytes(m), "coefficient workspace too small");
+    P2B_REQUIRE(((uintptr_t)mem % 16) == 0, "workspace must be 16-byte aligned");
+    P2B_REQUIRE(coeffs_pitch >= m->lev[m->nlevels - 1].n + 2, "coeffs_pitch too small");
+    for (int s = 0; s < 4; ++s) P2B_REQUIRE(coeffs_bc[s] >= P2B_BC_OUTFLOW && coeffs_bc[s] <= P2B_BC_PERIODIC, "bad coefficient bc");
+    cudaStream_t st = (cudaStream_t)stream;
+    P2B_CUDA_CHECK(cudaMemsetAsync(mem, 0, (size_t)p2b_mg_coeff_workspace_bytes(m), st));
+    double* p = (double*)mem;
+    for (int l = 0; l < m->nlevels; ++l) {
+        const long long plane = (long long)(m->lev[l].n + 2) * m->lev[l].pitch;
+        m->cc[l] = p; p += plane;
+        m->ex[l] = p; p += plane;
+        m->ey[l] = p; p += plane;
+    }
+    MgBC cb;
+    cb.xl = coeffs_bc[0]; cb.xr = coeffs_bc[1]; cb.yl = coeffs_bc[2]; cb.yr = coeffs_bc[3];
+    cb.xlv = cb.xrv = cb.ylv = cb.yrv = nullptr;
+    const int fin = m->nlevels - 1;
+    for (int l = fin; l >= 0; --l) {
+        MgLevel L = m->lev[l];
+        const int n = L.n, P = L.pitch;
+        L.v = m->cc[l];                       // the generic kernels below work on plane "v" / "r" / "f"
+        if (l == fin) {
+            P2B_CUDA_CHECK(cudaMemcpy2DAsync(m->cc[l] + P + 1, (size_t)P * 8, coeffs + coeffs_pitch + 1,
+                                             (size_t)coeffs_pitch * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, st));
+        } else {
+            // coeffs_c.v() = f_patch.restrict("coeffs").v()
+            MgLevel F = m->lev[l + 1], Cs = L;
+            F.r = m->cc[l + 1];
+            Cs.f = m->cc[l];
+            dim3 blk(64, 4);
+            dim3 grd((n + blk.x - 1) / blk.x, (n + blk.y - 1) / blk.y);
+            P2B_LAUNCH(mg_restrict_kernel, grd, blk, 0, st)(F, Cs, 0);
+        }
+        P2B_LAUNCH(mg_fill_kernel, (4 * n + 255) / 256, 256, 0, st)(L, cb);
+        dim3 blk(64, 4);
+        dim3 grd((n + 1 + blk.x - 1) / blk.x, (n + 1 + blk.y - 1) / blk.y);
+        if (l == fin) {
+            P2B_LAUNCH(mg_vc_edges_fine_kernel, grd, blk, 0, st)(m->cc[l], m->ex[l], m->ey[l], n, P,
+                                                                 make_div_const(L.dx * L.dx), make_div_const(L.dy * L.dy));
+        } else {
+            const MgLevel& F = m->lev[l + 1];
+            P2B_LAUNCH(mg_vc_edges_restrict_kernel, grd, blk, 0, st)(m->ex[l + 1], m->ey[l + 1], F.pitch, m->ex[l], m->ey[l],
+                                                                     n, P, F.dx * F.dx, make_div_const(L.dx * L.dx),
+                                                                     F.dy * F.dy, make_div_const(L.dy * L.dy));
+        }
+    }
+    P2B_CUDA_CHECK(cudaGetLastError());
+    m->varcoef = 1;
+    return P2B_OK;
+}
+
+// which: 0 eta (cell centres, ghost-filled), 1 eta_x, 2 eta_y; NULL before p2b_mg_set_coeffs
+void* p2b_mg_coeff_ptr(p2b_mg* m, int level, int which)
+{
+    if (!m || !m->varcoef || level < 0 || level >= m->nlevels) return nullptr;
+    return which == 0 ? m->cc[level] : which == 1 ? m->ex[level] : m->ey[level];
 }
 
 }  // extern "C"

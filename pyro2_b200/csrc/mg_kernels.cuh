@@ -665,4 +665,151 @@ __global__ void mg_diag_final_kernel(const double* part, int npart, double* out)
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
+// ---- variable coefficients: div(eta grad phi) = f  (VarCoeffCCMG2d) --------------------------------
+// eta_x[i, j] = eta_{i-1/2, j} / dx^2 and eta_y[i, j] = eta_{i, j-1/2} / dy^2 live in two planes with the
+// level's own pitch (edge_coeffs.py:16-26); entries outside [1, n+1]^2 are zero, as in the reference.
+struct VcEdges { const double* ex; const double* ey; };
+
+// variable_coeff_MG.py:150-164 for one point; up / dn = phi(i-1) / phi(i+1), lf / rt = phi(j-1) / phi(j+1),
+// exl / exh = eta_x at i / i+1, eyl / eyh = eta_y at j / j+1
+__device__ __forceinline__ double vc_gs_value(double f, double up, double dn, double lf, double rt,
+                                              double exl, double exh, double eyl, double eyh)
+{
+    double denom = exact_add(exact_add(exact_add(exh, exl), eyh), eyl);
+    double num = exact_add(exact_add(exact_add(exact_add(-f, exact_mul(exh, dn)), exact_mul(exl, up)),
+                                     exact_mul(eyh, rt)), exact_mul(eyl, lf));
+    return exact_div(num, denom);
+}
+
+// variable_coeff_MG.py:199-213:  f - L_eta phi
+__device__ __forceinline__ double vc_residual_value(double f, double c, double up, double dn, double lf, double rt,
+                                                    double exl, double exh, double eyl, double eyh)
+{
+    double a = exact_mul(exh, exact_sub(dn, c));
+    double b = exact_mul(exl, exact_sub(c, up));
+    double d = exact_mul(eyh, exact_sub(rt, c));
+    double e = exact_mul(eyl, exact_sub(c, lf));
+    return exact_sub(f, exact_sub(exact_add(exact_sub(a, b), d), e));
+}
+
+__device__ __forceinline__ double vc_gs_update(const double* v, const double* f, const VcEdges& E, int pitch, int i, int j)
+{
+    const long long k = (long long)i * pitch + j;
+    return vc_gs_value(f[k], v[k - pitch], v[k + pitch], v[k - 1], v[k + 1], E.ex[k], E.ex[k + pitch], E.ey[k], E.ey[k + 1]);
+}
+
+__device__ __forceinline__ double vc_residual_at(const MgLevel& L, const VcEdges& E, long long k)
+{
+    const double* v = L.v;
+    return vc_residual_value(L.f[k], v[k], v[k - L.pitch], v[k + L.pitch], v[k - 1], v[k + 1],
+                             E.ex[k], E.ex[k + L.pitch], E.ey[k], E.ey[k + 1]);
+}
+
+__global__ void mg_vc_halfsweep_kernel(MgLevel L, MgBC b, VcEdges E, int colour)
+{
+    const int half = L.n >> 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (k >= half || i > L.n) return;
+    const int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+    double val = vc_gs_update(L.v, L.f, E, L.pitch, i, j);
+    store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+}
+
+__global__ void mg_vc_smooth_small_kernel(MgLevel L, MgBC b, VcEdges E, int nsmooth)
+{
+    const int half = L.n >> 1;
+    const int npts = L.n * half;
+    for (int it = 0; it < 2 * nsmooth; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
+            int i = t / half + 1, k = t % half;
+            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
+            double val = vc_gs_update(L.v, L.f, E, L.pitch, i, j);
+            store_with_ghosts(L.v, L.n, L.n, L.pitch, i, j, val, b, L.dx, L.dy);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void mg_vc_residual_kernel(MgLevel L, VcEdges E)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > L.ni || j > L.n) return;
+    const long long k = (long long)i * L.pitch + j;
+    L.r[k] = vc_residual_at(L, E, k);
+}
+
+// EdgeCoeffs.__init__ (edge_coeffs.py:10-29) on the finest level, from the ghost-filled cell-centred eta
+__global__ void mg_vc_edges_fine_kernel(const double* __restrict__ c, double* __restrict__ ex, double* __restrict__ ey,
+                                        int n, int pitch, DivConst dx2, DivConst dy2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > n + 1 || j > n + 1) return;
+    const long long k = (long long)i * pitch + j;
+    ex[k] = div_const(exact_mul(0.5, exact_add(c[k - pitch], c[k])), dx2);
+    ey[k] = div_const(exact_mul(0.5, exact_add(c[k - 1], c[k])), dy2);
+}
+
+// EdgeCoeffs.restrict (edge_coeffs.py:31-54): average the two fine edges that make up a coarse edge,
+// then "redo the normalization": * dx_fine^2 / dx_coarse^2
+__global__ void mg_vc_edges_restrict_kernel(const double* __restrict__ xf, const double* __restrict__ yf, int pf,
+                                            double* __restrict__ ex, double* __restrict__ ey, int n, int pitch,
+                                            double fdx2, DivConst cdx2, double fdy2, DivConst cdy2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > n + 1 || j > n + 1) return;
+    const long long k = (long long)i * pitch + j;
+    const long long kf = (long long)(2 * i - 1) * pf + (2 * j - 1);
+    if (j <= n) ex[k] = div_const(exact_mul(exact_mul(0.5, exact_add(xf[kf], xf[kf + 1])), fdx2), cdx2);
+    if (i <= n) ey[k] = div_const(exact_mul(exact_mul(0.5, exact_add(yf[kf], yf[kf + pf])), fdy2), cdy2);
+}
+
+// solve()'s per-cycle bookkeeping, variable-coefficient residual (see mg_diag_partial_kernel)
+__global__ void __launch_bounds__(RED_THREADS)
+mg_vc_diag_partial_kernel(MgLevel L, VcEdges E, double* __restrict__ old_phi, double* __restrict__ part)
+{
+    __shared__ double sh[RED_THREADS];
+    double s_rel = 0.0, s_res = 0.0;
+    const int n = L.n, P = L.pitch;
+    const double* __restrict__ v = L.v;
+    const double* __restrict__ f = L.f;
+    double* __restrict__ r = L.r;
+    for (int i = 1 + blockIdx.x; i <= L.ni; i += gridDim.x) {
+        const long long base = (long long)i * P;
+        for (int j0 = 1 + threadIdx.x; j0 <= n; j0 += RED_THREADS * RED_PER_THREAD) {
+            double c[RED_PER_THREAD], up[RED_PER_THREAD], dn[RED_PER_THREAD], lf[RED_PER_THREAD],
+                rt[RED_PER_THREAD], ff[RED_PER_THREAD], oo[RED_PER_THREAD], exl[RED_PER_THREAD],
+                exh[RED_PER_THREAD], eyl[RED_PER_THREAD], eyh[RED_PER_THREAD];
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) {
+                int j = j0 + u * RED_THREADS;
+                bool ok = j <= n;
+                long long k = base + (ok ? j : 1);
+                c[u] = v[k]; up[u] = v[k - P]; dn[u] = v[k + P]; lf[u] = v[k - 1]; rt[u] = v[k + 1];
+                ff[u] = f[k]; oo[u] = old_phi[k];
+                exl[u] = E.ex[k]; exh[u] = E.ex[k + P]; eyl[u] = E.ey[k]; eyh[u] = E.ey[k + 1];
+            }
+#pragma unroll
+            for (int u = 0; u < RED_PER_THREAD; ++u) {
+                int j = j0 + u * RED_THREADS;
+                if (j > n) continue;
+                long long k = base + j;
+                old_phi[k] = c[u];
+                double d = (c[u] - oo[u]) / (c[u] + 1.e-16);
+                s_rel += d * d;
+                double res = vc_residual_value(ff[u], c[u], up[u], dn[u], lf[u], rt[u], exl[u], exh[u], eyl[u], eyh[u]);
+                r[k] = res;
+                s_res += res * res;
+            }
+        }
+    }
+    s_rel = block_sum(s_rel, sh);
+    s_res = block_sum(s_res, sh);
+    if (threadIdx.x == 0) { part[blockIdx.x] = s_rel; part[MG_NPART + blockIdx.x] = s_res; }
+}
+
 }  // namespace pyro

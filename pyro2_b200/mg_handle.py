@@ -102,6 +102,27 @@ class MGHandle:
         self._bc_vals = vals   # keep alive
         _lib.check(_lib.lib().p2b_mg_set_bc_values(self._h, *[None if v is None else v.data_ptr() for v in vals]))
 
+    def set_coeffs(self, coeffs, coeffs_bc):
+        """variable-coefficient mode: coeffs = eta on the finest level, an (n+2, n+2) CUDA float64 tensor
+        (any row stride, unit column stride); coeffs_bc = its four boundary-type names"""
+        L = _lib.lib()
+        assert self.decomp is None, "variable coefficients: single-GPU hierarchies only"
+        assert coeffs.is_cuda and coeffs.dtype == torch.float64 and coeffs.stride(1) == 1
+        nbytes = L.p2b_mg_coeff_workspace_bytes(self._h)
+        self.coeff_workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+        codes = (C.c_int * 4)(*[_lib.BC_CODES[b] for b in coeffs_bc])
+        _lib.check(L.p2b_mg_set_coeffs(self._h, self.coeff_workspace.data_ptr(), nbytes, coeffs.data_ptr(),
+                                       coeffs.stride(0), codes, self._s()))
+
+    def coeff_plane(self, level, which):
+        """(n+2, n+2) view of the level's eta ('c'), eta_x ('x') or eta_y ('y') plane"""
+        g = self.info(level)
+        ptr = _lib.lib().p2b_mg_coeff_ptr(self._h, level, {"c": 0, "x": 1, "y": 2}[which])
+        if not ptr:
+            raise ValueError("no coefficients set")
+        off = (ptr - self.coeff_workspace.data_ptr()) // 8
+        return self.coeff_workspace.as_strided((g["n"] + 2, g["n"] + 2), (g["pitch"], 1), off)
+
     def set_blocking(self, enable):
         _lib.check(_lib.lib().p2b_mg_set_blocking(self._h, int(bool(enable))))
 

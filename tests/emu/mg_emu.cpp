@@ -168,6 +168,8 @@ struct RegisterThreaded {
         emu::threaded((const void*)mg_sumsq_final_kernel);
         emu::threaded((const void*)mg_diag_partial_kernel);
         emu::threaded((const void*)mg_diag_final_kernel);
+        emu::threaded((const void*)mg_vc_smooth_small_kernel);
+        emu::threaded((const void*)mg_vc_diag_partial_kernel);
     }
 } register_threaded;
 }  // namespace

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from conftest import rel_l2
-from golden_util import GOLDEN, load_comp, load_mg
+from golden_util import GOLDEN, load_comp, load_mg, load_mgvc
 
 pytestmark = pytest.mark.gpu
 
@@ -129,6 +129,68 @@ def test_mg_inhomogeneous_dirichlet_matches_reference():
     a.solve(rtol=float(z["rtol"]))
     assert a.num_cycles == int(z["num_cycles"])
     assert np.array_equal(a.get_solution().numpy(), z["v"])
+
+
+def _vc_solver(nx, bc, cbc, coeffs):
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.mesh import patch
+    from pyro2_b200.multigrid import variable_coeff_MG as VMG
+    g = patch.Grid2d(nx, nx, ng=1)
+    d = patch.CellCenterData2d(g)
+    bc_c = bnd.BC(xlb=cbc[0], xrb=cbc[1], ylb=cbc[2], yrb=cbc[3])
+    d.register_var("c", bc_c)
+    d.create()
+    c = d.get_var("c")
+    c[:, :] = coeffs(g) if callable(coeffs) else coeffs
+    return VMG.VarCoeffCCMG2d(nx, nx, xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3],
+                              coeffs=c, coeffs_bc=bc_c)
+
+
+@pytest.mark.parametrize("name", ["dirichlet_64", "periodic_64", "constant_32", "dirichlet_128"])
+def test_mg_variable_coeff_solve_matches_reference(name):
+    """VarCoeffCCMG2d on the reference's mg_test_vc_{dirichlet,periodic,constant}.py setups"""
+    z = load_mgvc(name)
+    nx = int(z["nx"])
+    a = _vc_solver(nx, [str(b) for b in z["bc"]], [str(b) for b in z["coeffs_bc"]], z["coeffs"])
+    assert np.array_equal(a.edge_coeffs[2].x.numpy(), z["ex_coarse"])
+    assert np.array_equal(a.edge_coeffs[2].y.numpy(), z["ey_coarse"])
+    a.init_zeros()
+    a.init_RHS(z["f"])
+    assert a.source_norm == pytest.approx(float(z["source_norm"]), rel=1e-13)
+    a.solve(rtol=float(z["rtol"]))
+    assert a.num_cycles == int(z["num_cycles"])
+    assert np.array_equal(a.get_solution().numpy(), z["v"])
+    assert a.residual_error == pytest.approx(float(z["residual_error"]), rel=1e-9)
+    assert a.relative_error == pytest.approx(float(z["relative_error"]), rel=1e-9)
+
+
+def test_mg_variable_coeff_converges_second_order():
+    """mg_test_vc_dirichlet.py: alpha = 2 + cos(2 pi x) cos(2 pi y), exact phi = sin(2 pi x) sin(2 pi y)"""
+    import torch
+    pi = np.pi
+    errs = []
+    for nx in (64, 128, 256):
+        a = _vc_solver(nx, ("dirichlet",) * 4, ("neumann",) * 4,
+                       lambda g: 2.0 + torch.cos(2 * pi * g.x2d) * torch.cos(2 * pi * g.y2d))
+        x, y = a.x2d, a.y2d
+        a.init_zeros()
+        a.init_RHS(-16.0 * pi ** 2 * (torch.cos(2 * pi * x) * torch.cos(2 * pi * y) + 1) *
+                   torch.sin(2 * pi * x) * torch.sin(2 * pi * y))
+        a.solve(rtol=1.e-11)
+        e = a.get_solution() - torch.sin(2 * pi * x) * torch.sin(2 * pi * y)
+        errs.append(e.norm())
+    assert errs[0] / errs[1] == pytest.approx(4.0, rel=0.05)
+    assert errs[1] / errs[2] == pytest.approx(4.0, rel=0.05)
+
+
+def test_mg_variable_coeff_argument_errors():
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.multigrid import variable_coeff_MG as VMG
+    with pytest.raises(ValueError):
+        VMG.VarCoeffCCMG2d(32, 32)
+    with pytest.raises(IndexError):
+        VMG.VarCoeffCCMG2d(64, 64, coeffs=np.ones((34, 34)),
+                           coeffs_bc=bnd.BC(xlb="neumann", xrb="neumann", ylb="neumann", yrb="neumann"))
 
 
 def test_mg_gradient_known_answer():

@@ -149,3 +149,63 @@ def test_blocked_and_per_colour_smoothers_agree_bitwise(nsmooth):
     o.smooth(L, nsmooth); d.smooth(L, nsmooth); e.smooth(L, nsmooth)
     assert _same(o, d, L, "v")
     assert np.array_equal(d.plane(L, "v").cpu().numpy(), e.plane(L, "v").cpu().numpy())
+
+
+# ---- variable coefficients (VarCoeffCCMG2d) ------------------------------------------------------------
+def _vc_pair(nx, bc, cbc, seed=0):
+    import torch
+    o, d = _pair(nx, bc, 0.0, 0.0, seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    coeffs = 0.5 + rng.random((nx + 2, nx + 2))
+    o.set_coeffs(coeffs, cbc)
+    d.set_coeffs(torch.from_numpy(coeffs).cuda(), cbc)
+    return o, d
+
+
+VC_SETS = [(("dirichlet",) * 4, ("neumann",) * 4), (("periodic",) * 4, ("periodic",) * 4),
+           (("dirichlet", "neumann", "periodic", "periodic"), ("neumann", "reflect-even", "periodic", "periodic"))]
+
+
+@pytest.mark.parametrize("bc,cbc", VC_SETS)
+@pytest.mark.parametrize("nx", [4, 64, 256])
+def test_vc_edge_coefficients_bit_exact(bc, cbc, nx):
+    o, d = _vc_pair(nx, bc, cbc)
+    for lev in range(o.nlevels):
+        for a, b in (("c", "c"), ("ex", "x"), ("ey", "y")):
+            assert np.array_equal(d.coeff_plane(lev, b).cpu().numpy(), o.coef_plane(lev, a)), (lev, a)
+
+
+@pytest.mark.parametrize("bc,cbc", VC_SETS)
+@pytest.mark.parametrize("nx", [2, 16, 64, 128, 512])
+def test_vc_smooth_residual_vcycle_bit_exact(bc, cbc, nx):
+    o, d = _vc_pair(nx, bc, cbc, seed=nx)
+    L = o.nlevels - 1
+    o.smooth(L, 7); d.smooth(L, 7)
+    assert _same(o, d, L, "v")
+    o.residual(L); d.residual(L)
+    assert np.array_equal(d.plane(L, "r").cpu().numpy()[1:-1, 1:-1], o.plane(L, "r")[1:-1, 1:-1])
+    o.v_cycle(); d.vcycle()
+    assert _same(o, d, L, "v")
+    for lev in range(L):
+        assert _same(o, d, lev, "v"), lev
+
+
+def test_vc_cycle_diagnostics():
+    import torch
+    nx = 256
+    o, d = _vc_pair(nx, ("dirichlet",) * 4, ("neumann",) * 4, seed=9)
+    L = o.nlevels - 1
+    old = d.plane(L, "v").clone()
+    pitch = d.info(L)["pitch"]
+    old_phi = torch.zeros((nx + 2, pitch), dtype=torch.float64, device="cuda")
+    old_phi[:, :nx + 2] = old
+    o.v_cycle(); d.vcycle()
+    relsq, rsq = d.cycle_diagnostics(old_phi)
+    o.residual(L)
+    r = o.plane(L, "r")[1:-1, 1:-1]
+    assert rsq == pytest.approx(float((r ** 2).sum()), rel=1e-12)
+    assert np.array_equal(d.plane(L, "r").cpu().numpy()[1:-1, 1:-1], r)
+    v = o.plane(L, "v")[1:-1, 1:-1]
+    ref = (((v - old.cpu().numpy()[1:-1, 1:-1]) / (v + 1e-16)) ** 2).sum()
+    assert relsq == pytest.approx(float(ref), rel=1e-12)
+    assert np.array_equal(old_phi[:, :nx + 2].cpu().numpy()[1:-1, 1:-1], v)

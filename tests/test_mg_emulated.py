@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle
-from golden_util import load_mg
+from golden_util import load_mg, load_mgvc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
@@ -76,6 +76,22 @@ class EmuMG:
         self.keep = vals
         self.ck(self.lib.p2b_mg_set_bc_values(self.h, *[None if v is None else v.ctypes.data for v in vals]))
 
+    def set_coeffs(self, coeffs, coeffs_bc):
+        nbytes = self.lib.p2b_mg_coeff_workspace_bytes(self.h)
+        self.cws = np.zeros(nbytes // 8 + 2)
+        off = (-self.cws.ctypes.data // 8) % 2
+        self.cbase = self.cws[off:]
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        codes = (C.c_int * 4)(*[BC[b] for b in coeffs_bc])
+        self.ck(self.lib.p2b_mg_set_coeffs(self.h, self.cbase.ctypes.data, nbytes, c.ctypes.data, c.shape[1], codes, None))
+
+    def coef_plane(self, level, which):
+        n = 2 << level
+        pitch = self.lib.p2b_mg_level_pitch(self.h, level)
+        ptr = self.lib.p2b_mg_coeff_ptr(self.h, level, {"c": 0, "ex": 1, "ey": 2}[which])
+        off = (ptr - self.cbase.ctypes.data) // 8
+        return np.lib.stride_tricks.as_strided(self.cbase[off:], (n + 2, n + 2), (pitch * 8, 8))
+
     def sumsq(self, level, which):
         self.ck(self.lib.p2b_mg_norm2(self.h, level, {"v": 0, "f": 1, "r": 2}[which], self.out.ctypes.data, None))
         return float(self.out[0])
@@ -134,4 +150,36 @@ def test_emulated_blocked_smoother_interior_path_256(emu):
     m.ck(emu.p2b_mg_smooth(m.h, fine, 7, None))      # passes of 5 + 2 iterations, result copied back from w
     o.smooth(fine, 7)
     assert np.array_equal(m.plane(fine, "v"), o.plane(fine, "v"))
+    m.close()
+
+
+@pytest.mark.parametrize("name", ["dirichlet_64", "periodic_64", "constant_32", "dirichlet_128"])
+def test_emulated_variable_coefficient_solve_matches_reference(emu, name):
+    """VarCoeffCCMG2d fixtures produced by the reference (its mg_test_vc_* setups)"""
+    z = load_mgvc(name)
+    n = int(z["nx"])
+    m = EmuMG(emu, n, tuple(str(b) for b in z["bc"]), 0.0, 0.0)
+    m.set_coeffs(z["coeffs"], tuple(str(b) for b in z["coeffs_bc"]))
+    assert np.array_equal(m.coef_plane(2, "ex"), z["ex_coarse"])
+    assert np.array_equal(m.coef_plane(2, "ey"), z["ey_coarse"])
+    v = m.solve(z["f"], rtol=float(z["rtol"]))
+    assert m.num_cycles == int(z["num_cycles"])
+    assert np.array_equal(v, z["v"])
+    assert np.array_equal(m.plane(m.nlevels - 1, "r")[1:n + 1, 1:n + 1], z["r"][1:n + 1, 1:n + 1])
+    m.close()
+
+
+def test_emulated_variable_coefficient_hierarchy_matches_oracle(emu):
+    """every level's eta, eta_x, eta_y for random coefficients and mixed coefficient BCs"""
+    n = 64
+    rng = np.random.default_rng(11)
+    coeffs = 0.5 + rng.random((n + 2, n + 2))
+    cbc = ("neumann", "reflect-even", "periodic", "periodic")
+    m = EmuMG(emu, n, ("dirichlet", "neumann", "periodic", "periodic"), 0.0, 0.0)
+    m.set_coeffs(coeffs, cbc)
+    o = oracle.MG(n, bc=("dirichlet", "neumann", "periodic", "periodic"), alpha=0.0, beta=0.0)
+    o.set_coeffs(coeffs, cbc)
+    for lev in range(o.nlevels):
+        for which in ("c", "ex", "ey"):
+            assert np.array_equal(m.coef_plane(lev, which), o.coef_plane(lev, which)), (lev, which)
     m.close()
