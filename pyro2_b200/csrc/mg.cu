@@ -102,6 +102,26 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
     if (m->varcoef) {
         // variable_coeff_MG.py:112-171
         const VcEdges E = level_edges(m, level);
+        if (L.n >= MG_TB_MIN_N && !m->no_blocking && nsmooth > 0) {
+            // the blocked smoother with the coefficient tiles staged in shared memory
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(mg_vc_smooth_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_VC_SMEM_BYTES);
+                attr_set = true;
+            }
+            dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.n + TB_TI - 1) / TB_TI);
+            const double* src = L.v;
+            double* dst = L.w;
+            for (int left = nsmooth; left > 0;) {
+                int it = left < TB_K ? left : TB_K;
+                P2B_LAUNCH(mg_vc_smooth_tb_kernel, grd, 32 * TB_NW, TB_VC_SMEM_BYTES, st)(L, src, dst, b, E, it);
+                left -= it;
+                const double* t = src; src = dst; dst = const_cast<double*>(t);
+            }
+            if (src != L.v)
+                cudaMemcpyAsync(L.v, L.w, (size_t)(L.n + 2) * L.pitch * sizeof(double), cudaMemcpyDeviceToDevice, st);
+            return P2B_OK;
+        }
         if (fill_first) P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, st)(L, b);
         if (L.n <= MG_SMALL_N) {
             int threads = L.n * (L.n / 2);
@@ -217,16 +237,22 @@ static void coarse_vcycle_impl(p2b_mg* m, int top, cudaStream_t st)
     T.bc_coarse = level_bc(m, top == m->nlevels - 1 ? -1 : 0);   // homogeneous
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(mg_coarse_vcycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(mg_coarse_vcycle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(mg_coarse_vcycle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    P2B_LAUNCH(mg_coarse_vcycle_kernel, 1, MG_COARSE_THREADS, bytes, st)(T);
+    if (m->varcoef) {
+        for (int l = 0; l <= top; ++l) T.edges[l] = level_edges(m, l);
+        P2B_LAUNCH(mg_coarse_vcycle_kernel<true>, 1, MG_COARSE_THREADS, bytes, st)(T);
+    } else {
+        P2B_LAUNCH(mg_coarse_vcycle_kernel<false>, 1, MG_COARSE_THREADS, bytes, st)(T);
+    }
 }
 
 static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     // MG.py:699-778
-    if (!m->no_blocking && !m->varcoef && level <= coarse_top(m)) {
+    if (!m->no_blocking && level <= coarse_top(m)) {
         coarse_vcycle_impl(m, level, st);
         return;
     }

@@ -171,6 +171,34 @@ __global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmo
 }
 
 
+// ---- variable coefficients: div(eta grad phi) = f  (VarCoeffCCMG2d) --------------------------------
+// eta_x[i, j] = eta_{i-1/2, j} / dx^2 and eta_y[i, j] = eta_{i, j-1/2} / dy^2 live in two planes with the
+// level's own pitch (edge_coeffs.py:16-26); entries outside [1, n+1]^2 are zero, as in the reference.
+struct VcEdges { const double* ex; const double* ey; };
+
+// variable_coeff_MG.py:150-164 for one point; up / dn = phi(i-1) / phi(i+1), lf / rt = phi(j-1) / phi(j+1),
+// exl / exh = eta_x at i / i+1, eyl / eyh = eta_y at j / j+1
+__device__ __forceinline__ double vc_gs_value(double f, double up, double dn, double lf, double rt,
+                                              double exl, double exh, double eyl, double eyh)
+{
+    double denom = exact_add(exact_add(exact_add(exh, exl), eyh), eyl);
+    double num = exact_add(exact_add(exact_add(exact_add(-f, exact_mul(exh, dn)), exact_mul(exl, up)),
+                                     exact_mul(eyh, rt)), exact_mul(eyl, lf));
+    return exact_div(num, denom);
+}
+
+// variable_coeff_MG.py:199-213:  f - L_eta phi
+__device__ __forceinline__ double vc_residual_value(double f, double c, double up, double dn, double lf, double rt,
+                                                    double exl, double exh, double eyl, double eyh)
+{
+    double a = exact_mul(exh, exact_sub(dn, c));
+    double b = exact_mul(exl, exact_sub(c, up));
+    double d = exact_mul(eyh, exact_sub(rt, c));
+    double e = exact_mul(eyl, exact_sub(c, lf));
+    return exact_sub(f, exact_sub(exact_add(exact_sub(a, b), d), e));
+}
+
+
 // ---- temporally blocked smoother -------------------------------------------------------------------
 // One CTA owns a TI x TJ tile and loads it with a halo of H = 2*TB_K cells into REGISTERS: a thread
 // holds a 2-column x TB_R-row patch of v and f (lane t <-> columns 2t, 2t+1 of the 64-column
@@ -207,10 +235,21 @@ __device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [
 // EDGE = false: the whole 64 x 64 region lies strictly inside the domain (the case for all but the
 // outermost ring of CTAs): no wrap, no ghost logic, no per-cell predicates.  EDGE = true: the general
 // path.  The choice is block-uniform, so a CTA executes exactly one of the two instruction streams.
-template <bool EDGE>
+//
+// VC = true (variable coefficients): the CTA additionally stages the region's edge coefficients in
+// shared memory once per pass -- eta_x for region rows 0..TB_RH (a cell needs its own and the next
+// row's), eta_y for columns 0..TB_RW -- split by column parity so that the lanes of a warp read
+// consecutive doubles: exs[col & 1][row][col >> 1], eys[col & 1][row][col >> 1] (33 entries per row).
+// A periodic image of cell n takes eta at n + 1 (not at the image of n + 1, which is only the same
+// number when the coefficient's own BC is periodic): those seam cells read it from global memory.
+constexpr int TB_EXS = 2 * (TB_RH + 1) * 32;       // doubles in the eta_x tile
+constexpr int TB_EYS = 2 * TB_RH * 33;             // doubles in the eta_y tile
+
+template <bool EDGE, bool VC>
 __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
                                                double* __restrict__ vout, const MgBC& b, const SmoothCoef& c,
-                                               int niter, double (*edge)[TB_NW][2][TB_RW])
+                                               int niter, double (*edge)[TB_NW][2][TB_RW],
+                                               const VcEdges& E, double* __restrict__ exs, double* __restrict__ eys)
 {
     const int n = L.n, ni = L.ni, P = L.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -249,6 +288,35 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     if (EDGE && !yper) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) { col_lo[a] = (gj0 + a == 1); col_hi[a] = (gj0 + a == n); }
+    }
+
+    unsigned xseam = 0;                            // VC: bit r: this row is the periodic image of row ni
+    bool yseam[2] = {false, false};                //     column a is the periodic image of column n
+    if (VC) {
+        const int rbase = I0 - TB_H, cbase = J0 - TB_H;
+        for (int t = threadIdx.x; t < (TB_RH + 1) * TB_RW; t += 32 * TB_NW) {
+            const int rr = t / TB_RW, cc = t % TB_RW;
+            int si = rbase + rr, sj = cbase + cc;
+            if (xper) si = wrap1(si, ni);
+            if (yper) sj = wrap1(sj, n);
+            const bool ok = !EDGE || (si >= 1 && si <= ni + 1 && sj >= 1 && sj <= n);
+            exs[((cc & 1) * (TB_RH + 1) + rr) * 32 + (cc >> 1)] = ok ? E.ex[(long long)si * P + sj] : 0.0;
+        }
+        for (int t = threadIdx.x; t < TB_RH * (TB_RW + 1); t += 32 * TB_NW) {
+            const int rr = t / (TB_RW + 1), cc = t % (TB_RW + 1);
+            int si = rbase + rr, sj = cbase + cc;
+            if (xper) si = wrap1(si, ni);
+            if (yper) sj = wrap1(sj, n);
+            const bool ok = !EDGE || (si >= 1 && si <= ni && sj >= 1 && sj <= n + 1);
+            eys[((cc & 1) * TB_RH + rr) * 33 + (cc >> 1)] = ok ? E.ey[(long long)si * P + sj] : 0.0;
+        }
+        if (EDGE) {
+#pragma unroll
+            for (int r = 0; r < TB_R; ++r)
+                if (xper && wrap1(gi0 + r, ni) == ni) xseam |= 1u << r;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) yseam[a] = yper && wrap1(gj0 + a, n) == n;
+        }
     }
 
     double uph[2] = {0.0, 0.0}, dnh[2] = {0.0, 0.0};   // rows just above / below this thread's strip
@@ -291,10 +359,23 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                 if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, L.ioff + gi, L.dy);
                 if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, L.ioff + gi, L.dy);
             }
-            double sx = exact_add(dn, up);
-            double sy = exact_add(rt, lf);
-            double num = exact_add(exact_add(f[r][a], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
-            nv[r] = div_by_denom(num, c);
+            if (VC) {
+                const int rr = w * TB_R + r;
+                double exl = exs[(a * (TB_RH + 1) + rr) * 32 + lane];
+                double exh = exs[(a * (TB_RH + 1) + rr + 1) * 32 + lane];
+                double eyl = eys[(a * TB_RH + rr) * 33 + lane];
+                double eyh = eys[((a ^ 1) * TB_RH + rr) * 33 + lane + a];
+                if (EDGE && ((inmask >> (2 * r + a)) & 1u)) {
+                    if ((xseam >> r) & 1u) exh = E.ex[(long long)(ni + 1) * P + (yper ? wrap1(gj0 + a, n) : gj0 + a)];
+                    if (yseam[a]) eyh = E.ey[(long long)(xper ? wrap1(gi0 + r, ni) : gi0 + r) * P + n + 1];
+                }
+                nv[r] = vc_gs_value(f[r][a], up, dn, lf, rt, exl, exh, eyl, eyh);
+            } else {
+                double sx = exact_add(dn, up);
+                double sy = exact_add(rt, lf);
+                double num = exact_add(exact_add(f[r][a], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+                nv[r] = div_by_denom(num, c);
+            }
         }
 #pragma unroll
         for (int r = 0; r < TB_R; ++r) {
@@ -333,8 +414,29 @@ mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restric
     const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? L.ni : L.ni + TB_H;
     const bool interior = (I0 - TB_H >= rlo) && (I0 - TB_H + TB_RH - 1 <= rhi) &&
                           (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
-    if (interior) smooth_tb_body<false>(L, vin, vout, b, c, niter, edge);
-    else smooth_tb_body<true>(L, vin, vout, b, c, niter, edge);
+    const VcEdges none = {nullptr, nullptr};
+    if (interior) smooth_tb_body<false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr);
+    else smooth_tb_body<true, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr);
+}
+
+// the same pass with the variable-coefficient stencil; dynamic shared memory: the row-exchange buffers
+// followed by the two coefficient tiles (TB_VC_SMEM_BYTES, ~166 KB: one CTA per SM)
+constexpr size_t TB_VC_SMEM_BYTES = (size_t)(2 * TB_NW * 2 * TB_RW + TB_EXS + TB_EYS) * sizeof(double);
+
+__global__ void __launch_bounds__(32 * TB_NW, 1)
+mg_vc_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b, VcEdges E, int niter)
+{
+    P2B_DYN_SMEM(double, sm);
+    double (*edge)[TB_NW][2][TB_RW] = reinterpret_cast<double (*)[TB_NW][2][TB_RW]>(sm);
+    double* exs = sm + 2 * TB_NW * 2 * TB_RW;
+    double* eys = exs + TB_EXS;
+    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + TB_RH - 1 <= L.ni) &&
+                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
+    SmoothCoef c;
+    c.alpha = c.xc = c.yc = c.denom = c.rden = 0.0; c.fast = 0;
+    if (interior) smooth_tb_body<false, true>(L, vin, vout, b, c, niter, edge, E, exs, eys);
+    else smooth_tb_body<true, true>(L, vin, vout, b, c, niter, edge, E, exs, eys);
 }
 
 
@@ -366,9 +468,13 @@ struct CoarseTable {
     ResidCoef rcoef[MG_COARSE_LEVELS];
     SmoothCoef coef[MG_COARSE_LEVELS];
     MgBC bc_top, bc_coarse;             // bc_top carries the inhomogeneous values when top is the finest
+    VcEdges edges[MG_COARSE_LEVELS];    // variable coefficients: the levels' edge planes (global memory,
+                                        // read-only and L1-resident; indexed with the GLOBAL pitch g[l].pitch)
 };
 
-__device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, const SmoothCoef& c, int nsmooth)
+template <bool VC>
+__device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, const SmoothCoef& c, int nsmooth,
+                                           const VcEdges& E, int gpitch)
 {
     const int n = L.n, half = n >> 1, npts = n * half;
     const int ls = __ffs(n) - 1, hs = ls - 1;   // n and half are powers of two: shifts instead of divisions
@@ -385,7 +491,14 @@ __device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, cons
         for (int t = threadIdx.x; t < npts; t += blockDim.x) {
             int i = (t >> hs) + 1, k = t & (half - 1);
             int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
-            double val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            double val;
+            if (VC) {
+                const long long ks = (long long)i * L.pitch + j, kg = (long long)i * gpitch + j;
+                val = vc_gs_value(L.f[ks], L.v[ks - L.pitch], L.v[ks + L.pitch], L.v[ks - 1], L.v[ks + 1],
+                                  E.ex[kg], E.ex[kg + gpitch], E.ey[kg], E.ey[kg + 1]);
+            } else {
+                val = gs_update(L.v, L.f, L.pitch, i, j, c);
+            }
             store_with_ghosts(L.v, n, n, L.pitch, i, j, val, b, L.dx, L.dy);
         }
         __syncthreads();
@@ -397,6 +510,7 @@ __device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, cons
 #define MG_COARSE_THREADS 1024
 #endif
 
+template <bool VC>
 __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(CoarseTable T)
 {
     P2B_DYN_SMEM(double, sm);
@@ -429,11 +543,20 @@ __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(
 
     for (int l = T.top; l >= 1; --l) {
         const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
-        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+        cta_smooth<VC>(S[l], b, T.coef[l], T.nsmooth, T.edges[l], T.g[l].pitch);
         const int n = S[l].n;
         for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-            long long k = (long long)(t / n + 1) * S[l].pitch + (t % n + 1);
-            S[l].r[k] = residual_at(S[l], k, T.rcoef[l]);
+            const int i = t / n + 1, j = t % n + 1;
+            long long k = (long long)i * S[l].pitch + j;
+            if (VC) {
+                const int P = S[l].pitch, Pg = T.g[l].pitch;
+                const long long kg = (long long)i * Pg + j;
+                const double* v = S[l].v;
+                S[l].r[k] = vc_residual_value(S[l].f[k], v[k], v[k - P], v[k + P], v[k - 1], v[k + 1],
+                                              T.edges[l].ex[kg], T.edges[l].ex[kg + Pg], T.edges[l].ey[kg], T.edges[l].ey[kg + 1]);
+            } else {
+                S[l].r[k] = residual_at(S[l], k, T.rcoef[l]);
+            }
         }
         __syncthreads();
         const int nc = S[l - 1].n;
@@ -446,7 +569,7 @@ __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(
         }
         __syncthreads();
     }
-    cta_smooth(S[0], (T.top == 0) ? T.bc_top : T.bc_coarse, T.coef[0], T.nsmooth_bottom);
+    cta_smooth<VC>(S[0], (T.top == 0) ? T.bc_top : T.bc_coarse, T.coef[0], T.nsmooth_bottom, T.edges[0], T.g[0].pitch);
     for (int l = 1; l <= T.top; ++l) {
         const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
         const MgLevel &F = S[l], &Cs = S[l - 1];
@@ -466,7 +589,7 @@ __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(
             store_with_ghosts(v, F.n, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
         }
         __syncthreads();
-        cta_smooth(S[l], b, T.coef[l], T.nsmooth);
+        cta_smooth<VC>(S[l], b, T.coef[l], T.nsmooth, T.edges[l], T.g[l].pitch);
     }
 
     // store everything back (coarse planes stay observable through grids[level], like the reference's)
@@ -665,33 +788,7 @@ __global__ void mg_diag_final_kernel(const double* part, int npart, double* out)
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
-// ---- variable coefficients: div(eta grad phi) = f  (VarCoeffCCMG2d) --------------------------------
-// eta_x[i, j] = eta_{i-1/2, j} / dx^2 and eta_y[i, j] = eta_{i, j-1/2} / dy^2 live in two planes with the
-// level's own pitch (edge_coeffs.py:16-26); entries outside [1, n+1]^2 are zero, as in the reference.
-struct VcEdges { const double* ex; const double* ey; };
-
-// variable_coeff_MG.py:150-164 for one point; up / dn = phi(i-1) / phi(i+1), lf / rt = phi(j-1) / phi(j+1),
-// exl / exh = eta_x at i / i+1, eyl / eyh = eta_y at j / j+1
-__device__ __forceinline__ double vc_gs_value(double f, double up, double dn, double lf, double rt,
-                                              double exl, double exh, double eyl, double eyh)
-{
-    double denom = exact_add(exact_add(exact_add(exh, exl), eyh), eyl);
-    double num = exact_add(exact_add(exact_add(exact_add(-f, exact_mul(exh, dn)), exact_mul(exl, up)),
-                                     exact_mul(eyh, rt)), exact_mul(eyl, lf));
-    return exact_div(num, denom);
-}
-
-// variable_coeff_MG.py:199-213:  f - L_eta phi
-__device__ __forceinline__ double vc_residual_value(double f, double c, double up, double dn, double lf, double rt,
-                                                    double exl, double exh, double eyl, double eyh)
-{
-    double a = exact_mul(exh, exact_sub(dn, c));
-    double b = exact_mul(exl, exact_sub(c, up));
-    double d = exact_mul(eyh, exact_sub(rt, c));
-    double e = exact_mul(eyl, exact_sub(c, lf));
-    return exact_sub(f, exact_sub(exact_add(exact_sub(a, b), d), e));
-}
-
+// ---- variable coefficients: kernels (the per-point arithmetic is defined ahead of the blocked smoother)
 __device__ __forceinline__ double vc_gs_update(const double* v, const double* f, const VcEdges& E, int pitch, int i, int j)
 {
     const long long k = (long long)i * pitch + j;

@@ -163,12 +163,14 @@ struct RegisterThreaded {
         using namespace pyro;
         emu::threaded((const void*)mg_smooth_small_kernel);
         emu::threaded((const void*)mg_smooth_tb_kernel);
-        emu::threaded((const void*)mg_coarse_vcycle_kernel);
+        emu::threaded((const void*)mg_coarse_vcycle_kernel<false>);
+        emu::threaded((const void*)mg_coarse_vcycle_kernel<true>);
         emu::threaded((const void*)mg_sumsq_partial_kernel);
         emu::threaded((const void*)mg_sumsq_final_kernel);
         emu::threaded((const void*)mg_diag_partial_kernel);
         emu::threaded((const void*)mg_diag_final_kernel);
         emu::threaded((const void*)mg_vc_smooth_small_kernel);
+        emu::threaded((const void*)mg_vc_smooth_tb_kernel);
         emu::threaded((const void*)mg_vc_diag_partial_kernel);
     }
 } register_threaded;

@@ -183,3 +183,32 @@ def test_emulated_variable_coefficient_hierarchy_matches_oracle(emu):
         for which in ("c", "ex", "ey"):
             assert np.array_equal(m.coef_plane(lev, which), o.coef_plane(lev, which)), (lev, which)
     m.close()
+
+
+@pytest.mark.parametrize("n,bc,cbc", [
+    (128, ("periodic",) * 4, ("neumann", "neumann", "reflect-even", "neumann")),   # seam cells: eta(n+1) != eta(1)
+    (128, ("dirichlet", "neumann", "periodic", "periodic"), ("neumann", "neumann", "periodic", "periodic")),
+    (256, ("dirichlet", "neumann", "neumann", "dirichlet"), ("neumann",) * 4),    # has interior-path CTAs
+    (256, ("periodic",) * 4, ("periodic",) * 4),
+])
+def test_emulated_variable_coefficient_blocked_smoother(emu, n, bc, cbc):
+    """the temporally blocked smoother with the coefficient tiles in shared memory vs the oracle's
+    plain red-black sweeps, and vs the per-colour kernels of the same library"""
+    rng = np.random.default_rng(n)
+    coeffs = 0.5 + rng.random((n + 2, n + 2))
+    f = rng.standard_normal((n + 2, n + 2))
+    v0 = rng.standard_normal((n + 2, n + 2))
+    o = oracle.MG(n, bc=bc, alpha=0.0, beta=0.0)
+    o.set_coeffs(coeffs, cbc)
+    fine = o.nlevels - 1
+    o.plane(fine, "v")[:] = v0
+    o.plane(fine, "f")[:] = f
+    o.smooth(fine, 7)
+    for blocking in (True, False):
+        m = EmuMG(emu, n, bc, 0.0, 0.0, blocking)
+        m.set_coeffs(coeffs, cbc)
+        m.plane(fine, "v")[:] = v0
+        m.plane(fine, "f")[:] = f
+        m.ck(emu.p2b_mg_smooth(m.h, fine, 7, None))
+        assert np.array_equal(m.plane(fine, "v"), o.plane(fine, "v")), blocking
+        m.close()
