@@ -199,6 +199,25 @@ __device__ __forceinline__ double vc_residual_value(double f, double c, double u
 }
 
 
+// 8-byte asynchronous global -> shared copy (cp.async / LDGSTS) and the wait for all of a thread's
+// copies; visibility to the other threads still needs the __syncthreads that follows
+__device__ __forceinline__ void tile_copy8(double* dst_shared, const double* src_global)
+{
+#ifdef P2B_EMU_HEADER
+    *dst_shared = *src_global;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void tile_copy_wait()
+{
+#ifndef P2B_EMU_HEADER
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // ---- temporally blocked smoother -------------------------------------------------------------------
 // One CTA owns a TI x TJ tile and loads it with a halo of H = 2*TB_K cells into REGISTERS: a thread
 // holds a 2-column x TB_R-row patch of v and f (lane t <-> columns 2t, 2t+1 of the 64-column
@@ -225,6 +244,7 @@ constexpr int TB_RW = 64;               // region columns
 constexpr int TB_TI = TB_RH - 2 * TB_H; // tile rows    (44)
 constexpr int TB_TJ = TB_RW - 2 * TB_H; // tile columns (44)
 static_assert(TB_TI % 2 == 0 && TB_TJ % 2 == 0 && TB_R % 2 == 0, "parity bookkeeping needs even tile sizes");
+static_assert(TB_RW == 64 && TB_NW % 2 == 0, "the coefficient-tile copy maps thread t to column t & 63");
 
 __device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [1, n]
 {
@@ -261,6 +281,54 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     // rows received from it (they are updated redundantly, exactly like the periodic wrap)
     const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? ni : ni + TB_H;
 
+    unsigned xseam = 0;                            // VC: bit r: this row is the periodic image of row ni
+    bool yseam[2] = {false, false};                //     column a is the periodic image of column n
+    if (VC) {
+        // Stage the coefficient tiles first, as asynchronous global -> shared copies (LDGSTS) that need
+        // no registers and all fly at once; the v / f loads below overlap with them.  (The first
+        // version loaded through registers in a rolled loop: ncu showed 40% of the kernel's stall
+        // samples on those stores waiting for one load at a time.)  Thread t handles column t & 63 of
+        // rows t >> 6, + TB_NW / 2, ...; the 65th eta_y column is done by the first TB_RH threads.
+        const int rbase = I0 - TB_H, cbase = J0 - TB_H;
+        const int cc = threadIdx.x & (TB_RW - 1);
+        int sj = cbase + cc;
+        if (yper) sj = wrap1(sj, n);
+        const bool colx = !EDGE || (sj >= 1 && sj <= n);            // eta_x exists for columns 1..n
+        const bool coly = !EDGE || (sj >= 1 && sj <= n + 1);        // eta_y for columns 1..n+1
+        double* exd = exs + (cc & 1) * (TB_RH + 1) * 32 + (cc >> 1);
+        double* eyd = eys + (cc & 1) * TB_RH * 33 + (cc >> 1);
+#pragma unroll
+        for (int k = 0; k < (TB_RH + TB_NW / 2) / (TB_NW / 2); ++k) {
+            const int rr = (threadIdx.x >> 6) + k * (TB_NW / 2);
+            if (rr > TB_RH) break;
+            int si = rbase + rr;
+            if (xper) si = wrap1(si, ni);
+            const long long src = (long long)si * P + sj;
+            if (colx && (!EDGE || (si >= 1 && si <= ni + 1))) tile_copy8(exd + rr * 32, E.ex + src);
+            else exd[rr * 32] = 0.0;
+            if (rr < TB_RH) {
+                if (coly && (!EDGE || (si >= 1 && si <= ni))) tile_copy8(eyd + rr * 33, E.ey + src);
+                else eyd[rr * 33] = 0.0;
+            }
+        }
+        if (threadIdx.x < TB_RH) {
+            const int rr = threadIdx.x;
+            int si = rbase + rr, sjl = cbase + TB_RW;
+            if (xper) si = wrap1(si, ni);
+            if (yper) sjl = wrap1(sjl, n);
+            double* d = eys + rr * 33 + (TB_RW >> 1);               // column TB_RW: parity 0, entry 32
+            if (!EDGE || (si >= 1 && si <= ni && sjl >= 1 && sjl <= n + 1)) tile_copy8(d, E.ey + (long long)si * P + sjl);
+            else *d = 0.0;
+        }
+        if (EDGE) {
+#pragma unroll
+            for (int r = 0; r < TB_R; ++r)
+                if (xper && wrap1(gi0 + r, ni) == ni) xseam |= 1u << r;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) yseam[a] = yper && wrap1(gj0 + a, n) == n;
+        }
+    }
+
     double v[TB_R][2], f[TB_R][2];
     // EDGE only: bit r*2+a set = (r, a) is a real interior cell; per-row / per-column edge flags
     unsigned inmask = 0xffffffffu;
@@ -290,34 +358,7 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
         for (int a = 0; a < 2; ++a) { col_lo[a] = (gj0 + a == 1); col_hi[a] = (gj0 + a == n); }
     }
 
-    unsigned xseam = 0;                            // VC: bit r: this row is the periodic image of row ni
-    bool yseam[2] = {false, false};                //     column a is the periodic image of column n
-    if (VC) {
-        const int rbase = I0 - TB_H, cbase = J0 - TB_H;
-        for (int t = threadIdx.x; t < (TB_RH + 1) * TB_RW; t += 32 * TB_NW) {
-            const int rr = t / TB_RW, cc = t % TB_RW;
-            int si = rbase + rr, sj = cbase + cc;
-            if (xper) si = wrap1(si, ni);
-            if (yper) sj = wrap1(sj, n);
-            const bool ok = !EDGE || (si >= 1 && si <= ni + 1 && sj >= 1 && sj <= n);
-            exs[((cc & 1) * (TB_RH + 1) + rr) * 32 + (cc >> 1)] = ok ? E.ex[(long long)si * P + sj] : 0.0;
-        }
-        for (int t = threadIdx.x; t < TB_RH * (TB_RW + 1); t += 32 * TB_NW) {
-            const int rr = t / (TB_RW + 1), cc = t % (TB_RW + 1);
-            int si = rbase + rr, sj = cbase + cc;
-            if (xper) si = wrap1(si, ni);
-            if (yper) sj = wrap1(sj, n);
-            const bool ok = !EDGE || (si >= 1 && si <= ni && sj >= 1 && sj <= n + 1);
-            eys[((cc & 1) * TB_RH + rr) * 33 + (cc >> 1)] = ok ? E.ey[(long long)si * P + sj] : 0.0;
-        }
-        if (EDGE) {
-#pragma unroll
-            for (int r = 0; r < TB_R; ++r)
-                if (xper && wrap1(gi0 + r, ni) == ni) xseam |= 1u << r;
-#pragma unroll
-            for (int a = 0; a < 2; ++a) yseam[a] = yper && wrap1(gj0 + a, n) == n;
-        }
-    }
+    if (VC) tile_copy_wait();                      // the coefficient tiles requested above have landed
 
     double uph[2] = {0.0, 0.0}, dnh[2] = {0.0, 0.0};   // rows just above / below this thread's strip
     auto publish = [&](int buf) {
