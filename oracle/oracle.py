@@ -20,8 +20,8 @@ BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "di
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "pyro_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("pyro_oracle.c", "incomp_oracle.c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(src) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -71,6 +71,14 @@ def lib():
         L.orc_mg_set_coeffs.restype = None
         L.orc_mg_coef_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_mg_coef_plane.restype = C.POINTER(C.c_double)
+        L.orc_incomp_mac_vels.argtypes = [dp] * 4 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, dp, dp]
+        L.orc_incomp_mac_vels.restype = None
+        L.orc_incomp_states.argtypes = [dp] * 4 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] + [dp] * 6
+        L.orc_incomp_states.restype = None
+        L.orc_burgers_evolve.argtypes = [dp, dp] + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int]
+        L.orc_burgers_evolve.restype = None
+        L.orc_incomp_evolve.argtypes = [dp, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int, dp, dp, dp, dp]
+        L.orc_incomp_evolve.restype = None
         L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
         L.orc_norm.restype = C.c_double
         L.orc_mg_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp]
@@ -238,3 +246,50 @@ class MG:
 
     def get_solution(self):
         return self.plane(self.nlevels - 1, "v").copy()
+
+
+# ---- Burgers / incompressible (oracle/incomp_oracle.c) ------------------------------------------------
+def _c(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.ndim == 2
+    return a
+
+
+def incomp_mac_vels(u, v, gradp_x, gradp_y, ng, dx, dy, dt, limiter):
+    """incomp_interface.mac_vels on ghost-filled (qx, qy) arrays -> (u_MAC, v_MAC)"""
+    u, v, gx, gy = _c(u), _c(v), _c(gradp_x), _c(gradp_y)
+    um, vm = np.zeros_like(u), np.zeros_like(u)
+    lib().orc_incomp_mac_vels(_ptr(u), _ptr(v), _ptr(gx), _ptr(gy), u.shape[0] - 2 * ng, u.shape[1] - 2 * ng, ng,
+                              dx, dy, dt, limiter, _ptr(um), _ptr(vm))
+    return um, vm
+
+
+def incomp_states(u, v, gradp_x, gradp_y, ng, dx, dy, dt, limiter, u_mac, v_mac):
+    """incomp_interface.states -> (u_xint, v_xint, u_yint, v_yint)"""
+    u, v, gx, gy, um, vm = _c(u), _c(v), _c(gradp_x), _c(gradp_y), _c(u_mac), _c(v_mac)
+    out = [np.zeros_like(u) for _ in range(4)]
+    lib().orc_incomp_states(_ptr(u), _ptr(v), _ptr(gx), _ptr(gy), u.shape[0] - 2 * ng, u.shape[1] - 2 * ng, ng,
+                            dx, dy, dt, limiter, _ptr(um), _ptr(vm), *[_ptr(o) for o in out])
+    return out
+
+
+def burgers_evolve(u, v, ng, dx, dy, dt, limiter):
+    """burgers Simulation.evolve: returns the updated (u, v) (valid cells updated, ghosts untouched)"""
+    u, v = _c(u).copy(), _c(v).copy()
+    lib().orc_burgers_evolve(_ptr(u), _ptr(v), u.shape[0] - 2 * ng, u.shape[1] - 2 * ng, ng, dx, dy, dt, limiter)
+    return u, v
+
+
+def incomp_evolve(planes, ng, dt, limiter=2, proj_type=2, vel_bc=(("periodic",) * 4, ("periodic",) * 4),
+                  phi_bc=("periodic",) * 4, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, dump=False):
+    """incompressible Simulation.evolve on SoA planes [x-velocity, y-velocity, phi-MAC, phi, gradp_x, gradp_y]
+    of shape (6, n + 2 ng, n + 2 ng), updated in place; returns (cycles_MAC, cycles_final[, stage arrays])"""
+    assert planes.flags.c_contiguous and planes.dtype == np.float64 and planes.shape[0] == 6
+    n = planes.shape[1] - 2 * ng
+    vb = np.array(_bc4(vel_bc[0]) + _bc4(vel_bc[1]), dtype=np.int32)
+    pb = np.array(_bc4(phi_bc), dtype=np.int32)
+    cyc = np.zeros(2, dtype=np.int32)
+    d = np.zeros((6,) + planes.shape[1:]) if dump else None
+    lib().orc_incomp_evolve(_ptr(planes), n, ng, xmin, xmax, ymin, ymax, dt, limiter, proj_type, _ptr(vb), _ptr(pb),
+                            _ptr(cyc), _ptr(d))
+    return (int(cyc[0]), int(cyc[1]), d) if dump else (int(cyc[0]), int(cyc[1]))

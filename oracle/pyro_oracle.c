@@ -919,3 +919,8 @@ int orc_mg_solve(orc_mg *m, double rtol, double source_norm, int max_cycles, dou
     free(old_phi); free(diff);
     return cycle - 1;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Burgers / incompressible explicit part + the incompressible evolve() (uses the helpers above)
+ * ---------------------------------------------------------------------------------------- */
+#include "incomp_oracle.c"

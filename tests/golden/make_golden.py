@@ -7,6 +7,8 @@ Outputs (small .npz files, committed):
   comp_<problem>.npz   Pyro("compressible") runs: parameters, initial state, per-step dt, final state
   mg_<case>.npz        CellCenterMG2d solves: rhs, solution, cycle count, residual / relative errors
   mgvc_<case>.npz      VarCoeffCCMG2d solves (the reference's mg_test_vc_* setups): coefficients, rhs, solution
+  incomp_<problem>.npz Pyro("incompressible") runs: state after initialize + preevolve, per-step dt, final state
+  burgers_test.npz     Pyro("burgers") run of its "test" problem
   mesh_bcs.npz         ghost fill of an integer array for every standard BC type (test_patch.py style)
   ref_kats.npz         known answers quoted from the reference's own unit tests / stored outputs
 """
@@ -109,6 +111,35 @@ def mgvc_case(name, nx, phibc, cbc, kind, rtol=1.e-11):
     print(name, "cycles", a.num_cycles, "resid", a.residual_error)
 
 
+INCOMP_VARS = ["x-velocity", "y-velocity", "phi-MAC", "phi", "gradp_x", "gradp_y"]
+
+
+def flow_case(fname, solver, problem, params, nsteps, names):
+    """incompressible / burgers: planes [var, i, j] after initialize_problem (which includes the
+    incompressible solver's preevolve), the dt of every step, the planes after nsteps"""
+    p = ref_shim.make_sim(solver, problem, dict(params, **{"driver.max_steps": 100000}))
+    sim = p.sim
+    g = sim.cc_data.grid
+    P0 = np.stack([np.asarray(sim.cc_data.get_var(n)) for n in names]).copy()
+    dts = []
+    for _ in range(nsteps):
+        if sim.finished():
+            break
+        p.single_step()
+        dts.append(sim.dt)
+    rp = sim.rp
+    keys = ["driver.cfl", "driver.tmax", "driver.init_tstep_factor", "driver.max_dt_change", "driver.fix_dt",
+            "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
+            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
+    keys += ["incompressible.limiter", "incompressible.proj_type"] if solver == "incompressible" else ["advection.limiter"]
+    np.savez_compressed(os.path.join(HERE, fname), problem=problem,
+                        inputs=np.array([f"{k}={v}" for k, v in params.items()]),
+                        rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]), names=np.array(names),
+                        ng=g.ng, P0=P0, P=np.stack([np.asarray(sim.cc_data.get_var(n)) for n in names]),
+                        dts=np.array(dts), t=sim.cc_data.t, n=sim.n)
+    print(fname, "steps", sim.n, "t", sim.cc_data.t)
+
+
 def mesh_bcs():
     from pyro.mesh import boundary as bnd
     from pyro.mesh import patch
@@ -158,5 +189,11 @@ if __name__ == "__main__":
     mgvc_case("periodic_64", 64, "periodic", "periodic", "periodic")
     mgvc_case("constant_32", 32, "dirichlet", "neumann", "constant")
     mgvc_case("dirichlet_128", 128, "dirichlet", "neumann", "dirichlet")
+    flow_case("incomp_shear32.npz", "incompressible", "shear", {"mesh.nx": 32, "mesh.ny": 32}, 12, INCOMP_VARS)
+    flow_case("incomp_shear64.npz", "incompressible", "shear", {"mesh.nx": 64, "mesh.ny": 64}, 6, INCOMP_VARS)
+    flow_case("incomp_converge32.npz", "incompressible", "converge",
+              {"mesh.nx": 32, "mesh.ny": 32, "driver.cfl": 0.5, "driver.fix_dt": 5.e-3, "driver.init_tstep_factor": 1.0}, 10,
+              INCOMP_VARS)
+    flow_case("burgers_test.npz", "burgers", "test", {"mesh.nx": 64, "mesh.ny": 64}, 12, ["x-velocity", "y-velocity"])
     mesh_bcs()
     ref_kats()

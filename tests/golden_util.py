@@ -30,6 +30,14 @@ def load_mgvc(name):
     return np.load(os.path.join(GOLDEN, f"mgvc_{name}.npz"))
 
 
+def load_flow(fname):
+    """incompressible / burgers fixtures: (npz, runtime parameters of the run, the inputs it was started with)"""
+    z = np.load(os.path.join(GOLDEN, fname))
+    rp = {s.split("=", 1)[0]: _parse(s.split("=", 1)[1]) for s in z["rp"]}
+    inputs = {s.split("=", 1)[0]: _parse(s.split("=", 1)[1]) for s in z["inputs"]}
+    return z, rp, inputs
+
+
 def var_bcs(rp):
     """BC names per conserved variable (density, energy, x-momentum, y-momentum) following
     pyro/simulation_null.py:71-112: 'reflect' is even, except odd for the momentum normal to it"""

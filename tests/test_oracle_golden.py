@@ -7,7 +7,7 @@ import pytest
 
 import oracle
 from conftest import rel_l2
-from golden_util import load_comp, load_mg, load_mgvc, var_bcs
+from golden_util import load_comp, load_flow, load_mg, load_mgvc, var_bcs
 
 
 def _run_oracle(z, rp, nsteps=None):
@@ -122,3 +122,39 @@ def test_ghost_fill_matches_reference_int_and_all_types():
             b = z[f"base_ng{ng}"].astype(np.float64).copy()
             oracle.fill_ghost(b, ng, (t,) * 4)
             assert np.array_equal(b, z[f"{t}_ng{ng}"].astype(np.float64))
+
+
+@pytest.mark.parametrize("fname", ["incomp_shear32.npz", "incomp_shear64.npz", "incomp_converge32.npz"])
+def test_incompressible_run_matches_reference(fname):
+    """Pyro("incompressible") fixtures: the oracle's evolve (explicit part + two multigrid projections)
+    stepped with the recorded dts reproduces all six state planes bit for bit"""
+    z, rp, _ = load_flow(fname)
+    ng = int(z["ng"])
+    P = np.ascontiguousarray(z["P0"])
+    bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
+    assert bc == ("periodic",) * 4
+    for dt in z["dts"]:
+        for k in range(6):          # the driver's fill_BC_all before every step (pyro_sim.py:241-256)
+            oracle.fill_ghost(P[k], ng, bc)
+        oracle.incomp_evolve(P, ng, float(dt), limiter=rp["incompressible.limiter"], proj_type=rp["incompressible.proj_type"],
+                             vel_bc=(bc, bc), phi_bc=bc, xmin=rp["mesh.xmin"], xmax=rp["mesh.xmax"],
+                             ymin=rp["mesh.ymin"], ymax=rp["mesh.ymax"])
+    assert np.array_equal(P, z["P"])
+
+
+def test_burgers_run_matches_reference():
+    z, rp, _ = load_flow("burgers_test.npz")
+    ng = int(z["ng"])
+    u, v = z["P0"][0].copy(), z["P0"][1].copy()
+    n = rp["mesh.nx"]
+    dx = (rp["mesh.xmax"] - rp["mesh.xmin"]) / n
+    bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
+    for step, dt in enumerate(z["dts"]):
+        oracle.fill_ghost(u, ng, bc)
+        oracle.fill_ghost(v, ng, bc)
+        # burgers/simulation.py:41-58 (then the driver's first-step factor and growth limit, both inactive here)
+        raw = rp["driver.cfl"] * min(dx / max(np.abs(u).max(), 1.e-12), dx / max(np.abs(v).max(), 1.e-12))
+        if step > 0 and z["t"] > 0:
+            assert raw >= float(dt) * (1 - 1e-15)
+        u, v = oracle.burgers_evolve(u, v, ng, dx, dx, float(dt), rp["advection.limiter"])
+    assert np.array_equal(u, z["P"][0]) and np.array_equal(v, z["P"][1])
