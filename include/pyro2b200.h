@@ -173,6 +173,49 @@ int p2b_mg_set_coeffs(p2b_mg* m, void* device_mem, long long bytes, const double
                       const int* coeffs_bc, void* stream);
 void* p2b_mg_coeff_ptr(p2b_mg* m, int level, int which);
 
+/* ---- Burgers / incompressible explicit stages (the callers of the multigrid path).
+ * pyro/burgers/burgers_interface.py:4-312, pyro/incompressible/incomp_interface.py:4-211,
+ * pyro/mesh/reconstruction.py:11-120 and the array expressions of pyro/incompressible/simulation.py:67-404
+ * and pyro/burgers/simulation.py:41-131.  A p2b_flow handle describes the solver grid (ng >= 4; all planes
+ * share g->pitch) and owns 16 scratch planes in caller memory (p2b_flow_workspace_bytes, ZERO-INITIALISED:
+ * they stand in for the reference's grid.scratch_array() temporaries).  u, v, gradp_x, gradp_y, phi are the
+ * solver's state planes (device pointers, ghost cells filled by p2b_fill_ghost_f64).  Every array a stage
+ * produces is bit-identical to the reference's.  Call order of one incompressible step (simulation.py:159-404):
+ *   interface_states -> mac_vels -> mac_divergence -> [multigrid solve] -> mac_project -> upwind_states ->
+ *   advect_update -> [ghost fill] -> cc_divergence -> [multigrid solve] -> project -> [ghost fill]          */
+typedef struct p2b_flow p2b_flow;
+
+p2b_flow* p2b_flow_create(const p2b_grid* g);
+int p2b_flow_destroy(p2b_flow* f);
+long long p2b_flow_workspace_bytes(p2b_flow* f);
+int p2b_flow_bind(p2b_flow* f, void* device_mem, long long bytes);
+/* scratch plane n: 0..7 u_xl u_xr u_yl u_yr v_xl v_xr v_yl v_yr, 8..9 transverse Riemann velocities,
+ * 10..13 u_xint v_xint u_yint v_yint, 14..15 u_MAC v_MAC */
+void* p2b_flow_plane(p2b_flow* f, int n);
+/* limited slopes + get_interface_states + apply_transverse_corrections (+ apply_gradp_corrections unless
+ * gradp_x = gradp_y = NULL, the Burgers case) */
+int p2b_flow_interface_states(p2b_flow* f, const double* u, const double* v, const double* gradp_x,
+                              const double* gradp_y, double dt, int limiter, void* stream);
+int p2b_flow_mac_vels(p2b_flow* f, void* stream);                       /* riemann_and_upwind */
+/* (u_MAC.ip(1) - u_MAC.v())/dx + (v_MAC.jp(1) - v_MAC.v())/dy -> valid cells of an (nx+2) x (ny+2) plane */
+int p2b_flow_mac_divergence(p2b_flow* f, double* div, int div_pitch, void* stream);
+/* u_MAC, v_MAC -= face gradient of phi_mac (solver-grid plane holding the multigrid solution in buf = 1) */
+int p2b_flow_mac_project(p2b_flow* f, const double* phi_mac, void* stream);
+int p2b_flow_upwind_states(p2b_flow* f, void* stream);                  /* incomp_interface.states' upwinds */
+int p2b_flow_advect_update(p2b_flow* f, double* u, double* v, const double* gradp_x, const double* gradp_y,
+                           double dt, int proj_type, void* stream);
+/* 0.5*(u.ip(1) - u.ip(-1))/dx + 0.5*(v.jp(1) - v.jp(-1))/dy [ / dt when divide != 0 ] */
+int p2b_flow_cc_divergence(p2b_flow* f, const double* u, const double* v, double* div, int div_pitch, double dt,
+                           int divide, void* stream);
+/* u, v -= dt * centred grad(phi); proj_type 1: gradp += grad, 2: gradp = grad, 0: gradp untouched
+ * (dt = 1, proj_type = 0 is preevolve's initial projection) */
+int p2b_flow_project(p2b_flow* f, const double* phi, double* u, double* v, double* gradp_x, double* gradp_y,
+                     double dt, int proj_type, void* stream);
+/* Burgers: construct_unsplit_fluxes + the conservative update (after interface_states and mac_vels) */
+int p2b_flow_burgers_update(p2b_flow* f, double* u, double* v, double dt, void* stream);
+/* bit patterns of max|u|, max|v| over the full arrays (atomic max into scratch[0..1], zeroed by the caller) */
+int p2b_flow_maxabs(p2b_flow* f, const double* u, const double* v, uint64_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # P2B_SO overrides the library path (A/B timing of kernel variants during development)
 SO_PATH = os.environ.get("P2B_SO") or os.path.join(CSRC, "libpyro2b200.so")
-SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu"]
-HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "../../include/pyro2b200.h"]
+SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "../../include/pyro2b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -97,6 +97,21 @@ SIGNATURES = {
     "p2b_mg_coeff_workspace_bytes": (_ll, [_vp]),
     "p2b_mg_set_coeffs": (_i, [_vp, _vp, _ll, _vp, _i, C.POINTER(_i), _vp]),
     "p2b_mg_coeff_ptr": (_vp, [_vp, _i, _i]),
+    "p2b_flow_create": (_vp, [_PG]),
+    "p2b_flow_destroy": (_i, [_vp]),
+    "p2b_flow_workspace_bytes": (_ll, [_vp]),
+    "p2b_flow_bind": (_i, [_vp, _vp, _ll]),
+    "p2b_flow_plane": (_vp, [_vp, _i]),
+    "p2b_flow_interface_states": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_flow_mac_vels": (_i, [_vp, _vp]),
+    "p2b_flow_mac_divergence": (_i, [_vp, _vp, _i, _vp]),
+    "p2b_flow_mac_project": (_i, [_vp, _vp, _vp]),
+    "p2b_flow_upwind_states": (_i, [_vp, _vp]),
+    "p2b_flow_advect_update": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_flow_cc_divergence": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
+    "p2b_flow_project": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_flow_burgers_update": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "p2b_flow_maxabs": (_i, [_vp, _vp, _vp, _vp, _vp]),
 }
 
 

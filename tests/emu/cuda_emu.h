@@ -136,6 +136,14 @@ inline void __syncthreads()
 }
 inline double __shfl_up_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) - d); }
 inline double __shfl_down_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) + d); }
+inline double __shfl_xor_sync(unsigned, double v, int m) { return emu::exchange(v, (emu::lin_tid & 31) ^ m); }
+inline long long __double_as_longlong(double x) { long long b; memcpy(&b, &x, 8); return b; }
+inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v)
+{
+    const unsigned long long old = *a;       // fibers never run concurrently
+    if (v > old) *a = v;
+    return old;
+}
 
 #define P2B_LAUNCH(kernel, grid, block, smem, stream) ::emu::bind_launch(kernel, grid, block, smem)
 #define P2B_DYN_SMEM(type, name) type* name = (type*)::emu::dyn_smem

@@ -3,121 +3,18 @@ compiled for the host through tests/emu/cuda_emu.h and driven through the same p
 numpy memory, compared bit-for-bit with the oracle.  One fiber per CUDA thread for the kernels that
 synchronise (temporally blocked smoother, fused coarse V-cycle, reductions).  The emulator is test
 infrastructure: the product only loads the nvcc-built library and has no CPU path."""
-import ctypes as C
-import math
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
 import oracle
+from emu_util import EmuMG, load_mg_emu
 from golden_util import load_mg, load_mgvc
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-EMU_DIR = os.path.join(HERE, "emu")
-CSRC = os.path.join(os.path.dirname(HERE), "pyro2_b200", "csrc")
-BC = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2, "periodic": 3}
 
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libmg_emu.so")
-    deps = [os.path.join(EMU_DIR, f) for f in ("mg_emu.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("mg.cu", "mg_kernels.cuh", "hydro_core.cuh", "common.cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-x", "c++", "-DP2B_EMU_HEADER=\"../../tests/emu/cuda_emu.h\"",
-                               "-DMG_COARSE_THREADS=128", "-o", so, os.path.join(EMU_DIR, "mg_emu.cpp")],
-                              cwd=EMU_DIR)
-    lib = C.CDLL(so)
-    from pyro2_b200 import _lib
-    for name, (res, args) in _lib.SIGNATURES.items():
-        if name.startswith("p2b_mg_") or name == "p2b_last_error":
-            f = getattr(lib, name)
-            f.restype, f.argtypes = res, args
-    return lib
-
-
-class EmuMG:
-    """solve() of pyro2_b200/multigrid/MG.py re-stated over the emulated library (host memory)"""
-
-    def __init__(self, lib, nx, bc=("dirichlet",) * 4, alpha=0.0, beta=-1.0, blocking=True):
-        self.lib, self.nx = lib, nx
-        codes = (C.c_int * 4)(*[BC[b] for b in bc])
-        self.h = lib.p2b_mg_create(nx, codes, alpha, beta, 0.0, 1.0, 0.0, 1.0, 10, 50)
-        assert self.h, lib.p2b_last_error()
-        self.nlevels = lib.p2b_mg_nlevels(self.h)
-        nbytes = lib.p2b_mg_workspace_bytes(self.h)
-        self.ws = np.zeros(nbytes // 8 + 2)
-        off = (-self.ws.ctypes.data // 8) % 2          # 16-byte alignment
-        self.base = self.ws[off:]
-        self.ck(lib.p2b_mg_bind(self.h, self.base.ctypes.data, nbytes))
-        if not blocking:
-            self.ck(lib.p2b_mg_set_blocking(self.h, 0))
-        self.out = np.zeros(2)
-        self.keep = []
-
-    def ck(self, rc):
-        assert rc == 0, self.lib.p2b_last_error().decode()
-
-    def close(self):
-        self.lib.p2b_mg_destroy(self.h)
-
-    def plane(self, level, which):
-        n = 2 << level
-        pitch = self.lib.p2b_mg_level_pitch(self.h, level)
-        ptr = self.lib.p2b_mg_level_ptr(self.h, level, {"v": 0, "f": 1, "r": 2, "w": 3}[which])
-        off = (ptr - self.base.ctypes.data) // 8
-        return np.lib.stride_tricks.as_strided(self.base[off:], (n + 2, n + 2), (pitch * 8, 8))
-
-    def set_bc_values(self, xl, xr, yl, yr):
-        vals = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (xl, xr, yl, yr)]
-        self.keep = vals
-        self.ck(self.lib.p2b_mg_set_bc_values(self.h, *[None if v is None else v.ctypes.data for v in vals]))
-
-    def set_coeffs(self, coeffs, coeffs_bc):
-        nbytes = self.lib.p2b_mg_coeff_workspace_bytes(self.h)
-        self.cws = np.zeros(nbytes // 8 + 2)
-        off = (-self.cws.ctypes.data // 8) % 2
-        self.cbase = self.cws[off:]
-        c = np.ascontiguousarray(coeffs, dtype=np.float64)
-        codes = (C.c_int * 4)(*[BC[b] for b in coeffs_bc])
-        self.ck(self.lib.p2b_mg_set_coeffs(self.h, self.cbase.ctypes.data, nbytes, c.ctypes.data, c.shape[1], codes, None))
-
-    def coef_plane(self, level, which):
-        n = 2 << level
-        pitch = self.lib.p2b_mg_level_pitch(self.h, level)
-        ptr = self.lib.p2b_mg_coeff_ptr(self.h, level, {"c": 0, "ex": 1, "ey": 2}[which])
-        off = (ptr - self.cbase.ctypes.data) // 8
-        return np.lib.stride_tricks.as_strided(self.cbase[off:], (n + 2, n + 2), (pitch * 8, 8))
-
-    def sumsq(self, level, which):
-        self.ck(self.lib.p2b_mg_norm2(self.h, level, {"v": 0, "f": 1, "r": 2}[which], self.out.ctypes.data, None))
-        return float(self.out[0])
-
-    def solve(self, f, rtol=1e-11, max_cycles=100):
-        fine = self.nlevels - 1
-        n = self.nx
-        h2 = (1.0 / n) ** 2
-        self.plane(fine, "v")[:] = 0.0
-        self.plane(fine, "f")[:] = f
-        self.source_norm = math.sqrt(h2 * self.sumsq(fine, "f"))
-        pitch = self.lib.p2b_mg_level_pitch(self.h, fine)
-        old_phi = np.zeros((n + 2, pitch))
-        old_phi[:, :n + 2] = self.plane(fine, "v")
-        cycle, resid = 1, 1e33
-        while resid > rtol and cycle <= max_cycles:
-            self.ck(self.lib.p2b_mg_zero_coarse(self.h, None))
-            self.ck(self.lib.p2b_mg_vcycle(self.h, None))
-            self.ck(self.lib.p2b_mg_cycle_diagnostics(self.h, old_phi.ctypes.data, self.out.ctypes.data, None))
-            rnorm = math.sqrt(h2 * self.out[1])
-            resid = rnorm / self.source_norm if self.source_norm != 0.0 else rnorm
-            cycle += 1
-        self.ck(self.lib.p2b_mg_fill_bc(self.h, fine, None))
-        self.num_cycles = cycle - 1
-        self.residual_error = resid
-        return self.plane(fine, "v").copy()
+    return load_mg_emu()
 
 
 @pytest.mark.parametrize("name,blocking", [("poisson_dirichlet_64", True), ("poisson_periodic_64", True),
