@@ -49,4 +49,17 @@ SOLVER = {
         "sponge.do_sponge": (0, "not supported"),
         "particles.do_particles": (0, ""),
     },
+    "burgers": {
+        "driver.cfl": (0.8, "advective CFL number"),
+        "advection.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
+        "particles.do_particles": (0, "not supported"),
+        "particles.particle_generator": ("grid", ""),
+    },
+    "incompressible": {
+        "driver.cfl": (0.8, ""),
+        "incompressible.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
+        "incompressible.proj_type": (2, "what is projected: 1 includes the -Gp term in U*"),
+        "particles.do_particles": (0, "not supported"),
+        "particles.particle_generator": ("grid", ""),
+    },
 }

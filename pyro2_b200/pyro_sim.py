@@ -14,7 +14,7 @@ from .util import msg
 from .util import profile_pyro as profile
 from .util.runparams import RuntimeParameters
 
-valid_solvers = ["compressible"]
+valid_solvers = ["burgers", "compressible", "incompressible"]
 
 
 class Pyro:
