@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-mg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-incomp", action="store_true", help="skip the incompressible-shear leg (N = 1 only)")
+    ap.add_argument("--incomp-nx", type=int, default=2048)
     return ap.parse_args()
 
 
@@ -167,6 +169,26 @@ def cpu_mg(n, cycles):
         o.v_cycle()
     dt = time.perf_counter() - t0
     return cycles / dt, dt
+
+
+def cpu_incompressible(n):
+    """one step of the incompressible shear problem through the oracle (explicit stages + both projections)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import math
+    import numpy as np
+    import oracle
+    ng = 4
+    c = (np.arange(n + 2 * ng) + 0.5 - ng) / n
+    X, Y = np.meshgrid(c, c, indexing="ij")
+    P = np.zeros((6, n + 2 * ng, n + 2 * ng))
+    P[0] = np.where(Y <= 0.5, np.tanh(42.0 * (Y - 0.25)), np.tanh(42.0 * (0.75 - Y)))
+    P[1] = 0.05 * np.sin(2.0 * math.pi * X)
+    dt = 0.8 * min(1.0 / n / np.abs(P[0]).max(), 1.0 / n / np.abs(P[1]).max())
+    for k in range(6):
+        oracle.fill_ghost(P[k], ng, ("periodic",) * 4)
+    t0 = time.perf_counter()
+    cyc = oracle.incomp_evolve(P, ng, dt)
+    return time.perf_counter() - t0, cyc
 
 
 def host_threads():
@@ -383,6 +405,38 @@ def main():
                                    "blocked smoother moves ~40% of it"}}
         del a
 
+    # ---- incompressible shear 2048^2 (BASELINE config 4): explicit stages + two multigrid projections ----
+    incomp = None
+    if world == 1 and not args.skip_incomp:
+        torch.cuda.empty_cache()
+        ni = args.incomp_nx
+        pi = Pyro("incompressible")
+        pi.initialize_problem("shear", inputs_dict={"mesh.nx": ni, "mesh.ny": ni, "driver.max_steps": 10 ** 9,
+                                                    "driver.tmax": 1.e9})
+        isim = pi.sim
+        pi.single_step()
+        barrier()
+        ki = 3
+        cyc = 0
+        e0.record()
+        for _ in range(ki):
+            pi.single_step()
+        e1.record()
+        barrier()
+        ims = e0.elapsed_time(e1) / ki
+        solver = next(iter(isim._mg.values()))[0]
+        incomp = {"metric": "zone-updates/s", "value": ni * ni / (ims * 1e-3), "unit": "zone-updates/s", "ms_per_step": ims,
+                  "steps": ki, "config": {"workload": f"incompressible shear {ni}^2 fp64, periodic, limiter 2, proj_type 2",
+                                          "note": "each step = p2b_flow_* explicit stages + 2 multigrid projections at rtol 1e-12; "
+                                                  "at this size the reference's own stopping rule runs both to max_cycles = 100"},
+                  "v_cycles_last_solve": solver.num_cycles, "gpu_launches_explicit": 14}
+        if rank == 0 and not args.skip_cpu:
+            nc = min(ni, 1024)
+            secs, cyc = cpu_incompressible(nc)
+            incomp["cpu_baseline"] = {"value": nc * nc / secs, "unit": "zone-updates/s", "cores": host_threads(), "kind": "port",
+                                      "sample": f"1 step of the {nc}^2 shear problem ({cyc[0]} + {cyc[1]} V-cycles, {secs:.1f} s)"}
+        del pi, isim, solver
+
     # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -405,7 +459,7 @@ def main():
                        "l2": "state (2 x 539 MB at 4096^2) is larger than L2; no flush needed",
                        "sweep": ops.sweep_info()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
-            "roofline": roofline, "cpu_baseline": cpu, "mg": mg,
+            "roofline": roofline, "cpu_baseline": cpu, "mg": mg, "incompressible": incomp,
         }
         emit(line)
     if world > 1:
