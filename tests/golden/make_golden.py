@@ -178,6 +178,9 @@ if __name__ == "__main__":
     comp_case("quad64", "quad", {"mesh.nx": 64, "mesh.ny": 64, "driver.tmax": 0.3}, 40)
     comp_case("sod_x", "sod", {}, 1000)          # the reference's own regression setup: 128x10, limiter 1, 76 steps
     comp_case("kh32", "kh", {"mesh.nx": 32, "mesh.ny": 32, "driver.tmax": 0.2}, 25)
+    comp_case("acoustic64", "acoustic_pulse", {"mesh.nx": 64, "mesh.ny": 64, "driver.fix_dt": 3.0e-3}, 20)
+    comp_case("advect32", "advect", {"mesh.nx": 32, "mesh.ny": 32, "driver.fix_dt": 0.01}, 20)   # limiter 0
+    comp_case("gresho40", "gresho", {}, 15)
     mg_case("poisson_dirichlet_64", 64, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
     mg_case("poisson_dirichlet_256", 256, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
     mg_case("poisson_periodic_64", 64, ("periodic",) * 4, 0.0, -1.0, "periodic", 1.e-11)

@@ -17,7 +17,7 @@ from golden_util import GOLDEN, load_comp, load_mg, load_mgvc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32"])
+@pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40"])
 def test_pyro_compressible_run_matches_reference(name):
     from pyro2_b200.pyro_sim import Pyro
     z, rp, inputs = load_comp(name)

@@ -10,7 +10,7 @@ from conftest import rel_l2
 from golden_util import load_comp, load_flow, load_mg, load_mgvc, var_bcs
 
 
-def _run_oracle(z, rp, nsteps=None):
+def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
     ng = int(z["ng"])
     U = z["U0"].copy()
     nx, ny = rp["mesh.nx"], rp["mesh.ny"]
@@ -31,6 +31,8 @@ def _run_oracle(z, rp, nsteps=None):
         # NullSimulation.compute_timestep (simulation_null.py:222-244)
         dt = rp["driver.init_tstep_factor"] * dt if n == 0 else min(rp["driver.max_dt_change"] * dt_old, dt)
         dt_old = dt
+        if fix_dt > 0.0:
+            dt = fix_dt
         if t + dt > rp["driver.tmax"]:
             dt = rp["driver.tmax"] - t
         U = oracle.compressible_step(U, ng, dx, dy, dt, prm)
@@ -39,10 +41,10 @@ def _run_oracle(z, rp, nsteps=None):
     return U, np.array(dts), ng
 
 
-@pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32"])
+@pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40"])
 def test_compressible_run_matches_reference(name):
-    z, rp, _ = load_comp(name)
-    U, dts, ng = _run_oracle(z, rp)
+    z, rp, inputs = load_comp(name)
+    U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
     ref = z["U"]
     v = (slice(ng, -ng), slice(ng, -ng))
     assert np.allclose(dts, z["dts"], rtol=1e-12, atol=0)
