@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
-            "periodic": 3}
+            "periodic": 3, "hse": 4, "none": 4}   # 4: leave that side alone (user BCs are filled separately)
 
 
 def build(force=False):
@@ -29,7 +29,8 @@ def build(force=False):
 class CompParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double),
                 ("delta", C.c_double), ("cvisc", C.c_double), ("limiter", C.c_int),
-                ("use_flattening", C.c_int), ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int)]
+                ("use_flattening", C.c_int), ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
+                ("grav", C.c_double), ("src_bc", C.c_int * 16)]
 
 
 _STAGE_NAMES = ["q", "xi", "ldx", "ldy", "Uxl_hat", "Uxr_hat", "Uyl_hat", "Uyr_hat", "Fx_t", "Fy_t",
@@ -54,6 +55,8 @@ def lib():
         L.orc_compressible_step.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                             C.c_double, C.POINTER(CompParams), C.POINTER(CompStages)]
         L.orc_compressible_step.restype = C.c_int
+        L.orc_fill_hse.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.orc_fill_hse.restype = None
         L.orc_mg_create.argtypes = [C.c_int, C.POINTER(C.c_int * 4)] + [C.c_double] * 6 + [C.c_int] * 2
         L.orc_mg_create.restype = C.c_void_p
         L.orc_mg_destroy.argtypes = [C.c_void_p]
@@ -130,8 +133,22 @@ def cfl_dt(U_ijn, ng, dx, dy, gamma, cfl):
 
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
-                no_avisc_xhi=1, no_avisc_yhi=1):
-    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi)
+                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None):
+    """src_bcs: BC names (xlb, xrb, ylb, yrb) of the four source arrays in variable order dens, ener, xmom,
+    ymom (only needed with gravity); "hse" copies like outflow for them"""
+    codes = (C.c_int * 16)()
+    if src_bcs is not None:
+        flat = [BC_CODES["outflow" if b == "hse" else b] for bc in src_bcs for b in bc]
+        codes = (C.c_int * 16)(*flat)
+    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes)
+
+
+def fill_hse(P, ng, dy, grav, gamma, var, side):
+    """the "hse" boundary of compressible/BC.py for plane `var` (0 dens, 1 ener, 2 xmom, 3 ymom) of the SoA
+    state P[n, i, j] on side "ylb" / "yrb", in place"""
+    assert P.flags.c_contiguous and P.dtype == np.float64 and P.shape[0] == 4
+    lib().orc_fill_hse(_ptr(P), P.shape[1] - 2 * ng, P.shape[2] - 2 * ng, ng, dy, grav, gamma, var,
+                       {"ylb": 0, "yrb": 1}[side])
 
 
 def compressible_step(U_ijn, ng, dx, dy, dt, params=None, stages=False, planes=False):

@@ -139,6 +139,11 @@ typedef struct {
     int use_flattening; /* 0/1 */
     int no_avisc_xhi;   /* 1 (default): reproduce SURVEY 9.2-13, avisco_x not set on the +x face */
     int no_avisc_yhi;
+    /* gravity along -y (compressible.grav); src_bc = BC codes (xl, xr, yl, yr) of the four source arrays
+       dens_src, E_src, xmom_src, ymom_src in VARIABLE-INDEX order (dens, ener, xmom, ymom); the "hse" type
+       copies the first interior row like outflow (compressible/BC.py:55-63, 111-117) */
+    double grav;
+    int src_bc[16];
 } orc_comp_params;
 
 /* optional per-stage dumps, each (4 or 1) planes of qx*qy doubles; NULL = skip */
@@ -478,8 +483,41 @@ static void dump(double *dst, const double *src, size_t n)
     if (dst) memcpy(dst, src, n * sizeof(double));
 }
 
-/* one evolve() of compressible/simulation.py:290-450 (grav = 0, Cartesian, HLLC, no sponge,
- * no particles).  U (4 planes, ghosts already filled) is updated in place on the valid region.
+/* the compressible solver's "hse" boundary (compressible/BC.py:21-139) for ONE variable on ONE y side,
+ * as fill_BC(name) applies it after the standard x fill: all variables but the energy copy the first
+ * interior row; the energy integrates hydrostatic equilibrium outward at constant density from the
+ * pressure of that row (over the whole x extent, whatever the other variables' x ghost cells hold at
+ * that moment).  U = 4 planes (dens, ener, xmom, ymom); var = plane index; side 0 = ylb, 1 = yrb */
+void orc_fill_hse(double *U, int nx, int ny, int ng, double dy, double grav, double gamma, int var, int side)
+{
+    const int qx = nx + 2 * ng, qy = ny + 2 * ng;
+    const size_t np = (size_t)qx * qy;
+    const int jb = side == 0 ? ng : ng + ny - 1;          /* jlo / jhi */
+    const int step = side == 0 ? -1 : 1;
+    double *v = U + (size_t)var * np;
+    if (var != IENER) {
+        for (int i = 0; i < qx; i++)
+            for (int k = 1; k <= ng; k++) v[IDX(i, jb + step * k)] = v[IDX(i, jb)];
+        return;
+    }
+    const double *dens = U + IDENS * np, *xmom = U + IXMOM * np, *ymom = U + IYMOM * np;
+    for (int i = 0; i < qx; i++) {
+        const size_t kb = IDX(i, jb);
+        const double dens_base = dens[kb];
+        const double ke_base = 0.5 * (xmom[kb] * xmom[kb] + ymom[kb] * ymom[kb]) / dens[kb];
+        const double eint_base = (v[kb] - ke_base) / dens[kb];
+        double pres_base = dens_base * eint_base * (gamma - 1.0);
+        for (int k = 1; k <= ng; k++) {
+            /* ylb: pres_below = pres_base - grav*dens_base*dy;  yrb: pres_above = pres_base + grav*dens_base*dy */
+            const double pnext = side == 0 ? pres_base - grav * dens_base * dy : pres_base + grav * dens_base * dy;
+            v[IDX(i, jb + step * k)] = pnext / (gamma - 1.0) + ke_base;
+            pres_base = pnext;
+        }
+    }
+}
+
+/* one evolve() of compressible/simulation.py:290-450 (Cartesian, HLLC, gravity, no sponge,
+ * no particles, no problem sources).  U (4 planes, ghosts already filled) is updated in place on the valid region.
  * returns 0, or 3 if the cons_to_prim assertion (simulation.py:71) would fire. */
 int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double dy, double dt,
                           const orc_comp_params *P, const orc_comp_stages *S)
@@ -535,7 +573,33 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->Uxl_hat, U_xl, 4 * np); dump(S->Uxr_hat, U_xr, 4 * np);
     dump(S->Uyl_hat, U_yl, 4 * np); dump(S->Uyr_hat, U_yr, 4 * np);
 
-    /* apply_source_terms (unsplit_fluxes.py:247-330): all sources are zero for grav = 0 */
+    /* apply_source_terms (unsplit_fluxes.py:247-330) with get_external_sources (simulation.py:105-128):
+       S_ymom = dens * grav, S_ener = ymom * grav over the whole (ghost-filled) array, the source arrays
+       then get THEIR OWN ghost fill, and half a time step of them goes to the buf = 1 interface states */
+    if (P->grav != 0.0) {
+        double *src = zalloc(4 * np);
+        for (size_t k = 0; k < np; k++) {
+            src[IYMOM * np + k] = U[IDENS * np + k] * P->grav;
+            src[IENER * np + k] = U[IYMOM * np + k] * P->grav;
+        }
+        for (int n = 0; n < 4; n++)
+            orc_fill_ghost_f64(src + n * np, nx, ny, ng, P->src_bc[4 * n], P->src_bc[4 * n + 1], P->src_bc[4 * n + 2],
+                               P->src_bc[4 * n + 3], NULL, NULL, NULL, NULL, dx, dy);
+        const int vars[3] = {IXMOM, IYMOM, IENER};
+        for (int m = 0; m < 3; m++) {
+            const int n = vars[m];
+            const double *sv = src + n * np;
+            double *xl = U_xl + n * np, *xr = U_xr + n * np, *yl = U_yl + n * np, *yr = U_yr + n * np;
+            for (int i = ng - 1; i <= ng + nx; i++)
+                for (int j = ng - 1; j <= ng + ny; j++) {
+                    xl[IDX(i, j)] += 0.5 * dt * sv[IDX(i - 1, j)];
+                    xr[IDX(i, j)] += 0.5 * dt * sv[IDX(i, j)];
+                    yl[IDX(i, j)] += 0.5 * dt * sv[IDX(i, j - 1)];
+                    yr[IDX(i, j)] += 0.5 * dt * sv[IDX(i, j)];
+                }
+        }
+        free(src);
+    }
 
     /* apply_transverse_flux (unsplit_fluxes.py:420-471) */
     riemann_hllc(1, U_xl, U_xr, F_x, qx, qy, ng, gamma);
@@ -584,6 +648,9 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->Fx, F_x, 4 * np); dump(S->Fy, F_y, 4 * np);
 
     /* conservative update (simulation.py:377-384) */
+    double *Uold_dens = zalloc(np), *Uold_ymom = zalloc(np);
+    memcpy(Uold_dens, U + IDENS * np, np * sizeof(double));
+    memcpy(Uold_ymom, U + IYMOM * np, np * sizeof(double));
     {
         const double dtdV = dt / (dx * dy), Ax = dy, Ay = dx;
         for (int n = 0; n < 4; n++) {
@@ -596,8 +663,26 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
                                               fy[IDX(i, j)] * Ay - fy[IDX(i, j + 1)] * Ay);
         }
     }
-    /* sources: zero (grav = 0, no problem source); clean_state is a no-op for the default
-       small_dens = -1e200 */
+    /* external sources, predictor-corrector (simulation.py:398-423, get_external_sources :105-160):
+       U += dt S(U_old); S_new uses the updated density and a time-centred y-momentum;
+       U += dt/2 (S_new - S_old).  clean_state is a no-op for the default small_dens = -1e200 */
+    if (P->grav != 0.0) {
+        const double g = P->grav;
+#pragma omp parallel for
+        for (int i = ng; i < ng + nx; i++)
+            for (int j = ng; j < ng + ny; j++) {
+                const size_t k = IDX(i, j);
+                const double so_y = Uold_dens[k] * g, so_e = Uold_ymom[k] * g;
+                U[IYMOM * np + k] += dt * so_y;
+                U[IENER * np + k] += dt * so_e;
+                const double sn_y = U[IDENS * np + k] * g;
+                const double ymom_new = U[IYMOM * np + k] + 0.5 * dt * (sn_y - so_y);
+                const double sn_e = ymom_new * g;
+                U[IYMOM * np + k] += 0.5 * dt * (sn_y - so_y);
+                U[IENER * np + k] += 0.5 * dt * (sn_e - so_e);
+            }
+    }
+    free(Uold_dens); free(Uold_ymom);
 
     free(q); free(xi); free(xi_x); free(xi_y); free(ldx); free(ldy); free(tmp); free(tmp2);
     free(V_l); free(V_r); free(U_xl); free(U_xr); free(U_yl); free(U_yr); free(F_x); free(F_y);

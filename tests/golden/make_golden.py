@@ -40,7 +40,7 @@ def comp_case(name, problem, params, nsteps):
             "compressible.z0", "compressible.z1", "compressible.delta", "driver.cfl", "driver.tmax",
             "driver.init_tstep_factor", "driver.max_dt_change",
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
-            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
+            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav"]
     np.savez_compressed(os.path.join(HERE, f"comp_{name}.npz"),
                         problem=problem, inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]),
@@ -181,6 +181,12 @@ if __name__ == "__main__":
     comp_case("acoustic64", "acoustic_pulse", {"mesh.nx": 64, "mesh.ny": 64, "driver.fix_dt": 3.0e-3}, 20)
     comp_case("advect32", "advect", {"mesh.nx": 32, "mesh.ny": 32, "driver.fix_dt": 0.01}, 20)   # limiter 0
     comp_case("gresho40", "gresho", {}, 15)
+    # gravity + the compressible solver's "hse" boundary (compressible/BC.py)
+    comp_case("bubble32", "bubble", {"mesh.nx": 32, "mesh.ny": 64, "mesh.ymax": 4.0}, 25)
+    comp_case("rt16", "rt", {"mesh.nx": 16, "mesh.ny": 48}, 25)
+    comp_case("hse16", "hse", {"mesh.nx": 16, "mesh.ny": 48}, 20)
+    comp_case("rt16_reflect", "rt", {"mesh.nx": 16, "mesh.ny": 48, "mesh.xlboundary": "reflect", "mesh.xrboundary": "outflow",
+                                     "mesh.ylboundary": "reflect", "mesh.yrboundary": "reflect"}, 20)
     mg_case("poisson_dirichlet_64", 64, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
     mg_case("poisson_dirichlet_256", 256, ("dirichlet",) * 4, 0.0, -1.0, "poly", 1.e-11)
     mg_case("poisson_periodic_64", 64, ("periodic",) * 4, 0.0, -1.0, "periodic", 1.e-11)
