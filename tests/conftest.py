@@ -41,6 +41,24 @@ def rel_l2(a, b):
     return np.linalg.norm((a - b).ravel()) / (n if n > 0 else 1.0)
 
 
+def state_errors(U, ref, gamma=1.4):
+    """per-variable relative L2 errors of a conserved state [i, j, (dens, ener, xmom, ymom)] against `ref`.
+    A momentum component that is pure round-off noise in the reference (a static atmosphere: |m| ~ 1e-16) has
+    no meaningful relative error of its own; it is then measured against the acoustic momentum scale rho*cs."""
+    U = np.asarray(U, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    dens, ener, xmom, ymom = (ref[..., n] for n in range(4))
+    p = (ener - 0.5 * (xmom ** 2 + ymom ** 2) / dens) * (gamma - 1.0)
+    acoustic = np.linalg.norm((dens * np.sqrt(np.abs(gamma * p / dens))).ravel())
+    errs = []
+    for n in range(4):
+        scale = np.linalg.norm(ref[..., n].ravel())
+        if n >= 2 and scale < 1e-6 * acoustic:
+            scale = acoustic
+        errs.append(np.linalg.norm((U[..., n] - ref[..., n]).ravel()) / (scale if scale > 0 else 1.0))
+    return errs
+
+
 def make_state(nx, ny, ng, kind, seed=0, gamma=1.4):
     """synthetic conserved state [i, j, n] with ghosts (not yet filled consistently)"""
     rng = np.random.default_rng(seed)
