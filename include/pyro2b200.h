@@ -55,6 +55,11 @@ typedef struct {
     int use_flattening;
     int no_avisc_xhi;        /* 1 on the global +x face: reference leaves avisco_x unset there */
     int no_avisc_yhi;        /*   (pyro/compressible/interface.py:366-367); 0 on interior slab faces */
+    double grav;             /* compressible.grav: constant acceleration along y (0 = the gravity-free kernel);
+                              * sources as in pyro/compressible/simulation.py:105-160, 398-423 and
+                              * unsplit_fluxes.py:247-330 */
+    int src_flip_ylo;        /* 1 when the -y / +y boundary reflects: the reference fills the ghost cells of  */
+    int src_flip_yhi;        /*   its source arrays odd (ymom_src) / even (E_src) there (simulation.py:248-253) */
 } p2b_comp_params;
 
 /* device scratch the sweep needs, 8 x 64-bit words owned by the caller:
@@ -82,6 +87,13 @@ int p2b_fill_ghost_i64(int64_t* base, const p2b_grid* g, int nvar, const int* bc
 int p2b_fill_ghost_values_f64(double* plane, const p2b_grid* g, const int bc[4], const double* xl,
                               const double* xr, const double* yl, const double* yr, void* stream);
 
+/* ---- the compressible solver's "hse" boundary (pyro/compressible/BC.py:21-139), one variable (0 density,
+ * 1 energy, 2 x-momentum, 3 y-momentum) of a 4-plane state on side 0 = ylb / 1 = yrb: zero-gradient copy for
+ * all but the energy, which is integrated outward in hydrostatic equilibrium at the base density.  Called
+ * per variable after the standard fill, like the reference's ext_bcs hook (pyro/mesh/patch.py:582-624);
+ * bit-identical to the reference. */
+int p2b_fill_hse_f64(double* U, const p2b_grid* g, double grav, double gamma, int var, int side, void* stream);
+
 /* ---- CFL wave speeds: Simulation.method_compute_timestep (pyro/compressible/simulation.py:267-288)
  * over the FULL array including ghosts.  Accumulates (atomic max) the bit patterns of
  * max(|u|+cs), max(|v|+cs) into scratch[0], scratch[1]; the caller zeroes them first and forms
@@ -94,8 +106,8 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * riemann_hllc (riemann.py:682-860) folded into one kernel.  Uin must have its ghost cells filled;
  * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
- * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, grav = 0,
- * Cartesian geometry, HLLC. */
+ * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, Cartesian geometry,
+ * HLLC; prm->grav != 0 selects the instantiation with the gravity source terms. */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
 

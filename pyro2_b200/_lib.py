@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # P2B_SO overrides the library path (A/B timing of kernel variants during development)
 SO_PATH = os.environ.get("P2B_SO") or os.path.join(CSRC, "libpyro2b200.so")
-SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu"]
-HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "../../include/pyro2b200.h"]
+SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "../../include/pyro2b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -49,7 +49,8 @@ class Grid(C.Structure):
 class CompParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double), ("delta", C.c_double),
                 ("cvisc", C.c_double), ("limiter", C.c_int), ("use_flattening", C.c_int),
-                ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int)]
+                ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
+                ("grav", C.c_double), ("src_flip_ylo", C.c_int), ("src_flip_yhi", C.c_int)]
 
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
@@ -67,6 +68,7 @@ SIGNATURES = {
     "p2b_fill_ghost_f64": (_i, [_vp, _PG, _i, C.POINTER(_i), _vp]),
     "p2b_fill_ghost_i64": (_i, [_vp, _PG, _i, C.POINTER(_i), _vp]),
     "p2b_fill_ghost_values_f64": (_i, [_vp, _PG, C.POINTER(_i), _vp, _vp, _vp, _vp, _vp]),
+    "p2b_fill_hse_f64": (_i, [_vp, _PG, _d, _d, _i, _i, _vp]),
     "p2b_cfl_wavemax": (_i, [_vp, _PG, _d, _vp, _vp]),
     "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

@@ -10,7 +10,8 @@ What maps to what
   cons_to_prim / prim_to_cons         simulation.py:49-102   (torch, for users / tests / output)
   Variables                           simulation.py:12-46
 
-Scope: Cartesian grid, HLLC, no gravity / sponge / particles / problem sources.
+Scope: Cartesian grid, HLLC, constant gravity and the hse boundary; no sponge /
+particles / problem sources / ambient and ramp boundaries.
 Anything else raises instead of silently taking another path.
 """
 import torch
@@ -19,7 +20,7 @@ from .. import ops
 from ..mesh import boundary as bnd
 from ..simulation_null import NullSimulation, bc_setup, grid_setup
 from ..util import msg
-from . import derives, eos
+from . import BC, derives, eos
 
 
 class Variables:
@@ -84,8 +85,8 @@ class Simulation(NullSimulation):
         riemann_method = rp.get_param("compressible.riemann")
         if riemann_method != "HLLC":
             msg.fail(f"ERROR: the device sweep implements the HLLC Riemann solver only (got {riemann_method})")
-        if rp.get_param("compressible.grav") != 0.0:
-            msg.fail("ERROR: gravity source terms are not implemented in the device sweep (grav must be 0)")
+        # solver-specific boundary types (simulation.py:212-214); ambient and ramp are not built
+        bnd.define_bc("hse", BC.user, is_solid=False)
         try:
             if rp.get_param("sponge.do_sponge"):
                 msg.fail("ERROR: the sponge term is not implemented in the device sweep")
@@ -101,6 +102,12 @@ class Simulation(NullSimulation):
 
         bc, bc_xodd, bc_yodd = bc_setup(rp)
         self.solid = bnd.bc_is_solid(bc)
+        if self.decomposition is not None and any(t in bnd.ext_bcs for t in bc.names()):
+            msg.fail("ERROR: user-defined boundaries are not supported on a decomposed domain")
+        # the reference fills the ghost cells of its gravity-source arrays odd / even across a reflecting
+        # y wall (simulation.py:248-253): the sweep flips the sign of the ghost-cell sources there
+        self._src_flip = (int(bc.ylb in ("reflect", "reflect-even", "reflect-odd")),
+                          int(bc.yrb in ("reflect", "reflect-even", "reflect-odd")))
 
         # registration order fixes the variable indices: dens 0, ener 1, xmom 2, ymom 3
         # (simulation.py:223-226) -- the kernels rely on it
@@ -138,7 +145,9 @@ class Simulation(NullSimulation):
                                cvisc=rp.get_param("compressible.cvisc"),
                                limiter=rp.get_param("compressible.limiter"),
                                use_flattening=rp.get_param("compressible.use_flattening"),
-                               no_avisc_xhi=getattr(self, "_no_avisc_xhi", 1), no_avisc_yhi=1)
+                               no_avisc_xhi=getattr(self, "_no_avisc_xhi", 1), no_avisc_yhi=1,
+                               grav=rp.get_param("compressible.grav"),
+                               src_flip_ylo=self._src_flip[0], src_flip_yhi=self._src_flip[1])
 
     def _read_scratch(self):
         """one D2H copy: wave-speed maxima + status word of the last sweep"""

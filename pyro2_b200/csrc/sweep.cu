@@ -79,6 +79,7 @@ struct CudaWarp {
     }
 };
 
+template <bool GRAV>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
 {
@@ -94,7 +95,7 @@ sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
     __syncwarp();
 
     CudaWarp w;
-    SweepTask<CudaWarp> T(w, A, S, 0u);
+    SweepTask<CudaWarp, GRAV> T(w, A, S, 0u);
     for (;;) {
         int t = 0;
         if (lane == 0) t = (int)atomicAdd(task_counter, 1ull);
@@ -113,9 +114,12 @@ static int resident_warps()
     static int resident = 0;
     if (!resident) {
         int blocks = 0;
-        cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(SWEEP_WARPS * sizeof(SweepSmem)));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel, SWEEP_THREADS,
+        cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(SWEEP_WARPS * sizeof(SweepSmem)));
+        // the gravity instantiation has the same launch bounds, hence the same residency
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false>, SWEEP_THREADS,
                                                       SWEEP_WARPS * sizeof(SweepSmem));
         if (blocks < 1) blocks = 1;
         resident = blocks * SWEEP_WARPS * num_sms();
@@ -168,6 +172,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     A.z0 = prm->z0; A.z1 = prm->z1; A.delta = prm->delta; A.cvisc = prm->cvisc;
     A.limiter = prm->limiter; A.use_flattening = prm->use_flattening;
     A.no_avisc_xhi = prm->no_avisc_xhi; A.no_avisc_yhi = prm->no_avisc_yhi;
+    A.grav = prm->grav; A.src_flip_ylo = prm->src_flip_ylo; A.src_flip_yhi = prm->src_flip_yhi;
     A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
     A.seglen = choose_seglen(g->nx, A.nstrips, resident);
@@ -181,8 +186,12 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     int blocks = (ntasks + SWEEP_WARPS - 1) / SWEEP_WARPS;
     const int maxblocks = resident / SWEEP_WARPS;
     if (blocks > maxblocks) blocks = maxblocks;
-    sweep_kernel<<<blocks, SWEEP_THREADS, SWEEP_WARPS * sizeof(SweepSmem), st>>>(
-        A, (unsigned long long*)(scratch + 2), ntasks);
+    if (prm->grav != 0.0)
+        sweep_kernel<true><<<blocks, SWEEP_THREADS, SWEEP_WARPS * sizeof(SweepSmem), st>>>(
+            A, (unsigned long long*)(scratch + 2), ntasks);
+    else
+        sweep_kernel<false><<<blocks, SWEEP_THREADS, SWEEP_WARPS * sizeof(SweepSmem), st>>>(
+            A, (unsigned long long*)(scratch + 2), ntasks);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }

@@ -55,6 +55,9 @@ struct SweepArgs {
 #ifdef SWEEP_DEBUG
     double* dbg;                      // host emulator only: [k][i][j] planes of intermediates
 #endif
+    // gravity (GRAV instantiation only; kept at the end so the default kernel's parameter layout is unchanged)
+    double grav;                      // compressible.grav, acceleration along y
+    int src_flip_ylo, src_flip_yhi;   // 1: that y boundary reflects -> the ghost-cell SOURCES change sign
 };
 
 struct alignas(16) SweepSmem {
@@ -64,7 +67,13 @@ struct alignas(16) SweepSmem {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <class W>
+// GRAV = true adds the constant-gravity source terms of the reference: half a time step of
+// S = (0, rho g v... ) on the traced interface states (apply_source_terms, unsplit_fluxes.py:247-330) and the
+// predictor-corrector source update after the flux divergence (simulation.py:398-423,
+// get_external_sources :105-160).  The reference fills the ghost cells of the source ARRAYS with their own
+// BCs (ymom_src odd, E_src even across a reflecting y wall), which is the source of the ghost STATE with
+// the sign flipped there and identical to it for every other boundary type.
+template <class W, bool GRAV = false>
 struct SweepTask {
     W& w;
     const SweepArgs& A;
@@ -244,6 +253,16 @@ struct SweepTask {
                 YM = prim_to_cons(m, ginv1); YP = prim_to_cons(p, ginv1);
             }
 
+            if (GRAV) {
+                // U_xl[i+1], U_xr[i], U_yl[j+1], U_yr[j] += 0.5 dt S(i, j); S_ymom = rho g, S_ener = (rho v) g
+                const bool flip = (j < ng && A.src_flip_ylo) || (j >= jhi && A.src_flip_yhi);
+                double sy = Uc.dens * A.grav, se = Uc.ymom * A.grav;
+                if (flip) { sy = -sy; se = -se; }
+                const double hy = 0.5 * A.dt * sy, he = 0.5 * A.dt * se;
+                XM.ymom += hy; XP.ymom += hy; YM.ymom += hy; YP.ymom += hy;
+                XM.ener += he; XP.ener += he; YM.ener += he; YP.ener += he;
+            }
+
             // ---- H. vertex divergence for the artificial viscosity ---------------------------
             double divU = vertex_divU(Q(IU, i, cc), Q(IU, i, cc - 1), Q(IU, i - 1, cc), Q(IU, i - 1, cc - 1),
                                       Q(IV, i, cc), Q(IV, i, cc - 1), Q(IV, i - 1, cc), Q(IV, i - 1, cc - 1),
@@ -323,6 +342,18 @@ struct SweepTask {
                     Un.ener = U_prev.ener + dtdx * (Fx_prev.ener - Fx.ener) + dtdy * (Fy.ener - fe);
                     Un.xmom = U_prev.xmom + dtdx * (Fx_prev.xmom - Fx.xmom) + dtdy * (Fy.xmom - fx);
                     Un.ymom = U_prev.ymom + dtdx * (Fx_prev.ymom - Fx.ymom) + dtdy * (Fy.ymom - fy);
+                    if (GRAV) {
+                        // U += dt S(U_old); S_new from the new density and a time-centred y-momentum;
+                        // U += dt/2 (S_new - S_old)
+                        const double so_y = U_prev.dens * A.grav, so_e = U_prev.ymom * A.grav;
+                        Un.ymom += A.dt * so_y;
+                        Un.ener += A.dt * so_e;
+                        const double sn_y = Un.dens * A.grav;
+                        const double corr = 0.5 * A.dt * (sn_y - so_y);
+                        const double sn_e = (Un.ymom + corr) * A.grav;
+                        Un.ymom += corr;
+                        Un.ener += 0.5 * A.dt * (sn_e - so_e);
+                    }
                     if (out_lane && i > i0) {
                         double* o = Ocol + (long long)(i - 1) * A.pitch;
                         o[0] = Un.dens; o[A.plane_stride] = Un.ener;

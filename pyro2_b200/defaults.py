@@ -42,7 +42,7 @@ SOLVER = {
         "compressible.delta": (0.33, "flattening parameter"),
         "compressible.cvisc": (0.1, "artificial viscosity coefficient"),
         "compressible.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
-        "compressible.grav": (0.0, "gravity along y; the device sweep requires 0"),
+        "compressible.grav": (0.0, "constant gravitational acceleration along y"),
         "compressible.riemann": ("HLLC", "the device sweep implements HLLC"),
         "compressible.small_dens": (-1.e200, "density floor"),
         "compressible.small_eint": (-1.e200, "internal-energy floor"),

@@ -65,6 +65,14 @@ def fill_ghost_values(plane, nx, ny, ng, bc, dx, dy, xl=None, xr=None, yl=None, 
                                                     _lib.stream_ptr()))
 
 
+def fill_hse(planes, nx, ny, ng, dy, grav, gamma, var, side):
+    """the compressible "hse" boundary for plane `var` of the 4-plane state on side 0 (ylb) / 1 (yrb)"""
+    require_cuda()
+    assert planes.dim() == 3 and planes.shape[0] >= 4 and planes.dtype == torch.float64
+    g = grid_struct(planes, nx, ny, ng, 1.0, dy)
+    _lib.check(_lib.lib().p2b_fill_hse_f64(planes.data_ptr(), C.byref(g), grav, gamma, var, side, _lib.stream_ptr()))
+
+
 def new_scratch():
     require_cuda()
     return torch.zeros(8, dtype=torch.int64, device="cuda")
@@ -81,8 +89,9 @@ def cfl_wavemax(planes, nx, ny, ng, gamma, scratch):
 
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
-                no_avisc_xhi=1, no_avisc_yhi=1):
-    return _lib.CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi)
+                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_flip_ylo=0, src_flip_yhi=0):
+    return _lib.CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi,
+                           grav, src_flip_ylo, src_flip_yhi)
 
 
 def compressible_sweep(Uin, Uout, nx, ny, ng, dx, dy, dt, params, scratch):

@@ -76,14 +76,20 @@ struct LaneCtx {
     const pyro::SweepArgs* A;
     int lane;
     int ntasks;
+    bool grav;
 };
 
 void* lane_main(void* p)
 {
     LaneCtx* c = (LaneCtx*)p;
     EmuWarp w{c->ws, c->lane};
-    pyro::SweepTask<EmuWarp> T(w, *c->A, *c->smem, 0u);
-    for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+    if (c->grav) {
+        pyro::SweepTask<EmuWarp, true> T(w, *c->A, *c->smem, 0u);
+        for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+    } else {
+        pyro::SweepTask<EmuWarp> T(w, *c->A, *c->smem, 0u);
+        for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+    }
     return nullptr;
 }
 
@@ -93,7 +99,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
                                       long long plane_stride, double dx, double dy, double dt,
                                       double gamma, double z0, double z1, double delta, double cvisc,
                                       int limiter, int use_flattening, int no_avisc_xhi, int no_avisc_yhi,
-                                      int seglen, uint64_t* scratch, double* dbg)
+                                      int seglen, uint64_t* scratch, double* dbg, double grav, int src_flip_ylo,
+                                      int src_flip_yhi)
 {
     pyro::SweepArgs A;
     A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
@@ -101,6 +108,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     A.z0 = z0; A.z1 = z1; A.delta = delta; A.cvisc = cvisc;
     A.limiter = limiter; A.use_flattening = use_flattening;
     A.no_avisc_xhi = no_avisc_xhi; A.no_avisc_yhi = no_avisc_yhi;
+    A.grav = grav; A.src_flip_ylo = src_flip_ylo; A.src_flip_yhi = src_flip_yhi;
     A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
     A.seglen = seglen;
     A.nsegs = (nx + seglen - 1) / seglen;
@@ -122,7 +130,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     LaneCtx ctx[32];
     pthread_t th[32];
     for (int l = 0; l < 32; ++l) {
-        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs};
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0};
         pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
     }
     for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);

@@ -41,6 +41,11 @@ def load_mg_emu():
     return _load("mg", ["mg.cu", "mg_kernels.cuh"], "p2b_mg_", ["-DMG_COARSE_THREADS=128"])
 
 
+def load_bc_emu():
+    """pyro2_b200/csrc/bc_user.cu compiled for the host: p2b_fill_hse_f64 over numpy memory"""
+    return _load("bc", ["bc_user.cu", "bc_user_kernels.cuh"], "p2b_fill_hse")
+
+
 def load_flow_emu():
     """pyro2_b200/csrc/flow.cu compiled for the host: the p2b_flow_* ABI over numpy memory"""
     return _load("flow", ["flow.cu", "flow_kernels.cuh"], "p2b_flow_")

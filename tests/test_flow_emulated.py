@@ -103,3 +103,23 @@ def test_emulated_burgers_run_matches_reference(flow):
         f.burgers_evolve(u, v, float(dt), rp["advection.limiter"])
     assert np.array_equal(u, z["P"][0]) and np.array_equal(v, z["P"][1])
     f.close()
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 24), (40, 33)])
+def test_emulated_hse_boundary_matches_oracle(nx, ny):
+    """the compressible "hse" user boundary (compressible/BC.py): kernel vs the oracle, variable by variable"""
+    import ctypes as C
+    from emu_util import load_bc_emu
+    from pyro2_b200 import _lib
+    lib = load_bc_emu()
+    ng, gamma, grav, dy = 4, 1.4, -1.7, 0.031
+    rng = np.random.default_rng(nx)
+    P = 1.0 + rng.random((4, nx + 2 * ng, ny + 2 * ng))
+    P[1] += 3.0
+    Q = P.copy()
+    g = _lib.Grid(nx, ny, ng, ny + 2 * ng, (nx + 2 * ng) * (ny + 2 * ng), 1.0, dy)
+    for var in (0, 1, 2, 3, 1):
+        for side, name in ((0, "ylb"), (1, "yrb")):
+            assert lib.p2b_fill_hse_f64(P.ctypes.data, C.byref(g), grav, gamma, var, side, None) == 0
+            oracle.fill_hse(Q, ng, dy, grav, gamma, var, name)
+            assert np.array_equal(P, Q), (var, name)

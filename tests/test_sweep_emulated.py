@@ -27,11 +27,12 @@ def emu():
                                "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
     lib = C.CDLL(so)
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
-                                           [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2)
+                                           [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
+                                           [C.c_double, C.c_int, C.c_int])
     return lib
 
 
-def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen):
+def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0)):
     P = oracle.to_planes(U)
     _, qx, qy = P.shape
     pitch = (qy + 15) // 16 * 16
@@ -41,7 +42,8 @@ def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen):
     scratch = np.zeros(8, dtype=np.uint64)
     lib.emu_compressible_sweep(Pin.ctypes.data, Pout.ctypes.data, qx - 2 * ng, qy - 2 * ng, ng, pitch, qx * pitch,
                                dx, dy, dt, prm.gamma, prm.z0, prm.z1, prm.delta, prm.cvisc, prm.limiter,
-                               prm.use_flattening, prm.no_avisc_xhi, prm.no_avisc_yhi, seglen, scratch.ctypes.data, None)
+                               prm.use_flattening, prm.no_avisc_xhi, prm.no_avisc_yhi, seglen, scratch.ctypes.data, None,
+                               prm.grav, flips[0], flips[1])
     return oracle.from_planes(np.ascontiguousarray(Pout[:, :, :qy])), scratch
 
 
@@ -67,3 +69,43 @@ def test_emulated_sweep_matches_oracle(emu, kind, nx, ny, limiter, flat, seglen)
     assert scratch[3] == 0
     w = scratch[:2].view(np.float64)
     assert 0.8 * min(dx / w[0], dy / w[1]) == oracle.cfl_dt(np.ascontiguousarray(got[v]), 0, dx, dy, 1.4, 0.8)
+
+
+@pytest.mark.parametrize("bc,nx,ny,seglen", [
+    (("periodic", "periodic", "hse", "hse"), 24, 40, 8),
+    (("outflow", "outflow", "hse", "hse"), 33, 37, 11),
+    (("reflect", "outflow", "reflect", "reflect"), 16, 48, 16),     # ghost-cell sources change sign
+    (("periodic", "periodic", "reflect", "outflow"), 20, 36, 32)])
+def test_emulated_sweep_with_gravity_matches_oracle(emu, bc, nx, ny, seglen):
+    """the GRAV instantiation of the sweep (source terms on the interface states + predictor-corrector
+    source update) on a stratified atmosphere with a perturbation, ghost cells filled like the driver does"""
+    from golden_util import var_bcs
+    ng, gamma, grav = 4, 1.4, -1.5
+    dx, dy = 1.0 / nx, 2.0 / ny
+    rng = np.random.default_rng(nx)
+    y = (np.arange(ny + 2 * ng) + 0.5 - ng) * dy
+    dens = np.broadcast_to(2.0 * np.exp(-y / 1.3)[None, :], (nx + 2 * ng, ny + 2 * ng)).copy()
+    dens *= 1.0 + 0.05 * rng.standard_normal(dens.shape)
+    pres = 1.3 * abs(grav) * dens * (1.0 + 0.02 * rng.standard_normal(dens.shape))
+    u, v = 0.1 * rng.standard_normal(dens.shape), 0.1 * rng.standard_normal(dens.shape)
+    P = np.stack([dens, pres / (gamma - 1.0) + 0.5 * dens * (u * u + v * v), dens * u, dens * v])
+    rp = dict(zip(("mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary"), bc))
+    bcs = var_bcs(rp)
+    for k in range(4):
+        oracle.fill_ghost(P[k], ng, bcs[k])
+        for side in ("ylb", "yrb"):
+            if bcs[k][2 + (side == "yrb")] == "hse":
+                oracle.fill_hse(P, ng, dy, grav, gamma, k, side)
+    U = oracle.from_planes(P)
+    dt = 0.5 * oracle.cfl_dt(U, ng, dx, dy, gamma, 0.8)
+    prm = oracle.comp_params(grav=grav, src_bcs=bcs)
+    flips = (int(bc[2] == "reflect"), int(bc[3] == "reflect"))
+    got, scratch = _emu_step(emu, U, ng, dx, dy, dt, prm, seglen, flips)
+    ref = oracle.compressible_step(U, ng, dx, dy, dt, prm)
+    v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
+    assert not np.isnan(got[v_]).any() and scratch[3] == 0
+    for n in range(4):
+        assert rel_l2(got[v_][..., n], ref[v_][..., n]) < 1e-13
+    # and gravity really did something
+    ref0 = oracle.compressible_step(U, ng, dx, dy, dt, oracle.comp_params())
+    assert rel_l2(ref[v_][..., 3], ref0[v_][..., 3]) > 1e-4
