@@ -91,7 +91,7 @@ def test_compressible_unit_assertions():
 
 def test_unsupported_configurations_fail_loudly():
     from pyro2_b200.pyro_sim import Pyro
-    for key, val in (("compressible.riemann", "CGF"), ("compressible.grav", -1.0)):
+    for key, val in (("compressible.riemann", "CGF"), ("sponge.do_sponge", 1), ("mesh.ylboundary", "ambient")):
         p = Pyro("compressible")
         with pytest.raises(SystemExit):
             p.initialize_problem("sedov", inputs_dict={key: val})
