@@ -225,6 +225,9 @@ int p2b_flow_project(p2b_flow* f, const double* phi, double* u, double* v, doubl
                      double dt, int proj_type, void* stream);
 /* Burgers: construct_unsplit_fluxes + the conservative update (after interface_states and mac_vels) */
 int p2b_flow_burgers_update(p2b_flow* f, double* u, double* v, double dt, void* stream);
+/* linear advection, a_t + u a_x + v a_y = 0 (pyro/advection/interface.py, advective_fluxes.py:5-92,
+ * advection/simulation.py:56-92): one step for the ghost-filled scalar plane a (uses scratch planes 0..3) */
+int p2b_flow_advection_update(p2b_flow* f, double* a, double u, double v, double dt, int limiter, void* stream);
 /* bit patterns of max|u|, max|v| over the full arrays (atomic max into scratch[0..1], zeroed by the caller) */
 int p2b_flow_maxabs(p2b_flow* f, const double* u, const double* v, uint64_t* scratch, void* stream);
 

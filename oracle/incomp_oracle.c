@@ -323,4 +323,40 @@ void orc_incomp_evolve(double *S, int n, int ng, double xmin, double xmax, doubl
     free(um); free(vm); free(div); free(uxi); free(vxi); free(uyi); free(vyi); free(ax); free(ay);
 }
 
+/* linear advection: advection/interface.py:linear_interface + advective_fluxes.py:unsplit_fluxes +
+ * advection/simulation.py:evolve (:56-92); a = one ghost-filled plane, updated in its valid cells */
+void orc_advection_evolve(double *a, int nx, int ny, int ng, double dx, double dy, double dt, double u, double v,
+                          int limiter)
+{
+    const int qx = nx + 2 * ng, qy = ny + 2 * ng;
+    const size_t np = (size_t)qx * qy;
+    double *ldx = zalloc(np), *ldy = zalloc(np), *tmp = zalloc(np), *ax = zalloc(np), *ay = zalloc(np);
+    double *fxt = zalloc(np), *fyt = zalloc(np), *fx = zalloc(np), *fy = zalloc(np);
+    slopes(a, ldx, tmp, qx, qy, ng, 1, limiter);
+    slopes(a, ldy, tmp, qx, qy, ng, 2, limiter);
+    const double cx = u * dt / dx, cy = v * dt / dy;
+    for (int i = ng - 1; i <= ng + nx; i++)
+        for (int j = ng - 1; j <= ng + ny; j++) {
+            const size_t k = IDX(i, j);
+            ax[k] = (u < 0) ? a[k] - 0.5 * (1.0 + cx) * ldx[k] : a[IDX(i - 1, j)] + 0.5 * (1.0 - cx) * ldx[IDX(i - 1, j)];
+            ay[k] = (v < 0) ? a[k] - 0.5 * (1.0 + cy) * ldy[k] : a[IDX(i, j - 1)] + 0.5 * (1.0 - cy) * ldy[IDX(i, j - 1)];
+        }
+    for (size_t k = 0; k < np; k++) { fxt[k] = u * ax[k]; fyt[k] = v * ay[k]; }
+    const int mx = (u <= 0) ? 0 : -1, my = (v <= 0) ? 0 : -1;
+    const double dtdx2 = 0.5 * dt / dx, dtdy2 = 0.5 * dt / dy;
+    for (int i = ng - 1; i <= ng + nx; i++)
+        for (int j = ng - 1; j <= ng + ny; j++) {
+            const size_t k = IDX(i, j);
+            fx[k] = u * (ax[k] - dtdy2 * (fyt[IDX(i + mx, j + 1)] - fyt[IDX(i + mx, j)]));
+            fy[k] = v * (ay[k] - dtdx2 * (fxt[IDX(i + 1, j + my)] - fxt[IDX(i, j + my)]));
+        }
+    const double dtdx = dt / dx, dtdy = dt / dy;
+    for (int i = ng; i < ng + nx; i++)
+        for (int j = ng; j < ng + ny; j++) {
+            const size_t k = IDX(i, j);
+            a[k] = a[k] + dtdx * (fx[k] - fx[IDX(i + 1, j)]) + dtdy * (fy[k] - fy[IDX(i, j + 1)]);
+        }
+    free(ldx); free(ldy); free(tmp); free(ax); free(ay); free(fxt); free(fyt); free(fx); free(fy);
+}
+
 #undef FOR_BUF2

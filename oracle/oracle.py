@@ -80,6 +80,8 @@ def lib():
         L.orc_incomp_states.restype = None
         L.orc_burgers_evolve.argtypes = [dp, dp] + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int]
         L.orc_burgers_evolve.restype = None
+        L.orc_advection_evolve.argtypes = [dp] + [C.c_int] * 3 + [C.c_double] * 5 + [C.c_int]
+        L.orc_advection_evolve.restype = None
         L.orc_incomp_evolve.argtypes = [dp, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int, dp, dp, dp, dp]
         L.orc_incomp_evolve.restype = None
         L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
@@ -310,3 +312,10 @@ def incomp_evolve(planes, ng, dt, limiter=2, proj_type=2, vel_bc=(("periodic",) 
     lib().orc_incomp_evolve(_ptr(planes), n, ng, xmin, xmax, ymin, ymax, dt, limiter, proj_type, _ptr(vb), _ptr(pb),
                             _ptr(cyc), _ptr(d))
     return (int(cyc[0]), int(cyc[1]), d) if dump else (int(cyc[0]), int(cyc[1]))
+
+
+def advection_evolve(a, ng, dx, dy, dt, u, v, limiter):
+    """advection Simulation.evolve for one ghost-filled scalar plane; returns the updated plane"""
+    a = _c(a).copy()
+    lib().orc_advection_evolve(_ptr(a), a.shape[0] - 2 * ng, a.shape[1] - 2 * ng, ng, dx, dy, dt, u, v, limiter)
+    return a

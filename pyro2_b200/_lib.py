@@ -113,6 +113,7 @@ SIGNATURES = {
     "p2b_flow_cc_divergence": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
     "p2b_flow_project": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
     "p2b_flow_burgers_update": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "p2b_flow_advection_update": (_i, [_vp, _vp, _d, _d, _d, _i, _vp]),
     "p2b_flow_maxabs": (_i, [_vp, _vp, _vp, _vp, _vp]),
 }
 

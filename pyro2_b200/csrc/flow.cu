@@ -192,6 +192,25 @@ int p2b_flow_burgers_update(p2b_flow* f, double* u, double* v, double dt, void* 
     return P2B_OK;
 }
 
+// linear advection of one scalar with constant (u, v): interface states, transverse-corrected fluxes,
+// conservative update of the valid cells (uses scratch planes 0..3; a handle used for advection must not be
+// shared with the Burgers / incompressible stages, which write other index ranges of those planes)
+int p2b_flow_advection_update(p2b_flow* f, double* a, double u, double v, double dt, int limiter, void* stream)
+{
+    FLOW_CHECK(f);
+    P2B_REQUIRE(a, "null scalar");
+    P2B_REQUIRE(limiter >= 0 && limiter <= 2, "limiter must be 0, 1 or 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    const FlowGeom& g = f->g;
+    double *ax = f->S.u_xl, *ay = f->S.u_xr, *fx = f->S.u_yl, *fy = f->S.u_yr;
+    const dim3 blk = flow_block();
+    P2B_LAUNCH(flow_adv_states_kernel, flow_grid(g, 1, 1), blk, 0, st)(g, a, ax, ay, u, v, u * dt / g.dx, v * dt / g.dy, limiter);
+    P2B_LAUNCH(flow_adv_flux_kernel, flow_grid(g, 1, 1), blk, 0, st)(g, ax, ay, fx, fy, u, v, 0.5 * dt / g.dx, 0.5 * dt / g.dy);
+    P2B_LAUNCH(flow_adv_update_kernel, flow_grid(g, 0, 0), blk, 0, st)(g, a, fx, fy, dt / g.dx, dt / g.dy);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
 // bit patterns of max|u|, max|v| over the full arrays accumulated (atomic max) into scratch[0], scratch[1];
 // the caller zeroes them and forms dt = cfl * min(dx / max(umax, SMALL), dy / max(vmax, SMALL))
 int p2b_flow_maxabs(p2b_flow* f, const double* u, const double* v, uint64_t* scratch, void* stream)

@@ -312,6 +312,44 @@ __global__ void flow_burgers_update_kernel(FlowGeom g, FlowHat F, double* __rest
                      exact_mul(dtdy, exact_sub(F.vyi[k], F.vyi[ky])));
 }
 
+// ---- linear advection (pyro/advection/interface.py:linear_interface, advective_fluxes.py:unsplit_fluxes,
+// advection/simulation.py:56-92): a_t + u a_x + v a_y = 0 with constant u, v ---------------------------
+// upwinded, time-centred interface states over buf = 1 (zero elsewhere, like the reference's scratch arrays)
+__global__ void flow_adv_states_kernel(FlowGeom g, const double* __restrict__ a, double* __restrict__ ax,
+                                       double* __restrict__ ay, double u, double v, double cx, double cy, int limiter)
+{
+    int i, j;
+    if (!flow_cell(g, 1, i, j)) return;
+    const long long k = (long long)i * g.pitch + j;
+    if (u < 0) ax[k] = exact_sub(a[k], exact_mul(exact_mul(0.5, exact_add(1.0, cx)), flow_slope(a, g, i, j, 1, 0, limiter)));
+    else ax[k] = exact_add(a[k - g.pitch], exact_mul(exact_mul(0.5, exact_sub(1.0, cx)), flow_slope(a, g, i - 1, j, 1, 0, limiter)));
+    if (v < 0) ay[k] = exact_sub(a[k], exact_mul(exact_mul(0.5, exact_add(1.0, cy)), flow_slope(a, g, i, j, 0, 1, limiter)));
+    else ay[k] = exact_add(a[k - 1], exact_mul(exact_mul(0.5, exact_sub(1.0, cy)), flow_slope(a, g, i, j - 1, 0, 1, limiter)));
+}
+
+// fluxes with the transverse correction (advective_fluxes.py:74-92), buf = 1; F_xt = u a_x, F_yt = v a_y
+__global__ void flow_adv_flux_kernel(FlowGeom g, const double* __restrict__ ax, const double* __restrict__ ay,
+                                     double* __restrict__ fx, double* __restrict__ fy, double u, double v,
+                                     double dtdx2, double dtdy2)
+{
+    int i, j;
+    if (!flow_cell(g, 1, i, j)) return;
+    const long long k = (long long)i * g.pitch + j;
+    const long long mx = (u <= 0) ? 0 : -(long long)g.pitch, my = (v <= 0) ? 0 : -1;
+    fx[k] = exact_mul(u, exact_sub(ax[k], exact_mul(dtdy2, exact_sub(exact_mul(v, ay[k + mx + 1]), exact_mul(v, ay[k + mx])))));
+    fy[k] = exact_mul(v, exact_sub(ay[k], exact_mul(dtdx2, exact_sub(exact_mul(u, ax[k + g.pitch + my]), exact_mul(u, ax[k + my])))));
+}
+
+__global__ void flow_adv_update_kernel(FlowGeom g, double* __restrict__ a, const double* __restrict__ fx,
+                                       const double* __restrict__ fy, double dtdx, double dtdy)
+{
+    int i, j;
+    if (!flow_cell(g, 0, i, j)) return;
+    const long long k = (long long)i * g.pitch + j;
+    a[k] = exact_add(exact_add(a[k], exact_mul(dtdx, exact_sub(fx[k], fx[k + g.pitch]))),
+                     exact_mul(dtdy, exact_sub(fy[k], fy[k + 1])));
+}
+
 // max |u|, max |v| over the full arrays including ghost cells (burgers/simulation.py:51-58): the bit
 // patterns of the maxima are combined with atomicMax (non-negative doubles order like their bits)
 __global__ void flow_maxabs_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,

@@ -49,6 +49,14 @@ SOLVER = {
         "sponge.do_sponge": (0, "not supported"),
         "particles.do_particles": (0, ""),
     },
+    "advection": {
+        "driver.cfl": (0.8, "advective CFL number"),
+        "advection.u": (1.0, "advective velocity in x"),
+        "advection.v": (1.0, "advective velocity in y"),
+        "advection.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
+        "particles.do_particles": (0, "not supported"),
+        "particles.particle_generator": ("grid", ""),
+    },
     "burgers": {
         "driver.cfl": (0.8, "advective CFL number"),
         "advection.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),

@@ -93,6 +93,9 @@ class FlowHandle:
         p = self._check_plane
         _lib.check(_lib.lib().p2b_flow_burgers_update(self._h, p(u), p(v), dt, self._s()))
 
+    def advection_update(self, a, u, v, dt, limiter):
+        _lib.check(_lib.lib().p2b_flow_advection_update(self._h, self._check_plane(a), u, v, dt, limiter, self._s()))
+
     def maxabs(self, u, v):
         """(max|u|, max|v|) over the full arrays including ghost cells, as python floats"""
         p = self._check_plane

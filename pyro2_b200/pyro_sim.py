@@ -14,7 +14,7 @@ from .util import msg
 from .util import profile_pyro as profile
 from .util.runparams import RuntimeParameters
 
-valid_solvers = ["burgers", "compressible", "incompressible"]
+valid_solvers = ["advection", "burgers", "compressible", "incompressible"]
 
 
 class Pyro:

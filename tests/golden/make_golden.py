@@ -131,7 +131,8 @@ def flow_case(fname, solver, problem, params, nsteps, names):
     keys = ["driver.cfl", "driver.tmax", "driver.init_tstep_factor", "driver.max_dt_change", "driver.fix_dt",
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
             "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
-    keys += ["incompressible.limiter", "incompressible.proj_type"] if solver == "incompressible" else ["advection.limiter"]
+    keys += {"incompressible": ["incompressible.limiter", "incompressible.proj_type"], "burgers": ["advection.limiter"],
+             "advection": ["advection.limiter", "advection.u", "advection.v"]}[solver]
     np.savez_compressed(os.path.join(HERE, fname), problem=problem,
                         inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]), names=np.array(names),
@@ -204,5 +205,8 @@ if __name__ == "__main__":
               {"mesh.nx": 32, "mesh.ny": 32, "driver.cfl": 0.5, "driver.fix_dt": 5.e-3, "driver.init_tstep_factor": 1.0}, 10,
               INCOMP_VARS)
     flow_case("burgers_test.npz", "burgers", "test", {"mesh.nx": 64, "mesh.ny": 64}, 12, ["x-velocity", "y-velocity"])
+    # BASELINE config 1: advection smooth 64 x 64, 81 steps to t = 1 (sum(density) = 4.310466040637315e+03)
+    flow_case("advection_smooth64.npz", "advection", "smooth", {"mesh.nx": 64, "mesh.ny": 64, "particles.do_particles": 0}, 1000, ["density"])
+    flow_case("advection_tophat32.npz", "advection", "tophat", {"advection.u": -0.6, "advection.v": 1.0, "advection.limiter": 1}, 30, ["density"])
     mesh_bcs()
     ref_kats()

@@ -192,7 +192,8 @@ def test_compute_timestep_limits():
     ("compressible", "comp_rt16.npz", None), ("compressible", "comp_hse16.npz", None),
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_converge32.npz", ["x-velocity", "y-velocity"]),
-    ("burgers", "burgers_test.npz", ["x-velocity", "y-velocity"])])
+    ("burgers", "burgers_test.npz", ["x-velocity", "y-velocity"]),
+    ("advection", "advection_smooth64.npz", ["density"]), ("advection", "advection_tophat32.npz", ["density"])])
 def test_problem_initial_conditions_match_reference(solver, fname, names):
     """the host-side problem setups (numpy, like the reference's) against the fixtures' initial states;
     for the incompressible problems the fixture holds the state AFTER the initial projection, so only the
@@ -226,7 +227,8 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         from pyro2_b200.mesh import boundary as bnd
         bnd.define_bc("hse", BC.user, is_solid=False)       # what Simulation.initialize registers
     bc = bc_setup(rp)[0]
-    vars_ = ["density", "energy", "x-momentum", "y-momentum"] if solver == "compressible" else ["x-velocity", "y-velocity"]
+    vars_ = {"compressible": ["density", "energy", "x-momentum", "y-momentum"], "advection": ["density"]}.get(
+        solver, ["x-velocity", "y-velocity"])
     for n in vars_:
         d.register_var(n, bc)
     d.create()
@@ -236,7 +238,7 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         for k, n in enumerate(vars_):
             # (ghost cells included: the first hse fill reads them; rt / hse leave 0/0 there, like the reference)
             assert np.array_equal(d.get_var(n).numpy(), ref[:, :, k], equal_nan=True), n
-    elif solver == "burgers":
+    elif solver in ("burgers", "advection"):
         for k, n in enumerate(names):
             assert np.array_equal(d.get_var(n).numpy(), z["P0"][k]), n
     else:

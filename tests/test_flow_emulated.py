@@ -123,3 +123,21 @@ def test_emulated_hse_boundary_matches_oracle(nx, ny):
             assert lib.p2b_fill_hse_f64(P.ctypes.data, C.byref(g), grav, gamma, var, side, None) == 0
             oracle.fill_hse(Q, ng, dy, grav, gamma, var, name)
             assert np.array_equal(P, Q), (var, name)
+
+
+@pytest.mark.parametrize("u,v,limiter,nx,ny", [(1.0, 1.0, 2, 32, 32), (-0.7, 0.4, 1, 24, 40), (0.5, -1.2, 0, 16, 16),
+                                                (0.0, 1.0, 2, 16, 24)])
+def test_emulated_advection_matches_oracle(flow, u, v, limiter, nx, ny):
+    import ctypes as C
+    ng, dx, dy = 4, 1.0 / nx, 1.0 / ny
+    dt = 0.8 * min(dx / max(abs(u), 1e-12), dy / max(abs(v), 1e-12))
+    (a,) = _periodic_fields(nx, ny, ng, nx + limiter, 1)
+    ref = a.copy()
+    f = EmuFlow(flow, nx, ny, ng, dx, dy)
+    for _ in range(3):
+        oracle.fill_ghost(a, ng, ("periodic",) * 4)
+        oracle.fill_ghost(ref, ng, ("periodic",) * 4)
+        f.ck(flow.p2b_flow_advection_update(f.h, a.ctypes.data, u, v, dt, limiter, None))
+        ref = oracle.advection_evolve(ref, ng, dx, dy, dt, u, v, limiter)
+        assert np.array_equal(a, ref)
+    f.close()

@@ -96,6 +96,26 @@ def test_pyro_burgers_run_matches_reference():
     assert np.array_equal(state(), z["P"])
 
 
+@pytest.mark.parametrize("fname", ["advection_smooth64.npz", "advection_tophat32.npz"])
+def test_pyro_advection_run_matches_reference(fname):
+    """smooth64 = BASELINE config 1: 81 steps to t = 1, sum(density) = 4.310466040637315e+03 in the reference"""
+    p, sim, z, state = _run("advection", fname)
+    assert np.array_equal(state(), z["P0"])
+    dts = []
+    while not sim.finished() and len(dts) < len(z["dts"]):
+        p.single_step()
+        dts.append(sim.dt)
+    assert np.array_equal(np.array(dts), z["dts"])
+    g = sim.cc_data.grid
+    v = (slice(g.ilo, g.ihi + 1), slice(g.jlo, g.jhi + 1))
+    d = state()[0]
+    assert np.array_equal(d[v], z["P"][0][v])
+    if fname == "advection_smooth64.npz":
+        assert sim.n == 81 and sim.cc_data.t == 1.0
+        assert float(np.sum(d[v])) == 4.310466040637315e+03
+        assert d[v].min() == 0.9999998946441166
+
+
 def test_incompressible_projection_leaves_divergence_free_field():
     """after a step the cell-centred divergence of (u, v) is at the level the projection tolerance allows"""
     from pyro2_b200.pyro_sim import Pyro

@@ -167,3 +167,25 @@ def test_burgers_run_matches_reference():
             assert raw >= float(dt) * (1 - 1e-15)
         u, v = oracle.burgers_evolve(u, v, ng, dx, dx, float(dt), rp["advection.limiter"])
     assert np.array_equal(u, z["P"][0]) and np.array_equal(v, z["P"][1])
+
+
+@pytest.mark.parametrize("fname", ["advection_smooth64.npz", "advection_tophat32.npz"])
+def test_advection_run_matches_reference(fname):
+    """Pyro("advection") fixtures; smooth64 is BASELINE config 1 (81 steps to t = 1) with the known answers
+    SURVEY.md quotes for the reference: sum 4.310466040637315e+03, min 0.9999998946441166, max 1.960068731417340"""
+    z, rp, _ = load_flow(fname)
+    ng, n = int(z["ng"]), rp["mesh.nx"]
+    a = z["P0"][0].copy()
+    dx = (rp["mesh.xmax"] - rp["mesh.xmin"]) / n
+    dy = (rp["mesh.ymax"] - rp["mesh.ymin"]) / rp["mesh.ny"]
+    bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
+    for dt in z["dts"]:
+        oracle.fill_ghost(a, ng, bc)
+        a = oracle.advection_evolve(a, ng, dx, dy, float(dt), rp["advection.u"], rp["advection.v"], rp["advection.limiter"])
+    v = (slice(ng, -ng), slice(ng, -ng))
+    assert np.array_equal(a[v], z["P"][0][v])
+    if fname == "advection_smooth64.npz":
+        kat = np.load(__import__("os").path.join(__import__("golden_util").GOLDEN, "ref_kats.npz"))
+        assert len(z["dts"]) == 81
+        assert float(np.sum(a[v])) == float(kat["advection_smooth_sum"]) == 4.310466040637315e+03
+        assert a[v].min() == 0.9999998946441166 and abs(a[v].max() - 1.960068731417340) < 1e-15
