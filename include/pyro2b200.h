@@ -171,6 +171,14 @@ int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out_dev, void* stream)
  * old_phi is a caller-owned (n+2) x pitch buffer */
 int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out_dev, void* stream);
 
+/* ---- the diffusion solver's use of the hierarchy (pyro/diffusion/simulation.py:62-104: Crank-Nicolson,
+ * (1 - dt k/2 L) phi^{n+1} = phi^n + dt k/2 L phi^n).  p2b_mg_set_operator changes alpha / beta of an existing
+ * hierarchy (the reference constructs a new CellCenterMG2d with beta = 0.5*dt*k every step);
+ * p2b_mg_cn_rhs writes the right-hand side into the finest level's f plane from the solver's ghost-filled
+ * phi plane ((n+2) rows of phi_pitch doubles), coef = 0.5*dt*k; bit-identical to the reference's expression. */
+int p2b_mg_set_operator(p2b_mg* m, double alpha, double beta);
+int p2b_mg_cn_rhs(p2b_mg* m, const double* phi, int phi_pitch, double coef, void* stream);
+
 /* ---- variable coefficients: VarCoeffCCMG2d (pyro/multigrid/variable_coeff_MG.py:24-213) with EdgeCoeffs
  * (pyro/multigrid/edge_coeffs.py:1-54): div(eta grad phi) = f.  p2b_mg_set_coeffs does what the
  * reference's constructor does (:57-109), on the device: eta (finest level, (n+2) rows of coeffs_pitch

@@ -359,4 +359,33 @@ void orc_advection_evolve(double *a, int nx, int ny, int ng, double dx, double d
     free(ldx); free(ldy); free(tmp); free(ax); free(ay); free(fxt); free(fyt); free(fx); free(fy);
 }
 
+/* diffusion Simulation.evolve (pyro/diffusion/simulation.py:62-104): Crank-Nicolson with a multigrid solve of
+ * (1 - dt k/2 L) phi^{n+1} = phi^n + dt k/2 L phi^n.  phi = one (n+2)^2 plane (ng = 1), updated in its valid
+ * cells; returns the V-cycle count */
+int orc_diffusion_evolve(double *phi, int n, double xmin, double xmax, double ymin, double ymax, double dt, double k,
+                         const int *bc)
+{
+    const int qy = n + 2;
+    const size_t np = (size_t)qy * qy;
+    const double dx = (xmax - xmin) / n, dy = (ymax - ymin) / n;
+    orc_fill_ghost_f64(phi, n, n, 1, bc[0], bc[1], bc[2], bc[3], NULL, NULL, NULL, NULL, dx, dy);
+    orc_mg *m = orc_mg_create(n, bc, 1.0, 0.5 * dt * k, xmin, xmax, ymin, ymax, 10, 50);
+    const int L = m->nlevels - 1;
+    double *f = zalloc(np);
+    for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= n; j++) {
+            const size_t c = IDX(i, j);
+            f[c] = phi[c] + 0.5 * dt * k * ((phi[IDX(i + 1, j)] + phi[IDX(i - 1, j)] - 2.0 * phi[c]) / (dx * dx) +
+                                            (phi[IDX(i, j + 1)] + phi[IDX(i, j - 1)] - 2.0 * phi[c]) / (dy * dy));
+        }
+    const double snorm = mg_set_rhs(m, f);
+    memset(m->v[L], 0, np * sizeof(double));
+    const int cycles = orc_mg_solve(m, 1.e-10, snorm, 100, NULL, NULL);
+    for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= n; j++) phi[IDX(i, j)] = m->v[L][IDX(i, j)];
+    orc_mg_destroy(m);
+    free(f);
+    return cycles;
+}
+
 #undef FOR_BUF2

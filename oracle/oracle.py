@@ -82,6 +82,8 @@ def lib():
         L.orc_burgers_evolve.restype = None
         L.orc_advection_evolve.argtypes = [dp] + [C.c_int] * 3 + [C.c_double] * 5 + [C.c_int]
         L.orc_advection_evolve.restype = None
+        L.orc_diffusion_evolve.argtypes = [dp, C.c_int] + [C.c_double] * 6 + [dp]
+        L.orc_diffusion_evolve.restype = C.c_int
         L.orc_incomp_evolve.argtypes = [dp, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int, dp, dp, dp, dp]
         L.orc_incomp_evolve.restype = None
         L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
@@ -319,3 +321,10 @@ def advection_evolve(a, ng, dx, dy, dt, u, v, limiter):
     a = _c(a).copy()
     lib().orc_advection_evolve(_ptr(a), a.shape[0] - 2 * ng, a.shape[1] - 2 * ng, ng, dx, dy, dt, u, v, limiter)
     return a
+
+
+def diffusion_evolve(phi, dt, k, bc, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0):
+    """diffusion Simulation.evolve on an (n+2, n+2) plane (ng = 1), in place; returns the V-cycle count"""
+    assert phi.flags.c_contiguous and phi.dtype == np.float64 and phi.shape[0] == phi.shape[1]
+    codes = np.array(_bc4(bc), dtype=np.int32)
+    return lib().orc_diffusion_evolve(_ptr(phi), phi.shape[0] - 2, xmin, xmax, ymin, ymax, dt, k, _ptr(codes))

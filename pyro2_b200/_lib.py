@@ -96,6 +96,8 @@ SIGNATURES = {
     "p2b_mg_tb_iters": (_i, []),
     "p2b_mg_norm2": (_i, [_vp, _i, _i, _vp, _vp]),
     "p2b_mg_cycle_diagnostics": (_i, [_vp, _vp, _vp, _vp]),
+    "p2b_mg_set_operator": (_i, [_vp, _d, _d]),
+    "p2b_mg_cn_rhs": (_i, [_vp, _vp, _i, _d, _vp]),
     "p2b_mg_coeff_workspace_bytes": (_ll, [_vp]),
     "p2b_mg_set_coeffs": (_i, [_vp, _vp, _ll, _vp, _i, C.POINTER(_i), _vp]),
     "p2b_mg_coeff_ptr": (_vp, [_vp, _i, _i]),

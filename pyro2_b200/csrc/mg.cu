@@ -626,4 +626,30 @@ void* p2b_mg_coeff_ptr(p2b_mg* m, int level, int which)
     return which == 0 ? m->cc[level] : which == 1 ? m->ex[level] : m->ey[level];
 }
 
+// change alpha / beta of (alpha - beta L) phi = f on an existing hierarchy (the diffusion solver's beta is
+// 0.5*dt*k: the reference builds a new CellCenterMG2d every step, diffusion/simulation.py:76-85)
+int p2b_mg_set_operator(p2b_mg* m, double alpha, double beta)
+{
+    P2B_REQUIRE(m, "null handle");
+    P2B_REQUIRE(!m->varcoef, "variable-coefficient hierarchy");
+    m->alpha = alpha; m->beta = beta;
+    return P2B_OK;
+}
+
+// finest-level f <- phi + coef * (5-point Laplacian of phi), phi = a ghost-filled (n+2) x phi_pitch plane:
+// the Crank-Nicolson right-hand side of diffusion/simulation.py:87-91 (coef = 0.5*dt*k)
+int p2b_mg_cn_rhs(p2b_mg* m, const double* phi, int phi_pitch, double coef, void* stream)
+{
+    P2B_REQUIRE(m && m->base && phi, "null pointer");
+    P2B_REQUIRE(m->size == 1, "single-GPU hierarchies only");
+    const MgLevel& L = m->lev[m->nlevels - 1];
+    P2B_REQUIRE(phi_pitch >= L.n + 2, "phi_pitch too small");
+    dim3 blk(64, 4);
+    dim3 grd((L.n + blk.x - 1) / blk.x, (L.ni + blk.y - 1) / blk.y);
+    P2B_LAUNCH(mg_cn_rhs_kernel, grd, blk, 0, (cudaStream_t)stream)(L, phi, phi_pitch, coef, make_div_const(L.dx * L.dx),
+                                                                    make_div_const(L.dy * L.dy));
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
 }  // extern "C"

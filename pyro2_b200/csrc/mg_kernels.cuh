@@ -950,4 +950,20 @@ mg_vc_diag_partial_kernel(MgLevel L, VcEdges E, double* __restrict__ old_phi, do
     if (threadIdx.x == 0) { part[blockIdx.x] = s_rel; part[MG_NPART + blockIdx.x] = s_res; }
 }
 
+// Crank-Nicolson right-hand side of the diffusion solver (pyro/diffusion/simulation.py:87-91):
+//   f = phi + coef * ((phi[i+1] + phi[i-1] - 2 phi)/dx**2 + (phi[j+1] + phi[j-1] - 2 phi)/dy**2),  coef = 0.5*dt*k
+// phi is the solver's own ghost-filled (n+2)^2 plane (ng = 1); f is the level's right-hand-side plane
+__global__ void mg_cn_rhs_kernel(MgLevel L, const double* __restrict__ phi, int ppitch, double coef, DivConst dx2,
+                                 DivConst dy2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > L.ni || j > L.n) return;
+    const long long k = (long long)i * ppitch + j;
+    const double c2 = exact_mul(2.0, phi[k]);
+    const double lx = div_const(exact_sub(exact_add(phi[k + ppitch], phi[k - ppitch]), c2), dx2);
+    const double ly = div_const(exact_sub(exact_add(phi[k + 1], phi[k - 1]), c2), dy2);
+    L.f[(long long)i * L.pitch + j] = exact_add(phi[k], exact_mul(coef, exact_add(lx, ly)));
+}
+
 }  // namespace pyro

@@ -57,6 +57,10 @@ SOLVER = {
         "particles.do_particles": (0, "not supported"),
         "particles.particle_generator": ("grid", ""),
     },
+    "diffusion": {
+        "driver.cfl": (0.8, "diffusion CFL number (may exceed 1: the update is implicit)"),
+        "diffusion.k": (1.0, "conductivity"),
+    },
     "burgers": {
         "driver.cfl": (0.8, "advective CFL number"),
         "advection.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),

@@ -123,6 +123,14 @@ class MGHandle:
         off = (ptr - self.coeff_workspace.data_ptr()) // 8
         return self.coeff_workspace.as_strided((g["n"] + 2, g["n"] + 2), (g["pitch"], 1), off)
 
+    def set_operator(self, alpha, beta):
+        _lib.check(_lib.lib().p2b_mg_set_operator(self._h, alpha, beta))
+
+    def cn_rhs(self, phi, coef):
+        """finest-level f <- phi + coef * lap(phi) for a ghost-filled (n+2, n+2) CUDA plane phi"""
+        assert phi.is_cuda and phi.dtype == torch.float64 and phi.stride(1) == 1
+        _lib.check(_lib.lib().p2b_mg_cn_rhs(self._h, phi.data_ptr(), phi.stride(0), coef, self._s()))
+
     def set_blocking(self, enable):
         _lib.check(_lib.lib().p2b_mg_set_blocking(self._h, int(bool(enable))))
 

@@ -195,6 +195,22 @@ class CellCenterMG2d:
             print("Source norm = ", self.source_norm)
         self.initialized_rhs = 1
 
+    def set_operator(self, alpha, beta):
+        """(extension) change alpha / beta of this hierarchy in place -- what constructing a new solver with
+        other coefficients amounts to (the diffusion solver's beta follows dt).  A captured V-cycle graph holds
+        the old coefficients as kernel arguments, so it is dropped."""
+        if alpha != self.alpha or beta != self.beta:
+            self.alpha, self.beta = alpha, beta
+            self._h.set_operator(alpha, beta)
+            self._graph = None
+
+    def init_RHS_crank_nicolson(self, phi, coef):
+        """(extension) init_RHS(phi + coef * lap(phi)) evaluated on the device from the ghost-filled plane phi
+        (diffusion/simulation.py:87-93)"""
+        self._h.cn_rhs(phi, coef)
+        self.source_norm = self._norm(self.nlevels - 1, "f")
+        self.initialized_rhs = 1
+
     def _norm(self, level, which):
         g = self.grids[level].grid
         return math.sqrt(g.dx * g.dy * self._h.sumsq(level, which))

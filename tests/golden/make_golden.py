@@ -132,7 +132,7 @@ def flow_case(fname, solver, problem, params, nsteps, names):
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
             "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
     keys += {"incompressible": ["incompressible.limiter", "incompressible.proj_type"], "burgers": ["advection.limiter"],
-             "advection": ["advection.limiter", "advection.u", "advection.v"]}[solver]
+             "advection": ["advection.limiter", "advection.u", "advection.v"], "diffusion": ["diffusion.k"]}[solver]
     np.savez_compressed(os.path.join(HERE, fname), problem=problem,
                         inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]), names=np.array(names),
@@ -208,5 +208,9 @@ if __name__ == "__main__":
     # BASELINE config 1: advection smooth 64 x 64, 81 steps to t = 1 (sum(density) = 4.310466040637315e+03)
     flow_case("advection_smooth64.npz", "advection", "smooth", {"mesh.nx": 64, "mesh.ny": 64, "particles.do_particles": 0}, 1000, ["density"])
     flow_case("advection_tophat32.npz", "advection", "tophat", {"advection.u": -0.6, "advection.v": 1.0, "advection.limiter": 1}, 30, ["density"])
+    flow_case("diffusion_gaussian64.npz", "diffusion", "gaussian", {"mesh.nx": 64, "mesh.ny": 64}, 12, ["phi"])
+    flow_case("diffusion_gaussian32_mixed.npz", "diffusion", "gaussian",
+              {"mesh.nx": 32, "mesh.ny": 32, "mesh.xlboundary": "periodic", "mesh.xrboundary": "periodic",
+               "mesh.ylboundary": "dirichlet", "mesh.yrboundary": "neumann", "driver.cfl": 0.7, "driver.tmax": 1.0}, 10, ["phi"])
     mesh_bcs()
     ref_kats()

@@ -193,7 +193,8 @@ def test_compute_timestep_limits():
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_converge32.npz", ["x-velocity", "y-velocity"]),
     ("burgers", "burgers_test.npz", ["x-velocity", "y-velocity"]),
-    ("advection", "advection_smooth64.npz", ["density"]), ("advection", "advection_tophat32.npz", ["density"])])
+    ("advection", "advection_smooth64.npz", ["density"]), ("advection", "advection_tophat32.npz", ["density"]),
+    ("diffusion", "diffusion_gaussian64.npz", ["phi"])])
 def test_problem_initial_conditions_match_reference(solver, fname, names):
     """the host-side problem setups (numpy, like the reference's) against the fixtures' initial states;
     for the incompressible problems the fixture holds the state AFTER the initial projection, so only the
@@ -220,6 +221,9 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
     # explicit host device: data containers work there (the kernels do not); the product default is CUDA
     g = patch.Cartesian2d(rp.get_param("mesh.nx"), rp.get_param("mesh.ny"), ng=4, xmin=rp.get_param("mesh.xmin"),
                           xmax=rp.get_param("mesh.xmax"), ymin=rp.get_param("mesh.ymin"), ymax=rp.get_param("mesh.ymax"),
+                          device="cpu") if solver != "diffusion" else \
+        patch.Cartesian2d(rp.get_param("mesh.nx"), rp.get_param("mesh.ny"), ng=1, xmin=rp.get_param("mesh.xmin"),
+                          xmax=rp.get_param("mesh.xmax"), ymin=rp.get_param("mesh.ymin"), ymax=rp.get_param("mesh.ymax"),
                           device="cpu")
     d = patch.CellCenterData2d(g)
     if solver == "compressible":
@@ -227,7 +231,7 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         from pyro2_b200.mesh import boundary as bnd
         bnd.define_bc("hse", BC.user, is_solid=False)       # what Simulation.initialize registers
     bc = bc_setup(rp)[0]
-    vars_ = {"compressible": ["density", "energy", "x-momentum", "y-momentum"], "advection": ["density"]}.get(
+    vars_ = {"compressible": ["density", "energy", "x-momentum", "y-momentum"], "advection": ["density"], "diffusion": ["phi"]}.get(
         solver, ["x-velocity", "y-velocity"])
     for n in vars_:
         d.register_var(n, bc)
@@ -238,7 +242,7 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         for k, n in enumerate(vars_):
             # (ghost cells included: the first hse fill reads them; rt / hse leave 0/0 there, like the reference)
             assert np.array_equal(d.get_var(n).numpy(), ref[:, :, k], equal_nan=True), n
-    elif solver in ("burgers", "advection"):
+    elif solver in ("burgers", "advection", "diffusion"):
         for k, n in enumerate(names):
             assert np.array_equal(d.get_var(n).numpy(), z["P0"][k]), n
     else:

@@ -116,6 +116,34 @@ def test_pyro_advection_run_matches_reference(fname):
         assert d[v].min() == 0.9999998946441166
 
 
+@pytest.mark.parametrize("fname", ["diffusion_gaussian64.npz", "diffusion_gaussian32_mixed.npz"])
+def test_pyro_diffusion_run_matches_reference(fname):
+    """one Crank-Nicolson multigrid solve per step; the hierarchy is reused with beta following dt"""
+    p, sim, z, state = _run("diffusion", fname)
+    assert np.array_equal(state(), z["P0"])
+    dts = []
+    for _ in range(len(z["dts"])):
+        p.single_step()
+        dts.append(sim.dt)
+    assert np.array_equal(np.array(dts), z["dts"])
+    assert np.array_equal(state()[0][1:-1, 1:-1], z["P"][0][1:-1, 1:-1])
+
+
+def test_diffusion_gaussian_follows_analytic_solution():
+    from pyro2_b200.diffusion.problems.gaussian import phi_analytic
+    from pyro2_b200.pyro_sim import Pyro
+    p = Pyro("diffusion")
+    p.initialize_problem("gaussian", inputs_dict={"mesh.nx": 128, "mesh.ny": 128, "driver.tmax": 0.002})
+    p.run_sim()
+    sim = p.sim
+    g = sim.cc_data.grid
+    x, y = np.meshgrid(g.x, g.y, indexing="ij")
+    exact = phi_analytic(np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2), sim.cc_data.t, 1.e-4, 1.0, 1.0, 2.0)
+    phi = sim.cc_data.get_var("phi").numpy()
+    v = (slice(1, -1), slice(1, -1))
+    assert np.abs(phi[v] - exact[v]).max() < 5e-3 * (exact[v].max() - 1.0) + 2e-4
+
+
 def test_incompressible_projection_leaves_divergence_free_field():
     """after a step the cell-centred divergence of (u, v) is at the level the projection tolerance allows"""
     from pyro2_b200.pyro_sim import Pyro

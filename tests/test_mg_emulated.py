@@ -109,3 +109,26 @@ def test_emulated_variable_coefficient_blocked_smoother(emu, n, bc, cbc):
         m.ck(emu.p2b_mg_smooth(m.h, fine, 7, None))
         assert np.array_equal(m.plane(fine, "v"), o.plane(fine, "v")), blocking
         m.close()
+
+
+@pytest.mark.parametrize("n,bc", [(32, ("neumann",) * 4), (64, ("periodic", "periodic", "dirichlet", "neumann"))])
+def test_emulated_diffusion_step_matches_oracle(emu, n, bc):
+    """the diffusion solver's step (diffusion/simulation.py:62-104): Crank-Nicolson right-hand side kernel,
+    a hierarchy whose beta follows dt (p2b_mg_set_operator), solve to 1e-10"""
+    rng = np.random.default_rng(n)
+    phi = 1.0 + rng.random((n + 2, n + 2))
+    ref = phi.copy()
+    m = EmuMG(emu, n, bc, 1.0, 0.123)
+    fine = m.nlevels - 1
+    for dt in (0.4 / n ** 2, 1.7 / n ** 2):
+        k = 1.3
+        oracle.fill_ghost(phi, 1, bc)
+        m.ck(emu.p2b_mg_set_operator(m.h, 1.0, 0.5 * dt * k))
+        m.ck(emu.p2b_mg_cn_rhs(m.h, phi.ctypes.data, n + 2, 0.5 * dt * k, None))
+        f = m.plane(fine, "f").copy()
+        sol = m.solve(f, rtol=1e-10)
+        phi[1:-1, 1:-1] = sol[1:-1, 1:-1]
+        cyc = oracle.diffusion_evolve(ref, dt, k, bc)
+        assert cyc == m.num_cycles
+        assert np.array_equal(phi[1:-1, 1:-1], ref[1:-1, 1:-1])
+    m.close()

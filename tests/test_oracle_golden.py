@@ -189,3 +189,15 @@ def test_advection_run_matches_reference(fname):
         assert len(z["dts"]) == 81
         assert float(np.sum(a[v])) == float(kat["advection_smooth_sum"]) == 4.310466040637315e+03
         assert a[v].min() == 0.9999998946441166 and abs(a[v].max() - 1.960068731417340) < 1e-15
+
+
+@pytest.mark.parametrize("fname", ["diffusion_gaussian64.npz", "diffusion_gaussian32_mixed.npz"])
+def test_diffusion_run_matches_reference(fname):
+    """Pyro("diffusion") fixtures: one Crank-Nicolson multigrid solve per step"""
+    z, rp, _ = load_flow(fname)
+    phi = np.ascontiguousarray(z["P0"][0])
+    bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
+    for dt in z["dts"]:
+        oracle.diffusion_evolve(phi, float(dt), rp["diffusion.k"], bc, rp["mesh.xmin"], rp["mesh.xmax"],
+                                rp["mesh.ymin"], rp["mesh.ymax"])
+    assert np.array_equal(phi[1:-1, 1:-1], z["P"][0][1:-1, 1:-1])
