@@ -33,6 +33,13 @@ class CompParams(C.Structure):
                 ("grav", C.c_double), ("src_bc", C.c_int * 16)]
 
 
+class LmParams(C.Structure):
+    _fields_ = [("n", C.c_int), ("ng", C.c_int), ("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double),
+                ("ymax", C.c_double), ("grav", C.c_double), ("gamma", C.c_double), ("limiter", C.c_int),
+                ("proj_type", C.c_int), ("bc_dens", C.c_int * 4), ("bc_xvel", C.c_int * 4), ("bc_yvel", C.c_int * 4),
+                ("bc_phi", C.c_int * 4)]
+
+
 _STAGE_NAMES = ["q", "xi", "ldx", "ldy", "Uxl_hat", "Uxr_hat", "Uyl_hat", "Uyr_hat", "Fx_t", "Fy_t",
                 "Uxl", "Uxr", "Uyl", "Uyr", "Fx", "Fy"]
 
@@ -84,6 +91,12 @@ def lib():
         L.orc_advection_evolve.restype = None
         L.orc_diffusion_evolve.argtypes = [dp, C.c_int] + [C.c_double] * 6 + [dp]
         L.orc_diffusion_evolve.restype = C.c_int
+        L.orc_lm_evolve.argtypes = [dp, dp, C.POINTER(LmParams), C.c_double, dp]
+        L.orc_lm_evolve.restype = None
+        L.orc_lm_initial_projection.argtypes = [dp, dp, C.POINTER(LmParams)]
+        L.orc_lm_initial_projection.restype = C.c_int
+        L.orc_lm_timestep.argtypes = [dp, dp, C.POINTER(LmParams), C.c_double]
+        L.orc_lm_timestep.restype = C.c_double
         L.orc_incomp_evolve.argtypes = [dp, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int, dp, dp, dp, dp]
         L.orc_incomp_evolve.restype = None
         L.orc_norm.argtypes = [dp, C.c_int, C.c_double, C.c_double]
@@ -328,3 +341,35 @@ def diffusion_evolve(phi, dt, k, bc, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0):
     assert phi.flags.c_contiguous and phi.dtype == np.float64 and phi.shape[0] == phi.shape[1]
     codes = np.array(_bc4(bc), dtype=np.int32)
     return lib().orc_diffusion_evolve(_ptr(phi), phi.shape[0] - 2, xmin, xmax, ymin, ymax, dt, k, _ptr(codes))
+
+
+# ---- low Mach number atmosphere (oracle/lm_oracle.c) ----------------------------------------------------
+LM_VARS = ["density", "x-velocity", "y-velocity", "eint", "phi-MAC", "phi", "gradp_x", "gradp_y"]
+
+
+def lm_params(n, ng=4, grav=-2.0, gamma=1.4, limiter=2, proj_type=2, bc_dens=("periodic", "periodic", "reflect-even", "outflow"),
+              bc_xvel=None, bc_yvel=None, bc_phi=("periodic", "periodic", "neumann", "dirichlet"),
+              xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0):
+    """BC names per variable class as CellCenterData2d resolves them (reflect -> reflect-even / reflect-odd)"""
+    bc_xvel = bc_xvel or bc_dens
+    bc_yvel = bc_yvel or tuple("reflect-odd" if b == "reflect-even" and k >= 2 else b for k, b in enumerate(bc_dens))
+    mk = lambda bc: (C.c_int * 4)(*_bc4(bc))
+    return LmParams(n, ng, xmin, xmax, ymin, ymax, grav, gamma, limiter, proj_type, mk(bc_dens), mk(bc_xvel), mk(bc_yvel),
+                    mk(bc_phi))
+
+
+def lm_evolve(S, base, prm, dt):
+    """lm_atm Simulation.evolve on the 8 SoA state planes S[n, i, j] (ghost cells filled) and the base-state
+    arrays base[4, qy] = rho0, p0, beta0, beta0-edges; in place; returns the two V-cycle counts"""
+    assert S.flags.c_contiguous and S.shape[0] == 8 and base.flags.c_contiguous and base.shape[0] == 4
+    cyc = np.zeros(2, dtype=np.int32)
+    lib().orc_lm_evolve(_ptr(S), _ptr(base), C.byref(prm), dt, _ptr(cyc))
+    return int(cyc[0]), int(cyc[1])
+
+
+def lm_initial_projection(S, base, prm):
+    return lib().orc_lm_initial_projection(_ptr(S), _ptr(base), C.byref(prm))
+
+
+def lm_timestep(S, base, prm, cfl):
+    return lib().orc_lm_timestep(_ptr(S), _ptr(base), C.byref(prm), cfl)

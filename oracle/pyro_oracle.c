@@ -1009,3 +1009,4 @@ int orc_mg_solve(orc_mg *m, double rtol, double source_norm, int max_cycles, dou
  * Burgers / incompressible explicit part + the incompressible evolve() (uses the helpers above)
  * ---------------------------------------------------------------------------------------- */
 #include "incomp_oracle.c"
+#include "lm_oracle.c"

@@ -132,12 +132,16 @@ def flow_case(fname, solver, problem, params, nsteps, names):
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
             "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax"]
     keys += {"incompressible": ["incompressible.limiter", "incompressible.proj_type"], "burgers": ["advection.limiter"],
-             "advection": ["advection.limiter", "advection.u", "advection.v"], "diffusion": ["diffusion.k"]}[solver]
+             "advection": ["advection.limiter", "advection.u", "advection.v"], "diffusion": ["diffusion.k"],
+             "lm_atm": ["lm-atmosphere.limiter", "lm-atmosphere.proj_type", "lm-atmosphere.grav", "eos.gamma"]}[solver]
+    extra = {}
+    if solver == "lm_atm":      # the 1-d base state the problem setup builds (rho0, p0) and the derived beta0 arrays
+        extra["base"] = np.stack([sim.base[k].d for k in ("rho0", "p0", "beta0", "beta0-edges")])
     np.savez_compressed(os.path.join(HERE, fname), problem=problem,
                         inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]), names=np.array(names),
                         ng=g.ng, P0=P0, P=np.stack([np.asarray(sim.cc_data.get_var(n)) for n in names]),
-                        dts=np.array(dts), t=sim.cc_data.t, n=sim.n)
+                        dts=np.array(dts), t=sim.cc_data.t, n=sim.n, **extra)
     print(fname, "steps", sim.n, "t", sim.cc_data.t)
 
 
@@ -212,5 +216,9 @@ if __name__ == "__main__":
     flow_case("diffusion_gaussian32_mixed.npz", "diffusion", "gaussian",
               {"mesh.nx": 32, "mesh.ny": 32, "mesh.xlboundary": "periodic", "mesh.xrboundary": "periodic",
                "mesh.ylboundary": "dirichlet", "mesh.yrboundary": "neumann", "driver.cfl": 0.7, "driver.tmax": 1.0}, 10, ["phi"])
+    LM_VARS = ["density", "x-velocity", "y-velocity", "eint", "phi-MAC", "phi", "gradp_x", "gradp_y"]
+    flow_case("lm_bubble32.npz", "lm_atm", "bubble", {"mesh.nx": 32, "mesh.ny": 32}, 10, LM_VARS)
+    flow_case("lm_bubble64_lim1.npz", "lm_atm", "bubble",
+              {"mesh.nx": 64, "mesh.ny": 64, "lm-atmosphere.limiter": 1, "lm-atmosphere.proj_type": 1}, 6, LM_VARS)
     mesh_bcs()
     ref_kats()

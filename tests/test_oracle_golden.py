@@ -201,3 +201,35 @@ def test_diffusion_run_matches_reference(fname):
         oracle.diffusion_evolve(phi, float(dt), rp["diffusion.k"], bc, rp["mesh.xmin"], rp["mesh.xmax"],
                                 rp["mesh.ymin"], rp["mesh.ymax"])
     assert np.array_equal(phi[1:-1, 1:-1], z["P"][0][1:-1, 1:-1])
+
+
+def _lm_setup(z, rp):
+    names = [str(n) for n in z["names"]]
+    bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
+    assert bc == ("periodic", "periodic", "reflect", "outflow")      # the setup the fixtures were generated with
+    even = ("periodic", "periodic", "reflect-even", "outflow")
+    odd_y = ("periodic", "periodic", "reflect-odd", "outflow")
+    phi_bc = ("periodic", "periodic", "neumann", "dirichlet")
+    fills = dict(zip(names, (even, even, odd_y, even, phi_bc, phi_bc, even, even)))
+    prm = oracle.lm_params(rp["mesh.nx"], grav=rp["lm-atmosphere.grav"], gamma=rp["eos.gamma"],
+                           limiter=rp["lm-atmosphere.limiter"], proj_type=rp["lm-atmosphere.proj_type"],
+                           xmin=rp["mesh.xmin"], xmax=rp["mesh.xmax"], ymin=rp["mesh.ymin"], ymax=rp["mesh.ymax"])
+    return names, fills, prm
+
+
+@pytest.mark.parametrize("fname", ["lm_bubble32.npz", "lm_bubble64_lim1.npz"])
+def test_lm_atm_run_matches_reference(fname):
+    """Pyro("lm_atm") fixtures (bubble): the oracle's evolve -- numba interface routines restated, two
+    variable-coefficient multigrid projections -- reproduces all eight state planes bit for bit"""
+    z, rp, _ = load_flow(fname)
+    ng = int(z["ng"])
+    names, fills, prm = _lm_setup(z, rp)
+    S = np.ascontiguousarray(z["P0"])
+    base = np.ascontiguousarray(z["base"])
+    for n, dt in enumerate(z["dts"]):
+        for k, name in enumerate(names):
+            oracle.fill_ghost(S[k], ng, fills[name])
+        raw = oracle.lm_timestep(S, base, prm, rp["driver.cfl"])
+        assert raw >= float(dt) * (1 - 1e-15)          # the driver only ever shrinks the method's dt
+        oracle.lm_evolve(S, base, prm, float(dt))
+    assert np.array_equal(S, z["P"])

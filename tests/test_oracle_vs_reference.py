@@ -103,3 +103,44 @@ def test_incompressible_stages_bit_identical():
         sim.evolve()
         for k, n in enumerate(names):
             assert np.array_equal(P[k], np.asarray(sim.cc_data.get_var(n))), n
+
+
+def test_lm_atm_bit_identical():
+    """lm_atm: timestep, preevolve (initial projection + throw-away step) and steps against the live reference"""
+    ref_shim.load()
+    import pyro.lm_atm.simulation as lms
+    captured = {}
+    orig_pre = lms.Simulation.preevolve
+
+    def pre(self):
+        captured["S"] = np.ascontiguousarray(np.stack([np.asarray(self.cc_data.get_var(n)) for n in oracle.LM_VARS]))
+        orig_pre(self)
+    lms.Simulation.preevolve = pre
+    try:
+        p = ref_shim.make_sim("lm_atm", "bubble", {"mesh.nx": 32, "mesh.ny": 32, "driver.max_steps": 100})
+    finally:
+        lms.Simulation.preevolve = orig_pre
+    sim = p.sim
+    g = sim.cc_data.grid
+    base = np.ascontiguousarray(np.stack([sim.base[k].d for k in ("rho0", "p0", "beta0", "beta0-edges")]))
+    prm = oracle.lm_params(g.nx)
+    S = captured["S"].copy()
+    oracle.lm_initial_projection(S, base, prm)
+    saved = S.copy()
+    oracle.lm_evolve(S, base, prm, oracle.lm_timestep(S, base, prm, 0.8))
+    saved[6:8] = S[6:8]
+    S = saved
+    state = lambda: np.stack([np.asarray(sim.cc_data.get_var(n)) for n in oracle.LM_VARS])
+    assert np.array_equal(S, state())
+    bcn = {n: (sim.cc_data.BCs[n].xlb, sim.cc_data.BCs[n].xrb, sim.cc_data.BCs[n].ylb, sim.cc_data.BCs[n].yrb)
+           for n in oracle.LM_VARS}
+    for _ in range(2):
+        sim.cc_data.fill_BC_all()
+        for k, n in enumerate(oracle.LM_VARS):
+            oracle.fill_ghost(S[k], g.ng, bcn[n])
+        sim.method_compute_timestep()
+        assert sim.dt == oracle.lm_timestep(S, base, prm, 0.8)
+        sim.compute_timestep()
+        oracle.lm_evolve(S, base, prm, sim.dt)
+        sim.evolve()
+        assert np.array_equal(S, state())
