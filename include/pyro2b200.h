@@ -239,6 +239,54 @@ int p2b_flow_advection_update(p2b_flow* f, double* a, double u, double v, double
 /* bit patterns of max|u|, max|v| over the full arrays (atomic max into scratch[0..1], zeroed by the caller) */
 int p2b_flow_maxabs(p2b_flow* f, const double* u, const double* v, uint64_t* scratch, void* stream);
 
+/* ---- low Mach number atmosphere (lm_atm) explicit stages: the third caller of the multigrid path, through
+ * the variable-coefficient solver.  pyro/lm_atm/LM_atm_interface.py:181-703 (the numba routines mac_vels, states,
+ * rho_states, get_interface_states, upwind, riemann) and the array expressions of
+ * pyro/lm_atm/simulation.py:138-618.  A p2b_lm handle describes the solver grid (ng >= 4), points at the device
+ * copy of the 1-d base state (rho0, p0, beta0, beta0-edges: 4 x (ny + 2 ng) doubles, simulation.py:102-133) and owns
+ * 25 ZERO-INITIALISED scratch planes.  Planes 16 ("coeff") and 17 ("source_y") are the reference's aux_data: the
+ * caller ghost-fills them (p2b_fill_ghost_f64 with the density / y-velocity boundary types) between the calls that
+ * write and read them, exactly where the reference calls aux_data.fill_BC.  Every array is bit-identical to the
+ * reference's.  One step (simulation.py:286-618):
+ *   coeff(rho; beta0) + fill, source(rho) + fill -> interface_states -> mac_vels -> coeff(rho; beta0^2, buf 1) ->
+ *   mac_divergence -> [VarCoeff multigrid solve] -> coeff(rho; beta0) + fill -> mac_project -> density_update ->
+ *   [fill density] -> coeff(rho + rho_old, 2; beta0) + fill -> interface_states -> upwind_states -> advect_update ->
+ *   source(rho, rho_old) + fill -> add_source -> [fill u, v] -> coeff(rho; beta0^2) -> cc_divergence ->
+ *   [VarCoeff multigrid solve] -> project -> [fill u, v, gradp]                                                  */
+typedef struct p2b_lm p2b_lm;
+
+p2b_lm* p2b_lm_create(const p2b_grid* g, const double* basestate);
+int p2b_lm_destroy(p2b_lm* h);
+long long p2b_lm_workspace_bytes(p2b_lm* h);
+int p2b_lm_bind(p2b_lm* h, void* device_mem, long long bytes);
+/* scratch plane n: 0..7 u/v interface states, 8..9 transverse Riemann velocities, 10..13 u_xint v_xint u_yint v_yint,
+ * 14..15 u_MAC v_MAC, 16 coeff, 17 source_y, 18..21 density interface states, 22..23 rho_xint rho_yint, 24 rho_old */
+void* p2b_lm_plane(p2b_lm* h, int n);
+/* coeff <- numer / (d1 [+ d2]) * beta0 (squared: * beta0**2) over the buf-extended valid region */
+int p2b_lm_coeff(p2b_lm* h, const double* d1, const double* d2, double numer, int squared, int buf, void* stream);
+/* source_y <- rho' g / rho: valid cells from rho, or (rho_old given) the whole array from 0.5 (rho + rho_old) */
+int p2b_lm_source(p2b_lm* h, const double* rho, const double* rho_old, double grav, void* stream);
+int p2b_lm_interface_states(p2b_lm* h, const double* u, const double* v, const double* gradp_x, const double* gradp_y,
+                            double dt, int limiter, void* stream);
+int p2b_lm_mac_vels(p2b_lm* h, void* stream);
+int p2b_lm_mac_divergence(p2b_lm* h, double* div, int div_pitch, void* stream);      /* D(beta0 U_MAC) */
+int p2b_lm_mac_project(p2b_lm* h, const double* phi_mac, void* stream);
+/* rho_states + conservative density update + eint = p0/(gamma-1)/rho; keeps rho_old in plane 24 */
+int p2b_lm_density_update(p2b_lm* h, double* rho, double* eint, double dt, int limiter, double gamma, void* stream);
+int p2b_lm_upwind_states(p2b_lm* h, void* stream);
+int p2b_lm_advect_update(p2b_lm* h, double* u, double* v, const double* gradp_x, const double* gradp_y, double dt,
+                         int proj_type, void* stream);
+int p2b_lm_add_source(p2b_lm* h, double* v, double dt, void* stream);                 /* v += dt * source_y */
+int p2b_lm_cc_divergence(p2b_lm* h, const double* u, const double* v, double* div, int div_pitch, double dt, int divide,
+                         void* stream);                                                 /* D(beta0 U) [/ dt] */
+/* U -= dt (beta0/rho) G phi in the valid cells; proj_type 0: gradp untouched (dt = 1: preevolve), 1: +=, 2: = */
+int p2b_lm_project(p2b_lm* h, const double* rho, const double* phi, double* u, double* v, double* gradp_x,
+                   double* gradp_y, double dt, int proj_type, void* stream);
+/* scratch[0..4] (zeroed by the caller) <- bit patterns of max|u|, max|v| over the whole arrays and of max|u|, max|v|,
+ * max(|rho' g| / rho) over the valid cells: the inputs of method_compute_timestep (simulation.py:138-178) */
+int p2b_lm_reduce(p2b_lm* h, const double* rho, const double* u, const double* v, double grav, uint64_t* scratch,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # P2B_SO overrides the library path (A/B timing of kernel variants during development)
 SO_PATH = os.environ.get("P2B_SO") or os.path.join(CSRC, "libpyro2b200.so")
-SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu"]
-HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "../../include/pyro2b200.h"]
+SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu", "lm.cu"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "lm_kernels.cuh", "../../include/pyro2b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -117,6 +117,24 @@ SIGNATURES = {
     "p2b_flow_burgers_update": (_i, [_vp, _vp, _vp, _d, _vp]),
     "p2b_flow_advection_update": (_i, [_vp, _vp, _d, _d, _d, _i, _vp]),
     "p2b_flow_maxabs": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "p2b_lm_create": (_vp, [_PG, _vp]),
+    "p2b_lm_destroy": (_i, [_vp]),
+    "p2b_lm_workspace_bytes": (_ll, [_vp]),
+    "p2b_lm_bind": (_i, [_vp, _vp, _ll]),
+    "p2b_lm_plane": (_vp, [_vp, _i]),
+    "p2b_lm_coeff": (_i, [_vp, _vp, _vp, _d, _i, _i, _vp]),
+    "p2b_lm_source": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "p2b_lm_interface_states": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_lm_mac_vels": (_i, [_vp, _vp]),
+    "p2b_lm_mac_divergence": (_i, [_vp, _vp, _i, _vp]),
+    "p2b_lm_mac_project": (_i, [_vp, _vp, _vp]),
+    "p2b_lm_density_update": (_i, [_vp, _vp, _vp, _d, _i, _d, _vp]),
+    "p2b_lm_upwind_states": (_i, [_vp, _vp]),
+    "p2b_lm_advect_update": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_lm_add_source": (_i, [_vp, _vp, _d, _vp]),
+    "p2b_lm_cc_divergence": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
+    "p2b_lm_project": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
+    "p2b_lm_reduce": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp]),
 }
 
 

@@ -99,7 +99,7 @@ __device__ __forceinline__ double burgers_upwind(double l, double r, double s)
 }
 
 // slopes + get_interface_states (burgers_interface.py:45-77), over buf = 2
-__global__ void flow_states_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
+static __global__ void flow_states_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
                                    FlowFaces S, double dtdx, double dtdy, int limiter)
 {
     int i, j;
@@ -125,7 +125,7 @@ __global__ void flow_states_kernel(FlowGeom g, const double* __restrict__ u, con
 
 // first half of apply_transverse_corrections (burgers_interface.py:108-119): the Riemann velocities
 // and the states upwinded with them, over buf = 2
-__global__ void flow_hat_kernel(FlowGeom g, FlowFaces S, FlowHat H)
+static __global__ void flow_hat_kernel(FlowGeom g, FlowFaces S, FlowHat H)
 {
     int i, j;
     if (!flow_cell(g, 2, i, j)) return;
@@ -143,7 +143,7 @@ __global__ void flow_hat_kernel(FlowGeom g, FlowFaces S, FlowHat H)
 // second half (burgers_interface.py:121-155) followed by apply_gradp_corrections
 // (incomp_interface.py:190-209; gpx == nullptr for Burgers).  Thread (i, j) owns the entries
 // u_xl[i+1, j], u_xr[i, j], u_yl[i, j+1], u_yr[i, j] (and the same of v), so every entry is updated once.
-__global__ void flow_correct_kernel(FlowGeom g, FlowFaces S, FlowHat H, const double* __restrict__ gpx,
+static __global__ void flow_correct_kernel(FlowGeom g, FlowFaces S, FlowHat H, const double* __restrict__ gpx,
                                     const double* __restrict__ gpy, double dtdx, double dtdy, double dt)
 {
     int i, j;
@@ -175,7 +175,7 @@ __global__ void flow_correct_kernel(FlowGeom g, FlowFaces S, FlowHat H, const do
 }
 
 // riemann_and_upwind of the normal velocities (incomp_interface.py:64-69; burgers_interface.py:200-201)
-__global__ void flow_mac_kernel(FlowGeom g, FlowFaces S, double* __restrict__ umac, double* __restrict__ vmac)
+static __global__ void flow_mac_kernel(FlowGeom g, FlowFaces S, double* __restrict__ umac, double* __restrict__ vmac)
 {
     int i, j;
     if (!flow_cell(g, 2, i, j)) return;
@@ -186,7 +186,7 @@ __global__ void flow_mac_kernel(FlowGeom g, FlowFaces S, double* __restrict__ um
 }
 
 // divergence of the MAC velocities into a multigrid-grid plane (ng = 1) (incompressible/simulation.py:257-260)
-__global__ void flow_mac_div_kernel(FlowGeom g, const double* __restrict__ umac, const double* __restrict__ vmac,
+static __global__ void flow_mac_div_kernel(FlowGeom g, const double* __restrict__ umac, const double* __restrict__ vmac,
                                     double* __restrict__ div, int dpitch)
 {
     int i, j;
@@ -199,7 +199,7 @@ __global__ void flow_mac_div_kernel(FlowGeom g, const double* __restrict__ umac,
 
 // subtract the MAC gradient of phi-MAC (incompressible/simulation.py:277-284).  phi = the ng-ghost solver
 // plane whose buf = 1 region already holds the multigrid solution.  One thread per cell of v(buf=(0,1,0,1)).
-__global__ void flow_mac_project_kernel(FlowGeom g, const double* __restrict__ phi, double* __restrict__ umac,
+static __global__ void flow_mac_project_kernel(FlowGeom g, const double* __restrict__ phi, double* __restrict__ umac,
                                         double* __restrict__ vmac)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + g.ng;
@@ -211,7 +211,7 @@ __global__ void flow_mac_project_kernel(FlowGeom g, const double* __restrict__ p
 }
 
 // upwind all four interface states with the MAC velocities (incomp_interface.py:131-138)
-__global__ void flow_upwind_kernel(FlowGeom g, FlowFaces S, const double* __restrict__ umac,
+static __global__ void flow_upwind_kernel(FlowGeom g, FlowFaces S, const double* __restrict__ umac,
                                    const double* __restrict__ vmac, FlowHat H)
 {
     int i, j;
@@ -226,7 +226,7 @@ __global__ void flow_upwind_kernel(FlowGeom g, FlowFaces S, const double* __rest
 
 // advective terms and the provisional velocity update (incompressible/simulation.py:316-336), valid cells
 // (outside them the reference subtracts dt * 0, and the ghost cells are refilled right after)
-__global__ void flow_advect_kernel(FlowGeom g, const double* __restrict__ umac, const double* __restrict__ vmac,
+static __global__ void flow_advect_kernel(FlowGeom g, const double* __restrict__ umac, const double* __restrict__ vmac,
                                    FlowHat H, double* __restrict__ u, double* __restrict__ v,
                                    const double* __restrict__ gpx, const double* __restrict__ gpy, double dt, int proj_type)
 {
@@ -249,7 +249,7 @@ __global__ void flow_advect_kernel(FlowGeom g, const double* __restrict__ umac, 
 
 // cell-centred divergence 0.5*(u.ip(1) - u.ip(-1))/dx + 0.5*(v.jp(1) - v.jp(-1))/dy into a multigrid-grid
 // plane, optionally divided by dt (incompressible/simulation.py:96-97, 367-371)
-__global__ void flow_cc_div_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
+static __global__ void flow_cc_div_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
                                    double* __restrict__ div, int dpitch, double dt, int divide)
 {
     int i, j;
@@ -265,7 +265,7 @@ __global__ void flow_cc_div_kernel(FlowGeom g, const double* __restrict__ u, con
 // the final projection's update (incompressible/simulation.py:381-393; dt = 1, proj_type = 0 gives the
 // initial projection of preevolve, :113-118): over the whole array, with phi (whose buf = 1 region holds
 // the new solution) supplying the centred gradient in the valid cells and zero elsewhere
-__global__ void flow_project_kernel(FlowGeom g, const double* __restrict__ phi, double* __restrict__ u,
+static __global__ void flow_project_kernel(FlowGeom g, const double* __restrict__ phi, double* __restrict__ u,
                                     double* __restrict__ v, double* __restrict__ gpx, double* __restrict__ gpy,
                                     double dt, int proj_type)
 {
@@ -286,7 +286,7 @@ __global__ void flow_project_kernel(FlowGeom g, const double* __restrict__ phi, 
 }
 
 // Burgers: construct_unsplit_fluxes (burgers_interface.py:200-223) into four of the scratch planes ...
-__global__ void flow_burgers_flux_kernel(FlowGeom g, FlowFaces S, const double* __restrict__ umac,
+static __global__ void flow_burgers_flux_kernel(FlowGeom g, FlowFaces S, const double* __restrict__ umac,
                                          const double* __restrict__ vmac, FlowHat F)
 {
     int i, j;
@@ -300,7 +300,7 @@ __global__ void flow_burgers_flux_kernel(FlowGeom g, FlowFaces S, const double* 
 }
 
 // ... and the conservative update (burgers/simulation.py:117-121), valid cells
-__global__ void flow_burgers_update_kernel(FlowGeom g, FlowHat F, double* __restrict__ u, double* __restrict__ v,
+static __global__ void flow_burgers_update_kernel(FlowGeom g, FlowHat F, double* __restrict__ u, double* __restrict__ v,
                                            double dtdx, double dtdy)
 {
     int i, j;
@@ -315,7 +315,7 @@ __global__ void flow_burgers_update_kernel(FlowGeom g, FlowHat F, double* __rest
 // ---- linear advection (pyro/advection/interface.py:linear_interface, advective_fluxes.py:unsplit_fluxes,
 // advection/simulation.py:56-92): a_t + u a_x + v a_y = 0 with constant u, v ---------------------------
 // upwinded, time-centred interface states over buf = 1 (zero elsewhere, like the reference's scratch arrays)
-__global__ void flow_adv_states_kernel(FlowGeom g, const double* __restrict__ a, double* __restrict__ ax,
+static __global__ void flow_adv_states_kernel(FlowGeom g, const double* __restrict__ a, double* __restrict__ ax,
                                        double* __restrict__ ay, double u, double v, double cx, double cy, int limiter)
 {
     int i, j;
@@ -328,7 +328,7 @@ __global__ void flow_adv_states_kernel(FlowGeom g, const double* __restrict__ a,
 }
 
 // fluxes with the transverse correction (advective_fluxes.py:74-92), buf = 1; F_xt = u a_x, F_yt = v a_y
-__global__ void flow_adv_flux_kernel(FlowGeom g, const double* __restrict__ ax, const double* __restrict__ ay,
+static __global__ void flow_adv_flux_kernel(FlowGeom g, const double* __restrict__ ax, const double* __restrict__ ay,
                                      double* __restrict__ fx, double* __restrict__ fy, double u, double v,
                                      double dtdx2, double dtdy2)
 {
@@ -340,7 +340,7 @@ __global__ void flow_adv_flux_kernel(FlowGeom g, const double* __restrict__ ax, 
     fy[k] = exact_mul(v, exact_sub(ay[k], exact_mul(dtdx2, exact_sub(exact_mul(u, ax[k + g.pitch + my]), exact_mul(u, ax[k + my])))));
 }
 
-__global__ void flow_adv_update_kernel(FlowGeom g, double* __restrict__ a, const double* __restrict__ fx,
+static __global__ void flow_adv_update_kernel(FlowGeom g, double* __restrict__ a, const double* __restrict__ fx,
                                        const double* __restrict__ fy, double dtdx, double dtdy)
 {
     int i, j;
@@ -352,7 +352,7 @@ __global__ void flow_adv_update_kernel(FlowGeom g, double* __restrict__ a, const
 
 // max |u|, max |v| over the full arrays including ghost cells (burgers/simulation.py:51-58): the bit
 // patterns of the maxima are combined with atomicMax (non-negative doubles order like their bits)
-__global__ void flow_maxabs_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
+static __global__ void flow_maxabs_kernel(FlowGeom g, const double* __restrict__ u, const double* __restrict__ v,
                                    unsigned long long* out)
 {
     const long long total = (long long)g.qx * g.qy;

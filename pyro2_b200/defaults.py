@@ -61,6 +61,13 @@ SOLVER = {
         "driver.cfl": (0.8, "diffusion CFL number (may exceed 1: the update is implicit)"),
         "diffusion.k": (1.0, "conductivity"),
     },
+    "lm_atm": {
+        "driver.cfl": (0.8, ""),
+        "lm-atmosphere.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
+        "lm-atmosphere.proj_type": (2, "what is projected: 1 includes the -Gp term in U*"),
+        "lm-atmosphere.grav": (-2.0, "gravitational acceleration along y"),
+        "eos.gamma": (1.4, "pres = rho ener (gamma - 1)"),
+    },
     "burgers": {
         "driver.cfl": (0.8, "advective CFL number"),
         "advection.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),

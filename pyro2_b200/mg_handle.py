@@ -109,7 +109,8 @@ class MGHandle:
         assert self.decomp is None, "variable coefficients: single-GPU hierarchies only"
         assert coeffs.is_cuda and coeffs.dtype == torch.float64 and coeffs.stride(1) == 1
         nbytes = L.p2b_mg_coeff_workspace_bytes(self._h)
-        self.coeff_workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+        if getattr(self, "coeff_workspace", None) is None:      # kept across calls: views and graphs point into it
+            self.coeff_workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
         codes = (C.c_int * 4)(*[_lib.BC_CODES[b] for b in coeffs_bc])
         _lib.check(L.p2b_mg_set_coeffs(self._h, self.coeff_workspace.data_ptr(), nbytes, coeffs.data_ptr(),
                                        coeffs.stride(0), codes, self._s()))

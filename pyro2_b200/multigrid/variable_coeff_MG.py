@@ -39,6 +39,23 @@ class VarCoeffCCMG2d(MG.CellCenterMG2d):
                          yl_BC_type=yl_BC_type, yr_BC_type=yr_BC_type,
                          alpha=0.0, beta=0.0, nsmooth=nsmooth, nsmooth_bottom=nsmooth_bottom,
                          verbose=verbose, true_function=true_function, vis=vis, vis_title=vis_title)
+        self.coeffs_bc = coeffs_bc
+        self._nxy = (nx, ny)
+        self.set_coeffs(coeffs)
+        # coarsest first, like grids[] (variable_coeff_MG.py:44-46, 78-90)
+        self.coeffs = []
+        self.edge_coeffs = []
+        for level in range(self.nlevels):
+            lg = self.grids[level].grid
+            self.coeffs.append(ArrayIndexer(self._h.coeff_plane(level, "c"), grid=lg))
+            self.edge_coeffs.append(EdgeCoeffs(lg, self._h.coeff_plane(level, "x"), self._h.coeff_plane(level, "y")))
+
+    def set_coeffs(self, coeffs):
+        """(re)build every level's eta and edge coefficients from eta on the solution grid.  The constructor
+        calls this once, as the reference does; calling it again on an existing solver replaces what would be a
+        new VarCoeffCCMG2d with other coefficients (the lm_atm solver builds three per step) -- workspace, views
+        and a captured V-cycle graph stay valid because the planes are rewritten in place."""
+        nx, ny = self._nxy
         g = getattr(coeffs, "g", None)
         if g is not None and (g.nx != nx or g.ny != ny):
             raise IndexError("coefficient array not the same size as multigrid problem")
@@ -50,13 +67,5 @@ class VarCoeffCCMG2d(MG.CellCenterMG2d):
             raise IndexError("coefficient array not the same size as multigrid problem")
         if c.stride(1) != 1:
             c = c.contiguous()
-        names = (coeffs_bc.xlb, coeffs_bc.xrb, coeffs_bc.ylb, coeffs_bc.yrb)
-        self.coeffs_bc = coeffs_bc
-        self._h.set_coeffs(c, names)
-        # coarsest first, like grids[] (variable_coeff_MG.py:44-46, 78-90)
-        self.coeffs = []
-        self.edge_coeffs = []
-        for level in range(self.nlevels):
-            lg = self.grids[level].grid
-            self.coeffs.append(ArrayIndexer(self._h.coeff_plane(level, "c"), grid=lg))
-            self.edge_coeffs.append(EdgeCoeffs(lg, self._h.coeff_plane(level, "x"), self._h.coeff_plane(level, "y")))
+        bc = self.coeffs_bc
+        self._h.set_coeffs(c, (bc.xlb, bc.xrb, bc.ylb, bc.yrb))

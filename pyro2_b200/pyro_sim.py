@@ -14,7 +14,7 @@ from .util import msg
 from .util import profile_pyro as profile
 from .util.runparams import RuntimeParameters
 
-valid_solvers = ["advection", "burgers", "compressible", "diffusion", "incompressible"]
+valid_solvers = ["advection", "burgers", "compressible", "diffusion", "incompressible", "lm_atm"]
 
 
 class Pyro:

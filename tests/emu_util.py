@@ -46,6 +46,11 @@ def load_bc_emu():
     return _load("bc", ["bc_user.cu", "bc_user_kernels.cuh"], "p2b_fill_hse")
 
 
+def load_lm_emu():
+    """pyro2_b200/csrc/lm.cu compiled for the host: the p2b_lm_* ABI over numpy memory"""
+    return _load("lm", ["lm.cu", "lm_kernels.cuh", "flow_kernels.cuh"], "p2b_lm_", ["-Wno-unused-function"])
+
+
 def load_flow_emu():
     """pyro2_b200/csrc/flow.cu compiled for the host: the p2b_flow_* ABI over numpy memory"""
     return _load("flow", ["flow.cu", "flow_kernels.cuh"], "p2b_flow_")
@@ -208,3 +213,123 @@ class EmuFlow:
         phi[ng - 1:ng + n + 1, ng - 1:ng + n + 1] = sol
         self.ck(L.p2b_flow_project(h, ptr(phi), ptr(u), ptr(v), ptr(gpx), ptr(gpy), dt, proj_type, None))
         fill(u); fill(v)
+
+
+class EmuLm:
+    """the p2b_lm_* stage calls over numpy planes plus the orchestration of lm_atm Simulation.evolve / preevolve /
+    method_compute_timestep (lm_atm/simulation.py:138-618) with EmuMG doing the variable-coefficient projections --
+    the same sequence pyro2_b200/lm_atm/simulation.py issues on the device"""
+
+    COEFF, SOURCE = 16, 17
+
+    def __init__(self, lib, mg_lib, n, ng, base, fills, phi_bc, grav=-2.0, gamma=1.4, limiter=2, proj_type=2):
+        """base: (4, qy) rho0, p0, beta0, beta0-edges; fills: name -> BC names for oracle.fill_ghost"""
+        from pyro2_b200 import _lib
+        self.lib, self.mg_lib, self.n, self.ng = lib, mg_lib, n, ng
+        self.q = n + 2 * ng
+        self.base = np.ascontiguousarray(base, dtype=np.float64)
+        self.fills, self.phi_bc = fills, phi_bc
+        self.grav, self.gamma, self.limiter, self.proj_type = grav, gamma, limiter, proj_type
+        self.grid = _lib.Grid(n, n, ng, self.q, self.q * self.q, 1.0 / n, 1.0 / n)
+        self.h = lib.p2b_lm_create(C.byref(self.grid), self.base.ctypes.data)
+        assert self.h, lib.p2b_last_error()
+        nbytes = lib.p2b_lm_workspace_bytes(self.h)
+        self.ws = np.zeros(nbytes // 8)
+        self.ck(lib.p2b_lm_bind(self.h, self.ws.ctypes.data, nbytes))
+
+    def ck(self, rc):
+        assert rc == 0, self.lib.p2b_last_error().decode()
+
+    def close(self):
+        self.lib.p2b_lm_destroy(self.h)
+
+    def plane(self, idx):
+        ptr = self.lib.p2b_lm_plane(self.h, idx)
+        off = (ptr - self.ws.ctypes.data) // 8
+        return self.ws[off:off + self.q * self.q].reshape(self.q, self.q)
+
+    def _fill(self, a, name):
+        import oracle
+        oracle.fill_ghost(a, self.ng, self.fills[name])
+
+    def _solve(self, coeff_plane, div, rtol, v0=None):
+        n, ng = self.n, self.ng
+        mg = EmuMG(self.mg_lib, n, self.phi_bc, 0.0, 0.0)
+        mg.set_coeffs(np.ascontiguousarray(coeff_plane[ng - 1:ng + n + 1, ng - 1:ng + n + 1]), self.fills["density"])
+        sol = mg.solve(div, rtol=rtol, v0=v0)
+        cycles = mg.num_cycles
+        mg.close()
+        return sol, cycles
+
+    def timestep(self, S, cfl):
+        out = np.zeros(5, dtype=np.uint64)
+        self.ck(self.lib.p2b_lm_reduce(self.h, S[0].ctypes.data, S[1].ctypes.data, S[2].ctypes.data, self.grav,
+                                       out.ctypes.data, None))
+        uall, vall, uval, vval, fb = out.view(np.float64)
+        dx = 1.0 / self.n
+        xtmp = ytmp = 1.e33
+        if not uall == 0:
+            xtmp = dx / uval
+        if not vall == 0:
+            ytmp = dx / vval
+        dt = cfl * min(xtmp, ytmp)
+        with np.errstate(divide="ignore"):
+            dt_buoy = np.sqrt(2.0 * dx / fb)
+        return float(min(dt, dt_buoy))
+
+    def initial_projection(self, S):
+        L, h, n, ng = self.lib, self.h, self.n, self.ng
+        rho, u, v, phi = S[0], S[1], S[2], S[5]
+        p = lambda a: a.ctypes.data
+        self._fill(rho, "density"); self._fill(u, "x-velocity"); self._fill(v, "y-velocity")
+        self.ck(L.p2b_lm_coeff(h, p(rho), None, 1.0, 1, 0, None))
+        div = np.zeros((n + 2, n + 2))
+        self.ck(L.p2b_lm_cc_divergence(h, p(u), p(v), p(div), n + 2, 1.0, 0, None))
+        sol, _ = self._solve(self.plane(self.COEFF), div, 1.e-10)
+        phi[:] = 0.0
+        phi[ng - 1:ng + n + 1, ng - 1:ng + n + 1] = sol
+        self.ck(L.p2b_lm_project(h, p(rho), p(phi), p(u), p(v), None, None, 1.0, 0, None))
+        self._fill(u, "x-velocity"); self._fill(v, "y-velocity")
+
+    def evolve(self, S, dt):
+        L, h, n, ng = self.lib, self.h, self.n, self.ng
+        rho, u, v, eint, phi_mac, phi, gpx, gpy = (S[k] for k in range(8))
+        p = lambda a: a.ctypes.data
+        coeff, source = self.plane(self.COEFF), self.plane(self.SOURCE)
+        # MAC velocities
+        self.ck(L.p2b_lm_coeff(h, p(rho), None, 1.0, 0, 0, None)); self._fill(coeff, "density")
+        self.ck(L.p2b_lm_source(h, p(rho), None, self.grav, None)); self._fill(source, "y-velocity")
+        self.ck(L.p2b_lm_interface_states(h, p(u), p(v), p(gpx), p(gpy), dt, self.limiter, None))
+        self.ck(L.p2b_lm_mac_vels(h, None))
+        # MAC projection
+        self.ck(L.p2b_lm_coeff(h, p(rho), None, 1.0, 1, 1, None))
+        div = np.zeros((n + 2, n + 2))
+        self.ck(L.p2b_lm_mac_divergence(h, p(div), n + 2, None))
+        sol, c0 = self._solve(coeff, div, 1.e-12)
+        phi_mac[:] = 0.0
+        phi_mac[ng - 1:ng + n + 1, ng - 1:ng + n + 1] = sol
+        self.ck(L.p2b_lm_coeff(h, p(rho), None, 1.0, 0, 0, None)); self._fill(coeff, "density")
+        self.ck(L.p2b_lm_mac_project(h, p(phi_mac), None))
+        # density
+        self.ck(L.p2b_lm_density_update(h, p(rho), p(eint), dt, self.limiter, self.gamma, None))
+        self._fill(rho, "density")
+        # velocities
+        rho_old = self.plane(24)
+        self.ck(L.p2b_lm_coeff(h, p(rho), p(rho_old), 2.0, 0, 0, None)); self._fill(coeff, "density")
+        self.ck(L.p2b_lm_interface_states(h, p(u), p(v), p(gpx), p(gpy), dt, self.limiter, None))
+        self.ck(L.p2b_lm_upwind_states(h, None))
+        self.ck(L.p2b_lm_advect_update(h, p(u), p(v), p(gpx), p(gpy), dt, self.proj_type, None))
+        self.ck(L.p2b_lm_source(h, p(rho), p(rho_old), self.grav, None)); self._fill(source, "y-velocity")
+        self.ck(L.p2b_lm_add_source(h, p(v), dt, None))
+        self._fill(u, "x-velocity"); self._fill(v, "y-velocity")
+        # final projection
+        self.ck(L.p2b_lm_coeff(h, p(rho), None, 1.0, 1, 0, None))
+        div = np.zeros((n + 2, n + 2))
+        self.ck(L.p2b_lm_cc_divergence(h, p(u), p(v), p(div), n + 2, dt, 1, None))
+        sol, c1 = self._solve(coeff, div, 1.e-12, v0=phi[ng - 1:ng + n + 1, ng - 1:ng + n + 1].copy())
+        phi[:] = 0.0
+        phi[ng - 1:ng + n + 1, ng - 1:ng + n + 1] = sol
+        self.ck(L.p2b_lm_project(h, p(rho), p(phi), p(u), p(v), p(gpx), p(gpy), dt, self.proj_type, None))
+        self._fill(u, "x-velocity"); self._fill(v, "y-velocity")
+        self._fill(gpx, "gradp_x"); self._fill(gpy, "gradp_y")
+        return c0, c1

@@ -250,3 +250,40 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         v = (slice(4, -4), slice(4, -4))
         for k, n in enumerate(names):
             assert np.abs(d.get_var(n).numpy()[v] - z["P0"][k][v]).max() < 5e-3, n
+
+
+def test_lm_atm_problem_setup_matches_reference():
+    """lm_atm bubble: the 1-d base state (horizontal means, hydrostatic re-integration) and beta0 arrays the
+    host-side setup builds, against the fixture from the reference"""
+    import os
+    from golden_util import GOLDEN, _parse
+    from pyro2_b200 import defaults
+    from pyro2_b200.lm_atm.problems import bubble
+    from pyro2_b200.lm_atm.simulation import Basestate
+    from pyro2_b200.mesh import patch
+    from pyro2_b200.simulation_null import bc_setup
+    from pyro2_b200.util.runparams import RuntimeParameters
+    z = np.load(os.path.join(GOLDEN, "lm_bubble32.npz"))
+    rp = RuntimeParameters()
+    rp.load_dict(defaults.GLOBAL)
+    rp.load_dict(defaults.SOLVER["lm_atm"])
+    for k, v in bubble.PROBLEM_PARAMS.items():
+        rp.set_param(k, v, no_new=False)
+    rp.load_dict(bubble.INPUTS, no_new=True)
+    for s in z["inputs"]:
+        k, v = s.split("=", 1)
+        rp.set_param(k, _parse(v))
+    rp.set_param("driver.verbose", 0)
+    g = patch.Cartesian2d(32, 32, ng=4, device="cpu")
+    d = patch.CellCenterData2d(g)
+    bc = bc_setup(rp)[0]
+    for n in ("density", "x-velocity", "y-velocity", "eint"):
+        d.register_var(n, bc)
+    d.create()
+    base = {"rho0": Basestate(32, ng=4), "p0": Basestate(32, ng=4)}
+    bubble.init_data(d, base, rp)
+    assert np.array_equal(base["rho0"].d, z["base"][0]) and np.array_equal(base["p0"].d, z["base"][1])
+    beta0 = base["p0"].d ** (1.0 / 1.4)
+    assert np.array_equal(beta0, z["base"][2])
+    # density before the initial projection is what the fixture still holds (the projection moves only velocities)
+    assert np.array_equal(d.get_var("density").numpy()[4:-4, 4:-4], z["P0"][0][4:-4, 4:-4])

@@ -144,6 +144,33 @@ def test_diffusion_gaussian_follows_analytic_solution():
     assert np.abs(phi[v] - exact[v]).max() < 5e-3 * (exact[v].max() - 1.0) + 2e-4
 
 
+@pytest.mark.parametrize("fname", ["lm_bubble32.npz", "lm_bubble64_lim1.npz"])
+def test_pyro_lm_atm_run_matches_reference(fname):
+    """the low Mach number atmosphere solver (third multigrid caller, variable-coefficient projections): state
+    after initialize + preevolve, every dt and all eight planes after the run, bit for bit"""
+    p, sim, z, state = _run("lm_atm", fname)
+    assert np.array_equal(np.stack([sim.base[k].d for k in ("rho0", "p0", "beta0", "beta0-edges")]), z["base"])
+    assert np.array_equal(state(), z["P0"])
+    dts = []
+    for _ in range(len(z["dts"])):
+        p.single_step()
+        dts.append(sim.dt)
+    assert np.array_equal(np.array(dts), z["dts"])
+    assert np.array_equal(state(), z["P"])
+
+
+def test_lm_atm_bubble_rises():
+    from pyro2_b200.pyro_sim import Pyro
+    p = Pyro("lm_atm")
+    p.initialize_problem("bubble", inputs_dict={"mesh.nx": 64, "mesh.ny": 64, "driver.max_steps": 12})
+    p.run_sim()
+    sim = p.sim
+    v = sim.cc_data.get_var("y-velocity").v()
+    assert sim.n == 12 and float(v.max()) > 1e-3          # the light bubble accelerates upward
+    rho = sim.cc_data.get_var("density").v()
+    assert float(rho.min()) > 0.0
+
+
 def test_incompressible_projection_leaves_divergence_free_field():
     """after a step the cell-centred divergence of (u, v) is at the level the projection tolerance allows"""
     from pyro2_b200.pyro_sim import Pyro
