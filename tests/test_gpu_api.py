@@ -96,7 +96,7 @@ def test_unsupported_configurations_fail_loudly():
         with pytest.raises(SystemExit):
             p.initialize_problem("sedov", inputs_dict={key: val})
     with pytest.raises(SystemExit):
-        Pyro("advection")
+        Pyro("swe")          # a reference solver this build does not provide
 
 
 @pytest.mark.parametrize("name", ["poisson_dirichlet_64", "poisson_dirichlet_256", "poisson_periodic_64",
