@@ -60,6 +60,9 @@ typedef struct {
                               * unsplit_fluxes.py:247-330 */
     int src_flip_ylo;        /* 1 when the -y / +y boundary reflects: the reference fills the ghost cells of  */
     int src_flip_yhi;        /*   its source arrays odd (ymom_src) / even (E_src) there (simulation.py:248-253) */
+    int riemann;             /* compressible.riemann: 0 HLLC (riemann.py:682-860), 1 CGF (riemann.py:9-310 + consFlux) */
+    int xl_solid, yl_solid;  /* CGF: the -x / -y boundary is a solid wall (boundary.bc_is_solid): zero normal
+                              * velocity in the interface state on that face (riemann.py:283-292) */
 } p2b_comp_params;
 
 /* device scratch the sweep needs, 8 x 64-bit words owned by the caller:
@@ -107,7 +110,8 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
  * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, Cartesian geometry,
- * HLLC; prm->grav != 0 selects the instantiation with the gravity source terms. */
+ * Riemann solver HLLC or CGF (prm->riemann); prm->grav != 0 selects the instantiations with the gravity
+ * source terms. */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
 

@@ -30,7 +30,8 @@ class CompParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double),
                 ("delta", C.c_double), ("cvisc", C.c_double), ("limiter", C.c_int),
                 ("use_flattening", C.c_int), ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
-                ("grav", C.c_double), ("src_bc", C.c_int * 16)]
+                ("grav", C.c_double), ("src_bc", C.c_int * 16),
+                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int)]
 
 
 class LmParams(C.Structure):
@@ -150,14 +151,15 @@ def cfl_dt(U_ijn, ng, dx, dy, gamma, cfl):
 
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
-                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None):
+                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None, riemann="HLLC", xl_solid=0, yl_solid=0):
     """src_bcs: BC names (xlb, xrb, ylb, yrb) of the four source arrays in variable order dens, ener, xmom,
     ymom (only needed with gravity); "hse" copies like outflow for them"""
     codes = (C.c_int * 16)()
     if src_bcs is not None:
         flat = [BC_CODES["outflow" if b == "hse" else b] for bc in src_bcs for b in bc]
         codes = (C.c_int * 16)(*flat)
-    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes)
+    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes,
+                      {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid)
 
 
 def fill_hse(P, ng, dy, grav, gamma, var, side):

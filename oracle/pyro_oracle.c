@@ -144,6 +144,9 @@ typedef struct {
        copies the first interior row like outflow (compressible/BC.py:55-63, 111-117) */
     double grav;
     int src_bc[16];
+    /* compressible.riemann: 0 HLLC, 1 CGF; xl_solid / yl_solid: the -x / -y boundary is a solid wall
+       (boundary.bc_is_solid), which CGF uses to zero the normal velocity at that face */
+    int riemann, xl_solid, yl_solid;
 } orc_comp_params;
 
 /* optional per-stage dumps, each (4 or 1) planes of qx*qy doubles; NULL = skip */
@@ -443,6 +446,96 @@ static void riemann_hllc(int idir, const double *U_l, const double *U_r, double 
         }
 }
 
+/* riemann.py:9-310 (riemann_cgf: the two-shock solver of Colella, Glaz & Ferguson) followed by consFlux
+ * (riemann_flux :1075-1085); lower_solid: the normal velocity at the face on a solid lower boundary is zero
+ * (the upper test `i == ihi + 1` in the reference can never fire inside its loop range) */
+static void riemann_cgf(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
+                        double gamma, int lower_solid)
+{
+    const size_t np = (size_t)qx * qy;
+    const int nx = qx - 2 * ng, ny = qy - 2 * ng;
+    const int ilo = ng, ihi = ng + nx, jlo = ng, jhi = ng + ny;
+    const double smallc = 1.e-10, smallrho = 1.e-10, smallp = 1.e-10;
+    const int imn = idir == 1 ? IXMOM : IYMOM, imt = idir == 1 ? IYMOM : IXMOM;
+    memset(F, 0, 4 * np * sizeof(double));
+#pragma omp parallel for
+    for (int i = ilo - 1; i < ihi + 1; i++)
+        for (int j = jlo - 1; j < jhi + 1; j++) {
+            const size_t k = IDX(i, j);
+            const double rho_l = U_l[IDENS * np + k];
+            const double un_l = U_l[imn * np + k] / rho_l, ut_l = U_l[imt * np + k] / rho_l;
+            const double rhoe_l = U_l[IENER * np + k] - 0.5 * rho_l * (un_l * un_l + ut_l * ut_l);
+            const double p_l = fmax(rhoe_l * (gamma - 1.0), smallp);
+            const double rho_r = U_r[IDENS * np + k];
+            const double un_r = U_r[imn * np + k] / rho_r, ut_r = U_r[imt * np + k] / rho_r;
+            const double rhoe_r = U_r[IENER * np + k] - 0.5 * rho_r * (un_r * un_r + ut_r * ut_r);
+            const double p_r = fmax(rhoe_r * (gamma - 1.0), smallp);
+            const double W_l = fmax(smallrho * smallc, sqrt(gamma * p_l * rho_l));
+            const double W_r = fmax(smallrho * smallc, sqrt(gamma * p_r * rho_r));
+            const double c_l = fmax(smallc, sqrt(gamma * p_l / rho_l));
+            const double c_r = fmax(smallc, sqrt(gamma * p_r / rho_r));
+            double pstar = (W_l * p_r + W_r * p_l + W_l * W_r * (un_l - un_r)) / (W_l + W_r);
+            pstar = fmax(pstar, smallp);
+            const double ustar = (W_l * un_l + W_r * un_r + (p_l - p_r)) / (W_l + W_r);
+            const double rhostar_l = rho_l + (pstar - p_l) / (c_l * c_l);
+            const double rhostar_r = rho_r + (pstar - p_r) / (c_r * c_r);
+            const double rhoestar_l = rhoe_l + (pstar - p_l) * (rhoe_l / rho_l + p_l / rho_l) / (c_l * c_l);
+            const double rhoestar_r = rhoe_r + (pstar - p_r) * (rhoe_r / rho_r + p_r / rho_r) / (c_r * c_r);
+            const double cstar_l = fmax(smallc, sqrt(gamma * pstar / rhostar_l));
+            const double cstar_r = fmax(smallc, sqrt(gamma * pstar / rhostar_r));
+            double rho_s, un_s, ut_s, rhoe_s;
+            if (ustar > 0.0) {
+                ut_s = ut_l;
+                const double lam = un_l - c_l, lams = ustar - cstar_l;
+                int star;          /* 1: star state, 0: left state, 2: inside the rarefaction */
+                if (pstar > p_l) star = ((lam + lams) / 2.0 > 0.0) ? 0 : 1;
+                else star = (lam < 0.0 && lams < 0.0) ? 1 : ((lam > 0.0 && lams > 0.0) ? 0 : 2);
+                if (star == 0) { rho_s = rho_l; un_s = un_l; rhoe_s = rhoe_l; }
+                else if (star == 1) { rho_s = rhostar_l; un_s = ustar; rhoe_s = rhoestar_l; }
+                else {
+                    const double alpha = lam / (lam - lams);
+                    rho_s = alpha * rhostar_l + (1.0 - alpha) * rho_l;
+                    un_s = alpha * ustar + (1.0 - alpha) * un_l;
+                    rhoe_s = alpha * rhoestar_l + (1.0 - alpha) * rhoe_l;
+                }
+            } else if (ustar < 0) {
+                ut_s = ut_r;
+                const double lam = un_r + c_r, lams = ustar + cstar_r;
+                int star;          /* 1: star state, 0: right state, 2: inside the rarefaction */
+                if (pstar > p_r) star = ((lam + lams) / 2.0 > 0.0) ? 1 : 0;
+                else star = (lam < 0.0 && lams < 0.0) ? 0 : ((lam > 0.0 && lams > 0.0) ? 1 : 2);
+                if (star == 0) { rho_s = rho_r; un_s = un_r; rhoe_s = rhoe_r; }
+                else if (star == 1) { rho_s = rhostar_r; un_s = ustar; rhoe_s = rhoestar_r; }
+                else {
+                    const double alpha = lam / (lam - lams);
+                    rho_s = alpha * rhostar_r + (1.0 - alpha) * rho_r;
+                    un_s = alpha * ustar + (1.0 - alpha) * un_r;
+                    rhoe_s = alpha * rhoestar_r + (1.0 - alpha) * rhoe_r;
+                }
+            } else {
+                rho_s = 0.5 * (rhostar_l + rhostar_r);
+                un_s = ustar;
+                ut_s = 0.5 * (ut_l + ut_r);
+                rhoe_s = 0.5 * (rhoestar_l + rhoestar_r);
+            }
+            if (lower_solid && ((idir == 1 && i == ilo) || (idir == 2 && j == jlo))) un_s = 0.0;
+            double Us[4], Fk[4];
+            Us[IDENS] = rho_s;
+            Us[imn] = rho_s * un_s;
+            Us[imt] = rho_s * ut_s;
+            Us[IENER] = rhoe_s + 0.5 * rho_s * (un_s * un_s + ut_s * ut_s);
+            cons_flux(idir, gamma, Us, Fk);
+            for (int m = 0; m < 4; m++) F[m * np + k] = Fk[m];
+        }
+}
+
+static void riemann_solve(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
+                          const orc_comp_params *P)
+{
+    if (P->riemann == 1) riemann_cgf(idir, U_l, U_r, F, qx, qy, ng, P->gamma, idir == 1 ? P->xl_solid : P->yl_solid);
+    else riemann_hllc(idir, U_l, U_r, F, qx, qy, ng, P->gamma);
+}
+
 /* interface.py:240-378, Cartesian branch.  u, v full planes. */
 static void artificial_viscosity(const double *u, const double *v, double *ax, double *ay, int qx,
                                  int qy, int ng, double dx, double dy, double cvisc, int skip_xhi,
@@ -602,8 +695,8 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     }
 
     /* apply_transverse_flux (unsplit_fluxes.py:420-471) */
-    riemann_hllc(1, U_xl, U_xr, F_x, qx, qy, ng, gamma);
-    riemann_hllc(2, U_yl, U_yr, F_y, qx, qy, ng, gamma);
+    riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
+    riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
     dump(S->Fx_t, F_x, 4 * np); dump(S->Fy_t, F_y, 4 * np);
     {
         const double hdt = 0.5 * dt, hdtV = hdt / (dx * dy), Ax = dy, Ay = dx;
@@ -625,8 +718,8 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->Uyl, U_yl, 4 * np); dump(S->Uyr, U_yr, 4 * np);
 
     /* final fluxes (simulation.py:349-357) */
-    riemann_hllc(1, U_xl, U_xr, F_x, qx, qy, ng, gamma);
-    riemann_hllc(2, U_yl, U_yr, F_y, qx, qy, ng, gamma);
+    riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
+    riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
 
     /* artificial viscosity (simulation.py:361-365, unsplit_fluxes.py:497-549) */
     if (cons_to_prim(U, q, qx, qy, ng, gamma)) rc = 3;

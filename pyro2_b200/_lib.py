@@ -50,7 +50,8 @@ class CompParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("z0", C.c_double), ("z1", C.c_double), ("delta", C.c_double),
                 ("cvisc", C.c_double), ("limiter", C.c_int), ("use_flattening", C.c_int),
                 ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
-                ("grav", C.c_double), ("src_flip_ylo", C.c_int), ("src_flip_yhi", C.c_int)]
+                ("grav", C.c_double), ("src_flip_ylo", C.c_int), ("src_flip_yhi", C.c_int),
+                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int)]
 
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,

@@ -10,7 +10,7 @@ What maps to what
   cons_to_prim / prim_to_cons         simulation.py:49-102   (torch, for users / tests / output)
   Variables                           simulation.py:12-46
 
-Scope: Cartesian grid, HLLC, constant gravity and the hse boundary; no sponge /
+Scope: Cartesian grid, HLLC or CGF, constant gravity and the hse boundary; no sponge /
 particles / problem sources / ambient and ramp boundaries.
 Anything else raises instead of silently taking another path.
 """
@@ -83,8 +83,8 @@ class Simulation(NullSimulation):
         my_data = self.data_class(my_grid)
 
         riemann_method = rp.get_param("compressible.riemann")
-        if riemann_method != "HLLC":
-            msg.fail(f"ERROR: the device sweep implements the HLLC Riemann solver only (got {riemann_method})")
+        if riemann_method not in ("HLLC", "CGF"):
+            msg.fail(f"ERROR: the device sweep implements the HLLC and CGF Riemann solvers (got {riemann_method})")
         # solver-specific boundary types (simulation.py:212-214); ambient and ramp are not built
         bnd.define_bc("hse", BC.user, is_solid=False)
         try:
@@ -147,7 +147,10 @@ class Simulation(NullSimulation):
                                use_flattening=rp.get_param("compressible.use_flattening"),
                                no_avisc_xhi=getattr(self, "_no_avisc_xhi", 1), no_avisc_yhi=1,
                                grav=rp.get_param("compressible.grav"),
-                               src_flip_ylo=self._src_flip[0], src_flip_yhi=self._src_flip[1])
+                               src_flip_ylo=self._src_flip[0], src_flip_yhi=self._src_flip[1],
+                               riemann=rp.get_param("compressible.riemann"),
+                               xl_solid=int(self.solid.xl) if (self.decomposition is None or self.decomposition.is_first) else 0,
+                               yl_solid=int(self.solid.yl))
 
     def _read_scratch(self):
         """one D2H copy: wave-speed maxima + status word of the last sweep"""

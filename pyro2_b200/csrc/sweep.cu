@@ -79,7 +79,7 @@ struct CudaWarp {
     }
 };
 
-template <bool GRAV>
+template <bool GRAV, int RIEMANN>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
 {
@@ -95,7 +95,7 @@ sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
     __syncwarp();
 
     CudaWarp w;
-    SweepTask<CudaWarp, GRAV> T(w, A, S, 0u);
+    SweepTask<CudaWarp, GRAV, RIEMANN> T(w, A, S, 0u);
     for (;;) {
         int t = 0;
         if (lane == 0) t = (int)atomicAdd(task_counter, 1ull);
@@ -114,12 +114,13 @@ static int resident_warps()
     static int resident = 0;
     if (!resident) {
         int blocks = 0;
-        cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(SWEEP_WARPS * sizeof(SweepSmem)));
-        cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(SWEEP_WARPS * sizeof(SweepSmem)));
-        // the gravity instantiation has the same launch bounds, hence the same residency
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false>, SWEEP_THREADS,
+        const int smem = (int)(SWEEP_WARPS * sizeof(SweepSmem));
+        cudaFuncSetAttribute(sweep_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // every instantiation has the same launch bounds and shared memory, hence the same residency
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false, 0>, SWEEP_THREADS,
                                                       SWEEP_WARPS * sizeof(SweepSmem));
         if (blocks < 1) blocks = 1;
         resident = blocks * SWEEP_WARPS * num_sms();
@@ -162,6 +163,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     P2B_REQUIRE(g->pitch >= g->ny + 2 * g->ng && (g->pitch % 2) == 0, "pitch must be even and >= qy");
     P2B_REQUIRE((g->plane_stride % 2) == 0 && ((uintptr_t)Uin % 16) == 0, "planes must be 16-byte aligned");
     P2B_REQUIRE(prm->limiter >= 0 && prm->limiter <= 2, "limiter must be 0, 1 or 2");
+    P2B_REQUIRE(prm->riemann == 0 || prm->riemann == 1, "riemann must be 0 (HLLC) or 1 (CGF)");
     cudaStream_t st = (cudaStream_t)stream;
 
     SweepArgs A;
@@ -173,6 +175,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     A.limiter = prm->limiter; A.use_flattening = prm->use_flattening;
     A.no_avisc_xhi = prm->no_avisc_xhi; A.no_avisc_yhi = prm->no_avisc_yhi;
     A.grav = prm->grav; A.src_flip_ylo = prm->src_flip_ylo; A.src_flip_yhi = prm->src_flip_yhi;
+    A.xl_solid = prm->xl_solid; A.yl_solid = prm->yl_solid;
     A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
     A.seglen = choose_seglen(g->nx, A.nstrips, resident);
@@ -186,12 +189,16 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     int blocks = (ntasks + SWEEP_WARPS - 1) / SWEEP_WARPS;
     const int maxblocks = resident / SWEEP_WARPS;
     if (blocks > maxblocks) blocks = maxblocks;
-    if (prm->grav != 0.0)
-        sweep_kernel<true><<<blocks, SWEEP_THREADS, SWEEP_WARPS * sizeof(SweepSmem), st>>>(
-            A, (unsigned long long*)(scratch + 2), ntasks);
-    else
-        sweep_kernel<false><<<blocks, SWEEP_THREADS, SWEEP_WARPS * sizeof(SweepSmem), st>>>(
-            A, (unsigned long long*)(scratch + 2), ntasks);
+    const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
+    unsigned long long* counter = (unsigned long long*)(scratch + 2);
+    const bool grav = prm->grav != 0.0;
+    if (prm->riemann == 1) {
+        if (grav) sweep_kernel<true, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        else sweep_kernel<false, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+    } else {
+        if (grav) sweep_kernel<true, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        else sweep_kernel<false, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+    }
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }

@@ -58,6 +58,7 @@ struct SweepArgs {
     // gravity (GRAV instantiation only; kept at the end so the default kernel's parameter layout is unchanged)
     double grav;                      // compressible.grav, acceleration along y
     int src_flip_ylo, src_flip_yhi;   // 1: that y boundary reflects -> the ghost-cell SOURCES change sign
+    int xl_solid, yl_solid;           // CGF: the -x / -y boundary is a solid wall (boundary.bc_is_solid)
 };
 
 struct alignas(16) SweepSmem {
@@ -73,7 +74,8 @@ struct alignas(16) SweepSmem {
 // get_external_sources :105-160).  The reference fills the ghost cells of the source ARRAYS with their own
 // BCs (ymom_src odd, E_src even across a reflecting y wall), which is the source of the ghost STATE with
 // the sign flipped there and identical to it for every other boundary type.
-template <class W, bool GRAV = false>
+// RIEMANN: 0 = HLLC (riemann_hllc), 1 = CGF (riemann_cgf + consFlux); selected by compressible.riemann.
+template <class W, bool GRAV = false, int RIEMANN = 0>
 struct SweepTask {
     W& w;
     const SweepArgs& A;
@@ -83,6 +85,14 @@ struct SweepTask {
     HD SweepTask(W& w_, const SweepArgs& a, SweepSmem& s, unsigned ph) : w(w_), A(a), S(s), phase_bits(ph) {}
 
     HD double& Q(int n, int r, int c) { return S.q[n][r & (SW_RING - 1)][c]; }
+
+    // the Riemann problem at a face; `wall`: the face lies on a solid lower boundary (CGF only)
+    HD Flux riemann(double rho_l, double E_l, double mn_l, double mt_l, double rho_r, double E_r, double mn_r,
+                    double mt_r, const HllcPar& hp, bool wall)
+    {
+        if (RIEMANN == 1) return cgf(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp, wall);
+        return hllc(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp);
+    }
 
     // wait for the bulk copy of row r, convert cons -> prim in place, publish to the warp
     HD void ready(int r, int col0, int jvalid_lo, int jvalid_hi, bool row_valid)
@@ -146,6 +156,9 @@ struct SweepTask {
         const double dxinv = 1.0 / A.dx, dyinv = 1.0 / A.dy;
         const int lim = A.limiter;
         const bool flat = A.use_flattening != 0;
+        // CGF zeroes the normal velocity on a solid -x / -y boundary face (x face index ng, y face index ng)
+        const bool xwall = RIEMANN == 1 && A.xl_solid != 0;
+        const bool ywall = RIEMANN == 1 && A.yl_solid != 0 && j == ng;
 
         // raw U of the lane's own column is re-read from global (L2 hit: the bulk copy just
         // streamed it) so that the update adds the flux divergence to the unmodified state
@@ -276,7 +289,7 @@ struct SweepTask {
             Cons Fy;
             {
                 // ---- F. transverse x-flux at face i-1/2; dF_x of cell (i-1) -------------------
-                Flux f = hllc(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp);
+                Flux f = riemann(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp, xwall && i == ng);
                 Cons FxT = {f.dens, f.ener, f.mn, f.mt};
                 // ---- G. transverse correction of the y-face states of cell (i-1)
                 //         (unsplit_fluxes.py:463-471: U_yl[i,j+1], U_yr[i,j] -= dt/2dx * dF_x)
@@ -294,7 +307,7 @@ struct SweepTask {
                 {
                     // ---- I. final y-flux of row i-1 at face j-1/2 (left state from lane-1) ----
                     double ld = w.up(YPp.dens), le = w.up(YPp.ener), lx = w.up(YPp.xmom), ly = w.up(YPp.ymom);
-                    Flux g = hllc(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp);
+                    Flux g = riemann(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp, ywall);
                     Fy.dens = g.dens; Fy.ener = g.ener; Fy.ymom = g.mn; Fy.xmom = g.mt;
                     // viscosity (unsplit_fluxes.py:545-547); zero on the global +y face
                     double avy = avisc_coeff(divU_prev, divU, A.dy, A.cvisc);
@@ -311,7 +324,7 @@ struct SweepTask {
             Cons XMp, XPp;
             {
                 double ld = w.up(YP.dens), le = w.up(YP.ener), lx = w.up(YP.xmom), ly = w.up(YP.ymom);
-                Flux g = hllc(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp);
+                Flux g = riemann(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp, ywall);
                 // g.mn is the y-momentum flux, g.mt the x-momentum flux
                 double dd = w.down(g.dens) - g.dens, de = w.down(g.ener) - g.ener;
                 double dmy = w.down(g.mn) - g.mn, dmx = w.down(g.mt) - g.mt;
@@ -324,8 +337,8 @@ struct SweepTask {
 
             {
                 // ---- L. final x-flux at face i-1/2 ------------------------------------------
-                Flux f = hllc(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
-                              XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp);
+                Flux f = riemann(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
+                                 XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp, xwall && i == ng);
                 Cons Fx = {f.dens, f.ener, f.mn, f.mt};
                 double avx = avisc_coeff(divU, divU_jp1, A.dx, A.cvisc);
                 if (A.no_avisc_xhi && i == ihi) avx = 0.0;

@@ -43,7 +43,7 @@ SOLVER = {
         "compressible.cvisc": (0.1, "artificial viscosity coefficient"),
         "compressible.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
         "compressible.grav": (0.0, "constant gravitational acceleration along y"),
-        "compressible.riemann": ("HLLC", "the device sweep implements HLLC"),
+        "compressible.riemann": ("HLLC", "HLLC or CGF"),
         "compressible.small_dens": (-1.e200, "density floor"),
         "compressible.small_eint": (-1.e200, "internal-energy floor"),
         "sponge.do_sponge": (0, "not supported"),

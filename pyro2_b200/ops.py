@@ -89,9 +89,10 @@ def cfl_wavemax(planes, nx, ny, ng, gamma, scratch):
 
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
-                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_flip_ylo=0, src_flip_yhi=0):
+                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_flip_ylo=0, src_flip_yhi=0, riemann="HLLC",
+                xl_solid=0, yl_solid=0):
     return _lib.CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi,
-                           grav, src_flip_ylo, src_flip_yhi)
+                           grav, src_flip_ylo, src_flip_yhi, {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid)
 
 
 def compressible_sweep(Uin, Uout, nx, ny, ng, dx, dy, dt, params, scratch):

@@ -77,18 +77,20 @@ struct LaneCtx {
     int lane;
     int ntasks;
     bool grav;
+    int riemann;
 };
 
 void* lane_main(void* p)
 {
     LaneCtx* c = (LaneCtx*)p;
     EmuWarp w{c->ws, c->lane};
-    if (c->grav) {
-        pyro::SweepTask<EmuWarp, true> T(w, *c->A, *c->smem, 0u);
-        for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+    auto go = [&](auto& T) { for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips); };
+    if (c->riemann == 1) {
+        if (c->grav) { pyro::SweepTask<EmuWarp, true, 1> T(w, *c->A, *c->smem, 0u); go(T); }
+        else { pyro::SweepTask<EmuWarp, false, 1> T(w, *c->A, *c->smem, 0u); go(T); }
     } else {
-        pyro::SweepTask<EmuWarp> T(w, *c->A, *c->smem, 0u);
-        for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips);
+        if (c->grav) { pyro::SweepTask<EmuWarp, true, 0> T(w, *c->A, *c->smem, 0u); go(T); }
+        else { pyro::SweepTask<EmuWarp, false, 0> T(w, *c->A, *c->smem, 0u); go(T); }
     }
     return nullptr;
 }
@@ -100,7 +102,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
                                       double gamma, double z0, double z1, double delta, double cvisc,
                                       int limiter, int use_flattening, int no_avisc_xhi, int no_avisc_yhi,
                                       int seglen, uint64_t* scratch, double* dbg, double grav, int src_flip_ylo,
-                                      int src_flip_yhi)
+                                      int src_flip_yhi, int riemann, int xl_solid, int yl_solid)
 {
     pyro::SweepArgs A;
     A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
@@ -109,6 +111,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     A.limiter = limiter; A.use_flattening = use_flattening;
     A.no_avisc_xhi = no_avisc_xhi; A.no_avisc_yhi = no_avisc_yhi;
     A.grav = grav; A.src_flip_ylo = src_flip_ylo; A.src_flip_yhi = src_flip_yhi;
+    A.xl_solid = xl_solid; A.yl_solid = yl_solid;
     A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
     A.seglen = seglen;
     A.nsegs = (nx + seglen - 1) / seglen;
@@ -130,7 +133,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     LaneCtx ctx[32];
     pthread_t th[32];
     for (int l = 0; l < 32; ++l) {
-        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0};
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0, riemann};
         pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
     }
     for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);

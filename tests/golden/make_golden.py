@@ -40,7 +40,7 @@ def comp_case(name, problem, params, nsteps):
             "compressible.z0", "compressible.z1", "compressible.delta", "driver.cfl", "driver.tmax",
             "driver.init_tstep_factor", "driver.max_dt_change",
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
-            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav"]
+            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav", "compressible.riemann"]
     np.savez_compressed(os.path.join(HERE, f"comp_{name}.npz"),
                         problem=problem, inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]),
@@ -186,6 +186,11 @@ if __name__ == "__main__":
     comp_case("acoustic64", "acoustic_pulse", {"mesh.nx": 64, "mesh.ny": 64, "driver.fix_dt": 3.0e-3}, 20)
     comp_case("advect32", "advect", {"mesh.nx": 32, "mesh.ny": 32, "driver.fix_dt": 0.01}, 20)   # limiter 0
     comp_case("gresho40", "gresho", {}, 15)
+    # the CGF Riemann solver (riemann_cgf + consFlux), with and without solid walls
+    comp_case("sedov32_cgf", "sedov", {"mesh.nx": 32, "mesh.ny": 32, "sedov.r_init": 0.1, "compressible.riemann": "CGF"}, 30)
+    comp_case("quad32_cgf_walls", "quad", {"mesh.nx": 32, "mesh.ny": 32, "compressible.riemann": "CGF",
+                                           "mesh.xlboundary": "reflect", "mesh.xrboundary": "reflect",
+                                           "mesh.ylboundary": "reflect", "mesh.yrboundary": "outflow"}, 30)
     # gravity + the compressible solver's "hse" boundary (compressible/BC.py)
     comp_case("bubble32", "bubble", {"mesh.nx": 32, "mesh.ny": 64, "mesh.ymax": 4.0}, 25)
     comp_case("rt16", "rt", {"mesh.nx": 16, "mesh.ny": 48}, 25)

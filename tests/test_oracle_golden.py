@@ -24,7 +24,8 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
     prm = oracle.comp_params(gamma=gamma, z0=rp["compressible.z0"], z1=rp["compressible.z1"],
                              delta=rp["compressible.delta"], cvisc=rp["compressible.cvisc"],
                              limiter=rp["compressible.limiter"], use_flattening=rp["compressible.use_flattening"],
-                             grav=grav, src_bcs=bcs)
+                             grav=grav, src_bcs=bcs, riemann=rp.get("compressible.riemann", "HLLC"),
+                             xl_solid=int(rp["mesh.xlboundary"] == "reflect"), yl_solid=int(rp["mesh.ylboundary"] == "reflect"))
     t, dt_old, dts = 0.0, None, []
     nsteps = len(z["dts"]) if nsteps is None else nsteps
     for n in range(nsteps):
@@ -49,7 +50,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
-                                  "bubble32", "rt16", "hse16", "rt16_reflect"])
+                                  "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))

@@ -28,7 +28,7 @@ def emu():
     lib = C.CDLL(so)
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
                                            [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
-                                           [C.c_double, C.c_int, C.c_int])
+                                           [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3)
     return lib
 
 
@@ -43,7 +43,7 @@ def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0)):
     lib.emu_compressible_sweep(Pin.ctypes.data, Pout.ctypes.data, qx - 2 * ng, qy - 2 * ng, ng, pitch, qx * pitch,
                                dx, dy, dt, prm.gamma, prm.z0, prm.z1, prm.delta, prm.cvisc, prm.limiter,
                                prm.use_flattening, prm.no_avisc_xhi, prm.no_avisc_yhi, seglen, scratch.ctypes.data, None,
-                               prm.grav, flips[0], flips[1])
+                               prm.grav, flips[0], flips[1], prm.riemann, prm.xl_solid, prm.yl_solid)
     return oracle.from_planes(np.ascontiguousarray(Pout[:, :, :qy])), scratch
 
 
@@ -109,3 +109,33 @@ def test_emulated_sweep_with_gravity_matches_oracle(emu, bc, nx, ny, seglen):
     # and gravity really did something
     ref0 = oracle.compressible_step(U, ng, dx, dy, dt, oracle.comp_params())
     assert rel_l2(ref[v_][..., 3], ref0[v_][..., 3]) > 1e-4
+
+
+@pytest.mark.parametrize("kind,bc,nx,ny,grav,seglen", [
+    ("shock", ("outflow",) * 4, 33, 37, 0.0, 11), ("sedov", ("outflow",) * 4, 32, 32, 0.0, 5),
+    ("shock", ("reflect", "reflect", "reflect", "outflow"), 24, 40, 0.0, 8),        # solid -x / -y walls
+    ("smooth", ("reflect", "outflow", "reflect", "reflect"), 16, 48, -1.2, 16)])    # walls + gravity
+def test_emulated_sweep_with_cgf_matches_oracle(emu, kind, bc, nx, ny, grav, seglen):
+    """the RIEMANN = 1 instantiations: riemann_cgf + consFlux at all four Riemann problems of a cell"""
+    from golden_util import var_bcs
+    ng = 4
+    U = make_state(nx, ny, ng, kind)
+    rp = dict(zip(("mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary"), bc))
+    bcs = var_bcs(rp)
+    for n in range(4):
+        pl = np.ascontiguousarray(U[:, :, n])
+        oracle.fill_ghost(pl, ng, bcs[n])
+        U[:, :, n] = pl
+    dx, dy = 1.0 / nx, 1.0 / ny
+    dt = 0.5 * oracle.cfl_dt(U, ng, dx, dy, 1.4, 0.8)
+    prm = oracle.comp_params(riemann="CGF", xl_solid=int(bc[0] == "reflect"), yl_solid=int(bc[2] == "reflect"),
+                             grav=grav, src_bcs=bcs)
+    flips = (int(bc[2] == "reflect"), int(bc[3] == "reflect"))
+    got, scratch = _emu_step(emu, U, ng, dx, dy, dt, prm, seglen, flips)
+    ref = oracle.compressible_step(U, ng, dx, dy, dt, prm)
+    v = (slice(ng, ng + nx), slice(ng, ng + ny))
+    assert not np.isnan(got[v]).any() and scratch[3] == 0
+    for n in range(4):
+        assert rel_l2(got[v][..., n], ref[v][..., n]) < 1e-13
+    hllc = oracle.compressible_step(U, ng, dx, dy, dt, oracle.comp_params(grav=grav, src_bcs=bcs))
+    assert rel_l2(ref[v][..., 0], hllc[v][..., 0]) > 1e-6        # and it is a different solver
