@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
-            "periodic": 3, "hse": 4, "none": 4}   # 4: leave that side alone (user BCs are filled separately)
+            "periodic": 3, "hse": 4, "ambient": 4, "none": 4}   # 4: leave that side alone (user BCs are filled separately)
 
 
 def build(force=False):
@@ -31,7 +31,10 @@ class CompParams(C.Structure):
                 ("delta", C.c_double), ("cvisc", C.c_double), ("limiter", C.c_int),
                 ("use_flattening", C.c_int), ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
                 ("grav", C.c_double), ("src_bc", C.c_int * 16),
-                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int)]
+                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int),
+                ("heat_rate", C.c_double), ("heat_profile", C.c_void_p),
+                ("do_sponge", C.c_int), ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double),
+                ("sponge_timescale", C.c_double)]
 
 
 class LmParams(C.Structure):
@@ -151,15 +154,22 @@ def cfl_dt(U_ijn, ng, dx, dy, gamma, cfl):
 
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
-                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None, riemann="HLLC", xl_solid=0, yl_solid=0):
+                no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None, riemann="HLLC", xl_solid=0, yl_solid=0,
+                heat_rate=0.0, heat_profile=None, sponge=None):
     """src_bcs: BC names (xlb, xrb, ylb, yrb) of the four source arrays in variable order dens, ener, xmom,
-    ymom (only needed with gravity); "hse" copies like outflow for them"""
+    ymom (only needed with sources); "hse" and "ambient" copy like outflow for them.  heat_profile: (qx, qy)
+    array P, S_ener = dens * heat_rate * P; sponge: (rho_begin, rho_full, timescale) or None"""
     codes = (C.c_int * 16)()
     if src_bcs is not None:
-        flat = [BC_CODES["outflow" if b == "hse" else b] for bc in src_bcs for b in bc]
+        flat = [BC_CODES["outflow" if b in ("hse", "ambient") else b] for bc in src_bcs for b in bc]
         codes = (C.c_int * 16)(*flat)
-    return CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes,
-                      {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid)
+    hp = None if heat_profile is None else np.ascontiguousarray(heat_profile, dtype=np.float64)
+    sp = sponge or (0.0, 0.0, 1.0)
+    prm = CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes,
+                     {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid, heat_rate,
+                     None if hp is None else hp.ctypes.data, int(sponge is not None), sp[0], sp[1], sp[2])
+    prm._keepalive = hp
+    return prm
 
 
 def fill_hse(P, ng, dy, grav, gamma, var, side):

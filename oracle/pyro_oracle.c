@@ -147,6 +147,14 @@ typedef struct {
     /* compressible.riemann: 0 HLLC, 1 CGF; xl_solid / yl_solid: the -x / -y boundary is a solid wall
        (boundary.bc_is_solid), which CGF uses to zero the normal velocity at that face */
     int riemann, xl_solid, yl_solid;
+    /* problem heating source S_ener = dens * heat_rate * heat_profile[i, j] (compressible/problems/heating.py,
+       plume.py, convection.py: source_terms); heat_profile = NULL: none.  Its ghost cells are irrelevant: the
+       reference evaluates the source on the ghost-filled state and then ghost-fills the source arrays */
+    double heat_rate;
+    const double *heat_profile;
+    /* sponge (simulation.py:164-184, 425-441): do_sponge, rho_begin, rho_full, timescale */
+    int do_sponge;
+    double sponge_rho_begin, sponge_rho_full, sponge_timescale;
 } orc_comp_params;
 
 /* optional per-stage dumps, each (4 or 1) planes of qx*qy doubles; NULL = skip */
@@ -669,11 +677,12 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     /* apply_source_terms (unsplit_fluxes.py:247-330) with get_external_sources (simulation.py:105-128):
        S_ymom = dens * grav, S_ener = ymom * grav over the whole (ghost-filled) array, the source arrays
        then get THEIR OWN ghost fill, and half a time step of them goes to the buf = 1 interface states */
-    if (P->grav != 0.0) {
+    if (P->grav != 0.0 || P->heat_profile) {
         double *src = zalloc(4 * np);
         for (size_t k = 0; k < np; k++) {
             src[IYMOM * np + k] = U[IDENS * np + k] * P->grav;
             src[IENER * np + k] = U[IYMOM * np + k] * P->grav;
+            if (P->heat_profile) src[IENER * np + k] += U[IDENS * np + k] * P->heat_rate * P->heat_profile[k];
         }
         for (int n = 0; n < 4; n++)
             orc_fill_ghost_f64(src + n * np, nx, ny, ng, P->src_bc[4 * n], P->src_bc[4 * n + 1], P->src_bc[4 * n + 2],
@@ -759,20 +768,43 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     /* external sources, predictor-corrector (simulation.py:398-423, get_external_sources :105-160):
        U += dt S(U_old); S_new uses the updated density and a time-centred y-momentum;
        U += dt/2 (S_new - S_old).  clean_state is a no-op for the default small_dens = -1e200 */
-    if (P->grav != 0.0) {
+    if (P->grav != 0.0 || P->heat_profile) {
         const double g = P->grav;
 #pragma omp parallel for
         for (int i = ng; i < ng + nx; i++)
             for (int j = ng; j < ng + ny; j++) {
                 const size_t k = IDX(i, j);
-                const double so_y = Uold_dens[k] * g, so_e = Uold_ymom[k] * g;
+                const double hp = P->heat_profile ? P->heat_profile[k] : 0.0;
+                const double so_y = Uold_dens[k] * g;
+                double so_e = Uold_ymom[k] * g;
+                if (P->heat_profile) so_e += Uold_dens[k] * P->heat_rate * hp;
                 U[IYMOM * np + k] += dt * so_y;
                 U[IENER * np + k] += dt * so_e;
                 const double sn_y = U[IDENS * np + k] * g;
                 const double ymom_new = U[IYMOM * np + k] + 0.5 * dt * (sn_y - so_y);
-                const double sn_e = ymom_new * g;
+                double sn_e = ymom_new * g;
+                if (P->heat_profile) sn_e += U[IDENS * np + k] * P->heat_rate * hp;
                 U[IYMOM * np + k] += 0.5 * dt * (sn_y - so_y);
                 U[IENER * np + k] += 0.5 * dt * (sn_e - so_e);
+            }
+    }
+    /* sponge: implicit damping of the momenta where the density is low, kinetic-energy change booked into the
+       energy (simulation.py:425-441; the reference applies it to the whole array, ghost cells included, which the
+       next fill overwrites) */
+    if (P->do_sponge) {
+        const double rb = P->sponge_rho_begin, rf = P->sponge_rho_full;
+#pragma omp parallel for
+        for (int i = ng; i < ng + nx; i++)
+            for (int j = ng; j < ng + ny; j++) {
+                const size_t k = IDX(i, j);
+                const double rho = U[IDENS * np + k];
+                const double f = rho > rb ? 0.0 : (rho < rf ? 1.0 : 0.5 * (1.0 - cos(3.14159265358979323846 * (rho - rb) / (rf - rb))));
+                const double kappa = f / P->sponge_timescale;
+                const double xo = U[IXMOM * np + k], yo = U[IYMOM * np + k];
+                const double xn = xo / (1.0 + dt * kappa), yn = yo / (1.0 + dt * kappa);
+                U[IXMOM * np + k] = xn;
+                U[IYMOM * np + k] = yn;
+                U[IENER * np + k] += 0.5 * ((xn * xn + yn * yn) - (xo * xo + yo * yo)) / rho;
             }
     }
     free(Uold_dens); free(Uold_ymom);

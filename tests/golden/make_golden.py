@@ -40,8 +40,25 @@ def comp_case(name, problem, params, nsteps):
             "compressible.z0", "compressible.z1", "compressible.delta", "driver.cfl", "driver.tmax",
             "driver.init_tstep_factor", "driver.max_dt_change",
             "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary",
-            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav", "compressible.riemann"]
-    np.savez_compressed(os.path.join(HERE, f"comp_{name}.npz"),
+            "mesh.nx", "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav", "compressible.riemann",
+            "compressible.small_dens", "sponge.do_sponge", "sponge.sponge_rho_begin", "sponge.sponge_rho_full",
+            "sponge.sponge_timescale"]
+    extra = {}
+    import importlib
+    mod = importlib.import_module(f"pyro.compressible.problems.{problem}")
+    if hasattr(mod, "source_terms"):
+        # the heating profile P with S_ener = dens * e_rate * P, evaluated exactly as the reference does:
+        # its own source_terms() on a state of unit density with e_rate temporarily set to 1
+        e_rate = rp.get_param(f"{problem}.e_rate")
+        rp.set_param(f"{problem}.e_rate", 1.0)
+        ones = g.scratch_array(nvar=4)
+        ones[:, :, 0] = 1.0
+        extra["heat_profile"] = np.asarray(mod.source_terms(g, ones, sim.ivars, rp))[:, :, sim.ivars.iener].copy()
+        extra["heat_rate"] = e_rate
+        rp.set_param(f"{problem}.e_rate", e_rate)
+    if sim.cc_data.get_aux("ambient_rho") is not None:
+        extra["ambient"] = np.array([sim.cc_data.get_aux(k) for k in ("ambient_rho", "ambient_u", "ambient_v", "ambient_p")])
+    np.savez_compressed(os.path.join(HERE, f"comp_{name}.npz"), **extra,
                         problem=problem, inputs=np.array([f"{k}={v}" for k, v in params.items()]),
                         rp=np.array([f"{k}={rp.get_param(k)}" for k in keys]),
                         ng=g.ng, U0=U0, U=np.asarray(sim.cc_data.data).copy(), dts=np.array(dts),
@@ -191,6 +208,10 @@ if __name__ == "__main__":
     comp_case("quad32_cgf_walls", "quad", {"mesh.nx": 32, "mesh.ny": 32, "compressible.riemann": "CGF",
                                            "mesh.xlboundary": "reflect", "mesh.xrboundary": "reflect",
                                            "mesh.ylboundary": "reflect", "mesh.yrboundary": "outflow"}, 30)
+    # problem heating sources, the sponge, the "ambient" boundary, the density floor
+    comp_case("heating32", "heating", {"mesh.nx": 32, "mesh.ny": 32}, 25)
+    comp_case("plume32", "plume", {"mesh.nx": 32, "mesh.ny": 64, "mesh.ymax": 4.0}, 25)
+    comp_case("convection16", "convection", {"mesh.nx": 16, "mesh.ny": 96}, 25)
     # gravity + the compressible solver's "hse" boundary (compressible/BC.py)
     comp_case("bubble32", "bubble", {"mesh.nx": 32, "mesh.ny": 64, "mesh.ymax": 4.0}, 25)
     comp_case("rt16", "rt", {"mesh.nx": 16, "mesh.ny": 48}, 25)

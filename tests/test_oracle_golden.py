@@ -25,7 +25,16 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
                              delta=rp["compressible.delta"], cvisc=rp["compressible.cvisc"],
                              limiter=rp["compressible.limiter"], use_flattening=rp["compressible.use_flattening"],
                              grav=grav, src_bcs=bcs, riemann=rp.get("compressible.riemann", "HLLC"),
-                             xl_solid=int(rp["mesh.xlboundary"] == "reflect"), yl_solid=int(rp["mesh.ylboundary"] == "reflect"))
+                             xl_solid=int(rp["mesh.xlboundary"] == "reflect"), yl_solid=int(rp["mesh.ylboundary"] == "reflect"),
+                             heat_rate=float(z["heat_rate"]) if "heat_rate" in z else 0.0,
+                             heat_profile=z["heat_profile"] if "heat_profile" in z else None,
+                             sponge=(rp["sponge.sponge_rho_begin"], rp["sponge.sponge_rho_full"], rp["sponge.sponge_timescale"])
+                             if rp.get("sponge.do_sponge", 0) else None)
+    ambient = None
+    if "ambient" in z:        # compressible/BC.py:142-168: constant state above the top boundary
+        ar, au, av, ap = (float(x) for x in z["ambient"])
+        ambient = [ar, ap / (gamma - 1.0) + 0.5 * ar * (au ** 2 + av ** 2), ar * au, ar * av]
+    small_dens = rp.get("compressible.small_dens", -1.e200)
     t, dt_old, dts = 0.0, None, []
     nsteps = len(z["dts"]) if nsteps is None else nsteps
     for n in range(nsteps):
@@ -34,6 +43,8 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
             for side in ("ylb", "yrb"):
                 if bcs[k][2 + (side == "yrb")] == "hse":
                     oracle.fill_hse(P, ng, dy, grav, gamma, k, side)
+                if bcs[k][2 + (side == "yrb")] == "ambient":
+                    P[k][:, ng + ny:] = ambient[k]
         dt = oracle.cfl_dt(oracle.from_planes(P), ng, dx, dy, gamma, rp["driver.cfl"])
         # NullSimulation.compute_timestep (simulation_null.py:222-244)
         dt = rp["driver.init_tstep_factor"] * dt if n == 0 else min(rp["driver.max_dt_change"] * dt_old, dt)
@@ -42,6 +53,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
             dt = fix_dt
         if t + dt > rp["driver.tmax"]:
             dt = rp["driver.tmax"] - t
+        P[0][ng:-ng, ng:-ng] = np.maximum(P[0][ng:-ng, ng:-ng], small_dens)     # clean_state (simulation.py:296, 452-456)
         oracle.compressible_step(P, ng, dx, dy, dt, prm, planes=True)
         t += dt
         dts.append(dt)
@@ -50,7 +62,8 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
-                                  "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls"])
+                                  "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
+                                  "heating32", "plume32", "convection16"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
