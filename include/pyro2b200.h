@@ -63,6 +63,11 @@ typedef struct {
     int riemann;             /* compressible.riemann: 0 HLLC (riemann.py:682-860), 1 CGF (riemann.py:9-310 + consFlux) */
     int xl_solid, yl_solid;  /* CGF: the -x / -y boundary is a solid wall (boundary.bc_is_solid): zero normal
                               * velocity in the interface state on that face (riemann.py:283-292) */
+    double heat_rate;        /* problem heating source S_ener = dens * heat_rate * heat_profile[i, j]           */
+    const double* heat_profile; /* (source_terms of compressible/problems/heating.py, plume.py, convection.py): one
+                              * device plane with the state's pitch, ghost cells filled like a scalar; NULL = none */
+    int do_sponge;           /* sponge damping (simulation.py:164-184, 425-441): on/off, the density below which it   */
+    double sponge_rho_begin, sponge_rho_full, sponge_timescale; /* starts / is fully on, and its time scale          */
 } p2b_comp_params;
 
 /* device scratch the sweep needs, 8 x 64-bit words owned by the caller:
@@ -96,6 +101,9 @@ int p2b_fill_ghost_values_f64(double* plane, const p2b_grid* g, const int bc[4],
  * per variable after the standard fill, like the reference's ext_bcs hook (pyro/mesh/patch.py:582-624);
  * bit-identical to the reference. */
 int p2b_fill_hse_f64(double* U, const p2b_grid* g, double grav, double gamma, int var, int side, void* stream);
+/* the "ambient" boundary (pyro/compressible/BC.py:142-168): the ghost rows of variable `var` beyond side 0 (ylb) /
+ * 1 (yrb) are set to `value` (the ambient density, momenta or total energy) */
+int p2b_fill_ambient_f64(double* U, const p2b_grid* g, int var, int side, double value, void* stream);
 
 /* ---- CFL wave speeds: Simulation.method_compute_timestep (pyro/compressible/simulation.py:267-288)
  * over the FULL array including ghosts.  Accumulates (atomic max) the bit patterns of
@@ -110,8 +118,8 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
  * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, Cartesian geometry,
- * Riemann solver HLLC or CGF (prm->riemann); prm->grav != 0 selects the instantiations with the gravity
- * source terms. */
+ * Riemann solver HLLC or CGF (prm->riemann); gravity, a heating profile or the sponge select the
+ * instantiations with source terms. */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
 

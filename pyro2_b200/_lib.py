@@ -51,7 +51,9 @@ class CompParams(C.Structure):
                 ("cvisc", C.c_double), ("limiter", C.c_int), ("use_flattening", C.c_int),
                 ("no_avisc_xhi", C.c_int), ("no_avisc_yhi", C.c_int),
                 ("grav", C.c_double), ("src_flip_ylo", C.c_int), ("src_flip_yhi", C.c_int),
-                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int)]
+                ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int),
+                ("heat_rate", C.c_double), ("heat_profile", C.c_void_p), ("do_sponge", C.c_int),
+                ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double), ("sponge_timescale", C.c_double)]
 
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
@@ -70,6 +72,7 @@ SIGNATURES = {
     "p2b_fill_ghost_i64": (_i, [_vp, _PG, _i, C.POINTER(_i), _vp]),
     "p2b_fill_ghost_values_f64": (_i, [_vp, _PG, C.POINTER(_i), _vp, _vp, _vp, _vp, _vp]),
     "p2b_fill_hse_f64": (_i, [_vp, _PG, _d, _d, _i, _i, _vp]),
+    "p2b_fill_ambient_f64": (_i, [_vp, _PG, _i, _i, _d, _vp]),
     "p2b_cfl_wavemax": (_i, [_vp, _PG, _d, _vp, _vp]),
     "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

@@ -10,8 +10,8 @@ What maps to what
   cons_to_prim / prim_to_cons         simulation.py:49-102   (torch, for users / tests / output)
   Variables                           simulation.py:12-46
 
-Scope: Cartesian grid, HLLC or CGF, constant gravity and the hse boundary; no sponge /
-particles / problem sources / ambient and ramp boundaries.
+Scope: Cartesian grid, HLLC or CGF, constant gravity, heating
+sources dens * e_rate * profile, the sponge, the hse and ambient boundaries; no particles / ramp boundary.
 Anything else raises instead of silently taking another path.
 """
 import torch
@@ -87,18 +87,20 @@ class Simulation(NullSimulation):
             msg.fail(f"ERROR: the device sweep implements the HLLC and CGF Riemann solvers (got {riemann_method})")
         # solver-specific boundary types (simulation.py:212-214); ambient and ramp are not built
         bnd.define_bc("hse", BC.user, is_solid=False)
-        try:
-            if rp.get_param("sponge.do_sponge"):
-                msg.fail("ERROR: the sponge term is not implemented in the device sweep")
-        except KeyError:
-            pass
+        bnd.define_bc("ambient", BC.user, is_solid=False)
         try:
             if rp.get_param("particles.do_particles") == 1:
                 msg.fail("ERROR: particles are not supported")
         except KeyError:
             pass
+        # problem source terms: the reference's heating / plume / convection problems all heat at the rate
+        # dens * e_rate * profile(x, y); a problem describes that with heating(grid, rp) -> (e_rate, profile)
+        self._heating = None
         if self.problem_source is not None:
-            msg.fail("ERROR: problem source terms are not supported by the device sweep")
+            import sys
+            self._heating = getattr(sys.modules.get(self.problem_func.__module__), "heating", None)
+            if self._heating is None:
+                msg.fail("ERROR: problem source terms need a heating(grid, rp) description for the device sweep")
 
         bc, bc_xodd, bc_yodd = bc_setup(rp)
         self.solid = bnd.bc_is_solid(bc)
@@ -134,6 +136,18 @@ class Simulation(NullSimulation):
         self._pending_status = False
 
         self.problem_func(self.cc_data, self.rp)
+        self._heat_rate, self._heat_plane = 0.0, None
+        if self._heating is not None:
+            import numpy as np
+            rate, prof = self._heating(my_grid, rp)
+            plane = ops.alloc_planes(1, my_grid.qx, my_grid.qy, device=my_data.planes.device)
+            assert plane.stride(1) == my_data.planes.stride(1)
+            plane[0, :, :my_grid.qy].copy_(torch.from_numpy(np.ascontiguousarray(prof, dtype=np.float64)))
+            # the reference ghost-fills its energy-source array with the scalar BCs (user types copy like outflow):
+            # filling the profile the same way gives the kernel the source of the cell each ghost cell mirrors
+            names = tuple("outflow" if t in bnd.ext_bcs else t for t in bc.names())
+            ops.fill_ghost(plane, my_grid.nx, my_grid.ny, my_grid.ng, [names])
+            self._heat_rate, self._heat_plane = float(rate), plane
         if self.verbose > 0:
             print(my_data)
 
@@ -148,6 +162,9 @@ class Simulation(NullSimulation):
                                no_avisc_xhi=getattr(self, "_no_avisc_xhi", 1), no_avisc_yhi=1,
                                grav=rp.get_param("compressible.grav"),
                                src_flip_ylo=self._src_flip[0], src_flip_yhi=self._src_flip[1],
+                               heat_rate=self._heat_rate, heat_profile=self._heat_plane,
+                               sponge=(rp.get_param("sponge.sponge_rho_begin"), rp.get_param("sponge.sponge_rho_full"),
+                                       rp.get_param("sponge.sponge_timescale")) if rp.get_param("sponge.do_sponge") else None,
                                riemann=rp.get_param("compressible.riemann"),
                                xl_solid=int(self.solid.xl) if (self.decomposition is None or self.decomposition.is_first) else 0,
                                yl_solid=int(self.solid.yl))

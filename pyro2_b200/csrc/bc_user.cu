@@ -20,4 +20,17 @@ int p2b_fill_hse_f64(double* U, const p2b_grid* g, double grav, double gamma, in
     return P2B_OK;
 }
 
+// the "ambient" boundary of pyro/compressible/BC.py:142-168: ghost rows of variable `var` on side 0 (ylb) / 1 (yrb)
+// <- value (ambient_rho, ambient_rho * u, ambient_rho * v or p / (gamma - 1) + kinetic energy; the reference only
+// supports yrb)
+int p2b_fill_ambient_f64(double* U, const p2b_grid* g, int var, int side, double value, void* stream)
+{
+    P2B_REQUIRE(U && g, "null pointer");
+    P2B_REQUIRE(var >= 0 && var <= 3 && (side == 0 || side == 1), "bad variable / side");
+    const int qx = g->nx + 2 * g->ng;
+    P2B_LAUNCH(ambient_fill_kernel, (qx + 127) / 128, 128, 0, (cudaStream_t)stream)(U, *g, var, side, value);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
 }  // extern "C"

@@ -1,5 +1,5 @@
 // bc_user_kernels.cuh -- the compressible solver's user-defined boundary conditions as device code.
-// Reference: pyro/compressible/BC.py:21-139, the "hse" boundary ("ambient" and "ramp" are not built).
+// Reference: pyro/compressible/BC.py:21-168, the "hse" and "ambient" boundaries ("ramp" is not built).
 // Included by bc_user.cu (nvcc) and tests/emu/bc_emu.cpp (g++ through tests/emu/cuda_emu.h).
 #pragma once
 #include "../../include/pyro2b200.h"
@@ -37,6 +37,18 @@ __global__ void hse_fill_kernel(double* __restrict__ U, p2b_grid g, double grav,
         pres = side == 0 ? exact_sub(pres, dp) : exact_add(pres, dp);
         v[kb + step * k] = exact_add(exact_div(pres, exact_sub(gamma, 1.0)), ke);
     }
+}
+
+// "ambient" (BC.py:142-168): the ghost rows of one variable beyond the +y (side 1) or -y (side 0) boundary are set
+// to a constant -- the ambient density, momenta or total energy the problem registered; all x indices.
+__global__ void ambient_fill_kernel(double* __restrict__ U, p2b_grid g, int var, int side, double value)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.nx + 2 * g.ng) return;
+    const int jb = side == 0 ? g.ng : g.ng + g.ny - 1;
+    const int step = side == 0 ? -1 : 1;
+    double* v = U + (long long)var * g.plane_stride + (long long)i * g.pitch + jb;
+    for (int k = 1; k <= g.ng; ++k) v[step * k] = value;
 }
 
 }  // namespace pyro

@@ -176,6 +176,9 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     A.no_avisc_xhi = prm->no_avisc_xhi; A.no_avisc_yhi = prm->no_avisc_yhi;
     A.grav = prm->grav; A.src_flip_ylo = prm->src_flip_ylo; A.src_flip_yhi = prm->src_flip_yhi;
     A.xl_solid = prm->xl_solid; A.yl_solid = prm->yl_solid;
+    A.heat = prm->heat_profile; A.heat_rate = prm->heat_rate;
+    A.do_sponge = prm->do_sponge; A.sponge_rho_begin = prm->sponge_rho_begin;
+    A.sponge_rho_full = prm->sponge_rho_full; A.sponge_timescale = prm->sponge_timescale;
     A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
     A.seglen = choose_seglen(g->nx, A.nstrips, resident);
@@ -191,7 +194,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     if (blocks > maxblocks) blocks = maxblocks;
     const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
     unsigned long long* counter = (unsigned long long*)(scratch + 2);
-    const bool grav = prm->grav != 0.0;
+    const bool grav = prm->grav != 0.0 || prm->heat_profile != nullptr || prm->do_sponge != 0;   // any source term
     if (prm->riemann == 1) {
         if (grav) sweep_kernel<true, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
         else sweep_kernel<false, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);

@@ -59,6 +59,11 @@ struct SweepArgs {
     double grav;                      // compressible.grav, acceleration along y
     int src_flip_ylo, src_flip_yhi;   // 1: that y boundary reflects -> the ghost-cell SOURCES change sign
     int xl_solid, yl_solid;           // CGF: the -x / -y boundary is a solid wall (boundary.bc_is_solid)
+    // more sources of the GRAV ("with sources") instantiations
+    const double* heat;               // heating profile P (one plane, same pitch, ghost-filled like a scalar) or NULL:
+    double heat_rate;                 //   S_ener += dens * heat_rate * P  (problems heating / plume / convection)
+    int do_sponge;                    // sponge (simulation.py:164-184, 425-441)
+    double sponge_rho_begin, sponge_rho_full, sponge_timescale;
 };
 
 struct alignas(16) SweepSmem {
@@ -271,6 +276,8 @@ struct SweepTask {
                 const bool flip = (j < ng && A.src_flip_ylo) || (j >= jhi && A.src_flip_yhi);
                 double sy = Uc.dens * A.grav, se = Uc.ymom * A.grav;
                 if (flip) { sy = -sy; se = -se; }
+                // problem heating: the profile plane is ghost-filled like the (even) source array it feeds
+                if (A.heat) se += Uc.dens * A.heat_rate * A.heat[(long long)i * A.pitch + jj];
                 const double hy = 0.5 * A.dt * sy, he = 0.5 * A.dt * se;
                 XM.ymom += hy; XP.ymom += hy; YM.ymom += hy; YP.ymom += hy;
                 XM.ener += he; XP.ener += he; YM.ener += he; YP.ener += he;
@@ -358,14 +365,26 @@ struct SweepTask {
                     if (GRAV) {
                         // U += dt S(U_old); S_new from the new density and a time-centred y-momentum;
                         // U += dt/2 (S_new - S_old)
-                        const double so_y = U_prev.dens * A.grav, so_e = U_prev.ymom * A.grav;
+                        const double hp = A.heat ? A.heat_rate * A.heat[(long long)(i - 1) * A.pitch + jj] : 0.0;
+                        const double so_y = U_prev.dens * A.grav, so_e = U_prev.ymom * A.grav + U_prev.dens * hp;
                         Un.ymom += A.dt * so_y;
                         Un.ener += A.dt * so_e;
                         const double sn_y = Un.dens * A.grav;
                         const double corr = 0.5 * A.dt * (sn_y - so_y);
-                        const double sn_e = (Un.ymom + corr) * A.grav;
+                        const double sn_e = (Un.ymom + corr) * A.grav + Un.dens * hp;
                         Un.ymom += corr;
                         Un.ener += 0.5 * A.dt * (sn_e - so_e);
+                        if (A.do_sponge) {
+                            // implicit damping of the momenta in the low-density region, kinetic-energy change
+                            // booked into the energy (simulation.py:425-441)
+                            const double rb = A.sponge_rho_begin, rf = A.sponge_rho_full;
+                            const double f = Un.dens > rb ? 0.0 : (Un.dens < rf ? 1.0
+                                             : 0.5 * (1.0 - cos(3.14159265358979323846 * (Un.dens - rb) / (rf - rb))));
+                            const double damp = 1.0 / (1.0 + A.dt * (f / A.sponge_timescale));
+                            const double xo = Un.xmom, yo = Un.ymom;
+                            Un.xmom = xo * damp; Un.ymom = yo * damp;
+                            Un.ener += 0.5 * ((Un.xmom * Un.xmom + Un.ymom * Un.ymom) - (xo * xo + yo * yo)) / Un.dens;
+                        }
                     }
                     if (out_lane && i > i0) {
                         double* o = Ocol + (long long)(i - 1) * A.pitch;

@@ -46,7 +46,10 @@ SOLVER = {
         "compressible.riemann": ("HLLC", "HLLC or CGF"),
         "compressible.small_dens": (-1.e200, "density floor"),
         "compressible.small_eint": (-1.e200, "internal-energy floor"),
-        "sponge.do_sponge": (0, "not supported"),
+        "sponge.do_sponge": (0, "damp the velocities in the low-density region above the atmosphere"),
+        "sponge.sponge_rho_begin": (1.e-2, "density below which the sponge begins"),
+        "sponge.sponge_rho_full": (1.e-3, "density below which the sponge is fully on"),
+        "sponge.sponge_timescale": (1.e-2, "time scale of the damping"),
         "particles.do_particles": (0, ""),
     },
     "advection": {

@@ -102,7 +102,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
                                       double gamma, double z0, double z1, double delta, double cvisc,
                                       int limiter, int use_flattening, int no_avisc_xhi, int no_avisc_yhi,
                                       int seglen, uint64_t* scratch, double* dbg, double grav, int src_flip_ylo,
-                                      int src_flip_yhi, int riemann, int xl_solid, int yl_solid)
+                                      int src_flip_yhi, int riemann, int xl_solid, int yl_solid, const double* heat,
+                                      double heat_rate, int do_sponge, double sp_begin, double sp_full, double sp_tau)
 {
     pyro::SweepArgs A;
     A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
@@ -112,6 +113,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     A.no_avisc_xhi = no_avisc_xhi; A.no_avisc_yhi = no_avisc_yhi;
     A.grav = grav; A.src_flip_ylo = src_flip_ylo; A.src_flip_yhi = src_flip_yhi;
     A.xl_solid = xl_solid; A.yl_solid = yl_solid;
+    A.heat = heat; A.heat_rate = heat_rate; A.do_sponge = do_sponge;
+    A.sponge_rho_begin = sp_begin; A.sponge_rho_full = sp_full; A.sponge_timescale = sp_tau;
     A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
     A.seglen = seglen;
     A.nsegs = (nx + seglen - 1) / seglen;
@@ -133,7 +136,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     LaneCtx ctx[32];
     pthread_t th[32];
     for (int l = 0; l < 32; ++l) {
-        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0, riemann};
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0 || heat != nullptr || do_sponge != 0, riemann};
         pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
     }
     for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);

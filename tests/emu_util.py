@@ -43,7 +43,7 @@ def load_mg_emu():
 
 def load_bc_emu():
     """pyro2_b200/csrc/bc_user.cu compiled for the host: p2b_fill_hse_f64 over numpy memory"""
-    return _load("bc", ["bc_user.cu", "bc_user_kernels.cuh"], "p2b_fill_hse")
+    return _load("bc", ["bc_user.cu", "bc_user_kernels.cuh"], ("p2b_fill_hse", "p2b_fill_ambient"))
 
 
 def load_lm_emu():

@@ -190,6 +190,8 @@ def test_compute_timestep_limits():
     ("compressible", "comp_acoustic64.npz", None), ("compressible", "comp_advect32.npz", None),
     ("compressible", "comp_gresho40.npz", None), ("compressible", "comp_bubble32.npz", None),
     ("compressible", "comp_rt16.npz", None), ("compressible", "comp_hse16.npz", None),
+    ("compressible", "comp_heating32.npz", None), ("compressible", "comp_plume32.npz", None),
+    ("compressible", "comp_convection16.npz", None),
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_converge32.npz", ["x-velocity", "y-velocity"]),
     ("burgers", "burgers_test.npz", ["x-velocity", "y-velocity"]),
@@ -230,6 +232,7 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         from pyro2_b200.compressible import BC
         from pyro2_b200.mesh import boundary as bnd
         bnd.define_bc("hse", BC.user, is_solid=False)       # what Simulation.initialize registers
+        bnd.define_bc("ambient", BC.user, is_solid=False)
     bc = bc_setup(rp)[0]
     vars_ = {"compressible": ["density", "energy", "x-momentum", "y-momentum"], "advection": ["density"], "diffusion": ["phi"]}.get(
         solver, ["x-velocity", "y-velocity"])
@@ -242,6 +245,11 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         for k, n in enumerate(vars_):
             # (ghost cells included: the first hse fill reads them; rt / hse leave 0/0 there, like the reference)
             assert np.array_equal(d.get_var(n).numpy(), ref[:, :, k], equal_nan=True), n
+        if "heat_profile" in z:        # the heating description the device sweep uses vs the reference's source_terms
+            rate, prof = problem.heating(g, rp)
+            assert rate == float(z["heat_rate"]) and np.array_equal(prof, z["heat_profile"])
+        if "ambient" in z:
+            assert [d.get_aux(k) for k in ("ambient_rho", "ambient_u", "ambient_v", "ambient_p")] == list(z["ambient"])
     elif solver in ("burgers", "advection", "diffusion"):
         for k, n in enumerate(names):
             assert np.array_equal(d.get_var(n).numpy(), z["P0"][k]), n

@@ -141,3 +141,18 @@ def test_emulated_advection_matches_oracle(flow, u, v, limiter, nx, ny):
         ref = oracle.advection_evolve(ref, ng, dx, dy, dt, u, v, limiter)
         assert np.array_equal(a, ref)
     f.close()
+
+
+def test_emulated_ambient_boundary():
+    import ctypes as C
+    from emu_util import load_bc_emu
+    from pyro2_b200 import _lib
+    lib = load_bc_emu()
+    nx, ny, ng = 12, 20, 4
+    rng = np.random.default_rng(0)
+    P = rng.random((4, nx + 2 * ng, ny + 2 * ng))
+    Q = P.copy()
+    g = _lib.Grid(nx, ny, ng, ny + 2 * ng, (nx + 2 * ng) * (ny + 2 * ng), 1.0, 1.0)
+    assert lib.p2b_fill_ambient_f64(P.ctypes.data, C.byref(g), 2, 1, 0.375, None) == 0
+    Q[2][:, ng + ny:] = 0.375
+    assert np.array_equal(P, Q)

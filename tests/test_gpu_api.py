@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
-                                  "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls"])
+                                  "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
+                                  "heating32", "plume32", "convection16"])
 def test_pyro_compressible_run_matches_reference(name):
     from pyro2_b200.pyro_sim import Pyro
     z, rp, inputs = load_comp(name)
@@ -91,7 +92,7 @@ def test_compressible_unit_assertions():
 
 def test_unsupported_configurations_fail_loudly():
     from pyro2_b200.pyro_sim import Pyro
-    for key, val in (("compressible.riemann", "HLLC_lm"), ("sponge.do_sponge", 1), ("mesh.ylboundary", "ambient")):
+    for key, val in (("compressible.riemann", "HLLC_lm"), ("particles.do_particles", 1), ("mesh.ylboundary", "ramp")):
         p = Pyro("compressible")
         with pytest.raises(SystemExit):
             p.initialize_problem("sedov", inputs_dict={key: val})

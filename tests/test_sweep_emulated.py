@@ -28,22 +28,30 @@ def emu():
     lib = C.CDLL(so)
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
                                            [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
-                                           [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3)
+                                           [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
+                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double])
     return lib
 
 
-def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0)):
+def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0), heat=None):
+    """heat: the heating profile with its ghost cells filled like a scalar (what the product passes)"""
     P = oracle.to_planes(U)
     _, qx, qy = P.shape
     pitch = (qy + 15) // 16 * 16
     Pin = np.zeros((4, qx, pitch))
     Pin[:, :, :qy] = P
     Pout = Pin.copy()
+    heat_p = None
+    if heat is not None:
+        heat_p = np.zeros((qx, pitch))
+        heat_p[:, :qy] = heat
     scratch = np.zeros(8, dtype=np.uint64)
     lib.emu_compressible_sweep(Pin.ctypes.data, Pout.ctypes.data, qx - 2 * ng, qy - 2 * ng, ng, pitch, qx * pitch,
                                dx, dy, dt, prm.gamma, prm.z0, prm.z1, prm.delta, prm.cvisc, prm.limiter,
                                prm.use_flattening, prm.no_avisc_xhi, prm.no_avisc_yhi, seglen, scratch.ctypes.data, None,
-                               prm.grav, flips[0], flips[1], prm.riemann, prm.xl_solid, prm.yl_solid)
+                               prm.grav, flips[0], flips[1], prm.riemann, prm.xl_solid, prm.yl_solid,
+                               None if heat is None else heat_p.ctypes.data, prm.heat_rate, prm.do_sponge,
+                               prm.sponge_rho_begin, prm.sponge_rho_full, prm.sponge_timescale)
     return oracle.from_planes(np.ascontiguousarray(Pout[:, :, :qy])), scratch
 
 
@@ -139,3 +147,44 @@ def test_emulated_sweep_with_cgf_matches_oracle(emu, kind, bc, nx, ny, grav, seg
         assert rel_l2(got[v][..., n], ref[v][..., n]) < 1e-13
     hllc = oracle.compressible_step(U, ng, dx, dy, dt, oracle.comp_params(grav=grav, src_bcs=bcs))
     assert rel_l2(ref[v][..., 0], hllc[v][..., 0]) > 1e-6        # and it is a different solver
+
+
+@pytest.mark.parametrize("bc,nx,ny,grav,sponge,seglen", [
+    (("outflow",) * 4, 24, 24, 0.0, None, 8),                                   # the heating problem: no gravity
+    (("outflow", "outflow", "hse", "hse"), 20, 40, -2.0, None, 11),             # plume
+    (("periodic", "periodic", "reflect", "outflow"), 16, 48, -2.0, (0.6, 0.2, 1.e-2), 16)])   # convection-like
+def test_emulated_sweep_with_heating_and_sponge_matches_oracle(emu, bc, nx, ny, grav, sponge, seglen):
+    from golden_util import var_bcs
+    ng, gamma = 4, 1.4
+    dx, dy = 1.0 / nx, 2.0 / ny
+    rng = np.random.default_rng(ny)
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    y = (np.arange(qy) + 0.5 - ng) * dy
+    x = (np.arange(qx) + 0.5 - ng) * dx
+    dens = np.broadcast_to(1.5 * np.exp(-y / 0.9)[None, :], (qx, qy)) * (1.0 + 0.05 * rng.standard_normal((qx, qy)))
+    pres = 1.8 * dens * (1.0 + 0.02 * rng.standard_normal((qx, qy)))
+    u, v = 0.1 * rng.standard_normal((qx, qy)), 0.1 * rng.standard_normal((qx, qy))
+    P = np.stack([dens, pres / (gamma - 1.0) + 0.5 * dens * (u * u + v * v), dens * u, dens * v])
+    prof = np.exp(-(np.sqrt((x[:, None] - 0.5) ** 2 + (y[None, :] - 0.7) ** 2) / 0.3) ** 2)
+    rp = dict(zip(("mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary"), bc))
+    bcs = var_bcs(rp)
+    for k in range(4):
+        oracle.fill_ghost(P[k], ng, bcs[k])
+        for side in ("ylb", "yrb"):
+            if bcs[k][2 + (side == "yrb")] == "hse":
+                oracle.fill_hse(P, ng, dy, grav, gamma, k, side)
+    U = oracle.from_planes(P)
+    dt = 0.5 * oracle.cfl_dt(U, ng, dx, dy, gamma, 0.8)
+    prm = oracle.comp_params(grav=grav, src_bcs=bcs, heat_rate=0.7, heat_profile=prof, sponge=sponge)
+    # what the product hands the kernel: the profile ghost-filled like the (even) energy-source array
+    heat = prof.copy()
+    oracle.fill_ghost(heat, ng, tuple("outflow" if b == "hse" else b for b in bcs[1]))
+    flips = (int(bc[2] == "reflect"), int(bc[3] == "reflect"))
+    got, scratch = _emu_step(emu, U, ng, dx, dy, dt, prm, seglen, flips, heat=heat)
+    ref = oracle.compressible_step(U, ng, dx, dy, dt, prm)
+    v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
+    assert not np.isnan(got[v_]).any() and scratch[3] == 0
+    for n in range(4):
+        assert rel_l2(got[v_][..., n], ref[v_][..., n]) < 1e-13
+    plain = oracle.compressible_step(U, ng, dx, dy, dt, oracle.comp_params(grav=grav, src_bcs=bcs))
+    assert rel_l2(ref[v_][..., 1], plain[v_][..., 1]) > 1e-6
