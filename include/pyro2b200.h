@@ -68,6 +68,8 @@ typedef struct {
                               * device plane with the state's pitch, ghost cells filled like a scalar; NULL = none */
     int do_sponge;           /* sponge damping (simulation.py:164-184, 425-441): on/off, the density below which it   */
     double sponge_rho_begin, sponge_rho_full, sponge_timescale; /* starts / is fully on, and its time scale          */
+    int src_copy_yhi;        /* 1 when the +y boundary is "ambient": the ghost cells hold a constant state while the
+                              * reference's source arrays are zero-gradient copies there (compressible/BC.py:150-152) */
 } p2b_comp_params;
 
 /* device scratch the sweep needs, 8 x 64-bit words owned by the caller:

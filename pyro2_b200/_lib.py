@@ -53,7 +53,8 @@ class CompParams(C.Structure):
                 ("grav", C.c_double), ("src_flip_ylo", C.c_int), ("src_flip_yhi", C.c_int),
                 ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int),
                 ("heat_rate", C.c_double), ("heat_profile", C.c_void_p), ("do_sponge", C.c_int),
-                ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double), ("sponge_timescale", C.c_double)]
+                ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double), ("sponge_timescale", C.c_double),
+                ("src_copy_yhi", C.c_int)]
 
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,

@@ -163,6 +163,7 @@ class Simulation(NullSimulation):
                                grav=rp.get_param("compressible.grav"),
                                src_flip_ylo=self._src_flip[0], src_flip_yhi=self._src_flip[1],
                                heat_rate=self._heat_rate, heat_profile=self._heat_plane,
+                               src_copy_yhi=int(self.cc_data.BCs["density"].yrb == "ambient"),
                                sponge=(rp.get_param("sponge.sponge_rho_begin"), rp.get_param("sponge.sponge_rho_full"),
                                        rp.get_param("sponge.sponge_timescale")) if rp.get_param("sponge.do_sponge") else None,
                                riemann=rp.get_param("compressible.riemann"),

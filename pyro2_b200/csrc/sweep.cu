@@ -179,6 +179,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     A.heat = prm->heat_profile; A.heat_rate = prm->heat_rate;
     A.do_sponge = prm->do_sponge; A.sponge_rho_begin = prm->sponge_rho_begin;
     A.sponge_rho_full = prm->sponge_rho_full; A.sponge_timescale = prm->sponge_timescale;
+    A.src_copy_yhi = prm->src_copy_yhi;
     A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
     A.seglen = choose_seglen(g->nx, A.nstrips, resident);

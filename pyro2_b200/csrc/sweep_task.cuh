@@ -64,6 +64,8 @@ struct SweepArgs {
     double heat_rate;                 //   S_ener += dens * heat_rate * P  (problems heating / plume / convection)
     int do_sponge;                    // sponge (simulation.py:164-184, 425-441)
     double sponge_rho_begin, sponge_rho_full, sponge_timescale;
+    int src_copy_yhi;                 // 1: the +y boundary is "ambient": its ghost cells hold a constant state, but the
+                                      //    reference's source arrays are zero-gradient copies of row jhi there
 };
 
 struct alignas(16) SweepSmem {
@@ -274,10 +276,18 @@ struct SweepTask {
             if (GRAV) {
                 // U_xl[i+1], U_xr[i], U_yl[j+1], U_yr[j] += 0.5 dt S(i, j); S_ymom = rho g, S_ener = (rho v) g
                 const bool flip = (j < ng && A.src_flip_ylo) || (j >= jhi && A.src_flip_yhi);
-                double sy = Uc.dens * A.grav, se = Uc.ymom * A.grav;
+                // the state the ghost-cell source is evaluated from: the ghost state itself, except above an
+                // "ambient" boundary, where the reference's source arrays copy the last valid row's source
+                double sd = Uc.dens, sm = Uc.ymom;
+                if (A.src_copy_yhi && j >= jhi) {
+                    const int cl = jhi - 1 - col0;
+                    sd = Q(IRHO, i, cl);
+                    sm = sd * Q(IV, i, cl);
+                }
+                double sy = sd * A.grav, se = sm * A.grav;
                 if (flip) { sy = -sy; se = -se; }
                 // problem heating: the profile plane is ghost-filled like the (even) source array it feeds
-                if (A.heat) se += Uc.dens * A.heat_rate * A.heat[(long long)i * A.pitch + jj];
+                if (A.heat) se += sd * A.heat_rate * A.heat[(long long)i * A.pitch + jj];
                 const double hy = 0.5 * A.dt * sy, he = 0.5 * A.dt * se;
                 XM.ymom += hy; XP.ymom += hy; YM.ymom += hy; YP.ymom += hy;
                 XM.ener += he; XP.ener += he; YM.ener += he; YP.ener += he;

@@ -103,7 +103,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
                                       int limiter, int use_flattening, int no_avisc_xhi, int no_avisc_yhi,
                                       int seglen, uint64_t* scratch, double* dbg, double grav, int src_flip_ylo,
                                       int src_flip_yhi, int riemann, int xl_solid, int yl_solid, const double* heat,
-                                      double heat_rate, int do_sponge, double sp_begin, double sp_full, double sp_tau)
+                                      double heat_rate, int do_sponge, double sp_begin, double sp_full, double sp_tau,
+                                      int src_copy_yhi)
 {
     pyro::SweepArgs A;
     A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
@@ -115,6 +116,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     A.xl_solid = xl_solid; A.yl_solid = yl_solid;
     A.heat = heat; A.heat_rate = heat_rate; A.do_sponge = do_sponge;
     A.sponge_rho_begin = sp_begin; A.sponge_rho_full = sp_full; A.sponge_timescale = sp_tau;
+    A.src_copy_yhi = src_copy_yhi;
     A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
     A.seglen = seglen;
     A.nsegs = (nx + seglen - 1) / seglen;

@@ -29,11 +29,11 @@ def emu():
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
                                            [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
                                            [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
-                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double])
+                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int])
     return lib
 
 
-def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0), heat=None):
+def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0), heat=None, src_copy_yhi=0):
     """heat: the heating profile with its ghost cells filled like a scalar (what the product passes)"""
     P = oracle.to_planes(U)
     _, qx, qy = P.shape
@@ -51,7 +51,7 @@ def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0), heat=None):
                                prm.use_flattening, prm.no_avisc_xhi, prm.no_avisc_yhi, seglen, scratch.ctypes.data, None,
                                prm.grav, flips[0], flips[1], prm.riemann, prm.xl_solid, prm.yl_solid,
                                None if heat is None else heat_p.ctypes.data, prm.heat_rate, prm.do_sponge,
-                               prm.sponge_rho_begin, prm.sponge_rho_full, prm.sponge_timescale)
+                               prm.sponge_rho_begin, prm.sponge_rho_full, prm.sponge_timescale, src_copy_yhi)
     return oracle.from_planes(np.ascontiguousarray(Pout[:, :, :qy])), scratch
 
 
@@ -152,7 +152,8 @@ def test_emulated_sweep_with_cgf_matches_oracle(emu, kind, bc, nx, ny, grav, seg
 @pytest.mark.parametrize("bc,nx,ny,grav,sponge,seglen", [
     (("outflow",) * 4, 24, 24, 0.0, None, 8),                                   # the heating problem: no gravity
     (("outflow", "outflow", "hse", "hse"), 20, 40, -2.0, None, 11),             # plume
-    (("periodic", "periodic", "reflect", "outflow"), 16, 48, -2.0, (0.6, 0.2, 1.e-2), 16)])   # convection-like
+    (("periodic", "periodic", "reflect", "outflow"), 16, 48, -2.0, (0.6, 0.2, 1.e-2), 16),   # convection-like
+    (("periodic", "periodic", "reflect", "ambient"), 16, 48, -2.0, (0.6, 0.2, 1.e-2), 16)])  # convection: ambient top
 def test_emulated_sweep_with_heating_and_sponge_matches_oracle(emu, bc, nx, ny, grav, sponge, seglen):
     from golden_util import var_bcs
     ng, gamma = 4, 1.4
@@ -173,14 +174,16 @@ def test_emulated_sweep_with_heating_and_sponge_matches_oracle(emu, bc, nx, ny, 
         for side in ("ylb", "yrb"):
             if bcs[k][2 + (side == "yrb")] == "hse":
                 oracle.fill_hse(P, ng, dy, grav, gamma, k, side)
+            if bcs[k][2 + (side == "yrb")] == "ambient":          # constant state beyond the top boundary
+                P[k][:, ng + ny:] = (0.05, 0.4, 0.0, 0.0)[k]
     U = oracle.from_planes(P)
     dt = 0.5 * oracle.cfl_dt(U, ng, dx, dy, gamma, 0.8)
     prm = oracle.comp_params(grav=grav, src_bcs=bcs, heat_rate=0.7, heat_profile=prof, sponge=sponge)
     # what the product hands the kernel: the profile ghost-filled like the (even) energy-source array
     heat = prof.copy()
-    oracle.fill_ghost(heat, ng, tuple("outflow" if b == "hse" else b for b in bcs[1]))
+    oracle.fill_ghost(heat, ng, tuple("outflow" if b in ("hse", "ambient") else b for b in bcs[1]))
     flips = (int(bc[2] == "reflect"), int(bc[3] == "reflect"))
-    got, scratch = _emu_step(emu, U, ng, dx, dy, dt, prm, seglen, flips, heat=heat)
+    got, scratch = _emu_step(emu, U, ng, dx, dy, dt, prm, seglen, flips, heat=heat, src_copy_yhi=int(bc[3] == "ambient"))
     ref = oracle.compressible_step(U, ng, dx, dy, dt, prm)
     v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
     assert not np.isnan(got[v_]).any() and scratch[3] == 0
