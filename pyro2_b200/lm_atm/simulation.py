@@ -254,3 +254,17 @@ class Simulation(NullSimulation):
         if not self.in_preevolve:
             self.cc_data.t += self.dt
             self.n += 1
+
+    def write_extras(self, f):
+        """the 1-d base state goes into the snapshot with the 2-d fields (simulation.py:670-681)"""
+        gb = f.create_group("base state")
+        for name, state in self.base.items():
+            gb.create_dataset(name, data=state.d)
+
+    def read_extras(self, f):
+        """restore the base state of a snapshot (simulation.py:683-691)"""
+        gb = f["base state"]
+        g = self.cc_data.grid
+        for name in gb:
+            self.base[name] = Basestate(g.ny, ng=g.ng)
+            self.base[name].d[:] = np.asarray(gb[name])
