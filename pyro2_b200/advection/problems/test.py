@@ -1,0 +1,14 @@
+"""Uniform density: the setup the reference's unit tests build their simulations on
+(pyro/advection/problems/test.py).  It has no stock inputs file."""
+
+DEFAULT_INPUTS = None
+
+PROBLEM_PARAMS = {}
+
+
+def init_data(my_data, rp):   # pylint: disable=unused-argument
+    my_data.get_var("density")[:, :] = 1.0
+
+
+def finalize():
+    pass

@@ -192,6 +192,9 @@ def test_compute_timestep_limits():
     ("compressible", "comp_rt16.npz", None), ("compressible", "comp_hse16.npz", None),
     ("compressible", "comp_heating32.npz", None), ("compressible", "comp_plume32.npz", None),
     ("compressible", "comp_convection16.npz", None),
+    ("compressible", "comp_rt2_48.npz", None), ("compressible", "comp_rt_multimode16.npz", None),
+    ("burgers", "burgers_converge32.npz", ["x-velocity", "y-velocity"]),
+    ("burgers", "burgers_tophat32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_converge32.npz", ["x-velocity", "y-velocity"]),
     ("burgers", "burgers_test.npz", ["x-velocity", "y-velocity"]),
@@ -423,3 +426,47 @@ def test_simulation_snapshot_round_trip(monkeypatch, tmp_path):
             assert "hse" in bnd.ext_bcs and bnd.bc_solid["ambient"] is False
             # derived variables are attached on read (io_pyro.py:131-141)
             assert len(back.cc_data.derives) == 1
+
+
+def test_burgers_verify_shock_speed():
+    """burgers/problems/verify.py: the front tracker on two states of the `test` problem (advanced here by the
+    oracle) recovers the Rankine-Hugoniot speed sqrt(8) of the 3 -> 1 jump to within the half-cell resolution of
+    the tracker"""
+    import oracle
+    from pyro2_b200.burgers.problems import test as problem
+    from pyro2_b200.burgers.problems import verify
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.mesh import patch
+
+    class RP:
+        def get_param(self, k):
+            return 0
+
+    n, ng = 64, 4
+    bc = bnd.BC(xlb="outflow", xrb="outflow", ylb="outflow", yrb="outflow")
+
+    def container():
+        d = patch.CellCenterData2d(patch.Cartesian2d(n, n, ng=ng, device="cpu"))
+        d.register_var("x-velocity", bc)
+        d.register_var("y-velocity", bc)
+        d.create()
+        return d
+    d1 = container()
+    problem.init_data(d1, RP())
+    u, v = d1.get_var("x-velocity").numpy().copy(), d1.get_var("y-velocity").numpy().copy()
+    dx = 1.0 / n
+    snaps, t = [], 0.0
+    for step in range(48):
+        oracle.fill_ghost(u, ng, ("outflow",) * 4)
+        oracle.fill_ghost(v, ng, ("outflow",) * 4)
+        dt = 0.8 * min(dx / np.abs(u).max(), dx / np.abs(v).max())
+        u, v = oracle.burgers_evolve(u, v, ng, dx, dx, dt, 2)
+        t += dt
+        if step in (11, 47):
+            d = container()
+            d.get_var("x-velocity")[:, :] = u
+            d.get_var("y-velocity")[:, :] = v
+            d.t = t
+            snaps.append(d)
+    speed = verify.shock_speed(*snaps)
+    assert abs(speed - verify.SHOCK_SPEED) < 0.1 * verify.SHOCK_SPEED

@@ -91,8 +91,9 @@ def test_emulated_incompressible_proj_type_1(flow):
     f.close()
 
 
-def test_emulated_burgers_run_matches_reference(flow):
-    z, rp, _ = load_flow("burgers_test.npz")
+@pytest.mark.parametrize("fname", ["burgers_test.npz", "burgers_converge32.npz", "burgers_tophat32.npz"])
+def test_emulated_burgers_run_matches_reference(flow, fname):
+    z, rp, _ = load_flow(fname)
     ng, n = int(z["ng"]), rp["mesh.nx"]
     bc = (rp["mesh.xlboundary"], rp["mesh.xrboundary"], rp["mesh.ylboundary"], rp["mesh.yrboundary"])
     u, v = z["P0"][0].copy(), z["P0"][1].copy()

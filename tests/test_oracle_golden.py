@@ -63,7 +63,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
                                   "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
-                                  "heating32", "plume32", "convection16"])
+                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
@@ -165,8 +165,9 @@ def test_incompressible_run_matches_reference(fname):
     assert np.array_equal(P, z["P"])
 
 
-def test_burgers_run_matches_reference():
-    z, rp, _ = load_flow("burgers_test.npz")
+@pytest.mark.parametrize("fname", ["burgers_test.npz", "burgers_converge32.npz", "burgers_tophat32.npz"])
+def test_burgers_run_matches_reference(fname):
+    z, rp, _ = load_flow(fname)
     ng = int(z["ng"])
     u, v = z["P0"][0].copy(), z["P0"][1].copy()
     n = rp["mesh.nx"]
@@ -177,7 +178,9 @@ def test_burgers_run_matches_reference():
         oracle.fill_ghost(v, ng, bc)
         # burgers/simulation.py:41-58 (then the driver's first-step factor and growth limit, both inactive here)
         raw = rp["driver.cfl"] * min(dx / max(np.abs(u).max(), 1.e-12), dx / max(np.abs(v).max(), 1.e-12))
-        if step > 0 and z["t"] > 0:
+        if rp["driver.fix_dt"] > 0:
+            assert float(dt) == rp["driver.fix_dt"]
+        elif step > 0 and z["t"] > 0:
             assert raw >= float(dt) * (1 - 1e-15)
         u, v = oracle.burgers_evolve(u, v, ng, dx, dx, float(dt), rp["advection.limiter"])
     assert np.array_equal(u, z["P"][0]) and np.array_equal(v, z["P"][1])
