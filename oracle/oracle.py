@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,
-            "periodic": 3, "hse": 4, "ambient": 4, "none": 4}   # 4: leave that side alone (user BCs are filled separately)
+            "periodic": 3, "hse": 4, "ambient": 4, "ramp": 4, "none": 4}   # 4: leave that side alone (user BCs are filled separately)
 
 
 def build(force=False):
@@ -161,7 +161,7 @@ def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, u
     array P, S_ener = dens * heat_rate * P; sponge: (rho_begin, rho_full, timescale) or None"""
     codes = (C.c_int * 16)()
     if src_bcs is not None:
-        flat = [BC_CODES["outflow" if b in ("hse", "ambient") else b] for bc in src_bcs for b in bc]
+        flat = [BC_CODES["outflow" if b in ("hse", "ambient", "ramp") else b] for bc in src_bcs for b in bc]
         codes = (C.c_int * 16)(*flat)
     hp = None if heat_profile is None else np.ascontiguousarray(heat_profile, dtype=np.float64)
     sp = sponge or (0.0, 0.0, 1.0)
@@ -178,6 +178,45 @@ def fill_hse(P, ng, dy, grav, gamma, var, side):
     assert P.flags.c_contiguous and P.dtype == np.float64 and P.shape[0] == 4
     lib().orc_fill_hse(_ptr(P), P.shape[1] - 2 * ng, P.shape[2] - 2 * ng, ng, dy, grav, gamma, var,
                        {"ylb": 0, "yrb": 1}[side])
+
+
+def ramp_inflow(var, gamma, post=True):
+    """conserved post- / pre-shock value of plane `var` (0 dens, 1 ener, 2 xmom, 3 ymom) for the double Mach
+    reflection boundaries (compressible/BC.py:259-296: inflow_post_bc / inflow_pre_bc, constants in the source)"""
+    r, u, v, p = (8.0, 7.1447096, -4.125, 116.5) if post else (1.4, 0.0, 0.0, 1.0)
+    return [r, p / (gamma - 1.0) + 0.5 * r * (u * u + v * v), r * u, r * v][var]
+
+
+def fill_ramp(a, var, side, ng, x, y, dx, dy, t, gamma):
+    """the "ramp" boundary of compressible/BC.py:183-256 for one ghost-padded plane a[qx, qy] of variable `var`
+    on side "xlb" / "ylb" / "yrb" at time t, in place.  Plain numpy loops over the ghost cells, in the reference's
+    order: the upper boundary is a 2 x 2 supersampled average of the post- and pre-shock states about the
+    position of the Mach-10 shock, summed as ((q1 + q2) + q3) + q4."""
+    import math
+    qx, qy = a.shape
+    nx, ny = qx - 2 * ng, qy - 2 * ng
+    post, pre = ramp_inflow(var, gamma, True), ramp_inflow(var, gamma, False)
+    if side == "xlb":                        # post-shock inflow
+        a[:ng, :] = post
+    elif side == "ylb":                      # inflow left of the ramp's foot at x = 1/6, reflecting wall right of it
+        left = x < 1.0 / 6.0
+        right = ~left
+        for jj in range(ng):
+            j = ng - 1 - jj
+            a[left, j] = post
+            a[right, j] = (-1.0 if var == 3 else 1.0) * a[right, ng + jj]
+    elif side == "yrb":                      # the shock's intersection with each ghost row moves with time
+        for j in range(ng + ny, qy):
+            fronts = [1.0 / 6.0 + (y[j] + s * 0.5 * dy * math.sqrt(3)) / math.tan(math.pi / 3.0)
+                      + (10.0 / math.sin(math.pi / 3.0)) * t for s in (-1.0, 1.0)]
+            for i in range(qx):
+                acc = 0.0
+                for sf in fronts:
+                    for cx in (x[i] - 0.5 * dx * math.sqrt(3), x[i] + 0.5 * dx * math.sqrt(3)):
+                        acc = acc + 0.25 * (post if cx < sf else pre)
+                a[i, j] = acc
+    else:
+        raise ValueError(side)
 
 
 def compressible_step(U_ijn, ng, dx, dy, dt, params=None, stages=False, planes=False):

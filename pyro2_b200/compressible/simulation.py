@@ -85,9 +85,10 @@ class Simulation(NullSimulation):
         riemann_method = rp.get_param("compressible.riemann")
         if riemann_method not in ("HLLC", "CGF"):
             msg.fail(f"ERROR: the device sweep implements the HLLC and CGF Riemann solvers (got {riemann_method})")
-        # solver-specific boundary types (simulation.py:212-214); ambient and ramp are not built
+        # solver-specific boundary types (simulation.py:212-214)
         bnd.define_bc("hse", BC.user, is_solid=False)
         bnd.define_bc("ambient", BC.user, is_solid=False)
+        bnd.define_bc("ramp", BC.user, is_solid=False)
         try:
             if rp.get_param("particles.do_particles") == 1:
                 msg.fail("ERROR: particles are not supported")

@@ -154,8 +154,8 @@ int fill_ghost_impl(T* base, const p2b_grid* g, int nvar, const int* bc, cudaStr
         const int qx = g->nx + 2 * g->ng, qy = g->ny + 2 * g->ng;
         T* b = base + (long long)n0 * g->plane_stride;
         int tx = nv * 2 * g->ng * qy, ty = nv * qx * 2 * g->ng;
-        fill_x_kernel<T><<<(tx + 255) / 256 < 1184 ? (tx + 255) / 256 : 1184, 256, 0, st>>>(b, *g, nv, t);
-        fill_y_kernel<T><<<(ty + 255) / 256 < 1184 ? (ty + 255) / 256 : 1184, 256, 0, st>>>(b, *g, nv, t);
+        P2B_LAUNCH(fill_x_kernel<T>, (tx + 255) / 256 < 1184 ? (tx + 255) / 256 : 1184, 256, 0, st)(b, *g, nv, t);
+        P2B_LAUNCH(fill_y_kernel<T>, (ty + 255) / 256 < 1184 ? (ty + 255) / 256 : 1184, 256, 0, st)(b, *g, nv, t);
     }
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -233,13 +233,13 @@ int p2b_fill_ghost_values_f64(double* plane, const p2b_grid* g, const int bc[4],
     memset(&t, 0, sizeof t);
     for (int s = 0; s < 4; ++s) t.code[0][s] = codes[s];
     int tx = 2 * g->ng * qy, ty = qx * 2 * g->ng;
-    fill_x_kernel<double><<<(tx + 255) / 256, 256, 0, st>>>(plane, *g, 1, t);
-    if (xl || xr) fill_x_values_kernel<<<(qy + 255) / 256, 256, 0, st>>>(plane, *g, bc[0], bc[1], xl, xr);
+    P2B_LAUNCH(fill_x_kernel<double>, (tx + 255) / 256, 256, 0, st)(plane, *g, 1, t);
+    if (xl || xr) P2B_LAUNCH(fill_x_values_kernel, (qy + 255) / 256, 256, 0, st)(plane, *g, bc[0], bc[1], xl, xr);
     t.code[0][0] = t.code[0][1] = P2B_BC_NONE;
     t.code[0][2] = yl ? P2B_BC_NONE : bc[2];
     t.code[0][3] = yr ? P2B_BC_NONE : bc[3];
-    fill_y_kernel<double><<<(ty + 255) / 256, 256, 0, st>>>(plane, *g, 1, t);
-    if (yl || yr) fill_y_values_kernel<<<(qx + 255) / 256, 256, 0, st>>>(plane, *g, bc[2], bc[3], yl, yr);
+    P2B_LAUNCH(fill_y_kernel<double>, (ty + 255) / 256, 256, 0, st)(plane, *g, 1, t);
+    if (yl || yr) P2B_LAUNCH(fill_y_values_kernel, (qx + 255) / 256, 256, 0, st)(plane, *g, bc[2], bc[3], yl, yr);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
@@ -251,7 +251,7 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    cfl_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(U, *g, gamma, (unsigned long long*)scratch);
+    P2B_LAUNCH(cfl_kernel, (int)blocks, 256, 0, (cudaStream_t)stream)(U, *g, gamma, (unsigned long long*)scratch);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }

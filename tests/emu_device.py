@@ -1,0 +1,147 @@
+"""An emulated device for the CPU-only build box: the product's Python layer (pyro2_b200: Pyro, the solvers, the
+multigrid classes, the handles) runs unchanged, but every C-ABI call it makes lands in the host-compiled kernel
+libraries of tests/emu/ (the same .cu sources built with g++ against the CUDA execution-model emulator) and its
+"device" tensors live in host memory.
+
+TEST INFRASTRUCTURE ONLY.  It exists so that the bodies of the `-m gpu` tests -- public API in, reference fixtures
+out -- can be rehearsed here, where there is no GPU: host-side logic (parameter plumbing, boundary hooks, time-step
+control, problem setups) and kernel indexing are then both checked before a GPU run is spent on them.  Nothing in
+pyro2_b200/ imports this file; the product has no CPU path and fails loudly without a CUDA device.
+
+    with emu_device.emulated_device():
+        p = Pyro("compressible"); p.initialize_problem(...); p.single_step()
+
+What is patched while the context is active (and restored afterwards):
+  * pyro2_b200._lib.lib()         -> a facade that routes each p2b_* symbol to the emulator library built from the
+                                     .cu file that defines it (the sweep goes to the warp emulator of sweep_task.cuh)
+  * pyro2_b200._lib.stream_ptr()  -> NULL (the emulator runs launches synchronously)
+  * ops.require_cuda()            -> no-op; the default device of grids -> cpu
+  * torch.zeros / torch.empty / Tensor.to / Tensor.cuda: a "cuda" device argument means host memory;
+    Tensor.is_cuda -> True; torch.cuda.synchronize -> no-op (CUDA-graph capture then fails and the callers fall back
+    to eager launches, which is their documented behaviour)
+"""
+import contextlib
+import ctypes as C
+from unittest import mock
+
+import torch
+
+import emu_util
+
+SW_OUT = 30            # output columns per warp task (sweep_task.cuh)
+RESIDENT_WARPS = 148 * 12   # what choose_seglen() is given here: any value works, this one makes small grids split into segments
+
+
+def _choose_seglen(nx, nstrips, resident):
+    """pyro2_b200/csrc/sweep.cu choose_seglen(), restated (the result only affects how the work is cut up)"""
+    overhead = 3
+    best_len, best_cost = nx, 1 << 30
+    for k in range(1, 25):
+        cap = k * resident // nstrips
+        if cap < 1:
+            continue
+        length = max((nx + cap - 1) // cap, 8)
+        nseg = (nx + length - 1) // length
+        rounds = (nseg * nstrips + resident - 1) // resident
+        cost = rounds * (length + overhead)
+        if cost <= best_cost:
+            best_cost, best_len = cost, length
+    return best_len
+
+
+class EmuLibrary:
+    """stands in for the ctypes handle of libpyro2b200.so"""
+    ROUTES = (("p2b_mg_", emu_util.load_mg_emu), ("p2b_flow_", emu_util.load_flow_emu), ("p2b_lm_", emu_util.load_lm_emu),
+              ("p2b_fill_hse", emu_util.load_bc_emu), ("p2b_fill_ambient", emu_util.load_bc_emu),
+              ("p2b_fill_ghost", emu_util.load_ghost_emu), ("p2b_cfl_wavemax", emu_util.load_ghost_emu),
+              ("p2b_device_sms", emu_util.load_ghost_emu))
+
+    def __init__(self):
+        self.calls = {}          # symbol -> number of calls, for the tests to see what really ran
+        self._used = []
+        self._info = (0, 0, 0)
+
+    def _counted(self, name, f):
+        def call(*a):
+            self.calls[name] = self.calls.get(name, 0) + 1
+            return f(*a)
+        return call
+
+    def __getattr__(self, name):
+        if name == "p2b_compressible_sweep":
+            return self._counted(name, self._sweep)
+        if name == "p2b_sweep_info":
+            return self._sweep_info
+        if name == "p2b_last_error":
+            return lambda: b"; ".join(lib.p2b_last_error() or b"" for lib in self._used)
+        if name == "p2b_version":
+            return lambda: 1
+        for prefix, loader in self.ROUTES:
+            if name.startswith(prefix):
+                lib = loader()
+                if lib not in self._used:
+                    self._used.append(lib)
+                return self._counted(name, getattr(lib, name))
+        raise AttributeError(name)
+
+    def _sweep(self, uin, uout, g_ref, prm_ref, dt, scratch, stream):   # pylint: disable=unused-argument
+        """p2b_compressible_sweep (sweep.cu) over the warp emulator: same argument checks that matter here, same
+        work decomposition rule, same scratch words (wave-speed maxima in [0], [1], status in [3])"""
+        g, p = g_ref._obj, prm_ref._obj
+        if uin == uout or g.ng < 4 or g.pitch % 2 or g.pitch < g.ny + 2 * g.ng or p.riemann not in (0, 1):
+            return -1
+        nstrips = (g.ny + SW_OUT - 1) // SW_OUT
+        seglen = _choose_seglen(g.nx, nstrips, RESIDENT_WARPS)
+        self._info = (nstrips * ((g.nx + seglen - 1) // seglen), RESIDENT_WARPS, seglen)
+        lib = emu_util.load_sweep_emu()
+        return lib.emu_compressible_sweep(uin, uout, g.nx, g.ny, g.ng, g.pitch, g.plane_stride, g.dx, g.dy, dt,
+                                          p.gamma, p.z0, p.z1, p.delta, p.cvisc, p.limiter, p.use_flattening,
+                                          p.no_avisc_xhi, p.no_avisc_yhi, seglen, scratch, None,
+                                          p.grav, p.src_flip_ylo, p.src_flip_yhi, p.riemann, p.xl_solid, p.yl_solid,
+                                          p.heat_profile, p.heat_rate, p.do_sponge, p.sponge_rho_begin, p.sponge_rho_full,
+                                          p.sponge_timescale, p.src_copy_yhi)
+
+    def _sweep_info(self, a, b, c):
+        for ref, val in zip((a, b, c), self._info):
+            ref._obj.value = val
+        return 0
+
+
+def _is_cuda(dev):
+    return dev is not None and (dev == "cuda" or (isinstance(dev, str) and dev.startswith("cuda"))
+                                or (isinstance(dev, torch.device) and dev.type == "cuda"))
+
+
+def _host_device(fn):
+    def wrapped(*a, **k):
+        if _is_cuda(k.get("device")):
+            k["device"] = "cpu"
+        return fn(*a, **k)
+    return wrapped
+
+
+@contextlib.contextmanager
+def emulated_device():
+    """run the enclosed product code against the emulator libraries; yields the EmuLibrary (see .calls)"""
+    from pyro2_b200 import _lib, mg_handle, ops
+    from pyro2_b200.mesh import patch
+    facade = EmuLibrary()
+    real_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if _is_cuda(x) else x for x in a)
+        if _is_cuda(k.get("device")):
+            k["device"] = "cpu"
+        return real_to(self, *a, **k)
+    with contextlib.ExitStack() as st:
+        for target, attr, new in (
+                (_lib, "lib", lambda: facade), (_lib, "stream_ptr", lambda: None),
+                (ops, "require_cuda", lambda: None), (mg_handle, "require_cuda", lambda: None),
+                (patch, "_default_device", lambda: torch.device("cpu")),
+                (torch, "zeros", _host_device(torch.zeros)), (torch, "empty", _host_device(torch.empty)),
+                (torch, "as_tensor", _host_device(torch.as_tensor)),
+                (torch.Tensor, "to", to), (torch.Tensor, "cuda", lambda self, *a, **k: self),
+                (torch.cuda, "synchronize", lambda *a, **k: None)):
+            st.enter_context(mock.patch.object(target, attr, new))
+        st.enter_context(mock.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)))
+        yield facade

@@ -46,6 +46,31 @@ def load_bc_emu():
     return _load("bc", ["bc_user.cu", "bc_user_kernels.cuh"], ("p2b_fill_hse", "p2b_fill_ambient"))
 
 
+def load_ghost_emu():
+    """pyro2_b200/csrc/ghost_cfl.cu compiled for the host: ghost fill and CFL wave speeds over numpy memory"""
+    return _load("ghost", ["ghost_cfl.cu"], ("p2b_fill_ghost", "p2b_cfl_wavemax", "p2b_device_sms"))
+
+
+def load_sweep_emu():
+    """the fused sweep's task source (sweep_task.cuh) under its own warp emulator (tests/emu/sweep_emu.cpp: 32 host
+    threads in lock step stand in for the lanes, memcpy for the TMA bulk copies)"""
+    if "sweep" in _LIBS:
+        return _LIBS["sweep"]
+    so = os.path.join(EMU_DIR, "libsweep_emu.so")
+    src = os.path.join(EMU_DIR, "sweep_emu.cpp")
+    hdrs = [os.path.join(CSRC, h) for h in ("sweep_task.cuh", "hydro_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
+    lib = C.CDLL(so)
+    lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
+                                           [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
+                                           [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
+                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int])
+    _LIBS["sweep"] = lib
+    return lib
+
+
 def load_lm_emu():
     """pyro2_b200/csrc/lm.cu compiled for the host: the p2b_lm_* ABI over numpy memory"""
     return _load("lm", ["lm.cu", "lm_kernels.cuh", "flow_kernels.cuh"], "p2b_lm_", ["-Wno-unused-function"])

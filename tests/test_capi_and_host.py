@@ -193,6 +193,7 @@ def test_compute_timestep_limits():
     ("compressible", "comp_heating32.npz", None), ("compressible", "comp_plume32.npz", None),
     ("compressible", "comp_convection16.npz", None),
     ("compressible", "comp_rt2_48.npz", None), ("compressible", "comp_rt_multimode16.npz", None),
+    ("compressible", "comp_ramp64.npz", None),
     ("burgers", "burgers_converge32.npz", ["x-velocity", "y-velocity"]),
     ("burgers", "burgers_tophat32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
@@ -236,6 +237,7 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         from pyro2_b200.mesh import boundary as bnd
         bnd.define_bc("hse", BC.user, is_solid=False)       # what Simulation.initialize registers
         bnd.define_bc("ambient", BC.user, is_solid=False)
+        bnd.define_bc("ramp", BC.user, is_solid=False)
     bc = bc_setup(rp)[0]
     vars_ = {"compressible": ["density", "energy", "x-momentum", "y-momentum"], "advection": ["density"], "diffusion": ["phi"]}.get(
         solver, ["x-velocity", "y-velocity"])
@@ -470,3 +472,34 @@ def test_burgers_verify_shock_speed():
             snaps.append(d)
     speed = verify.shock_speed(*snaps)
     assert abs(speed - verify.SHOCK_SPEED) < 0.1 * verify.SHOCK_SPEED
+
+
+def test_ramp_boundary_matches_oracle():
+    """the "ramp" user boundary (compressible/BC.py:183-256) as the product fills it (device slice assignments +
+    host-evaluated top rows) against the oracle's loop restatement, at two times, bit for bit"""
+    import oracle
+    from pyro2_b200.compressible import BC
+    from pyro2_b200.mesh import boundary as bnd
+    from pyro2_b200.mesh import patch
+    bnd.define_bc("ramp", BC.user, is_solid=False)
+    names = ("density", "energy", "x-momentum", "y-momentum")
+    rng = np.random.default_rng(3)
+    g = patch.Cartesian2d(48, 12, ng=4, xmax=4.0, ymax=1.0, device="cpu")
+    d = patch.CellCenterData2d(g)
+    bc = bnd.BC(xlb="ramp", xrb="outflow", ylb="ramp", yrb="ramp")
+    for n in names:
+        d.register_var(n, bc)
+    d.set_aux("gamma", 1.4)
+    d.create()
+    for t in (0.0, 0.0371):
+        d.t = t
+        ref = rng.standard_normal((4, g.qx, g.qy))
+        for k, n in enumerate(names):
+            d.get_var(n)[:, :] = ref[k]
+            for side in ("xlb", "ylb", "yrb"):          # the order CellCenterData2d.fill_BC calls the hooks in
+                BC.user("ramp", side, n, d)
+                oracle.fill_ramp(ref[k], k, side, g.ng, g.x, g.y, g.dx, g.dy, t, 1.4)
+            assert np.array_equal(d.get_var(n).numpy(), ref[k]), (n, t)
+    # the top rows really are a mixture: pre-shock right of the front, post-shock left of it, blends in between
+    top = d.get_var("density").numpy()[:, g.jhi + 1]
+    assert top[0] == 8.0 and top[-1] == 1.4 and np.any((top > 1.4) & (top < 8.0))

@@ -21,6 +21,8 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
     grav = rp.get("compressible.grav", 0.0)
     gamma = rp["eos.gamma"]
     bcs = var_bcs(rp)
+    xc = (np.arange(nx + 2 * ng) + 0.5 - ng) * dx + rp["mesh.xmin"]
+    yc = (np.arange(ny + 2 * ng) + 0.5 - ng) * dy + rp["mesh.ymin"]
     prm = oracle.comp_params(gamma=gamma, z0=rp["compressible.z0"], z1=rp["compressible.z1"],
                              delta=rp["compressible.delta"], cvisc=rp["compressible.cvisc"],
                              limiter=rp["compressible.limiter"], use_flattening=rp["compressible.use_flattening"],
@@ -45,6 +47,9 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
                     oracle.fill_hse(P, ng, dy, grav, gamma, k, side)
                 if bcs[k][2 + (side == "yrb")] == "ambient":
                     P[k][:, ng + ny:] = ambient[k]
+            for s_, side in enumerate(("xlb", "xrb", "ylb", "yrb")):      # user boundaries after the standard ones, in this order
+                if bcs[k][s_] == "ramp":
+                    oracle.fill_ramp(P[k], k, side, ng, xc, yc, dx, dy, t, gamma)
         dt = oracle.cfl_dt(oracle.from_planes(P), ng, dx, dy, gamma, rp["driver.cfl"])
         # NullSimulation.compute_timestep (simulation_null.py:222-244)
         dt = rp["driver.init_tstep_factor"] * dt if n == 0 else min(rp["driver.max_dt_change"] * dt_old, dt)
@@ -63,7 +68,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
                                   "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
-                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16"])
+                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16", "ramp64"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))

@@ -179,3 +179,31 @@ def test_fv2d_conversions_bit_identical():
     d.fill_BC = lambda name: None               # the product's ghost fill is a device kernel (tested on the GPU)
     d.from_centers("a")
     assert np.array_equal(np.asarray(rd.get_var("a")), d.get_var("a").numpy())
+
+
+def test_ramp_boundary_bit_identical():
+    """oracle.fill_ramp against the reference's own fill_BC with its "ramp" user boundary (compressible/BC.py:183-256)
+    on random data, at t = 0 and at a later time"""
+    ref_shim.load()
+    import pyro.compressible.BC as rBC
+    import pyro.mesh.boundary as rbnd
+    import pyro.mesh.patch as rpatch
+    rbnd.define_bc("ramp", rBC.user, is_solid=False)
+    names = ("density", "energy", "x-momentum", "y-momentum")
+    rng = np.random.default_rng(8)
+    g = rpatch.Cartesian2d(40, 10, ng=4, xmax=4.0, ymax=1.0)
+    d = rpatch.CellCenterData2d(g)
+    for n in names:
+        d.register_var(n, rbnd.BC(xlb="ramp", xrb="outflow", ylb="ramp", yrb="ramp"))
+    d.set_aux("gamma", 1.4)
+    d.create()
+    for t in (0.0, 0.0123):
+        d.t = t
+        mine = rng.standard_normal((4, g.qx, g.qy))
+        for k, n in enumerate(names):
+            d.get_var(n)[:, :] = mine[k]
+            d.fill_BC(n)
+            oracle.fill_ghost(mine[k], g.ng, ("ramp", "outflow", "ramp", "ramp"))
+            for side in ("xlb", "ylb", "yrb"):
+                oracle.fill_ramp(mine[k], k, side, g.ng, g.x, g.y, g.dx, g.dy, t, 1.4)
+            assert np.array_equal(np.asarray(d.get_var(n)), mine[k]), (n, t)

@@ -19,18 +19,8 @@ EMU_DIR = os.path.join(HERE, "emu")
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libsweep_emu.so")
-    src = os.path.join(EMU_DIR, "sweep_emu.cpp")
-    hdrs = [os.path.join(HERE, "..", "pyro2_b200", "csrc", h) for h in ("sweep_task.cuh", "hydro_core.cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
-    lib = C.CDLL(so)
-    lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
-                                           [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
-                                           [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
-                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int])
-    return lib
+    from emu_util import load_sweep_emu
+    return load_sweep_emu()
 
 
 def _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips=(0, 0), heat=None, src_copy_yhi=0):
