@@ -60,7 +60,8 @@ typedef struct {
                               * unsplit_fluxes.py:247-330 */
     int src_flip_ylo;        /* 1 when the -y / +y boundary reflects: the reference fills the ghost cells of  */
     int src_flip_yhi;        /*   its source arrays odd (ymom_src) / even (E_src) there (simulation.py:248-253) */
-    int riemann;             /* compressible.riemann: 0 HLLC (riemann.py:682-860), 1 CGF (riemann.py:9-310 + consFlux) */
+    int riemann;             /* compressible.riemann: 0 HLLC (riemann.py:682-860), 1 CGF (riemann.py:9-310 + consFlux),
+                              * 2 HLLC_lm (riemann_hllc_lowspeed, riemann.py:864-1019) */
     int xl_solid, yl_solid;  /* CGF: the -x / -y boundary is a solid wall (boundary.bc_is_solid): zero normal
                               * velocity in the interface state on that face (riemann.py:283-292) */
     double heat_rate;        /* problem heating source S_ener = dens * heat_rate * heat_profile[i, j]           */
@@ -120,7 +121,7 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
  * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, Cartesian geometry,
- * Riemann solver HLLC or CGF (prm->riemann); gravity, a heating profile or the sponge select the
+ * Riemann solver HLLC, CGF or HLLC_lm (prm->riemann); gravity, a heating profile or the sponge select the
  * instantiations with source terms. */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);

@@ -166,7 +166,7 @@ def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, u
     hp = None if heat_profile is None else np.ascontiguousarray(heat_profile, dtype=np.float64)
     sp = sponge or (0.0, 0.0, 1.0)
     prm = CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes,
-                     {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid, heat_rate,
+                     {"HLLC": 0, "CGF": 1, "HLLC_lm": 2}[riemann], xl_solid, yl_solid, heat_rate,
                      None if hp is None else hp.ctypes.data, int(sponge is not None), sp[0], sp[1], sp[2])
     prm._keepalive = hp
     return prm

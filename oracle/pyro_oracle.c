@@ -144,7 +144,7 @@ typedef struct {
        copies the first interior row like outflow (compressible/BC.py:55-63, 111-117) */
     double grav;
     int src_bc[16];
-    /* compressible.riemann: 0 HLLC, 1 CGF; xl_solid / yl_solid: the -x / -y boundary is a solid wall
+    /* compressible.riemann: 0 HLLC, 1 CGF, 2 HLLC_lm; xl_solid / yl_solid: the -x / -y boundary is a solid wall
        (boundary.bc_is_solid), which CGF uses to zero the normal velocity at that face */
     int riemann, xl_solid, yl_solid;
     /* problem heating source S_ener = dens * heat_rate * heat_profile[i, j] (compressible/problems/heating.py,
@@ -537,10 +537,69 @@ static void riemann_cgf(int idir, const double *U_l, const double *U_r, double *
         }
 }
 
+/* riemann.py:864-1019 (riemann_hllc_lowspeed): HLLC in Toro's alternate form (Eqs. 10.43, 10.44) with the low Mach
+ * number fix of Minoshima & Miyoshi (2021) -- the star-region pressure is blended towards the arithmetic mean as the
+ * local Mach number drops */
+static void riemann_hllc_lowspeed(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy,
+                                  int ng, double gamma)
+{
+    const size_t np = (size_t)qx * qy;
+    const int nx = qx - 2 * ng, ny = qy - 2 * ng;
+    const int ilo = ng, ihi = ng + nx, jlo = ng, jhi = ng + ny;
+    const double smallc = 1.e-10, smallp = 1.e-10;
+    const int imn = idir == 1 ? IXMOM : IYMOM, imt = idir == 1 ? IYMOM : IXMOM;
+    memset(F, 0, 4 * np * sizeof(double));
+#pragma omp parallel for
+    for (int i = ilo - 1; i < ihi + 1; i++)
+        for (int j = jlo - 1; j < jhi + 1; j++) {
+            size_t k = IDX(i, j);
+            double Ul[4], Ur[4], Fl[4], Fr[4], Fk[4], D[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int m = 0; m < 4; m++) { Ul[m] = U_l[m * np + k]; Ur[m] = U_r[m * np + k]; }
+            double rho_l = Ul[IDENS];
+            double un_l = Ul[imn] / rho_l, ut_l = Ul[imt] / rho_l;
+            double rhoe_l = Ul[IENER] - 0.5 * rho_l * (un_l * un_l + ut_l * ut_l);
+            double p_l = fmax(rhoe_l * (gamma - 1.0), smallp);
+            double rho_r = Ur[IDENS];
+            double un_r = Ur[imn] / rho_r, ut_r = Ur[imt] / rho_r;
+            double rhoe_r = Ur[IENER] - 0.5 * rho_r * (un_r * un_r + ut_r * ut_r);
+            double p_r = fmax(rhoe_r * (gamma - 1.0), smallp);
+            double c_l = fmax(smallc, sqrt(gamma * p_l / rho_l));
+            double c_r = fmax(smallc, sqrt(gamma * p_r / rho_r));
+            double S_l, S_r;
+            estimate_wave_speed(rho_l, un_l, p_l, c_l, rho_r, un_r, p_r, c_r, gamma, &S_l, &S_r);
+            double S_c = (p_r - p_l + rho_l * un_l * (S_l - un_l) - rho_r * un_r * (S_r - un_r)) /
+                         (rho_l * (S_l - un_l) - rho_r * (S_r - un_r));
+            D[imn] = 1.0;
+            D[IENER] = S_c;
+            cons_flux(idir, gamma, Ul, Fl);
+            cons_flux(idir, gamma, Ur, Fr);
+            double vmag_l = sqrt(un_l * un_l + ut_l * ut_l);
+            double vmag_r = sqrt(un_r * un_r + ut_r * ut_r);
+            double cs_max = fmax(c_l, c_r);
+            double chi = fmin(1.0, fmax(vmag_l, vmag_r) / cs_max);
+            double phi = chi * (2.0 - chi);
+            double pstar_lr = 0.5 * (p_l + p_r) +
+                              0.5 * phi * (rho_l * (S_l - un_l) * (S_c - un_l) + rho_r * (S_r - un_r) * (S_c - un_r));
+            if (S_r <= 0.0) {
+                for (int m = 0; m < 4; m++) Fk[m] = Fr[m];
+            } else if (S_c <= 0.0 && 0.0 < S_r) {
+                for (int m = 0; m < 4; m++)
+                    Fk[m] = (S_c * (S_r * Ur[m] - Fr[m]) + S_r * pstar_lr * D[m]) / (S_r - S_c);
+            } else if (S_l < 0.0 && 0.0 < S_c) {
+                for (int m = 0; m < 4; m++)
+                    Fk[m] = (S_c * (S_l * Ul[m] - Fl[m]) + S_l * pstar_lr * D[m]) / (S_l - S_c);
+            } else {
+                for (int m = 0; m < 4; m++) Fk[m] = Fl[m];
+            }
+            for (int m = 0; m < 4; m++) F[m * np + k] = Fk[m];
+        }
+}
+
 static void riemann_solve(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
                           const orc_comp_params *P)
 {
     if (P->riemann == 1) riemann_cgf(idir, U_l, U_r, F, qx, qy, ng, P->gamma, idir == 1 ? P->xl_solid : P->yl_solid);
+    else if (P->riemann == 2) riemann_hllc_lowspeed(idir, U_l, U_r, F, qx, qy, ng, P->gamma);
     else riemann_hllc(idir, U_l, U_r, F, qx, qy, ng, P->gamma);
 }
 

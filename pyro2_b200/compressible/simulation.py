@@ -83,8 +83,8 @@ class Simulation(NullSimulation):
         my_data = self.data_class(my_grid)
 
         riemann_method = rp.get_param("compressible.riemann")
-        if riemann_method not in ("HLLC", "CGF"):
-            msg.fail(f"ERROR: the device sweep implements the HLLC and CGF Riemann solvers (got {riemann_method})")
+        if riemann_method not in ("HLLC", "HLLC_lm", "CGF"):
+            msg.fail("ERROR: Riemann solver undefined")
         # solver-specific boundary types (simulation.py:212-214)
         bnd.define_bc("hse", BC.user, is_solid=False)
         bnd.define_bc("ambient", BC.user, is_solid=False)

@@ -119,6 +119,8 @@ static int resident_warps()
         cudaFuncSetAttribute(sweep_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(sweep_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(sweep_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         // every instantiation has the same launch bounds and shared memory, hence the same residency
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false, 0>, SWEEP_THREADS,
                                                       SWEEP_WARPS * sizeof(SweepSmem));
@@ -163,7 +165,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     P2B_REQUIRE(g->pitch >= g->ny + 2 * g->ng && (g->pitch % 2) == 0, "pitch must be even and >= qy");
     P2B_REQUIRE((g->plane_stride % 2) == 0 && ((uintptr_t)Uin % 16) == 0, "planes must be 16-byte aligned");
     P2B_REQUIRE(prm->limiter >= 0 && prm->limiter <= 2, "limiter must be 0, 1 or 2");
-    P2B_REQUIRE(prm->riemann == 0 || prm->riemann == 1, "riemann must be 0 (HLLC) or 1 (CGF)");
+    P2B_REQUIRE(prm->riemann >= 0 && prm->riemann <= 2, "riemann must be 0 (HLLC), 1 (CGF) or 2 (HLLC_lm)");
     cudaStream_t st = (cudaStream_t)stream;
 
     SweepArgs A;
@@ -196,7 +198,10 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
     unsigned long long* counter = (unsigned long long*)(scratch + 2);
     const bool grav = prm->grav != 0.0 || prm->heat_profile != nullptr || prm->do_sponge != 0;   // any source term
-    if (prm->riemann == 1) {
+    if (prm->riemann == 2) {
+        if (grav) sweep_kernel<true, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        else sweep_kernel<false, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+    } else if (prm->riemann == 1) {
         if (grav) sweep_kernel<true, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
         else sweep_kernel<false, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
     } else {

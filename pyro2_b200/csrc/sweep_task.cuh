@@ -81,7 +81,8 @@ struct alignas(16) SweepSmem {
 // get_external_sources :105-160).  The reference fills the ghost cells of the source ARRAYS with their own
 // BCs (ymom_src odd, E_src even across a reflecting y wall), which is the source of the ghost STATE with
 // the sign flipped there and identical to it for every other boundary type.
-// RIEMANN: 0 = HLLC (riemann_hllc), 1 = CGF (riemann_cgf + consFlux); selected by compressible.riemann.
+// RIEMANN: 0 = HLLC (riemann_hllc), 1 = CGF (riemann_cgf + consFlux), 2 = low-Mach HLLC (riemann_hllc_lowspeed);
+// selected by compressible.riemann.
 template <class W, bool GRAV = false, int RIEMANN = 0>
 struct SweepTask {
     W& w;
@@ -98,6 +99,7 @@ struct SweepTask {
                     double mt_r, const HllcPar& hp, bool wall)
     {
         if (RIEMANN == 1) return cgf(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp, wall);
+        if (RIEMANN == 2) return hllc_lm(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp);
         return hllc(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp);
     }
 

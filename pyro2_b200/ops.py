@@ -102,7 +102,7 @@ def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, u
     sponge: (rho_begin, rho_full, timescale) or None"""
     sp = sponge or (0.0, 0.0, 1.0)
     return _lib.CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi,
-                           grav, src_flip_ylo, src_flip_yhi, {"HLLC": 0, "CGF": 1}[riemann], xl_solid, yl_solid,
+                           grav, src_flip_ylo, src_flip_yhi, {"HLLC": 0, "CGF": 1, "HLLC_lm": 2}[riemann], xl_solid, yl_solid,
                            heat_rate, None if heat_profile is None else heat_profile.data_ptr(),
                            int(sponge is not None), sp[0], sp[1], sp[2], src_copy_yhi)
 

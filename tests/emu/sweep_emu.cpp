@@ -85,7 +85,10 @@ void* lane_main(void* p)
     LaneCtx* c = (LaneCtx*)p;
     EmuWarp w{c->ws, c->lane};
     auto go = [&](auto& T) { for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips); };
-    if (c->riemann == 1) {
+    if (c->riemann == 2) {
+        if (c->grav) { pyro::SweepTask<EmuWarp, true, 2> T(w, *c->A, *c->smem, 0u); go(T); }
+        else { pyro::SweepTask<EmuWarp, false, 2> T(w, *c->A, *c->smem, 0u); go(T); }
+    } else if (c->riemann == 1) {
         if (c->grav) { pyro::SweepTask<EmuWarp, true, 1> T(w, *c->A, *c->smem, 0u); go(T); }
         else { pyro::SweepTask<EmuWarp, false, 1> T(w, *c->A, *c->smem, 0u); go(T); }
     } else {

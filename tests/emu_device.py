@@ -88,7 +88,7 @@ class EmuLibrary:
         """p2b_compressible_sweep (sweep.cu) over the warp emulator: same argument checks that matter here, same
         work decomposition rule, same scratch words (wave-speed maxima in [0], [1], status in [3])"""
         g, p = g_ref._obj, prm_ref._obj
-        if uin == uout or g.ng < 4 or g.pitch % 2 or g.pitch < g.ny + 2 * g.ng or p.riemann not in (0, 1):
+        if uin == uout or g.ng < 4 or g.pitch % 2 or g.pitch < g.ny + 2 * g.ng or p.riemann not in (0, 1, 2):
             return -1
         nstrips = (g.ny + SW_OUT - 1) // SW_OUT
         seglen = _choose_seglen(g.nx, nstrips, RESIDENT_WARPS)

@@ -241,6 +241,8 @@ if __name__ == "__main__":
     comp_case("bubble32", "bubble", {"mesh.nx": 32, "mesh.ny": 64, "mesh.ymax": 4.0}, 25)
     comp_case("rt16", "rt", {"mesh.nx": 16, "mesh.ny": 48}, 25)
     comp_case("hse16", "hse", {"mesh.nx": 16, "mesh.ny": 48}, 20)
+    comp_case("gresho40_lm", "gresho", {"compressible.riemann": "HLLC_lm"}, 15)
+    comp_case("sedov32_lm", "sedov", {"mesh.nx": 32, "mesh.ny": 32, "sedov.r_init": 0.1, "compressible.riemann": "HLLC_lm"}, 30)
     comp_case("ramp64", "ramp", {"mesh.nx": 64, "mesh.ny": 16}, 30)
     comp_case("rt2_48", "rt2", {"mesh.nx": 48, "mesh.ny": 48, "rt2.sigma": 0.1}, 25)
     comp_case("rt_multimode16", "rt_multimode", {"mesh.nx": 16, "mesh.ny": 48}, 25)

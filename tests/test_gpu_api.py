@@ -92,7 +92,7 @@ def test_compressible_unit_assertions():
 
 def test_unsupported_configurations_fail_loudly():
     from pyro2_b200.pyro_sim import Pyro
-    for key, val in (("compressible.riemann", "HLLC_lm"), ("particles.do_particles", 1), ("mesh.ylboundary", "sliding-wall")):
+    for key, val in (("compressible.riemann", "Roe"), ("particles.do_particles", 1), ("mesh.ylboundary", "sliding-wall")):
         p = Pyro("compressible")
         with pytest.raises(SystemExit):
             p.initialize_problem("sedov", inputs_dict={key: val})

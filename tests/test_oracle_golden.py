@@ -68,7 +68,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
                                   "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
-                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16", "ramp64"])
+                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16", "ramp64", "gresho40_lm", "sedov32_lm"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
