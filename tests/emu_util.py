@@ -1,6 +1,8 @@
 """Shared helpers of the emulator-based CPU tests: build / load the host-compiled kernel libraries
 (tests/emu/) and drive them through the product's own ctypes signatures.  TEST INFRASTRUCTURE ONLY."""
+import contextlib
 import ctypes as C
+import fcntl
 import math
 import os
 import subprocess
@@ -16,16 +18,35 @@ BC = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichle
 _LIBS = {}
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """several test processes (multi-rank gloo tests, xdist workers) may find the same library stale at the same
+    time: one builds, the others wait and then find it fresh"""
+    with open(os.path.join(EMU_DIR, ".build.lock"), "w") as fh:
+        fcntl.flock(fh, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(fh, fcntl.LOCK_UN)
+
+
+def _build(so, deps, cmd, cwd=None):
+    with _build_lock():
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            tmp = so + f".{os.getpid()}.tmp"
+            subprocess.check_call([c if c != so else tmp for c in cmd], cwd=cwd)
+            os.replace(tmp, so)
+
+
 def _load(kind, sources, prefix, extra=()):
     if kind in _LIBS:
         return _LIBS[kind]
     so = os.path.join(EMU_DIR, f"lib{kind}_emu.so")
     deps = [os.path.join(EMU_DIR, f) for f in (f"{kind}_emu.cpp", "cuda_emu.h", "cuda_emu_runtime.inc")] + \
            [os.path.join(CSRC, f) for f in sources + ["hydro_core.cuh", "common.cuh"]]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-x", "c++", "-DP2B_EMU_HEADER=\"../../tests/emu/cuda_emu.h\"", *extra,
-                               "-o", so, os.path.join(EMU_DIR, f"{kind}_emu.cpp")], cwd=EMU_DIR)
+    _build(so, deps, ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                      "-x", "c++", "-DP2B_EMU_HEADER=\"../../tests/emu/cuda_emu.h\"", *extra,
+                      "-o", so, os.path.join(EMU_DIR, f"{kind}_emu.cpp")], cwd=EMU_DIR)
     lib = C.CDLL(so)
     from pyro2_b200 import _lib
     for name, (res, args) in _lib.SIGNATURES.items():
@@ -59,9 +80,8 @@ def load_sweep_emu():
     so = os.path.join(EMU_DIR, "libsweep_emu.so")
     src = os.path.join(EMU_DIR, "sweep_emu.cpp")
     hdrs = [os.path.join(CSRC, h) for h in ("sweep_task.cuh", "hydro_core.cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
+    _build(so, [src] + hdrs, ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                              "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
     lib = C.CDLL(so)
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
                                            [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +

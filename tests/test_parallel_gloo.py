@@ -3,6 +3,7 @@ single-domain ghost rows, including the periodic wrap and the 2-rank case where 
 the same peer; allreduce_max_ gives the global wave-speed maxima."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -85,3 +86,124 @@ def test_decomposition_rules():
     g = Cartesian2d(24, 8, ng=4, xmax=3.0, device="cpu")
     s = Cartesian2d(6, 8, ng=4, xmax=3.0, device="cpu", nx_global=24, ioffset=12)
     assert s.dx == g.dx and np.array_equal(s.x[4:10], g.x[16:22]) and np.array_equal(s.xl, g.xl[12:26])
+
+
+def _emulated_run_worker(rank, size, port, problem, nx, ny, nsteps, q):
+    """the body of tests/multi_gpu_worker.py on the emulated device over gloo: a decomposed Pyro("compressible") run,
+    slabs gathered on rank 0 and compared with the single-domain run bit for bit (state and every dt)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        import emu_device
+        from pyro2_b200.parallel import SlabDecomposition
+        from pyro2_b200.pyro_sim import Pyro
+        inputs = {"mesh.nx": nx, "mesh.ny": ny, "driver.max_steps": 10 ** 6, "driver.tmax": 1e9, "driver.verbose": 0}
+        if problem == "sedov":
+            inputs["sedov.r_init"] = 0.15
+        with emu_device.emulated_device() as dev:
+            p = Pyro("compressible")
+            p.initialize_problem(problem, inputs_dict=inputs, decomposition=SlabDecomposition())
+            dts = []
+            for _ in range(nsteps):
+                p.single_step()
+                dts.append(p.sim.dt)
+            p.sim.check_state()
+            g = p.sim.cc_data.grid
+            assert g.nx == nx // size and dev.calls["p2b_compressible_sweep"] == nsteps
+            mine = p.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].contiguous()
+            parts = [torch.empty_like(mine) for _ in range(size)] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            ok = True
+            if rank == 0:
+                full = torch.cat(parts, dim=1).numpy()
+                s = Pyro("compressible")
+                s.initialize_problem(problem, inputs_dict=inputs)
+                dts1 = []
+                for _ in range(nsteps):
+                    s.single_step()
+                    dts1.append(s.sim.dt)
+                g1 = s.sim.cc_data.grid
+                one = s.sim.cc_data.planes[:, g1.ilo:g1.ihi + 1, g1.jlo:g1.jhi + 1].numpy()
+                ok = bool(np.array_equal(full, one)) and dts == dts1
+        dist.barrier()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("problem,nx,ny,nsteps,size", [("sedov", 32, 16, 4, 2), ("kh", 24, 16, 3, 2), ("quad", 24, 12, 3, 3)])
+def test_decomposed_run_is_bit_identical_on_emulated_device(problem, nx, ny, nsteps, size):
+    """the N > 1 product path end to end without a GPU: SlabDecomposition + halo exchange over gloo, the sweep / ghost
+    fill / CFL kernels through the host-compiled libraries (tests/emu_device.py).  periodic (kh) and physical
+    (sedov, quad) x boundaries; the all-reduced time step must agree on every rank and with the single-domain run"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emulated_run_worker, args=(r, size, port, problem, nx, ny, nsteps, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(size))
+    assert res == {r: True for r in range(size)}
+
+
+def _emulated_mg_worker(rank, size, port, kind, n, split, q):
+    """the body of tests/multi_gpu_mg_worker.py on the emulated device over gloo: x-slab multigrid (deep-halo exchange
+    per blocked-smoother pass, replicated coarse levels) against the single-domain solve, bit for bit"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "oracle")]
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        import emu_device
+        from multi_gpu_mg_worker import rhs
+        from pyro2_b200.multigrid import MG
+        from pyro2_b200.parallel import SlabDecomposition
+        bc = {"dirichlet": ("dirichlet",) * 4, "periodic": ("periodic",) * 4,
+              "mixed": ("neumann", "dirichlet", "dirichlet", "neumann")}[kind]
+        kw = dict(xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3])
+        if kind == "mixed":
+            kw.update(alpha=1.0, beta=0.05)
+        with emu_device.emulated_device():
+            a = MG.CellCenterMG2d(n, n, decomposition=SlabDecomposition(), split_n=split, **kw)
+            a.init_zeros()
+            a.init_RHS(rhs(kind, a.x2d.t(), a.y2d.t()))
+            a.solve(rtol=1.e-11)
+            g = a.soln_grid
+            mine = a.get_solution().t()[g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].contiguous()
+            parts = [torch.empty_like(mine) for _ in range(size)] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            ok = True
+            if rank == 0:
+                full = torch.cat(parts, dim=0).numpy()
+                b = MG.CellCenterMG2d(n, n, **kw)
+                b.init_zeros()
+                b.init_RHS(rhs(kind, b.x2d.t(), b.y2d.t()))
+                b.solve(rtol=1.e-11)
+                one = b.get_solution().numpy()[1:-1, 1:-1]
+                ok = bool(np.array_equal(full, one)) and a.num_cycles == b.num_cycles
+        dist.barrier()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,n,split,size", [("dirichlet", 128, 32, 2), ("periodic", 128, 64, 2), ("mixed", 128, 64, 2)])
+def test_decomposed_multigrid_is_bit_identical_on_emulated_device(kind, n, split, size):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emulated_mg_worker, args=(r, size, port, kind, n, split, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(size))
+    assert res == {r: True for r in range(size)}
