@@ -8,11 +8,14 @@ from ..simulation_null import NullSimulation, bc_setup, grid_setup
 
 class Simulation(NullSimulation):
     def initialize(self):
-        my_grid = grid_setup(self.rp, ng=4)
+        # decomposition (extension, as in the compressible solver): this rank owns an x-slab; the update's stencil
+        # fits in the ng = 4 halo rows that fill_BC_all exchanges, and dt is analytic, so nothing else changes
+        my_grid = grid_setup(self.rp, ng=4, decomposition=self.decomposition)
         my_data = self.data_class(my_grid)
         bc = bc_setup(self.rp)[0]
         my_data.register_var("density", bc)
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
         _no_particles(self.rp)
         self._flow = FlowHandle(my_data.planes, my_grid)

@@ -1,6 +1,8 @@
 """Burgers solver front end: pyro/burgers/simulation.py (Simulation :12-131) with the interface-state
 construction, Riemann / upwinding, flux differencing and the CFL reduction executed by the p2b_flow_*
 kernels.  u_t + u u_x + v u_y = 0, v_t + u v_x + v v_y = 0."""
+import torch
+
 from ..flow_handle import FlowHandle
 from ..simulation_null import NullSimulation, bc_setup, grid_setup
 from ..util import msg
@@ -20,12 +22,14 @@ class Simulation(NullSimulation):
 
     def initialize(self):
         """grid, the two velocities, their BCs, problem initial conditions (burgers/simulation.py:14-39)"""
-        my_grid = grid_setup(self.rp, ng=4)
+        # decomposition (extension, as in the compressible solver): this rank owns an x-slab with ng = 4 halo rows
+        my_grid = grid_setup(self.rp, ng=4, decomposition=self.decomposition)
         my_data = self.data_class(my_grid)
         bc = bc_setup(self.rp)[0]
         my_data.register_var("x-velocity", bc)
         my_data.register_var("y-velocity", bc)
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
         _no_particles(self.rp)
         self._make_flow()
@@ -42,6 +46,10 @@ class Simulation(NullSimulation):
         g = self.cc_data.grid
         u, v = self._velocities()
         umax, vmax = self._flow.maxabs(u[:, :g.qy], v[:, :g.qy])
+        if self.decomposition is not None and self.decomposition.size > 1:
+            # the slabs with their halo rows and physical ghost cells cover the global array exactly
+            w = torch.tensor([umax, vmax], dtype=torch.float64, device=u.device)
+            umax, vmax = self.decomposition.allreduce_max_(w).tolist()
         xtmp = g.dx / max(umax, self.SMALL)
         ytmp = g.dy / max(vmax, self.SMALL)
         self.dt = cfl * min(xtmp, ytmp)

@@ -81,6 +81,8 @@ SOLVER = {
         "driver.cfl": (0.8, ""),
         "incompressible.limiter": (2, "0 none, 1 second-order MC, 2 fourth-order MC"),
         "incompressible.proj_type": (2, "what is projected: 1 includes the -Gp term in U*"),
+        "incompressible.mg_split_n": (1024, "multi-GPU runs (extension): multigrid levels with at least this many columns "
+                                            "are split into x-slabs, coarser ones are replicated"),
         "particles.do_particles": (0, "not supported"),
         "particles.particle_generator": ("grid", ""),
     },

@@ -28,7 +28,10 @@ from ..util import msg
 
 class Simulation(burgers_simulation):
     def initialize(self, *, other_bc=False, aux_vars=()):
-        my_grid = grid_setup(self.rp, ng=4)
+        # decomposition (extension): this rank owns an x-slab with ng = 4 halo rows; every fill_BC then exchanges the
+        # halo rows first, the projections run on the x-slab multigrid (bit-identical to the single-domain solver)
+        # and the time step is all-reduced -- the stage kernels themselves are unchanged
+        my_grid = grid_setup(self.rp, ng=4, decomposition=self.decomposition)
         my_data = self.data_class(my_grid)
         if other_bc:
             self.define_other_bc()
@@ -48,6 +51,7 @@ class Simulation(burgers_simulation):
         for keyword, value in aux_vars:
             my_data.set_aux(keyword=keyword, value=value)
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
         _no_particles(self.rp)
         self._make_flow()
@@ -70,8 +74,14 @@ class Simulation(burgers_simulation):
         key = tuple(bc_types)
         if key not in self._mg:
             g = self.cc_data.grid
-            mg = MG.CellCenterMG2d(g.nx, g.ny, xl_BC_type=key[0], xr_BC_type=key[1], yl_BC_type=key[2],
-                                   yr_BC_type=key[3], xmin=g.xmin, xmax=g.xmax, ymin=g.ymin, ymax=g.ymax, verbose=0)
+            split = {}
+            if self.decomposition is not None and self.decomposition.size > 1:
+                split = {"decomposition": self.decomposition, "split_n": self.rp.get_param("incompressible.mg_split_n")}
+            mg = MG.CellCenterMG2d(g.nx_global, g.ny, xl_BC_type=key[0], xr_BC_type=key[1], yl_BC_type=key[2],
+                                   yr_BC_type=key[3], xmin=g.xmin, xmax=g.xmax, ymin=g.ymin, ymax=g.ymax, verbose=0,
+                                   **split)
+            if mg.soln_grid.nx != g.nx:
+                msg.fail("ERROR: the finest multigrid level must be split like the solver grid (lower incompressible.mg_split_n)")
             self._mg[key] = (mg, mg.soln_grid.scratch_array())
         return self._mg[key]
 

@@ -43,3 +43,21 @@ def test_decomposed_multigrid_is_bit_identical(kind, n, split):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "bit_identical=True" in res.stdout
+
+
+@pytest.mark.parametrize("solver,problem,nx,ny,nsteps,extra", [
+    ("advection", "smooth", 256, 256, 20, []), ("burgers", "test", 256, 128, 20, []),
+    ("incompressible", "shear", 256, 256, 3, ["incompressible.mg_split_n=128"])])
+def test_decomposed_flow_solvers_are_bit_identical(solver, problem, nx, ny, nsteps, extra):
+    """advection / burgers (explicit stages on x-slabs, all-reduced dt) and the incompressible solver (plus two
+    x-slab multigrid projections per step) against the single-GPU run"""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29613",
+           os.path.join(HERE, "multi_gpu_flow_worker.py"), solver, problem, str(nx), str(ny), str(nsteps)] + extra
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "bit_identical=True" in res.stdout and "dt_identical=True" in res.stdout

@@ -207,3 +207,70 @@ def test_decomposed_multigrid_is_bit_identical_on_emulated_device(kind, n, split
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(size))
     assert res == {r: True for r in range(size)}
+
+
+def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
+    """a decomposed Pyro(solver) run of the explicit-stage solvers (advection, burgers) or the incompressible
+    solver (explicit stages + two x-slab multigrid projections per step) on the emulated device over gloo; every
+    state plane gathered on rank 0 and compared with the single-domain run bit for bit, and every dt"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "oracle")]
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        import emu_device
+        from pyro2_b200.parallel import SlabDecomposition
+        from pyro2_b200.pyro_sim import Pyro
+        inputs = dict(inputs, **{"driver.max_steps": 10 ** 6, "driver.tmax": 1e9, "driver.verbose": 0})
+        with emu_device.emulated_device():
+            p = Pyro(solver)
+            p.initialize_problem(problem, inputs_dict=inputs, decomposition=SlabDecomposition())
+            dts = []
+            for _ in range(nsteps):
+                p.single_step()
+                dts.append(p.sim.dt)
+            g = p.sim.cc_data.grid
+            assert g.nx == inputs["mesh.nx"] // size
+            mine = p.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].contiguous()
+            parts = [torch.empty_like(mine) for _ in range(size)] if rank == 0 else None
+            dist.gather(mine, parts, dst=0)
+            ok = True
+            if rank == 0:
+                full = torch.cat(parts, dim=1).numpy()
+                s = Pyro(solver)
+                s.initialize_problem(problem, inputs_dict=inputs)
+                dts1 = []
+                for _ in range(nsteps):
+                    s.single_step()
+                    dts1.append(s.sim.dt)
+                g1 = s.sim.cc_data.grid
+                one = s.sim.cc_data.planes[:, g1.ilo:g1.ihi + 1, g1.jlo:g1.jhi + 1].numpy()
+                ok = bool(np.array_equal(full, one)) and dts == dts1
+                if not ok:
+                    print("MISMATCH", solver, problem, np.abs(full - one).max(axis=(1, 2)), dts, dts1, flush=True)
+        dist.barrier()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("solver,problem,inputs,nsteps,size", [
+    ("advection", "smooth", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),
+    ("advection", "tophat", {"mesh.nx": 36, "mesh.ny": 24, "advection.u": -0.6, "advection.limiter": 1}, 5, 3),
+    ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
+    ("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3),                # periodic
+    ("incompressible", "shear", {"mesh.nx": 128, "mesh.ny": 128, "incompressible.mg_split_n": 64}, 1, 2)])
+def test_decomposed_flow_solvers_are_bit_identical_on_emulated_device(solver, problem, inputs, nsteps, size):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emulated_flow_worker, args=(r, size, port, solver, problem, inputs, nsteps, q))
+             for r in range(size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(900)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(size))
+    assert res == {r: True for r in range(size)}
