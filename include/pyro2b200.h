@@ -190,7 +190,8 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out_dev, void* 
  * (1 - dt k/2 L) phi^{n+1} = phi^n + dt k/2 L phi^n).  p2b_mg_set_operator changes alpha / beta of an existing
  * hierarchy (the reference constructs a new CellCenterMG2d with beta = 0.5*dt*k every step);
  * p2b_mg_cn_rhs writes the right-hand side into the finest level's f plane from the solver's ghost-filled
- * phi plane ((n+2) rows of phi_pitch doubles), coef = 0.5*dt*k; bit-identical to the reference's expression. */
+ * phi plane ((n+2) rows of phi_pitch doubles; on a decomposed hierarchy this rank's slab, ni+2 rows with the halo rows
+ * already exchanged), coef = 0.5*dt*k; bit-identical to the reference's expression. */
 int p2b_mg_set_operator(p2b_mg* m, double alpha, double beta);
 int p2b_mg_cn_rhs(p2b_mg* m, const double* phi, int phi_pitch, double coef, void* stream);
 

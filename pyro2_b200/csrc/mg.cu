@@ -641,7 +641,7 @@ int p2b_mg_set_operator(p2b_mg* m, double alpha, double beta)
 int p2b_mg_cn_rhs(p2b_mg* m, const double* phi, int phi_pitch, double coef, void* stream)
 {
     P2B_REQUIRE(m && m->base && phi, "null pointer");
-    P2B_REQUIRE(m->size == 1, "single-GPU hierarchies only");
+    // on a decomposed hierarchy phi is this rank's slab: L.ni + 2 rows, halo rows already exchanged by the caller
     const MgLevel& L = m->lev[m->nlevels - 1];
     P2B_REQUIRE(phi_pitch >= L.n + 2, "phi_pitch too small");
     dim3 blk(64, 4);

@@ -63,6 +63,8 @@ SOLVER = {
     "diffusion": {
         "driver.cfl": (0.8, "diffusion CFL number (may exceed 1: the update is implicit)"),
         "diffusion.k": (1.0, "conductivity"),
+        "diffusion.mg_split_n": (1024, "multi-GPU runs (extension): multigrid levels with at least this many columns "
+                                       "are split into x-slabs, coarser ones are replicated"),
     },
     "lm_atm": {
         "driver.cfl": (0.8, ""),

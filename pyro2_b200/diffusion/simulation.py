@@ -14,11 +14,12 @@ from ..util import msg
 
 class Simulation(NullSimulation):
     def initialize(self):
-        my_grid = grid_setup(self.rp, ng=1)
-        if my_grid.nx != my_grid.ny:
+        # decomposition (extension): this rank owns an x-slab; the solve runs on the x-slab multigrid
+        my_grid = grid_setup(self.rp, ng=1, decomposition=self.decomposition)
+        if my_grid.nx_global != my_grid.ny:
             msg.fail("need nx = ny for diffusion problems")
-        n = int(np.log(my_grid.nx) / np.log(2.0))
-        if 2 ** n != my_grid.nx and my_grid.nx & (my_grid.nx - 1):
+        n = int(np.log(my_grid.nx_global) / np.log(2.0))
+        if 2 ** n != my_grid.nx_global and my_grid.nx_global & (my_grid.nx_global - 1):
             msg.fail("grid needs to be a power of 2")
         bc, _, _ = bc_setup(self.rp)
         for b in (bc.xlb, bc.xrb, bc.ylb, bc.yrb):
@@ -27,6 +28,7 @@ class Simulation(NullSimulation):
         my_data = self.data_class(my_grid)
         my_data.register_var("phi", bc)
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
         self._mg = None
         self.problem_func(self.cc_data, self.rp)
@@ -47,9 +49,14 @@ class Simulation(NullSimulation):
         b = self.cc_data.BCs["phi"]
         beta = 0.5 * self.dt * k
         if self._mg is None:
-            self._mg = MG.CellCenterMG2d(g.nx, g.ny, xmin=g.xmin, xmax=g.xmax, ymin=g.ymin, ymax=g.ymax,
+            split = {}
+            if self.decomposition is not None and self.decomposition.size > 1:
+                split = {"decomposition": self.decomposition, "split_n": self.rp.get_param("diffusion.mg_split_n")}
+            self._mg = MG.CellCenterMG2d(g.nx_global, g.ny, xmin=g.xmin, xmax=g.xmax, ymin=g.ymin, ymax=g.ymax,
                                          xl_BC_type=b.xlb, xr_BC_type=b.xrb, yl_BC_type=b.ylb, yr_BC_type=b.yrb,
-                                         alpha=1.0, beta=beta, verbose=0)
+                                         alpha=1.0, beta=beta, verbose=0, **split)
+            if self._mg.soln_grid.nx != g.nx:
+                msg.fail("ERROR: the finest multigrid level must be split like the solver grid (lower diffusion.mg_split_n)")
         mg = self._mg
         mg.set_operator(1.0, beta)
         mg.init_RHS_crank_nicolson(phi, beta)

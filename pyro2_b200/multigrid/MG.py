@@ -209,6 +209,8 @@ class CellCenterMG2d:
         (diffusion/simulation.py:87-93)"""
         self._h.cn_rhs(phi, coef)
         self.source_norm = self._norm(self.nlevels - 1, "f")
+        if self._decomp is not None:
+            self._h.exchange(self.nlevels - 1, "f", self._h.tb_halo)   # halo cells need f too (as in init_RHS)
         self.initialized_rhs = 1
 
     def _norm(self, level, which):

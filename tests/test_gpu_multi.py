@@ -47,6 +47,7 @@ def test_decomposed_multigrid_is_bit_identical(kind, n, split):
 
 @pytest.mark.parametrize("solver,problem,nx,ny,nsteps,extra", [
     ("advection", "smooth", 256, 256, 20, []), ("burgers", "test", 256, 128, 20, []),
+    ("diffusion", "gaussian", 256, 256, 5, ["diffusion.mg_split_n=128"]),
     ("incompressible", "shear", 256, 256, 3, ["incompressible.mg_split_n=128"])])
 def test_decomposed_flow_solvers_are_bit_identical(solver, problem, nx, ny, nsteps, extra):
     """advection / burgers (explicit stages on x-slabs, all-reduced dt) and the incompressible solver (plus two

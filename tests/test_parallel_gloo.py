@@ -260,6 +260,7 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
     ("advection", "tophat", {"mesh.nx": 36, "mesh.ny": 24, "advection.u": -0.6, "advection.limiter": 1}, 5, 3),
     ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
     ("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3),                # periodic
+    ("diffusion", "gaussian", {"mesh.nx": 128, "mesh.ny": 128, "diffusion.mg_split_n": 64}, 2, 2),
     ("incompressible", "shear", {"mesh.nx": 128, "mesh.ny": 128, "incompressible.mg_split_n": 64}, 1, 2)])
 def test_decomposed_flow_solvers_are_bit_identical_on_emulated_device(solver, problem, inputs, nsteps, size):
     ctx = mp.get_context("spawn")
