@@ -55,6 +55,8 @@ class Simulation(NullSimulation):
         self.in_preevolve = False
 
     def initialize(self):
+        if self.decomposition is not None and self.decomposition.size > 1:
+            msg.fail("ERROR: lm_atm runs on one GPU (the variable-coefficient multigrid is not decomposed)")
         myg = grid_setup(self.rp, ng=4)
         bc_dens, bc_xodd, bc_yodd = bc_setup(self.rp)
         my_data = self.data_class(myg)
