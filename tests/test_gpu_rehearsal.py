@@ -1,0 +1,67 @@
+"""CPU: a fast subset of the `-m gpu` tests, their bodies run unchanged on the emulated device (tests/emu_device.py:
+the product's Python layer over the host-compiled kernel libraries).  One case per GPU test function that finishes
+in seconds here; `python tests/rehearse.py test_gpu_api test_gpu_flow test_gpu_hydro test_gpu_mg test_gpu_zz_problems`
+rehearses every case (about 40 minutes on 8 cores; all of them passed at the end of round 1).
+
+What this buys: a GPU test that breaks because of host-side logic (a stale expectation, parameter plumbing, a
+boundary hook, a problem setup) or kernel indexing fails here first, where there is no GPU budget to lose."""
+import pytest
+
+import rehearse
+
+# (module, test function, substring selecting the parametrised case or None)
+SUBSET = [
+    ("test_gpu_api", "test_pyro_compressible_run_matches_reference", "[rt16]"),            # gravity + hse boundaries
+    ("test_gpu_api", "test_pyro_run_sim_and_accessors", None),
+    ("test_gpu_api", "test_compressible_unit_assertions", None),
+    ("test_gpu_api", "test_unsupported_configurations_fail_loudly", None),
+    ("test_gpu_api", "test_mg_solve_matches_reference", "helmholtz_neumann_64"),
+    ("test_gpu_api", "test_mg_inhomogeneous_dirichlet_matches_reference", None),
+    ("test_gpu_api", "test_mg_variable_coeff_solve_matches_reference", "constant_32"),
+    ("test_gpu_api", "test_mg_variable_coeff_argument_errors", None),
+    ("test_gpu_api", "test_mg_gradient_known_answer", None),
+    ("test_gpu_api", "test_mg_subclass_hooks_are_used", None),
+    ("test_gpu_api", "test_mg_argument_errors", None),
+    ("test_gpu_api", "test_cellcenterdata_fill_bc_matches_reference_fixture", None),
+    ("test_gpu_api", "test_user_defined_bc_callback_runs_after_standard_fill", None),
+    ("test_gpu_flow", "test_flow_stages_bit_exact", "[16-16-2]"),
+    ("test_gpu_flow", "test_pyro_burgers_run_matches_reference", None),
+    ("test_gpu_flow", "test_pyro_advection_run_matches_reference", "tophat32"),
+    ("test_gpu_flow", "test_pyro_diffusion_run_matches_reference", "gaussian32_mixed"),
+    ("test_gpu_flow", "test_incompressible_rejects_unsupported_boundaries", None),
+    ("test_gpu_hydro", "test_fill_ghost_mixed_per_variable", None),
+    ("test_gpu_hydro", "test_cfl_dt_bit_exact", "shock-100-37"),
+    ("test_gpu_hydro", "test_sweep_one_step", "shock-20-20-0-0"),
+    ("test_gpu_hydro", "test_sweep_invalid_state_flag", None),
+    ("test_gpu_hydro", "test_sweep_rejects_bad_arguments", None),
+    ("test_gpu_mg", "test_smooth_residual_bit_exact", "[16-"),
+    ("test_gpu_mg", "test_restrict_prolong_bit_exact", "[4-"),
+    ("test_gpu_mg", "test_vcycle_bit_exact", "[8-"),
+    ("test_gpu_zz_problems", "test_pyro_burgers_problems_match_reference", "converge32"),
+    ("test_gpu_zz_problems", "test_pyro_burgers_problems_match_reference", "tophat32"),
+]
+
+
+def _find(module, name, pick):
+    for ident, fn, kw in rehearse.cases(module):
+        if ident.split("[")[0] == name and (pick is None or pick in ident):
+            return fn, kw
+    raise LookupError(f"{module}::{name} {pick}: no such case (was the GPU test renamed?)")
+
+
+@pytest.mark.parametrize("module,name,pick", SUBSET, ids=[f"{m}::{n}{p or ''}" for m, n, p in SUBSET])
+def test_gpu_test_body_on_emulated_device(module, name, pick):
+    fn, kw = _find(module, name, pick)
+    calls = rehearse.run_case(fn, kw)
+    assert isinstance(calls, dict)
+
+
+def test_every_gpu_test_function_is_enumerated():
+    """the enumeration sees the parametrisation of the GPU test modules (a rename or a new fixture argument that the
+    rehearsal cannot supply shows up here)"""
+    import inspect
+    for module in ("test_gpu_api", "test_gpu_flow", "test_gpu_hydro", "test_gpu_mg", "test_gpu_zz_problems"):
+        cs = rehearse.cases(module)
+        assert cs
+        for ident, fn, kw in cs:
+            assert set(inspect.signature(fn).parameters) == set(kw), ident
