@@ -166,6 +166,13 @@ typedef struct {
     double *Fx, *Fy;                               /* final fluxes incl. artificial viscosity */
 } orc_comp_stages;
 
+
+/* max / min with the semantics of Python's built-ins, which numba compiles the reference's scalar max() / min()
+ * calls to: the SECOND argument wins only if it compares greater (less), so max(a, nan) = a and max(nan, b) = nan
+ * (C's fmax / fmin would return the non-NaN operand in both cases).  It matters where the reference feeds an
+ * unphysical interface state to a Riemann solver -- c = max(smallc, sqrt(negative)) = smallc -- and carries on. */
+static inline double pymax(double a, double b) { return b > a ? b : a; }
+static inline double pymin(double a, double b) { return b < a ? b : a; }
 static double *zalloc(size_t n) { return (double *)calloc(n, sizeof(double)); }
 
 /* simulation.py:49-80 */
@@ -226,12 +233,12 @@ static void flatten1d(const double *q, double *xi, int qx, int qy, int ng, int i
                 t1 = fabs(p[IDX(i + di, j + dj)] - p[IDX(i - di, j - dj)]);
                 t2 = fabs(p[IDX(i + 2 * di, j + 2 * dj)] - p[IDX(i - 2 * di, j - 2 * dj)]);
             }
-            double z = t1 / fmax(t2, smallp);
+            double z = t1 / pymax(t2, smallp);
             if (in) {
-                t2b = t1 / fmin(p[IDX(i + di, j + dj)], p[IDX(i - di, j - dj)]);
+                t2b = t1 / pymin(p[IDX(i + di, j + dj)], p[IDX(i - di, j - dj)]);
                 t1b = un[IDX(i - di, j - dj)] - un[IDX(i + di, j + dj)];
             }
-            double x = fmin(1.0, fmax(0.0, 1.0 - (z - z0) / (z1 - z0)));
+            double x = pymin(1.0, pymax(0.0, 1.0 - (z - z0) / (z1 - z0)));
             xi[IDX(i, j)] = (t1b > 0.0 && t2b > delta) ? x : 1.0;
         }
 }
@@ -248,7 +255,7 @@ static void flatten_multid(const double *q, const double *xi_x, const double *xi
         for (int j = ng - 2; j <= qy - ng + 1; j++) {
             double px = (p[IDX(i + 1, j)] - p[IDX(i - 1, j)] > 0) ? xi_x[IDX(i - 1, j)] : xi_x[IDX(i + 1, j)];
             double py = (p[IDX(i, j + 1)] - p[IDX(i, j - 1)] > 0) ? xi_y[IDX(i, j - 1)] : xi_y[IDX(i, j + 1)];
-            xi[IDX(i, j)] = fmin(fmin(xi_x[IDX(i, j)], px), fmin(xi_y[IDX(i, j)], py));
+            xi[IDX(i, j)] = pymin(pymin(xi_x[IDX(i, j)], px), pymin(xi_y[IDX(i, j)], py));
         }
 }
 
@@ -321,10 +328,10 @@ static void trace_states(int idir, const double *qv, const double *dqv, double *
             rvec[2][it] = 1.0;
             rvec[3][IRHO] = 1.0; rvec[3][in] = cs / q[IRHO];  rvec[3][IP] = cs * cs;
 
-            double factor = 0.5 * (1.0 - dtdx * fmax(e_val[3], 0.0));
+            double factor = 0.5 * (1.0 - dtdx * pymax(e_val[3], 0.0));
             double ql[4], qr[4];
             for (int m = 0; m < 4; m++) ql[m] = q[m] + factor * dq[m];
-            factor = 0.5 * (1.0 + dtdx * fmin(e_val[0], 0.0));
+            factor = 0.5 * (1.0 + dtdx * pymin(e_val[0], 0.0));
             for (int m = 0; m < 4; m++) qr[m] = q[m] - factor * dq[m];
 
             for (int m = 0; m < 4; m++) {
@@ -347,7 +354,7 @@ static void estimate_wave_speed(double rho_l, double u_l, double p_l, double c_l
                                 double u_r, double p_r, double c_r, double gamma, double *S_l,
                                 double *S_r)
 {
-    double p_max = fmax(p_l, p_r), p_min = fmin(p_l, p_r);
+    double p_max = pymax(p_l, p_r), p_min = pymin(p_l, p_r);
     double Q = p_max / p_min;
     double rho_avg = 0.5 * (rho_l + rho_r), c_avg = 0.5 * (c_l + c_r);
     double factor = rho_avg * c_avg;
@@ -364,7 +371,7 @@ static void estimate_wave_speed(double rho_l, double u_l, double p_l, double c_l
         } else {
             double A_r = 2.0 / ((gamma + 1.0) * rho_r), B_r = p_r * (gamma - 1.0) / (gamma + 1.0);
             double A_l = 2.0 / ((gamma + 1.0) * rho_l), B_l = p_l * (gamma - 1.0) / (gamma + 1.0);
-            double p_guess = fmax(0.0, pstar);
+            double p_guess = pymax(0.0, pstar);
             double g_l = sqrt(A_l / (p_guess + B_l)), g_r = sqrt(A_r / (p_guess + B_r));
             pstar = (g_l * p_l + g_r * p_r - (u_r - u_l)) / (g_l + g_r);
             ustar = 0.5 * (u_l + u_r) + 0.5 * ((pstar - p_r) * g_r - (pstar - p_l) * g_l);
@@ -418,13 +425,13 @@ static void riemann_hllc(int idir, const double *U_l, const double *U_r, double 
             double rho_l = Ul[IDENS];
             double un_l = Ul[imn] / rho_l, ut_l = Ul[imt] / rho_l;
             double rhoe_l = Ul[IENER] - 0.5 * rho_l * (un_l * un_l + ut_l * ut_l);
-            double p_l = fmax(rhoe_l * (gamma - 1.0), smallp);
+            double p_l = pymax(rhoe_l * (gamma - 1.0), smallp);
             double rho_r = Ur[IDENS];
             double un_r = Ur[imn] / rho_r, ut_r = Ur[imt] / rho_r;
             double rhoe_r = Ur[IENER] - 0.5 * rho_r * (un_r * un_r + ut_r * ut_r);
-            double p_r = fmax(rhoe_r * (gamma - 1.0), smallp);
-            double c_l = fmax(smallc, sqrt(gamma * p_l / rho_l));
-            double c_r = fmax(smallc, sqrt(gamma * p_r / rho_r));
+            double p_r = pymax(rhoe_r * (gamma - 1.0), smallp);
+            double c_l = pymax(smallc, sqrt(gamma * p_l / rho_l));
+            double c_r = pymax(smallc, sqrt(gamma * p_r / rho_r));
             double S_l, S_r;
             estimate_wave_speed(rho_l, un_l, p_l, c_l, rho_r, un_r, p_r, c_r, gamma, &S_l, &S_r);
             double S_c = (p_r - p_l + rho_l * un_l * (S_l - un_l) - rho_r * un_r * (S_r - un_r)) /
@@ -473,24 +480,24 @@ static void riemann_cgf(int idir, const double *U_l, const double *U_r, double *
             const double rho_l = U_l[IDENS * np + k];
             const double un_l = U_l[imn * np + k] / rho_l, ut_l = U_l[imt * np + k] / rho_l;
             const double rhoe_l = U_l[IENER * np + k] - 0.5 * rho_l * (un_l * un_l + ut_l * ut_l);
-            const double p_l = fmax(rhoe_l * (gamma - 1.0), smallp);
+            const double p_l = pymax(rhoe_l * (gamma - 1.0), smallp);
             const double rho_r = U_r[IDENS * np + k];
             const double un_r = U_r[imn * np + k] / rho_r, ut_r = U_r[imt * np + k] / rho_r;
             const double rhoe_r = U_r[IENER * np + k] - 0.5 * rho_r * (un_r * un_r + ut_r * ut_r);
-            const double p_r = fmax(rhoe_r * (gamma - 1.0), smallp);
-            const double W_l = fmax(smallrho * smallc, sqrt(gamma * p_l * rho_l));
-            const double W_r = fmax(smallrho * smallc, sqrt(gamma * p_r * rho_r));
-            const double c_l = fmax(smallc, sqrt(gamma * p_l / rho_l));
-            const double c_r = fmax(smallc, sqrt(gamma * p_r / rho_r));
+            const double p_r = pymax(rhoe_r * (gamma - 1.0), smallp);
+            const double W_l = pymax(smallrho * smallc, sqrt(gamma * p_l * rho_l));
+            const double W_r = pymax(smallrho * smallc, sqrt(gamma * p_r * rho_r));
+            const double c_l = pymax(smallc, sqrt(gamma * p_l / rho_l));
+            const double c_r = pymax(smallc, sqrt(gamma * p_r / rho_r));
             double pstar = (W_l * p_r + W_r * p_l + W_l * W_r * (un_l - un_r)) / (W_l + W_r);
-            pstar = fmax(pstar, smallp);
+            pstar = pymax(pstar, smallp);
             const double ustar = (W_l * un_l + W_r * un_r + (p_l - p_r)) / (W_l + W_r);
             const double rhostar_l = rho_l + (pstar - p_l) / (c_l * c_l);
             const double rhostar_r = rho_r + (pstar - p_r) / (c_r * c_r);
             const double rhoestar_l = rhoe_l + (pstar - p_l) * (rhoe_l / rho_l + p_l / rho_l) / (c_l * c_l);
             const double rhoestar_r = rhoe_r + (pstar - p_r) * (rhoe_r / rho_r + p_r / rho_r) / (c_r * c_r);
-            const double cstar_l = fmax(smallc, sqrt(gamma * pstar / rhostar_l));
-            const double cstar_r = fmax(smallc, sqrt(gamma * pstar / rhostar_r));
+            const double cstar_l = pymax(smallc, sqrt(gamma * pstar / rhostar_l));
+            const double cstar_r = pymax(smallc, sqrt(gamma * pstar / rhostar_r));
             double rho_s, un_s, ut_s, rhoe_s;
             if (ustar > 0.0) {
                 ut_s = ut_l;
@@ -558,13 +565,13 @@ static void riemann_hllc_lowspeed(int idir, const double *U_l, const double *U_r
             double rho_l = Ul[IDENS];
             double un_l = Ul[imn] / rho_l, ut_l = Ul[imt] / rho_l;
             double rhoe_l = Ul[IENER] - 0.5 * rho_l * (un_l * un_l + ut_l * ut_l);
-            double p_l = fmax(rhoe_l * (gamma - 1.0), smallp);
+            double p_l = pymax(rhoe_l * (gamma - 1.0), smallp);
             double rho_r = Ur[IDENS];
             double un_r = Ur[imn] / rho_r, ut_r = Ur[imt] / rho_r;
             double rhoe_r = Ur[IENER] - 0.5 * rho_r * (un_r * un_r + ut_r * ut_r);
-            double p_r = fmax(rhoe_r * (gamma - 1.0), smallp);
-            double c_l = fmax(smallc, sqrt(gamma * p_l / rho_l));
-            double c_r = fmax(smallc, sqrt(gamma * p_r / rho_r));
+            double p_r = pymax(rhoe_r * (gamma - 1.0), smallp);
+            double c_l = pymax(smallc, sqrt(gamma * p_l / rho_l));
+            double c_r = pymax(smallc, sqrt(gamma * p_r / rho_r));
             double S_l, S_r;
             estimate_wave_speed(rho_l, un_l, p_l, c_l, rho_r, un_r, p_r, c_r, gamma, &S_l, &S_r);
             double S_c = (p_r - p_l + rho_l * un_l * (S_l - un_l) - rho_r * un_r * (S_r - un_r)) /
@@ -575,8 +582,8 @@ static void riemann_hllc_lowspeed(int idir, const double *U_l, const double *U_r
             cons_flux(idir, gamma, Ur, Fr);
             double vmag_l = sqrt(un_l * un_l + ut_l * ut_l);
             double vmag_r = sqrt(un_r * un_r + ut_r * ut_r);
-            double cs_max = fmax(c_l, c_r);
-            double chi = fmin(1.0, fmax(vmag_l, vmag_r) / cs_max);
+            double cs_max = pymax(c_l, c_r);
+            double chi = pymin(1.0, pymax(vmag_l, vmag_r) / cs_max);
             double phi = chi * (2.0 - chi);
             double pstar_lr = 0.5 * (p_l + p_r) +
                               0.5 * phi * (rho_l * (S_l - un_l) * (S_c - un_l) + rho_r * (S_r - un_r) * (S_c - un_r));
@@ -632,8 +639,8 @@ static void artificial_viscosity(const double *u, const double *v, double *ax, d
         for (int j = jlo; j < jend; j++) {
             double divU_x = 0.5 * (divU[IDX(i, j)] + divU[IDX(i, j + 1)]);
             double divU_y = 0.5 * (divU[IDX(i, j)] + divU[IDX(i + 1, j)]);
-            ax[IDX(i, j)] = cvisc * fmax(-divU_x * dx, 0.0);
-            ay[IDX(i, j)] = cvisc * fmax(-divU_y * dy, 0.0);
+            ax[IDX(i, j)] = cvisc * pymax(-divU_x * dx, 0.0);
+            ay[IDX(i, j)] = cvisc * pymax(-divU_y * dy, 0.0);
         }
     free(divU);
 }

@@ -207,3 +207,36 @@ def test_ramp_boundary_bit_identical():
             for side in ("xlb", "ylb", "yrb"):
                 oracle.fill_ramp(mine[k], k, side, g.ng, g.x, g.y, g.dx, g.dy, t, 1.4)
             assert np.array_equal(np.asarray(d.get_var(n)), mine[k]), (n, t)
+
+
+@pytest.mark.parametrize("riemann", ["HLLC", "CGF", "HLLC_lm"])
+def test_unphysical_interface_states_follow_the_reference(riemann):
+    """unlimited slopes (limiter 0) at a 10x density / pressure jump give interface states with negative density; the
+    reference's numba max(smallc, sqrt(negative)) is smallc (Python max semantics), so it carries on with finite
+    numbers.  The oracle (and the kernel, tests/test_sweep_emulated.py) must do the same, not propagate NaN."""
+    p = ref_shim.make_sim("compressible", "kh", {"mesh.nx": 8, "mesh.ny": 32, "compressible.limiter": 0,
+                                                 "compressible.use_flattening": 0, "compressible.cvisc": 0.0,
+                                                 "compressible.riemann": riemann, "driver.tmax": 10.0})
+    sim = p.sim
+    g = sim.cc_data.grid
+    rng = np.random.default_rng(135)
+    y = np.asarray(g.y)
+    dens = np.broadcast_to(1.5 * np.exp(-y / 0.4)[None, :], (g.qx, g.qy)) * (1.0 + 0.1 * rng.standard_normal((g.qx, g.qy)))
+    pres = 1.8 * dens * (1.0 + 0.05 * rng.standard_normal((g.qx, g.qy)))
+    u, v = 0.3 * rng.standard_normal((g.qx, g.qy)), 0.3 * rng.standard_normal((g.qx, g.qy))
+    for name, a in (("density", dens), ("x-momentum", dens * u), ("y-momentum", dens * v),
+                    ("energy", pres / 0.4 + 0.5 * dens * (u * u + v * v))):
+        sim.cc_data.get_var(name)[:, :] = a
+    sim.cc_data.fill_BC_all()                       # periodic in y: the stratification wraps into a strong jump
+    U0 = np.asarray(sim.cc_data.data).copy()
+    sim.dt = 0.4 * oracle.cfl_dt(U0, g.ng, g.dx, g.dy, 1.4, 0.8)
+    import pyro.compressible.unsplit_fluxes as flx
+    hat = flx.interface_states(sim.cc_data, sim.rp, sim.ivars, sim.tc, sim.dt)
+    assert min(float(np.asarray(h)[..., sim.ivars.idens].min()) for h in hat) < 0.0        # the regime in question
+    prm = oracle.comp_params(limiter=0, use_flattening=0, cvisc=0.0, riemann=riemann)
+    Unew = oracle.compressible_step(U0, g.ng, g.dx, g.dy, sim.dt, prm)
+    sim.evolve()
+    v_ = (slice(g.ilo, g.ihi + 1), slice(g.jlo, g.jhi + 1))
+    ref = np.asarray(sim.cc_data.data)[v_]
+    assert np.isfinite(ref).all() and np.isfinite(Unew[v_]).all()
+    assert np.abs(Unew[v_] - ref).max() < 1e-12 * np.abs(ref).max()
