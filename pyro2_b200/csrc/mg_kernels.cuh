@@ -394,7 +394,9 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
             double rt = (a == 0) ? v[r][1] : __shfl_down_sync(0xffffffffu, v[r][0], 1);
             if (EDGE) {
                 // domain edges: the ghost value fill_BC would hold, from the cell's own current value
-                const int gi = gi0 + r, gj = gj0 + a;
+                // (inhomogeneous boundary values are indexed by the cell's own row / column: a halo cell that is the
+                // periodic image of an interior cell uses that cell's index)
+                const int gi = xper ? wrap1(gi0 + r, ni) : gi0 + r, gj = yper ? wrap1(gj0 + a, n) : gj0 + a;
                 if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
                 if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
                 if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, L.ioff + gi, L.dy);

@@ -1,0 +1,94 @@
+"""Randomised comparison of the ghost-fill, CFL and explicit-stage kernels (host-compiled under the CUDA emulator) with
+the oracle: tiny and odd grid shapes, every boundary combination, all limiters.  Development tool (CPU only):
+
+    python scripts/fuzz_ghost_flow_emulated.py [ncases] [seed]
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), ROOT]
+import oracle  # noqa: E402
+from emu_util import EmuFlow, load_flow_emu, load_ghost_emu  # noqa: E402
+from pyro2_b200 import _lib  # noqa: E402
+
+BCS = ["outflow", "periodic", "reflect-even", "reflect-odd", "dirichlet", "neumann"]
+
+
+def ghost_case(lib, rng):
+    ng = int(rng.integers(1, 5))
+    nx, ny = int(rng.integers(1, 14)), int(rng.integers(1, 14))
+    nvar = int(rng.integers(1, 4))
+    bcs = []
+    for _ in range(nvar):
+        xb = str(rng.choice(BCS))
+        yb = str(rng.choice(BCS))
+        # periodic comes in pairs; a periodic / reflecting side needs at least ng valid cells (array_indexer.py reads them)
+        xs = (xb, xb) if xb == "periodic" else (xb, str(rng.choice([b for b in BCS if b != "periodic"])))
+        ys = (yb, yb) if yb == "periodic" else (yb, str(rng.choice([b for b in BCS if b != "periodic"])))
+        bcs.append(xs + ys)
+    if nx < ng and any(b in ("periodic", "reflect-even", "reflect-odd") for bc in bcs for b in bc[:2]):
+        nx = ng
+    if ny < ng and any(b in ("periodic", "reflect-even", "reflect-odd") for bc in bcs for b in bc[2:]):
+        ny = ng
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    pitch = (qy + 15) // 16 * 16 if qy >= 16 else (qy + 1) // 2 * 2
+    dtype = np.float64 if rng.integers(2) else np.int64
+    P = np.zeros((nvar, qx, pitch), dtype=dtype)
+    P[:, :, :qy] = rng.integers(-50, 50, (nvar, qx, qy)) if dtype == np.int64 else rng.standard_normal((nvar, qx, qy))
+    ref = P.copy()
+    for k in range(nvar):
+        a = np.ascontiguousarray(ref[k, :, :qy])
+        oracle.fill_ghost(a, ng, bcs[k])
+        ref[k, :, :qy] = a
+    g = _lib.Grid(nx, ny, ng, pitch, qx * pitch, 1.0, 1.0)
+    arr = _lib.bc_array(bcs)
+    f = lib.p2b_fill_ghost_f64 if dtype == np.float64 else lib.p2b_fill_ghost_i64
+    rc = f(P.ctypes.data, C.byref(g), nvar, arr, None)
+    ok = rc == 0 and np.array_equal(P[:, :, :qy], ref[:, :, :qy])
+    return ok, dict(kind="ghost", nx=nx, ny=ny, ng=ng, bcs=bcs, dtype=dtype.__name__, rc=rc)
+
+
+def flow_case(lib, rng):
+    ng = 4
+    nx, ny = int(rng.integers(4, 40)), int(rng.integers(4, 40))
+    limiter = int(rng.integers(3))
+    dx, dy = 1.0 / nx, float(rng.choice([1.0, 0.5])) / ny
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    u, v = rng.standard_normal((qx, qy)), rng.standard_normal((qx, qy))
+    dt = 0.4 * min(dx / np.abs(u).max(), dy / np.abs(v).max())
+    f = EmuFlow(lib, nx, ny, ng, dx, dy)
+    which = str(rng.choice(["burgers", "advection"]))
+    if which == "burgers":
+        ou, ov = oracle.burgers_evolve(u.copy(), v.copy(), ng, dx, dy, dt, limiter)
+        gu, gv = u.copy(), v.copy()
+        f.burgers_evolve(gu, gv, dt, limiter)
+        v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
+        ok = np.array_equal(gu[v_], ou[v_]) and np.array_equal(gv[v_], ov[v_])
+    else:
+        a = rng.standard_normal((qx, qy))
+        cu, cv = float(rng.standard_normal()), float(rng.standard_normal())
+        ref = oracle.advection_evolve(a.copy(), ng, dx, dy, dt, cu, cv, limiter)
+        got = a.copy()
+        f.ck(lib.p2b_flow_advection_update(f.h, got.ctypes.data, cu, cv, dt, limiter, None))
+        v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
+        ok = np.array_equal(got[v_], ref[v_])
+    f.close()
+    return ok, dict(kind=which, nx=nx, ny=ny, limiter=limiter)
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    ghost, flow = load_ghost_emu(), load_flow_emu()
+    bad = 0
+    for c in range(n):
+        ok, desc = ghost_case(ghost, rng) if c % 3 else flow_case(flow, rng)
+        if not ok:
+            bad += 1
+            print("FAIL", c, desc, flush=True)
+    print(f"{n} cases, {bad} failed")
+    sys.exit(1 if bad else 0)

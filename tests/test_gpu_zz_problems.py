@@ -48,3 +48,37 @@ def test_pyro_burgers_problems_match_reference(fname):
         dts.append(sim.dt)
     assert np.array_equal(np.array(dts), z["dts"])
     assert np.array_equal(state(), z["P"])
+
+
+@pytest.mark.parametrize("nx,bc", [(128, ("dirichlet",) * 4), (128, ("dirichlet", "neumann", "periodic", "periodic")),
+                                   (256, ("periodic", "periodic", "dirichlet", "dirichlet"))])
+def test_blocked_smoother_with_inhomogeneous_boundary_values(nx, bc):
+    """inhomogeneous Dirichlet values on levels the temporally blocked smoother handles (n >= 128), also with the other
+    direction periodic: a halo cell that is the periodic image of an interior cell must index the boundary values
+    with that cell's row / column (found by scripts/fuzz_mg_emulated.py: the tests before it stopped at n = 64)"""
+    import torch
+    import oracle
+    from pyro2_b200.mg_handle import MGHandle
+    o = oracle.MG(nx, bc=bc)
+    d = MGHandle(nx, bc, 0.0, -1.0, 0.0, 1.0, 0.0, 1.0, 10, 50)
+    rng = np.random.default_rng(nx)
+    vals = {k: (rng.standard_normal(nx + 2) if b == "dirichlet" else None) for k, b in zip(("xl", "xr", "yl", "yr"), bc)}
+    for k, v in vals.items():
+        if v is not None:
+            o.set_bc_values(k, v)
+    d.set_bc_values(**vals)
+    L = o.nlevels - 1
+    f = rng.standard_normal((nx + 2, nx + 2))
+    o.init_zeros()
+    o.init_RHS(f)
+    d.plane(L, "f").copy_(torch.from_numpy(f))
+    o.smooth(L, 7)
+    d.smooth(L, 7)
+    assert np.array_equal(d.plane(L, "v").cpu().numpy()[1:-1, 1:-1], o.plane(L, "v")[1:-1, 1:-1])
+    for _ in range(2):
+        for lev in range(L):
+            o.plane(lev, "v")[:] = 0.0
+        d.zero_coarse()
+        o.v_cycle()
+        d.vcycle()
+        assert np.array_equal(d.plane(L, "v").cpu().numpy(), o.plane(L, "v"))

@@ -132,3 +132,27 @@ def test_emulated_diffusion_step_matches_oracle(emu, n, bc):
         assert cyc == m.num_cycles
         assert np.array_equal(phi[1:-1, 1:-1], ref[1:-1, 1:-1])
     m.close()
+
+
+@pytest.mark.parametrize("bc", [("dirichlet", "neumann", "periodic", "periodic"), ("periodic", "periodic", "dirichlet", "dirichlet")])
+def test_emulated_blocked_smoother_inhomogeneous_values_with_periodic_other_direction(emu, bc):
+    """n = 128 (the temporally blocked smoother) with inhomogeneous Dirichlet values on one pair of sides and periodic
+    boundaries on the other: halo cells that are periodic images must index the boundary values with the wrapped
+    row / column.  Found by scripts/fuzz_mg_emulated.py; the fixed-case tests had inhomogeneous values only at n = 64."""
+    n = 128
+    rng = np.random.default_rng(7)
+    o = oracle.MG(n, bc=bc)
+    m = EmuMG(emu, n, bc, 0.0, -1.0, True)
+    vals = [rng.standard_normal(n + 2) if b == "dirichlet" else None for b in bc]
+    for side, v in zip(("xl", "xr", "yl", "yr"), vals):
+        if v is not None:
+            o.set_bc_values(side, v)
+    m.set_bc_values(*vals)
+    fine = o.nlevels - 1
+    f = rng.standard_normal((n + 2, n + 2))
+    o.plane(fine, "f")[:] = f
+    m.plane(fine, "f")[:] = f
+    o.smooth(fine, 7)
+    m.ck(emu.p2b_mg_smooth(m.h, fine, 7, None))
+    assert np.array_equal(m.plane(fine, "v")[1:-1, 1:-1], o.plane(fine, "v")[1:-1, 1:-1])
+    m.close()
