@@ -52,6 +52,30 @@ def ghost_case(lib, rng):
     return ok, dict(kind="ghost", nx=nx, ny=ny, ng=ng, bcs=bcs, dtype=dtype.__name__, rc=rc)
 
 
+def cfl_case(lib, rng):
+    """max(|u| + cs), max(|v| + cs) over the whole padded array -> the reference's dt, bit for bit"""
+    ng = int(rng.integers(1, 5))
+    nx, ny = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    pitch = (qy + 15) // 16 * 16 if qy >= 16 else (qy + 1) // 2 * 2
+    gamma = float(rng.choice([1.4, 5.0 / 3.0]))
+    dens = 0.1 + rng.random((qx, qy)) * float(rng.choice([1.0, 100.0]))
+    pres = 0.01 + rng.random((qx, qy)) * float(rng.choice([1.0, 1000.0]))
+    u, v = rng.standard_normal((qx, qy)) * 3.0, rng.standard_normal((qx, qy)) * 3.0
+    P = np.zeros((4, qx, pitch))
+    P[:, :, :qy] = np.stack([dens, pres / (gamma - 1.0) + 0.5 * dens * (u * u + v * v), dens * u, dens * v])
+    P[0, :, qy:] = 1.0                      # padding columns are never read: make them valid but extreme
+    P[1, :, qy:] = 1e9
+    dx, dy = 1.0 / nx, float(rng.choice([1.0, 0.3])) / ny
+    g = _lib.Grid(nx, ny, ng, pitch, qx * pitch, dx, dy)
+    scratch = np.zeros(8, dtype=np.uint64)
+    rc = lib.p2b_cfl_wavemax(P.ctypes.data, C.byref(g), gamma, scratch.ctypes.data, None)
+    w = scratch[:2].view(np.float64)
+    U = oracle.from_planes(np.ascontiguousarray(P[:, :, :qy]))
+    ok = rc == 0 and 0.8 * min(dx / w[0], dy / w[1]) == oracle.cfl_dt(U, ng, dx, dy, gamma, 0.8)
+    return ok, dict(kind="cfl", nx=nx, ny=ny, ng=ng, gamma=gamma)
+
+
 def flow_case(lib, rng):
     ng = 4
     nx, ny = int(rng.integers(4, 40)), int(rng.integers(4, 40))
@@ -86,7 +110,7 @@ if __name__ == "__main__":
     ghost, flow = load_ghost_emu(), load_flow_emu()
     bad = 0
     for c in range(n):
-        ok, desc = ghost_case(ghost, rng) if c % 3 else flow_case(flow, rng)
+        ok, desc = (flow_case(flow, rng), cfl_case(ghost, rng), ghost_case(ghost, rng))[c % 3]
         if not ok:
             bad += 1
             print("FAIL", c, desc, flush=True)
