@@ -27,6 +27,9 @@ def grid_setup(rp, ng=1, decomposition=None):
         # SphericalPolar is outside the B200 hot-path scope
         raise ValueError("Unsupported grid type!")
     if decomposition is not None and decomposition.size > 1:
+        if decomposition.local_nx(nx) < ng:
+            # a halo of ng rows must come from the adjacent slab alone
+            raise ValueError(f"mesh.nx = {nx} on {decomposition.size} slabs leaves fewer than ng = {ng} rows per slab")
         return patch.Cartesian2d(decomposition.local_nx(nx), ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax,
                                  ng=ng, nx_global=nx, ioffset=decomposition.ioffset(nx))
     return patch.Cartesian2d(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)

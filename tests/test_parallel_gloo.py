@@ -86,6 +86,14 @@ def test_decomposition_rules():
     g = Cartesian2d(24, 8, ng=4, xmax=3.0, device="cpu")
     s = Cartesian2d(6, 8, ng=4, xmax=3.0, device="cpu", nx_global=24, ioffset=12)
     assert s.dx == g.dx and np.array_equal(s.x[4:10], g.x[16:22]) and np.array_equal(s.xl, g.xl[12:26])
+    # a slab must hold at least ng rows: its neighbour's halo comes from it alone
+    from pyro2_b200.simulation_null import grid_setup
+
+    class RP:
+        def get_param(self, k):
+            return {"mesh.nx": 8, "mesh.ny": 8}[k]
+    with pytest.raises(ValueError):
+        grid_setup(RP(), ng=4, decomposition=d)            # 8 rows on 4 slabs: 2 < ng
 
 
 def _emulated_run_worker(rank, size, port, problem, nx, ny, nsteps, q):
