@@ -34,7 +34,12 @@ class CompParams(C.Structure):
                 ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int),
                 ("heat_rate", C.c_double), ("heat_profile", C.c_void_p),
                 ("do_sponge", C.c_int), ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double),
-                ("sponge_timescale", C.c_double)]
+                ("sponge_timescale", C.c_double), ("geom", C.c_void_p)]
+
+
+class Geom(C.Structure):
+    _fields_ = [("xmin", C.c_double), ("ymin", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("Ly", "Ax", "Ay", "V", "dlogAx", "dlogAy", "x2d")]
 
 
 class LmParams(C.Structure):
@@ -155,8 +160,8 @@ def cfl_dt(U_ijn, ng, dx, dy, gamma, cfl):
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
                 no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_bcs=None, riemann="HLLC", xl_solid=0, yl_solid=0,
-                heat_rate=0.0, heat_profile=None, sponge=None):
-    """src_bcs: BC names (xlb, xrb, ylb, yrb) of the four source arrays in variable order dens, ener, xmom,
+                heat_rate=0.0, heat_profile=None, sponge=None, geom=None):
+    """geom: a spherical_geometry() dict for SphericalPolar grids (CGF only).  src_bcs: BC names (xlb, xrb, ylb, yrb) of the four source arrays in variable order dens, ener, xmom,
     ymom (only needed with sources); "hse" and "ambient" copy like outflow for them.  heat_profile: (qx, qy)
     array P, S_ener = dens * heat_rate * P; sponge: (rho_begin, rho_full, timescale) or None"""
     codes = (C.c_int * 16)()
@@ -167,9 +172,48 @@ def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, u
     sp = sponge or (0.0, 0.0, 1.0)
     prm = CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi, grav, codes,
                      {"HLLC": 0, "CGF": 1, "HLLC_lm": 2}[riemann], xl_solid, yl_solid, heat_rate,
-                     None if hp is None else hp.ctypes.data, int(sponge is not None), sp[0], sp[1], sp[2])
+                     None if hp is None else hp.ctypes.data, int(sponge is not None), sp[0], sp[1], sp[2], None)
     prm._keepalive = hp
+    if geom is not None:
+        arrs = {k: np.ascontiguousarray(geom[k], dtype=np.float64) for k in ("Ly", "Ax", "Ay", "V", "dlogAx", "dlogAy", "x2d")}
+        gs = Geom(geom["xmin"], geom["ymin"], *[arrs[k].ctypes.data for k in ("Ly", "Ax", "Ay", "V", "dlogAx", "dlogAy", "x2d")])
+        prm._geom = (gs, arrs)
+        prm.geom = C.addressof(gs)
     return prm
+
+
+def spherical_geometry(nx, ny, ng, xmin, xmax, ymin, ymax):
+    """the arrays of a SphericalPolar grid (pyro/mesh/patch.py:242-312; x = r, y = theta), with the reference's numpy
+    expressions: side lengths Lx = dx, Ly = r dtheta, face areas Ax, Ay (on the low faces), cell volumes V and the
+    logarithmic area derivatives that appear as geometric sources in the characteristic tracing"""
+    dx, dy = (xmax - xmin) / nx, (ymax - ymin) / ny
+    xl = (np.arange(nx + 2 * ng) - ng) * dx + xmin
+    xr = (np.arange(nx + 2 * ng) + 1.0 - ng) * dx + xmin
+    x = 0.5 * (xl + xr)
+    yl = (np.arange(ny + 2 * ng) - ng) * dy + ymin
+    yr = (np.arange(ny + 2 * ng) + 1.0 - ng) * dy + ymin
+    y = 0.5 * (yl + yr)
+    x2d, y2d = np.meshgrid(x, y, indexing="ij")
+    xl2d, yl2d = np.meshgrid(xl, yl, indexing="ij")
+    xr2d, yr2d = np.meshgrid(xr, yr, indexing="ij")
+    return {"xmin": xmin, "ymin": ymin, "dx": dx, "dy": dy, "x2d": x2d, "y2d": y2d,
+            "Lx": np.full(x2d.shape, dx), "Ly": x2d * dy,
+            "Ax": np.abs(-2.0 * np.pi * xl2d ** 2 * (np.cos(yr2d) - np.cos(yl2d))),
+            "Ay": np.abs(np.pi * np.sin(yl2d) * (xr2d ** 2 - xl2d ** 2)),
+            "dlogAx": 2.0 / x2d, "dlogAy": 1.0 / (np.tan(y2d) * x2d),
+            "V": np.abs(-2.0 * np.pi / 3.0 * (np.cos(yr2d) - np.cos(yl2d)) * (xr2d - xl2d) *
+                        (xr2d ** 2 + xl2d ** 2 + xr2d * xl2d))}
+
+
+def cfl_dt_spherical(U_ijn, gamma, cfl, geom):
+    """method_compute_timestep with the cell side lengths of a curvilinear grid (compressible/simulation.py:267-288):
+    cfl * min(Lx / (|u| + cs), Ly / (|v| + cs)) over the whole array"""
+    P = to_planes(U_ijn)
+    rho = P[0]
+    u, v = P[2] / rho, P[3] / rho
+    e = (P[1] - 0.5 * rho * (u * u + v * v)) / rho
+    cs = np.sqrt(gamma * (rho * e * (gamma - 1.0)) / rho)
+    return cfl * float(min((geom["Lx"] / (np.abs(u) + cs)).min(), (geom["Ly"] / (np.abs(v) + cs)).min()))
 
 
 def fill_hse(P, ng, dy, grav, gamma, var, side):

@@ -155,7 +155,15 @@ typedef struct {
     /* sponge (simulation.py:164-184, 425-441): do_sponge, rho_begin, rho_full, timescale */
     int do_sponge;
     double sponge_rho_begin, sponge_rho_full, sponge_timescale;
+    /* SphericalPolar geometry (mesh/patch.py:242-312; x = r, y = theta), NULL = Cartesian: full (qx, qy) planes
+       computed by the caller with the reference's numpy expressions (oracle.py: spherical_geometry) */
+    const struct orc_geom *geom;
 } orc_comp_params;
+
+typedef struct orc_geom {
+    double xmin, ymin;
+    const double *Ly, *Ax, *Ay, *V, *dlogAx, *dlogAy, *x2d;      /* Lx = dx everywhere */
+} orc_geom;
 
 /* optional per-stage dumps, each (4 or 1) planes of qx*qy doubles; NULL = skip */
 typedef struct {
@@ -298,12 +306,13 @@ static void limit4(const double *a, double *lda, double *tmp, int qx, int qy, in
 
 /* interface.py:6-236 (Cartesian: dloga = 0 so the geometric source vanishes) */
 static void trace_states(int idir, const double *qv, const double *dqv, double *q_l, double *q_r,
-                         int qx, int qy, int ng, double dx, double dt, double gamma)
+                         int qx, int qy, int ng, double dx, double dt, double gamma, const double *Larr,
+                         const double *dloga)
 {
     const size_t np = (size_t)qx * qy;
     const int nx = qx - 2 * ng, ny = qy - 2 * ng;
     const int ilo = ng, ihi = ng + nx, jlo = ng, jhi = ng + ny;
-    const double dtdx = dt / dx, dtdx4 = 0.25 * dtdx;
+    const double dtdx_c = dt / dx;
     const int in = idir == 1 ? IU : IV; /* normal velocity slot */
     const int it = idir == 1 ? IV : IU; /* transverse velocity slot */
     memset(q_l, 0, 4 * np * sizeof(double));
@@ -313,6 +322,8 @@ static void trace_states(int idir, const double *qv, const double *dqv, double *
         for (int j = jlo - 2; j < jhi + 2; j++) {
             size_t k = IDX(i, j);
             size_t kl = idir == 1 ? IDX(i + 1, j) : IDX(i, j + 1);
+            /* dtdx = dt / dx[i, j]: the cell's own length along idir (SphericalPolar: Ly = r dtheta varies with i) */
+            const double dtdx = Larr ? dt / Larr[k] : dtdx_c, dtdx4 = 0.25 * dtdx;
             double q[4], dq[4], lvec[4][4], rvec[4][4], e_val[4], betal[4], betar[4];
             for (int m = 0; m < 4; m++) { q[m] = qv[m * np + k]; dq[m] = dqv[m * np + k]; }
             double cs = sqrt(gamma * q[IP] / q[IRHO]);
@@ -345,6 +356,14 @@ static void trace_states(int idir, const double *qv, const double *dqv, double *
                 for (int n = 0; n < 4; n++) { sum_l += betal[n] * rvec[n][m]; sum_r += betar[n] * rvec[n][m]; }
                 q_l[m * np + kl] = ql[m] + sum_l;
                 q_r[m * np + k] = qr[m] + sum_r;
+            }
+            if (dloga) {
+                /* geometric source of the divergence in curvilinear coordinates (interface.py:218-234) */
+                const double rho_source = -0.5 * dt * dloga[k] * q[IRHO] * q[in];
+                q_l[IRHO * np + kl] += rho_source;
+                q_r[IRHO * np + k] += rho_source;
+                q_l[IP * np + kl] += rho_source * cs * cs;
+                q_r[IP * np + k] += rho_source * cs * cs;
             }
         }
 }
@@ -386,7 +405,11 @@ static void estimate_wave_speed(double rho_l, double u_l, double p_l, double c_l
 }
 
 /* riemann.py:1105-1179, 1-d state branch, Cartesian */
-static void cons_flux(int idir, double gamma, const double U[4], double F[4])
+static void cons_flux_geom(int idir, double gamma, const double U[4], double F[4], int coord_type);
+static void cons_flux(int idir, double gamma, const double U[4], double F[4]) { cons_flux_geom(idir, gamma, U, F, 0); }
+/* coord_type 1 (SphericalPolar): the pressure is left out of the momentum flux, its gradient is applied
+   separately (riemann.py:1156-1158, 1171-1173) */
+static void cons_flux_geom(int idir, double gamma, const double U[4], double F[4], int coord_type)
 {
     double u = 0.0, v = 0.0;
     if (U[IDENS] != 0.0) { u = U[IXMOM] / U[IDENS]; v = U[IYMOM] / U[IDENS]; }
@@ -394,14 +417,14 @@ static void cons_flux(int idir, double gamma, const double U[4], double F[4])
     if (idir == 1) {
         F[IDENS] = U[IDENS] * u;
         F[IXMOM] = U[IXMOM] * u;
-        F[IXMOM] += p;
+        if (coord_type == 0) F[IXMOM] += p;
         F[IYMOM] = U[IYMOM] * u;
         F[IENER] = (U[IENER] + p) * u;
     } else {
         F[IDENS] = U[IDENS] * v;
         F[IXMOM] = U[IXMOM] * v;
         F[IYMOM] = U[IYMOM] * v;
-        F[IYMOM] += p;
+        if (coord_type == 0) F[IYMOM] += p;
         F[IENER] = (U[IENER] + p) * v;
     }
 }
@@ -464,8 +487,17 @@ static void riemann_hllc(int idir, const double *U_l, const double *U_r, double 
 /* riemann.py:9-310 (riemann_cgf: the two-shock solver of Colella, Glaz & Ferguson) followed by consFlux
  * (riemann_flux :1075-1085); lower_solid: the normal velocity at the face on a solid lower boundary is zero
  * (the upper test `i == ihi + 1` in the reference can never fire inside its loop range) */
+static void riemann_cgf_geom(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
+                             double gamma, int lower_solid, int coord_type, double *Ustate);
 static void riemann_cgf(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
                         double gamma, int lower_solid)
+{
+    riemann_cgf_geom(idir, U_l, U_r, F, qx, qy, ng, gamma, lower_solid, 0, NULL);
+}
+/* Ustate (optional, 4 planes): the conserved interface state itself (riemann_flux(..., return_cons=True),
+   riemann.py:1097-1099), whose pressure the SphericalPolar update differences */
+static void riemann_cgf_geom(int idir, const double *U_l, const double *U_r, double *F, int qx, int qy, int ng,
+                             double gamma, int lower_solid, int coord_type, double *Ustate)
 {
     const size_t np = (size_t)qx * qy;
     const int nx = qx - 2 * ng, ny = qy - 2 * ng;
@@ -539,8 +571,10 @@ static void riemann_cgf(int idir, const double *U_l, const double *U_r, double *
             Us[imn] = rho_s * un_s;
             Us[imt] = rho_s * ut_s;
             Us[IENER] = rhoe_s + 0.5 * rho_s * (un_s * un_s + ut_s * ut_s);
-            cons_flux(idir, gamma, Us, Fk);
+            cons_flux_geom(idir, gamma, Us, Fk, coord_type);
             for (int m = 0; m < 4; m++) F[m * np + k] = Fk[m];
+            if (Ustate)
+                for (int m = 0; m < 4; m++) Ustate[m * np + k] = Us[m];
         }
 }
 
@@ -613,7 +647,7 @@ static void riemann_solve(int idir, const double *U_l, const double *U_r, double
 /* interface.py:240-378, Cartesian branch.  u, v full planes. */
 static void artificial_viscosity(const double *u, const double *v, double *ax, double *ay, int qx,
                                  int qy, int ng, double dx, double dy, double cvisc, int skip_xhi,
-                                 int skip_yhi)
+                                 int skip_yhi, const orc_geom *G)
 {
     const size_t np = (size_t)qx * qy;
     const int nx = qx - 2 * ng, ny = qy - 2 * ng;
@@ -628,6 +662,17 @@ static void artificial_viscosity(const double *u, const double *v, double *ax, d
             double ul = 0.5 * (u[IDX(i - 1, j)] + u[IDX(i - 1, j - 1)]);
             double vt = 0.5 * (v[IDX(i, j)] + v[IDX(i - 1, j)]);
             double vb = 0.5 * (v[IDX(i, j - 1)] + v[IDX(i - 1, j - 1)]);
+            if (G) {
+                /* divergence at the vertex in spherical polar coordinates (interface.py:332-353) */
+                const double rr = (i + 0.5 - ng) * dx + G->xmin, rl = (i - 0.5 - ng) * dx + G->xmin;
+                const double rc = (i - ng) * dx + G->xmin;
+                const double ux = (ur * rr * rr - ul * rl * rl) / (rc * rc * dx);
+                const double sint = sin((j + 0.5 - ng) * dy + G->ymin), sinb = sin((j - 0.5 - ng) * dy + G->ymin);
+                const double sinc = sin((j - ng) * dy + G->ymin);
+                const double vy = sinc == 0.0 ? 0.0 : (sint * vt - sinb * vb) / (rc * sinc * dy);
+                divU[IDX(i, j)] = ux + vy;
+                continue;
+            }
             divU[IDX(i, j)] = (ur - ul) / dx + (vt - vb) / dy;
         }
     /* the reference loops range(ilo, ihi) x range(jlo, jhi): the +x / +y boundary faces are never
@@ -640,7 +685,7 @@ static void artificial_viscosity(const double *u, const double *v, double *ax, d
             double divU_x = 0.5 * (divU[IDX(i, j)] + divU[IDX(i, j + 1)]);
             double divU_y = 0.5 * (divU[IDX(i, j)] + divU[IDX(i + 1, j)]);
             ax[IDX(i, j)] = cvisc * pymax(-divU_x * dx, 0.0);
-            ay[IDX(i, j)] = cvisc * pymax(-divU_y * dy, 0.0);
+            ay[IDX(i, j)] = cvisc * pymax(-divU_y * (G ? G->Ly[IDX(i, j)] : dy), 0.0);
         }
     free(divU);
 }
@@ -695,6 +740,8 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     orc_comp_stages none;
     memset(&none, 0, sizeof none);
     if (!S) S = &none;
+    const orc_geom *G = P->geom;       /* SphericalPolar: x = r, y = theta; CGF only (simulation.py:201-209) */
+    if (G && P->riemann != 1) return 4;
 
     double *q = zalloc(4 * np), *xi = zalloc(np), *xi_x = zalloc(np), *xi_y = zalloc(np);
     double *ldx = zalloc(4 * np), *ldy = zalloc(4 * np), *tmp = zalloc(np), *tmp2 = zalloc(np);
@@ -731,10 +778,10 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->ldy, ldy, 4 * np);
 
     /* unsplit_fluxes.py:207-242 */
-    trace_states(1, q, ldx, V_l, V_r, qx, qy, ng, dx, dt, gamma);
+    trace_states(1, q, ldx, V_l, V_r, qx, qy, ng, dx, dt, gamma, NULL, G ? G->dlogAx : NULL);
     prim_to_cons(V_l, U_xl, qx, qy, gamma);
     prim_to_cons(V_r, U_xr, qx, qy, gamma);
-    trace_states(2, q, ldy, V_l, V_r, qx, qy, ng, dy, dt, gamma);
+    trace_states(2, q, ldy, V_l, V_r, qx, qy, ng, dy, dt, gamma, G ? G->Ly : NULL, G ? G->dlogAy : NULL);
     prim_to_cons(V_l, U_yl, qx, qy, gamma);
     prim_to_cons(V_r, U_yr, qx, qy, gamma);
     dump(S->Uxl_hat, U_xl, 4 * np); dump(S->Uxr_hat, U_xr, 4 * np);
@@ -743,11 +790,19 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     /* apply_source_terms (unsplit_fluxes.py:247-330) with get_external_sources (simulation.py:105-128):
        S_ymom = dens * grav, S_ener = ymom * grav over the whole (ghost-filled) array, the source arrays
        then get THEIR OWN ghost fill, and half a time step of them goes to the buf = 1 interface states */
-    if (P->grav != 0.0 || P->heat_profile) {
+    if (P->grav != 0.0 || P->heat_profile || G) {
         double *src = zalloc(4 * np);
         for (size_t k = 0; k < np; k++) {
-            src[IYMOM * np + k] = U[IDENS * np + k] * P->grav;
-            src[IENER * np + k] = U[IYMOM * np + k] * P->grav;
+            if (G) {
+                /* radial gravity plus the geometric (centrifugal / Coriolis-like) terms (simulation.py:117-124) */
+                src[IXMOM * np + k] = U[IDENS * np + k] * P->grav;
+                src[IENER * np + k] = U[IXMOM * np + k] * P->grav;
+                src[IXMOM * np + k] += U[IYMOM * np + k] * U[IYMOM * np + k] / (U[IDENS * np + k] * G->x2d[k]);
+                src[IYMOM * np + k] += -U[IXMOM * np + k] * U[IYMOM * np + k] / U[IDENS * np + k];
+            } else {
+                src[IYMOM * np + k] = U[IDENS * np + k] * P->grav;
+                src[IENER * np + k] = U[IYMOM * np + k] * P->grav;
+            }
             if (P->heat_profile) src[IENER * np + k] += U[IDENS * np + k] * P->heat_rate * P->heat_profile[k];
         }
         for (int n = 0; n < 4; n++)
@@ -770,10 +825,44 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     }
 
     /* apply_transverse_flux (unsplit_fluxes.py:420-471) */
-    riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
-    riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
+    double *Ust_x = NULL, *Ust_y = NULL, *qfx = NULL, *qfy = NULL;     /* SphericalPolar: interface states, their primitives */
+    if (G) {
+        Ust_x = zalloc(4 * np); Ust_y = zalloc(4 * np); qfx = zalloc(4 * np); qfy = zalloc(4 * np);
+        riemann_cgf_geom(1, U_xl, U_xr, F_x, qx, qy, ng, gamma, P->xl_solid, 1, Ust_x);
+        riemann_cgf_geom(2, U_yl, U_yr, F_y, qx, qy, ng, gamma, P->yl_solid, 1, Ust_y);
+        cons_to_prim(Ust_x, qfx, qx, qy, ng, gamma);
+        cons_to_prim(Ust_y, qfy, qx, qy, ng, gamma);
+    } else {
+        riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
+        riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
+    }
     dump(S->Fx_t, F_x, 4 * np); dump(S->Fy_t, F_y, 4 * np);
-    {
+    if (G) {
+        /* unsplit_fluxes.py:449-490 with face areas and cell volumes; note that the low-side states U_xl[i, j] /
+           U_yl[i, j] use V, Ly, Lx of cell (i, j), the cell on the HIGH side of the face, like the reference */
+        const double hdt = 0.5 * dt;
+        const double *Axp = G->Ax, *Ayp = G->Ay, *pxf = qfx + IP * np, *pyf = qfy + IP * np;
+        for (int n = 0; n < 4; n++) {
+            double *xl = U_xl + n * np, *xr = U_xr + n * np, *yl = U_yl + n * np, *yr = U_yr + n * np;
+            const double *fx = F_x + n * np, *fy = F_y + n * np;
+            for (int i = ng - 2; i <= ng + nx; i++)
+                for (int j = ng - 2; j <= ng + ny; j++) {
+                    const double hdtV = hdt / G->V[IDX(i, j)];
+                    xl[IDX(i, j)] += -hdtV * (fy[IDX(i - 1, j + 1)] * Ayp[IDX(i - 1, j + 1)] - fy[IDX(i - 1, j)] * Ayp[IDX(i - 1, j)]);
+                    xr[IDX(i, j)] += -hdtV * (fy[IDX(i, j + 1)] * Ayp[IDX(i, j + 1)] - fy[IDX(i, j)] * Ayp[IDX(i, j)]);
+                    yl[IDX(i, j)] += -hdtV * (fx[IDX(i + 1, j - 1)] * Axp[IDX(i + 1, j - 1)] - fx[IDX(i, j - 1)] * Axp[IDX(i, j - 1)]);
+                    yr[IDX(i, j)] += -hdtV * (fx[IDX(i + 1, j)] * Axp[IDX(i + 1, j)] - fx[IDX(i, j)] * Axp[IDX(i, j)]);
+                }
+        }
+        for (int i = ng - 2; i <= ng + nx; i++)
+            for (int j = ng - 2; j <= ng + ny; j++) {
+                const size_t k = IDX(i, j);
+                U_xl[IYMOM * np + k] += -hdt * (pyf[IDX(i - 1, j + 1)] - pyf[IDX(i - 1, j)]) / G->Ly[k];
+                U_xr[IYMOM * np + k] += -hdt * (pyf[IDX(i, j + 1)] - pyf[k]) / G->Ly[k];
+                U_yl[IXMOM * np + k] += -hdt * (pxf[IDX(i + 1, j - 1)] - pxf[IDX(i, j - 1)]) / dx;
+                U_yr[IXMOM * np + k] += -hdt * (pxf[IDX(i + 1, j)] - pxf[k]) / dx;
+            }
+    } else {
         const double hdt = 0.5 * dt, hdtV = hdt / (dx * dy), Ax = dy, Ay = dx;
         /* buf = (2, 1): i in [ilo-2, ihi+1], j likewise (inclusive ihi = ng+nx-1) */
         for (int n = 0; n < 4; n++) {
@@ -792,16 +881,24 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->Uxl, U_xl, 4 * np); dump(S->Uxr, U_xr, 4 * np);
     dump(S->Uyl, U_yl, 4 * np); dump(S->Uyr, U_yr, 4 * np);
 
-    /* final fluxes (simulation.py:349-357) */
-    riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
-    riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
+    /* final fluxes (simulation.py:330-357) */
+    if (G) {
+        memset(Ust_x, 0, 4 * np * sizeof(double)); memset(Ust_y, 0, 4 * np * sizeof(double));
+        riemann_cgf_geom(1, U_xl, U_xr, F_x, qx, qy, ng, gamma, P->xl_solid, 1, Ust_x);
+        riemann_cgf_geom(2, U_yl, U_yr, F_y, qx, qy, ng, gamma, P->yl_solid, 1, Ust_y);
+        cons_to_prim(Ust_x, qfx, qx, qy, ng, gamma);
+        cons_to_prim(Ust_y, qfy, qx, qy, ng, gamma);
+    } else {
+        riemann_solve(1, U_xl, U_xr, F_x, qx, qy, ng, P);
+        riemann_solve(2, U_yl, U_yr, F_y, qx, qy, ng, P);
+    }
 
     /* artificial viscosity (simulation.py:361-365, unsplit_fluxes.py:497-549) */
     if (cons_to_prim(U, q, qx, qy, ng, gamma)) rc = 3;
     {
         double *ax = tmp, *ay = tmp2;
         artificial_viscosity(q + IU * np, q + IV * np, ax, ay, qx, qy, ng, dx, dy, P->cvisc,
-                             P->no_avisc_xhi, P->no_avisc_yhi);
+                             P->no_avisc_xhi, P->no_avisc_yhi, G);
         for (int n = 0; n < 4; n++) {
             const double *var = U + n * np;
             double *fx = F_x + n * np, *fy = F_y + n * np;
@@ -816,10 +913,29 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     dump(S->Fx, F_x, 4 * np); dump(S->Fy, F_y, 4 * np);
 
     /* conservative update (simulation.py:377-384) */
-    double *Uold_dens = zalloc(np), *Uold_ymom = zalloc(np);
+    double *Uold_dens = zalloc(np), *Uold_ymom = zalloc(np), *Uold_xmom = zalloc(np);
     memcpy(Uold_dens, U + IDENS * np, np * sizeof(double));
     memcpy(Uold_ymom, U + IYMOM * np, np * sizeof(double));
-    {
+    memcpy(Uold_xmom, U + IXMOM * np, np * sizeof(double));
+    if (G) {
+        /* simulation.py:377-396: flux differences with face areas over the cell volume, then the pressure gradients */
+        for (int n = 0; n < 4; n++) {
+            double *var = U + n * np;
+            const double *fx = F_x + n * np, *fy = F_y + n * np;
+            for (int i = ng; i < ng + nx; i++)
+                for (int j = ng; j < ng + ny; j++) {
+                    const double dtdV = dt / G->V[IDX(i, j)];
+                    var[IDX(i, j)] += dtdV * (fx[IDX(i, j)] * G->Ax[IDX(i, j)] - fx[IDX(i + 1, j)] * G->Ax[IDX(i + 1, j)] +
+                                              fy[IDX(i, j)] * G->Ay[IDX(i, j)] - fy[IDX(i, j + 1)] * G->Ay[IDX(i, j + 1)]);
+                }
+        }
+        const double *pxf = qfx + IP * np, *pyf = qfy + IP * np;
+        for (int i = ng; i < ng + nx; i++)
+            for (int j = ng; j < ng + ny; j++) {
+                U[IXMOM * np + IDX(i, j)] -= dt * (pxf[IDX(i + 1, j)] - pxf[IDX(i, j)]) / dx;
+                U[IYMOM * np + IDX(i, j)] -= dt * (pyf[IDX(i, j + 1)] - pyf[IDX(i, j)]) / G->Ly[IDX(i, j)];
+            }
+    } else {
         const double dtdV = dt / (dx * dy), Ax = dy, Ay = dx;
         for (int n = 0; n < 4; n++) {
             double *var = U + n * np;
@@ -834,7 +950,33 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
     /* external sources, predictor-corrector (simulation.py:398-423, get_external_sources :105-160):
        U += dt S(U_old); S_new uses the updated density and a time-centred y-momentum;
        U += dt/2 (S_new - S_old).  clean_state is a no-op for the default small_dens = -1e200 */
-    if (P->grav != 0.0 || P->heat_profile) {
+    if (G) {
+        /* simulation.py:398-423 with the SphericalPolar branches of get_external_sources (:117-124, :135-146) */
+        const double g = P->grav;
+        for (int i = ng; i < ng + nx; i++)
+            for (int j = ng; j < ng + ny; j++) {
+                const size_t k = IDX(i, j);
+                const double r = G->x2d[k];
+                /* S_old from U_old */
+                double so_x = Uold_dens[k] * g;
+                const double so_e = Uold_xmom[k] * g;
+                so_x += Uold_ymom[k] * Uold_ymom[k] / (Uold_dens[k] * r);
+                const double so_y = 0.0 + -Uold_xmom[k] * Uold_ymom[k] / Uold_dens[k];
+                U[IXMOM * np + k] += dt * so_x;
+                U[IYMOM * np + k] += dt * so_y;
+                U[IENER * np + k] += dt * so_e;
+                /* S_new from the updated state, energy source with the time-centred radial momentum */
+                double sn_x = U[IDENS * np + k] * g;
+                const double so_xg = Uold_dens[k] * g;
+                const double xmom_new = U[IXMOM * np + k] + 0.5 * dt * (sn_x - so_xg);
+                const double sn_e = xmom_new * g;
+                sn_x += U[IYMOM * np + k] * U[IYMOM * np + k] / (U[IDENS * np + k] * r);
+                const double sn_y = 0.0 + -U[IXMOM * np + k] * U[IYMOM * np + k] / U[IDENS * np + k];
+                U[IXMOM * np + k] += 0.5 * dt * (sn_x - so_x);
+                U[IYMOM * np + k] += 0.5 * dt * (sn_y - so_y);
+                U[IENER * np + k] += 0.5 * dt * (sn_e - so_e);
+            }
+    } else if (P->grav != 0.0 || P->heat_profile) {
         const double g = P->grav;
 #pragma omp parallel for
         for (int i = ng; i < ng + nx; i++)
@@ -873,7 +1015,8 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
                 U[IENER * np + k] += 0.5 * ((xn * xn + yn * yn) - (xo * xo + yo * yo)) / rho;
             }
     }
-    free(Uold_dens); free(Uold_ymom);
+    free(Uold_dens); free(Uold_ymom); free(Uold_xmom);
+    free(Ust_x); free(Ust_y); free(qfx); free(qfy);
 
     free(q); free(xi); free(xi_x); free(xi_y); free(ldx); free(ldy); free(tmp); free(tmp2);
     free(V_l); free(V_r); free(U_xl); free(U_xr); free(U_yl); free(U_yr); free(F_x); free(F_y);
