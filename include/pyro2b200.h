@@ -71,6 +71,19 @@ typedef struct {
     double sponge_rho_begin, sponge_rho_full, sponge_timescale; /* starts / is fully on, and its time scale          */
     int src_copy_yhi;        /* 1 when the +y boundary is "ambient": the ghost cells hold a constant state while the
                               * reference's source arrays are zero-gradient copies there (compressible/BC.py:150-152) */
+    /* SphericalPolar grids (pyro/mesh/patch.py:242-312; x = r, y = theta; CGF only, like the reference): geo_i != NULL
+     * selects the instantiation with the coord_type == 1 branches of the solver.  Device tables of doubles built on
+     * the host with the reference's numpy expressions, geo_i = 9 rows of geo_ni (>= nx + 2 ng) entries, geo_j = 7 rows
+     * of geo_nj (>= ny + 2 ng + 1) entries:
+     *   geo_i: r_i; r of the row the reference's source arrays mirror into row i; -2 pi rl^2; rr^2 - rl^2; rr - rl;
+     *          rr^2 + rl^2 + rr rl; then the viscosity's (i + 1/2 - ng) dx + xmin, (i - 1/2 - ng) dx + xmin, (i - ng) dx + xmin
+     *   geo_j: cos(th_r) - cos(th_l); -2 pi / 3 times that; pi sin(th_l); tan(th);
+     *          sin((j + 1/2 - ng) dy + ymin), sin((j - 1/2 - ng) dy + ymin), sin((j - ng) dy + ymin)
+     * src_flip_xlo / xhi: that x boundary is "reflect" (the ghost rows of the source arrays change sign) */
+    const double* geo_i;
+    const double* geo_j;
+    int geo_ni, geo_nj;
+    int src_flip_xlo, src_flip_xhi;
 } p2b_comp_params;
 
 /* device scratch the sweep needs, 8 x 64-bit words owned by the caller:
@@ -120,9 +133,9 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * riemann_hllc (riemann.py:682-860) folded into one kernel.  Uin must have its ghost cells filled;
  * the valid region of Uout (a different buffer) receives U^{n+1}; scratch[0..1] accumulate the new
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
- * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4, Cartesian geometry,
+ * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4,
  * Riemann solver HLLC, CGF or HLLC_lm (prm->riemann); gravity, a heating profile or the sponge select the
- * instantiations with source terms. */
+ * instantiations with source terms; prm->geo_i selects SphericalPolar geometry (CGF, no heating / sponge / ambient). */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
 

@@ -54,7 +54,9 @@ class CompParams(C.Structure):
                 ("riemann", C.c_int), ("xl_solid", C.c_int), ("yl_solid", C.c_int),
                 ("heat_rate", C.c_double), ("heat_profile", C.c_void_p), ("do_sponge", C.c_int),
                 ("sponge_rho_begin", C.c_double), ("sponge_rho_full", C.c_double), ("sponge_timescale", C.c_double),
-                ("src_copy_yhi", C.c_int)]
+                ("src_copy_yhi", C.c_int),
+                ("geo_i", C.c_void_p), ("geo_j", C.c_void_p), ("geo_ni", C.c_int), ("geo_nj", C.c_int),
+                ("src_flip_xlo", C.c_int), ("src_flip_xhi", C.c_int)]
 
 
 BC_CODES = {"outflow": 0, "neumann": 0, "reflect-even": 1, "reflect-odd": 2, "dirichlet": 2,

@@ -79,7 +79,7 @@ struct CudaWarp {
     }
 };
 
-template <bool GRAV, int RIEMANN>
+template <bool GRAV, int RIEMANN, bool SPH = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
 {
@@ -95,7 +95,7 @@ sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
     __syncwarp();
 
     CudaWarp w;
-    SweepTask<CudaWarp, GRAV, RIEMANN> T(w, A, S, 0u);
+    SweepTask<CudaWarp, GRAV, RIEMANN, SPH> T(w, A, S, 0u);
     for (;;) {
         int t = 0;
         if (lane == 0) t = (int)atomicAdd(task_counter, 1ull);
@@ -121,6 +121,7 @@ static int resident_warps()
         cudaFuncSetAttribute(sweep_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(sweep_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(sweep_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(sweep_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         // every instantiation has the same launch bounds and shared memory, hence the same residency
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false, 0>, SWEEP_THREADS,
                                                       SWEEP_WARPS * sizeof(SweepSmem));
@@ -182,6 +183,15 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     A.do_sponge = prm->do_sponge; A.sponge_rho_begin = prm->sponge_rho_begin;
     A.sponge_rho_full = prm->sponge_rho_full; A.sponge_timescale = prm->sponge_timescale;
     A.src_copy_yhi = prm->src_copy_yhi;
+    A.geo_i = prm->geo_i; A.geo_j = prm->geo_j; A.geo_ni = prm->geo_ni; A.geo_nj = prm->geo_nj;
+    A.src_flip_xlo = prm->src_flip_xlo; A.src_flip_xhi = prm->src_flip_xhi;
+    if (prm->geo_i) {
+        P2B_REQUIRE(prm->geo_j, "SphericalPolar: geo_j missing");
+        P2B_REQUIRE(prm->riemann == 1, "SphericalPolar geometry needs the CGF Riemann solver");
+        P2B_REQUIRE(prm->geo_ni >= g->nx + 2 * g->ng && prm->geo_nj >= g->ny + 2 * g->ng + 1, "geometry tables too short");
+        P2B_REQUIRE(!prm->heat_profile && !prm->do_sponge && !prm->src_copy_yhi,
+                    "SphericalPolar: heating, sponge and ambient boundaries are not supported");
+    }
     A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
     A.seglen = choose_seglen(g->nx, A.nstrips, resident);
@@ -198,7 +208,9 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
     unsigned long long* counter = (unsigned long long*)(scratch + 2);
     const bool grav = prm->grav != 0.0 || prm->heat_profile != nullptr || prm->do_sponge != 0;   // any source term
-    if (prm->riemann == 2) {
+    if (prm->geo_i) {
+        sweep_kernel<true, 1, true><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+    } else if (prm->riemann == 2) {
         if (grav) sweep_kernel<true, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
         else sweep_kernel<false, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
     } else if (prm->riemann == 1) {

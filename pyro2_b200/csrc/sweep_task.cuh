@@ -66,6 +66,18 @@ struct SweepArgs {
     double sponge_rho_begin, sponge_rho_full, sponge_timescale;
     int src_copy_yhi;                 // 1: the +y boundary is "ambient": its ghost cells hold a constant state, but the
                                       //    reference's source arrays are zero-gradient copies of row jhi there
+    // SphericalPolar grids (SPH instantiation; x = r, y = theta): separable geometry tables built on the host with the
+    // reference's numpy expressions (mesh/patch.py:242-312), so that products formed here in the reference's order
+    // reproduce its Ax, Ay, V, Ly, dlogA arrays bit for bit.
+    //   geo_i[k * geo_ni + i], k = 0 r_i (cell centre), 1 r of the row whose source the reference's source arrays hold
+    //                          in row i (itself; the boundary image for ghost rows), 2 -2 pi rl^2, 3 rr^2 - rl^2,
+    //                          4 rr - rl, 5 rr^2 + rl^2 + rr rl, 6..8 the viscosity's vertex radii (rr, rl, rc)
+    //   geo_j[k * geo_nj + j], k = 0 cos(th_r) - cos(th_l), 1 -2 pi / 3 times that, 2 pi sin(th_l), 3 tan(th),
+    //                          4..6 the viscosity's sines at / around the vertex (sint, sinb, sinc)
+    const double* geo_i;
+    const double* geo_j;
+    int geo_ni, geo_nj;
+    int src_flip_xlo, src_flip_xhi;   // 1: that x boundary is "reflect" -> the ghost-row SOURCES change sign
 };
 
 struct alignas(16) SweepSmem {
@@ -83,7 +95,10 @@ struct alignas(16) SweepSmem {
 // the sign flipped there and identical to it for every other boundary type.
 // RIEMANN: 0 = HLLC (riemann_hllc), 1 = CGF (riemann_cgf + consFlux), 2 = low-Mach HLLC (riemann_hllc_lowspeed);
 // selected by compressible.riemann.
-template <class W, bool GRAV = false, int RIEMANN = 0>
+// SPH = true (with GRAV = true, RIEMANN = 1 -- the reference insists on CGF there): SphericalPolar geometry, i.e. the
+// coord_type == 1 branches of interface.states, get_external_sources, riemann_flux / consFlux,
+// apply_transverse_flux, the conservative update and the artificial viscosity.
+template <class W, bool GRAV = false, int RIEMANN = 0, bool SPH = false>
 struct SweepTask {
     W& w;
     const SweepArgs& A;
@@ -101,6 +116,13 @@ struct SweepTask {
         if (RIEMANN == 1) return cgf(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp, wall);
         if (RIEMANN == 2) return hllc_lm(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp);
         return hllc(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp);
+    }
+
+    // SphericalPolar: CGF flux without the pressure in the normal momentum, and the interface pressure
+    HD Flux riemann_p(double rho_l, double E_l, double mn_l, double mt_l, double rho_r, double E_r, double mn_r,
+                      double mt_r, const HllcPar& hp, bool wall, double& pface)
+    {
+        return cgf_impl<true>(rho_l, E_l, mn_l, mt_l, rho_r, E_r, mn_r, mt_r, hp, wall, pface);
     }
 
     // wait for the bulk copy of row r, convert cons -> prim in place, publish to the warp
@@ -169,6 +191,23 @@ struct SweepTask {
         const bool xwall = RIEMANN == 1 && A.xl_solid != 0;
         const bool ywall = RIEMANN == 1 && A.yl_solid != 0 && j == ng;
 
+        // SphericalPolar: this lane's theta factors (and those of column j + 1, whose cell volume and low-face area
+        // enter the corrections of the states this lane owns)
+        const int jg = (j < A.geo_nj - 1) ? j : A.geo_nj - 2;
+        const double g_cd = SPH ? A.geo_j[jg] : 0.0, g_kc = SPH ? A.geo_j[A.geo_nj + jg] : 0.0;
+        const double g_kc1 = SPH ? A.geo_j[A.geo_nj + jg + 1] : 0.0;
+        const double g_ps = SPH ? A.geo_j[2 * A.geo_nj + jg] : 0.0, g_ps1 = SPH ? A.geo_j[2 * A.geo_nj + jg + 1] : 0.0;
+        const double g_tn = SPH ? A.geo_j[3 * A.geo_nj + jg] : 1.0;
+        const double g_sint = SPH ? A.geo_j[4 * A.geo_nj + jg] : 0.0, g_sinb = SPH ? A.geo_j[5 * A.geo_nj + jg] : 0.0;
+        const double g_sinc = SPH ? A.geo_j[6 * A.geo_nj + jg] : 0.0;
+        const double* GI = A.geo_i;
+        auto gi = [&](int k, int r) { return GI[k * A.geo_ni + (r < 0 ? 0 : (r < A.geo_ni ? r : A.geo_ni - 1))]; };
+        auto area_x = [&](int r) { return fabs(gi(2, r) * g_cd); };                 // Ax(r, j): the low-r face
+        auto area_y = [&](int r) { return fabs(g_ps * gi(3, r)); };                 // Ay(r, j): the low-theta face
+        auto area_y1 = [&](int r) { return fabs(g_ps1 * gi(3, r)); };               // Ay(r, j + 1)
+        auto vol = [&](int r) { return fabs(g_kc * gi(4, r) * gi(5, r)); };         // V(r, j)
+        auto vol1 = [&](int r) { return fabs(g_kc1 * gi(4, r) * gi(5, r)); };       // V(r, j + 1)
+
         // raw U of the lane's own column is re-read from global (L2 hit: the bulk copy just
         // streamed it) so that the update adds the flux divergence to the unmodified state
         const long long jj = (j < A.pitch) ? j : A.pitch - 1;
@@ -198,6 +237,7 @@ struct SweepTask {
         Cons Fx_prev = {0, 0, 0, 0};                    // final x-flux at face (i-1)-1/2
         Cons U_prev = {0, 0, 0, 0};                     // raw U(i-1, j)
         double divU_prev = 0.0;                         // vertex divergence at (i-1 -1/2, j-1/2)
+        double pxT_prev = 0.0, pxF_prev = 0.0;          // SPH: interface pressures at face (i-1)-1/2 (transverse, final)
         double wmax_x = 0.0, wmax_y = 0.0;
 
         for (int i = i0 - 1; i <= i1; ++i) {
@@ -269,13 +309,40 @@ struct SweepTask {
                 Prim m, p;
                 trace_1d(q0.rho, q0.u, q0.v, q0.p, ldx[IRHO], ldx[IU], ldx[IV], ldx[IP], g, dtdx,
                          m.rho, m.u, m.v, m.p, p.rho, p.u, p.v, p.p);
+                if (SPH) {
+                    // geometric source of the divergence, dlogAx = 2 / r (interface.py:218-225)
+                    const double rs = -0.5 * A.dt * (2.0 / gi(0, i)) * q0.rho * q0.u;
+                    m.rho += rs; p.rho += rs; m.p += rs * g.cs2; p.p += rs * g.cs2;
+                }
                 XM = prim_to_cons(m, ginv1); XP = prim_to_cons(p, ginv1);
-                trace_1d(q0.rho, q0.v, q0.u, q0.p, ldy[IRHO], ldy[IV], ldy[IU], ldy[IP], g, dtdy,
+                // SPH: the cell's own length along theta, Ly = r dtheta
+                trace_1d(q0.rho, q0.v, q0.u, q0.p, ldy[IRHO], ldy[IV], ldy[IU], ldy[IP], g,
+                         SPH ? A.dt / (gi(0, i) * A.dy) : dtdy,
                          m.rho, m.v, m.u, m.p, p.rho, p.v, p.u, p.p);
+                if (SPH) {
+                    // dlogAy = cot(theta) / r (interface.py:227-234)
+                    const double rs = -0.5 * A.dt * (1.0 / (g_tn * gi(0, i))) * q0.rho * q0.v;
+                    m.rho += rs; p.rho += rs; m.p += rs * g.cs2; p.p += rs * g.cs2;
+                }
                 YM = prim_to_cons(m, ginv1); YP = prim_to_cons(p, ginv1);
             }
 
-            if (GRAV) {
+            if (SPH) {
+                // S_xmom = rho g + ymom^2 / (rho r), S_ymom = -xmom ymom / rho, S_ener = xmom g (radial gravity plus the
+                // geometric terms, simulation.py:117-124).  The reference fills the ghost cells of the source ARRAYS
+                // with their own BCs: for a ghost row that is the source of the row's boundary image -- the ghost
+                // state itself evaluated at the image's radius, sign flipped across a reflecting wall; ghost columns
+                // need nothing (the radius does not change and the parities of S match those of the state)
+                const bool flip = (i < ng && A.src_flip_xlo) || (i >= ihi && A.src_flip_xhi);
+                const double r = gi(1, i);
+                double sx = Uc.dens * A.grav + Uc.ymom * Uc.ymom / (Uc.dens * r);
+                double sy = -Uc.xmom * Uc.ymom / Uc.dens, se = Uc.xmom * A.grav;
+                if (flip) { sx = -sx; sy = -sy; se = -se; }
+                const double hx = 0.5 * A.dt * sx, hy = 0.5 * A.dt * sy, he = 0.5 * A.dt * se;
+                XM.xmom += hx; XP.xmom += hx; YM.xmom += hx; YP.xmom += hx;
+                XM.ymom += hy; XP.ymom += hy; YM.ymom += hy; YP.ymom += hy;
+                XM.ener += he; XP.ener += he; YM.ener += he; YP.ener += he;
+            } else if (GRAV) {
                 // U_xl[i+1], U_xr[i], U_yl[j+1], U_yr[j] += 0.5 dt S(i, j); S_ymom = rho g, S_ener = (rho v) g
                 const bool flip = (j < ng && A.src_flip_ylo) || (j >= jhi && A.src_flip_yhi);
                 // the state the ghost-cell source is evaluated from: the ghost state itself, except above an
@@ -296,9 +363,13 @@ struct SweepTask {
             }
 
             // ---- H. vertex divergence for the artificial viscosity ---------------------------
-            double divU = vertex_divU(Q(IU, i, cc), Q(IU, i, cc - 1), Q(IU, i - 1, cc), Q(IU, i - 1, cc - 1),
-                                      Q(IV, i, cc), Q(IV, i, cc - 1), Q(IV, i - 1, cc), Q(IV, i - 1, cc - 1),
-                                      dxinv, dyinv);
+            double divU = SPH
+                ? vertex_divU_sph(Q(IU, i, cc), Q(IU, i, cc - 1), Q(IU, i - 1, cc), Q(IU, i - 1, cc - 1),
+                                  Q(IV, i, cc), Q(IV, i, cc - 1), Q(IV, i - 1, cc), Q(IV, i - 1, cc - 1),
+                                  gi(6, i), gi(7, i), gi(8, i), A.dx, g_sint, g_sinb, g_sinc, A.dy)
+                : vertex_divU(Q(IU, i, cc), Q(IU, i, cc - 1), Q(IU, i - 1, cc), Q(IU, i - 1, cc - 1),
+                              Q(IV, i, cc), Q(IV, i, cc - 1), Q(IV, i - 1, cc), Q(IV, i - 1, cc - 1),
+                              dxinv, dyinv);
             double divU_jp1 = w.down(divU);
 
             // The first one / two iterations of a segment run F..M on not-yet-meaningful carried state
@@ -306,13 +377,31 @@ struct SweepTask {
             // it is used for real.  Keeping the body branch-free lets the scheduler interleave the
             // independent Riemann problems (F with J, I with L).
             Cons Fy;
+            double pyF = 0.0;                               // SPH: pressure of the final y-interface state of row i-1
             {
                 // ---- F. transverse x-flux at face i-1/2; dF_x of cell (i-1) -------------------
-                Flux f = riemann(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp, xwall && i == ng);
+                double pxT = 0.0;
+                Flux f = SPH ? riemann_p(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp, xwall && i == ng, pxT)
+                             : riemann(XPc.dens, XPc.ener, XPc.xmom, XPc.ymom, XM.dens, XM.ener, XM.xmom, XM.ymom, hp, xwall && i == ng);
                 Cons FxT = {f.dens, f.ener, f.mn, f.mt};
                 // ---- G. transverse correction of the y-face states of cell (i-1)
                 //         (unsplit_fluxes.py:463-471: U_yl[i,j+1], U_yr[i,j] -= dt/2dx * dF_x)
                 Cons YMp, YPp;
+                if (SPH) {
+                    // fluxes times face areas over the cell volume, then the radial pressure gradient
+                    // (unsplit_fluxes.py:463-490).  The "+" state of cell (i-1, j) is U_yl[i-1, j+1], which the
+                    // reference corrects with the volume of cell (i-1, j+1) -- the cell on the far side of the face
+                    const double a0 = area_x(i - 1), a1 = area_x(i);
+                    const double hv = (0.5 * A.dt) / vol(i - 1), hv1 = (0.5 * A.dt) / vol1(i - 1);
+                    const double dd = FxT.dens * a1 - FxT_prev.dens * a0, de = FxT.ener * a1 - FxT_prev.ener * a0;
+                    const double dmx = FxT.xmom * a1 - FxT_prev.xmom * a0, dmy = FxT.ymom * a1 - FxT_prev.ymom * a0;
+                    const double gp = (0.5 * A.dt) * (pxT - pxT_prev) / A.dx;
+                    YMp.dens = YMc.dens - hv * dd; YMp.ener = YMc.ener - hv * de;
+                    YMp.xmom = YMc.xmom - hv * dmx - gp; YMp.ymom = YMc.ymom - hv * dmy;
+                    YPp.dens = YPc.dens - hv1 * dd; YPp.ener = YPc.ener - hv1 * de;
+                    YPp.xmom = YPc.xmom - hv1 * dmx - gp; YPp.ymom = YPc.ymom - hv1 * dmy;
+                    pxT_prev = pxT;
+                } else {
                 YMp.dens = YMc.dens - hdtdx * (FxT.dens - FxT_prev.dens);
                 YMp.ener = YMc.ener - hdtdx * (FxT.ener - FxT_prev.ener);
                 YMp.xmom = YMc.xmom - hdtdx * (FxT.xmom - FxT_prev.xmom);
@@ -321,15 +410,17 @@ struct SweepTask {
                 YPp.ener = YPc.ener - hdtdx * (FxT.ener - FxT_prev.ener);
                 YPp.xmom = YPc.xmom - hdtdx * (FxT.xmom - FxT_prev.xmom);
                 YPp.ymom = YPc.ymom - hdtdx * (FxT.ymom - FxT_prev.ymom);
+                }
                 FxT_prev = FxT;
 
                 {
                     // ---- I. final y-flux of row i-1 at face j-1/2 (left state from lane-1) ----
                     double ld = w.up(YPp.dens), le = w.up(YPp.ener), lx = w.up(YPp.xmom), ly = w.up(YPp.ymom);
-                    Flux g = riemann(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp, ywall);
+                    Flux g = SPH ? riemann_p(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp, ywall, pyF)
+                                 : riemann(ld, le, ly, lx, YMp.dens, YMp.ener, YMp.ymom, YMp.xmom, hp, ywall);
                     Fy.dens = g.dens; Fy.ener = g.ener; Fy.ymom = g.mn; Fy.xmom = g.mt;
                     // viscosity (unsplit_fluxes.py:545-547); zero on the global +y face
-                    double avy = avisc_coeff(divU_prev, divU, A.dy, A.cvisc);
+                    double avy = avisc_coeff(divU_prev, divU, SPH ? gi(0, i - 1) * A.dy : A.dy, A.cvisc);
                     if (A.no_avisc_yhi && j == jhi) avy = 0.0;
                     double bd = w.up(U_prev.dens), be = w.up(U_prev.ener), bx = w.up(U_prev.xmom), by = w.up(U_prev.ymom);
                     Fy.dens += avy * (bd - U_prev.dens);
@@ -343,21 +434,38 @@ struct SweepTask {
             Cons XMp, XPp;
             {
                 double ld = w.up(YP.dens), le = w.up(YP.ener), lx = w.up(YP.xmom), ly = w.up(YP.ymom);
-                Flux g = riemann(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp, ywall);
+                double pyT = 0.0;
+                Flux g = SPH ? riemann_p(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp, ywall, pyT)
+                             : riemann(ld, le, ly, lx, YM.dens, YM.ener, YM.ymom, YM.xmom, hp, ywall);
+                if (SPH) { const double ay = area_y(i); g.dens *= ay; g.ener *= ay; g.mn *= ay; g.mt *= ay; }
                 // g.mn is the y-momentum flux, g.mt the x-momentum flux
                 double dd = w.down(g.dens) - g.dens, de = w.down(g.ener) - g.ener;
                 double dmy = w.down(g.mn) - g.mn, dmx = w.down(g.mt) - g.mt;
                 // ---- K. (unsplit_fluxes.py:453-461: U_xl[i+1,j], U_xr[i,j] -= dt/2dy * dF_y)
+                if (SPH) {
+                    // unsplit_fluxes.py:453-461, 478-484: the "+" state of cell (i, j) is U_xl[i+1, j], corrected with
+                    // the volume and theta-length of cell (i+1, j)
+                    const double dp = w.down(pyT) - pyT;
+                    const double hv = (0.5 * A.dt) / vol(i), hv1 = (0.5 * A.dt) / vol(i + 1);
+                    XMp.dens = XM.dens - hv * dd; XMp.ener = XM.ener - hv * de;
+                    XMp.xmom = XM.xmom - hv * dmx; XMp.ymom = XM.ymom - hv * dmy - (0.5 * A.dt) * dp / (gi(0, i) * A.dy);
+                    XPp.dens = XP.dens - hv1 * dd; XPp.ener = XP.ener - hv1 * de;
+                    XPp.xmom = XP.xmom - hv1 * dmx; XPp.ymom = XP.ymom - hv1 * dmy - (0.5 * A.dt) * dp / (gi(0, i + 1) * A.dy);
+                } else {
                 XMp.dens = XM.dens - hdtdy * dd; XMp.ener = XM.ener - hdtdy * de;
                 XMp.xmom = XM.xmom - hdtdy * dmx; XMp.ymom = XM.ymom - hdtdy * dmy;
                 XPp.dens = XP.dens - hdtdy * dd; XPp.ener = XP.ener - hdtdy * de;
                 XPp.xmom = XP.xmom - hdtdy * dmx; XPp.ymom = XP.ymom - hdtdy * dmy;
+                }
             }
 
             {
                 // ---- L. final x-flux at face i-1/2 ------------------------------------------
-                Flux f = riemann(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
-                                 XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp, xwall && i == ng);
+                double pxF = 0.0;
+                Flux f = SPH ? riemann_p(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
+                                         XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp, xwall && i == ng, pxF)
+                             : riemann(XPpc.dens, XPpc.ener, XPpc.xmom, XPpc.ymom,
+                                       XMp.dens, XMp.ener, XMp.xmom, XMp.ymom, hp, xwall && i == ng);
                 Cons Fx = {f.dens, f.ener, f.mn, f.mt};
                 double avx = avisc_coeff(divU, divU_jp1, A.dx, A.cvisc);
                 if (A.no_avisc_xhi && i == ihi) avx = 0.0;
@@ -370,11 +478,39 @@ struct SweepTask {
                     // ---- M. conservative update of cell (i-1, j) (simulation.py:377-384) ------
                     double fd = w.down(Fy.dens), fe = w.down(Fy.ener), fx = w.down(Fy.xmom), fy = w.down(Fy.ymom);
                     Cons Un;
+                    if (SPH) {
+                        // simulation.py:377-396: area-weighted flux differences over the cell volume, then the pressure
+                        // gradients along r and theta
+                        const double a0 = area_x(i - 1), a1 = area_x(i), b0 = area_y(i - 1), b1 = area_y1(i - 1);
+                        const double dtv = A.dt / vol(i - 1);
+                        Un.dens = U_prev.dens + dtv * (Fx_prev.dens * a0 - Fx.dens * a1 + Fy.dens * b0 - fd * b1);
+                        Un.ener = U_prev.ener + dtv * (Fx_prev.ener * a0 - Fx.ener * a1 + Fy.ener * b0 - fe * b1);
+                        Un.xmom = U_prev.xmom + dtv * (Fx_prev.xmom * a0 - Fx.xmom * a1 + Fy.xmom * b0 - fx * b1);
+                        Un.ymom = U_prev.ymom + dtv * (Fx_prev.ymom * a0 - Fx.ymom * a1 + Fy.ymom * b0 - fy * b1);
+                        Un.xmom -= A.dt * (pxF - pxF_prev) / A.dx;
+                        Un.ymom -= A.dt * (w.down(pyF) - pyF) / (gi(0, i - 1) * A.dy);
+                        // sources, predictor-corrector with the SphericalPolar branches of get_external_sources
+                        // (simulation.py:398-423, :117-124, :135-146)
+                        const double r = gi(0, i - 1), g = A.grav;
+                        const double so_xg = U_prev.dens * g;
+                        const double so_x = so_xg + U_prev.ymom * U_prev.ymom / (U_prev.dens * r);
+                        const double so_y = -U_prev.xmom * U_prev.ymom / U_prev.dens, so_e = U_prev.xmom * g;
+                        Un.xmom += A.dt * so_x; Un.ymom += A.dt * so_y; Un.ener += A.dt * so_e;
+                        const double sn_xg = Un.dens * g;
+                        const double sn_e = (Un.xmom + 0.5 * A.dt * (sn_xg - so_xg)) * g;
+                        const double sn_x = sn_xg + Un.ymom * Un.ymom / (Un.dens * r);
+                        const double sn_y = -Un.xmom * Un.ymom / Un.dens;
+                        Un.xmom += 0.5 * A.dt * (sn_x - so_x);
+                        Un.ymom += 0.5 * A.dt * (sn_y - so_y);
+                        Un.ener += 0.5 * A.dt * (sn_e - so_e);
+                        pxF_prev = pxF;
+                    } else {
                     Un.dens = U_prev.dens + dtdx * (Fx_prev.dens - Fx.dens) + dtdy * (Fy.dens - fd);
                     Un.ener = U_prev.ener + dtdx * (Fx_prev.ener - Fx.ener) + dtdy * (Fy.ener - fe);
                     Un.xmom = U_prev.xmom + dtdx * (Fx_prev.xmom - Fx.xmom) + dtdy * (Fy.xmom - fx);
                     Un.ymom = U_prev.ymom + dtdx * (Fx_prev.ymom - Fx.ymom) + dtdy * (Fy.ymom - fy);
-                    if (GRAV) {
+                    }
+                    if (GRAV && !SPH) {
                         // U += dt S(U_old); S_new from the new density and a time-centred y-momentum;
                         // U += dt/2 (S_new - S_old)
                         const double hp = A.heat ? A.heat_rate * A.heat[(long long)(i - 1) * A.pitch + jj] : 0.0;

@@ -144,6 +144,80 @@ class Cartesian2d(Grid2d):
                 f"ymax = {self.ymax}, nx = {self.nx}, ny = {self.ny}, ng = {self.ng}")
 
 
+def spherical_sweep_tables(grid, nj, xlb, xrb):
+    """the separable geometry tables the SphericalPolar instantiation of the sweep reads (include/pyro2b200.h,
+    p2b_comp_params.geo_i / geo_j), as host arrays: geo_i (9, qx), geo_j (7, nj) with nj >= qy + 1.  Every entry is the
+    sub-expression of mesh/patch.py:272-305 (or of the viscosity's vertex coordinates, interface.py:333-341) that
+    depends on one index only, evaluated with numpy like the reference, so that the kernel's products -- formed in the
+    reference's order -- give its 2-d arrays bit for bit.  xlb / xrb: the x boundary types; they decide which row's
+    radius the reference's ghost-filled source arrays carry in the ghost rows (row 1 of geo_i)"""
+    g = grid
+    xl, xr, x = g.xl, g.xr, g.x
+    ximg = x.copy()
+    for side, btype in (("lo", xlb), ("hi", xrb)):
+        for k in range(g.ng):
+            i = g.ilo - 1 - k if side == "lo" else g.ihi + 1 + k
+            if btype == "periodic":
+                src = i + g.nx if side == "lo" else i - g.nx
+            elif str(btype).startswith("reflect"):
+                src = g.ilo + k if side == "lo" else g.ihi - k
+            else:                                   # zero-gradient copies (outflow and everything that fills like it)
+                src = g.ilo if side == "lo" else g.ihi
+            ximg[i] = x[src]
+    idx = np.arange(g.qx)
+    geo_i = np.stack([x, ximg, -2.0 * np.pi * xl ** 2, xr ** 2 - xl ** 2, xr - xl, xr ** 2 + xl ** 2 + xr * xl,
+                      (idx + 0.5 - g.ng) * g.dx + g.xmin, (idx - 0.5 - g.ng) * g.dx + g.xmin, (idx - g.ng) * g.dx + g.xmin])
+    jdx = np.arange(nj)
+    yl = (jdx - g.ng) * g.dy + g.ymin
+    yr = (jdx + 1.0 - g.ng) * g.dy + g.ymin
+    y = 0.5 * (yl + yr)
+    cd = np.cos(yr) - np.cos(yl)
+    geo_j = np.stack([cd, -2.0 * np.pi / 3.0 * cd, np.pi * np.sin(yl), np.tan(y),
+                      np.sin((jdx + 0.5 - g.ng) * g.dy + g.ymin), np.sin((jdx - 0.5 - g.ng) * g.dy + g.ymin),
+                      np.sin((jdx - g.ng) * g.dy + g.ymin)])
+    return np.ascontiguousarray(geo_i), np.ascontiguousarray(geo_j)
+
+
+class SphericalPolar(Grid2d):
+    """spherical polar geometry with azimuthal symmetry, x = r, y = theta (patch.py:242-312): coord_type 1; side
+    lengths, face areas (on the low faces), cell volumes and logarithmic area derivatives as device arrays"""
+
+    def __init__(self, nx, ny, *, ng=1, xmin=0.2, xmax=1.0, ymin=0.0, ymax=1.0, device=None):
+        super().__init__(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device=device)
+        assert ymin >= 0.0 and ymax <= np.pi, "y or \u03b8 should be within [0, \u03c0]."
+        assert xmin - ng * self.dx >= 0.0, \
+            "xmin (r-direction), must be large enough so ghost cell doesn't have negative x."
+        self.coord_type = 1
+
+    def _geom(self, name):
+        if name not in self._lazy:
+            x2d, _ = np.meshgrid(self.x, self.y, indexing="ij")
+            xl2d, yl2d = np.meshgrid(self.xl, self.yl, indexing="ij")
+            xr2d, yr2d = np.meshgrid(self.xr, self.yr, indexing="ij")
+            y2d = np.meshgrid(self.x, self.y, indexing="ij")[1]
+            host = {"Lx": lambda: np.full((self.qx, self.qy), self.dx), "Ly": lambda: x2d * self.dy,
+                    "Ax": lambda: np.abs(-2.0 * np.pi * xl2d ** 2 * (np.cos(yr2d) - np.cos(yl2d))),
+                    "Ay": lambda: np.abs(np.pi * np.sin(yl2d) * (xr2d ** 2 - xl2d ** 2)),
+                    "dlogAx": lambda: 2.0 / x2d, "dlogAy": lambda: 1.0 / (np.tan(y2d) * x2d),
+                    "V": lambda: np.abs(-2.0 * np.pi / 3.0 * (np.cos(yr2d) - np.cos(yl2d)) * (xr2d - xl2d) *
+                                        (xr2d ** 2 + xl2d ** 2 + xr2d * xl2d))}[name]()
+            self._lazy[name] = ArrayIndexer(torch.from_numpy(np.ascontiguousarray(host)).to(self.device), grid=self)
+        return self._lazy[name]
+
+    Lx = property(lambda self: self._geom("Lx"))
+    Ly = property(lambda self: self._geom("Ly"))
+    Ax = property(lambda self: self._geom("Ax"))
+    Ay = property(lambda self: self._geom("Ay"))
+    dlogAx = property(lambda self: self._geom("dlogAx"))
+    dlogAy = property(lambda self: self._geom("dlogAy"))
+    V = property(lambda self: self._geom("V"))
+
+    def __str__(self):
+        return ("Spherical Polar 2D Grid: Define x : r, y : \u03b8. " +
+                f"xmin (r) = {self.xmin}, xmax= {self.xmax}, ymin = {self.ymin}, ymax = {self.ymax}, "
+                f"nx = {self.nx}, ny = {self.ny}, ng = {self.ng}")
+
+
 class CellCenterData2d:
     """named cell-centred variables on a grid (patch.py:315-795): register_var / set_aux / create,
     then get_var, fill_BC, restrict, prolong, ..."""

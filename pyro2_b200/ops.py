@@ -97,14 +97,20 @@ def cfl_wavemax(planes, nx, ny, ng, gamma, scratch):
 
 def comp_params(gamma=1.4, z0=0.75, z1=0.85, delta=0.33, cvisc=0.1, limiter=2, use_flattening=1,
                 no_avisc_xhi=1, no_avisc_yhi=1, grav=0.0, src_flip_ylo=0, src_flip_yhi=0, riemann="HLLC",
-                xl_solid=0, yl_solid=0, heat_rate=0.0, heat_profile=None, sponge=None, src_copy_yhi=0):
+                xl_solid=0, yl_solid=0, heat_rate=0.0, heat_profile=None, sponge=None, src_copy_yhi=0,
+                geometry=None, src_flip_xlo=0, src_flip_xhi=0):
     """heat_profile: a (qx, pitch) CUDA plane laid out like one state plane (the caller keeps it alive);
-    sponge: (rho_begin, rho_full, timescale) or None"""
+    sponge: (rho_begin, rho_full, timescale) or None; geometry: (geo_i, geo_j) device tables of a SphericalPolar
+    grid (mesh.patch.SphericalPolar.sweep_tables), the caller keeps them alive"""
     sp = sponge or (0.0, 0.0, 1.0)
     return _lib.CompParams(gamma, z0, z1, delta, cvisc, limiter, use_flattening, no_avisc_xhi, no_avisc_yhi,
                            grav, src_flip_ylo, src_flip_yhi, {"HLLC": 0, "CGF": 1, "HLLC_lm": 2}[riemann], xl_solid, yl_solid,
                            heat_rate, None if heat_profile is None else heat_profile.data_ptr(),
-                           int(sponge is not None), sp[0], sp[1], sp[2], src_copy_yhi)
+                           int(sponge is not None), sp[0], sp[1], sp[2], src_copy_yhi,
+                           None if geometry is None else geometry[0].data_ptr(),
+                           None if geometry is None else geometry[1].data_ptr(),
+                           0 if geometry is None else geometry[0].shape[1], 0 if geometry is None else geometry[1].shape[1],
+                           src_flip_xlo, src_flip_xhi)
 
 
 def compressible_sweep(Uin, Uout, nx, ny, ng, dx, dy, dt, params, scratch):

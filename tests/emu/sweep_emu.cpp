@@ -78,6 +78,7 @@ struct LaneCtx {
     int ntasks;
     bool grav;
     int riemann;
+    bool sph;
 };
 
 void* lane_main(void* p)
@@ -85,7 +86,9 @@ void* lane_main(void* p)
     LaneCtx* c = (LaneCtx*)p;
     EmuWarp w{c->ws, c->lane};
     auto go = [&](auto& T) { for (int t = 0; t < c->ntasks; ++t) T.run(t % c->A->nstrips, t / c->A->nstrips); };
-    if (c->riemann == 2) {
+    if (c->sph) {
+        pyro::SweepTask<EmuWarp, true, 1, true> T(w, *c->A, *c->smem, 0u); go(T);
+    } else if (c->riemann == 2) {
         if (c->grav) { pyro::SweepTask<EmuWarp, true, 2> T(w, *c->A, *c->smem, 0u); go(T); }
         else { pyro::SweepTask<EmuWarp, false, 2> T(w, *c->A, *c->smem, 0u); go(T); }
     } else if (c->riemann == 1) {
@@ -107,7 +110,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
                                       int seglen, uint64_t* scratch, double* dbg, double grav, int src_flip_ylo,
                                       int src_flip_yhi, int riemann, int xl_solid, int yl_solid, const double* heat,
                                       double heat_rate, int do_sponge, double sp_begin, double sp_full, double sp_tau,
-                                      int src_copy_yhi)
+                                      int src_copy_yhi, const double* geo_i, const double* geo_j, int geo_ni, int geo_nj,
+                                      int src_flip_xlo, int src_flip_xhi)
 {
     pyro::SweepArgs A;
     A.Uin = Uin; A.Uout = Uout; A.plane_stride = plane_stride; A.pitch = pitch;
@@ -120,6 +124,8 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     A.heat = heat; A.heat_rate = heat_rate; A.do_sponge = do_sponge;
     A.sponge_rho_begin = sp_begin; A.sponge_rho_full = sp_full; A.sponge_timescale = sp_tau;
     A.src_copy_yhi = src_copy_yhi;
+    A.geo_i = geo_i; A.geo_j = geo_j; A.geo_ni = geo_ni; A.geo_nj = geo_nj;
+    A.src_flip_xlo = src_flip_xlo; A.src_flip_xhi = src_flip_xhi;
     A.nstrips = (ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
     A.seglen = seglen;
     A.nsegs = (nx + seglen - 1) / seglen;
@@ -141,7 +147,7 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
     LaneCtx ctx[32];
     pthread_t th[32];
     for (int l = 0; l < 32; ++l) {
-        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0 || heat != nullptr || do_sponge != 0, riemann};
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0 || heat != nullptr || do_sponge != 0, riemann, geo_i != nullptr};
         pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
     }
     for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);

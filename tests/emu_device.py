@@ -99,7 +99,8 @@ class EmuLibrary:
                                           p.no_avisc_xhi, p.no_avisc_yhi, seglen, scratch, None,
                                           p.grav, p.src_flip_ylo, p.src_flip_yhi, p.riemann, p.xl_solid, p.yl_solid,
                                           p.heat_profile, p.heat_rate, p.do_sponge, p.sponge_rho_begin, p.sponge_rho_full,
-                                          p.sponge_timescale, p.src_copy_yhi)
+                                          p.sponge_timescale, p.src_copy_yhi, p.geo_i, p.geo_j, p.geo_ni, p.geo_nj,
+                                          p.src_flip_xlo, p.src_flip_xhi)
 
     def _sweep_info(self, a, b, c):
         for ref, val in zip((a, b, c), self._info):

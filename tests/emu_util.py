@@ -86,7 +86,8 @@ def load_sweep_emu():
     lib.emu_compressible_sweep.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_longlong] +
                                            [C.c_double] * 8 + [C.c_int] * 5 + [C.c_void_p] * 2 +
                                            [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
-                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int])
+                                           [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int] +
+                                           [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])
     _LIBS["sweep"] = lib
     return lib
 
