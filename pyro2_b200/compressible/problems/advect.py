@@ -27,6 +27,16 @@ def init_data(my_data, rp):
     y = np.broadcast_to(g.y[None, :], (g.qx, g.qy))
     dens = 1.0 + np.exp(-60.0 * ((x - xctr) ** 2 + (y - yctr) ** 2))
     u = v = 1.0                      # diagonal flow
+    if getattr(g, "coord_type", 0) == 1:
+        # SphericalPolar (advect.py:57-72): the blob sits at mid radius on the bisector of the theta range (in the
+        # Cartesian coordinates r sin(theta), r cos(theta)) and moves along theta
+        xmin, xmax = rp.get_param("mesh.xmin"), rp.get_param("mesh.xmax")
+        ymin, ymax = rp.get_param("mesh.ymin"), rp.get_param("mesh.ymax")
+        xc = 0.5 * (xmin + xmax) * np.sin((ymin + ymax) * 0.25)
+        yc = 0.5 * (xmin + xmax) * np.cos((ymin + ymax) * 0.25)
+        xx, yy = x * np.sin(y), x * np.cos(y)
+        dens = 1.0 + np.exp(-120.0 * ((xx - xc) ** 2 + (yy - yc) ** 2))
+        u, v = 0.0, 1.0
     xmom, ymom = dens * u, dens * v
     p = 1.0
     my_data.get_var("density")[:, :] = dens

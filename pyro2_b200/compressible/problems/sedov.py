@@ -32,6 +32,16 @@ def init_data(my_data, rp):
     E_sedov = 1.0
     p_ambient = 1.e-5
 
+    if getattr(g, "coord_type", 0) == 1:
+        # SphericalPolar (sedov.py:84-93): a large energy inside r < r_init, nothing sub-sampled
+        ener = np.full((g.qx, g.qy), 1.e-6 / (gamma - 1.0))
+        ener[np.broadcast_to(g.x[:, None], (g.qx, g.qy)) < r_init] = 1.e6
+        my_data.get_var("density")[:, :] = 1.0
+        my_data.get_var("x-momentum")[:, :] = 0.0
+        my_data.get_var("y-momentum")[:, :] = 0.0
+        my_data.get_var("energy")[:, :] = ener
+        return
+
     ener = np.full((g.qx, g.qy), p_ambient / (gamma - 1.0))
 
     # zones whose centre is within 2 r_init of the centre get an area-weighted pressure from

@@ -18,6 +18,7 @@ import torch
 
 from .. import ops
 from ..mesh import boundary as bnd
+from ..mesh import patch
 from ..simulation_null import NullSimulation, bc_setup, grid_setup
 from ..util import msg
 from . import BC, derives, eos
@@ -85,6 +86,10 @@ class Simulation(NullSimulation):
         riemann_method = rp.get_param("compressible.riemann")
         if riemann_method not in ("HLLC", "HLLC_lm", "CGF"):
             msg.fail("ERROR: Riemann solver undefined")
+        self._spherical = getattr(my_grid, "coord_type", 0) == 1
+        if self._spherical and riemann_method != "CGF":
+            # the reference refuses HLLC (simulation.py:201-209): the update needs the interface pressure
+            msg.fail("ERROR: the SphericalPolar geometry needs the CGF Riemann solver")
         # solver-specific boundary types (simulation.py:212-214)
         bnd.define_bc("hse", BC.user, is_solid=False)
         bnd.define_bc("ambient", BC.user, is_solid=False)
@@ -136,6 +141,21 @@ class Simulation(NullSimulation):
         self._wave_version = None     # cc_data.version for which the cached wave speeds are valid
         self._pending_status = False
 
+        self._geometry = None
+        if self._spherical:
+            if self._heating is not None or rp.get_param("sponge.do_sponge") or any(
+                    t in bnd.ext_bcs for t in bc.names()):
+                msg.fail("ERROR: heating, sponge and the hse / ambient / ramp boundaries are not built for SphericalPolar grids")
+            gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1), bc.xlb, bc.xrb)
+            dev = my_data.planes.device
+            self._geometry = (torch.from_numpy(gi).to(dev), torch.from_numpy(gj).to(dev))
+            # across a "reflect" x boundary the reference's source arrays change sign (their own BCs, odd for the
+            # normal momentum's source, with the state's parities: every product of them is -1); the literal
+            # reflect-even / reflect-odd types and everything else leave the sign alone
+            self._src_flip_x = (int(rp.get_param("mesh.xlboundary") == "reflect"), int(rp.get_param("mesh.xrboundary") == "reflect"))
+            # ... and no flips in y: the parities of the spherical sources match those of the state there
+            self._src_flip = (0, 0)
+
         self.problem_func(self.cc_data, self.rp)
         self._heat_rate, self._heat_plane = 0.0, None
         if self._heating is not None:
@@ -167,6 +187,9 @@ class Simulation(NullSimulation):
                                src_copy_yhi=int(self.cc_data.BCs["density"].yrb == "ambient"),
                                sponge=(rp.get_param("sponge.sponge_rho_begin"), rp.get_param("sponge.sponge_rho_full"),
                                        rp.get_param("sponge.sponge_timescale")) if rp.get_param("sponge.do_sponge") else None,
+                               geometry=self._geometry,
+                               src_flip_xlo=self._src_flip_x[0] if self._geometry is not None else 0,
+                               src_flip_xhi=self._src_flip_x[1] if self._geometry is not None else 0,
                                riemann=rp.get_param("compressible.riemann"),
                                xl_solid=int(self.solid.xl) if (self.decomposition is None or self.decomposition.is_first) else 0,
                                yl_solid=int(self.solid.yl))
@@ -196,6 +219,16 @@ class Simulation(NullSimulation):
         (SURVEY.md 9.2-3)."""
         cfl = self.rp.get_param("driver.cfl")
         g = self.cc_data.grid
+        if getattr(self, "_spherical", False):
+            # min(Lx / (|u| + cs), Ly / (|v| + cs)) over the whole array (simulation.py:285-288): Ly = r dtheta shrinks
+            # towards the inner ghost rows, so the ghost cells can set the step and the fused maxima do not apply
+            if self._pending_status:
+                self._read_scratch()
+            u, v, cs = self.cc_data.get_var(["velocity", "soundspeed"])
+            xtmp = g.Lx.t() / (u.t().abs() + cs.t())
+            ytmp = g.Ly.t() / (v.t().abs() + cs.t())
+            self.dt = cfl * float(min(xtmp.min(), ytmp.min()))
+            return
         standard = all(t not in bnd.ext_bcs for b in self.cc_data.BCs.values() for t in b.names())
         if self._wave_version is not None and self._wave_version == self.cc_data.version and standard:
             wx, wy = self._read_scratch()

@@ -1,5 +1,7 @@
 """Solver-independent simulation scaffolding: mirror of pyro/simulation_null.py
 (grid_setup :10-68, bc_setup :71-112, NullSimulation :115-300)."""
+import numpy as np
+
 from .mesh import boundary as bnd
 from .mesh import patch
 from .util import msg
@@ -23,8 +25,20 @@ def grid_setup(rp, ng=1, decomposition=None):
     ymin = _param(rp, "mesh.ymin", 0.0)
     ymax = _param(rp, "mesh.ymax", 1.0)
     grid_type = _param(rp, "mesh.grid_type", "Cartesian2d")
+    if grid_type == "SphericalPolar":
+        # x = r, y = theta (simulation_null.py:46-68); single GPU
+        if decomposition is not None and decomposition.size > 1:
+            raise ValueError("SphericalPolar grids are not decomposed")
+        my_grid = patch.SphericalPolar(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)
+        # the polar axis is a reflecting boundary
+        if ymin <= 0.05:
+            rp.set_param("mesh.ylboundary", "reflect")
+            msg.warning("With SphericalPolar grid, mesh.ylboundary auto set to reflect when ymin ~ 0")
+        if abs(np.pi - ymax) <= 0.05:
+            rp.set_param("mesh.yrboundary", "reflect")
+            msg.warning("With SphericalPolar grid, mesh.yrboundary auto set to reflect when ymax ~ pi")
+        return my_grid
     if grid_type != "Cartesian2d":
-        # SphericalPolar is outside the B200 hot-path scope
         raise ValueError("Unsupported grid type!")
     if decomposition is not None and decomposition.size > 1:
         if decomposition.local_nx(nx) < ng:

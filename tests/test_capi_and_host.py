@@ -194,6 +194,7 @@ def test_compute_timestep_limits():
     ("compressible", "comp_convection16.npz", None),
     ("compressible", "comp_rt2_48.npz", None), ("compressible", "comp_rt_multimode16.npz", None),
     ("compressible", "comp_ramp64.npz", None),
+    ("compressible", "comp_sedov_sph32.npz", None), ("compressible", "comp_advect_sph32.npz", None),
     ("burgers", "burgers_converge32.npz", ["x-velocity", "y-velocity"]),
     ("burgers", "burgers_tophat32.npz", ["x-velocity", "y-velocity"]),
     ("incompressible", "incomp_shear32.npz", ["x-velocity", "y-velocity"]),
@@ -225,9 +226,10 @@ def test_problem_initial_conditions_match_reference(solver, fname, names):
         rp.set_param(k, v)
     rp.set_param("driver.verbose", 0)
     # explicit host device: data containers work there (the kernels do not); the product default is CUDA
-    g = patch.Cartesian2d(rp.get_param("mesh.nx"), rp.get_param("mesh.ny"), ng=4, xmin=rp.get_param("mesh.xmin"),
-                          xmax=rp.get_param("mesh.xmax"), ymin=rp.get_param("mesh.ymin"), ymax=rp.get_param("mesh.ymax"),
-                          device="cpu") if solver != "diffusion" else \
+    grid_class = patch.SphericalPolar if inputs.get("mesh.grid_type") == "SphericalPolar" else patch.Cartesian2d
+    g = grid_class(rp.get_param("mesh.nx"), rp.get_param("mesh.ny"), ng=4, xmin=rp.get_param("mesh.xmin"),
+                   xmax=rp.get_param("mesh.xmax"), ymin=rp.get_param("mesh.ymin"), ymax=rp.get_param("mesh.ymax"),
+                   device="cpu") if solver != "diffusion" else \
         patch.Cartesian2d(rp.get_param("mesh.nx"), rp.get_param("mesh.ny"), ng=1, xmin=rp.get_param("mesh.xmin"),
                           xmax=rp.get_param("mesh.xmax"), ymin=rp.get_param("mesh.ymin"), ymax=rp.get_param("mesh.ymax"),
                           device="cpu")

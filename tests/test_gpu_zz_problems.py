@@ -1,7 +1,7 @@
 """Further stock problems through the public Pyro API against reference-generated fixtures: the second and the
 multi-mode Rayleigh-Taylor setups, double Mach reflection with its "ramp" boundaries (device slice assignments
-plus host-evaluated top rows), the low-Mach HLLC solver (RIEMANN = 2 instantiations of the sweep), the Burgers
-convergence and tophat problems.  Same kernels and code paths as
+plus host-evaluated top rows), the low-Mach HLLC solver (RIEMANN = 2 instantiations of the sweep), SphericalPolar
+grids (the SPH instantiation), the Burgers convergence and tophat problems.  Same kernels and code paths as
 the rt16 / burgers_test cases in test_gpu_api.py / test_gpu_flow.py; only the initial conditions differ (those
 are checked on the CPU in test_capi_and_host.py)."""
 import numpy as np
@@ -13,7 +13,7 @@ from golden_util import load_comp, load_flow
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["rt2_48", "rt_multimode16", "ramp64", "gresho40_lm", "sedov32_lm"])
+@pytest.mark.parametrize("name", ["rt2_48", "rt_multimode16", "ramp64", "gresho40_lm", "sedov32_lm", "sedov_sph32", "advect_sph32"])
 def test_pyro_compressible_rt_variants_match_reference(name):
     from pyro2_b200.pyro_sim import Pyro
     z, rp, inputs = load_comp(name)

@@ -21,6 +21,9 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
     grav = rp.get("compressible.grav", 0.0)
     gamma = rp["eos.gamma"]
     bcs = var_bcs(rp)
+    geom = None
+    if rp.get("mesh.grid_type", "Cartesian2d") == "SphericalPolar":
+        geom = oracle.spherical_geometry(nx, ny, ng, rp["mesh.xmin"], rp["mesh.xmax"], rp["mesh.ymin"], rp["mesh.ymax"])
     xc = (np.arange(nx + 2 * ng) + 0.5 - ng) * dx + rp["mesh.xmin"]
     yc = (np.arange(ny + 2 * ng) + 0.5 - ng) * dy + rp["mesh.ymin"]
     prm = oracle.comp_params(gamma=gamma, z0=rp["compressible.z0"], z1=rp["compressible.z1"],
@@ -31,7 +34,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
                              heat_rate=float(z["heat_rate"]) if "heat_rate" in z else 0.0,
                              heat_profile=z["heat_profile"] if "heat_profile" in z else None,
                              sponge=(rp["sponge.sponge_rho_begin"], rp["sponge.sponge_rho_full"], rp["sponge.sponge_timescale"])
-                             if rp.get("sponge.do_sponge", 0) else None)
+                             if rp.get("sponge.do_sponge", 0) else None, geom=geom)
     ambient = None
     if "ambient" in z:        # compressible/BC.py:142-168: constant state above the top boundary
         ar, au, av, ap = (float(x) for x in z["ambient"])
@@ -50,7 +53,8 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
             for s_, side in enumerate(("xlb", "xrb", "ylb", "yrb")):      # user boundaries after the standard ones, in this order
                 if bcs[k][s_] == "ramp":
                     oracle.fill_ramp(P[k], k, side, ng, xc, yc, dx, dy, t, gamma)
-        dt = oracle.cfl_dt(oracle.from_planes(P), ng, dx, dy, gamma, rp["driver.cfl"])
+        dt = oracle.cfl_dt(oracle.from_planes(P), ng, dx, dy, gamma, rp["driver.cfl"]) if geom is None else \
+            oracle.cfl_dt_spherical(oracle.from_planes(P), gamma, rp["driver.cfl"], geom)
         # NullSimulation.compute_timestep (simulation_null.py:222-244)
         dt = rp["driver.init_tstep_factor"] * dt if n == 0 else min(rp["driver.max_dt_change"] * dt_old, dt)
         dt_old = dt
@@ -68,7 +72,7 @@ def _run_oracle(z, rp, nsteps=None, fix_dt=-1.0):
 
 @pytest.mark.parametrize("name", ["sedov64", "quad64", "sod_x", "kh32", "acoustic64", "advect32", "gresho40",
                                   "bubble32", "rt16", "hse16", "rt16_reflect", "sedov32_cgf", "quad32_cgf_walls",
-                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16", "ramp64", "gresho40_lm", "sedov32_lm"])
+                                  "heating32", "plume32", "convection16", "rt2_48", "rt_multimode16", "ramp64", "gresho40_lm", "sedov32_lm", "sedov_sph32", "advect_sph32"])
 def test_compressible_run_matches_reference(name):
     z, rp, inputs = load_comp(name)
     U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
