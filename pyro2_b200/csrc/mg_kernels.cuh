@@ -84,13 +84,15 @@ __device__ __forceinline__ void store_with_ghosts(double* v, int ni, int n, int 
     double glo = 0.0, ghi = 0.0;
     if (lo) { glo = ghost_lo(val, b.xl, b.xlv, j, dx); v[j] = glo; }
     if (hi) { ghi = ghost_hi(val, b.xr, b.xrv, j, dx); v[(long long)(ni + 1) * pitch + j] = ghi; }
+    // y-side values are indexed with the global row; a slab's halo row across the periodic x boundary wraps
+    const int grow = ioff + i < 1 ? ioff + i + n : (ioff + i > n ? ioff + i - n : ioff + i);
     if (j == syl) {
-        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, ioff + i, dy);
+        v[(long long)i * pitch] = ghost_lo(val, b.yl, b.ylv, grow, dy);
         if (lo) v[0] = ghost_lo(glo, b.yl, b.ylv, ioff, dy);
         if (hi) v[(long long)(ni + 1) * pitch] = ghost_lo(ghi, b.yl, b.ylv, ioff + ni + 1, dy);
     }
     if (j == syh) {
-        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, ioff + i, dy);
+        v[(long long)i * pitch + n + 1] = ghost_hi(val, b.yr, b.yrv, grow, dy);
         if (lo) v[n + 1] = ghost_hi(glo, b.yr, b.yrv, ioff, dy);
         if (hi) v[(long long)(ni + 1) * pitch + n + 1] = ghost_hi(ghi, b.yr, b.yrv, ioff + ni + 1, dy);
     }
@@ -396,11 +398,15 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                 // domain edges: the ghost value fill_BC would hold, from the cell's own current value
                 // (inhomogeneous boundary values are indexed by the cell's own row / column: a halo cell that is the
                 // periodic image of an interior cell uses that cell's index)
+                // The y-side values are indexed with the GLOBAL row: on a slab, a halo row received from the
+                // neighbour across the periodic x boundary lies outside 1..n before the wrap.
                 const int gi = xper ? wrap1(gi0 + r, ni) : gi0 + r, gj = yper ? wrap1(gj0 + a, n) : gj0 + a;
+                int grow = L.ioff + gi;
+                grow = grow < 1 ? grow + n : (grow > n ? grow - n : grow);
                 if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
                 if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
-                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, L.ioff + gi, L.dy);
-                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, L.ioff + gi, L.dy);
+                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, grow, L.dy);
+                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, grow, L.dy);
             }
             if (VC) {
                 const int rr = w * TB_R + r;

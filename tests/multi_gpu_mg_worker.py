@@ -25,10 +25,15 @@ def main():
     from pyro2_b200.multigrid import MG
     from pyro2_b200.parallel import SlabDecomposition
     bc = {"dirichlet": ("dirichlet",) * 4, "periodic": ("periodic",) * 4,
-          "mixed": ("neumann", "dirichlet", "dirichlet", "neumann")}[kind]
+          "mixed": ("neumann", "dirichlet", "dirichlet", "neumann"),
+          "xper_inhom": ("periodic", "periodic", "dirichlet", "neumann")}[kind]
     kw = dict(xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3])
     if kind == "mixed":
         kw.update(alpha=1.0, beta=0.05)
+    if kind == "xper_inhom":
+        # inhomogeneous values along the y sides, indexed by the GLOBAL row: the halo rows a slab receives across the
+        # periodic x boundary must wrap that index
+        kw.update(yl_BC=lambda s: 0.3 + np.sin(2.0 * np.pi * s), yr_BC=lambda s: np.cos(4.0 * np.pi * s))
 
     a = MG.CellCenterMG2d(n, n, decomposition=SlabDecomposition(), split_n=split, **kw)
     a.init_zeros()

@@ -29,7 +29,8 @@ def test_decomposed_run_is_bit_identical(problem, nx, ny, nsteps):
     assert "bit_identical=True" in res.stdout and "dt_identical=True" in res.stdout
 
 
-@pytest.mark.parametrize("kind,n,split", [("dirichlet", 1024, 256), ("periodic", 512, 256), ("mixed", 1024, 512)])
+@pytest.mark.parametrize("kind,n,split", [("dirichlet", 1024, 256), ("periodic", 512, 256), ("mixed", 1024, 512),
+                                          ("xper_inhom", 512, 256)])
 def test_decomposed_multigrid_is_bit_identical(kind, n, split):
     """x-slab multigrid (NCCL deep-halo exchange per blocked-smoother pass, replicated coarse levels)
     vs the single-GPU solve: identical solution bits and cycle counts"""

@@ -174,10 +174,15 @@ def _emulated_mg_worker(rank, size, port, kind, n, split, q):
         from pyro2_b200.multigrid import MG
         from pyro2_b200.parallel import SlabDecomposition
         bc = {"dirichlet": ("dirichlet",) * 4, "periodic": ("periodic",) * 4,
-              "mixed": ("neumann", "dirichlet", "dirichlet", "neumann")}[kind]
+              "mixed": ("neumann", "dirichlet", "dirichlet", "neumann"),
+              "xper_inhom": ("periodic", "periodic", "dirichlet", "neumann")}[kind]
         kw = dict(xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3])
         if kind == "mixed":
             kw.update(alpha=1.0, beta=0.05)
+        if kind == "xper_inhom":
+            # inhomogeneous values along the y sides, indexed by the GLOBAL row: the halo rows a slab receives across the
+            # periodic x boundary must wrap that index
+            kw.update(yl_BC=lambda s: 0.3 + np.sin(2.0 * np.pi * s), yr_BC=lambda s: np.cos(4.0 * np.pi * s))
         with emu_device.emulated_device():
             a = MG.CellCenterMG2d(n, n, decomposition=SlabDecomposition(), split_n=split, **kw)
             a.init_zeros()
@@ -207,7 +212,8 @@ def _emulated_mg_worker(rank, size, port, kind, n, split, q):
 _FULL = pytest.mark.skipif(not os.environ.get("P2B_FULL_TESTS"), reason="set P2B_FULL_TESTS=1 for the long cases")
 
 
-@pytest.mark.parametrize("kind,n,split,size", [("dirichlet", 128, 32, 2), pytest.param("periodic", 128, 64, 2, marks=_FULL),
+@pytest.mark.parametrize("kind,n,split,size", [("dirichlet", 128, 32, 2), ("xper_inhom", 128, 32, 2),
+                                               pytest.param("periodic", 128, 64, 2, marks=_FULL),
                                                pytest.param("mixed", 128, 64, 2, marks=_FULL)])
 def test_decomposed_multigrid_is_bit_identical_on_emulated_device(kind, n, split, size):
     ctx = mp.get_context("spawn")
