@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # P2B_SO overrides the library path (A/B timing of kernel variants during development)
 SO_PATH = os.environ.get("P2B_SO") or os.path.join(CSRC, "libpyro2b200.so")
 SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu", "lm.cu"]
-HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "lm_kernels.cuh", "../../include/pyro2b200.h"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "sweep_args.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "lm_kernels.cuh", "../../include/pyro2b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 

@@ -5,7 +5,7 @@
 // (cp.async.bulk 1-d copies completing on an mbarrier: UBLKCP in SASS); no block-wide barrier is
 // ever executed after the mbarrier initialisation.
 #include "common.cuh"
-#include "sweep_task.cuh"
+#include "sweep_args.cuh"
 
 namespace pyro {
 
@@ -131,25 +131,6 @@ static int resident_warps()
     return resident;
 }
 
-// Uniform tasks scheduled on `resident` warp slots finish in ceil(tasks / resident) rounds, so pick
-// the segment length that minimises rounds * (rows per task + per-task overhead).
-static int choose_seglen(int nx, int nstrips, int resident)
-{
-    const int overhead = 3;   // prologue + the two partial iterations of a segment, in row units
-    int best_len = nx, best_cost = 1 << 30;
-    for (int k = 1; k <= 24; ++k) {
-        long long cap = (long long)k * resident / nstrips;   // segments we can afford in k rounds
-        if (cap < 1) continue;
-        int len = (int)((nx + cap - 1) / cap);
-        if (len < 8) len = 8;
-        int nseg = (nx + len - 1) / len;
-        long long rounds = ((long long)nseg * nstrips + resident - 1) / resident;
-        int cost = (int)(rounds * (len + overhead));
-        if (cost <= best_cost) { best_cost = cost; best_len = len; }   // ties -> more, smaller tasks
-    }
-    return best_len;
-}
-
 }  // namespace pyro
 
 using namespace pyro;
@@ -159,45 +140,13 @@ extern "C" {
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, const p2b_comp_params* prm,
                            double dt, uint64_t* scratch, void* stream)
 {
-    P2B_REQUIRE(Uin && Uout && g && prm && scratch, "null pointer");
-    P2B_REQUIRE(Uin != Uout, "the sweep is out of place: Uin == Uout");
-    P2B_REQUIRE(g->ng >= 4, "compressible sweep needs ng >= 4");
-    P2B_REQUIRE(g->nx >= 1 && g->ny >= 1, "empty grid");
-    P2B_REQUIRE(g->pitch >= g->ny + 2 * g->ng && (g->pitch % 2) == 0, "pitch must be even and >= qy");
-    P2B_REQUIRE((g->plane_stride % 2) == 0 && ((uintptr_t)Uin % 16) == 0, "planes must be 16-byte aligned");
-    P2B_REQUIRE(prm->limiter >= 0 && prm->limiter <= 2, "limiter must be 0, 1 or 2");
-    P2B_REQUIRE(prm->riemann >= 0 && prm->riemann <= 2, "riemann must be 0 (HLLC), 1 (CGF) or 2 (HLLC_lm)");
     cudaStream_t st = (cudaStream_t)stream;
-
     SweepArgs A;
-    A.Uin = Uin; A.Uout = Uout;
-    A.plane_stride = g->plane_stride; A.pitch = g->pitch;
-    A.nx = g->nx; A.ny = g->ny; A.ng = g->ng;
-    A.dx = g->dx; A.dy = g->dy; A.dt = dt; A.gamma = prm->gamma;
-    A.z0 = prm->z0; A.z1 = prm->z1; A.delta = prm->delta; A.cvisc = prm->cvisc;
-    A.limiter = prm->limiter; A.use_flattening = prm->use_flattening;
-    A.no_avisc_xhi = prm->no_avisc_xhi; A.no_avisc_yhi = prm->no_avisc_yhi;
-    A.grav = prm->grav; A.src_flip_ylo = prm->src_flip_ylo; A.src_flip_yhi = prm->src_flip_yhi;
-    A.xl_solid = prm->xl_solid; A.yl_solid = prm->yl_solid;
-    A.heat = prm->heat_profile; A.heat_rate = prm->heat_rate;
-    A.do_sponge = prm->do_sponge; A.sponge_rho_begin = prm->sponge_rho_begin;
-    A.sponge_rho_full = prm->sponge_rho_full; A.sponge_timescale = prm->sponge_timescale;
-    A.src_copy_yhi = prm->src_copy_yhi;
-    A.geo_i = prm->geo_i; A.geo_j = prm->geo_j; A.geo_ni = prm->geo_ni; A.geo_nj = prm->geo_nj;
-    A.src_flip_xlo = prm->src_flip_xlo; A.src_flip_xhi = prm->src_flip_xhi;
-    if (prm->geo_i) {
-        P2B_REQUIRE(prm->geo_j, "SphericalPolar: geo_j missing");
-        P2B_REQUIRE(prm->riemann == 1, "SphericalPolar geometry needs the CGF Riemann solver");
-        P2B_REQUIRE(prm->geo_ni >= g->nx + 2 * g->ng && prm->geo_nj >= g->ny + 2 * g->ng + 1, "geometry tables too short");
-        P2B_REQUIRE(!prm->heat_profile && !prm->do_sponge && !prm->src_copy_yhi,
-                    "SphericalPolar: heating, sponge and ambient boundaries are not supported");
-    }
-    A.nstrips = (g->ny + SW_OUT - 1) / SW_OUT;
     const int resident = resident_warps();
-    A.seglen = choose_seglen(g->nx, A.nstrips, resident);
-    A.nsegs = (g->nx + A.seglen - 1) / A.seglen;
-    A.wavemax = (unsigned long long*)scratch;
-    A.status = (int*)(scratch + 3);
+    if (const char* why = sweep_args_from_abi(Uin, Uout, g, prm, dt, scratch, resident, A)) {
+        pyro::set_error("invalid argument: %s (p2b_compressible_sweep)", why);
+        return P2B_EINVAL;
+    }
     const int ntasks = A.nstrips * A.nsegs;
     g_last_ntasks = ntasks; g_last_resident = resident; g_last_seglen = A.seglen;
 
@@ -207,7 +156,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     if (blocks > maxblocks) blocks = maxblocks;
     const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
     unsigned long long* counter = (unsigned long long*)(scratch + 2);
-    const bool grav = prm->grav != 0.0 || prm->heat_profile != nullptr || prm->do_sponge != 0;   // any source term
+    const bool grav = sweep_has_sources(prm);
     if (prm->geo_i) {
         sweep_kernel<true, 1, true><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
     } else if (prm->riemann == 2) {

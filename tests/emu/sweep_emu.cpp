@@ -13,7 +13,7 @@
 #include <atomic>
 #include <vector>
 
-#include "../../pyro2_b200/csrc/sweep_task.cuh"
+#include "../../pyro2_b200/csrc/sweep_args.cuh"
 
 namespace {
 
@@ -103,6 +103,29 @@ void* lane_main(void* p)
 
 }  // namespace
 
+namespace {
+// one emulated warp works through every task of the launch
+int run_tasks(const pyro::SweepArgs& A, bool sources, int riemann, bool sph)
+{
+    WarpShared ws;
+    pthread_barrier_init(&ws.bar, nullptr, 32);
+    memset(ws.flip, 0, sizeof ws.flip);
+    pyro::SweepSmem* smem = new pyro::SweepSmem;
+    // poison the ring so that stale-slot reads show up as NaNs in the comparison
+    memset(smem, 0xff, sizeof *smem);
+    LaneCtx ctx[32];
+    pthread_t th[32];
+    for (int l = 0; l < 32; ++l) {
+        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, sources, riemann, sph};
+        pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
+    }
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&ws.bar);
+    delete smem;
+    return 0;
+}
+}  // namespace
+
 extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, int ny, int ng, int pitch,
                                       long long plane_stride, double dx, double dy, double dt,
                                       double gamma, double z0, double z1, double delta, double cvisc,
@@ -137,21 +160,25 @@ extern "C" int emu_compressible_sweep(const double* Uin, double* Uout, int nx, i
 #else
     (void)dbg;
 #endif
+    return run_tasks(A, grav != 0.0 || heat != nullptr || do_sponge != 0, riemann, geo_i != nullptr);
+}
 
-    WarpShared ws;
-    pthread_barrier_init(&ws.bar, nullptr, 32);
-    memset(ws.flip, 0, sizeof ws.flip);
-    pyro::SweepSmem* smem = new pyro::SweepSmem;
-    // poison the ring so that stale-slot reads show up as NaNs in the comparison
-    memset(smem, 0xff, sizeof *smem);
-    LaneCtx ctx[32];
-    pthread_t th[32];
-    for (int l = 0; l < 32; ++l) {
-        ctx[l] = LaneCtx{&ws, smem, &A, l, A.nstrips * A.nsegs, grav != 0.0 || heat != nullptr || do_sponge != 0, riemann, geo_i != nullptr};
-        pthread_create(&th[l], nullptr, lane_main, &ctx[l]);
-    }
-    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
-    pthread_barrier_destroy(&ws.bar);
-    delete smem;
-    return 0;
+// The C ABI of p2b_compressible_sweep over the emulated warp: same argument checks, field copy and work decomposition
+// as the device launch (pyro2_b200/csrc/sweep_args.cuh); `resident` stands in for the device's warp slots.
+extern "C" int emu_compressible_sweep_abi(const double* Uin, double* Uout, const p2b_grid* g, const p2b_comp_params* prm,
+                                          double dt, uint64_t* scratch, int resident, const char** why)
+{
+    pyro::SweepArgs A;
+    const char* e = pyro::sweep_args_from_abi(Uin, Uout, g, prm, dt, scratch, resident, A);
+    if (why) *why = e;
+    if (e) return -1;
+    memset(scratch, 0, 4 * sizeof(uint64_t));
+    return run_tasks(A, pyro::sweep_has_sources(prm), prm->riemann, prm->geo_i != nullptr);
+}
+
+extern "C" void emu_sweep_decomposition(const p2b_grid* g, int resident, int* ntasks, int* seglen)
+{
+    const int nstrips = (g->ny + pyro::SW_OUT - 1) / pyro::SW_OUT;
+    *seglen = pyro::choose_seglen(g->nx, nstrips, resident);
+    *ntasks = nstrips * ((g->nx + *seglen - 1) / *seglen);
 }

@@ -28,25 +28,7 @@ import torch
 
 import emu_util
 
-SW_OUT = 30            # output columns per warp task (sweep_task.cuh)
-RESIDENT_WARPS = 148 * 12   # what choose_seglen() is given here: any value works, this one makes small grids split into segments
-
-
-def _choose_seglen(nx, nstrips, resident):
-    """pyro2_b200/csrc/sweep.cu choose_seglen(), restated (the result only affects how the work is cut up)"""
-    overhead = 3
-    best_len, best_cost = nx, 1 << 30
-    for k in range(1, 25):
-        cap = k * resident // nstrips
-        if cap < 1:
-            continue
-        length = max((nx + cap - 1) // cap, 8)
-        nseg = (nx + length - 1) // length
-        rounds = (nseg * nstrips + resident - 1) // resident
-        cost = rounds * (length + overhead)
-        if cost <= best_cost:
-            best_cost, best_len = cost, length
-    return best_len
+RESIDENT_WARPS = 148 * 12   # the device's warp slots as choose_seglen() sees them; small grids then split into segments
 
 
 class EmuLibrary:
@@ -73,7 +55,7 @@ class EmuLibrary:
         if name == "p2b_sweep_info":
             return self._sweep_info
         if name == "p2b_last_error":
-            return lambda: b"; ".join(lib.p2b_last_error() or b"" for lib in self._used)
+            return lambda: b"; ".join([lib.p2b_last_error() or b"" for lib in self._used] + [getattr(self, "_sweep_error", b"")])
         if name == "p2b_version":
             return lambda: 1
         for prefix, loader in self.ROUTES:
@@ -85,22 +67,19 @@ class EmuLibrary:
         raise AttributeError(name)
 
     def _sweep(self, uin, uout, g_ref, prm_ref, dt, scratch, stream):   # pylint: disable=unused-argument
-        """p2b_compressible_sweep (sweep.cu) over the warp emulator: same argument checks that matter here, same
-        work decomposition rule, same scratch words (wave-speed maxima in [0], [1], status in [3])"""
-        g, p = g_ref._obj, prm_ref._obj
-        if uin == uout or g.ng < 4 or g.pitch % 2 or g.pitch < g.ny + 2 * g.ng or p.riemann not in (0, 1, 2):
-            return -1
-        nstrips = (g.ny + SW_OUT - 1) // SW_OUT
-        seglen = _choose_seglen(g.nx, nstrips, RESIDENT_WARPS)
-        self._info = (nstrips * ((g.nx + seglen - 1) // seglen), RESIDENT_WARPS, seglen)
+        """p2b_compressible_sweep over the warp emulator: the argument checks, the copy into the kernel's argument
+        struct and the work decomposition are the device launch's own (csrc/sweep_args.cuh, compiled into the
+        emulator library); the scratch words come back the same way (wave-speed maxima in [0], [1], status in [3])"""
         lib = emu_util.load_sweep_emu()
-        return lib.emu_compressible_sweep(uin, uout, g.nx, g.ny, g.ng, g.pitch, g.plane_stride, g.dx, g.dy, dt,
-                                          p.gamma, p.z0, p.z1, p.delta, p.cvisc, p.limiter, p.use_flattening,
-                                          p.no_avisc_xhi, p.no_avisc_yhi, seglen, scratch, None,
-                                          p.grav, p.src_flip_ylo, p.src_flip_yhi, p.riemann, p.xl_solid, p.yl_solid,
-                                          p.heat_profile, p.heat_rate, p.do_sponge, p.sponge_rho_begin, p.sponge_rho_full,
-                                          p.sponge_timescale, p.src_copy_yhi, p.geo_i, p.geo_j, p.geo_ni, p.geo_nj,
-                                          p.src_flip_xlo, p.src_flip_xhi)
+        why = C.c_char_p()
+        rc = lib.emu_compressible_sweep_abi(uin, uout, g_ref, prm_ref, dt, scratch, RESIDENT_WARPS, C.byref(why))
+        if rc:
+            self._sweep_error = why.value or b"sweep refused"
+            return -1
+        ntasks, seglen = C.c_int(), C.c_int()
+        lib.emu_sweep_decomposition(g_ref, RESIDENT_WARPS, C.byref(ntasks), C.byref(seglen))
+        self._info = (ntasks.value, RESIDENT_WARPS, seglen.value)
+        return 0
 
     def _sweep_info(self, a, b, c):
         for ref, val in zip((a, b, c), self._info):

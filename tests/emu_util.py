@@ -79,7 +79,8 @@ def load_sweep_emu():
         return _LIBS["sweep"]
     so = os.path.join(EMU_DIR, "libsweep_emu.so")
     src = os.path.join(EMU_DIR, "sweep_emu.cpp")
-    hdrs = [os.path.join(CSRC, h) for h in ("sweep_task.cuh", "hydro_core.cuh")]
+    hdrs = [os.path.join(CSRC, h) for h in ("sweep_task.cuh", "sweep_args.cuh", "hydro_core.cuh")] + \
+           [os.path.join(os.path.dirname(CSRC), "..", "include", "pyro2b200.h")]
     _build(so, [src] + hdrs, ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                               "-Wno-unknown-pragmas", "-pthread", src, "-o", so])
     lib = C.CDLL(so)
@@ -88,6 +89,11 @@ def load_sweep_emu():
                                            [C.c_double, C.c_int, C.c_int] + [C.c_int] * 3 +
                                            [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int] +
                                            [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])
+    from pyro2_b200 import _lib
+    lib.emu_compressible_sweep_abi.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_lib.Grid), C.POINTER(_lib.CompParams),
+                                               C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
+    lib.emu_sweep_decomposition.argtypes = [C.POINTER(_lib.Grid), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.emu_sweep_decomposition.restype = None
     _LIBS["sweep"] = lib
     return lib
 

@@ -505,3 +505,28 @@ def test_ramp_boundary_matches_oracle():
     # the top rows really are a mixture: pre-shock right of the front, post-shock left of it, blends in between
     top = d.get_var("density").numpy()[:, g.jhi + 1]
     assert top[0] == 8.0 and top[-1] == 1.4 and np.any((top > 1.4) & (top < 8.0))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """the ctypes mirrors of p2b_grid / p2b_comp_params (pyro2_b200/_lib.py) against the C compiler's layout of the
+    structs in include/pyro2b200.h: same size, same offset for every field.  (The emulated device reads the ctypes
+    struct directly, so only this test ties it to what the CUDA library's host code sees.)"""
+    import ctypes as C
+    import subprocess
+    from pyro2_b200 import _lib
+    fields = {"p2b_grid": [n for n, _ in _lib.Grid._fields_], "p2b_comp_params": [n for n, _ in _lib.CompParams._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "pyro2b200.h")}"', "int main(void) {"]
+    for st, names in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            src.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-o", str(exe), str(c)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for st, cls in (("p2b_grid", _lib.Grid), ("p2b_comp_params", _lib.CompParams)):
+        assert int(got[st]) == C.sizeof(cls), st
+        for n, _ in cls._fields_:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, f"{st}.{n}"
