@@ -1,7 +1,8 @@
 // sweep_task.cuh -- one warp's share of the fused compressible CTU sweep (HP-1).
 //
 // Replaces, in a single pass over the state, everything the reference does in
-// pyro/compressible/simulation.py:290-450 (evolve) for Cartesian/HLLC/grav=0:
+// pyro/compressible/simulation.py:290-450 (evolve); the default instantiation is Cartesian / HLLC / no sources, the
+// template parameters of SweepTask add the source terms, the other Riemann solvers and SphericalPolar geometry:
 //   cons_to_prim -> flatten/flatten_multid -> limit -> interface.states (x, y) -> prim_to_cons ->
 //   transverse riemann_hllc (x, y) -> transverse correction -> final riemann_hllc (x, y) ->
 //   artificial viscosity -> conservative update, plus the wave-speed maxima the next

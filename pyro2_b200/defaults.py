@@ -22,7 +22,7 @@ GLOBAL = {
     "io.force_final_output": (0, "write the last state even if do_io is off"),
     "vis.dovis": (0, "runtime visualisation (not provided by the device build)"),
     "vis.store_images": (0, ""),
-    "mesh.grid_type": ("Cartesian2d", "only Cartesian2d is supported by the device sweep"),
+    "mesh.grid_type": ("Cartesian2d", "Cartesian2d or SphericalPolar (x = r, y = theta; compressible solver with CGF)"),
     "mesh.xmin": (0.0, ""), "mesh.xmax": (1.0, ""), "mesh.ymin": (0.0, ""), "mesh.ymax": (1.0, ""),
     "mesh.xlboundary": ("reflect", "reflect, outflow or periodic"),
     "mesh.xrboundary": ("reflect", ""),
