@@ -65,3 +65,18 @@ def test_every_gpu_test_function_is_enumerated():
         assert cs
         for ident, fn, kw in cs:
             assert set(inspect.signature(fn).parameters) == set(kw), ident
+
+
+def test_smoke_on_emulated_device():
+    """__graft_entry__.smoke() -- the first thing the driver runs on the GPU box -- with the product on the emulated
+    device (CUDA availability patched for the duration): Pyro("compressible") and CellCenterMG2d against the oracle"""
+    from unittest import mock
+
+    import torch
+
+    import __graft_entry__ as ge
+    import emu_device
+    with emu_device.emulated_device() as dev, mock.patch.object(torch.cuda, "is_available", lambda: True), \
+            mock.patch.object(torch.cuda, "set_device", lambda d: None), mock.patch.object(ge, "build", lambda: None):
+        ge.smoke()
+    assert dev.calls["p2b_compressible_sweep"] == 3 and dev.calls["p2b_mg_vcycle"] >= 1
