@@ -6,15 +6,15 @@ Differences from the reference, all deliberate:
   * `device=` selects where the planes are allocated (default: the CUDA device, like every container here);
   * the step counter is restored from the file's "nsteps" attribute (the reference overwrites it with a
     variable name through a reused loop variable, io_pyro.py:79-82,124);
-  * SphericalPolar grids and particle records are not part of this build: a file holding either is refused
-    rather than read into something else."""
+  * particle records are not part of this build: a file holding them is refused rather than read into
+    something else."""
 import importlib
 
 import numpy as np
 import torch
 
 from ..mesh import boundary as bnd
-from ..mesh.patch import Cartesian2d, CellCenterData2d
+from ..mesh.patch import Cartesian2d, CellCenterData2d, SphericalPolar
 
 # solvers whose user boundary conditions live in another solver's BC module (io_pyro.py:69-72)
 _BC_MODULE = {"compressible_fv4": "compressible", "compressible_rk": "compressible", "compressible_sdc": "compressible"}
@@ -56,11 +56,10 @@ def read(filename, device=None):
             coord_type = int(grid["coord_type"])
         except KeyError:
             coord_type = 0
-        if coord_type != 0:
-            raise NotImplementedError("SphericalPolar grids are not part of the B200 build")
+        grid_class = SphericalPolar if coord_type == 1 else Cartesian2d
         if "particles" in f:
             raise NotImplementedError("particle records are not part of the B200 build")
-        myg = Cartesian2d(int(grid["nx"]), int(grid["ny"]), ng=int(grid["ng"]),
+        myg = grid_class(int(grid["nx"]), int(grid["ny"]), ng=int(grid["ng"]),
                           xmin=float(grid["xmin"]), xmax=float(grid["xmax"]),
                           ymin=float(grid["ymin"]), ymax=float(grid["ymax"]), device=device)
         # custom boundary types must exist before variables carrying them are registered

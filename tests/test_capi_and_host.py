@@ -372,6 +372,16 @@ def test_patch_write_read_round_trip(monkeypatch, tmp_path):
     assert compare.compare(myd, nd) == 0
     nd.get_var("a").v()[3, 3] += 1.0e-3
     assert compare.compare(myd, nd) == "varerr"
+    # a SphericalPolar patch comes back as one (coord_type is part of the grid record, patch.py:771-774)
+    sg = patch.SphericalPolar(8, 6, ng=2, xmin=0.5, xmax=1.5, ymin=0.4, ymax=2.0, device="cpu")
+    sd = patch.CellCenterData2d(sg)
+    sd.register_var("a", bnd.BC(xlb="outflow", xrb="outflow", ylb="outflow", yrb="outflow"))
+    sd.create()
+    sd.get_var("a").v()[:, :] = np.arange(48.0).reshape(8, 6)
+    sd.write(str(tmp_path / "sph_test"))
+    back = io_pyro.read(str(tmp_path / "sph_test"), device="cpu")
+    assert type(back.grid) is patch.SphericalPolar and back.grid == sg
+    assert np.array_equal(back.grid.V.numpy(), sg.V.numpy()) and compare.compare(sd, back) == 0
     other = patch.CellCenterData2d(patch.Grid2d(8, 8, ng=2, device="cpu"))
     other.register_var("a", bnd.BC())
     other.create()
