@@ -135,7 +135,7 @@ int p2b_cfl_wavemax(const double* U, const p2b_grid* g, double gamma, uint64_t* 
  * state's wave-speed maxima, scratch[3] is set if a valid cell had rho <= 0 or e <= 0.
  * scratch[0..3] are zeroed by this call before the kernel runs.  Requires ng >= 4,
  * Riemann solver HLLC, CGF or HLLC_lm (prm->riemann); gravity, a heating profile or the sponge select the
- * instantiations with source terms; prm->geo_i selects SphericalPolar geometry (CGF, no heating / sponge / ambient). */
+ * instantiations with source terms; prm->geo_i selects SphericalPolar geometry (CGF only, no ambient boundary). */
 int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
                            const p2b_comp_params* prm, double dt, uint64_t* scratch, void* stream);
 

@@ -957,9 +957,11 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
             for (int j = ng; j < ng + ny; j++) {
                 const size_t k = IDX(i, j);
                 const double r = G->x2d[k];
+                const double hp = P->heat_profile ? P->heat_profile[k] : 0.0;
                 /* S_old from U_old */
                 double so_x = Uold_dens[k] * g;
-                const double so_e = Uold_xmom[k] * g;
+                double so_e = Uold_xmom[k] * g;
+                if (P->heat_profile) so_e += Uold_dens[k] * P->heat_rate * hp;
                 so_x += Uold_ymom[k] * Uold_ymom[k] / (Uold_dens[k] * r);
                 const double so_y = 0.0 + -Uold_xmom[k] * Uold_ymom[k] / Uold_dens[k];
                 U[IXMOM * np + k] += dt * so_x;
@@ -969,7 +971,8 @@ int orc_compressible_step(double *U, int nx, int ny, int ng, double dx, double d
                 double sn_x = U[IDENS * np + k] * g;
                 const double so_xg = Uold_dens[k] * g;
                 const double xmom_new = U[IXMOM * np + k] + 0.5 * dt * (sn_x - so_xg);
-                const double sn_e = xmom_new * g;
+                double sn_e = xmom_new * g;
+                if (P->heat_profile) sn_e += U[IDENS * np + k] * P->heat_rate * hp;
                 sn_x += U[IYMOM * np + k] * U[IYMOM * np + k] / (U[IDENS * np + k] * r);
                 const double sn_y = 0.0 + -U[IXMOM * np + k] * U[IYMOM * np + k] / U[IDENS * np + k];
                 U[IXMOM * np + k] += 0.5 * dt * (sn_x - so_x);

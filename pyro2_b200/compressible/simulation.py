@@ -143,9 +143,8 @@ class Simulation(NullSimulation):
 
         self._geometry = None
         if self._spherical:
-            if self._heating is not None or rp.get_param("sponge.do_sponge") or any(
-                    t in bnd.ext_bcs for t in bc.names()):
-                msg.fail("ERROR: heating, sponge and the hse / ambient / ramp boundaries are not built for SphericalPolar grids")
+            if any(t in bnd.ext_bcs for t in bc.names()):
+                msg.fail("ERROR: the hse / ambient / ramp boundaries are not built for SphericalPolar grids")
             gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1), bc.xlb, bc.xrb)
             dev = my_data.planes.device
             self._geometry = (torch.from_numpy(gi).to(dev), torch.from_numpy(gj).to(dev))

@@ -52,8 +52,7 @@ inline const char* sweep_args_from_abi(const double* Uin, double* Uout, const p2
         if (!prm->geo_j) return "SphericalPolar: geo_j missing";
         if (prm->riemann != 1) return "SphericalPolar geometry needs the CGF Riemann solver";
         if (prm->geo_ni < g->nx + 2 * g->ng || prm->geo_nj < g->ny + 2 * g->ng + 1) return "geometry tables too short";
-        if (prm->heat_profile || prm->do_sponge || prm->src_copy_yhi)
-            return "SphericalPolar: heating, sponge and ambient boundaries are not supported";
+        if (prm->src_copy_yhi) return "SphericalPolar: the ambient boundary is not supported";
     }
     A.Uin = Uin; A.Uout = Uout;
     A.plane_stride = g->plane_stride; A.pitch = g->pitch;

@@ -339,6 +339,8 @@ struct SweepTask {
                 double sx = Uc.dens * A.grav + Uc.ymom * Uc.ymom / (Uc.dens * r);
                 double sy = -Uc.xmom * Uc.ymom / Uc.dens, se = Uc.xmom * A.grav;
                 if (flip) { sx = -sx; sy = -sy; se = -se; }
+                // problem heating: the profile plane is ghost-filled like the (even) source array it feeds
+                if (A.heat) se += Uc.dens * A.heat_rate * A.heat[(long long)i * A.pitch + jj];
                 const double hx = 0.5 * A.dt * sx, hy = 0.5 * A.dt * sy, he = 0.5 * A.dt * se;
                 XM.xmom += hx; XP.xmom += hx; YM.xmom += hx; YP.xmom += hx;
                 XM.ymom += hy; XP.ymom += hy; YM.ymom += hy; YP.ymom += hy;
@@ -493,12 +495,13 @@ struct SweepTask {
                         // sources, predictor-corrector with the SphericalPolar branches of get_external_sources
                         // (simulation.py:398-423, :117-124, :135-146)
                         const double r = gi(0, i - 1), g = A.grav;
+                        const double hp = A.heat ? A.heat_rate * A.heat[(long long)(i - 1) * A.pitch + jj] : 0.0;
                         const double so_xg = U_prev.dens * g;
                         const double so_x = so_xg + U_prev.ymom * U_prev.ymom / (U_prev.dens * r);
-                        const double so_y = -U_prev.xmom * U_prev.ymom / U_prev.dens, so_e = U_prev.xmom * g;
+                        const double so_y = -U_prev.xmom * U_prev.ymom / U_prev.dens, so_e = U_prev.xmom * g + U_prev.dens * hp;
                         Un.xmom += A.dt * so_x; Un.ymom += A.dt * so_y; Un.ener += A.dt * so_e;
                         const double sn_xg = Un.dens * g;
-                        const double sn_e = (Un.xmom + 0.5 * A.dt * (sn_xg - so_xg)) * g;
+                        const double sn_e = (Un.xmom + 0.5 * A.dt * (sn_xg - so_xg)) * g + Un.dens * hp;
                         const double sn_x = sn_xg + Un.ymom * Un.ymom / (Un.dens * r);
                         const double sn_y = -Un.xmom * Un.ymom / Un.dens;
                         Un.xmom += 0.5 * A.dt * (sn_x - so_x);
@@ -523,6 +526,8 @@ struct SweepTask {
                         const double sn_e = (Un.ymom + corr) * A.grav + Un.dens * hp;
                         Un.ymom += corr;
                         Un.ener += 0.5 * A.dt * (sn_e - so_e);
+                    }
+                    if (GRAV) {
                         if (A.do_sponge) {
                             // implicit damping of the momenta in the low-density region, kinetic-energy change
                             // booked into the energy (simulation.py:425-441)

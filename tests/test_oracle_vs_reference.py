@@ -246,7 +246,11 @@ def test_unphysical_interface_states_follow_the_reference(riemann):
     ("sedov", {"mesh.xmin": 0.2, "mesh.xmax": 1.0, "mesh.ymin": 0.785, "mesh.ymax": 2.355, "mesh.xlboundary": "reflect-odd",
                "sedov.r_init": 0.3, "compressible.limiter": 2}),
     ("advect", {"mesh.xmin": 1.0, "mesh.xmax": 2.0, "mesh.ymin": 0.523, "mesh.ymax": 2.617, "mesh.xlboundary": "outflow",
-                "compressible.limiter": 0, "compressible.grav": -0.7})])
+                "compressible.limiter": 0, "compressible.grav": -0.7}),
+    # problem heating and the sponge apply in any geometry (simulation.py:148-153, 425-441)
+    ("heating", {"mesh.xmin": 0.5, "mesh.xmax": 1.5, "mesh.ymin": 0.6, "mesh.ymax": 2.4, "mesh.xlboundary": "reflect",
+                 "compressible.limiter": 2, "compressible.grav": -0.5, "sponge.do_sponge": 1, "sponge.sponge_rho_begin": 1.2,
+                 "sponge.sponge_rho_full": 0.8, "sponge.sponge_timescale": 0.01, "heating.e_rate": 2.0})])
 def test_spherical_polar_step_matches_reference(problem, extra):
     """SphericalPolar geometry (mesh/patch.py:242-312 and the coord_type == 1 branches of the compressible solver):
     geometry arrays bit for bit, the CFL time step, and whole steps of the live reference against the oracle"""
@@ -261,8 +265,20 @@ def test_spherical_polar_step_matches_reference(problem, extra):
         assert np.array_equal(geom[k], np.asarray(getattr(g, k))), k
     bcs = [tuple(getattr(sim.cc_data.BCs[n], s) for s in ("xlb", "xrb", "ylb", "yrb"))
            for n in ("density", "energy", "x-momentum", "y-momentum")]
+    heat = {}
+    if sim.problem_source is not None:
+        # the profile P with S_ener = dens * e_rate * P: the reference's own source_terms() on unit density, e_rate = 1
+        rate = sim.rp.get_param(f"{problem}.e_rate")
+        sim.rp.set_param(f"{problem}.e_rate", 1.0)
+        ones = g.scratch_array(nvar=4)
+        ones[:, :, 0] = 1.0
+        heat = {"heat_rate": rate, "heat_profile": np.asarray(sim.problem_source(g, ones, sim.ivars, sim.rp))[:, :, sim.ivars.iener].copy()}
+        sim.rp.set_param(f"{problem}.e_rate", rate)
+    sponge = None
+    if sim.rp.get_param("sponge.do_sponge"):
+        sponge = tuple(sim.rp.get_param(f"sponge.sponge_{k}") for k in ("rho_begin", "rho_full", "timescale"))
     prm = oracle.comp_params(limiter=extra["compressible.limiter"], riemann="CGF", grav=sim.rp.get_param("compressible.grav"),
-                             src_bcs=bcs, geom=geom, xl_solid=int(sim.solid.xl), yl_solid=int(sim.solid.yl))
+                             src_bcs=bcs, geom=geom, xl_solid=int(sim.solid.xl), yl_solid=int(sim.solid.yl), sponge=sponge, **heat)
     v = (slice(g.ilo, g.ihi + 1), slice(g.jlo, g.jhi + 1))
     for _ in range(4):
         sim.cc_data.fill_BC_all()

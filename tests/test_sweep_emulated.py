@@ -224,6 +224,42 @@ def test_emulated_sweep_with_unphysical_interface_states_matches_oracle(emu, sol
         assert rel_l2(got[v_][..., n], ref[v_][..., n]) < 1e-12
 
 
+def test_emulated_sweep_spherical_polar_with_heating_and_sponge(emu):
+    """problem heating and the sponge on a SphericalPolar grid (the reference applies both in any geometry)"""
+    from golden_util import var_bcs
+    from pyro2_b200.mesh import patch
+    ng, gamma, nx, ny = 4, 1.4, 16, 33
+    xmin, xmax, ymin, ymax = 0.6, 1.4, 0.6, 2.4
+    g = patch.SphericalPolar(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device="cpu")
+    geom = oracle.spherical_geometry(nx, ny, ng, xmin, xmax, ymin, ymax)
+    rng = np.random.default_rng(3)
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    r = geom["x2d"]
+    dens = np.exp(-(r - xmin) / 0.3) * (1.0 + 0.1 * rng.standard_normal((qx, qy)))      # falls through the sponge range
+    pres = 1.5 * dens * (1.0 + 0.05 * rng.standard_normal((qx, qy)))
+    u, v = 0.2 * rng.standard_normal((qx, qy)), 0.2 * rng.standard_normal((qx, qy))
+    P = np.stack([dens, pres / (gamma - 1.0) + 0.5 * dens * (u * u + v * v), dens * u, dens * v])
+    bc = ("reflect", "outflow", "outflow", "outflow")
+    bcs = var_bcs(dict(zip(("mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary"), bc)))
+    for k in range(4):
+        oracle.fill_ghost(P[k], ng, bcs[k])
+    U = oracle.from_planes(P)
+    dt = 0.5 * oracle.cfl_dt_spherical(U, gamma, 0.8, geom)
+    prof = np.exp(-((r - 1.0) ** 2 + (geom["y2d"] - 1.5) ** 2) / 0.05)
+    prm = oracle.comp_params(riemann="CGF", grav=-0.8, src_bcs=bcs, geom=geom, xl_solid=1, heat_rate=0.7, heat_profile=prof,
+                             sponge=(0.5, 0.15, 1.e-2))
+    ref = oracle.compressible_step(U, ng, g.dx, g.dy, dt, prm)
+    heat = prof.copy()
+    oracle.fill_ghost(heat, ng, bcs[1])
+    tables = patch.spherical_sweep_tables(g, (qy + 15) // 16 * 16, bc[0], bc[1])
+    got, scratch = _emu_step(emu, U, ng, g.dx, g.dy, dt, prm, 8, heat=heat, geometry=tables, xflips=(1, 0))
+    v_ = (slice(ng, ng + nx), slice(ng, ng + ny))
+    assert np.isfinite(got[v_]).all() and scratch[3] == 0
+    assert np.abs(got[v_] - ref[v_]).max() < 2e-14 * np.abs(ref[v_]).max()
+    plain = oracle.compressible_step(U, ng, g.dx, g.dy, dt, oracle.comp_params(riemann="CGF", grav=-0.8, src_bcs=bcs, geom=geom, xl_solid=1))
+    assert rel_l2(ref[v_][..., 1], plain[v_][..., 1]) > 1e-6 and rel_l2(ref[v_][..., 2], plain[v_][..., 2]) > 1e-6
+
+
 @pytest.mark.parametrize("xbc,ybc,nx,ny,grav,limiter,seglen", [
     (("reflect-odd", "outflow"), ("outflow", "outflow"), 20, 37, 0.0, 2, 8),        # the reference's sedov.spherical setup
     (("outflow", "outflow"), ("outflow", "outflow"), 24, 31, -0.7, 0, 11),          # advect.spherical + radial gravity
