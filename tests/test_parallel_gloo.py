@@ -142,7 +142,8 @@ def _emulated_run_worker(rank, size, port, problem, nx, ny, nsteps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("problem,nx,ny,nsteps,size", [("sedov", 32, 16, 4, 2), ("kh", 24, 16, 3, 2), ("quad", 24, 12, 3, 3)])
+@pytest.mark.parametrize("problem,nx,ny,nsteps,size", [("sedov", 32, 16, 4, 2), ("kh", 24, 16, 3, 2), ("quad", 24, 12, 3, 3)][::2] +
+                         [pytest.param("kh", 24, 16, 3, 2, marks=pytest.mark.skipif(not os.environ.get("P2B_FULL_TESTS"), reason="long cases"))])
 def test_decomposed_run_is_bit_identical_on_emulated_device(problem, nx, ny, nsteps, size):
     """the N > 1 product path end to end without a GPU: SlabDecomposition + halo exchange over gloo, the sweep / ghost
     fill / CFL kernels through the host-compiled libraries (tests/emu_device.py).  periodic (kh) and physical
@@ -212,7 +213,7 @@ def _emulated_mg_worker(rank, size, port, kind, n, split, q):
 _FULL = pytest.mark.skipif(not os.environ.get("P2B_FULL_TESTS"), reason="set P2B_FULL_TESTS=1 for the long cases")
 
 
-@pytest.mark.parametrize("kind,n,split,size", [("dirichlet", 128, 32, 2), ("xper_inhom", 128, 32, 2),
+@pytest.mark.parametrize("kind,n,split,size", [("xper_inhom", 128, 32, 2), pytest.param("dirichlet", 128, 32, 2, marks=_FULL),
                                                pytest.param("periodic", 128, 64, 2, marks=_FULL),
                                                pytest.param("mixed", 128, 64, 2, marks=_FULL)])
 def test_decomposed_multigrid_is_bit_identical_on_emulated_device(kind, n, split, size):
@@ -276,12 +277,14 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
 
 
 @pytest.mark.parametrize("solver,problem,inputs,nsteps,size", [
-    ("advection", "smooth", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),
+    pytest.param("advection", "smooth", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2, marks=_FULL),
     ("advection", "tophat", {"mesh.nx": 36, "mesh.ny": 24, "advection.u": -0.6, "advection.limiter": 1}, 5, 3),
     ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
-    ("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3),                # periodic
+    pytest.param("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3, marks=_FULL),                # periodic
     ("diffusion", "gaussian", {"mesh.nx": 128, "mesh.ny": 128, "diffusion.mg_split_n": 64}, 2, 2),
-    ("incompressible", "shear", {"mesh.nx": 128, "mesh.ny": 128, "incompressible.mg_split_n": 64}, 1, 2)])
+    # (initialize_problem already runs the initial projection and one full step in preevolve: no further steps needed)
+    ("incompressible", "shear", {"mesh.nx": 128, "mesh.ny": 128, "incompressible.mg_split_n": 64}, 0, 2),
+    pytest.param("incompressible", "converge", {"mesh.nx": 128, "mesh.ny": 128, "incompressible.mg_split_n": 32}, 1, 4, marks=_FULL)])
 def test_decomposed_flow_solvers_are_bit_identical_on_emulated_device(solver, problem, inputs, nsteps, size):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
