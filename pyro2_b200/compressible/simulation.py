@@ -145,7 +145,8 @@ class Simulation(NullSimulation):
         if self._spherical:
             if any(t in bnd.ext_bcs for t in bc.names()):
                 msg.fail("ERROR: the hse / ambient / ramp boundaries are not built for SphericalPolar grids")
-            gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1), bc.xlb, bc.xrb)
+            # (one entry more than the padded row: the kernel also reads column j + 1 of the per-column tables)
+            gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1) + 2, bc.xlb, bc.xrb)
             dev = my_data.planes.device
             self._geometry = (torch.from_numpy(gi).to(dev), torch.from_numpy(gj).to(dev))
             # across a "reflect" x boundary the reference's source arrays change sign (their own BCs, odd for the

@@ -28,13 +28,18 @@ PROBLEMS = {  # problem -> (base inputs, allowed y boundaries, allowed x boundar
     "heating": ({"mesh.nx": 20, "mesh.ny": 20}, ["outflow"], ["outflow", "periodic"]),
     "plume": ({"mesh.nx": 16, "mesh.ny": 32, "mesh.ymax": 4.0}, ["hse"], ["outflow", "reflect"]),
     "convection": ({"mesh.nx": 12, "mesh.ny": 72}, ["reflect+ambient"], ["periodic"]),
+    # SphericalPolar grids (CGF only); sizes chosen per case below
+    "sedov:sph": ({"mesh.grid_type": "SphericalPolar", "mesh.xmin": 0.4, "mesh.xmax": 1.2, "mesh.ymin": 0.785, "mesh.ymax": 2.355,
+                   "sedov.r_init": 0.6}, ["outflow", "reflect"], ["reflect", "outflow"]),
+    "advect:sph": ({"mesh.grid_type": "SphericalPolar", "mesh.xmin": 1.0, "mesh.xmax": 2.0, "mesh.ymin": 0.523, "mesh.ymax": 2.617,
+                    "driver.fix_dt": -1.0}, ["outflow", "reflect"], ["outflow", "periodic"]),
 }
 KEYS = ["eos.gamma", "compressible.limiter", "compressible.use_flattening", "compressible.cvisc", "compressible.z0",
         "compressible.z1", "compressible.delta", "driver.cfl", "driver.tmax", "driver.init_tstep_factor",
         "driver.max_dt_change", "mesh.xlboundary", "mesh.xrboundary", "mesh.ylboundary", "mesh.yrboundary", "mesh.nx",
         "mesh.ny", "mesh.xmin", "mesh.xmax", "mesh.ymin", "mesh.ymax", "compressible.grav", "compressible.riemann",
         "compressible.small_dens", "sponge.do_sponge", "sponge.sponge_rho_begin", "sponge.sponge_rho_full",
-        "sponge.sponge_timescale"]
+        "sponge.sponge_timescale", "mesh.grid_type"]
 
 
 def one_case(rng):
@@ -42,6 +47,10 @@ def one_case(rng):
     problem = str(rng.choice(list(PROBLEMS)))
     base, ybcs, xbcs = PROBLEMS[problem]
     inputs = dict(base)
+    spherical = problem.endswith(":sph")
+    problem = problem.split(":")[0]
+    if spherical:
+        inputs.update({"mesh.nx": int(rng.choice([16, 20, 24])), "mesh.ny": int(rng.choice([16, 24, 31, 40]))})
     yb, xb = str(rng.choice(ybcs)), str(rng.choice(xbcs))
     if yb == "reflect+ambient":
         inputs.update({"mesh.ylboundary": "reflect", "mesh.yrboundary": "ambient"})
@@ -50,7 +59,9 @@ def one_case(rng):
         if problem in ("bubble", "rt", "hse", "plume") and inputs["mesh.yrboundary"] == "outflow" and yb == "hse":
             inputs["mesh.yrboundary"] = "hse"
     inputs.update({"mesh.xlboundary": xb, "mesh.xrboundary": xb if xb == "periodic" or rng.integers(2) else "outflow"})
-    inputs["compressible.riemann"] = str(rng.choice(["HLLC", "CGF", "HLLC_lm"]))
+    inputs["compressible.riemann"] = "CGF" if spherical else str(rng.choice(["HLLC", "CGF", "HLLC_lm"]))
+    if spherical:
+        inputs["compressible.grav"] = float(rng.choice([0.0, -0.5]))
     inputs["compressible.limiter"] = int(rng.choice([1, 2, 2]))
     inputs["compressible.use_flattening"] = int(rng.integers(2))
     inputs["compressible.cvisc"] = float(rng.choice([0.1, 0.0]))
