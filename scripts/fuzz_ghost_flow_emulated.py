@@ -76,6 +76,32 @@ def cfl_case(lib, rng):
     return ok, dict(kind="cfl", nx=nx, ny=ny, ng=ng, gamma=gamma)
 
 
+def ghost_values_case(lib, rng):
+    """inhomogeneous Dirichlet / Neumann values on some sides (array_indexer.py:165-183, 220-238)"""
+    ng = int(rng.integers(1, 5))
+    nx, ny = int(rng.integers(ng, 14)), int(rng.integers(ng, 14))
+    kinds = ["dirichlet", "neumann", "outflow", "reflect-even"]
+    xb, yb = str(rng.choice(kinds + ["periodic"])), str(rng.choice(kinds + ["periodic"]))
+    bc = ((xb, xb) if xb == "periodic" else (xb, str(rng.choice(kinds)))) + ((yb, yb) if yb == "periodic" else (yb, str(rng.choice(kinds))))
+    qx, qy = nx + 2 * ng, ny + 2 * ng
+    pitch = (qy + 15) // 16 * 16 if qy >= 16 else (qy + 1) // 2 * 2
+    vals = []
+    for s_, b in enumerate(bc):
+        length = qy if s_ < 2 else qx
+        vals.append(rng.standard_normal(length) if b in ("dirichlet", "neumann") and rng.integers(3) else None)
+    dx, dy = 1.0 / nx, 0.7 / ny
+    a = np.zeros((qx, pitch))
+    a[:, :qy] = rng.standard_normal((qx, qy))
+    ref = np.ascontiguousarray(a[:, :qy])
+    oracle.fill_ghost(ref, ng, bc, values=tuple(vals), dx=dx, dy=dy)
+    g = _lib.Grid(nx, ny, ng, pitch, qx * pitch, dx, dy)
+    codes = (C.c_int * 4)(*[_lib.BC_CODES[b] for b in bc])
+    ptr = [None if (v is None or codes[s_] not in (0, 2)) else v.ctypes.data for s_, v in enumerate(vals)]
+    rc = lib.p2b_fill_ghost_values_f64(a.ctypes.data, C.byref(g), codes, *ptr, None)
+    ok = rc == 0 and np.array_equal(a[:, :qy], ref)
+    return ok, dict(kind="ghost_values", nx=nx, ny=ny, ng=ng, bc=bc, given=[v is not None for v in vals], rc=rc)
+
+
 def flow_case(lib, rng):
     ng = 4
     nx, ny = int(rng.integers(4, 40)), int(rng.integers(4, 40))
@@ -110,7 +136,7 @@ if __name__ == "__main__":
     ghost, flow = load_ghost_emu(), load_flow_emu()
     bad = 0
     for c in range(n):
-        ok, desc = (flow_case(flow, rng), cfl_case(ghost, rng), ghost_case(ghost, rng))[c % 3]
+        ok, desc = (flow_case, cfl_case, ghost_case, ghost_values_case)[c % 4](flow if c % 4 == 0 else ghost, rng)
         if not ok:
             bad += 1
             print("FAIL", c, desc, flush=True)
