@@ -146,13 +146,19 @@ class Simulation(NullSimulation):
             if any(t in bnd.ext_bcs for t in bc.names()):
                 msg.fail("ERROR: the hse / ambient / ramp boundaries are not built for SphericalPolar grids")
             # (one entry more than the padded row: the kernel also reads column j + 1 of the per-column tables)
-            gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1) + 2, bc.xlb, bc.xrb)
+            xl_type, xr_type = bc.xlb, bc.xrb
+            lo_int = hi_int = False
+            if self.decomposition is not None and self.decomposition.size > 1:
+                lo_int, hi_int = self.decomposition.interior_sides(bc.xlb == "periodic")
+                xl_type, xr_type = (None if lo_int else bc.xlb), (None if hi_int else bc.xrb)
+            gi, gj = patch.spherical_sweep_tables(my_grid, my_data.planes.stride(1) + 2, xl_type, xr_type)
             dev = my_data.planes.device
             self._geometry = (torch.from_numpy(gi).to(dev), torch.from_numpy(gj).to(dev))
             # across a "reflect" x boundary the reference's source arrays change sign (their own BCs, odd for the
             # normal momentum's source, with the state's parities: every product of them is -1); the literal
             # reflect-even / reflect-odd types and everything else leave the sign alone
-            self._src_flip_x = (int(rp.get_param("mesh.xlboundary") == "reflect"), int(rp.get_param("mesh.xrboundary") == "reflect"))
+            self._src_flip_x = (int(rp.get_param("mesh.xlboundary") == "reflect" and not lo_int),
+                                int(rp.get_param("mesh.xrboundary") == "reflect" and not hi_int))
             # ... and no flips in y: the parities of the spherical sources match those of the state there
             self._src_flip = (0, 0)
 
@@ -227,7 +233,10 @@ class Simulation(NullSimulation):
             u, v, cs = self.cc_data.get_var(["velocity", "soundspeed"])
             xtmp = g.Lx.t() / (u.t().abs() + cs.t())
             ytmp = g.Ly.t() / (v.t().abs() + cs.t())
-            self.dt = cfl * float(min(xtmp.min(), ytmp.min()))
+            local = torch.minimum(xtmp.min(), ytmp.min())
+            if self.decomposition is not None and self.decomposition.size > 1:
+                local = -self.decomposition.allreduce_max_((-local).reshape(1))[0]     # min over the slabs
+            self.dt = cfl * float(local)
             return
         standard = all(t not in bnd.ext_bcs for b in self.cc_data.BCs.values() for t in b.names())
         if self._wave_version is not None and self._wave_version == self.cc_data.version and standard:

@@ -150,21 +150,24 @@ def spherical_sweep_tables(grid, nj, xlb, xrb):
     sub-expression of mesh/patch.py:272-305 (or of the viscosity's vertex coordinates, interface.py:333-341) that
     depends on one index only, evaluated with numpy like the reference, so that the kernel's products -- formed in the
     reference's order -- give its 2-d arrays bit for bit.  xlb / xrb: the x boundary types; they decide which row's
-    radius the reference's ghost-filled source arrays carry in the ghost rows (row 1 of geo_i)"""
+    radius the reference's ghost-filled source arrays carry in the ghost rows (row 1 of geo_i); None for a side that
+    faces another x-slab"""
     g = grid
     xl, xr, x = g.xl, g.xr, g.x
     ximg = x.copy()
     for side, btype in (("lo", xlb), ("hi", xrb)):
         for k in range(g.ng):
             i = g.ilo - 1 - k if side == "lo" else g.ihi + 1 + k
-            if btype == "periodic":
+            if btype is None:                       # the side faces another slab: the halo rows are real cells
+                src = i
+            elif btype == "periodic":
                 src = i + g.nx if side == "lo" else i - g.nx
             elif str(btype).startswith("reflect"):
                 src = g.ilo + k if side == "lo" else g.ihi - k
             else:                                   # zero-gradient copies (outflow and everything that fills like it)
                 src = g.ilo if side == "lo" else g.ihi
             ximg[i] = x[src]
-    idx = np.arange(g.qx)
+    idx = np.arange(g.qx) + g.ioffset                # global row index (a slab's rows start at ioffset)
     geo_i = np.stack([x, ximg, -2.0 * np.pi * xl ** 2, xr ** 2 - xl ** 2, xr - xl, xr ** 2 + xl ** 2 + xr * xl,
                       (idx + 0.5 - g.ng) * g.dx + g.xmin, (idx - 0.5 - g.ng) * g.dx + g.xmin, (idx - g.ng) * g.dx + g.xmin])
     jdx = np.arange(nj)
@@ -182,8 +185,10 @@ class SphericalPolar(Grid2d):
     """spherical polar geometry with azimuthal symmetry, x = r, y = theta (patch.py:242-312): coord_type 1; side
     lengths, face areas (on the low faces), cell volumes and logarithmic area derivatives as device arrays"""
 
-    def __init__(self, nx, ny, *, ng=1, xmin=0.2, xmax=1.0, ymin=0.0, ymax=1.0, device=None):
-        super().__init__(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device=device)
+    def __init__(self, nx, ny, *, ng=1, xmin=0.2, xmax=1.0, ymin=0.0, ymax=1.0, device=None,
+                 nx_global=None, ioffset=0):
+        super().__init__(nx, ny, ng=ng, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, device=device,
+                         nx_global=nx_global, ioffset=ioffset)
         assert ymin >= 0.0 and ymax <= np.pi, "y or \u03b8 should be within [0, \u03c0]."
         assert xmin - ng * self.dx >= 0.0, \
             "xmin (r-direction), must be large enough so ghost cell doesn't have negative x."

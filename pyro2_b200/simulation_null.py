@@ -26,10 +26,14 @@ def grid_setup(rp, ng=1, decomposition=None):
     ymax = _param(rp, "mesh.ymax", 1.0)
     grid_type = _param(rp, "mesh.grid_type", "Cartesian2d")
     if grid_type == "SphericalPolar":
-        # x = r, y = theta (simulation_null.py:46-68); single GPU
+        # x = r, y = theta (simulation_null.py:46-68)
         if decomposition is not None and decomposition.size > 1:
-            raise ValueError("SphericalPolar grids are not decomposed")
-        my_grid = patch.SphericalPolar(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)
+            if decomposition.local_nx(nx) < ng:
+                raise ValueError(f"mesh.nx = {nx} on {decomposition.size} slabs leaves fewer than ng = {ng} rows per slab")
+            my_grid = patch.SphericalPolar(decomposition.local_nx(nx), ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax,
+                                           ng=ng, nx_global=nx, ioffset=decomposition.ioffset(nx))
+        else:
+            my_grid = patch.SphericalPolar(nx, ny, xmin=xmin, xmax=xmax, ymin=ymin, ymax=ymax, ng=ng)
         # the polar axis is a reflecting boundary
         if ymin <= 0.05:
             rp.set_param("mesh.ylboundary", "reflect")

@@ -279,6 +279,10 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
 @pytest.mark.parametrize("solver,problem,inputs,nsteps,size", [
     pytest.param("advection", "smooth", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2, marks=_FULL),
     ("advection", "tophat", {"mesh.nx": 36, "mesh.ny": 24, "advection.u": -0.6, "advection.limiter": 1}, 5, 3),
+    ("compressible", "advect", {"mesh.grid_type": "SphericalPolar", "mesh.nx": 24, "mesh.ny": 20, "mesh.xmin": 1.0, "mesh.xmax": 2.0,
+                                "mesh.ymin": 0.523, "mesh.ymax": 2.617, "mesh.xlboundary": "reflect", "mesh.xrboundary": "outflow",
+                                "mesh.ylboundary": "outflow", "mesh.yrboundary": "outflow", "compressible.riemann": "CGF",
+                                "compressible.grav": -0.5, "driver.fix_dt": -1.0}, 3, 3),      # SphericalPolar on slabs
     ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
     pytest.param("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3, marks=_FULL),                # periodic
     ("diffusion", "gaussian", {"mesh.nx": 128, "mesh.ny": 128, "diffusion.mg_split_n": 64}, 2, 2),
