@@ -50,7 +50,9 @@ def init_data(my_data, rp):
     ener = p / (gamma - 1.0)
     # seeded velocity perturbation with Mach number < 0.05 wherever the gas is dense enough
     rng = np.random.default_rng(12345)
-    vel_pert = 2.0 * rng.random(size=(g.qx, g.qy, 2)) - 1
+    # (drawn for the global array, of which an x-slab takes its rows: a decomposed run then starts from the
+    # single-domain state)
+    vel_pert = 2.0 * rng.random(size=(g.nx_global + 2 * g.ng, g.qy, 2))[g.ioffset:g.ioffset + g.qx] - 1
     with np.errstate(invalid="ignore", divide="ignore"):
         cs = np.sqrt(gamma * p / dens)
     vel_pert[:, :, 0] *= 0.05 * cs

@@ -110,8 +110,6 @@ class Simulation(NullSimulation):
 
         bc, bc_xodd, bc_yodd = bc_setup(rp)
         self.solid = bnd.bc_is_solid(bc)
-        if self.decomposition is not None and any(t in bnd.ext_bcs for t in bc.names()):
-            msg.fail("ERROR: user-defined boundaries are not supported on a decomposed domain")
         # the reference fills the ghost cells of its gravity-source arrays odd / even across a reflecting
         # y wall (simulation.py:248-253): the sweep flips the sign of the ghost-cell sources there
         self._src_flip = (int(bc.ylb in ("reflect", "reflect-even", "reflect-odd")),
@@ -172,8 +170,12 @@ class Simulation(NullSimulation):
             plane[0, :, :my_grid.qy].copy_(torch.from_numpy(np.ascontiguousarray(prof, dtype=np.float64)))
             # the reference ghost-fills its energy-source array with the scalar BCs (user types copy like outflow):
             # filling the profile the same way gives the kernel the source of the cell each ghost cell mirrors
-            names = tuple("outflow" if t in bnd.ext_bcs else t for t in bc.names())
-            ops.fill_ghost(plane, my_grid.nx, my_grid.ny, my_grid.ng, [names])
+            names = ["outflow" if t in bnd.ext_bcs else t for t in bc.names()]
+            if self.decomposition is not None and self.decomposition.size > 1:
+                # the profile was evaluated on the slab's own coordinates: the rows facing another slab are right already
+                lo_int, hi_int = self.decomposition.interior_sides(bc.xlb == "periodic")
+                names = [None if lo_int else names[0], None if hi_int else names[1], names[2], names[3]]
+            ops.fill_ghost(plane, my_grid.nx, my_grid.ny, my_grid.ng, [tuple(names)])
             self._heat_rate, self._heat_plane = float(rate), plane
         if self.verbose > 0:
             print(my_data)

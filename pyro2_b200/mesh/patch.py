@@ -335,10 +335,11 @@ class CellCenterData2d:
             return
         ops.fill_ghost(self.planes, g.nx, g.ny, g.ng, [b.names() for b in bcs])
 
-    def _fill_BC_all_slab(self, bcs, planes=None):
+    def _fill_BC_all_slab(self, bcs, planes=None, first=0):
         """x-slab of a decomposed domain: neighbour rows first (they are the "x fill" of interior
         sides), then the physical x sides and the y sides over the full x range -- the same order as
-        the single-domain fill (array_indexer.py:164-274), so corners come out identical."""
+        the single-domain fill (array_indexer.py:164-274), so corners come out identical.  planes: the planes of the
+        variables bcs describes (default: all of them), the first of which is variable number `first`"""
         g = self.grid
         planes = self.planes if planes is None else planes
         periodic = bcs[0].xlb == "periodic"
@@ -346,13 +347,28 @@ class CellCenterData2d:
         lo_int, hi_int = self.decomposition.interior_sides(periodic)
         names = []
         for b in bcs:
-            n = list(b.names())
+            n = [None if t in bnd.ext_bcs else t for t in b.names()]     # user types: filled by their hooks below
             if lo_int:
                 n[0] = None
             if hi_int:
                 n[1] = None
             names.append(tuple(n))
-        ops.fill_ghost(planes, g.nx, g.ny, g.ng, names)
+        if not any(t in bnd.ext_bcs for b in bcs for t in b.names()):
+            ops.fill_ghost(planes, g.nx, g.ny, g.ng, names)
+            return
+        # user-defined boundaries: variable by variable like the single-domain fill (standard types, then the hooks in
+        # the order xlb, xrb, ylb, yrb -- patch.py:582-624), after ALL halo rows have arrived: a hook may read other
+        # variables (the hse energy uses the base row's density and momenta), and the halo rows stand for cells that
+        # are ordinary interior cells of the single domain.  Hooks on an x side run on the physical sides only.
+        for k, b in enumerate(bcs):
+            ops.fill_ghost(planes[k:k + 1], g.nx, g.ny, g.ng, [names[k]])
+            name = self.names[first + k]
+            for side, btype, interior in zip(("xlb", "xrb", "ylb", "yrb"), b.names(), (lo_int, hi_int, False, False)):
+                if btype in bnd.ext_bcs and not interior:
+                    try:
+                        bnd.ext_bcs[btype](btype, side, name, self, self.ivars)
+                    except TypeError:
+                        bnd.ext_bcs[btype](btype, side, name, self)
 
     def fill_BC(self, name):
         """one variable: standard types on the device, then any user-registered callbacks
@@ -360,7 +376,7 @@ class CellCenterData2d:
         n = self.names.index(name)
         bc = self.BCs[name]
         if self.decomposition is not None and self.decomposition.size > 1:
-            self._fill_BC_all_slab([bc], planes=self.planes[n:n + 1])
+            self._fill_BC_all_slab([bc], planes=self.planes[n:n + 1], first=n)
             return
         self.get_var_by_index(n).fill_ghost(bc=_StandardOnly(bc))
         for side, btype in zip(("xlb", "xrb", "ylb", "yrb"), bc.names()):

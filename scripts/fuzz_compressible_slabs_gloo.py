@@ -62,7 +62,12 @@ PROBLEMS = {"sedov": ({"sedov.r_init": 0.15}, ["outflow", "reflect", "periodic"]
             "quad": ({}, ["outflow", "reflect"], ["outflow", "reflect"]),
             "kh": ({}, ["periodic"], ["periodic", "reflect"]),
             "rt": ({"mesh.ymax": 3.0}, ["periodic", "reflect"], ["reflect"]),
-            "advect": ({}, ["periodic", "outflow"], ["periodic", "outflow"])}
+            "advect": ({}, ["periodic", "outflow"], ["periodic", "outflow"]),
+            # gravity problems with the user-defined y boundaries (hooks run per slab after the halo exchange)
+            "bubble": ({"mesh.ymax": 4.0}, ["outflow", "periodic", "reflect"], ["hse"]),
+            "hse": ({}, ["periodic"], ["hse"]),
+            "plume": ({"mesh.ymax": 4.0}, ["outflow", "reflect"], ["hse"]),
+            "convection": ({}, ["periodic"], ["reflect+ambient"])}
 
 if __name__ == "__main__":
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 10
@@ -77,10 +82,14 @@ if __name__ == "__main__":
         inputs = dict(base)
         inputs.update({"mesh.nx": size * int(rng.integers(4, 9)), "mesh.ny": int(rng.choice([12, 31, 36])),
                        "mesh.xlboundary": xb, "mesh.xrboundary": xb if xb == "periodic" or rng.integers(2) else "outflow",
-                       "mesh.ylboundary": yb, "mesh.yrboundary": yb if yb == "periodic" or rng.integers(2) else "outflow",
+                       "mesh.ylboundary": yb, "mesh.yrboundary": yb if yb in ("periodic", "hse") or rng.integers(2) else "outflow",
                        "compressible.riemann": str(rng.choice(["HLLC", "CGF", "HLLC_lm"])),
                        "compressible.limiter": int(rng.integers(3)), "compressible.cvisc": float(rng.choice([0.1, 0.0])),
                        "driver.max_steps": 10 ** 6, "driver.tmax": 1e9, "driver.verbose": 0})
+        if yb == "reflect+ambient":
+            inputs.update({"mesh.ylboundary": "reflect", "mesh.yrboundary": "ambient", "mesh.ny": 72})
+        if yb == "hse":
+            inputs["mesh.ny"] = 36
         if problem == "rt":
             inputs["compressible.grav"] = -1.0
         if problem in ("sedov", "quad") and inputs["compressible.limiter"] == 0:

@@ -283,6 +283,10 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
                                 "mesh.ymin": 0.523, "mesh.ymax": 2.617, "mesh.xlboundary": "reflect", "mesh.xrboundary": "outflow",
                                 "mesh.ylboundary": "outflow", "mesh.yrboundary": "outflow", "compressible.riemann": "CGF",
                                 "compressible.grav": -0.5, "driver.fix_dt": -1.0}, 3, 3),      # SphericalPolar on slabs
+    # user-defined y boundaries: the hse hooks run per slab after all halo rows have arrived
+    ("compressible", "bubble", {"mesh.nx": 18, "mesh.ny": 36, "mesh.ymax": 4.0, "mesh.xlboundary": "outflow", "mesh.xrboundary": "outflow",
+                                "mesh.ylboundary": "hse", "mesh.yrboundary": "hse"}, 3, 3),
+    pytest.param("compressible", "convection", {"mesh.nx": 16, "mesh.ny": 72}, 3, 4, marks=_FULL),    # ambient top, heating, sponge
     ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
     pytest.param("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3, marks=_FULL),                # periodic
     ("diffusion", "gaussian", {"mesh.nx": 128, "mesh.ny": 128, "diffusion.mg_split_n": 64}, 2, 2),
