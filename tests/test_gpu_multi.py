@@ -48,6 +48,11 @@ def test_decomposed_multigrid_is_bit_identical(kind, n, split):
 
 @pytest.mark.parametrize("solver,problem,nx,ny,nsteps,extra", [
     ("advection", "smooth", 256, 256, 20, []), ("burgers", "test", 256, 128, 20, []),
+    ("compressible", "bubble", 128, 256, 10, ["mesh.ymax=4.0", "mesh.ylboundary=hse", "mesh.yrboundary=hse"]),
+    ("compressible", "advect", 128, 96, 10, ["mesh.grid_type=SphericalPolar", "mesh.xmin=1.0", "mesh.xmax=2.0", "mesh.ymin=0.523",
+                                             "mesh.ymax=2.617", "mesh.xlboundary=reflect", "mesh.xrboundary=outflow",
+                                             "mesh.ylboundary=outflow", "mesh.yrboundary=outflow", "compressible.riemann=CGF",
+                                             "driver.fix_dt=-1.0"]),
     ("diffusion", "gaussian", 256, 256, 5, ["diffusion.mg_split_n=128"]),
     ("incompressible", "shear", 256, 256, 3, ["incompressible.mg_split_n=128"])])
 def test_decomposed_flow_solvers_are_bit_identical(solver, problem, nx, ny, nsteps, extra):
