@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-incomp", action="store_true", help="skip the incompressible-shear leg (N = 1 only)")
     ap.add_argument("--incomp-nx", type=int, default=2048)
+    ap.add_argument("--incomp-multi", action="store_true",
+                    help="N > 1: also run the incompressible leg, on x-slabs of the same global problem (strong scaling; "
+                         "off by default until the decomposed flow solvers have been run over NCCL)")
     return ap.parse_args()
 
 
@@ -407,12 +410,12 @@ def main():
 
     # ---- incompressible shear 2048^2 (BASELINE config 4): explicit stages + two multigrid projections ----
     incomp = None
-    if world == 1 and not args.skip_incomp:
+    if (world == 1 or args.incomp_multi) and not args.skip_incomp:
         torch.cuda.empty_cache()
         ni = args.incomp_nx
         pi = Pyro("incompressible")
         pi.initialize_problem("shear", inputs_dict={"mesh.nx": ni, "mesh.ny": ni, "driver.max_steps": 10 ** 9,
-                                                    "driver.tmax": 1.e9})
+                                                    "driver.tmax": 1.e9}, **({"decomposition": slab} if slab else {}))
         isim = pi.sim
         pi.single_step()
         barrier()
@@ -424,9 +427,14 @@ def main():
         e1.record()
         barrier()
         ims = e0.elapsed_time(e1) / ki
+        if world > 1:
+            tms = torch.tensor([ims], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ims = float(tms)
         solver = next(iter(isim._mg.values()))[0]
         incomp = {"metric": "zone-updates/s", "value": ni * ni / (ims * 1e-3), "unit": "zone-updates/s", "ms_per_step": ims,
-                  "steps": ki, "config": {"workload": f"incompressible shear {ni}^2 fp64, periodic, limiter 2, proj_type 2",
+                  "steps": ki, "n_gpus": world, "scaling": "strong",
+                  "config": {"workload": f"incompressible shear {ni}^2 fp64 (global), periodic, limiter 2, proj_type 2",
                                           "note": "each step = p2b_flow_* explicit stages + 2 multigrid projections at rtol 1e-12; "
                                                   "at this size the reference's own stopping rule runs both to max_cycles = 100"},
                   "v_cycles_last_solve": solver.num_cycles, "gpu_launches_explicit": 14}
