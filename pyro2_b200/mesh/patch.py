@@ -360,6 +360,8 @@ class CellCenterData2d:
         # the order xlb, xrb, ylb, yrb -- patch.py:582-624), after ALL halo rows have arrived: a hook may read other
         # variables (the hse energy uses the base row's density and momenta), and the halo rows stand for cells that
         # are ordinary interior cells of the single domain.  Hooks on an x side run on the physical sides only.
+        # (fill_BC(name) exchanges that variable's planes alone: a hook that reads OTHER variables then sees their halo
+        # rows as of the last full fill -- the solvers here only ever fill all variables together.)
         for k, b in enumerate(bcs):
             ops.fill_ghost(planes[k:k + 1], g.nx, g.ny, g.ng, [names[k]])
             name = self.names[first + k]
