@@ -148,3 +148,59 @@ class Pyro:
 
     def get_sim(self):
         return self.sim
+
+
+class PyroBenchmark(Pyro):
+    """Pyro plus the regression bookkeeping of the reference (pyro_sim.py:324-408): compare the final state with a stored
+    snapshot <pyro_home>/<solver>/tests/<basename><nnnn>.h5, or store one.  Snapshots need h5py (util/io_pyro.py)."""
+
+    def __init__(self, solver_name, *, comp_bench=False, reset_bench_on_fail=False, make_bench=False):
+        super().__init__(solver_name)
+        self.comp_bench = comp_bench
+        self.reset_bench_on_fail = reset_bench_on_fail
+        self.make_bench = make_bench
+
+    def _bench_file(self):
+        basename = self.rp.get_param("io.basename")
+        return f"{self.pyro_home}{self.solver_name}/tests/{basename}{self.sim.n:04d}"
+
+    def run_sim(self, rtol=1.e-12):
+        """evolve to the end, then compare with / store the benchmark; returns the comparison result when
+        comparing (0 = match), else the simulation object"""
+        super().run_sim()
+        result = 0
+        if self.comp_bench:
+            result = self.compare_to_benchmark(rtol)
+        if self.make_bench or (result != 0 and self.reset_bench_on_fail):
+            self.store_as_benchmark()
+        if self.comp_bench:
+            return result
+        return self.sim
+
+    def compare_to_benchmark(self, rtol):
+        from .util import compare   # pylint: disable=import-outside-toplevel
+        from .util import io_pyro as io   # pylint: disable=import-outside-toplevel
+        compare_file = self._bench_file()
+        msg.warning(f"comparing to: {compare_file} ")
+        try:
+            sim_bench = io.read(compare_file, device=self.sim.cc_data.grid.device)
+        except OSError:
+            msg.warning("ERROR opening compare file")
+            return "ERROR opening compare file"
+        result = compare.compare(self.sim.cc_data, sim_bench.cc_data, rtol)
+        if result == 0:
+            msg.success(f"results match benchmark to within relative tolerance of {rtol}\n")
+        else:
+            msg.warning("ERROR: " + compare.errors[result] + "\n")
+        return result
+
+    def store_as_benchmark(self):
+        tests = f"{self.pyro_home}{self.solver_name}/tests/"
+        if not os.path.isdir(tests):
+            try:
+                os.mkdir(tests)
+            except (FileNotFoundError, PermissionError):
+                msg.fail("ERROR: unable to create the solver's tests/ directory")
+        bench_file = self._bench_file()
+        msg.warning(f"storing new benchmark: {bench_file}\n")
+        self.sim.write(bench_file)
