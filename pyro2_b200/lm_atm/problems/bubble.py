@@ -30,21 +30,26 @@ def init_data(my_data, base, rp):
     x_pert, y_pert, r_pert = rp.get_param("bubble.x_pert"), rp.get_param("bubble.y_pert"), rp.get_param("bubble.r_pert")
     factor = rp.get_param("bubble.pert_amplitude_factor")
 
-    dens = np.full((g.qx, g.qy), dens_cutoff)
+    # The fields are built for the whole domain (an x-slab of a decomposed run takes its rows at the end): the base
+    # state is the mean over ALL rows, summed in the single-domain order.
+    qx, ng = g.nx_global + 2 * g.ng, g.ng
+    gx = 0.5 * (((np.arange(qx) - ng) * g.dx + g.xmin) + ((np.arange(qx) + 1.0 - ng) * g.dx + g.xmin))   # Grid2d's x, all rows
+    dens = np.full((qx, g.qy), dens_cutoff)
     for j in range(g.jlo, g.jhi + 1):
         dens[:, j] = max(dens_base * np.exp(-g.y[j] / scale_height), dens_cutoff)
     cs2 = scale_height * abs(grav)
     pres = cs2 * dens                                    # isothermal: p = cs^2 rho
     eint = pres / (gamma - 1.0) / dens
-    x = np.broadcast_to(g.x[:, None], (g.qx, g.qy))
-    y = np.broadcast_to(g.y[None, :], (g.qx, g.qy))
+    x = np.broadcast_to(gx[:, None], (qx, g.qy))
+    y = np.broadcast_to(g.y[None, :], (qx, g.qy))
     idx = np.sqrt((x - x_pert) ** 2 + (y - y_pert) ** 2) <= r_pert
     eint[idx] = eint[idx] * factor                       # hotter at constant pressure -> lighter
     dens[idx] = pres[idx] / (eint[idx] * (gamma - 1.0))
-    my_data.get_var("density")[:, :] = dens
+    rows = slice(g.ioffset, g.ioffset + g.qx)
+    my_data.get_var("density")[:, :] = dens[rows]
     my_data.get_var("x-velocity")[:, :] = 0.0
     my_data.get_var("y-velocity")[:, :] = 0.0
-    my_data.get_var("eint")[:, :] = eint
+    my_data.get_var("eint")[:, :] = eint[rows]
 
     base["rho0"].d[:] = np.mean(dens, axis=0)
     base["p0"].d[:] = np.mean(pres, axis=0)

@@ -46,6 +46,16 @@ class Basestate:
         return self.d[self.jlo - buf + shift:self.jhi + 1 + buf + shift]
 
 
+class _Plain:
+    """a bare device array with the one ArrayIndexer method the divergence kernels' callers use"""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def t(self):
+        return self._t
+
+
 class Simulation(NullSimulation):
     def __init__(self, solver_name, problem_name, problem_func, rp, *, problem_finalize_func=None,
                  problem_source_func=None, timers=None):
@@ -55,9 +65,14 @@ class Simulation(NullSimulation):
         self.in_preevolve = False
 
     def initialize(self):
-        if self.decomposition is not None and self.decomposition.size > 1:
-            msg.fail("ERROR: lm_atm runs on one GPU (the variable-coefficient multigrid is not decomposed)")
-        myg = grid_setup(self.rp, ng=4)
+        # decomposition (extension): x-slabs for the explicit stages; the two variable-coefficient projections of a
+        # step are solved REPLICATED -- coefficients, right-hand side and initial guess are all-gathered and every rank
+        # runs the single-domain solver (the variable-coefficient hierarchy itself is not decomposed), then keeps its
+        # slab of the solution.  Bit-identical to the single-domain run; periodic in x only.
+        self._decomposed = self.decomposition is not None and self.decomposition.size > 1
+        if self._decomposed and self.rp.get_param("mesh.xlboundary") != "periodic":
+            msg.fail("ERROR: a decomposed lm_atm run needs periodic x boundaries")
+        myg = grid_setup(self.rp, ng=4, decomposition=self.decomposition)
         bc_dens, bc_xodd, bc_yodd = bc_setup(self.rp)
         my_data = self.data_class(myg)
         my_data.register_var("density", bc_dens)
@@ -78,6 +93,7 @@ class Simulation(NullSimulation):
         my_data.register_var("gradp_x", bc_dens)
         my_data.register_var("gradp_y", bc_dens)
         my_data.create()
+        my_data.decomposition = self.decomposition
         self.cc_data = my_data
         self._bc_dens, self._bc_yodd, self._bc_phi = bc_dens, bc_yodd, bc_phi
 
@@ -111,22 +127,62 @@ class Simulation(NullSimulation):
         g = self.cc_data.grid
         return plane[g.ilo - 1:g.ihi + 2, g.jlo - 1:g.jhi + 2]
 
+    def _gather_rows(self, local):
+        """slab runs: the (nx_global + 2, ny + 2) array of the whole domain from every rank's (nx + 2, ny + 2) buf-1
+        array -- the owned rows of each slab, the low ghost row of the first and the high ghost row of the last"""
+        import torch.distributed as dist   # pylint: disable=import-outside-toplevel
+        d, g = self.decomposition, self.cc_data.grid
+        mine = local.contiguous()
+        parts = torch.empty((d.size,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(parts.view(-1), mine.reshape(-1), group=d.group)
+        full = torch.empty((g.nx_global + 2, mine.shape[1]), dtype=mine.dtype, device=mine.device)
+        full[1:-1] = parts[:, 1:-1].reshape(g.nx_global, mine.shape[1])
+        full[0], full[-1] = parts[0, 0], parts[-1, -1]
+        return full
+
+    def _my_rows(self, full):
+        """this slab's buf-1 rows of a whole-domain (nx_global + 2, ny + 2) array"""
+        g = self.cc_data.grid
+        return full[g.ioffset:g.ioffset + g.nx + 2]
+
     def _solver(self):
         """the variable-coefficient solver on the solver's domain with phi's boundary types; its coefficients are
-        replaced before every projection (the MAC and final projections share the BCs, simulation.py:75-96)"""
+        replaced before every projection (the MAC and final projections share the BCs, simulation.py:75-96).
+        Returns (solver, the array the divergence is written into); slab runs: the solver covers the whole domain and
+        the divergence array is this slab's part, handed to the solver by _set_rhs"""
         g = self.cc_data.grid
         coeff = self._buf1(self._lm.plane(LmHandle.COEFF)[:, :g.qy])
+        if self._decomposed:
+            coeff = self._gather_rows(coeff)
         if self._mg is None:
             b = self._bc_phi
-            self._mg = vcMG.VarCoeffCCMG2d(g.nx, g.ny, xl_BC_type=b.xlb, xr_BC_type=b.xrb, yl_BC_type=b.ylb,
+            self._mg = vcMG.VarCoeffCCMG2d(g.nx_global, g.ny, xl_BC_type=b.xlb, xr_BC_type=b.xrb, yl_BC_type=b.ylb,
                                            yr_BC_type=b.yrb, xmin=g.xmin, xmax=g.xmax, ymin=g.ymin, ymax=g.ymax,
                                            coeffs=coeff, coeffs_bc=self._bc_dens, verbose=0)
             self._divU = self._mg.soln_grid.scratch_array()
+            if self._decomposed:
+                self._divU = _Plain(torch.zeros((g.nx + 2, self._divU.shape[1]), dtype=torch.float64,
+                                                device=self.cc_data.planes.device))
         else:
             self._mg.set_coeffs(coeff)
         return self._mg, self._divU
 
+    def _set_rhs(self, mg, divU):
+        mg.init_RHS(self._gather_rows(divU.t()) if self._decomposed else divU)
+
+    def _solution(self, mg):
+        """the buf-1 part of the solution this rank's phi planes take"""
+        soln = mg.grids[mg.nlevels - 1].get_var("v").t()
+        return self._my_rows(soln) if self._decomposed else soln
+
     def _fill_aux(self, plane, bc):
+        if self._decomposed:
+            # periodic x: both sides face another slab -- their rows are exchanged, the y sides filled as usual
+            g = self.cc_data.grid
+            self.decomposition.exchange(self._lm.plane(plane).unsqueeze(0), g.nx, g.ng, periodic=True)
+            names = bc.names()
+            self._lm.fill(plane, (None, None, names[2], names[3]))
+            return
         self._lm.fill(plane, bc.names())
 
     # ---- timestep (simulation.py:138-178) ---------------------------------------------------------------------
@@ -135,7 +191,11 @@ class Simulation(NullSimulation):
         cfl = self.rp.get_param("driver.cfl")
         P = self._planes()
         grav = self.rp.get_param("lm-atmosphere.grav")
-        uall, vall, uval, vval, fbuoy = self._lm.reduce(P["density"], P["x-velocity"], P["y-velocity"], grav)
+        red = self._lm.reduce(P["density"], P["x-velocity"], P["y-velocity"], grav)
+        if self._decomposed:
+            red = self.decomposition.allreduce_max_(torch.tensor(red, dtype=torch.float64,
+                                                                 device=self.cc_data.planes.device)).tolist()
+        uall, vall, uval, vval, fbuoy = red
         xtmp = ytmp = 1.e33
         if not uall == 0:
             xtmp = g.dx / uval
@@ -162,10 +222,10 @@ class Simulation(NullSimulation):
         mg, divU = self._solver()
         lm.cc_divergence(u, v, divU.t())
         mg.init_zeros()
-        mg.init_RHS(divU)
+        self._set_rhs(mg, divU)
         mg.solve(rtol=1.e-10)
         phi.zero_()
-        self._buf1(phi).copy_(mg.grids[mg.nlevels - 1].get_var("v").t())
+        self._buf1(phi).copy_(self._solution(mg))
         lm.project(rho, phi, u, v, None, None, 1.0, 0)
         self.cc_data.fill_BC("x-velocity")
         self.cc_data.fill_BC("y-velocity")
@@ -208,16 +268,23 @@ class Simulation(NullSimulation):
             print("  MAC projection")
         lm.coeff(rho, None, 1.0, True, 1)                  # coeff.v(buf=1) = beta0^2 / rho
         mg, divU = self._solver()
-        soln = mg.grids[mg.nlevels - 1].get_var("v").t()
         lm.mac_divergence(divU.t())
         mg.init_zeros()
-        mg.init_RHS(divU)
+        self._set_rhs(mg, divU)
         mg.solve(rtol=1.e-12)
         phi_MAC.zero_()
-        self._buf1(phi_MAC).copy_(soln)
+        self._buf1(phi_MAC).copy_(self._solution(mg))
         lm.coeff(rho, None, 1.0, False, 0)
         self._fill_aux(LmHandle.COEFF, self._bc_dens)
         lm.mac_project(phi_MAC)
+        if self._decomposed:
+            # The density prediction in a cell next to a slab boundary upwinds against the neighbour cell's state, which
+            # is traced with the MAC velocities on THAT cell's faces: projected interior faces in the single-domain run.
+            # The halo faces here were not projected (the projection covers the owned faces), so take the neighbour's.
+            # Only across interior slab boundaries: at the domain's periodic seam the single-domain run itself uses the
+            # unprojected ghost-face velocities.
+            for k in (LmHandle.U_MAC, LmHandle.V_MAC):
+                self.decomposition.exchange(lm.plane(k).unsqueeze(0), g.nx, g.ng, periodic=False)
 
         # density: predict to the faces with the MAC velocities, conservative update, eint from the base pressure
         lm.density_update(rho, eint, dt, limiter, gamma)
@@ -243,11 +310,11 @@ class Simulation(NullSimulation):
         lm.coeff(rho, None, 1.0, True, 0)
         mg, divU = self._solver()
         lm.cc_divergence(u, v, divU.t(), dt=dt, divide=True)
-        mg.init_RHS(divU)
-        mg.init_solution(self._buf1(phi))
+        self._set_rhs(mg, divU)
+        mg.init_solution(self._gather_rows(self._buf1(phi)) if self._decomposed else self._buf1(phi))
         mg.solve(rtol=1.e-12)
         phi.zero_()
-        self._buf1(phi).copy_(soln)
+        self._buf1(phi).copy_(self._solution(mg))
         lm.project(rho, phi, u, v, gradp_x, gradp_y, dt, proj_type)
         for name in ("x-velocity", "y-velocity", "gradp_x", "gradp_y"):
             self.cc_data.fill_BC(name)

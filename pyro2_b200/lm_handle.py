@@ -10,7 +10,7 @@ from . import _lib, ops
 
 
 class LmHandle:
-    COEFF, SOURCE, RHO_OLD = 16, 17, 24
+    U_MAC, V_MAC, COEFF, SOURCE, RHO_OLD = 14, 15, 16, 17, 24
 
     def __init__(self, planes, grid, basestate):
         """planes: the solver's (nvar, qx, pitch) state storage; basestate: (4, qy) CUDA float64 tensor holding

@@ -53,6 +53,7 @@ def test_decomposed_multigrid_is_bit_identical(kind, n, split):
                                              "mesh.ymax=2.617", "mesh.xlboundary=reflect", "mesh.xrboundary=outflow",
                                              "mesh.ylboundary=outflow", "mesh.yrboundary=outflow", "compressible.riemann=CGF",
                                              "driver.fix_dt=-1.0"]),
+    ("lm_atm", "bubble", 128, 128, 3, []),
     ("diffusion", "gaussian", 256, 256, 5, ["diffusion.mg_split_n=128"]),
     ("incompressible", "shear", 256, 256, 3, ["incompressible.mg_split_n=128"])])
 def test_decomposed_flow_solvers_are_bit_identical(solver, problem, nx, ny, nsteps, extra):

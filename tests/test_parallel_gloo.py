@@ -287,6 +287,8 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
     ("compressible", "bubble", {"mesh.nx": 18, "mesh.ny": 36, "mesh.ymax": 4.0, "mesh.xlboundary": "outflow", "mesh.xrboundary": "outflow",
                                 "mesh.ylboundary": "hse", "mesh.yrboundary": "hse"}, 3, 3),
     pytest.param("compressible", "convection", {"mesh.nx": 16, "mesh.ny": 72}, 3, 4, marks=_FULL),    # ambient top, heating, sponge
+    # lm_atm: explicit stages on slabs, the two variable-coefficient projections replicated after all-gathers
+    ("lm_atm", "bubble", {"mesh.nx": 32, "mesh.ny": 32}, 1, 2),
     ("burgers", "test", {"mesh.nx": 32, "mesh.ny": 32}, 5, 2),                  # outflow x sides
     pytest.param("burgers", "tophat", {"mesh.nx": 48, "mesh.ny": 32}, 4, 3, marks=_FULL),                # periodic
     ("diffusion", "gaussian", {"mesh.nx": 128, "mesh.ny": 128, "diffusion.mg_split_n": 64}, 2, 2),
