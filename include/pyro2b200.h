@@ -142,6 +142,13 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
 /* launch geometry chosen for the last sweep (bench diagnostics): tasks, resident warps, seglen */
 int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
 
+/* test probe of the sweep's branch-free fp64 helpers (csrc/hydro_core.cuh: rcp / fdiv / fsqrt -- MUFU seed + Newton,
+ * no special-case handling), so their behaviour on 0, denormals, inf and the <= 2 ulp bound can be pinned on the
+ * device (the host emulator has its own restatement).  op 0: out = rcp(a), 1: out = fdiv(a, b), 2: out = fsqrt(a),
+ * 3: out = the HLLC_lm solver's normal-momentum flux for the face (rho, E, mn, mt) = (a[4k..4k+3]) | (b[4k..4k+3]),
+ * gamma = 1.4 (riemann.py:864-1019; n counts faces for op 3).  Device pointers. */
+int p2b_test_fastmath(int op, const double* a, const double* b, double* out, int n, void* stream);
+
 /* ---- multigrid: CellCenterMG2d (pyro/multigrid/MG.py:77-778), constant coefficients,
  * (alpha - beta L) phi = f, nx = ny = 2^k, ng = 1.  The handle is a host object; the hierarchy's
  * device memory (p2b_mg_workspace_bytes, zero-initialised, 16-byte aligned) is allocated by the

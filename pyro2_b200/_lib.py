@@ -18,12 +18,31 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--shared"]
 
 
+def source_hash():
+    """sha256 over the compiler flags and every source / header of the library: the staleness criterion (mtimes do
+    not survive a snapshot to the GPU box, and the .so is git-ignored but shipped in-tree)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in SOURCES + HEADERS:
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            h.update(name.encode())
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
+def built_hash():
+    """the source hash recorded when the in-tree .so was built (None: no record)"""
+    try:
+        with open(SO_PATH + ".hash") as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def _stale():
-    if not os.path.exists(SO_PATH):
-        return True
-    t = os.path.getmtime(SO_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(SO_PATH) or built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -32,10 +51,33 @@ def build(force=False, verbose=False):
         return SO_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    tmp = SO_PATH + f".{os.getpid()}.tmp"
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + f".{os.getpid()}.o")
+        res = subprocess.run([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src],
+                             capture_output=True, text=True)
+        return obj, res
+
+    # one nvcc per translation unit, in parallel (the sweep and multigrid units dominate), then one link
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    log = "".join(r.stdout + r.stderr for _, r in results)
+    if any(r.returncode != 0 for _, r in results):
+        raise RuntimeError("nvcc failed:\n" + log)
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
+    for o, _ in results:
+        os.remove(o)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    res.stderr = log + res.stderr
+    os.replace(tmp, SO_PATH)
+    with open(SO_PATH + ".hash", "w") as fh:
+        fh.write(source_hash() + "\n")
     if verbose:
         print(res.stderr)
     return SO_PATH
@@ -79,6 +121,7 @@ SIGNATURES = {
     "p2b_cfl_wavemax": (_i, [_vp, _PG, _d, _vp, _vp]),
     "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "p2b_test_fastmath": (_i, [_i, _vp, _vp, _vp, _i, _vp]),
     "p2b_mg_create": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i]),
     "p2b_mg_create_slab": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i]),
     "p2b_mg_level_info": (_i, [_vp, _i, C.POINTER(_ll)]),

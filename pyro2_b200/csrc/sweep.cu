@@ -107,6 +107,19 @@ sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
     }
 }
 
+__global__ void fastmath_probe_kernel(int op, const double* a, const double* b, double* out, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (op == 0) out[k] = rcp(a[k]);
+    else if (op == 1) out[k] = fdiv(a[k], b[k]);
+    else if (op == 2) out[k] = fsqrt(a[k]);
+    else {
+        const double* l = a + 4 * k; const double* r = b + 4 * k;
+        out[k] = hllc_lm(l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], hllc_par(1.4)).mn;
+    }
+}
+
 static int g_last_ntasks = 0, g_last_resident = 0, g_last_seglen = 0;
 
 static int resident_warps()
@@ -169,6 +182,15 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
         if (grav) sweep_kernel<true, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
         else sweep_kernel<false, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
     }
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+int p2b_test_fastmath(int op, const double* a, const double* b, double* out, int n, void* stream)
+{
+    P2B_REQUIRE(op >= 0 && op <= 3 && a && out && n >= 0 && (b || op == 0 || op == 2), "bad probe arguments");
+    if (n == 0) return P2B_OK;
+    fastmath_probe_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(op, a, b, out, n);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }

@@ -182,3 +182,19 @@ extern "C" void emu_sweep_decomposition(const p2b_grid* g, int resident, int* nt
     *seglen = pyro::choose_seglen(g->nx, nstrips, resident);
     *ntasks = nstrips * ((g->nx + *seglen - 1) / *seglen);
 }
+
+// the device's branch-free helpers as the emulator restates them (hydro_core.cuh, host branch): same ABI as
+// p2b_test_fastmath over host memory
+extern "C" int emu_test_fastmath(int op, const double* a, const double* b, double* out, int n)
+{
+    for (int k = 0; k < n; ++k) {
+        if (op == 0) out[k] = pyro::rcp(a[k]);
+        else if (op == 1) out[k] = pyro::fdiv(a[k], b[k]);
+        else if (op == 2) out[k] = pyro::fsqrt(a[k]);
+        else {
+            const double* l = a + 4 * k; const double* r = b + 4 * k;
+            out[k] = pyro::hllc_lm(l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], pyro::hllc_par(1.4)).mn;
+        }
+    }
+    return 0;
+}

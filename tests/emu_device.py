@@ -54,6 +54,9 @@ class EmuLibrary:
             return self._counted(name, self._sweep)
         if name == "p2b_sweep_info":
             return self._sweep_info
+        if name == "p2b_test_fastmath":
+            lib = emu_util.load_sweep_emu()
+            return lambda op, a, b, out, n, stream: lib.emu_test_fastmath(op, a, b, out, n)
         if name == "p2b_last_error":
             return lambda: b"; ".join([lib.p2b_last_error() or b"" for lib in self._used] + [getattr(self, "_sweep_error", b"")])
         if name == "p2b_version":

@@ -94,6 +94,7 @@ def load_sweep_emu():
                                                C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
     lib.emu_sweep_decomposition.argtypes = [C.POINTER(_lib.Grid), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.emu_sweep_decomposition.restype = None
+    lib.emu_test_fastmath.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _LIBS["sweep"] = lib
     return lib
 

@@ -317,3 +317,23 @@ def test_emulated_sweep_spherical_polar_matches_oracle(emu, xbc, ybc, nx, ny, gr
         assert rel_l2(got[v_][..., n], ref[v_][..., n]) < 1e-10, n
     cart = oracle.compressible_step(U, ng, g.dx, g.dy, dt, oracle.comp_params(limiter=limiter, riemann="CGF"))
     assert rel_l2(ref[v_][..., 0], cart[v_][..., 0]) > 1e-4                 # the geometry matters
+
+
+# ---- the device's branch-free fp64 helpers as the emulator restates them ------------------------------------------------
+def _emu_probe(lib):
+    def probe(op, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        out = np.empty(len(a))
+        lib.emu_test_fastmath(op, a.ctypes.data, None if b is None else b.ctypes.data, out.ctypes.data, len(a))
+        return out
+    return probe
+
+
+def test_emulated_fastmath_helpers_have_the_device_special_cases(emu):
+    """round 1's HLLC_lm defect (fsqrt(0) = NaN on the device, sqrt(0) = 0 under the emulator) was invisible here: the
+    host build now runs the device's own Newton sequences on an emulated MUFU seed, special operands included.  The same
+    checks run against the device in tests/test_gpu_hydro.py."""
+    from test_gpu_hydro import check_fastmath, check_hllc_lm_at_rest
+    check_fastmath(_emu_probe(emu))
+    check_hllc_lm_at_rest(_emu_probe(emu))
