@@ -79,8 +79,9 @@ class Simulation(NullSimulation):
             raise NotImplementedError("passively advected extra variables are not in the device sweep")
         rp = self.rp
         my_grid = grid_setup(rp, ng=ng, decomposition=self.decomposition)
-        if ng < 4:
-            raise ValueError("the compressible sweep needs ng >= 4 (dependency radius, SURVEY.md 9.3)")
+        if ng < 4 or ng % 2:
+            raise ValueError("the compressible sweep needs an even ng >= 4 (dependency radius, SURVEY.md 9.3; 16-byte "
+                             "aligned row copies)")
         my_data = self.data_class(my_grid)
 
         riemann_method = rp.get_param("compressible.riemann")
@@ -218,7 +219,8 @@ class Simulation(NullSimulation):
 
     def check_state(self):
         """raise now if the last evolve() saw an invalid state (otherwise raised by the next dt)"""
-        self._read_scratch()
+        if getattr(self, "_pending_status", False):
+            self._read_scratch()
 
     def method_compute_timestep(self):
         """CFL timestep (simulation.py:267-288): cfl * min(dx/(|u|+cs), dy/(|v|+cs)), bit-identical.

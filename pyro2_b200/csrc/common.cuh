@@ -39,14 +39,15 @@ void set_error(const char* fmt, ...);
 
 inline int num_sms()
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[64] = {0};                 // per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] <= 0) sms[dev] = 148;
     }
-    return sms;
+    return sms[dev];
 }
 
 }  // namespace pyro

@@ -122,11 +122,15 @@ __global__ void fastmath_probe_kernel(int op, const double* a, const double* b, 
 
 static int g_last_ntasks = 0, g_last_resident = 0, g_last_seglen = 0;
 
+// function attributes and SM counts are per device: cached per device ordinal
 static int resident_warps()
 {
-    static int resident = 0;
-    if (!resident) {
-        int blocks = 0;
+    static int resident[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!resident[dev]) {
+        int blocks = 0, sms = 0;
         const int smem = (int)(SWEEP_WARPS * sizeof(SweepSmem));
         cudaFuncSetAttribute(sweep_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(sweep_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -139,9 +143,11 @@ static int resident_warps()
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sweep_kernel<false, 0>, SWEEP_THREADS,
                                                       SWEEP_WARPS * sizeof(SweepSmem));
         if (blocks < 1) blocks = 1;
-        resident = blocks * SWEEP_WARPS * num_sms();
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        resident[dev] = blocks * SWEEP_WARPS * sms;
     }
-    return resident;
+    return resident[dev];
 }
 
 }  // namespace pyro

@@ -43,6 +43,9 @@ inline const char* sweep_args_from_abi(const double* Uin, double* Uout, const p2
     if (!(Uin && Uout && g && prm && scratch)) return "null pointer";
     if (Uin == Uout) return "the sweep is out of place: Uin == Uout";
     if (g->ng < 4) return "compressible sweep needs ng >= 4";
+    // the bulk copies start at column ng + 30 * strip - 4 and need 16-byte aligned sources and byte counts
+    if ((g->ng % 2) != 0) return "compressible sweep needs an even ng (16-byte aligned row copies)";
+    if (((uintptr_t)Uout % 16) != 0) return "planes must be 16-byte aligned";
     if (g->nx < 1 || g->ny < 1) return "empty grid";
     if (g->pitch < g->ny + 2 * g->ng || (g->pitch % 2) != 0) return "pitch must be even and >= qy";
     if ((g->plane_stride % 2) != 0 || ((uintptr_t)Uin % 16) != 0) return "planes must be 16-byte aligned";

@@ -126,6 +126,7 @@ class NullSimulation:
         fix_dt = self.rp.get_param("driver.fix_dt")
         if fix_dt > 0.0:
             self.dt = fix_dt
+            self.check_state()     # the method's timestep code, which reads the device status word, is skipped
         else:
             self.method_compute_timestep()
             if self.n == 0:
@@ -135,6 +136,9 @@ class NullSimulation:
             self.dt_old = self.dt
         if self.cc_data.t + self.dt > self.tmax:
             self.dt = self.tmax - self.cc_data.t
+
+    def check_state(self):
+        """raise if the last evolve() left an invalid state (solvers whose kernels keep a device-side status word)"""
 
     def preevolve(self):
         pass
@@ -153,6 +157,12 @@ class NullSimulation:
     def write(self, filename):
         """HDF5 snapshot in the reference's layout (simulation_null.py:270-290); needs h5py"""
         import h5py   # pylint: disable=import-outside-toplevel
+        decomp = getattr(self, "decomposition", None)
+        if decomp is not None and decomp.size > 1:
+            # every rank holds one x-slab: writing it under the domain's name and extent would race between ranks
+            # and leave an inconsistent file.  No parallel writer exists; refuse instead of corrupting.
+            msg.fail("ERROR: snapshots of a decomposed run are not supported (gather the slabs and write from one process)")
+        self.check_state()
         if not filename.endswith(".h5"):
             filename += ".h5"
         with h5py.File(filename, "w") as f:

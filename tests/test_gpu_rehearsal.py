@@ -142,32 +142,3 @@ def test_bench_on_emulated_device(capfd, monkeypatch):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["roofline"]["bound"] == "hbm"
     assert dev.calls["p2b_compressible_sweep"] >= 2 + 3 and dev.calls["p2b_mg_vcycle"] >= 2
 
-
-def test_pyro_benchmark_store_and_compare(monkeypatch, tmp_path):
-    """PyroBenchmark (pyro_sim.py:324-408): store a run's final snapshot as the benchmark, compare a second run with
-    it (match), then a run with another CFL number (mismatch) -- on the emulated device, snapshots through the h5py
-    stand-in"""
-    import sys
-
-    import emu_device
-    import fake_h5py
-    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
-    inputs = {"mesh.nx": 16, "mesh.ny": 16, "driver.max_steps": 3, "driver.verbose": 0, "io.basename": "bench_test_",
-              "advection.limiter": 1}
-    with emu_device.emulated_device():
-        from pyro2_b200.pyro_sim import PyroBenchmark
-
-        def run(extra=None, **kw):
-            p = PyroBenchmark("advection", **kw)
-            p.pyro_home = str(tmp_path) + "/"
-            (tmp_path / "advection").mkdir(exist_ok=True)
-            p.initialize_problem("tophat", inputs_dict=dict(inputs, **(extra or {})))
-            return p.run_sim()
-        sim = run(make_bench=True)
-        assert sim.n == 3 and (tmp_path / "advection" / "tests" / "bench_test_0003.h5").exists()
-        assert run(comp_bench=True) == 0
-        assert run({"driver.cfl": 0.4}, comp_bench=True) == "varerr"
-        other = PyroBenchmark("advection", comp_bench=True)
-        other.pyro_home = str(tmp_path / "nowhere") + "/"
-        other.initialize_problem("tophat", inputs_dict=inputs)
-        assert other.run_sim() == "ERROR opening compare file"
