@@ -206,6 +206,28 @@ int p2b_mg_norm2(p2b_mg* m, int level, int which, double* out_dev, void* stream)
  * old_phi is a caller-owned (n+2) x pitch buffer */
 int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out_dev, void* stream);
 
+/* ---- decomposed hierarchies: peer-memory communication (no NCCL inside a V-cycle) --------------------------------
+ * The x-slabs of a hierarchy created with p2b_mg_create_slab talk through each other's workspaces: a kernel that
+ * produces rows a neighbour needs (smoother pass, restrict, prolong) stores them straight into the neighbour's halo rows
+ * and raises a flag there; the kernels that read halo rows wait on the flag (bounded spin; a time-out is reported
+ * through p2b_mg_result, never a hang).  All ranks call the same sequence of p2b_mg_* functions (SPMD).  The workspaces
+ * must be mapped into every rank's address space: same process -> plain pointers; several processes on one node ->
+ * p2b_shared_alloc / _handle / _open (cudaIpc).  This replaces the reference's fill_BC after every smoothing colour
+ * (pyro/multigrid/MG.py:565, 591-599) across slab boundaries by one message per five red-black iterations. */
+int p2b_mg_set_peers(p2b_mg* m, void* const* bases);      /* bases[r]: rank r's workspace as mapped here; [rank] = own */
+int p2b_mg_exchange(p2b_mg* m, int level, int which, int depth, void* stream);   /* stand-alone halo exchange (collective) */
+/* the stopping rule of solve() evaluated on the device (pyro/multigrid/MG.py:654-697): lets the host enqueue cycles
+ * ahead; once residual_error <= rtol or max_cycles cycles ran, the kernels of the cycles enqueued ahead return at once */
+int p2b_mg_set_stop(p2b_mg* m, int enable, double source_norm, double rtol, int max_cycles, void* stream);
+int p2b_mg_result(p2b_mg* m, double* out4, long long* comm_error, void* stream);   /* (relsq, rsq, residual_error, cycles); syncs */
+void* p2b_mg_control_ptr(p2b_mg* m);
+void* p2b_shared_alloc(long long bytes);                  /* cudaMalloc'd + zeroed; mappable by other processes */
+int p2b_shared_free(void* p);
+int p2b_shared_handle(void* p, unsigned char* out64);     /* 64 opaque bytes (cudaIpcMemHandle_t) */
+void* p2b_shared_open(const unsigned char* handle64);     /* maps another process's allocation, enables peer access */
+int p2b_shared_close(void* p);
+
+
 /* ---- the diffusion solver's use of the hierarchy (pyro/diffusion/simulation.py:62-104: Crank-Nicolson,
  * (1 - dt k/2 L) phi^{n+1} = phi^n + dt k/2 L phi^n).  p2b_mg_set_operator changes alpha / beta of an existing
  * hierarchy (the reference constructs a new CellCenterMG2d with beta = 0.5*dt*k every step);

@@ -147,6 +147,16 @@ SIGNATURES = {
     "p2b_mg_norm2": (_i, [_vp, _i, _i, _vp, _vp]),
     "p2b_mg_cycle_diagnostics": (_i, [_vp, _vp, _vp, _vp]),
     "p2b_mg_set_operator": (_i, [_vp, _d, _d]),
+    "p2b_mg_set_peers": (_i, [_vp, C.POINTER(_vp)]),
+    "p2b_mg_exchange": (_i, [_vp, _i, _i, _i, _vp]),
+    "p2b_mg_set_stop": (_i, [_vp, _i, _d, _d, _i, _vp]),
+    "p2b_mg_result": (_i, [_vp, C.POINTER(_d), C.POINTER(_ll), _vp]),
+    "p2b_mg_control_ptr": (_vp, [_vp]),
+    "p2b_shared_alloc": (_vp, [_ll]),
+    "p2b_shared_free": (_i, [_vp]),
+    "p2b_shared_handle": (_i, [_vp, C.c_char_p]),
+    "p2b_shared_open": (_vp, [C.c_char_p]),
+    "p2b_shared_close": (_i, [_vp]),
     "p2b_mg_cn_rhs": (_i, [_vp, _vp, _i, _d, _vp]),
     "p2b_mg_coeff_workspace_bytes": (_ll, [_vp]),
     "p2b_mg_set_coeffs": (_i, [_vp, _vp, _ll, _vp, _i, C.POINTER(_i), _vp]),

@@ -32,6 +32,15 @@ struct p2b_mg {
     int no_blocking;                          // debugging / A-B switch: 1 = plain half-sweep kernels
     int rank, size;                           // x-slab decomposition (size 1 = single GPU)
     int split_level;                          // levels >= split_level are slabs when size > 1
+    // peer-memory communication (mg_kernels.cuh): control words at the end of the workspace, the other ranks'
+    // workspaces, and the bookkeeping of the running program
+    unsigned long long* ctl;
+    double* peer_base[pyro::MG_MAX_RANKS];
+    int peers_set;
+    int ord;                                  // ordinal of the last pushing launch of the running program
+    int last_push[pyro::MG_MAX_LEVELS][4];    // ordinal of the launch that last filled the neighbours' halo rows of
+                                              // (level, plane) in the running program; -1: delivered before it began
+    double source_norm, rtol; int max_cycles, stop_enabled;   // the device-side stopping rule of solve()
     // variable-coefficient mode (VarCoeffCCMG2d): per level the cell-centred eta and the two edge planes
     int varcoef;
     double *cc[pyro::MG_MAX_LEVELS], *ex[pyro::MG_MAX_LEVELS], *ey[pyro::MG_MAX_LEVELS];
@@ -89,6 +98,72 @@ static VcEdges level_edges(const p2b_mg* m, int level)
     VcEdges E;
     E.ex = m->ex[level]; E.ey = m->ey[level];
     return E;
+}
+
+// ---- communication descriptors -----------------------------------------------------------------------------
+static MgComm comm_none()
+{
+    MgComm c;
+    memset(&c, 0, sizeof c);
+    c.ctl = nullptr; c.wait_ord = -1; c.sig_ord = -1; c.size = 1;
+    return c;
+}
+
+static MgComm comm_base(const p2b_mg* m)
+{
+    MgComm c = comm_none();
+    if (m->size <= 1) return c;
+    const bool xper = (m->bc[0] == P2B_BC_PERIODIC);
+    c.ctl = m->ctl; c.rank = m->rank; c.size = m->size;
+    c.has_lo = (m->rank > 0 || xper) ? 1 : 0;
+    c.has_hi = (m->rank < m->size - 1 || xper) ? 1 : 0;
+    const int lo = (m->rank + m->size - 1) % m->size, hi = (m->rank + 1) % m->size;
+    c.dlo = m->peer_base[lo] - m->base;
+    c.dhi = m->peer_base[hi] - m->base;
+    return c;
+}
+
+#ifdef P2B_EMU_HEADER
+#define P2B_EMU_THREADED(flag) ::emu::force_threaded = (flag)
+#else
+#define P2B_EMU_THREADED(flag) ((void)0)
+#endif
+
+static bool is_slab(const p2b_mg* m, int level) { return m->size > 1 && level >= m->split_level; }
+
+static void begin_program(p2b_mg* m, cudaStream_t st)
+{
+    if (m->size <= 1) return;
+    P2B_LAUNCH(mg_epoch_kernel, 1, 1, 0, st)(m->ctl);
+    m->ord = 0;
+    for (int l = 0; l < MG_MAX_LEVELS; ++l) for (int k = 0; k < 4; ++k) m->last_push[l][k] = -1;
+}
+
+// every program ends by waiting for the neighbours' (all ranks') last push of it: when the next program starts,
+// every halo row is in place and no flag of an older program is ever waited on
+static void end_program(p2b_mg* m, cudaStream_t st, bool gather = false)
+{
+    if (m->size <= 1 || m->ord == 0) return;
+    MgComm c = comm_base(m);
+    c.wait_ord = m->ord;
+    P2B_LAUNCH(mg_comm_wait_kernel, 1, 32, 0, st)(c, gather ? 1 : 0);
+}
+
+// stand-alone exchange of `depth` halo rows of one plane of a slab level (a program of its own, safe at any point:
+// it first agrees with the neighbours that earlier work on both sides has finished)
+static void exchange_impl(p2b_mg* m, int level, double* plane, int depth, cudaStream_t st)
+{
+    if (!is_slab(m, level)) return;
+    const MgLevel& L = m->lev[level];
+    MgComm c = comm_base(m);
+    P2B_EMU_THREADED(true);
+    P2B_LAUNCH(mg_xchg_arrive_kernel, 1, 1, 0, st)(c);
+    dim3 grd((L.pitch + 255) / 256, depth);
+    c.sig_ord = 1; c.n_lo = c.n_hi = (int)(grd.x * grd.y);
+    P2B_LAUNCH(mg_xchg_push_kernel, grd, 256, 0, st)(plane, L.ni, L.pitch, depth, c);
+    c.sig_ord = -1; c.wait_ord = 1;
+    P2B_LAUNCH(mg_comm_wait_kernel, 1, 32, 0, st)(c, 0);
+    P2B_EMU_THREADED(false);
 }
 
 constexpr int MG_SMALL_N = 64;   // levels up to 64^2 are smoothed by one CTA in one launch
@@ -152,7 +227,7 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
         if (left == 0 && fill_first) P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, st)(L, b);
         while (left > 0) {
             int it = left < TB_K ? left : TB_K;
-            P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, src, dst, b, c, it);
+            P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, src, dst, b, c, it, comm_none());
             left -= it;
             const double* t = src; src = dst; dst = const_cast<double*>(t);
         }
@@ -174,13 +249,50 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
 // a non-zero offset into the coarse array only when the coarse level is replicated (ioff = 0 there)
 static int coarse_row_offset(const MgLevel& F, const MgLevel& Cs) { return F.ioff / 2 - Cs.ioff; }
 
-static bool is_slab(const p2b_mg* m, int level) { return m->size > 1 && level >= m->split_level; }
+static int imax(int a, int b) { return a > b ? a : b; }
 
-static void tb_pass_impl(p2b_mg* m, int level, const double* src, double* dst, int niter, cudaStream_t st)
+// one blocked pass on a level.  On a slab level the launch waits (edge tiles only) for the halo rows of its source
+// plane and of f, and pushes the first / last TB_H rows of its result into the neighbours' halo rows.
+static void tb_pass_impl(p2b_mg* m, int level, int src, int dst, int niter, cudaStream_t st)
 {
     const MgLevel& L = m->lev[level];
     dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.ni + TB_TI - 1) / TB_TI);
-    P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, src, dst, level_bc(m, level), level_coef(m, L), niter);
+    MgComm c = comm_none();
+    if (is_slab(m, level)) {
+        c = comm_base(m);
+        c.wait_ord = imax(m->last_push[level][src], m->last_push[level][1]);
+        c.sig_ord = ++m->ord;
+        c.n_lo = (int)grd.x;                                                       // tile row 0 holds rows 1..TB_H
+        c.n_hi = (int)grd.x * ((L.ni - 1) / TB_TI - (L.ni - TB_H) / TB_TI + 1);     // tile rows meeting ni-TB_H+1..ni
+        m->last_push[level][dst] = c.sig_ord;
+    }
+    const double* sp = src == 0 ? L.v : L.w;
+    double* dp = dst == 0 ? L.v : L.w;
+    P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, sp, dp, level_bc(m, level), level_coef(m, L), niter, c);
+}
+
+// nsmooth red-black iterations on a slab level: passes of <= TB_K iterations, halo rows travelling in the passes' own
+// epilogues (communication-avoiding: one message per 5 iterations instead of one per colour)
+static void smooth_slab_impl(p2b_mg* m, int level, int nsmooth, cudaStream_t st)
+{
+    const MgLevel& L = m->lev[level];
+    int src = 0, dst = 3;
+    for (int left = nsmooth; left > 0;) {
+        const int it = left < TB_K ? left : TB_K;
+        tb_pass_impl(m, level, src, dst, it, st);
+        left -= it;
+        const int t = src; src = dst; dst = t;
+    }
+    if (src != 0) {
+        // odd number of passes: the result sits in w.  Its halo rows are in flight: wait, then copy the whole plane.
+        MgComm c = comm_base(m);
+        c.wait_ord = m->last_push[level][3];
+        P2B_LAUNCH(mg_comm_wait_kernel, 1, 32, 0, st)(c, 0);
+        const long long rows = L.ni + 2 * L.gx;
+        cudaMemcpyAsync(L.v - (long long)(L.gx - 1) * L.pitch, L.w - (long long)(L.gx - 1) * L.pitch,
+                        (size_t)rows * L.pitch * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        m->last_push[level][0] = -1;
+    }
 }
 
 static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
@@ -192,23 +304,56 @@ static void residual_impl(p2b_mg* m, int level, cudaStream_t st)
         P2B_LAUNCH(mg_vc_residual_kernel, grd, blk, 0, st)(L, level_edges(m, level));
         return;
     }
-    P2B_LAUNCH(mg_residual_kernel, grd, blk, 0, st)(L, level_rcoef(m, L));
+    MgComm c = comm_none();
+    if (is_slab(m, level)) { c = comm_base(m); c.wait_ord = m->last_push[level][0]; }
+    P2B_LAUNCH(mg_residual_kernel, grd, blk, 0, st)(L, level_rcoef(m, L), c);
 }
 
 static void restrict_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
     dim3 blk(64, 4);
-    dim3 grd((Cs.n + blk.x - 1) / blk.x, (F.ni / 2 + blk.y - 1) / blk.y);
-    P2B_LAUNCH(mg_restrict_kernel, grd, blk, 0, st)(F, Cs, coarse_row_offset(F, Cs));
+    const int nic = F.ni / 2;
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (nic + blk.y - 1) / blk.y);
+    MgComm c = comm_none();
+    int to_all = 0;
+    if (is_slab(m, level)) {
+        c = comm_base(m);
+        c.sig_ord = ++m->ord;
+        to_all = is_slab(m, level - 1) ? 0 : 1;
+        if (!to_all) {
+            c.n_lo = (int)grd.x * count_rows_meet((int)grd.y, (int)blk.y, 1, Cs.gx);
+            c.n_hi = (int)grd.x * count_rows_meet((int)grd.y, (int)blk.y, nic - Cs.gx + 1, nic);
+            m->last_push[level - 1][1] = c.sig_ord;
+        }
+    }
+    P2B_LAUNCH(mg_restrict_kernel, grd, blk, 0, st)(F, Cs, coarse_row_offset(F, Cs), c, to_all);
+    if (to_all) {
+        // slab -> replicated: wait until every rank's rows of the coarse right-hand side have landed here
+        c.sig_ord = -1; c.wait_ord = m->ord;
+        P2B_LAUNCH(mg_comm_wait_kernel, 1, 32, 0, st)(c, 1);
+    }
 }
 
 static void prolong_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     const MgLevel &F = m->lev[level], &Cs = m->lev[level - 1];
     dim3 blk(64, 4);
-    dim3 grd((Cs.n + blk.x - 1) / blk.x, (F.ni / 2 + blk.y - 1) / blk.y);
-    P2B_LAUNCH(mg_prolong_kernel, grd, blk, 0, st)(F, Cs, level_bc(m, level), coarse_row_offset(F, Cs));
+    const int nic = F.ni / 2;
+    dim3 grd((Cs.n + blk.x - 1) / blk.x, (nic + blk.y - 1) / blk.y);
+    MgComm c = comm_none();
+    int coarse_slab = 0;
+    if (is_slab(m, level)) {
+        c = comm_base(m);
+        coarse_slab = is_slab(m, level - 1) ? 1 : 0;
+        c.wait_ord = coarse_slab ? m->last_push[level - 1][0] : -1;
+        c.sig_ord = ++m->ord;
+        const int hp = F.gx / 2;
+        c.n_lo = (int)grd.x * count_rows_meet((int)grd.y, (int)blk.y, 1, hp);
+        c.n_hi = (int)grd.x * count_rows_meet((int)grd.y, (int)blk.y, nic - hp + 1, nic);
+        m->last_push[level][0] = c.sig_ord;
+    }
+    P2B_LAUNCH(mg_prolong_kernel, grd, blk, 0, st)(F, Cs, level_bc(m, level), coarse_row_offset(F, Cs), c, coarse_slab);
 }
 
 static int coarse_top(const p2b_mg* m)
@@ -252,6 +397,16 @@ static void coarse_vcycle_impl(p2b_mg* m, int top, cudaStream_t st)
 static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
 {
     // MG.py:699-778
+    if (is_slab(m, level)) {
+        // x-slab level: same operations, halo rows pushed by the producers (see mg_kernels.cuh)
+        smooth_slab_impl(m, level, m->nsmooth, st);
+        residual_impl(m, level, st);
+        restrict_impl(m, level, st);
+        vcycle_impl(m, level - 1, st);
+        prolong_impl(m, level, st);
+        smooth_slab_impl(m, level, m->nsmooth, st);
+        return;
+    }
     if (!m->no_blocking && level <= coarse_top(m)) {
         coarse_vcycle_impl(m, level, st);
         return;
@@ -273,7 +428,8 @@ static int sumsq_impl(p2b_mg* m, const double* a, int level, double* out, cudaSt
     const MgLevel& L = m->lev[level];
     int blocks = L.ni < MG_NPART ? L.ni : MG_NPART;
     P2B_LAUNCH(mg_sumsq_partial_kernel, blocks, RED_THREADS, 0, st)(a, L.ni, L.n, L.pitch, m->partials);
-    P2B_LAUNCH(mg_sumsq_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out);
+    // a slab level's sum runs over all ranks (a program of its own: the kernel starts it)
+    P2B_LAUNCH(mg_sumsq_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out, is_slab(m, level) ? comm_base(m) : comm_none());
     return P2B_OK;
 }
 
@@ -289,7 +445,10 @@ static p2b_mg* mg_create_impl(int nx, const int* bc, double alpha, double beta, 
 {
     if (nx < 2 || (nx & (nx - 1)) != 0) { set_error("multigrid requires nx = ny = power of two (got %d)", nx); return nullptr; }
     if (!bc) { set_error("null bc"); return nullptr; }
-    if (size < 1 || (size & (size - 1)) != 0 || rank < 0 || rank >= size) { set_error("slab count must be a power of two"); return nullptr; }
+    if (size < 1 || (size & (size - 1)) != 0 || rank < 0 || rank >= size || size > MG_MAX_RANKS) {
+        set_error("slab count must be a power of two <= %d", MG_MAX_RANKS);
+        return nullptr;
+    }
     p2b_mg* m = new p2b_mg();
     memset(m, 0, sizeof *m);
     int nl = 0;
@@ -337,6 +496,7 @@ static p2b_mg* mg_create_impl(int nx, const int* bc, double alpha, double beta, 
         L.w = (double*)(off + row0); off += plane;
     }
     m->partials = (double*)off; off += 2 * MG_NPART;
+    m->ctl = (unsigned long long*)off; off += CW_WORDS;       // control words (communication, stopping rule)
     m->bytes = off * 8;
     return m;
 }
@@ -389,6 +549,26 @@ int p2b_mg_bind(p2b_mg* m, void* mem, long long bytes)
         m->lev[l].w = m->base + (long long)m->lev[l].w;
     }
     m->partials = m->base + (long long)m->partials;
+    m->ctl = reinterpret_cast<unsigned long long*>(m->base + (long long)m->ctl);
+    for (int l = 0; l < m->nlevels; ++l) m->lev[l].ctl = m->ctl;
+    m->peer_base[m->rank] = m->base;
+    return P2B_OK;
+}
+
+// decomposed hierarchy: bases[r] = rank r's workspace as mapped into THIS process (bases[rank] = the pointer given to
+// p2b_mg_bind); see p2b_shared_* for the mapping across processes.  Needed before any operation on a slab level.
+int p2b_mg_set_peers(p2b_mg* m, void* const* bases)
+{
+    P2B_REQUIRE(m && m->base && bases, "hierarchy not bound");
+    P2B_REQUIRE(bases[m->rank] == (void*)m->base, "bases[rank] must be this rank's own workspace");
+    unsigned long long off[MG_MAX_RANKS] = {0};
+    for (int r = 0; r < m->size; ++r) {
+        P2B_REQUIRE(bases[r] && ((uintptr_t)bases[r] % 16) == 0, "bad peer workspace");
+        m->peer_base[r] = (double*)bases[r];
+        off[r] = (unsigned long long)(m->peer_base[r] - m->base);
+    }
+    P2B_CUDA_CHECK(cudaMemcpy(m->ctl + CW_PEER, off, sizeof off, cudaMemcpyHostToDevice));
+    m->peers_set = 1;
     return P2B_OK;
 }
 
@@ -410,12 +590,26 @@ int p2b_mg_set_bc_values(p2b_mg* m, const double* xl, const double* xr, const do
 
 #define MG_CHECK_LEVEL(m, level) \
     P2B_REQUIRE((m) && (m)->base, "hierarchy not bound"); \
-    P2B_REQUIRE((level) >= 0 && (level) < (m)->nlevels, "bad level")
+    P2B_REQUIRE((level) >= 0 && (level) < (m)->nlevels, "bad level"); \
+    P2B_REQUIRE(!is_slab(m, level) || (m)->peers_set, "decomposed hierarchy: call p2b_mg_set_peers first")
 
 int p2b_mg_smooth(p2b_mg* m, int level, int nsmooth, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
-    P2B_REQUIRE(!is_slab(m, level), "smooth() on a slab level needs halo exchanges: drive it with p2b_mg_tb_pass");
+    if (is_slab(m, level)) {
+        // a stand-alone smooth(): bring the halo rows of v up to date (the caller may have changed v), then the
+        // passes as one program
+        cudaStream_t st = (cudaStream_t)stream;
+        P2B_REQUIRE(!m->varcoef && m->lev[level].n >= MG_TB_MIN_N, "slab levels use the blocked constant-coefficient smoother");
+        exchange_impl(m, level, m->lev[level].v, TB_H, st);
+        P2B_EMU_THREADED(true);
+        begin_program(m, st);
+        smooth_slab_impl(m, level, nsmooth, st);
+        end_program(m, st);
+        P2B_EMU_THREADED(false);
+        P2B_CUDA_CHECK(cudaGetLastError());
+        return P2B_OK;
+    }
     smooth_impl(m, level, nsmooth, true, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -424,6 +618,8 @@ int p2b_mg_smooth(p2b_mg* m, int level, int nsmooth, void* stream)
 int p2b_mg_residual(p2b_mg* m, int level, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
+    if (is_slab(m, level)) exchange_impl(m, level, m->lev[level].v, 1, (cudaStream_t)stream);   // rows 0 and ni + 1
+    if (is_slab(m, level)) for (int k = 0; k < 4; ++k) m->last_push[level][k] = -1;
     residual_impl(m, level, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -433,7 +629,11 @@ int p2b_mg_restrict(p2b_mg* m, int level, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
     P2B_REQUIRE(level >= 1, "no coarser level");
+    P2B_EMU_THREADED(is_slab(m, level));
+    if (is_slab(m, level)) begin_program(m, (cudaStream_t)stream);
     restrict_impl(m, level, (cudaStream_t)stream);
+    if (is_slab(m, level) && is_slab(m, level - 1)) end_program(m, (cudaStream_t)stream);
+    P2B_EMU_THREADED(false);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
@@ -442,6 +642,17 @@ int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
     P2B_REQUIRE(level >= 1, "no coarser level");
+    if (is_slab(m, level)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (is_slab(m, level - 1)) exchange_impl(m, level - 1, m->lev[level - 1].v, 1, st);   // coarse rows 0, nic + 1
+        P2B_EMU_THREADED(true);
+        begin_program(m, st);
+        prolong_impl(m, level, st);
+        end_program(m, st);
+        P2B_EMU_THREADED(false);
+        P2B_CUDA_CHECK(cudaGetLastError());
+        return P2B_OK;
+    }
     prolong_impl(m, level, (cudaStream_t)stream);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -450,7 +661,12 @@ int p2b_mg_prolong_correct(p2b_mg* m, int level, void* stream)
 int p2b_mg_fill_bc(p2b_mg* m, int level, void* stream)
 {
     MG_CHECK_LEVEL(m, level);
-    P2B_REQUIRE(!is_slab(m, level), "fill_bc on a slab level: exchange the halo rows instead");
+    if (is_slab(m, level)) {
+        // the slab's x "ghost" rows are the neighbours' rows; its physical sides were kept by the writers
+        exchange_impl(m, level, m->lev[level].v, 1, (cudaStream_t)stream);
+        P2B_CUDA_CHECK(cudaGetLastError());
+        return P2B_OK;
+    }
     const MgLevel& L = m->lev[level];
     P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, (cudaStream_t)stream)(L, level_bc(m, level));
     P2B_CUDA_CHECK(cudaGetLastError());
@@ -463,6 +679,7 @@ int p2b_mg_zero_coarse(p2b_mg* m, void* stream)
     P2B_REQUIRE(m && m->base, "hierarchy not bound");
     if (m->nlevels < 2) return P2B_OK;
     MgZeroTable t;
+    t.ctl = m->ctl;
     t.nlev = m->nlevels - 1;
     long long most = 0;
     for (int l = 0; l < t.nlev; ++l) {
@@ -487,8 +704,17 @@ int p2b_mg_tb_pass(p2b_mg* m, int level, int src, int dst, int niter, void* stre
     P2B_REQUIRE(niter >= 1 && niter <= TB_K, "niter out of range");
     P2B_REQUIRE(m->lev[level].n >= MG_TB_MIN_N, "level too small for the blocked smoother");
     P2B_REQUIRE(!m->varcoef, "the blocked smoother is constant-coefficient only");
-    const MgLevel& L = m->lev[level];
-    tb_pass_impl(m, level, src == 0 ? L.v : L.w, dst == 0 ? L.v : L.w, niter, (cudaStream_t)stream);
+    if (is_slab(m, level)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        exchange_impl(m, level, src == 0 ? m->lev[level].v : m->lev[level].w, TB_H, st);
+        P2B_EMU_THREADED(true);
+        begin_program(m, st);
+        tb_pass_impl(m, level, src, dst, niter, st);
+        end_program(m, st);
+        P2B_EMU_THREADED(false);
+    } else {
+        tb_pass_impl(m, level, src, dst, niter, (cudaStream_t)stream);
+    }
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
@@ -510,8 +736,14 @@ int p2b_mg_vcycle_level(p2b_mg* m, int level, void* stream)
 int p2b_mg_vcycle(p2b_mg* m, void* stream)
 {
     P2B_REQUIRE(m && m->base, "hierarchy not bound");
-    P2B_REQUIRE(m->size == 1, "decomposed hierarchy: the V-cycle is driven level by level (halo exchanges)");
+    P2B_REQUIRE(m->size == 1 || m->peers_set, "decomposed hierarchy: call p2b_mg_set_peers first");
+    // decomposed: one program -- every halo row travels in a producer's epilogue, nothing but kernels is enqueued
+    // (capturable as a CUDA graph); the halo rows of the finest v and f must be current on entry (p2b_mg_exchange)
+    P2B_EMU_THREADED(m->size > 1);
+    begin_program(m, (cudaStream_t)stream);
     vcycle_impl(m, m->nlevels - 1, (cudaStream_t)stream);
+    end_program(m, (cudaStream_t)stream);
+    P2B_EMU_THREADED(false);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
@@ -542,10 +774,92 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stre
         P2B_LAUNCH(mg_vc_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, level_edges(m, lf), old_phi, m->partials);
     else
         P2B_LAUNCH(mg_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, old_phi, level_rcoef(m, L), m->partials);
-    P2B_LAUNCH(mg_diag_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out);
+    MgStop stop;
+    stop.scale = L.dx * L.dy; stop.source_norm = m->source_norm; stop.rtol = m->rtol;
+    stop.max_cycles = m->max_cycles; stop.enabled = m->stop_enabled;
+    P2B_LAUNCH(mg_diag_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out, is_slab(m, lf) ? comm_base(m) : comm_none(),
+                                                             m->ctl, stop);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
+
+// stand-alone halo exchange of `depth` rows of plane `which` (0 v, 1 f, 2 r, 3 w) of a slab level with the neighbouring
+// ranks, through peer memory (no-op on a replicated level).  Collective: every rank calls it at the same point.
+int p2b_mg_exchange(p2b_mg* m, int level, int which, int depth, void* stream)
+{
+    MG_CHECK_LEVEL(m, level);
+    P2B_REQUIRE(which >= 0 && which <= 3, "bad plane");
+    const MgLevel& L = m->lev[level];
+    P2B_REQUIRE(depth >= 1 && depth <= L.gx && depth <= L.ni, "bad depth");
+    double* plane = which == 0 ? L.v : which == 1 ? L.f : which == 2 ? L.r : L.w;
+    exchange_impl(m, level, plane, depth, (cudaStream_t)stream);
+    P2B_CUDA_CHECK(cudaGetLastError());
+    return P2B_OK;
+}
+
+// the stopping rule of solve() on the device (MG.py:654-697).  enable = 1: each p2b_mg_cycle_diagnostics also evaluates
+// residual_error = sqrt(dx dy sum r^2) / source_norm, counts the cycle and, when residual_error <= rtol or max_cycles
+// cycles have run, raises the stop word that turns every kernel of cycles enqueued ahead into a no-op.  Calling it
+// (enable 0 or 1) clears the stop word and the cycle count.  p2b_mg_result copies (relsq, rsq, residual_error, cycles)
+// of the last counted cycle to the host (synchronises the stream) together with the communication error word.
+int p2b_mg_set_stop(p2b_mg* m, int enable, double source_norm, double rtol, int max_cycles, void* stream)
+{
+    P2B_REQUIRE(m && m->base, "hierarchy not bound");
+    m->stop_enabled = enable; m->source_norm = source_norm; m->rtol = rtol; m->max_cycles = max_cycles;
+    P2B_CUDA_CHECK(cudaMemsetAsync(m->ctl + CW_STOP, 0, 8, (cudaStream_t)stream));
+    P2B_CUDA_CHECK(cudaMemsetAsync(m->ctl + CW_RESULT, 0, 4 * 8, (cudaStream_t)stream));
+    return P2B_OK;
+}
+
+int p2b_mg_result(p2b_mg* m, double* out4, long long* comm_error, void* stream)
+{
+    P2B_REQUIRE(m && m->base && out4, "null pointer");
+    unsigned long long words[CW_WORDS];
+    P2B_CUDA_CHECK(cudaMemcpyAsync(words, m->ctl, sizeof words, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    P2B_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(out4, words + CW_RESULT, 4 * sizeof(double));
+    if (comm_error) *comm_error = (long long)words[CW_ERR];
+    return P2B_OK;
+}
+
+// device address of the control words (diagnostics; CW_* in mg_kernels.cuh)
+void* p2b_mg_control_ptr(p2b_mg* m) { return m ? (void*)m->ctl : nullptr; }
+
+// ---- device memory that other processes can map (the workspaces of a decomposed hierarchy) ---------------------
+// p2b_shared_alloc: cudaMalloc'd, zeroed.  p2b_shared_handle: 64 opaque bytes (cudaIpcMemHandle_t) another process on
+// the same node passes to p2b_shared_open to map the allocation (peer access is enabled by the open).
+void* p2b_shared_alloc(long long bytes)
+{
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed", bytes); return nullptr; }
+    cudaMemset(p, 0, (size_t)bytes);
+    cudaDeviceSynchronize();
+    return p;
+}
+
+int p2b_shared_free(void* p) { P2B_CUDA_CHECK(cudaFree(p)); return P2B_OK; }
+
+int p2b_shared_handle(void* p, unsigned char* out64)
+{
+    P2B_REQUIRE(p && out64, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    P2B_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+    memcpy(out64, &h, 64);
+    return P2B_OK;
+}
+
+void* p2b_shared_open(const unsigned char* handle64)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+int p2b_shared_close(void* p) { P2B_CUDA_CHECK(cudaIpcCloseMemHandle(p)); return P2B_OK; }
 
 // ---- variable coefficients: VarCoeffCCMG2d.__init__ (variable_coeff_MG.py:40-109) --------------------
 // three planes (eta at cell centres, eta_x, eta_y) per level, each the size of one of the level's planes
@@ -599,7 +913,7 @@ int p2b_mg_set_coeffs(p2b_mg* m, void* mem, long long bytes, const double* coeff
             Cs.f = m->cc[l];
             dim3 blk(64, 4);
             dim3 grd((n + blk.x - 1) / blk.x, (n + blk.y - 1) / blk.y);
-            P2B_LAUNCH(mg_restrict_kernel, grd, blk, 0, st)(F, Cs, 0);
+            P2B_LAUNCH(mg_restrict_kernel, grd, blk, 0, st)(F, Cs, 0, comm_none(), 0);
         }
         P2B_LAUNCH(mg_fill_kernel, (4 * n + 255) / 256, 256, 0, st)(L, cb);
         dim3 blk(64, 4);

@@ -32,6 +32,7 @@ struct MgLevel {
     // ni = n, ioff = 0, gx = 1, both x sides physical.
     int ni, ioff, gx;
     int xlo_phys, xhi_phys;
+    const unsigned long long* ctl;   // control words of the hierarchy (CW_STOP makes every kernel a no-op) or NULL
 };
 
 struct MgBC {
@@ -41,6 +42,167 @@ struct MgBC {
 
 constexpr int MG_MAX_LEVELS = 24;
 constexpr int MG_NPART = 16384;               // partial sums of the deterministic norms (one per row)
+
+// ---- peer-memory communication between the x-slabs of a decomposed hierarchy ---------------------------------
+// Every rank's workspace (planes + a small control area) has the SAME layout and is mapped into every other rank's
+// address space (cudaIpc; plain pointers when the ranks share a process), so "the same location on rank r" is a
+// constant element offset from a local pointer.  Halo rows are written straight into the neighbour's planes by the
+// kernel that produces them (the smoother's epilogue, restrict, prolong): the transfer needs no extra launch and
+// overlaps with the producer's interior tiles; there is no NCCL call and no host involvement inside a V-cycle, so
+// the whole cycle is capturable as one CUDA graph per rank.
+//
+// Ordering: one monotone 64-bit word per direction.  All ranks run the same sequence of "programs" (a V-cycle, a
+// diagnostics all-reduce, a stand-alone exchange); a program starts by incrementing the rank's epoch, and each
+// pushing launch of a program has a host-assigned ordinal, so value = epoch * MG_ORD_STRIDE + ordinal grows along
+// every rank's stream.  A producer's last edge CTA (counted with a local atomic after a system-scope fence) stores
+// that value into the neighbour's FROM_LO / FROM_HI word; a consumer's CTAs that read halo rows spin (thread 0,
+// acquire loads, bounded by a time-out that raises the error word instead of hanging) until the word has reached the
+// value of the launch that filled those rows.  Kernels run in stream order on every rank, so "flag >= value of
+// launch k" means every push of launches <= k has landed.  Why no write can overtake a reader is argued launch by
+// launch in DESIGN.md (multi-GPU section): in short, a rank only writes a halo after it has waited on a signal the
+// neighbour issued after its last reader of that halo.
+constexpr int MG_MAX_RANKS = 16;
+constexpr unsigned long long MG_ORD_STRIDE = 1024;
+enum {
+    CW_EPOCH = 0,        // programs started on this rank
+    CW_ERR = 1,          // non-zero: a wait timed out (1 + the word waited on)
+    CW_STOP = 2,         // non-zero: solve() has converged; the kernels of a speculatively enqueued cycle return at once
+    CW_FROM_LO = 3,      // written by the lo neighbour: value of its last completed push towards me
+    CW_FROM_HI = 4,      // ... by the hi neighbour
+    CW_CNT_LO = 5, CW_CNT_HI = 6, CW_CNT_ALL = 7,    // local counters of pushing CTAs (reset by the last one)
+    CW_GFLAG = 8,        // [MG_MAX_RANKS] written by rank r: value of its last completed push to ALL ranks
+    CW_PEER = 24,        // [MG_MAX_RANKS] element offsets from my workspace to rank r's (host-written)
+    CW_SUMS = 40,        // doubles [2][MG_MAX_RANKS][4]: all-reduce slots, double-buffered by epoch parity
+    CW_RESULT = 168,     // doubles [4]: the last diagnostics (relsq, rsq, residual_error, cycles run)
+    CW_WORDS = 176
+};
+
+struct MgComm {
+    unsigned long long* ctl;     // this rank's control words; NULL on a single GPU (no communication code runs)
+    long long dlo, dhi;          // element offsets to the lo / hi neighbour's workspace
+    int has_lo, has_hi;
+    int rank, size;
+    // per launch
+    int wait_ord;                // >= 0: CTAs that read halo rows wait for the neighbour's word >= epoch * STRIDE + wait_ord
+    int sig_ord;                 // >= 0: this launch pushes halo rows; value it signals
+    int n_lo, n_hi;              // CTAs that push towards the lo / hi neighbour (the last to finish signals)
+};
+
+}  // namespace pyro
+
+namespace pyro {
+
+#ifndef MG_COMM_TIMEOUT_NS
+#define MG_COMM_TIMEOUT_NS 4000000000LL
+#endif
+
+#ifdef P2B_EMU_HEADER
+__device__ __forceinline__ unsigned long long comm_load(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void comm_store(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ long long comm_clock_ns() { return emu_clock_ns(); }
+__device__ __forceinline__ void comm_pause() { emu_pause(); }
+__device__ __forceinline__ int comm_tid() { return emu::lin_tid; }
+#else
+__device__ __forceinline__ unsigned long long comm_load(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void comm_store(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long comm_clock_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void comm_pause() { __nanosleep(20); }
+__device__ __forceinline__ int comm_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+#endif
+
+// one thread: spin until ctl[word] >= target; a time-out raises the error word and gives up (never a hang)
+__device__ __forceinline__ void comm_wait_ge(unsigned long long* ctl, int word, unsigned long long target)
+{
+    if (comm_load(ctl + word) >= target) return;
+    const long long t0 = comm_clock_ns();
+    while (comm_load(ctl + word) < target) {
+        comm_pause();
+        if (comm_clock_ns() - t0 > MG_COMM_TIMEOUT_NS) { atomicExch(ctl + CW_ERR, 1ull + (unsigned long long)word); break; }
+    }
+}
+
+__device__ __forceinline__ unsigned long long comm_value(const MgComm& c, int ord)
+{
+    return c.ctl[CW_EPOCH] * MG_ORD_STRIDE + (unsigned long long)ord;
+}
+
+// all threads of a CTA call this (block-uniform arguments): wait for the halo rows this CTA is about to read
+__device__ __forceinline__ void comm_block_wait(const MgComm& c, bool need_lo, bool need_hi)
+{
+    if (!c.ctl || c.wait_ord < 0) return;
+    need_lo = need_lo && c.has_lo; need_hi = need_hi && c.has_hi;
+    if (!(need_lo || need_hi)) return;
+    if (comm_tid() == 0) {
+        const unsigned long long target = comm_value(c, c.wait_ord);
+        if (need_lo) comm_wait_ge(c.ctl, CW_FROM_LO, target);
+        if (need_hi) comm_wait_ge(c.ctl, CW_FROM_HI, target);
+    }
+    __syncthreads();
+}
+
+// all threads of a CTA call this after their pushes (block-uniform arguments): the last pushing CTA of each side
+// tells the neighbour
+__device__ __forceinline__ void comm_block_signal(const MgComm& c, bool lo_edge, bool hi_edge)
+{
+    if (!c.ctl || c.sig_ord < 0) return;
+    lo_edge = lo_edge && c.has_lo; hi_edge = hi_edge && c.has_hi;
+    if (!(lo_edge || hi_edge)) return;
+    __syncthreads();
+    if (comm_tid() == 0) {
+        __threadfence_system();
+        const unsigned long long val = comm_value(c, c.sig_ord);
+        if (lo_edge && atomicAdd(c.ctl + CW_CNT_LO, 1ull) == (unsigned long long)(c.n_lo - 1)) {
+            atomicExch(c.ctl + CW_CNT_LO, 0ull);
+            __threadfence_system();
+            comm_store(c.ctl + c.dlo + CW_FROM_HI, val);       // I am my lo neighbour's hi neighbour
+        }
+        if (hi_edge && atomicAdd(c.ctl + CW_CNT_HI, 1ull) == (unsigned long long)(c.n_hi - 1)) {
+            atomicExch(c.ctl + CW_CNT_HI, 0ull);
+            __threadfence_system();
+            comm_store(c.ctl + c.dhi + CW_FROM_LO, val);
+        }
+    }
+}
+
+// the same for a launch whose every CTA pushes to EVERY rank (slab -> replicated transfer): the last CTA signals all
+__device__ __forceinline__ void comm_block_signal_all(const MgComm& c, int nblocks)
+{
+    if (!c.ctl || c.sig_ord < 0) return;
+    __syncthreads();
+    if (comm_tid() == 0) {
+        __threadfence_system();
+        if (atomicAdd(c.ctl + CW_CNT_ALL, 1ull) == (unsigned long long)(nblocks - 1)) {
+            atomicExch(c.ctl + CW_CNT_ALL, 0ull);
+            __threadfence_system();
+            const unsigned long long val = comm_value(c, c.sig_ord);
+            for (int r = 0; r < c.size; ++r)
+                comm_store(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
+        }
+    }
+}
+
+// number of blocks by in [0, nby) whose rows [by * bh + 1, by * bh + bh] meet [a, b]  (host and device agree on
+// which CTAs push: the producer counts arrivals against this number)
+__host__ __device__ inline bool rows_meet(int by, int bh, int a, int b) { return by * bh + 1 <= b && by * bh + bh >= a; }
+inline int count_rows_meet(int nby, int bh, int a, int b)
+{
+    int k = 0;
+    for (int by = 0; by < nby; ++by) k += rows_meet(by, bh, a, b) ? 1 : 0;
+    return k;
+}
 
 }  // namespace pyro
 
@@ -146,6 +308,7 @@ __device__ __forceinline__ double gs_update(const double* v, const double* f, in
 // one colour of one red-black iteration; colour 0 = (i+j) even = the reference's groups (0,0),(1,1)
 __global__ void mg_halfsweep_kernel(MgLevel L, MgBC b, SmoothCoef c, int colour)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int half = L.n >> 1;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -158,6 +321,7 @@ __global__ void mg_halfsweep_kernel(MgLevel L, MgBC b, SmoothCoef c, int colour)
 // whole smooth() for a small level in one CTA (global memory, __syncthreads between colours)
 __global__ void mg_smooth_small_kernel(MgLevel L, MgBC b, SmoothCoef c, int nsmooth)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int half = L.n >> 1;
     const int npts = L.n * half;
     for (int it = 0; it < 2 * nsmooth; ++it) {
@@ -248,10 +412,9 @@ constexpr int TB_TJ = TB_RW - 2 * TB_H; // tile columns (44)
 static_assert(TB_TI % 2 == 0 && TB_TJ % 2 == 0 && TB_R % 2 == 0, "parity bookkeeping needs even tile sizes");
 static_assert(TB_RW == 64 && TB_NW % 2 == 0, "the coefficient-tile copy maps thread t to column t & 63");
 
-__device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [1, n]
-{
-    int k = (i - 1) % n;
-    return (k < 0 ? k + n : k) + 1;
+__device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [1, n]; n is a power of two (levels
+{                                                    // have 2^k columns and slabs 2^k / 2^m rows)
+    return ((i - 1) & (n - 1)) + 1;
 }
 
 // EDGE = false: the whole 64 x 64 region lies strictly inside the domain (the case for all but the
@@ -267,12 +430,18 @@ __device__ __forceinline__ int wrap1(int i, int n)   // periodic image of i in [
 constexpr int TB_EXS = 2 * (TB_RH + 1) * 32;       // doubles in the eta_x tile
 constexpr int TB_EYS = 2 * TB_RH * 33;             // doubles in the eta_y tile
 
-template <bool EDGE, bool VC>
+// INHOM = false: no side carries inhomogeneous boundary values (every level but the finest, and the finest of most
+// callers): the ghost a cell generates is +-(its own value) and none of the index arithmetic for the value tables is
+// compiled in.  cm: slab communication of this launch (cm.ctl == NULL: none).
+template <bool EDGE, bool VC, bool INHOM>
 __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
-                                               double* __restrict__ vout, const MgBC& b, const SmoothCoef& c,
+                                               double* __restrict__ vout, const MgBC& bb, const SmoothCoef& c,
                                                int niter, double (*edge)[TB_NW][2][TB_RW],
-                                               const VcEdges& E, double* __restrict__ exs, double* __restrict__ eys)
+                                               const VcEdges& E, double* __restrict__ exs, double* __restrict__ eys,
+                                               const MgComm& cm)
 {
+    MgBC b = bb;
+    if (!INHOM) { b.xlv = nullptr; b.xrv = nullptr; b.ylv = nullptr; b.yrv = nullptr; }
     const int n = L.n, ni = L.ni, P = L.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
@@ -282,6 +451,9 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     // rows that hold real cells: the owned rows plus, on a side facing another slab, the TB_H halo
     // rows received from it (they are updated redundantly, exactly like the periodic wrap)
     const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? ni : ni + TB_H;
+
+    // slab: this CTA's region reaches into halo rows the neighbour writes -- wait until they have landed
+    if (EDGE) comm_block_wait(cm, I0 - TB_H < 1, I0 - TB_H + TB_RH - 1 > ni);
 
     unsigned xseam = 0;                            // VC: bit r: this row is the periodic image of row ni
     bool yseam[2] = {false, false};                //     column a is the periodic image of column n
@@ -400,9 +572,13 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                 // periodic image of an interior cell uses that cell's index)
                 // The y-side values are indexed with the GLOBAL row: on a slab, a halo row received from the
                 // neighbour across the periodic x boundary lies outside 1..n before the wrap.
-                const int gi = xper ? wrap1(gi0 + r, ni) : gi0 + r, gj = yper ? wrap1(gj0 + a, n) : gj0 + a;
-                int grow = L.ioff + gi;
-                grow = grow < 1 ? grow + n : (grow > n ? grow - n : grow);
+                int gj = 0, grow = 0;
+                if (INHOM) {
+                    const int gi = xper ? wrap1(gi0 + r, ni) : gi0 + r;
+                    gj = yper ? wrap1(gj0 + a, n) : gj0 + a;
+                    grow = L.ioff + gi;
+                    grow = grow < 1 ? grow + n : (grow > n ? grow - n : grow);
+                }
                 if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
                 if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
                 if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, grow, L.dy);
@@ -450,22 +626,33 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
             if (gj < J0 || gj >= J0 + TB_TJ || gj > n) continue;
             if (EDGE) store_with_ghosts(vout, ni, n, P, gi, gj, v[r][a], b, L.dx, L.dy, L.ioff);
             else vout[(long long)gi * P + gj] = v[r][a];
+            // slab: my first / last TB_H rows are the neighbours' halo rows of the plane just written
+            if (EDGE && cm.ctl && cm.sig_ord >= 0) {
+                if (cm.has_lo && gi <= TB_H) (vout + cm.dlo)[(long long)(ni + gi) * P + gj] = v[r][a];
+                if (cm.has_hi && gi > ni - TB_H) (vout + cm.dhi)[(long long)(gi - ni) * P + gj] = v[r][a];
+            }
         }
     }
+    if (EDGE) comm_block_signal(cm, I0 <= TB_H, I0 + TB_TI - 1 > ni - TB_H && I0 <= ni);
 }
 
 __global__ void __launch_bounds__(32 * TB_NW, (TB_NW <= 8 ? 2 : 1))
 mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
-                    SmoothCoef c, int niter)
+                    SmoothCoef c, int niter, MgComm cm)
 {
     __shared__ __align__(16) double edge[2][TB_NW][2][TB_RW];   // [buffer][warp][first/last row][column]
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
-    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? L.ni : L.ni + TB_H;
-    const bool interior = (I0 - TB_H >= rlo) && (I0 - TB_H + TB_RH - 1 <= rhi) &&
-                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
+    // the branch-free interior path needs the whole region strictly inside the rank's OWNED rows: a region that
+    // reaches into halo rows waits for them and one that holds the first / last owned rows pushes them (EDGE path)
+    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + TB_RH - 1 <= L.ni) &&
+                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n) &&
+                          (!cm.ctl || (I0 > TB_H && I0 + TB_TI - 1 <= L.ni - TB_H));
     const VcEdges none = {nullptr, nullptr};
-    if (interior) smooth_tb_body<false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr);
-    else smooth_tb_body<true, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr);
+    const bool inhom = b.xlv || b.xrv || b.ylv || b.yrv;
+    if (interior) smooth_tb_body<false, false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    else if (inhom) smooth_tb_body<true, false, true>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    else smooth_tb_body<true, false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
 }
 
 // the same pass with the variable-coefficient stencil; dynamic shared memory: the row-exchange buffers
@@ -476,6 +663,7 @@ __global__ void __launch_bounds__(32 * TB_NW, 1)
 mg_vc_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b, VcEdges E, int niter)
 {
     P2B_DYN_SMEM(double, sm);
+    if (L.ctl && L.ctl[CW_STOP]) return;
     double (*edge)[TB_NW][2][TB_RW] = reinterpret_cast<double (*)[TB_NW][2][TB_RW]>(sm);
     double* exs = sm + 2 * TB_NW * 2 * TB_RW;
     double* eys = exs + TB_EXS;
@@ -484,8 +672,10 @@ mg_vc_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __rest
                           (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
     SmoothCoef c;
     c.alpha = c.xc = c.yc = c.denom = c.rden = 0.0; c.fast = 0;
-    if (interior) smooth_tb_body<false, true>(L, vin, vout, b, c, niter, edge, E, exs, eys);
-    else smooth_tb_body<true, true>(L, vin, vout, b, c, niter, edge, E, exs, eys);
+    MgComm cm;
+    cm.ctl = nullptr; cm.sig_ord = cm.wait_ord = -1;
+    if (interior) smooth_tb_body<false, true, false>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm);
+    else smooth_tb_body<true, true, true>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm);
 }
 
 
@@ -563,6 +753,7 @@ template <bool VC>
 __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(CoarseTable T)
 {
     P2B_DYN_SMEM(double, sm);
+    if (T.g[0].ctl && T.g[0].ctl[CW_STOP]) return;
     MgLevel S[MG_COARSE_LEVELS];
     {
         double* p = sm;
@@ -657,6 +848,7 @@ __global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(
 // full ghost fill of v from the interior (used once per smooth() like MG.py:565)
 __global__ void mg_fill_kernel(MgLevel L, MgBC b)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     // every interior edge cell re-stores itself with its ghosts
     const int n = L.n;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 4 * n; t += gridDim.x * blockDim.x) {
@@ -669,10 +861,13 @@ __global__ void mg_fill_kernel(MgLevel L, MgBC b)
     }
 }
 
-__global__ void mg_residual_kernel(MgLevel L, ResidCoef rc)
+__global__ void mg_residual_kernel(MgLevel L, ResidCoef rc, MgComm cm)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    // slab: rows 0 and ni + 1 are the neighbours' rows, pushed by their last smoothing pass
+    comm_block_wait(cm, rows_meet(blockIdx.y, blockDim.y, 1, 1), rows_meet(blockIdx.y, blockDim.y, L.ni, L.ni));
     if (i > L.ni || j > L.n) return;
     const long long k = (long long)i * L.pitch + j;
     L.r[k] = residual_at(L, k, rc);
@@ -680,40 +875,77 @@ __global__ void mg_residual_kernel(MgLevel L, ResidCoef rc)
 
 // fine r -> coarse f, valid region (patch.py:659-662, MG.py:731-732).  crow: row offset of this
 // rank's rows inside the coarse array (non-zero when a slab level restricts into a replicated one)
-__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs, int crow)
+__global__ void mg_restrict_kernel(MgLevel F, MgLevel Cs, int crow, MgComm cm, int to_all)
 {
+    if (F.ctl && F.ctl[CW_STOP]) return;
     const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (ic > F.ni / 2 || jc > Cs.n) return;
-    const long long k = (long long)(2 * ic - 1) * F.pitch + (2 * jc - 1);
-    const double* r = F.r;
-    double s = exact_add(exact_add(exact_add(r[k], r[k + F.pitch]), r[k + 1]), r[k + F.pitch + 1]);
-    Cs.f[(long long)(ic + crow) * Cs.pitch + jc] = exact_mul(0.25, s);
+    const int nic = F.ni / 2;
+    if (ic <= nic && jc <= Cs.n) {
+        const long long k = (long long)(2 * ic - 1) * F.pitch + (2 * jc - 1);
+        const double* r = F.r;
+        double s = exact_add(exact_add(exact_add(r[k], r[k + F.pitch]), r[k + 1]), r[k + F.pitch + 1]);
+        const double val = exact_mul(0.25, s);
+        const long long kc = (long long)(ic + crow) * Cs.pitch + jc;
+        Cs.f[kc] = val;
+        if (cm.ctl && cm.sig_ord >= 0) {
+            if (to_all) {
+                // slab -> replicated: every rank needs the whole coarse right-hand side
+                for (int p = 0; p < cm.size; ++p)
+                    if (p != cm.rank) (Cs.f + (long long)cm.ctl[CW_PEER + p])[kc] = val;
+            } else {
+                // slab -> slab: the blocked smoother updates halo cells redundantly and needs their right-hand side
+                if (cm.has_lo && ic <= Cs.gx) (Cs.f + cm.dlo)[(long long)(nic + ic) * Cs.pitch + jc] = val;
+                if (cm.has_hi && ic > nic - Cs.gx) (Cs.f + cm.dhi)[(long long)(ic - nic) * Cs.pitch + jc] = val;
+            }
+        }
+    }
+    if (to_all) comm_block_signal_all(cm, gridDim.x * gridDim.y);
+    else comm_block_signal(cm, rows_meet(blockIdx.y, blockDim.y, 1, Cs.gx), rows_meet(blockIdx.y, blockDim.y, nic - Cs.gx + 1, nic));
 }
 
 // v_fine += prolong(v_coarse), ghosts refreshed (patch.py:716-734, MG.py:745-751)
-__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b, int crow)
+__global__ void mg_prolong_kernel(MgLevel F, MgLevel Cs, MgBC b, int crow, MgComm cm, int coarse_is_slab)
 {
+    if (F.ctl && F.ctl[CW_STOP]) return;
     const int jc = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int ic = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (ic > F.ni / 2 || jc > Cs.n) return;
-    const double* c = Cs.v;
-    const long long kc = (long long)(ic + crow) * Cs.pitch + jc;
-    double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
-    double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
-    double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my);
-    double c0 = c[kc];
-    const int i = 2 * ic - 1, j = 2 * jc - 1;
-    double e00 = exact_sub(exact_sub(c0, qx), qy);
-    double e10 = exact_sub(exact_add(c0, qx), qy);
-    double e01 = exact_add(exact_sub(c0, qx), qy);
-    double e11 = exact_add(exact_add(c0, qx), qy);
-    double* v = F.v;
-    const int P = F.pitch;
-    store_with_ghosts(v, F.ni, F.n, P, i, j, exact_add(v[(long long)i * P + j], e00), b, F.dx, F.dy, F.ioff);
-    store_with_ghosts(v, F.ni, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], e10), b, F.dx, F.dy, F.ioff);
-    store_with_ghosts(v, F.ni, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], e01), b, F.dx, F.dy, F.ioff);
-    store_with_ghosts(v, F.ni, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], e11), b, F.dx, F.dy, F.ioff);
+    const int nic = F.ni / 2, hp = F.gx / 2;      // coarse rows whose fine rows are the neighbours' halo rows: hp per side
+    // coarse rows 0 and nic + 1 of a slab are the neighbours' rows, pushed by their last smoothing pass
+    if (coarse_is_slab) comm_block_wait(cm, rows_meet(blockIdx.y, blockDim.y, 1, 1), rows_meet(blockIdx.y, blockDim.y, nic, nic));
+    if (ic <= nic && jc <= Cs.n) {
+        const double* c = Cs.v;
+        const long long kc = (long long)(ic + crow) * Cs.pitch + jc;
+        double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
+        double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+        double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my);
+        double c0 = c[kc];
+        const int i = 2 * ic - 1, j = 2 * jc - 1;
+        double* v = F.v;
+        const int P = F.pitch, ni = F.ni;
+        const double n00 = exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy));
+        const double n10 = exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy));
+        const double n01 = exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy));
+        const double n11 = exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy));
+        store_with_ghosts(v, ni, F.n, P, i, j, n00, b, F.dx, F.dy, F.ioff);
+        store_with_ghosts(v, ni, F.n, P, i + 1, j, n10, b, F.dx, F.dy, F.ioff);
+        store_with_ghosts(v, ni, F.n, P, i, j + 1, n01, b, F.dx, F.dy, F.ioff);
+        store_with_ghosts(v, ni, F.n, P, i + 1, j + 1, n11, b, F.dx, F.dy, F.ioff);
+        if (cm.ctl && cm.sig_ord >= 0) {
+            // slab: the corrected first / last gx rows are the neighbours' halo rows for the smoothing that follows
+            if (cm.has_lo && ic <= hp) {
+                double* d = v + cm.dlo;
+                d[(long long)(ni + i) * P + j] = n00; d[(long long)(ni + i + 1) * P + j] = n10;
+                d[(long long)(ni + i) * P + j + 1] = n01; d[(long long)(ni + i + 1) * P + j + 1] = n11;
+            }
+            if (cm.has_hi && ic > nic - hp) {
+                double* d = v + cm.dhi;
+                d[(long long)(i - ni) * P + j] = n00; d[(long long)(i + 1 - ni) * P + j] = n10;
+                d[(long long)(i - ni) * P + j + 1] = n01; d[(long long)(i + 1 - ni) * P + j + 1] = n11;
+            }
+        }
+    }
+    comm_block_signal(cm, rows_meet(blockIdx.y, blockDim.y, 1, hp), rows_meet(blockIdx.y, blockDim.y, nic - hp + 1, nic));
 }
 
 // ---- deterministic reductions over the valid region ------------------------------------------------
@@ -760,19 +992,47 @@ __global__ void __launch_bounds__(RED_THREADS) mg_sumsq_partial_kernel(const dou
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
-__global__ void mg_sumsq_final_kernel(const double* part, int npart, double* out)
+// thread 0 of a single-CTA kernel: sum (a, b) over all ranks in rank order (every rank gets the same bits).  Each rank
+// writes its pair into its slot on every rank, publishes, waits for everybody's slot.  A program of its own
+// (new_program) or a step of the running one.
+__device__ __forceinline__ void comm_allreduce2(const MgComm& c, double& a, double& b, bool new_program)
+{
+    if (!c.ctl) return;
+    if (new_program) c.ctl[CW_EPOCH] += 1;
+    const unsigned long long ep = c.ctl[CW_EPOCH], val = ep * MG_ORD_STRIDE + (unsigned long long)(c.sig_ord < 0 ? 0 : c.sig_ord);
+    double* slots = reinterpret_cast<double*>(c.ctl + CW_SUMS) + (ep & 1ull) * MG_MAX_RANKS * 4;
+    for (int r = 0; r < c.size; ++r) {
+        double* dst = slots + (long long)c.ctl[CW_PEER + r] + c.rank * 4;
+        dst[0] = a; dst[1] = b;
+    }
+    __threadfence_system();
+    for (int r = 0; r < c.size; ++r) comm_store(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
+    for (int r = 0; r < c.size; ++r) comm_wait_ge(c.ctl, CW_GFLAG + r, val);
+    a = 0.0; b = 0.0;
+    for (int r = 0; r < c.size; ++r) {
+        const volatile double* src = slots + r * 4;
+        a += src[0]; b += src[1];
+    }
+}
+
+__global__ void mg_sumsq_final_kernel(const double* part, int npart, double* out, MgComm cm)
 {
     __shared__ double sh[RED_THREADS];
     double s = 0.0;
     for (int t = threadIdx.x; t < npart; t += RED_THREADS) s += part[t];
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) *out = s;
+    if (threadIdx.x == 0) {
+        double z = 0.0;
+        comm_allreduce2(cm, s, z, true);
+        *out = s;
+    }
 }
 
-struct MgZeroTable { double* v[MG_MAX_LEVELS]; long long count[MG_MAX_LEVELS]; int nlev; };
+struct MgZeroTable { double* v[MG_MAX_LEVELS]; long long count[MG_MAX_LEVELS]; int nlev; const unsigned long long* ctl; };
 
 __global__ void mg_zero_kernel(MgZeroTable t)
 {
+    if (t.ctl && t.ctl[CW_STOP]) return;
     for (int l = 0; l < t.nlev; ++l)
         for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < t.count[l];
              k += (long long)gridDim.x * blockDim.x)
@@ -786,6 +1046,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 mg_diag_partial_kernel(MgLevel L, double* __restrict__ old_phi, ResidCoef rc, double* __restrict__ part)
 {
     __shared__ double sh[RED_THREADS];
+    if (L.ctl && L.ctl[CW_STOP]) return;
     double s_rel = 0.0, s_res = 0.0;
     const int n = L.n, P = L.pitch;
     const double* __restrict__ v = L.v;
@@ -827,14 +1088,79 @@ mg_diag_partial_kernel(MgLevel L, double* __restrict__ old_phi, ResidCoef rc, do
     if (threadIdx.x == 0) { part[blockIdx.x] = s_rel; part[MG_NPART + blockIdx.x] = s_res; }
 }
 
-__global__ void mg_diag_final_kernel(const double* part, int npart, double* out)
+// second stage of the per-cycle bookkeeping: sums over the rows (and over the ranks of a decomposed hierarchy), and the
+// stopping rule of solve() evaluated on the device (MG.py:654-697: while residual_error > rtol and cycle <= max_cycles):
+// stop.scale = dx * dy, stop.source_norm, stop.rtol as the host would use them -- same IEEE operations, same decision.
+// When the rule says stop, CW_STOP turns every kernel of a cycle that was enqueued ahead into a no-op, so the host can
+// enqueue cycles without waiting for each cycle's two scalars.  results: (relsq, rsq, residual_error, cycles run).
+struct MgStop { double scale, source_norm, rtol; int max_cycles, enabled; };
+
+__global__ void mg_diag_final_kernel(const double* part, int npart, double* out, MgComm cm, unsigned long long* ctl, MgStop stop)
 {
     __shared__ double sh[RED_THREADS];
+    if (ctl && ctl[CW_STOP]) return;
     double a = 0.0, b = 0.0;
     for (int t = threadIdx.x; t < npart; t += RED_THREADS) { a += part[t]; b += part[MG_NPART + t]; }
     a = block_sum(a, sh);
     b = block_sum(b, sh);
-    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+    if (threadIdx.x == 0) {
+        comm_allreduce2(cm, a, b, true);
+        out[0] = a; out[1] = b;
+        if (ctl && stop.enabled) {
+            double* res = reinterpret_cast<double*>(ctl + CW_RESULT);
+            const double rnorm = exact_sqrt(exact_mul(stop.scale, b));
+            const double err = stop.source_norm != 0.0 ? exact_div(rnorm, stop.source_norm) : rnorm;
+            const double ncyc = res[3] + 1.0;
+            res[0] = a; res[1] = b; res[2] = err; res[3] = ncyc;
+            if (!(err > stop.rtol) || ncyc >= (double)stop.max_cycles) ctl[CW_STOP] = 1ull;
+        }
+    }
+}
+
+// ---- small communication kernels -------------------------------------------------------------------------
+// starts a program on this rank
+__global__ void mg_epoch_kernel(unsigned long long* ctl)
+{
+    if (ctl[CW_STOP]) return;
+    ctl[CW_EPOCH] += 1;
+}
+
+// <<<1, 32>>>: wait until both neighbours' words (gather = 0) or every rank's all-rank word (gather = 1) have reached
+// the value of launch cm.wait_ord of the running program
+__global__ void mg_comm_wait_kernel(MgComm cm, int gather)
+{
+    if (cm.ctl[CW_STOP]) return;
+    const unsigned long long target = comm_value(cm, cm.wait_ord);
+    const int t = threadIdx.x;
+    if (gather) { if (t < cm.size) comm_wait_ge(cm.ctl, CW_GFLAG + t, target); }
+    else {
+        if (t == 0 && cm.has_lo) comm_wait_ge(cm.ctl, CW_FROM_LO, target);
+        if (t == 1 && cm.has_hi) comm_wait_ge(cm.ctl, CW_FROM_HI, target);
+    }
+}
+
+// stand-alone halo exchange, phase 1 (<<<1, 1>>>): start a program, tell both neighbours "everything I enqueued
+// before this exchange has finished -- my halo rows may be overwritten", wait for the same from them
+__global__ void mg_xchg_arrive_kernel(MgComm cm)
+{
+    cm.ctl[CW_EPOCH] += 1;
+    const unsigned long long val = comm_value(cm, 0);
+    __threadfence_system();
+    if (cm.has_lo) comm_store(cm.ctl + cm.dlo + CW_FROM_HI, val);
+    if (cm.has_hi) comm_store(cm.ctl + cm.dhi + CW_FROM_LO, val);
+    if (cm.has_lo) comm_wait_ge(cm.ctl, CW_FROM_LO, val);
+    if (cm.has_hi) comm_wait_ge(cm.ctl, CW_FROM_HI, val);
+}
+
+// phase 2: copy my first / last `depth` owned rows (whole rows, ghost columns included) into the neighbours' halo rows
+__global__ void mg_xchg_push_kernel(double* plane, int ni, int pitch, int depth, MgComm cm)
+{
+    const int r = blockIdx.y + 1, col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < pitch) {
+        if (cm.has_lo) (plane + cm.dlo)[(long long)(ni + r) * pitch + col] = plane[(long long)r * pitch + col];
+        if (cm.has_hi) (plane + cm.dhi)[(long long)(r - depth) * pitch + col] = plane[(long long)(ni - depth + r) * pitch + col];
+    }
+    comm_block_signal(cm, true, true);
 }
 
 // ---- variable coefficients: kernels (the per-point arithmetic is defined ahead of the blocked smoother)
@@ -853,6 +1179,7 @@ __device__ __forceinline__ double vc_residual_at(const MgLevel& L, const VcEdges
 
 __global__ void mg_vc_halfsweep_kernel(MgLevel L, MgBC b, VcEdges E, int colour)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int half = L.n >> 1;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -864,6 +1191,7 @@ __global__ void mg_vc_halfsweep_kernel(MgLevel L, MgBC b, VcEdges E, int colour)
 
 __global__ void mg_vc_smooth_small_kernel(MgLevel L, MgBC b, VcEdges E, int nsmooth)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int half = L.n >> 1;
     const int npts = L.n * half;
     for (int it = 0; it < 2 * nsmooth; ++it) {
@@ -880,6 +1208,7 @@ __global__ void mg_vc_smooth_small_kernel(MgLevel L, MgBC b, VcEdges E, int nsmo
 
 __global__ void mg_vc_residual_kernel(MgLevel L, VcEdges E)
 {
+    if (L.ctl && L.ctl[CW_STOP]) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
     if (i > L.ni || j > L.n) return;
@@ -919,6 +1248,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 mg_vc_diag_partial_kernel(MgLevel L, VcEdges E, double* __restrict__ old_phi, double* __restrict__ part)
 {
     __shared__ double sh[RED_THREADS];
+    if (L.ctl && L.ctl[CW_STOP]) return;
     double s_rel = 0.0, s_res = 0.0;
     const int n = L.n, P = L.pitch;
     const double* __restrict__ v = L.v;

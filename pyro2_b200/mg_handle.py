@@ -6,6 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from . import ops
 from .ops import require_cuda
 
 
@@ -31,16 +32,36 @@ class MGHandle:
         self.xperiodic = bc[0] == "periodic"
         self._info = {}
         nbytes = L.p2b_mg_workspace_bytes(self._h)
-        self.workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+        self._shared_ptr = None
+        self._peer_ptrs = None
+        if self.decomp is None:
+            self.workspace = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+        else:
+            # the slabs talk through each other's workspaces (csrc/mg_kernels.cuh, "peer-memory communication"): the
+            # allocation must be mappable by the other ranks, so the library owns it
+            self._shared_ptr = L.p2b_shared_alloc(nbytes)
+            if not self._shared_ptr:
+                raise RuntimeError(L.p2b_last_error().decode())
+            self.workspace = ops.tensor_from_pointer(self._shared_ptr, nbytes // 8)
         _lib.check(L.p2b_mg_bind(self._h, self.workspace.data_ptr(), nbytes))
+        if self.decomp is not None:
+            self._peer_ptrs = self.decomp.map_peer_workspaces(self._shared_ptr)
+            arr = (C.c_void_p * len(self._peer_ptrs))(*self._peer_ptrs)
+            _lib.check(L.p2b_mg_set_peers(self._h, arr))
         self._bc_vals = [None] * 4
         self._out = torch.zeros(2, dtype=torch.float64, device="cuda")
         self._planes = {}
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib().p2b_mg_destroy(self._h)
+            L = _lib.lib()
+            L.p2b_mg_destroy(self._h)
             self._h = None
+            if self._peer_ptrs is not None and type(self.decomp).__name__ == "SlabDecomposition":
+                for r, p in enumerate(self._peer_ptrs):
+                    if r != self.decomp.rank:
+                        L.p2b_shared_close(C.c_void_p(p))
+            # the shared allocation itself is released when the process ends: a neighbour may still have it mapped
 
     def __del__(self):
         try:
@@ -82,12 +103,12 @@ class MGHandle:
         return self.workspace.as_strided((g["ni"] + 2 * depth, g["pitch"]), (g["pitch"], 1), off)
 
     def exchange(self, level, which, depth):
-        """halo exchange of `depth` rows with the neighbouring slabs (no-op on replicated levels)"""
+        """halo exchange of `depth` rows with the neighbouring slabs through peer memory (no-op on replicated levels;
+        collective)"""
         g = self.info(level)
         if self.decomp is None or not g["slab"]:
             return
-        self.decomp.exchange(self.halo_rows(level, which, depth).unsqueeze(0), g["ni"], depth,
-                             periodic=self.xperiodic)
+        _lib.check(_lib.lib().p2b_mg_exchange(self._h, level, self._WHICH[which], depth, self._s()))
 
     def tb_pass(self, level, src, dst, niter):
         _lib.check(_lib.lib().p2b_mg_tb_pass(self._h, level, self._WHICH[src], self._WHICH[dst], niter, self._s()))
@@ -161,24 +182,30 @@ class MGHandle:
 
     def sumsq(self, level, which):
         idx = {"v": 0, "f": 1, "r": 2}[which]
+        # on a slab level the library sums over the ranks (rank order, same bits everywhere)
         _lib.check(_lib.lib().p2b_mg_norm2(self._h, level, idx, self._out.data_ptr(), self._s()))
-        if self.decomp is not None and self.info(level)["slab"]:
-            import torch.distributed as dist
-            dist.all_reduce(self._out[:1], group=self.decomp.group)
         return float(self._out[0])
 
     def cycle_diagnostics_enqueue(self, old_phi):
         """device part of cycle_diagnostics (capturable in a CUDA graph): results land in self._out"""
         _lib.check(_lib.lib().p2b_mg_cycle_diagnostics(self._h, old_phi.data_ptr(), self._out.data_ptr(), self._s()))
-        if self.decomp is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self._out, group=self.decomp.group)
+
+    def set_stop(self, enable, source_norm=0.0, rtol=0.0, max_cycles=0):
+        """arm / disarm the device-side stopping rule of solve(); clears the stop word and the cycle count"""
+        _lib.check(_lib.lib().p2b_mg_set_stop(self._h, int(enable), source_norm, rtol, max_cycles, self._s()))
+
+    def result(self):
+        """(relsq, rsq, residual_error, cycles) of the last counted cycle; synchronises.  Raises if a wait on another
+        rank timed out."""
+        out = (C.c_double * 4)()
+        err = C.c_longlong(0)
+        _lib.check(_lib.lib().p2b_mg_result(self._h, out, C.byref(err), self._s()))
+        if err.value:
+            raise RuntimeError(f"multigrid: a wait on a neighbouring rank timed out (control word {err.value - 1})")
+        return tuple(out)
 
     def cycle_diagnostics(self, old_phi):
         """returns (sum rel-change^2, sum r^2); updates old_phi <- v and the r plane"""
         _lib.check(_lib.lib().p2b_mg_cycle_diagnostics(self._h, old_phi.data_ptr(), self._out.data_ptr(), self._s()))
-        if self.decomp is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self._out, group=self.decomp.group)
         a, b = self._out.tolist()
         return a, b

@@ -139,6 +139,7 @@ class CellCenterMG2d:
         self.frame = 0
         self._old_phi = None
         self.use_graph = True       # replay the V-cycle as a CUDA graph after one eager cycle
+        self.enqueue_ahead = 2      # cycles enqueued per read-back of the device-side stopping rule (solve())
         self._graph = None
         self._graph_error = None
 
@@ -232,10 +233,9 @@ class CellCenterMG2d:
         """one V-cycle from `level` down and back (MG.py:699-778).  With the stock smoother and
         residual the whole hierarchy is traversed inside the library; subclasses that override the
         hooks get the reference's recursion with their hooks called per level."""
-        if self._decomp is not None:
-            self._v_cycle_slabs(level)
-            return
         if self._stock() and level == self.nlevels - 1 and not self.verbose:
+            # (decomposed hierarchies too: slab levels push their halo rows from the kernels' epilogues,
+            # csrc/mg_kernels.cuh "peer-memory communication"; nothing but kernels is enqueued)
             self.current_level = level
             self._h.vcycle()
             return
@@ -270,54 +270,15 @@ class CellCenterMG2d:
             self.smooth(level, self.nsmooth_bottom)
             self._h.fill_bc(level)
 
-    # ---- multi-GPU V-cycle: slab levels with NCCL halo exchange, replicated coarse levels ----------
-    def _smooth_slabs(self, level, nsmooth):
-        """nsmooth red-black iterations on a slab level: passes of <= 5 iterations of the temporally
-        blocked kernel, each preceded by one exchange of its 10-row halo (communication-avoiding:
-        one message per 5 iterations instead of one per colour)"""
-        h = self._h
-        src, dst = "v", "w"
-        left = nsmooth
-        while left > 0:
-            it = min(left, h.tb_iters)
-            h.exchange(level, src, h.tb_halo)
-            h.tb_pass(level, src, dst, it)
-            left -= it
-            src, dst = dst, src
-        if src != "v":
-            g = h.info(level)
-            h.halo_rows(level, "v", g["gx"]).copy_(h.halo_rows(level, "w", g["gx"]))
-
-    def _v_cycle_slabs(self, level):
-        import torch.distributed as dist
-        h = self._h
-        if level < self._split:
-            # replicated levels: every rank runs the identical sub-V-cycle, no communication
-            h.vcycle_level(level)
-            return
-        self.current_level = level
-        self._smooth_slabs(level, self.nsmooth)
-        h.exchange(level, "v", 1)
-        h.residual(level)
-        h.restrict(level)
-        if level - 1 < self._split:
-            # slab -> replicated: everyone needs the whole coarse right-hand side
-            g = h.info(level - 1)
-            f = h.halo_rows(level - 1, "f", 0)                  # owned rows = the whole level, contiguous
-            mine = f[self._decomp.rank * (g["ni"] // self._decomp.size):][:g["ni"] // self._decomp.size]
-            dist.all_gather_into_tensor(f.view(-1), mine.reshape(-1), group=self._decomp.group)
-        else:
-            # the blocked smoother updates the halo cells redundantly, so it needs their right-hand side
-            h.exchange(level - 1, "f", h.tb_halo)
-        self._v_cycle_slabs(level - 1)
-        if level - 1 >= self._split:
-            h.exchange(level - 1, "v", 1)
-        h.prolong_correct(level)
-        self._smooth_slabs(level, self.nsmooth)
-
     def solve(self, rtol=1.e-11):
-        """V-cycles until ||r|| / ||f|| <= rtol or max_cycles (MG.py:623-697); one host read-back of
-        two scalars per cycle"""
+        """V-cycles until ||r|| / ||f|| <= rtol or max_cycles (MG.py:623-697).
+
+        The cycle body (zero the coarse v, V-cycle, bookkeeping) is ~60 kernel launches and nothing else -- also on a
+        decomposed hierarchy, whose halo rows travel in the kernels' epilogues -- so after one eager cycle it is
+        captured into a CUDA graph and replayed.  The stopping rule runs on the device (p2b_mg_set_stop): the host
+        enqueues `enqueue_ahead` cycles at a time and reads the scalars back once per batch; once the rule has
+        fired, the kernels of the cycles enqueued ahead return at once, so the solution and the cycle count are the
+        reference's.  Verbose mode and subclasses that override the hooks stay eager, one read-back per cycle."""
         if not self.initialized_rhs:
             msg.fail("ERROR: RHS not initialized")
         if self.verbose:
@@ -330,76 +291,81 @@ class CellCenterMG2d:
             self._old_phi = torch.empty((g.qx, pitch), dtype=torch.float64, device=v.device)
         old_phi = self._old_phi
         old_phi[:, :g.qy].copy_(v)
+        h = self._h
+        if self._decomp is not None:
+            h.exchange(fine, "v", h.tb_halo)        # the blocked smoother reads tb_halo rows of the neighbours' v
 
         residual_error = 1.e33
         relative_error = 1.e33
-        cycle = 1
-        graph = self._graph             # captured by an earlier solve() on this object
-        eager_done = 0
-        # The cycle body (zero coarse v, V-cycle, diagnostics) is ~60 small launches (plus the NCCL
-        # exchanges when decomposed): after one eager cycle it is captured into a CUDA graph and
-        # replayed, so a cycle costs one launch on the host.  Verbose mode and subclasses that
-        # override the hooks stay eager (their hooks may synchronise).
-        # (not when decomposed: a captured graph holding NCCL work kept the process from shutting
-        # down cleanly in testing, and only bought 6%)
-        use_graph = self.use_graph and self._stock() and not self.verbose and self._decomp is None
+        fast = self._stock() and not self.verbose
 
         def body():
-            self._h.zero_coarse()
+            h.zero_coarse()
             self.v_cycle(fine)
-            if self._decomp is not None:
-                self._h.exchange(fine, "v", 1)      # the residual stencil reads the neighbours' rows
-            self._h.cycle_diagnostics_enqueue(old_phi)
+            h.cycle_diagnostics_enqueue(old_phi)
 
-        while residual_error > rtol and cycle <= self.max_cycles:
-            self.current_cycle = cycle
-            if self.verbose:
-                print(f"<<< beginning V-cycle (cycle {cycle}) >>>\n")
-            if use_graph:
-                if graph is not None:
-                    graph.replay()
-                elif eager_done >= 1:
-                    try:
-                        torch.cuda.synchronize()
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
+        if fast:
+            h.set_stop(True, self.source_norm, rtol, self.max_cycles)
+            use_graph = self.use_graph
+            enq = 0
+            while True:
+                batch = 1 if enq == 0 else max(1, int(self.enqueue_ahead))
+                for _ in range(batch):
+                    self.current_cycle = enq + 1
+                    if use_graph and self._graph is not None:
+                        self._graph.replay()
+                    elif use_graph and enq >= 1:
+                        try:
+                            torch.cuda.synchronize()
+                            graph = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(graph):
+                                body()
+                            self._graph = graph
+                            graph.replay()
+                        except Exception as exc:   # pylint: disable=broad-except
+                            # capture is an optimisation only: fall back to eager launches
+                            use_graph = self.use_graph = False
+                            self._graph_error = repr(exc)
+                            torch.cuda.synchronize()
                             body()
-                        self._graph = graph
-                        graph.replay()
-                    except Exception as exc:   # pylint: disable=broad-except
-                        # capture is an optimisation only: fall back to eager launches
-                        graph, use_graph = None, False
-                        self.use_graph = False
-                        self._graph_error = repr(exc)
-                        torch.cuda.synchronize()
+                    else:
                         body()
-                else:
-                    body()
-                    eager_done += 1
-                relsq, rsq = self._h._out.tolist()
-            else:
-                self._h.zero_coarse()
+                    enq += 1
+                relsq, rsq, residual_error, ncyc = h.result()
+                if ncyc < enq or not residual_error > rtol or ncyc >= self.max_cycles:
+                    break
+            relative_error = math.sqrt(g.dx * g.dy * relsq)
+            cycle = int(ncyc) + 1
+            h.set_stop(False)
+        else:
+            h.set_stop(False)
+            cycle = 1
+            while residual_error > rtol and cycle <= self.max_cycles:
+                self.current_cycle = cycle
+                if self.verbose:
+                    print(f"<<< beginning V-cycle (cycle {cycle}) >>>\n")
+                h.zero_coarse()
                 self.v_cycle(fine)
                 # relative change, old_phi <- v, residual and its norm, all on the device
                 if self._decomp is not None:
-                    self._h.exchange(fine, "v", 1)
+                    h.exchange(fine, "v", 1)
                 if self._stock():
-                    relsq, rsq = self._h.cycle_diagnostics(old_phi)
+                    relsq, rsq = h.cycle_diagnostics(old_phi)
                 else:
-                    relsq, _ = self._h.cycle_diagnostics(old_phi)
+                    relsq, _ = h.cycle_diagnostics(old_phi)
                     self._compute_residual(fine)
-                    rsq = self._h.sumsq(fine, "r")
-            relative_error = math.sqrt(g.dx * g.dy * relsq)
-            rnorm = math.sqrt(g.dx * g.dy * rsq)
-            residual_error = rnorm / self.source_norm if self.source_norm != 0.0 else rnorm
-            if self.verbose:
-                print(f"cycle {cycle}: relative err = {relative_error}, residual err = {residual_error}\n")
-            cycle += 1
+                    rsq = h.sumsq(fine, "r")
+                relative_error = math.sqrt(g.dx * g.dy * relsq)
+                rnorm = math.sqrt(g.dx * g.dy * rsq)
+                residual_error = rnorm / self.source_norm if self.source_norm != 0.0 else rnorm
+                if self.verbose:
+                    print(f"cycle {cycle}: relative err = {relative_error}, residual err = {residual_error}\n")
+                cycle += 1
 
         self.num_cycles = cycle - 1
         self.relative_error = relative_error
         self.residual_error = residual_error
         if self._decomp is not None:
-            self._h.exchange(fine, "v", 1)      # the slab's x "ghost" rows are the neighbours' rows
+            h.exchange(fine, "v", 1)      # the slab's x "ghost" rows are the neighbours' rows
         else:
-            self._h.fill_bc(fine)
+            h.fill_bc(fine)

@@ -125,3 +125,18 @@ def sweep_info():
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     _lib.lib().p2b_sweep_info(C.byref(a), C.byref(b), C.byref(c))
     return {"ntasks": a.value, "resident_warps": b.value, "seglen": c.value}
+
+
+class _RawDeviceMemory:
+    """a device allocation owned by libpyro2b200 (p2b_shared_alloc), exposed to torch through the CUDA array interface"""
+
+    def __init__(self, ptr, nelem):
+        self.ptr, self.nelem = ptr, nelem
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def tensor_from_pointer(ptr, nelem):
+    """float64 CUDA tensor over `nelem` doubles at device address `ptr` (no copy; the caller keeps the allocation alive)"""
+    require_cuda()
+    return torch.as_tensor(_RawDeviceMemory(ptr, nelem), device="cuda")

@@ -71,6 +71,28 @@ class SlabDecomposition:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def map_peer_workspaces(self, ptr):
+        """collective: every rank passes the device address of its (p2b_shared_alloc'd) multigrid workspace and gets the
+        list of all ranks' workspaces as mapped into THIS process (its own address at [rank]).  Processes on one node:
+        cudaIpc handles travel through torch.distributed, the mapping is opened by libpyro2b200 (p2b_shared_open)."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        buf = C.create_string_buffer(64)
+        _lib.check(L.p2b_shared_handle(C.c_void_p(ptr), buf))
+        handles = [None] * self.size
+        dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
+        out = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                out.append(ptr)
+                continue
+            p = L.p2b_shared_open(C.create_string_buffer(h, 64))
+            if not p:
+                raise RuntimeError("cannot map rank %d's multigrid workspace: %s" % (r, L.p2b_last_error().decode()))
+            out.append(p)
+        return out
+
     def allreduce_max_(self, t):
         if self.size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -80,3 +102,44 @@ class SlabDecomposition:
         """(low_is_interior, high_is_interior)"""
         lo, hi = self.neighbours(periodic)
         return lo is not None, hi is not None
+
+
+class LocalSlabGroup:
+    """Several ranks inside ONE process (one host thread each, one stream each): the slabs of a decomposed multigrid
+    then share an address space and reach each other's workspaces through plain pointers.  Used to exercise the
+    peer-memory protocol on a single GPU (and by the CPU tests on the emulated device); real multi-GPU runs use one
+    process per GPU (SlabDecomposition)."""
+
+    def __init__(self, size):
+        import threading
+        self.size = size
+        self._barrier = threading.Barrier(size)
+        self._slots = [None] * size
+
+    def member(self, rank):
+        return _LocalSlab(self, rank)
+
+
+class _LocalSlab(SlabDecomposition):
+    def __init__(self, group, rank):
+        self.group = None
+        self._g = group
+        self.rank, self.size = rank, group.size
+
+    def map_peer_workspaces(self, ptr):
+        g = self._g
+        g._barrier.wait()
+        g._slots[self.rank] = ptr
+        g._barrier.wait()
+        out = list(g._slots)
+        g._barrier.wait()
+        return out
+
+    def barrier(self):
+        self._g._barrier.wait()
+
+    def exchange(self, planes, nx, ng, periodic=False):
+        raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")
+
+    def allreduce_max_(self, t):
+        raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")

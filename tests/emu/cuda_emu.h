@@ -28,21 +28,26 @@ struct emu_uint3 { unsigned x, y, z; };
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
-extern emu_uint3 threadIdx, blockIdx;   // of the running fiber (saved / restored by the scheduler)
-extern dim3 blockDim, gridDim;
+// of the running fiber (saved / restored by the scheduler).  Everything the scheduler keeps is thread_local: several
+// OS threads may each run an emulated "GPU" at the same time (the ranks of a decomposed multigrid talk to each other
+// through plain memory, tests/test_mg_emulated.py), each with its own fibers.
+extern thread_local emu_uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static            // CTAs run one at a time, so one static copy is the CTA's copy
+#define __shared__ static thread_local   // CTAs of one emulated GPU run one at a time: one copy per OS thread is the CTA's copy
 #define __align__(n) __attribute__((aligned(n)))
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
-enum { cudaMemcpyDeviceToDevice = 3 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaDevAttrMultiProcessorCount = 16 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
@@ -51,6 +56,85 @@ inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// cudaMalloc is only used for allocations that other ranks map (p2b_shared_alloc): POSIX shared memory, so that the
+// ranks may be threads of one process or separate processes (the gloo tests).  The "IPC handle" is the segment's name.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
+#include <mutex>
+#include <string>
+namespace emu {
+struct Shm { std::string name; size_t bytes; bool owner; };
+inline std::map<void*, Shm>& shm_table() { static std::map<void*, Shm> t; return t; }
+inline std::mutex& shm_mutex() { static std::mutex m; return m; }
+}  // namespace emu
+inline cudaError_t cudaMalloc(void** p, size_t n)
+{
+    static int counter = 0;
+    std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    char name[64];
+    snprintf(name, sizeof name, "/p2b_emu_%d_%d", (int)getpid(), counter++);
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return 1;
+    if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); return 1; }
+    void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) { shm_unlink(name); return 1; }
+    emu::shm_table()[q] = emu::Shm{name, n, true};
+    *p = q;
+    return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* p)
+{
+    std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    auto it = emu::shm_table().find(p);
+    if (it == emu::shm_table().end()) return 1;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    emu::shm_table().erase(it);
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+    std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    auto it = emu::shm_table().find(p);
+    if (it == emu::shm_table().end()) return 1;
+    memset(h, 0, sizeof *h);
+    snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    memcpy(h->reserved + 48, &it->second.bytes, sizeof(size_t));
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+    std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    const std::string name(h.reserved);
+    for (auto& kv : emu::shm_table())
+        if (kv.second.name == name && kv.second.owner) { *p = kv.first; return cudaSuccess; }   // a rank of this very process
+    size_t n = 0;
+    memcpy(&n, h.reserved + 48, sizeof n);
+    int fd = shm_open(name.c_str(), O_RDWR, 0600);
+    if (fd < 0) return 1;
+    void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return 1;
+    emu::shm_table()[q] = emu::Shm{name, n, false};
+    *p = q;
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void* p)
+{
+    std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    auto it = emu::shm_table().find(p);
+    if (it == emu::shm_table().end() || it->second.owner) return cudaSuccess;
+    munmap(p, it->second.bytes);
+    emu::shm_table().erase(it);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int, cudaStream_t)
 {
     for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
@@ -74,9 +158,10 @@ struct Cta {
     std::vector<int> flip;             // exchange-buffer parity per thread
 };
 
-extern Cta* cta;                       // null in sequential mode
-extern int lin_tid;                    // linear thread index of the running fiber
-extern void* dyn_smem;                 // dynamic shared memory of the running CTA
+extern thread_local Cta* cta;          // null in sequential mode
+extern thread_local int lin_tid;       // linear thread index of the running fiber
+extern thread_local void* dyn_smem;    // dynamic shared memory of the running CTA
+extern thread_local bool force_threaded;   // run every kernel with fibers (set by host code whose launches may synchronise)
 void yield();                          // switch to the next fiber of the CTA
 
 std::set<const void*>& threaded_set();
@@ -144,6 +229,16 @@ inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v)
     if (v > old) *a = v;
     return old;
 }
+// cross-"GPU" primitives (ranks are OS threads sharing the address space): real atomics and fences
+inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicExch(unsigned long long* a, unsigned long long v) { return __atomic_exchange_n(a, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+#include <sched.h>
+#include <time.h>
+inline long long emu_clock_ns() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (long long)t.tv_sec * 1000000000LL + t.tv_nsec; }
+inline void emu_pause() { sched_yield(); }
 
 #define P2B_LAUNCH(kernel, grid, block, smem, stream) ::emu::bind_launch(kernel, grid, block, smem)
 #define P2B_DYN_SMEM(type, name) type* name = (type*)::emu::dyn_smem

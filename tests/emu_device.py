@@ -33,7 +33,7 @@ RESIDENT_WARPS = 148 * 12   # the device's warp slots as choose_seglen() sees th
 
 class EmuLibrary:
     """stands in for the ctypes handle of libpyro2b200.so"""
-    ROUTES = (("p2b_mg_", emu_util.load_mg_emu), ("p2b_flow_", emu_util.load_flow_emu), ("p2b_lm_", emu_util.load_lm_emu),
+    ROUTES = (("p2b_mg_", emu_util.load_mg_emu), ("p2b_shared_", emu_util.load_mg_emu), ("p2b_flow_", emu_util.load_flow_emu), ("p2b_lm_", emu_util.load_lm_emu),
               ("p2b_fill_hse", emu_util.load_bc_emu), ("p2b_fill_ambient", emu_util.load_bc_emu),
               ("p2b_fill_ghost", emu_util.load_ghost_emu), ("p2b_cfl_wavemax", emu_util.load_ghost_emu),
               ("p2b_device_sms", emu_util.load_ghost_emu))
@@ -103,6 +103,11 @@ def _host_device(fn):
     return wrapped
 
 
+def _host_tensor_from_pointer(ptr, nelem):
+    """ops.tensor_from_pointer over host ("device") memory"""
+    return torch.frombuffer((C.c_double * nelem).from_address(ptr), dtype=torch.float64)
+
+
 @contextlib.contextmanager
 def emulated_device():
     """run the enclosed product code against the emulator libraries; yields the EmuLibrary (see .calls)"""
@@ -120,6 +125,7 @@ def emulated_device():
         for target, attr, new in (
                 (_lib, "lib", lambda: facade), (_lib, "stream_ptr", lambda: None),
                 (ops, "require_cuda", lambda: None), (mg_handle, "require_cuda", lambda: None),
+                (ops, "tensor_from_pointer", _host_tensor_from_pointer),
                 (patch, "_default_device", lambda: torch.device("cpu")),
                 (torch, "zeros", _host_device(torch.zeros)), (torch, "empty", _host_device(torch.empty)),
                 (torch, "as_tensor", _host_device(torch.as_tensor)),

@@ -59,7 +59,7 @@ def _load(kind, sources, prefix, extra=()):
 
 def load_mg_emu():
     """pyro2_b200/csrc/mg.cu compiled for the host: the p2b_mg_* ABI over numpy memory"""
-    return _load("mg", ["mg.cu", "mg_kernels.cuh"], "p2b_mg_", ["-DMG_COARSE_THREADS=128"])
+    return _load("mg", ["mg.cu", "mg_kernels.cuh"], ("p2b_mg_", "p2b_shared_"), ["-DMG_COARSE_THREADS=128"])
 
 
 def load_bc_emu():

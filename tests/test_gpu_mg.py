@@ -209,3 +209,76 @@ def test_vc_cycle_diagnostics():
     ref = (((v - old.cpu().numpy()[1:-1, 1:-1]) / (v + 1e-16)) ** 2).sum()
     assert relsq == pytest.approx(float(ref), rel=1e-12)
     assert np.array_equal(old_phi[:, :nx + 2].cpu().numpy()[1:-1, 1:-1], v)
+
+
+def slabs_in_one_process(size, n, split, kw, rhs, use_graph=False, rtol=1.e-11):
+    """solve on `size` x-slabs that live in ONE process (a host thread and a stream each; the slabs reach each other's
+    workspaces through plain pointers) and on a single domain; returns (stitched solution, cycles, single, cycles).
+    Exercises the peer-memory protocol of the decomposed V-cycle (csrc/mg_kernels.cuh) where only one device exists;
+    shared by the GPU test below and by the emulated-device CPU test."""
+    import threading
+
+    import torch
+    from pyro2_b200.multigrid import MG
+    from pyro2_b200.parallel import LocalSlabGroup
+    group = LocalSlabGroup(size)
+    out, errs = [None] * size, []
+
+    def run(rank):
+        try:
+            stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+            ctx = torch.cuda.stream(stream) if stream is not None else __import__("contextlib").nullcontext()
+            with ctx:
+                a = MG.CellCenterMG2d(n, n, decomposition=group.member(rank), split_n=split, **kw)
+                a.use_graph = use_graph
+                a.init_zeros()
+                a.init_RHS(rhs(a.x2d.t(), a.y2d.t()))
+                a.solve(rtol=rtol)
+                g = a.soln_grid
+                out[rank] = (a.get_solution().t()[g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].cpu().numpy().copy(), a.num_cycles,
+                             a.residual_error)
+        except Exception as exc:   # pylint: disable=broad-except
+            errs.append(repr(exc))
+            group._barrier.abort()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(size)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(600)
+    assert not errs, errs
+    b = MG.CellCenterMG2d(n, n, **kw)
+    b.init_zeros()
+    b.init_RHS(rhs(b.x2d.t(), b.y2d.t()))
+    b.solve(rtol=rtol)
+    assert len({o[1] for o in out}) == 1 and len({o[2] for o in out}) == 1      # every rank stopped at the same cycle
+    return np.concatenate([o[0] for o in out], axis=0), out[0][1], b.get_solution().cpu().numpy()[1:-1, 1:-1], b.num_cycles
+
+
+SLAB_CASES = [("dirichlet", 2, 256, 64), ("periodic", 2, 256, 128), ("mixed", 4, 512, 128), ("xper_inhom", 2, 256, 64)]
+
+
+def slab_case(kind):
+    import torch
+    bc = {"dirichlet": ("dirichlet",) * 4, "periodic": ("periodic",) * 4,
+          "mixed": ("neumann", "dirichlet", "dirichlet", "neumann"),
+          "xper_inhom": ("periodic", "periodic", "dirichlet", "neumann")}[kind]
+    kw = dict(xl_BC_type=bc[0], xr_BC_type=bc[1], yl_BC_type=bc[2], yr_BC_type=bc[3])
+    if kind == "mixed":
+        kw.update(alpha=1.0, beta=0.05)
+    if kind == "xper_inhom":
+        kw.update(yl_BC=lambda s: 0.3 + np.sin(2.0 * np.pi * s), yr_BC=lambda s: np.cos(4.0 * np.pi * s))
+
+    def rhs(x, y):
+        if kind == "periodic":
+            return torch.sin(2 * np.pi * x) * torch.cos(4 * np.pi * y)
+        return -2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2))
+    return kw, rhs
+
+
+@pytest.mark.parametrize("kind,size,n,split", SLAB_CASES)
+def test_slabs_sharing_one_gpu_are_bit_identical(kind, size, n, split):
+    """the decomposed V-cycle's peer-memory protocol on ONE device: each slab a host thread + stream, halo rows pushed
+    from the kernels' epilogues, flags, device-side all-reduce -- identical solution bits and cycle count"""
+    kw, rhs = slab_case(kind)
+    full, cyc, one, cyc1 = slabs_in_one_process(size, n, split, kw, rhs)
+    assert cyc == cyc1 and np.array_equal(full, one)

@@ -156,3 +156,15 @@ def test_emulated_blocked_smoother_inhomogeneous_values_with_periodic_other_dire
     m.ck(emu.p2b_mg_smooth(m.h, fine, 7, None))
     assert np.array_equal(m.plane(fine, "v")[1:-1, 1:-1], o.plane(fine, "v")[1:-1, 1:-1])
     m.close()
+
+
+@pytest.mark.parametrize("kind,size,n,split", [("dirichlet", 2, 128, 64), ("xper_inhom", 2, 128, 32)])
+def test_slabs_as_threads_on_the_emulated_device(kind, size, n, split):
+    """ranks as host threads of one process (parallel.LocalSlabGroup): the hardware test of the same name minus the
+    hardware -- the peer-memory protocol of the decomposed V-cycle over plain pointers"""
+    import emu_device
+    from test_gpu_mg import slab_case, slabs_in_one_process
+    kw, rhs = slab_case(kind)
+    with emu_device.emulated_device():
+        full, cyc, one, cyc1 = slabs_in_one_process(size, n, split, kw, rhs)
+    assert cyc == cyc1 and np.array_equal(full, one)
