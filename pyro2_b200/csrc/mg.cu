@@ -40,7 +40,6 @@ struct p2b_mg {
     int ord;                                  // ordinal of the last pushing launch of the running program
     int last_push[pyro::MG_MAX_LEVELS][4];    // ordinal of the launch that last filled the neighbours' halo rows of
                                               // (level, plane) in the running program; -1: delivered before it began
-    double source_norm, rtol; int max_cycles, stop_enabled;   // the device-side stopping rule of solve()
     // variable-coefficient mode (VarCoeffCCMG2d): per level the cell-centred eta and the two edge planes
     int varcoef;
     double *cc[pyro::MG_MAX_LEVELS], *ex[pyro::MG_MAX_LEVELS], *ey[pyro::MG_MAX_LEVELS];
@@ -774,11 +773,8 @@ int p2b_mg_cycle_diagnostics(p2b_mg* m, double* old_phi, double* out, void* stre
         P2B_LAUNCH(mg_vc_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, level_edges(m, lf), old_phi, m->partials);
     else
         P2B_LAUNCH(mg_diag_partial_kernel, blocks, RED_THREADS, 0, st)(L, old_phi, level_rcoef(m, L), m->partials);
-    MgStop stop;
-    stop.scale = L.dx * L.dy; stop.source_norm = m->source_norm; stop.rtol = m->rtol;
-    stop.max_cycles = m->max_cycles; stop.enabled = m->stop_enabled;
     P2B_LAUNCH(mg_diag_final_kernel, 1, RED_THREADS, 0, st)(m->partials, blocks, out, is_slab(m, lf) ? comm_base(m) : comm_none(),
-                                                             m->ctl, stop);
+                                                             m->ctl, L.dx * L.dy);
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
@@ -805,9 +801,8 @@ int p2b_mg_exchange(p2b_mg* m, int level, int which, int depth, void* stream)
 int p2b_mg_set_stop(p2b_mg* m, int enable, double source_norm, double rtol, int max_cycles, void* stream)
 {
     P2B_REQUIRE(m && m->base, "hierarchy not bound");
-    m->stop_enabled = enable; m->source_norm = source_norm; m->rtol = rtol; m->max_cycles = max_cycles;
-    P2B_CUDA_CHECK(cudaMemsetAsync(m->ctl + CW_STOP, 0, 8, (cudaStream_t)stream));
-    P2B_CUDA_CHECK(cudaMemsetAsync(m->ctl + CW_RESULT, 0, 4 * 8, (cudaStream_t)stream));
+    P2B_LAUNCH(mg_set_stop_kernel, 1, 1, 0, (cudaStream_t)stream)(m->ctl, source_norm, rtol, (double)max_cycles, enable ? 1.0 : 0.0);
+    P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
 

@@ -74,6 +74,8 @@ enum {
     CW_PEER = 24,        // [MG_MAX_RANKS] element offsets from my workspace to rank r's (host-written)
     CW_SUMS = 40,        // doubles [2][MG_MAX_RANKS][4]: all-reduce slots, double-buffered by epoch parity
     CW_RESULT = 168,     // doubles [4]: the last diagnostics (relsq, rsq, residual_error, cycles run)
+    CW_STOPPAR = 172,    // doubles [4]: the stopping rule (source_norm, rtol, max_cycles, enabled) -- in memory, not a
+                         // kernel argument: a captured cycle is replayed by later solve() calls with other values
     CW_WORDS = 176
 };
 
@@ -1090,12 +1092,19 @@ mg_diag_partial_kernel(MgLevel L, double* __restrict__ old_phi, ResidCoef rc, do
 
 // second stage of the per-cycle bookkeeping: sums over the rows (and over the ranks of a decomposed hierarchy), and the
 // stopping rule of solve() evaluated on the device (MG.py:654-697: while residual_error > rtol and cycle <= max_cycles):
-// stop.scale = dx * dy, stop.source_norm, stop.rtol as the host would use them -- same IEEE operations, same decision.
+// scale = dx * dy, source_norm and rtol as the host would use them -- same IEEE operations, same decision.
 // When the rule says stop, CW_STOP turns every kernel of a cycle that was enqueued ahead into a no-op, so the host can
 // enqueue cycles without waiting for each cycle's two scalars.  results: (relsq, rsq, residual_error, cycles run).
-struct MgStop { double scale, source_norm, rtol; int max_cycles, enabled; };
+__global__ void mg_set_stop_kernel(unsigned long long* ctl, double source_norm, double rtol, double max_cycles, double enabled)
+{
+    double* par = reinterpret_cast<double*>(ctl + CW_STOPPAR);
+    par[0] = source_norm; par[1] = rtol; par[2] = max_cycles; par[3] = enabled;
+    double* res = reinterpret_cast<double*>(ctl + CW_RESULT);
+    res[0] = res[1] = res[2] = res[3] = 0.0;
+    ctl[CW_STOP] = 0ull;
+}
 
-__global__ void mg_diag_final_kernel(const double* part, int npart, double* out, MgComm cm, unsigned long long* ctl, MgStop stop)
+__global__ void mg_diag_final_kernel(const double* part, int npart, double* out, MgComm cm, unsigned long long* ctl, double scale)
 {
     __shared__ double sh[RED_THREADS];
     if (ctl && ctl[CW_STOP]) return;
@@ -1106,13 +1115,14 @@ __global__ void mg_diag_final_kernel(const double* part, int npart, double* out,
     if (threadIdx.x == 0) {
         comm_allreduce2(cm, a, b, true);
         out[0] = a; out[1] = b;
-        if (ctl && stop.enabled) {
+        const double* par = reinterpret_cast<const double*>(ctl + CW_STOPPAR);
+        if (ctl && par[3] != 0.0) {
             double* res = reinterpret_cast<double*>(ctl + CW_RESULT);
-            const double rnorm = exact_sqrt(exact_mul(stop.scale, b));
-            const double err = stop.source_norm != 0.0 ? exact_div(rnorm, stop.source_norm) : rnorm;
+            const double rnorm = exact_sqrt(exact_mul(scale, b));
+            const double err = par[0] != 0.0 ? exact_div(rnorm, par[0]) : rnorm;
             const double ncyc = res[3] + 1.0;
             res[0] = a; res[1] = b; res[2] = err; res[3] = ncyc;
-            if (!(err > stop.rtol) || ncyc >= (double)stop.max_cycles) ctl[CW_STOP] = 1ull;
+            if (!(err > par[1]) || ncyc >= par[2]) ctl[CW_STOP] = 1ull;
         }
     }
 }

@@ -46,6 +46,12 @@ class EmuLibrary:
     def _counted(self, name, f):
         def call(*a):
             self.calls[name] = self.calls.get(name, 0) + 1
+            rec = getattr(_CAPTURE, "graph", None)
+            if rec is not None and name not in ("p2b_last_error", "p2b_mg_result"):
+                # stream capture: the launch is recorded with its argument VALUES (as a CUDA graph freezes kernel
+                # arguments) and runs only when the graph is replayed
+                rec.calls.append((f, a))
+                return 0
             return f(*a)
         return call
 
@@ -103,6 +109,34 @@ def _host_device(fn):
     return wrapped
 
 
+import threading
+_CAPTURE = threading.local()
+
+
+class EmuGraph:
+    """stand-in for torch.cuda.CUDAGraph on the emulated device: library calls made inside `with torch.cuda.graph(g)` are
+    recorded, not executed; g.replay() executes them with the recorded argument values.  Catches what a real graph
+    would: a replayed cycle that depends on a by-value argument which a later call meant to change."""
+
+    def __init__(self):
+        self.calls = []
+
+    def replay(self):
+        for f, a in self.calls:
+            rc = f(*a)
+            assert not rc, rc
+
+
+@contextlib.contextmanager
+def _emu_graph_capture(g, *a, **k):
+    assert getattr(_CAPTURE, "graph", None) is None
+    _CAPTURE.graph = g
+    try:
+        yield
+    finally:
+        _CAPTURE.graph = None
+
+
 def _host_tensor_from_pointer(ptr, nelem):
     """ops.tensor_from_pointer over host ("device") memory"""
     return torch.frombuffer((C.c_double * nelem).from_address(ptr), dtype=torch.float64)
@@ -130,7 +164,8 @@ def emulated_device():
                 (torch, "zeros", _host_device(torch.zeros)), (torch, "empty", _host_device(torch.empty)),
                 (torch, "as_tensor", _host_device(torch.as_tensor)),
                 (torch.Tensor, "to", to), (torch.Tensor, "cuda", lambda self, *a, **k: self),
-                (torch.cuda, "synchronize", lambda *a, **k: None)):
+                (torch.cuda, "synchronize", lambda *a, **k: None),
+                (torch.cuda, "CUDAGraph", EmuGraph), (torch.cuda, "graph", _emu_graph_capture)):
             st.enter_context(mock.patch.object(target, attr, new))
         st.enter_context(mock.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)))
         yield facade
