@@ -273,6 +273,99 @@ class Simulation(NullSimulation):
         self.n += 1
         tm_evolve.end()
 
+    # ---- host-resident state: one step with the copies pipelined against the sweep ------------------------------
+    def step_streamed(self, host_in, host_out, nchunks=16):
+        """One driver step (fill_BC_all -> compute_timestep -> evolve, pyro/pyro_sim.py:241-256) of a state that lives
+        in HOST memory: host_in -> device, step, device -> host_out (both pinned, shaped and strided like
+        cc_data.planes; the x ghost rows of host_in need not be current, host_out's valid rows are written).
+
+        The fused sweep consumes rows in order and needs only 4 rows of context, so the grid is cut into nchunks row
+        blocks: block c + 1 travels host -> device on one stream while block c is swept on the compute stream and block
+        c - 1 travels device -> host on a third: PCIe runs in both directions at once and the step costs about one
+        transfer of the state instead of two plus the sweep.  Every block is an x-slab of the domain exactly as in the
+        multi-GPU decomposition (interior block faces get the artificial viscosity, the global +x face does not --
+        SURVEY.md 9.2-13), so the result is bit-identical to single_step() on a resident state.
+
+        The time step needs max(|u| + cs) over the WHOLE incoming state before the first block can be swept.  When
+        host_in is the buffer the previous step_streamed() wrote, those maxima are the ones the previous sweep's
+        epilogue accumulated (same data, same bits as the stand-alone reduction); otherwise the state is copied in one
+        piece first and reduced on the device (no overlap for that step)."""
+        myd = self.cc_data
+        g = myd.grid
+        ng, nx, ny = g.ng, g.nx, g.ny
+        if (self.decomposition is not None and self.decomposition.size > 1) or getattr(self, "_spherical", False):
+            raise NotImplementedError("step_streamed: single-GPU Cartesian grids")
+        names = [myd.BCs[n].names() for n in myd.names]
+        if any(t in bnd.ext_bcs or t == "periodic" for b in names for t in b[:2]) or any(t in bnd.ext_bcs for b in names for t in b):
+            raise NotImplementedError("step_streamed: standard, non-periodic x boundaries")
+        dev = myd.planes
+        for h in (host_in, host_out):
+            assert h.shape == dev.shape and h.stride() == dev.stride() and h.dtype == dev.dtype and h.is_pinned()
+        if getattr(self, "_st_h2d", None) is None:
+            self._st_h2d, self._st_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            self._chunk_scratch = None
+        nchunks = max(1, min(int(nchunks), nx // (4 * ng)))      # a block is a grid of its own: >= 4 ng rows
+        if self._chunk_scratch is None or self._chunk_scratch.shape[0] != nchunks:
+            self._chunk_scratch = torch.zeros((nchunks, 8), dtype=torch.int64, device=dev.device)
+        bounds = [ng + (nx * c) // nchunks for c in range(nchunks + 1)]        # block c = rows bounds[c] .. bounds[c+1]-1
+        cur = torch.cuda.current_stream()
+        h2d_done = [torch.cuda.Event() for _ in range(nchunks)]
+        swept = [torch.cuda.Event() for _ in range(nchunks)]
+
+        known = getattr(self, "_streamed_out_ptr", None) == host_in.data_ptr() and self._wave_version == myd.version
+        self._st_h2d.wait_stream(cur)              # the device buffer may still be read by earlier work
+        with torch.cuda.stream(self._st_h2d):
+            for c in range(nchunks):
+                a, b = bounds[c], bounds[c + 1]
+                dev[:, a:b].copy_(host_in[:, a:b], non_blocking=True)
+                h2d_done[c].record()
+        if not known:
+            # the whole state first, then the ordinary ghost fill and CFL reduction
+            cur.wait_stream(self._st_h2d)
+            myd.version += 1
+            myd.fill_BC_all()
+        self.compute_timestep()
+        prm = self._comp_params()
+        out = self._alt_planes
+        self.clean_state(None)
+
+        def block_bcs(c):
+            # an x side of a block that faces another block is left alone (its rows arrive with that block)
+            return [(b[0] if c == 0 else None, b[1] if c == nchunks - 1 else None, b[2], b[3]) for b in names]
+
+        def fill_block(c):
+            # the block's own rows (plus the global x ghost rows for the first / last block) as a grid of its own whose
+            # outermost ng rows play the part of ghost rows: x sides that face another block are None (left alone),
+            # the y fill runs over exactly these rows
+            a, b = bounds[c], bounds[c + 1]
+            cur.wait_event(h2d_done[c])
+            lo = 0 if c == 0 else a
+            hi = g.qx if c == nchunks - 1 else b
+            ops.fill_ghost(dev[:, lo:hi], hi - lo - 2 * ng, ny, ng, block_bcs(c))
+
+        if known:
+            fill_block(0)
+        for c in range(nchunks):
+            a, b = bounds[c], bounds[c + 1]
+            if known and c + 1 < nchunks:
+                fill_block(c + 1)                   # block c reads 4 rows of block c + 1
+            prm.no_avisc_xhi = 1 if c == nchunks - 1 else 0
+            ops.compressible_sweep(dev[:, a - ng:b + ng], out[:, a - ng:b + ng], b - a, ny, ng, g.dx, g.dy, float(self.dt),
+                                   prm, self._chunk_scratch[c])
+            swept[c].record()
+            with torch.cuda.stream(self._st_d2h):
+                self._st_d2h.wait_event(swept[c])
+                host_out[:, a:b].copy_(out[:, a:b], non_blocking=True)
+        # maxima and status of the whole grid from the blocks' (positive doubles order like their bit patterns)
+        self._scratch[:4] = self._chunk_scratch[:, :4].max(dim=0).values
+        cur.wait_stream(self._st_d2h)               # the step is complete when its result is on the host
+        myd.planes, self._alt_planes = self._alt_planes, myd.planes
+        self._wave_version = myd.version
+        self._pending_status = True
+        self._streamed_out_ptr = host_out.data_ptr()
+        myd.t += self.dt
+        self.n += 1
+
     def clean_state(self, U):   # pylint: disable=unused-argument
         """density floor (simulation.py:452-456); a no-op for the default small_dens = -1e200"""
         small = self.rp.get_param("compressible.small_dens")

@@ -16,6 +16,8 @@
 //
 // Ghost cells (ng = 1) are kept consistent by the thread that updates the interior source cell of
 // each ghost ("fused fill_BC"), so a half-sweep is one launch.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mg_kernels.cuh"
 
@@ -165,6 +167,36 @@ static void exchange_impl(p2b_mg* m, int level, double* plane, int depth, cudaSt
     P2B_EMU_THREADED(false);
 }
 
+// which geometry of the blocked pass a level uses (mg_kernels.cuh, tb_cfg): the throughput geometry when its grid
+// gives the chip at least two waves, otherwise the short-chain one.  P2B_TB_CFG=<k> forces one (A/B timing).
+static int tb_choose(const p2b_mg* m, const MgLevel& L)
+{
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("P2B_TB_CFG");
+        forced = e ? atoi(e) : -1;
+        if (forced >= TB_NCFG) forced = -1;
+    }
+    if (forced >= 0) return forced;
+    (void)m;
+    const TbCfg big = tb_cfg(0);
+    const long long ctas = (long long)((L.n + TB_TJ - 1) / TB_TJ) * ((L.ni + big.TI - 1) / big.TI);
+    return ctas >= 2LL * num_sms() ? 0 : 1;
+}
+
+static void tb_launch(int cfg, dim3 grd, cudaStream_t st, const MgLevel& L, const double* src, double* dst, const MgBC& b,
+                      const SmoothCoef& c, int niter, const MgComm& cm)
+{
+    auto k0 = mg_smooth_tb_kernel_t<8, 16, 1>;
+    auto k1 = mg_smooth_tb_kernel_t<4, 16, 2>;
+    auto k2 = mg_smooth_tb_kernel_t<8, 8, 2>;
+    switch (cfg) {
+        case 1: P2B_LAUNCH(k1, grd, 512, 0, st)(L, src, dst, b, c, niter, cm); break;
+        case 2: P2B_LAUNCH(k2, grd, 256, 0, st)(L, src, dst, b, c, niter, cm); break;
+        default: P2B_LAUNCH(k0, grd, 512, 0, st)(L, src, dst, b, c, niter, cm); break;
+    }
+}
+
 constexpr int MG_SMALL_N = 64;   // levels up to 64^2 are smoothed by one CTA in one launch
 constexpr int MG_TB_MIN_N = 128;  // from here up the temporally blocked kernel is used
 
@@ -219,14 +251,15 @@ static int smooth_impl(p2b_mg* m, int level, int nsmooth, bool fill_first, cudaS
     } else if (L.n >= MG_TB_MIN_N && !m->no_blocking) {
         // passes of up to TB_K iterations, ping-ponging v <-> w; the blocked kernel derives ghost
         // values from interior cells itself, so no separate fill_BC is needed before it
-        dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.n + TB_TI - 1) / TB_TI);
+        const int cfg = tb_choose(m, L);
+        dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.n + tb_cfg(cfg).TI - 1) / tb_cfg(cfg).TI);
         const double* src = L.v;
         double* dst = L.w;
         int left = nsmooth;
         if (left == 0 && fill_first) P2B_LAUNCH(mg_fill_kernel, (4 * L.n + 255) / 256, 256, 0, st)(L, b);
         while (left > 0) {
             int it = left < TB_K ? left : TB_K;
-            P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, src, dst, b, c, it, comm_none());
+            tb_launch(cfg, grd, st, L, src, dst, b, c, it, comm_none());
             left -= it;
             const double* t = src; src = dst; dst = const_cast<double*>(t);
         }
@@ -255,19 +288,21 @@ static int imax(int a, int b) { return a > b ? a : b; }
 static void tb_pass_impl(p2b_mg* m, int level, int src, int dst, int niter, cudaStream_t st)
 {
     const MgLevel& L = m->lev[level];
-    dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.ni + TB_TI - 1) / TB_TI);
+    const int cfg = tb_choose(m, L);
+    const int TI = tb_cfg(cfg).TI;
+    dim3 grd((L.n + TB_TJ - 1) / TB_TJ, (L.ni + TI - 1) / TI);
     MgComm c = comm_none();
     if (is_slab(m, level)) {
         c = comm_base(m);
         c.wait_ord = imax(m->last_push[level][src], m->last_push[level][1]);
         c.sig_ord = ++m->ord;
-        c.n_lo = (int)grd.x;                                                       // tile row 0 holds rows 1..TB_H
-        c.n_hi = (int)grd.x * ((L.ni - 1) / TB_TI - (L.ni - TB_H) / TB_TI + 1);     // tile rows meeting ni-TB_H+1..ni
+        c.n_lo = (int)grd.x;                                                 // tile row 0 holds rows 1..TB_H (TI >= TB_H)
+        c.n_hi = (int)grd.x * ((L.ni - 1) / TI - (L.ni - TB_H) / TI + 1);     // tile rows meeting ni-TB_H+1..ni
         m->last_push[level][dst] = c.sig_ord;
     }
     const double* sp = src == 0 ? L.v : L.w;
     double* dp = dst == 0 ? L.v : L.w;
-    P2B_LAUNCH(mg_smooth_tb_kernel, grd, 32 * TB_NW, 0, st)(L, sp, dp, level_bc(m, level), level_coef(m, L), niter, c);
+    tb_launch(cfg, grd, st, L, sp, dp, level_bc(m, level), level_coef(m, L), niter, c);
 }
 
 // nsmooth red-black iterations on a slab level: passes of <= TB_K iterations, halo rows travelling in the passes' own
@@ -406,7 +441,8 @@ static void vcycle_impl(p2b_mg* m, int level, cudaStream_t st)
         smooth_slab_impl(m, level, m->nsmooth, st);
         return;
     }
-    if (!m->no_blocking && level <= coarse_top(m)) {
+    static const bool no_fused_coarse = getenv("P2B_MG_NO_FUSED_COARSE") != nullptr;     // A/B switch (development)
+    if (!m->no_blocking && !no_fused_coarse && level <= coarse_top(m)) {
         coarse_vcycle_impl(m, level, st);
         return;
     }
@@ -438,6 +474,35 @@ using namespace pyro;
 
 extern "C" {
 
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2): the FIRST launch of a kernel loads it,
+// and loading synchronises with the kernels running on the device.  A rank's kernel that spins on a flag another rank's
+// not-yet-loaded kernel will raise then never sees it: the load waits for the spin, the spin for the load (observed with
+// two slabs on one GPU: the first all-reduce timed out whenever the diagnostics kernels had not run before).  Loading
+// every kernel of this translation unit when the first hierarchy is created removes the hazard.
+static void preload_kernels()
+{
+#ifndef P2B_EMU_HEADER
+    static bool done = false;
+    if (done) return;
+    done = true;
+    cudaFuncAttributes a;
+#define P2B_PRELOAD(k) cudaFuncGetAttributes(&a, k)
+    P2B_PRELOAD(mg_halfsweep_kernel); P2B_PRELOAD(mg_smooth_small_kernel); P2B_PRELOAD(mg_fill_kernel);
+    P2B_PRELOAD((mg_smooth_tb_kernel_t<8, 16, 1>)); P2B_PRELOAD((mg_smooth_tb_kernel_t<4, 16, 2>));
+    P2B_PRELOAD((mg_smooth_tb_kernel_t<8, 8, 2>)); P2B_PRELOAD(mg_vc_smooth_tb_kernel);
+    P2B_PRELOAD(mg_coarse_vcycle_kernel<false>); P2B_PRELOAD(mg_coarse_vcycle_kernel<true>);
+    P2B_PRELOAD(mg_residual_kernel); P2B_PRELOAD(mg_restrict_kernel); P2B_PRELOAD(mg_prolong_kernel);
+    P2B_PRELOAD(mg_sumsq_partial_kernel); P2B_PRELOAD(mg_sumsq_final_kernel); P2B_PRELOAD(mg_zero_kernel);
+    P2B_PRELOAD(mg_diag_partial_kernel); P2B_PRELOAD(mg_diag_final_kernel); P2B_PRELOAD(mg_set_stop_kernel);
+    P2B_PRELOAD(mg_epoch_kernel); P2B_PRELOAD(mg_comm_wait_kernel); P2B_PRELOAD(mg_xchg_arrive_kernel);
+    P2B_PRELOAD(mg_xchg_push_kernel); P2B_PRELOAD(mg_cn_rhs_kernel);
+    P2B_PRELOAD(mg_vc_halfsweep_kernel); P2B_PRELOAD(mg_vc_smooth_small_kernel); P2B_PRELOAD(mg_vc_residual_kernel);
+    P2B_PRELOAD(mg_vc_diag_partial_kernel); P2B_PRELOAD(mg_vc_edges_fine_kernel); P2B_PRELOAD(mg_vc_edges_restrict_kernel);
+#undef P2B_PRELOAD
+    cudaGetLastError();
+#endif
+}
+
 static p2b_mg* mg_create_impl(int nx, const int* bc, double alpha, double beta, double xmin, double xmax,
                               double ymin, double ymax, int nsmooth, int nsmooth_bottom, int rank, int size,
                               int split_n)
@@ -448,6 +513,7 @@ static p2b_mg* mg_create_impl(int nx, const int* bc, double alpha, double beta, 
         set_error("slab count must be a power of two <= %d", MG_MAX_RANKS);
         return nullptr;
     }
+    preload_kernels();
     p2b_mg* m = new p2b_mg();
     memset(m, 0, sizeof *m);
     int nl = 0;

@@ -435,13 +435,17 @@ constexpr int TB_EYS = 2 * TB_RH * 33;             // doubles in the eta_y tile
 // INHOM = false: no side carries inhomogeneous boundary values (every level but the finest, and the finest of most
 // callers): the ghost a cell generates is +-(its own value) and none of the index arithmetic for the value tables is
 // compiled in.  cm: slab communication of this launch (cm.ctl == NULL: none).
-template <bool EDGE, bool VC, bool INHOM>
+// R / NW: rows per thread and warps per CTA of this instantiation (region R * NW rows x 64 columns).  The constants of
+// the default geometry are shadowed inside the body, which is otherwise written in terms of TB_R, TB_NW, TB_RH, TB_TI.
+template <bool EDGE, bool VC, bool INHOM, int R = 8, int NW = TB_NW_CFG>
 __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
                                                double* __restrict__ vout, const MgBC& bb, const SmoothCoef& c,
-                                               int niter, double (*edge)[TB_NW][2][TB_RW],
+                                               int niter, double (*edge)[NW][2][TB_RW],
                                                const VcEdges& E, double* __restrict__ exs, double* __restrict__ eys,
                                                const MgComm& cm)
 {
+    constexpr int TB_R = R, TB_NW = NW, TB_RH = R * NW, TB_TI = TB_RH - 2 * TB_H;
+    static_assert(TB_TI % 2 == 0 && TB_TI > 0 && R % 2 == 0 && (!VC || (R == 8 && NW == TB_NW_CFG)), "tile geometry");
     MgBC b = bb;
     if (!INHOM) { b.xlv = nullptr; b.xrv = nullptr; b.ylv = nullptr; b.yrv = nullptr; }
     const int n = L.n, ni = L.ni, P = L.pitch;
@@ -638,23 +642,41 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     if (EDGE) comm_block_signal(cm, I0 <= TB_H, I0 + TB_TI - 1 > ni - TB_H && I0 <= ni);
 }
 
-__global__ void __launch_bounds__(32 * TB_NW, (TB_NW <= 8 ? 2 : 1))
-mg_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
-                    SmoothCoef c, int niter, MgComm cm)
+// Geometries of the constant-coefficient pass.  The per-CTA time of a pass is set by its serial chain (load, 10
+// half-sweeps with a CTA barrier each, store), not by the SM's throughput, so:
+//   cfg 0  R = 8, 16 warps: 128 x 64 region, 108 x 44 tile (58% useful), 1 CTA / SM  -- big grids (many waves)
+//   cfg 1  R = 4, 16 warps:  64 x 64 region,  44 x 44 tile, <= 64 registers, 2 CTAs / SM: half the chain per thread and
+//          twice the CTAs -- levels whose cfg-0 grid does not fill the chip (128^2 .. 1024^2, thin slabs)
+//   cfg 2  R = 8,  8 warps:  64 x 64 region,  44 x 44 tile, 2 CTAs / SM
+template <int R, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+mg_smooth_tb_kernel_t(MgLevel L, const double* __restrict__ vin, double* __restrict__ vout, MgBC b,
+                      SmoothCoef c, int niter, MgComm cm)
 {
-    __shared__ __align__(16) double edge[2][TB_NW][2][TB_RW];   // [buffer][warp][first/last row][column]
+    constexpr int RH = R * NW, TI = RH - 2 * TB_H;
+    __shared__ __align__(16) double edge[2][NW][2][TB_RW];   // [buffer][warp][first/last row][column]
     if (L.ctl && L.ctl[CW_STOP]) return;
-    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int I0 = 1 + blockIdx.y * TI, J0 = 1 + blockIdx.x * TB_TJ;
     // the branch-free interior path needs the whole region strictly inside the rank's OWNED rows: a region that
     // reaches into halo rows waits for them and one that holds the first / last owned rows pushes them (EDGE path)
-    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + TB_RH - 1 <= L.ni) &&
+    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + RH - 1 <= L.ni) &&
                           (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n) &&
-                          (!cm.ctl || (I0 > TB_H && I0 + TB_TI - 1 <= L.ni - TB_H));
+                          (!cm.ctl || (I0 > TB_H && I0 + TI - 1 <= L.ni - TB_H));
     const VcEdges none = {nullptr, nullptr};
     const bool inhom = b.xlv || b.xrv || b.ylv || b.yrv;
-    if (interior) smooth_tb_body<false, false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
-    else if (inhom) smooth_tb_body<true, false, true>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
-    else smooth_tb_body<true, false, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    if (interior) smooth_tb_body<false, false, false, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    else if (inhom) smooth_tb_body<true, false, true, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    else smooth_tb_body<true, false, false, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+}
+
+struct TbCfg { int R, NW, TI, threads; };
+constexpr int TB_NCFG = 3;
+inline TbCfg tb_cfg(int k)
+{
+    const int R[TB_NCFG] = {8, 4, 8}, NW[TB_NCFG] = {16, 16, 8};
+    TbCfg c;
+    c.R = R[k]; c.NW = NW[k]; c.TI = R[k] * NW[k] - 2 * TB_H; c.threads = 32 * NW[k];
+    return c;
 }
 
 // the same pass with the variable-coefficient stencil; dynamic shared memory: the row-exchange buffers
@@ -713,138 +735,281 @@ struct CoarseTable {
                                         // read-only and L1-resident; indexed with the GLOBAL pitch g[l].pitch)
 };
 
-template <bool VC>
-__device__ __forceinline__ void cta_smooth(const MgLevel& L, const MgBC& b, const SmoothCoef& c, int nsmooth,
-                                           const VcEdges& E, int gpitch)
-{
-    const int n = L.n, half = n >> 1, npts = n * half;
-    const int ls = __ffs(n) - 1, hs = ls - 1;   // n and half are powers of two: shifts instead of divisions
-    // fill_BC("v") at the start of smooth() (MG.py:565)
-    for (int t = threadIdx.x; t < 4 * n; t += blockDim.x) {
-        int side = t >> ls, q = (t & (n - 1)) + 1;
-        int i = side == 0 ? 1 : side == 1 ? n : q;
-        int j = side == 2 ? 1 : side == 3 ? n : q;
-        store_with_ghosts(L.v, n, n, L.pitch, i, j, L.v[(long long)i * L.pitch + j], b, L.dx, L.dy);
-    }
-    __syncthreads();
-    for (int it = 0; it < 2 * nsmooth; ++it) {
-        const int colour = it & 1;
-        for (int t = threadIdx.x; t < npts; t += blockDim.x) {
-            int i = (t >> hs) + 1, k = t & (half - 1);
-            int j = 1 + ((i + 1 + colour) & 1) + 2 * k;
-            double val;
-            if (VC) {
-                const long long ks = (long long)i * L.pitch + j, kg = (long long)i * gpitch + j;
-                val = vc_gs_value(L.f[ks], L.v[ks - L.pitch], L.v[ks + L.pitch], L.v[ks - 1], L.v[ks + 1],
-                                  E.ex[kg], E.ex[kg + gpitch], E.ey[kg], E.ey[kg + 1]);
-            } else {
-                val = gs_update(L.v, L.f, L.pitch, i, j, c);
-            }
-            store_with_ghosts(L.v, n, n, L.pitch, i, j, val, b, L.dx, L.dy);
-        }
-        __syncthreads();
-    }
-}
-
-
+// Shared-memory geometry of coarse level L, known at compile time: n = 2^(L+1) cells per side, q = n + 2 rows of q
+// doubles, planes v, f, r back to back, levels packed from the coarsest up.  (The first version kept an MgLevel array
+// indexed with the run-time level in LOCAL memory and ran every level, the 2 x 2 bottom solve included, on 1024
+// threads with a CTA barrier per colour: 280 us for the sub-cycle below 128^2, 70 us of it the bottom solve alone.)
 #ifndef MG_COARSE_THREADS
 #define MG_COARSE_THREADS 1024
 #endif
 
+template <int L> struct CoarseGeom {
+    static constexpr int n = 2 << L, q = n + 2, plane = q * q;
+    static constexpr int base = CoarseGeom<L - 1>::base + 3 * CoarseGeom<L - 1>::plane;
+};
+template <> struct CoarseGeom<0> { static constexpr int n = 2, q = 4, plane = 16, base = 0; };
+// A level is run by as many warps as it has points of one colour (one point per thread, two at 64^2), the others skip
+// it: a warp that runs alone issues one instruction every 5-8 cycles, so the cost of a colour is the length of ONE point's
+// instruction chain plus the barrier -- both kept short: the thread's two points (one per colour), their addresses,
+// right-hand sides and boundary flags are fixed for the whole smooth(), and the barrier spans only the level's warps
+// (bar.sync with a thread count; __syncwarp when one warp suffices).
+template <int L> struct CoarseWarps {
+    static constexpr int pts = CoarseGeom<L>::n * CoarseGeom<L>::n / 2;
+    static constexpr int warps = pts <= 32 ? 1 : (pts / 32 > MG_COARSE_THREADS / 32 ? MG_COARSE_THREADS / 32 : pts / 32);
+};
+
+__device__ __forceinline__ void named_barrier(int id, int nthreads)
+{
+#ifdef P2B_EMU_HEADER
+    emu_bar_sync(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
+template <int L> __device__ __forceinline__ void coarse_sync()
+{
+    if (CoarseWarps<L>::warps == 1) __syncwarp();
+    else named_barrier(1 + L, 32 * CoarseWarps<L>::warps);
+}
+
+template <int L> __device__ __forceinline__ MgLevel coarse_level_view(const CoarseTable& T, double* sm)
+{
+    using G = CoarseGeom<L>;
+    MgLevel S = T.g[L];
+    S.pitch = G::q;
+    S.v = sm + G::base; S.f = S.v + G::plane; S.r = S.f + G::plane;
+    return S;
+}
+
+// A point of a level and the ghost cells it generates, worked out once per smooth(): store_with_ghosts() is a dozen
+// data-dependent branches, and a warp running on its own pays 10-20 cycles for each of them (measured: 1300 cycles per
+// colour of the 2 x 2 bottom solve, all in that function).  Without inhomogeneous boundary values a ghost is +-(the
+// cell's value), so a point has at most an x ghost, a y ghost and their corner, each a fixed offset and sign:
+//   k: offset of the cell; ox / oy / oc: offsets of the x ghost, y ghost, corner (-1: none);
+//   mx / my: XOR masks for the sign word of the x / y ghost (reflect-odd / homogeneous dirichlet negate)
+struct CoarsePt { int k, ox, oy, oc; unsigned mx, my; };
+
+__device__ __forceinline__ CoarsePt coarse_point(int n, int P, int i, int j, const MgBC& b)
+{
+    CoarsePt p;
+    p.k = i * P + j;
+    p.ox = p.oy = p.oc = -1;
+    p.mx = p.my = 0u;
+    const int sxl = (b.xl == P2B_BC_PERIODIC) ? n : 1, sxh = (b.xr == P2B_BC_PERIODIC) ? 1 : n;
+    const int syl = (b.yl == P2B_BC_PERIODIC) ? n : 1, syh = (b.yr == P2B_BC_PERIODIC) ? 1 : n;
+    int gi = -1, gj = -1;                                 // ghost row / column this cell feeds
+    if (i == sxl) { gi = 0; p.mx = (b.xl == P2B_BC_REFLECT_ODD) ? 0x80000000u : 0u; }
+    else if (i == sxh) { gi = n + 1; p.mx = (b.xr == P2B_BC_REFLECT_ODD) ? 0x80000000u : 0u; }
+    if (j == syl) { gj = 0; p.my = (b.yl == P2B_BC_REFLECT_ODD) ? 0x80000000u : 0u; }
+    else if (j == syh) { gj = n + 1; p.my = (b.yr == P2B_BC_REFLECT_ODD) ? 0x80000000u : 0u; }
+    if (gi >= 0) p.ox = gi * P + j;
+    if (gj >= 0) p.oy = i * P + gj;
+    if (gi >= 0 && gj >= 0) p.oc = gi * P + gj;
+    return p;
+}
+
+__device__ __forceinline__ double flip_sign(double x, unsigned mask)
+{
+#ifdef P2B_EMU_HEADER
+    unsigned long long bits;
+    memcpy(&bits, &x, 8);
+    bits ^= (unsigned long long)mask << 32;
+    memcpy(&x, &bits, 8);
+    return x;
+#else
+    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+#endif
+}
+
+__device__ __forceinline__ void coarse_store(double* v, const CoarsePt& p, double val)
+{
+    v[p.k] = val;
+    if (p.ox >= 0) v[p.ox] = flip_sign(val, p.mx);
+    if (p.oy >= 0) {
+        v[p.oy] = flip_sign(val, p.my);
+        if (p.oc >= 0) v[p.oc] = flip_sign(val, p.mx ^ p.my);
+    }
+}
+
+// smooth() of one level in shared memory (MG.py:544-599): fill_BC, then nsmooth red-black iterations with the ghost
+// update fused into the writers.  t: this thread's index among the nt = 32 * CoarseWarps<L>::warps threads of the level.
+template <bool VC, int L>
+__device__ __forceinline__ void coarse_smooth(const MgLevel& S, const MgBC& b, const SmoothCoef& c, int nsmooth,
+                                              const VcEdges& E, int gpitch, int t)
+{
+    constexpr int n = CoarseGeom<L>::n, half = n / 2, npts = n * half, P = CoarseGeom<L>::q;
+    constexpr int nt = 32 * CoarseWarps<L>::warps, PER = (npts + nt - 1) / nt;      // points per thread and colour: 1 or 2
+    // inhomogeneous boundary values (only when this level is the finest of the hierarchy): the general writer
+    const bool inhom = b.xlv || b.xrv || b.ylv || b.yrv;
+    for (int u = t; u < 4 * n; u += nt) {
+        const int side = u / n, q = u % n + 1;
+        const int i = side == 0 ? 1 : side == 1 ? n : q;
+        const int j = side == 2 ? 1 : side == 3 ? n : q;
+        if (inhom) store_with_ghosts(S.v, n, n, P, i, j, S.v[i * P + j], b, S.dx, S.dy);
+        else coarse_store(S.v, coarse_point(n, P, i, j, b), S.v[i * P + j]);
+    }
+    // this thread's points: index u = t + p * nt -> row i, the k-th point of the colour in that row
+    CoarsePt pt[PER][2];
+    double ff[PER][2];
+    bool act[PER];
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        const int u = t + p * nt;
+        act[p] = u < npts;
+        const int i = (act[p] ? u : 0) / half + 1, k = (act[p] ? u : 0) % half;
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+            const int j = 1 + ((i + 1 + col) & 1) + 2 * k;
+            pt[p][col] = coarse_point(n, P, i, j, b);
+            ff[p][col] = S.f[pt[p][col].k];
+        }
+    }
+    coarse_sync<L>();
+    for (int it = 0; it < nsmooth; ++it) {
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                if (!act[p]) continue;
+                const int k = pt[p][col].k;
+                const double* v = S.v;
+                double val;
+                if (VC) {
+                    const int i = k / P, j = k % P;
+                    const long long kg = (long long)i * gpitch + j;
+                    val = vc_gs_value(ff[p][col], v[k - P], v[k + P], v[k - 1], v[k + 1],
+                                      E.ex[kg], E.ex[kg + gpitch], E.ey[kg], E.ey[kg + 1]);
+                } else {
+                    // MG.py:593-596, the operations of gs_update()
+                    const double sx = exact_add(v[k + P], v[k - P]);
+                    const double sy = exact_add(v[k + 1], v[k - 1]);
+                    const double num = exact_add(exact_add(ff[p][col], exact_mul(c.xc, sx)), exact_mul(c.yc, sy));
+                    val = div_by_denom(num, c);
+                }
+                if (inhom) store_with_ghosts(S.v, n, n, P, k / P, k % P, val, b, S.dx, S.dy);
+                else coarse_store(S.v, pt[p][col], val);
+            }
+            coarse_sync<L>();
+        }
+    }
+}
+
+// the sub-V-cycle from level L down and back (MG.py:699-778) on shared-memory planes; entered by the first
+// CoarseWarps<L>::warps warps of the CTA only
+template <bool VC, int L>
+__device__ void coarse_cycle(const CoarseTable& T, double* sm, int tid)
+{
+    const MgBC& b = (L == T.top) ? T.bc_top : T.bc_coarse;
+    MgLevel S = coarse_level_view<L>(T, sm);
+    if (L == 0) {
+        coarse_smooth<VC, L>(S, b, T.coef[L], T.nsmooth_bottom, T.edges[L], T.g[L].pitch, tid);
+        return;
+    }
+    constexpr int LC = L > 0 ? L - 1 : 0;
+    constexpr int n = CoarseGeom<L>::n, P = CoarseGeom<L>::q, nc = CoarseGeom<LC>::n, Pc = CoarseGeom<LC>::q;
+    constexpr int nt = 32 * CoarseWarps<L>::warps;
+    MgLevel C = coarse_level_view<LC>(T, sm);
+    coarse_smooth<VC, L>(S, b, T.coef[L], T.nsmooth, T.edges[L], T.g[L].pitch, tid);
+    for (int t = tid; t < n * n; t += nt) {
+        const int i = t / n + 1, j = t % n + 1, k = i * P + j;
+        if (VC) {
+            const int Pg = T.g[L].pitch;
+            const long long kg = (long long)i * Pg + j;
+            const double* v = S.v;
+            S.r[k] = vc_residual_value(S.f[k], v[k], v[k - P], v[k + P], v[k - 1], v[k + 1],
+                                       T.edges[L].ex[kg], T.edges[L].ex[kg + Pg], T.edges[L].ey[kg], T.edges[L].ey[kg + 1]);
+        } else {
+            S.r[k] = residual_at(S, k, T.rcoef[L]);
+        }
+    }
+    coarse_sync<L>();
+    for (int t = tid; t < nc * nc; t += nt) {
+        const int ic = t / nc + 1, jc = t % nc + 1;
+        const double* r = S.r;
+        const int k = (2 * ic - 1) * P + (2 * jc - 1);
+        double sum = exact_add(exact_add(exact_add(r[k], r[k + P]), r[k + 1]), r[k + P + 1]);
+        C.f[ic * Pc + jc] = exact_mul(0.25, sum);
+    }
+    coarse_sync<L>();
+    if (tid < 32 * CoarseWarps<LC>::warps) coarse_cycle<VC, LC>(T, sm, tid);
+    coarse_sync<L>();
+    for (int t = tid; t < nc * nc; t += nt) {
+        const int ic = t / nc + 1, jc = t % nc + 1;
+        const double* c = C.v;
+        const int kc = ic * Pc + jc;
+        double mx = exact_mul(0.5, exact_sub(c[kc + Pc], c[kc - Pc]));
+        double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
+        double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my), c0 = c[kc];
+        const int i = 2 * ic - 1, j = 2 * jc - 1;
+        double* v = S.v;
+        const double n00 = exact_add(v[i * P + j], exact_sub(exact_sub(c0, qx), qy));
+        const double n10 = exact_add(v[(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy));
+        const double n01 = exact_add(v[i * P + j + 1], exact_add(exact_sub(c0, qx), qy));
+        const double n11 = exact_add(v[(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy));
+        if (b.xlv || b.xrv || b.ylv || b.yrv) {
+            store_with_ghosts(v, n, n, P, i, j, n00, b, S.dx, S.dy);
+            store_with_ghosts(v, n, n, P, i + 1, j, n10, b, S.dx, S.dy);
+            store_with_ghosts(v, n, n, P, i, j + 1, n01, b, S.dx, S.dy);
+            store_with_ghosts(v, n, n, P, i + 1, j + 1, n11, b, S.dx, S.dy);
+        } else if (ic == 1 || ic == nc || jc == 1 || jc == nc) {
+            coarse_store(v, coarse_point(n, P, i, j, b), n00);
+            coarse_store(v, coarse_point(n, P, i + 1, j, b), n10);
+            coarse_store(v, coarse_point(n, P, i, j + 1, b), n01);
+            coarse_store(v, coarse_point(n, P, i + 1, j + 1, b), n11);
+        } else {
+            v[i * P + j] = n00; v[(i + 1) * P + j] = n10; v[i * P + j + 1] = n01; v[(i + 1) * P + j + 1] = n11;
+        }
+    }
+    coarse_sync<L>();
+    coarse_smooth<VC, L>(S, b, T.coef[L], T.nsmooth, T.edges[L], T.g[L].pitch, tid);
+}
+
+// global <-> shared copy of one level's planes (all threads): load v and f of the top level (v is the current iterate
+// there) and zero below it (MG.py:658-659); store v, f, r of every level back (coarse planes stay observable through
+// grids[level], like the reference's)
+template <int L>
+__device__ __forceinline__ void coarse_io(const CoarseTable& T, double* sm, bool load, int tid, int nthreads)
+{
+    using G = CoarseGeom<L>;
+    if (L > T.top) return;
+    double* v = sm + G::base;
+    double* f = v + G::plane;
+    double* r = f + G::plane;
+    const MgLevel& g = T.g[L];
+    for (int t = tid; t < G::plane; t += nthreads) {
+        const int i = t / G::q, j = t % G::q;
+        const long long kg = (long long)i * g.pitch + j;
+        if (load) {
+            v[t] = (L == T.top) ? g.v[kg] : 0.0;
+            f[t] = (L == T.top) ? g.f[kg] : 0.0;
+            r[t] = g.r[kg];
+        } else {
+            g.v[kg] = v[t]; g.f[kg] = f[t]; g.r[kg] = r[t];
+        }
+    }
+}
+
 template <bool VC>
-__global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(CoarseTable T)
+__global__ void __launch_bounds__(MG_COARSE_THREADS, 1) mg_coarse_vcycle_kernel(const __grid_constant__ CoarseTable T)
 {
     P2B_DYN_SMEM(double, sm);
     if (T.g[0].ctl && T.g[0].ctl[CW_STOP]) return;
-    MgLevel S[MG_COARSE_LEVELS];
-    {
-        double* p = sm;
-        for (int l = 0; l <= T.top; ++l) {
-            S[l] = T.g[l];
-            const int q = S[l].n + 2;
-            S[l].pitch = (q + 1) & ~1;
-            const long long plane = (long long)q * S[l].pitch;
-            S[l].v = p; p += plane;
-            S[l].f = p; p += plane;
-            S[l].r = p; p += plane;
-        }
-    }
-    // load: v and f of the top level come from global (v is the current iterate there: zero on a
-    // coarse top level, the solution when the top level is the finest); everything below starts at 0
-    for (int l = 0; l <= T.top; ++l) {
-        const int q = S[l].n + 2;
-        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
-            int i = t / q, j = t % q;
-            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
-            S[l].v[ks] = (l == T.top) ? T.g[l].v[kg] : 0.0;
-            S[l].f[ks] = (l == T.top) ? T.g[l].f[kg] : 0.0;
-            S[l].r[ks] = T.g[l].r[kg];
-        }
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    coarse_io<0>(T, sm, true, tid, nthreads); coarse_io<1>(T, sm, true, tid, nthreads); coarse_io<2>(T, sm, true, tid, nthreads);
+    coarse_io<3>(T, sm, true, tid, nthreads); coarse_io<4>(T, sm, true, tid, nthreads); coarse_io<5>(T, sm, true, tid, nthreads);
+    __syncthreads();
+    switch (T.top) {
+        case 5: if (tid < 32 * CoarseWarps<5>::warps) coarse_cycle<VC, 5>(T, sm, tid); break;
+        case 4: if (tid < 32 * CoarseWarps<4>::warps) coarse_cycle<VC, 4>(T, sm, tid); break;
+        case 3: if (tid < 32 * CoarseWarps<3>::warps) coarse_cycle<VC, 3>(T, sm, tid); break;
+        case 2: if (tid < 32 * CoarseWarps<2>::warps) coarse_cycle<VC, 2>(T, sm, tid); break;
+        case 1: if (tid < 32 * CoarseWarps<1>::warps) coarse_cycle<VC, 1>(T, sm, tid); break;
+        default: if (tid < 32 * CoarseWarps<0>::warps) coarse_cycle<VC, 0>(T, sm, tid); break;
     }
     __syncthreads();
-
-    for (int l = T.top; l >= 1; --l) {
-        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
-        cta_smooth<VC>(S[l], b, T.coef[l], T.nsmooth, T.edges[l], T.g[l].pitch);
-        const int n = S[l].n;
-        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-            const int i = t / n + 1, j = t % n + 1;
-            long long k = (long long)i * S[l].pitch + j;
-            if (VC) {
-                const int P = S[l].pitch, Pg = T.g[l].pitch;
-                const long long kg = (long long)i * Pg + j;
-                const double* v = S[l].v;
-                S[l].r[k] = vc_residual_value(S[l].f[k], v[k], v[k - P], v[k + P], v[k - 1], v[k + 1],
-                                              T.edges[l].ex[kg], T.edges[l].ex[kg + Pg], T.edges[l].ey[kg], T.edges[l].ey[kg + 1]);
-            } else {
-                S[l].r[k] = residual_at(S[l], k, T.rcoef[l]);
-            }
-        }
-        __syncthreads();
-        const int nc = S[l - 1].n;
-        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
-            int ic = t / nc + 1, jc = t % nc + 1;
-            const double* r = S[l].r;
-            long long k = (long long)(2 * ic - 1) * S[l].pitch + (2 * jc - 1);
-            double sum = exact_add(exact_add(exact_add(r[k], r[k + S[l].pitch]), r[k + 1]), r[k + S[l].pitch + 1]);
-            S[l - 1].f[(long long)ic * S[l - 1].pitch + jc] = exact_mul(0.25, sum);
-        }
-        __syncthreads();
-    }
-    cta_smooth<VC>(S[0], (T.top == 0) ? T.bc_top : T.bc_coarse, T.coef[0], T.nsmooth_bottom, T.edges[0], T.g[0].pitch);
-    for (int l = 1; l <= T.top; ++l) {
-        const MgBC& b = (l == T.top) ? T.bc_top : T.bc_coarse;
-        const MgLevel &F = S[l], &Cs = S[l - 1];
-        const int nc = Cs.n;
-        for (int t = threadIdx.x; t < nc * nc; t += blockDim.x) {
-            int ic = t / nc + 1, jc = t % nc + 1;
-            const double* c = Cs.v;
-            const long long kc = (long long)ic * Cs.pitch + jc;
-            double mx = exact_mul(0.5, exact_sub(c[kc + Cs.pitch], c[kc - Cs.pitch]));
-            double my = exact_mul(0.5, exact_sub(c[kc + 1], c[kc - 1]));
-            double qx = exact_mul(0.25, mx), qy = exact_mul(0.25, my), c0 = c[kc];
-            const int i = 2 * ic - 1, j = 2 * jc - 1, P = F.pitch;
-            double* v = F.v;
-            store_with_ghosts(v, F.n, F.n, P, i, j, exact_add(v[(long long)i * P + j], exact_sub(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, F.n, P, i + 1, j, exact_add(v[(long long)(i + 1) * P + j], exact_sub(exact_add(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, F.n, P, i, j + 1, exact_add(v[(long long)i * P + j + 1], exact_add(exact_sub(c0, qx), qy)), b, F.dx, F.dy);
-            store_with_ghosts(v, F.n, F.n, P, i + 1, j + 1, exact_add(v[(long long)(i + 1) * P + j + 1], exact_add(exact_add(c0, qx), qy)), b, F.dx, F.dy);
-        }
-        __syncthreads();
-        cta_smooth<VC>(S[l], b, T.coef[l], T.nsmooth, T.edges[l], T.g[l].pitch);
-    }
-
-    // store everything back (coarse planes stay observable through grids[level], like the reference's)
-    for (int l = 0; l <= T.top; ++l) {
-        const int q = S[l].n + 2;
-        for (int t = threadIdx.x; t < q * q; t += blockDim.x) {
-            int i = t / q, j = t % q;
-            long long ks = (long long)i * S[l].pitch + j, kg = (long long)i * T.g[l].pitch + j;
-            T.g[l].v[kg] = S[l].v[ks];
-            T.g[l].f[kg] = S[l].f[ks];
-            T.g[l].r[kg] = S[l].r[ks];
-        }
-    }
+    coarse_io<0>(T, sm, false, tid, nthreads); coarse_io<1>(T, sm, false, tid, nthreads); coarse_io<2>(T, sm, false, tid, nthreads);
+    coarse_io<3>(T, sm, false, tid, nthreads); coarse_io<4>(T, sm, false, tid, nthreads); coarse_io<5>(T, sm, false, tid, nthreads);
 }
 
 // full ghost fill of v from the interior (used once per smooth() like MG.py:565)

@@ -201,8 +201,17 @@ class MGHandle:
         err = C.c_longlong(0)
         _lib.check(_lib.lib().p2b_mg_result(self._h, out, C.byref(err), self._s()))
         if err.value:
-            raise RuntimeError(f"multigrid: a wait on a neighbouring rank timed out (control word {err.value - 1})")
+            w = self.control_words()
+            raise RuntimeError(f"multigrid: a wait on another rank timed out (control word {err.value - 1}); rank "
+                               f"{self.decomp.rank if self.decomp else 0}: epoch {w[0]} from_lo {w[3]} from_hi {w[4]} counters "
+                               f"{w[5:8]} all-rank words {w[8:8 + (self.decomp.size if self.decomp else 1)]}")
         return tuple(out)
+
+    def control_words(self):
+        """the hierarchy's control words (csrc/mg_kernels.cuh, CW_*) as a list of ints -- diagnostics"""
+        ptr = _lib.lib().p2b_mg_control_ptr(self._h)
+        off = (ptr - self.workspace.data_ptr()) // 8
+        return self.workspace[off:off + 24].view(torch.int64).tolist()
 
     def cycle_diagnostics(self, old_phi):
         """returns (sum rel-change^2, sum r^2); updates old_phi <- v and the r plane"""

@@ -96,6 +96,14 @@ class Pyro:
         if sim.do_output():
             self._snapshot()
 
+    def single_step_streamed(self, host_in, host_out, nchunks=16):
+        """single_step() for a state that lives in pinned host memory (compressible solver): host_in -> device -> step
+        -> host_out with the copies pipelined against the sweep (Simulation.step_streamed)"""
+        sim = self._require_sim()
+        sim.step_streamed(host_in, host_out, nchunks=nchunks)
+        if self.verbose > 0:
+            print(f"{sim.n:5d} {sim.cc_data.t:10.5f} {sim.dt:10.5f}")
+
     def _snapshot(self):
         self.sim.write(f"{self.rp.get_param('io.basename')}{self.sim.n:04d}")
 

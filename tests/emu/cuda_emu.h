@@ -37,6 +37,7 @@ extern thread_local dim3 blockDim, gridDim;
 #define __global__
 #define __device__
 #define __host__
+#define __grid_constant__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static thread_local   // CTAs of one emulated GPU run one at a time: one copy per OS thread is the CTA's copy
@@ -156,6 +157,8 @@ struct Cta {
     std::vector<unsigned> warp_gen;
     std::vector<double> slot;          // [warp][2][32]
     std::vector<int> flip;             // exchange-buffer parity per thread
+    int bar_count[16] = {0};           // named barriers (bar.sync id, nthreads)
+    unsigned bar_gen[16] = {0};
 };
 
 extern thread_local Cta* cta;          // null in sequential mode
@@ -219,6 +222,15 @@ inline void __syncthreads()
     if (++c->all_count == c->live) { c->all_count = 0; ++c->all_gen; }
     while (c->all_gen == gen) emu::yield();
 }
+inline void emu_bar_sync(int id, int nthreads)
+{
+    emu::Cta* c = emu::cta;
+    if (!c) emu::need_threads("bar.sync");
+    const unsigned gen = c->bar_gen[id];
+    if (++c->bar_count[id] == nthreads) { c->bar_count[id] = 0; ++c->bar_gen[id]; }
+    while (c->bar_gen[id] == gen) emu::yield();
+}
+inline void __syncwarp() { (void)emu::exchange(0.0, -1); }      // a warp-wide rendezvous
 inline double __shfl_up_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) - d); }
 inline double __shfl_down_sync(unsigned, double v, int d) { return emu::exchange(v, (emu::lin_tid & 31) + d); }
 inline double __shfl_xor_sync(unsigned, double v, int m) { return emu::exchange(v, (emu::lin_tid & 31) ^ m); }

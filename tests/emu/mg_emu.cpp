@@ -33,7 +33,9 @@ struct RegisterThreaded {
     {
         using namespace pyro;
         emu::threaded((const void*)mg_smooth_small_kernel);
-        emu::threaded((const void*)mg_smooth_tb_kernel);
+        emu::threaded((const void*)mg_smooth_tb_kernel_t<8, 16, 1>);
+        emu::threaded((const void*)mg_smooth_tb_kernel_t<4, 16, 2>);
+        emu::threaded((const void*)mg_smooth_tb_kernel_t<8, 8, 2>);
         emu::threaded((const void*)mg_coarse_vcycle_kernel<false>);
         emu::threaded((const void*)mg_coarse_vcycle_kernel<true>);
         emu::threaded((const void*)mg_sumsq_partial_kernel);
