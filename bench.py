@@ -531,7 +531,7 @@ def main():
         parts = {"cycle_ms": mms,
                  "vcycle_only_ms": timed(lambda: (h.zero_coarse(), h.vcycle())),
                  "diagnostics_ms": timed(lambda: h.cycle_diagnostics_enqueue(old_phi)),
-                 "coarse_fused_le_64_ms": timed(lambda: h.vcycle_level(5))}
+                 "coarse_fused_le_64_ms": timed(lambda: h.vcycle_level(min(5, fine)))}
         if world > 1:
             parts["replicated_levels_ms"] = timed(lambda: h.vcycle_level(split - 1))
             parts["split_levels_incl_halo_waits_ms"] = parts["vcycle_only_ms"] - parts["replicated_levels_ms"]

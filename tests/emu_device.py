@@ -137,6 +137,28 @@ def _emu_graph_capture(g, *a, **k):
         _CAPTURE.graph = None
 
 
+class EmuStream:
+    """stand-in for torch.cuda.Stream / Event on the emulated device: the emulated kernels run synchronously, so every
+    ordering call is a no-op"""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    cuda_stream = None
+
+
 def _host_tensor_from_pointer(ptr, nelem):
     """ops.tensor_from_pointer over host ("device") memory"""
     return torch.frombuffer((C.c_double * nelem).from_address(ptr), dtype=torch.float64)
@@ -165,7 +187,11 @@ def emulated_device():
                 (torch, "as_tensor", _host_device(torch.as_tensor)),
                 (torch.Tensor, "to", to), (torch.Tensor, "cuda", lambda self, *a, **k: self),
                 (torch.cuda, "synchronize", lambda *a, **k: None),
-                (torch.cuda, "CUDAGraph", EmuGraph), (torch.cuda, "graph", _emu_graph_capture)):
+                (torch.cuda, "CUDAGraph", EmuGraph), (torch.cuda, "graph", _emu_graph_capture),
+                (torch.cuda, "Stream", EmuStream), (torch.cuda, "Event", EmuStream),
+                (torch.cuda, "current_stream", lambda *a, **k: EmuStream()),
+                (torch.cuda, "stream", lambda s: contextlib.nullcontext()),
+                (torch.Tensor, "is_pinned", lambda self, *a, **k: True)):
             st.enter_context(mock.patch.object(target, attr, new))
         st.enter_context(mock.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)))
         yield facade

@@ -142,3 +142,32 @@ def test_bench_on_emulated_device(capfd, monkeypatch):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["roofline"]["bound"] == "hbm"
     assert dev.calls["p2b_compressible_sweep"] >= 2 + 3 and dev.calls["p2b_mg_vcycle"] >= 2
 
+
+
+def test_streamed_step_on_emulated_device(monkeypatch):
+    """Pyro.single_step_streamed() (host-resident state, row blocks host -> device -> host) against resident steps, bit for
+    bit, on the emulated device: the block decomposition, per-block ghost fill and the reuse of the fused wave-speed maxima
+    are host logic that runs here exactly as on the GPU (streams and events are no-ops: emulated kernels are synchronous)"""
+    import torch
+
+    import emu_device
+    from test_gpu_api import test_streamed_steps_are_bit_identical_to_resident_steps as body
+    real_empty = torch.empty
+
+    def empty(*a, **k):
+        k.pop("pin_memory", None)
+        return real_empty(*a, **k)
+    monkeypatch.setattr(torch, "empty", empty)
+    with emu_device.emulated_device():
+        body(64, 48, 4, "sedov")
+        body(48, 40, 1, "quad")
+
+
+def test_scale_tests_rehearsed_small():
+    """the bodies of tests/test_gpu_scale.py at toy sizes on the emulated device (driver dt limits, per-cycle comparison,
+    the solve with the device-side stopping rule and the emulated graph replay)"""
+    import emu_device
+    import test_gpu_scale as ts
+    with emu_device.emulated_device():
+        ts.test_sedov_through_the_driver_at_scale(64, (1, 6))
+        ts.test_multigrid_2048_cycle_by_cycle(128)
