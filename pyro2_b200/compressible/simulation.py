@@ -317,7 +317,8 @@ class Simulation(NullSimulation):
         with torch.cuda.stream(self._st_h2d):
             for c in range(nchunks):
                 a, b = bounds[c], bounds[c + 1]
-                dev[:, a:b].copy_(host_in[:, a:b], non_blocking=True)
+                for k in range(dev.shape[0]):       # rows a..b-1 of ONE plane are contiguous: a plain DMA each
+                    dev[k, a:b].copy_(host_in[k, a:b], non_blocking=True)
                 h2d_done[c].record()
         if not known:
             # the whole state first, then the ordinary ghost fill and CFL reduction
@@ -355,7 +356,8 @@ class Simulation(NullSimulation):
             swept[c].record()
             with torch.cuda.stream(self._st_d2h):
                 self._st_d2h.wait_event(swept[c])
-                host_out[:, a:b].copy_(out[:, a:b], non_blocking=True)
+                for k in range(out.shape[0]):
+                    host_out[k, a:b].copy_(out[k, a:b], non_blocking=True)
         # maxima and status of the whole grid from the blocks' (positive doubles order like their bit patterns)
         self._scratch[:4] = self._chunk_scratch[:, :4].max(dim=0).values
         cur.wait_stream(self._st_d2h)               # the step is complete when its result is on the host
