@@ -141,6 +141,15 @@ __device__ __forceinline__ unsigned long long comm_value(const MgComm& c, int or
     return c.ctl[CW_EPOCH] * MG_ORD_STRIDE + (unsigned long long)ord;
 }
 
+// Tile row a CTA works on.  With communication the tile rows are rotated by one: CTAs are dispatched in blockIdx order, so
+// the tile rows that wait for the neighbours' halo rows (the first and the last) run LAST, after the interior tiles --
+// by then the rows pushed at the end of the neighbours' previous pass have long arrived, and no SM sits in a spin loop
+// while interior work is pending (measured at N = 2: edge tiles dispatched first held ~1/3 of the SMs for most of a pass).
+__device__ __forceinline__ int comm_tile_row(const MgComm& c)
+{
+    return c.ctl ? (int)((blockIdx.y + 1u) % gridDim.y) : (int)blockIdx.y;
+}
+
 // all threads of a CTA call this (block-uniform arguments): wait for the halo rows this CTA is about to read
 __device__ __forceinline__ void comm_block_wait(const MgComm& c, bool need_lo, bool need_hi)
 {
@@ -450,7 +459,7 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     if (!INHOM) { b.xlv = nullptr; b.xrv = nullptr; b.ylv = nullptr; b.yrv = nullptr; }
     const int n = L.n, ni = L.ni, P = L.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int I0 = 1 + blockIdx.y * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int I0 = 1 + comm_tile_row(cm) * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
     const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd; local index)
     const int gj0 = J0 - TB_H + 2 * lane;          // first of its two columns (odd)
     const bool xper = EDGE && (b.xl == P2B_BC_PERIODIC), yper = EDGE && (b.yl == P2B_BC_PERIODIC);
@@ -656,7 +665,7 @@ mg_smooth_tb_kernel_t(MgLevel L, const double* __restrict__ vin, double* __restr
     constexpr int RH = R * NW, TI = RH - 2 * TB_H;
     __shared__ __align__(16) double edge[2][NW][2][TB_RW];   // [buffer][warp][first/last row][column]
     if (L.ctl && L.ctl[CW_STOP]) return;
-    const int I0 = 1 + blockIdx.y * TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int I0 = 1 + comm_tile_row(cm) * TI, J0 = 1 + blockIdx.x * TB_TJ;
     // the branch-free interior path needs the whole region strictly inside the rank's OWNED rows: a region that
     // reaches into halo rows waits for them and one that holds the first / last owned rows pushes them (EDGE path)
     const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + RH - 1 <= L.ni) &&
