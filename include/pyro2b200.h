@@ -146,7 +146,8 @@ int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
  * no special-case handling), so their behaviour on 0, denormals, inf and the <= 2 ulp bound can be pinned on the
  * device (the host emulator has its own restatement).  op 0: out = rcp(a), 1: out = fdiv(a, b), 2: out = fsqrt(a),
  * 3: out = the HLLC_lm solver's normal-momentum flux for the face (rho, E, mn, mt) = (a[4k..4k+3]) | (b[4k..4k+3]),
- * gamma = 1.4 (riemann.py:864-1019; n counts faces for op 3).  Device pointers. */
+ * gamma = 1.4 (riemann.py:864-1019; n counts faces for op 3); 4: out = a / b through the shared-divisor quotient of
+ * cons_to_prim (must equal IEEE division), 5: out = IEEE a / b (__ddiv_rn).  Device pointers. */
 int p2b_test_fastmath(int op, const double* a, const double* b, double* out, int n, void* stream);
 
 /* ---- multigrid: CellCenterMG2d (pyro/multigrid/MG.py:77-778), constant coefficients,

@@ -9,7 +9,10 @@
 
 namespace pyro {
 
-constexpr int SWEEP_WARPS = 4;                 // warps per CTA (independent of each other)
+#ifndef SWEEP_WARPS_CFG
+#define SWEEP_WARPS_CFG 4
+#endif
+constexpr int SWEEP_WARPS = SWEEP_WARPS_CFG;   // warps per CTA (independent of each other)
 constexpr int SWEEP_THREADS = 32 * SWEEP_WARPS;
 #ifndef SWEEP_MIN_BLOCKS
 #define SWEEP_MIN_BLOCKS 3                     // 12 warps/SM -> <= 168 registers per thread
@@ -114,6 +117,8 @@ __global__ void fastmath_probe_kernel(int op, const double* a, const double* b, 
     if (op == 0) out[k] = rcp(a[k]);
     else if (op == 1) out[k] = fdiv(a[k], b[k]);
     else if (op == 2) out[k] = fsqrt(a[k]);
+    else if (op == 4) out[k] = div_by(a[k], shared_div(b[k]));
+    else if (op == 5) out[k] = __ddiv_rn(a[k], b[k]);
     else {
         const double* l = a + 4 * k; const double* r = b + 4 * k;
         out[k] = hllc_lm(l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], hllc_par(1.4)).mn;
@@ -194,7 +199,7 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
 
 int p2b_test_fastmath(int op, const double* a, const double* b, double* out, int n, void* stream)
 {
-    P2B_REQUIRE(op >= 0 && op <= 3 && a && out && n >= 0 && (b || op == 0 || op == 2), "bad probe arguments");
+    P2B_REQUIRE(op >= 0 && op <= 5 && a && out && n >= 0 && (b || op == 0 || op == 2), "bad probe arguments");
     if (n == 0) return P2B_OK;
     fastmath_probe_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(op, a, b, out, n);
     P2B_CUDA_CHECK(cudaGetLastError());

@@ -191,6 +191,8 @@ extern "C" int emu_test_fastmath(int op, const double* a, const double* b, doubl
         if (op == 0) out[k] = pyro::rcp(a[k]);
         else if (op == 1) out[k] = pyro::fdiv(a[k], b[k]);
         else if (op == 2) out[k] = pyro::fsqrt(a[k]);
+        else if (op == 4) out[k] = pyro::div_by(a[k], pyro::shared_div(b[k]));
+        else if (op == 5) out[k] = a[k] / b[k];
         else {
             const double* l = a + 4 * k; const double* r = b + 4 * k;
             out[k] = pyro::hllc_lm(l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], pyro::hllc_par(1.4)).mn;

@@ -323,3 +323,24 @@ def test_sweep_other_riemann_solvers_gas_at_rest(solver):
     for n in range(4):
         scale = np.linalg.norm(ref[v][..., n].ravel()) if n < 2 else np.linalg.norm(ref[v][..., 1].ravel())
         assert np.linalg.norm((got[v][..., n] - ref[v][..., n]).ravel()) < 1e-12 * scale
+
+
+def test_shared_divisor_quotients_are_ieee_on_device():
+    """cons_to_prim / cfl_speeds divide by the density through one refined reciprocal (hydro_core.cuh: shared_div / div_by);
+    the quotients must be the IEEE ones bit for bit -- zero numerators of either sign (gas at rest, reflected ghosts) and
+    negative or extreme divisors (library fallback) included"""
+    rng = np.random.default_rng(11)
+    n = 20000
+    a = np.concatenate([rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 8, n), np.zeros(64), -np.zeros(64),
+                        10.0 ** rng.uniform(-280, 280, 256), [1.0, -1.0, 3.0, 1e-300, 1e300]])
+    b = np.concatenate([10.0 ** rng.uniform(-6, 6, n) * np.where(rng.random(n) < 0.1, -1.0, 1.0),
+                        10.0 ** rng.uniform(-3, 3, 64), -(10.0 ** rng.uniform(-3, 3, 64)),
+                        10.0 ** rng.uniform(-3, 3, 256), [3.0, 3.0, 1e-250, 1e-300, 1e250]])
+    with np.errstate(all="ignore"):
+        want = a / b
+    sane = (np.abs(a) == 0) | ((np.abs(a) > 2.0 ** -900) & (np.abs(a) < 2.0 ** 900))
+    got = _device_probe(4, a, b)
+    lib = _device_probe(5, a, b)
+    assert np.array_equal(lib.view(np.int64), want.view(np.int64))                       # __ddiv_rn is IEEE (sanity)
+    assert np.array_equal(got[sane].view(np.int64), want[sane].view(np.int64))           # bits, signed zeros included
+    assert (np.signbit(got[n:n + 128]) == np.signbit(want[n:n + 128])).all()
