@@ -9,13 +9,17 @@
 
 namespace pyro {
 
+// One warp per CTA, 12 CTAs per SM.  Warps never talk to each other, so the CTA size is free: with a single warp the
+// warp's shared-memory block sits at a compile-time address (no per-access base arithmetic) -- measured 2.56 -> 2.32 ms
+// per 4096^2 sweep against 4-warp CTAs at the same 168 registers and 12 warps per SM (profiles/r2_sweep_ab.txt).  Eight
+// warps without spills (242 registers) and sixteen with more (128) are both slower.
 #ifndef SWEEP_WARPS_CFG
-#define SWEEP_WARPS_CFG 4
+#define SWEEP_WARPS_CFG 1
 #endif
 constexpr int SWEEP_WARPS = SWEEP_WARPS_CFG;   // warps per CTA (independent of each other)
 constexpr int SWEEP_THREADS = 32 * SWEEP_WARPS;
 #ifndef SWEEP_MIN_BLOCKS
-#define SWEEP_MIN_BLOCKS 3                     // 12 warps/SM -> <= 168 registers per thread
+#define SWEEP_MIN_BLOCKS 11                    // register cap 186; ptxas settles on 168 -> 12 warps / SM
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
