@@ -333,10 +333,14 @@ class LaunchCounter:
 def main():
     args = parse()
     guard_stdout()
-    pin_host_threads()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # OpenMP pinning is for the CPU legs only (reference arm; cpu_baseline at N = 1).  Under torchrun every rank would bind
+    # its threads -- the main thread included -- to the SAME first cores: eight GPU ranks sharing one core made every
+    # launch-bound leg 10x slower in an N = 8 run of this round.
+    if args.impl == "reference" or world == 1:
+        pin_host_threads()
     if args.impl == "reference":
         run_reference(args, rank)
         return
