@@ -101,6 +101,7 @@ namespace pyro {
 #ifdef P2B_EMU_HEADER
 __device__ __forceinline__ unsigned long long comm_load(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void comm_store(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ void comm_store_relaxed(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 __device__ __forceinline__ long long comm_clock_ns() { return emu_clock_ns(); }
 __device__ __forceinline__ void comm_pause() { emu_pause(); }
 __device__ __forceinline__ int comm_tid() { return emu::lin_tid; }
@@ -114,6 +115,11 @@ __device__ __forceinline__ unsigned long long comm_load(const unsigned long long
 __device__ __forceinline__ void comm_store(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// after an explicit system-scope fence: a flag store that need not drain the write queue again
+__device__ __forceinline__ void comm_store_relaxed(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ long long comm_clock_ns()
 {
@@ -141,13 +147,15 @@ __device__ __forceinline__ unsigned long long comm_value(const MgComm& c, int or
     return c.ctl[CW_EPOCH] * MG_ORD_STRIDE + (unsigned long long)ord;
 }
 
-// Tile row a CTA works on.  With communication the tile rows are rotated by one: CTAs are dispatched in blockIdx order, so
-// the tile rows that wait for the neighbours' halo rows (the first and the last) run LAST, after the interior tiles --
-// by then the rows pushed at the end of the neighbours' previous pass have long arrived, and no SM sits in a spin loop
-// while interior work is pending (measured at N = 2: edge tiles dispatched first held ~1/3 of the SMs for most of a pass).
+// Tile row a CTA works on.  CTAs are dispatched in blockIdx order; with communication the tile rows are rotated so that the
+// first and the last -- the ones that wait for the neighbours' halo rows and push their own -- are dispatched in the MIDDLE
+// of the launch: late enough that the rows pushed in the middle of the neighbours' previous pass have long arrived (no SM
+// sits in a spin loop: dispatched first, the edge tiles held ~1/3 of the SMs for most of a pass at N = 2), early enough
+// that their system-scope fences and flag stores are hidden behind the remaining interior tiles instead of forming the
+// tail of the kernel.
 __device__ __forceinline__ int comm_tile_row(const MgComm& c)
 {
-    return c.ctl ? (int)((blockIdx.y + 1u) % gridDim.y) : (int)blockIdx.y;
+    return c.ctl ? (int)((blockIdx.y + gridDim.y / 2u + 1u) % gridDim.y) : (int)blockIdx.y;
 }
 
 // all threads of a CTA call this (block-uniform arguments): wait for the halo rows this CTA is about to read
@@ -175,14 +183,14 @@ __device__ __forceinline__ void comm_block_signal(const MgComm& c, bool lo_edge,
     if (comm_tid() == 0) {
         __threadfence_system();
         const unsigned long long val = comm_value(c, c.sig_ord);
+        // (every pushing CTA fenced at system scope before it counted itself: when the last one sees the full count, all
+        // pushes have been performed; its release store orders the observation before the flag)
         if (lo_edge && atomicAdd(c.ctl + CW_CNT_LO, 1ull) == (unsigned long long)(c.n_lo - 1)) {
             atomicExch(c.ctl + CW_CNT_LO, 0ull);
-            __threadfence_system();
             comm_store(c.ctl + c.dlo + CW_FROM_HI, val);       // I am my lo neighbour's hi neighbour
         }
         if (hi_edge && atomicAdd(c.ctl + CW_CNT_HI, 1ull) == (unsigned long long)(c.n_hi - 1)) {
             atomicExch(c.ctl + CW_CNT_HI, 0ull);
-            __threadfence_system();
             comm_store(c.ctl + c.dhi + CW_FROM_LO, val);
         }
     }
@@ -200,7 +208,7 @@ __device__ __forceinline__ void comm_block_signal_all(const MgComm& c, int nbloc
             __threadfence_system();
             const unsigned long long val = comm_value(c, c.sig_ord);
             for (int r = 0; r < c.size; ++r)
-                comm_store(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
+                comm_store_relaxed(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
         }
     }
 }
@@ -1181,8 +1189,8 @@ __device__ __forceinline__ void comm_allreduce2(const MgComm& c, double& a, doub
         double* dst = slots + (long long)c.ctl[CW_PEER + r] + c.rank * 4;
         dst[0] = a; dst[1] = b;
     }
-    __threadfence_system();
-    for (int r = 0; r < c.size; ++r) comm_store(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
+    __threadfence_system();        // one drain of the write queue, then the flags
+    for (int r = 0; r < c.size; ++r) comm_store_relaxed(c.ctl + (long long)c.ctl[CW_PEER + r] + CW_GFLAG + c.rank, val);
     for (int r = 0; r < c.size; ++r) comm_wait_ge(c.ctl, CW_GFLAG + r, val);
     a = 0.0; b = 0.0;
     for (int r = 0; r < c.size; ++r) {
