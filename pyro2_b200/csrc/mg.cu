@@ -296,8 +296,15 @@ static void tb_pass_impl(p2b_mg* m, int level, int src, int dst, int niter, cuda
         c = comm_base(m);
         c.wait_ord = imax(m->last_push[level][src], m->last_push[level][1]);
         c.sig_ord = ++m->ord;
-        c.n_lo = (int)grd.x;                                                 // tile row 0 holds rows 1..TB_H (TI >= TB_H)
-        c.n_hi = (int)grd.x * ((L.ni - 1) / TI - (L.ni - TB_H) / TI + 1);     // tile rows meeting ni-TB_H+1..ni
+        // tile rows that store first / last owned rows push them; the kernel's last pushing CTA of a side signals
+        int rows_lo = 0, rows_hi = 0;
+        for (int ty = 0; ty < (int)grd.y; ++ty) {
+            const int I0 = tb_tile_origin(ty, TI, L.ni, !L.xhi_phys);
+            rows_lo += tb_pushes_lo(I0) ? 1 : 0;
+            rows_hi += tb_pushes_hi(I0, TI, L.ni) ? 1 : 0;
+        }
+        c.n_lo = (int)grd.x * rows_lo;
+        c.n_hi = (int)grd.x * rows_hi;
         m->last_push[level][dst] = c.sig_ord;
     }
     const double* sp = src == 0 ? L.v : L.w;

@@ -454,12 +454,29 @@ constexpr int TB_EYS = 2 * TB_RH * 33;             // doubles in the eta_y tile
 // compiled in.  cm: slab communication of this launch (cm.ctl == NULL: none).
 // R / NW: rows per thread and warps per CTA of this instantiation (region R * NW rows x 64 columns).  The constants of
 // the default geometry are shadowed inside the body, which is otherwise written in terms of TB_R, TB_NW, TB_RH, TB_TI.
-template <bool EDGE, bool VC, bool INHOM, int R = 8, int NW = TB_NW_CFG>
+// First row of tile row ty.  clamp (a slab whose hi side faces another slab): a last tile row that would overhang is moved
+// up so that it ends at the last owned row and its region at the last halo row -- all real cells, the branch-free path
+// applies; the rows it shares with the tile row before it are computed twice with the same bits.  Host and device use the
+// same function: the host counts the tile rows that push (the last one to finish signals).
+__host__ __device__ inline int tb_tile_origin(int ty, int TI, int ni, bool clamp)
+{
+    int I0 = 1 + ty * TI;
+    if (clamp && ni >= TI && I0 + TI - 1 > ni) I0 = ni - TI + 1;
+    return I0;
+}
+__host__ __device__ inline bool tb_pushes_lo(int I0) { return I0 <= TB_H; }
+__host__ __device__ inline bool tb_pushes_hi(int I0, int TI, int ni) { return I0 + TI - 1 > ni - TB_H && I0 <= ni; }
+
+// COMM: this CTA takes part in the slab communication of the launch (waits for halo rows its region reaches into, pushes
+// the first / last owned rows it stores); independent of EDGE, so that a tile at a slab boundary whose region holds real
+// cells only -- halo rows included -- runs the branch-free path: at N = 8 two of the five tile rows of the finest level are
+// such tiles.  I0: first row of the tile (the kernel clamps the last tile row of a slab so that it does not overhang).
+template <bool EDGE, bool VC, bool INHOM, int R = 8, int NW = TB_NW_CFG, bool COMM = EDGE>
 __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* __restrict__ vin,
                                                double* __restrict__ vout, const MgBC& bb, const SmoothCoef& c,
                                                int niter, double (*edge)[NW][2][TB_RW],
                                                const VcEdges& E, double* __restrict__ exs, double* __restrict__ eys,
-                                               const MgComm& cm)
+                                               const MgComm& cm, int I0)
 {
     constexpr int TB_R = R, TB_NW = NW, TB_RH = R * NW, TB_TI = TB_RH - 2 * TB_H;
     static_assert(TB_TI % 2 == 0 && TB_TI > 0 && R % 2 == 0 && (!VC || (R == 8 && NW == TB_NW_CFG)), "tile geometry");
@@ -467,7 +484,7 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     if (!INHOM) { b.xlv = nullptr; b.xrv = nullptr; b.ylv = nullptr; b.yrv = nullptr; }
     const int n = L.n, ni = L.ni, P = L.pitch;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int I0 = 1 + comm_tile_row(cm) * TB_TI, J0 = 1 + blockIdx.x * TB_TJ;
+    const int J0 = 1 + blockIdx.x * TB_TJ;
     const int gi0 = I0 - TB_H + w * TB_R;          // first region row of this thread (odd; local index)
     const int gj0 = J0 - TB_H + 2 * lane;          // first of its two columns (odd)
     const bool xper = EDGE && (b.xl == P2B_BC_PERIODIC), yper = EDGE && (b.yl == P2B_BC_PERIODIC);
@@ -476,7 +493,7 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
     const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? ni : ni + TB_H;
 
     // slab: this CTA's region reaches into halo rows the neighbour writes -- wait until they have landed
-    if (EDGE) comm_block_wait(cm, I0 - TB_H < 1, I0 - TB_H + TB_RH - 1 > ni);
+    if (COMM) comm_block_wait(cm, I0 - TB_H < 1, I0 - TB_H + TB_RH - 1 > ni);
 
     unsigned xseam = 0;                            // VC: bit r: this row is the periodic image of row ni
     bool yseam[2] = {false, false};                //     column a is the periodic image of column n
@@ -650,13 +667,13 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
             if (EDGE) store_with_ghosts(vout, ni, n, P, gi, gj, v[r][a], b, L.dx, L.dy, L.ioff);
             else vout[(long long)gi * P + gj] = v[r][a];
             // slab: my first / last TB_H rows are the neighbours' halo rows of the plane just written
-            if (EDGE && cm.ctl && cm.sig_ord >= 0) {
+            if (COMM && cm.ctl && cm.sig_ord >= 0) {
                 if (cm.has_lo && gi <= TB_H) (vout + cm.dlo)[(long long)(ni + gi) * P + gj] = v[r][a];
                 if (cm.has_hi && gi > ni - TB_H) (vout + cm.dhi)[(long long)(gi - ni) * P + gj] = v[r][a];
             }
         }
     }
-    if (EDGE) comm_block_signal(cm, I0 <= TB_H, I0 + TB_TI - 1 > ni - TB_H && I0 <= ni);
+    if (COMM) comm_block_signal(cm, tb_pushes_lo(I0), tb_pushes_hi(I0, TB_TI, ni));
 }
 
 // Geometries of the constant-coefficient pass.  The per-CTA time of a pass is set by its serial chain (load, 10
@@ -673,17 +690,21 @@ mg_smooth_tb_kernel_t(MgLevel L, const double* __restrict__ vin, double* __restr
     constexpr int RH = R * NW, TI = RH - 2 * TB_H;
     __shared__ __align__(16) double edge[2][NW][2][TB_RW];   // [buffer][warp][first/last row][column]
     if (L.ctl && L.ctl[CW_STOP]) return;
-    const int I0 = 1 + comm_tile_row(cm) * TI, J0 = 1 + blockIdx.x * TB_TJ;
-    // the branch-free interior path needs the whole region strictly inside the rank's OWNED rows: a region that
-    // reaches into halo rows waits for them and one that holds the first / last owned rows pushes them (EDGE path)
-    const bool interior = (I0 - TB_H >= 1) && (I0 - TB_H + RH - 1 <= L.ni) &&
-                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n) &&
-                          (!cm.ctl || (I0 > TB_H && I0 + TI - 1 <= L.ni - TB_H));
+    const int I0 = tb_tile_origin(comm_tile_row(cm), TI, L.ni, cm.ctl && !L.xhi_phys);
+    const int J0 = 1 + blockIdx.x * TB_TJ;
+    // rows that hold real cells: the owned rows plus TB_H halo rows on a side that faces another slab
+    const int rlo = L.xlo_phys ? 1 : 1 - TB_H, rhi = L.xhi_phys ? L.ni : L.ni + TB_H;
+    // branch-free path: the whole region holds real cells (no ghost logic, no wrap, no masks)
+    const bool interior = (I0 - TB_H >= rlo) && (I0 - TB_H + RH - 1 <= rhi) &&
+                          (J0 - TB_H >= 1) && (J0 - TB_H + TB_RW - 1 <= L.n);
+    // ... and it communicates iff it reaches into halo rows or stores first / last owned rows
+    const bool comm = cm.ctl && (I0 - TB_H < 1 || I0 - TB_H + RH - 1 > L.ni || I0 <= TB_H || I0 + TI - 1 > L.ni - TB_H);
     const VcEdges none = {nullptr, nullptr};
     const bool inhom = b.xlv || b.xrv || b.ylv || b.yrv;
-    if (interior) smooth_tb_body<false, false, false, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
-    else if (inhom) smooth_tb_body<true, false, true, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
-    else smooth_tb_body<true, false, false, R, NW>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm);
+    if (interior && !comm) smooth_tb_body<false, false, false, R, NW, false>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm, I0);
+    else if (interior) smooth_tb_body<false, false, false, R, NW, true>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm, I0);
+    else if (inhom) smooth_tb_body<true, false, true, R, NW, true>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm, I0);
+    else smooth_tb_body<true, false, false, R, NW, true>(L, vin, vout, b, c, niter, edge, none, nullptr, nullptr, cm, I0);
 }
 
 struct TbCfg { int R, NW, TI, threads; };
@@ -715,8 +736,8 @@ mg_vc_smooth_tb_kernel(MgLevel L, const double* __restrict__ vin, double* __rest
     c.alpha = c.xc = c.yc = c.denom = c.rden = 0.0; c.fast = 0;
     MgComm cm;
     cm.ctl = nullptr; cm.sig_ord = cm.wait_ord = -1;
-    if (interior) smooth_tb_body<false, true, false>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm);
-    else smooth_tb_body<true, true, true>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm);
+    if (interior) smooth_tb_body<false, true, false>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm, I0);
+    else smooth_tb_body<true, true, true>(L, vin, vout, b, c, niter, edge, E, exs, eys, cm, I0);
 }
 
 
