@@ -141,6 +141,8 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g,
 
 /* launch geometry chosen for the last sweep (bench diagnostics): tasks, resident warps, seglen */
 int p2b_sweep_info(int* ntasks, int* resident_warps, int* seglen);
+/* 1: the last sweep staged its rows through a TMA tensor map (one 3-d copy per row), 0: 1-d bulk copies per plane */
+int p2b_sweep_uses_tensor_map(void);
 
 /* test probe of the sweep's branch-free fp64 helpers (csrc/hydro_core.cuh: rcp / fdiv / fsqrt -- MUFU seed + Newton,
  * no special-case handling), so their behaviour on 0, denormals, inf and the <= 2 ulp bound can be pinned on the

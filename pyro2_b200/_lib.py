@@ -122,6 +122,7 @@ SIGNATURES = {
     "p2b_compressible_sweep": (_i, [_vp, _vp, _PG, C.POINTER(CompParams), _d, _vp, _vp]),
     "p2b_sweep_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "p2b_test_fastmath": (_i, [_i, _vp, _vp, _vp, _i, _vp]),
+    "p2b_sweep_uses_tensor_map": (_i, []),
     "p2b_mg_create": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i]),
     "p2b_mg_create_slab": (_vp, [_i, C.POINTER(_i), _d, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i]),
     "p2b_mg_level_info": (_i, [_vp, _i, C.POINTER(_ll)]),

@@ -168,7 +168,8 @@ static void exchange_impl(p2b_mg* m, int level, double* plane, int depth, cudaSt
 }
 
 // which geometry of the blocked pass a level uses (mg_kernels.cuh, tb_cfg): the throughput geometry when its grid
-// gives the chip at least two waves, otherwise the short-chain one.  P2B_TB_CFG=<k> forces one (A/B timing).
+// gives the chip at least eight waves, otherwise the short-chain one (equal throughput at many waves -- 4096^2: 239 vs
+// 256 us, 2048^2: 74 vs 74 -- but half the per-CTA time and two CTAs per SM: less wave quantisation on slabs).  P2B_TB_CFG=<k> forces one (A/B timing).
 static int tb_choose(const p2b_mg* m, const MgLevel& L)
 {
     static int forced = -2;
@@ -181,7 +182,7 @@ static int tb_choose(const p2b_mg* m, const MgLevel& L)
     (void)m;
     const TbCfg big = tb_cfg(0);
     const long long ctas = (long long)((L.n + TB_TJ - 1) / TB_TJ) * ((L.ni + big.TI - 1) / big.TI);
-    return ctas >= 2LL * num_sms() ? 0 : 1;
+    return ctas >= 8LL * num_sms() ? 0 : 1;
 }
 
 static void tb_launch(int cfg, dim3 grd, cudaStream_t st, const MgLevel& L, const double* src, double* dst, const MgBC& b,

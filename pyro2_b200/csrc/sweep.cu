@@ -4,6 +4,8 @@
 // the conserved state are staged into the warp's shared-memory ring by the TMA engine
 // (cp.async.bulk 1-d copies completing on an mbarrier: UBLKCP in SASS); no block-wide barrier is
 // ever executed after the mbarrier initialisation.
+#include <cuda.h>            // CUtensorMap and the encode entry point's types only: no libcuda at link time
+
 #include "common.cuh"
 #include "sweep_args.cuh"
 
@@ -33,36 +35,48 @@ struct CudaWarp {
     __device__ __forceinline__ double down(double v) const { return __shfl_down_sync(0xffffffffu, v, 1); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
 
-    // lane 0 arms the slot's mbarrier with the byte count and issues one bulk copy per variable
-    __device__ __forceinline__ void load_issue(unsigned long long& mbar, double* d0, double* d1, double* d2,
-                                               double* d3, const double* src, long long plane_stride,
-                                               int ncols) const
+    // lane 0 arms the slot's mbarrier with the byte count and issues ONE 3-d tensor copy (38 columns x 1 row x 4 planes,
+    // UTMALDG in SASS) through the launch's tensor map; columns past the end of the row arrive as zeros.  Without a tensor
+    // map (P2B_SWEEP_NO_TMAP builds / driver without cuTensorMapEncodeTiled): one 1-d bulk copy per plane (UBLKCP).
+    const CUtensorMap* tmap;
+    __device__ __forceinline__ void load_issue(unsigned long long& mbar, double* dst, const double* U, long long plane_stride,
+                                               int pitch, int r, int col0, int ncols) const
     {
         if (lane() == 0) {
-            const uint32_t bytes = (uint32_t)ncols * 8u;
             const uint32_t bar = smem_u32(&mbar);
             // the slot was last written through the generic proxy (cons->prim in place); order
-            // those writes before the async-proxy writes of the bulk copies
+            // those writes before the async-proxy writes of the copy
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 4u)
-                         : "memory");
-            double* dst[4] = {d0, d1, d2, d3};
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            if (tmap) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * SW_QW * 8u) : "memory");
                 asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        smem_u32(dst[n])),
-                    "l"(src + n * plane_stride), "r"(bytes), "r"(bar)
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(smem_u32(dst)), "l"(tmap), "r"(col0), "r"(r), "r"(0), "r"(bar)
                     : "memory");
+            } else {
+                const uint32_t bytes = (uint32_t)ncols * 8u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 4u) : "memory");
+                const double* src = U + (long long)r * pitch + col0;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            smem_u32(dst + n * SW_QW)),
+                        "l"(src + n * plane_stride), "r"(bytes), "r"(bar)
+                        : "memory");
+                }
             }
         }
     }
 
+    // bounded: a copy that never lands (a bad tensor map, a protocol error) must not hang the device -- after ~1 s the warp
+    // gives up, raises the status word (2) and carries on with whatever the slot holds
+    int* status;
     __device__ __forceinline__ void load_wait(unsigned long long& mbar, unsigned parity) const
     {
         const uint32_t bar = smem_u32(&mbar);
         uint32_t done = 0;
-        while (!done) {
+        for (unsigned spins = 0; !done; ++spins) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -70,6 +84,7 @@ struct CudaWarp {
                 : "=r"(done)
                 : "r"(bar), "r"(parity)
                 : "memory");
+            if (spins > (1u << 22)) { if (status) *status = 2; break; }
         }
     }
 
@@ -88,9 +103,9 @@ struct CudaWarp {
 
 template <bool GRAV, int RIEMANN, bool SPH = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
-sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
+sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks, const __grid_constant__ CUtensorMap tmap, int use_tmap)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     SweepSmem& S = reinterpret_cast<SweepSmem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -102,6 +117,8 @@ sweep_kernel(SweepArgs A, unsigned long long* task_counter, int ntasks)
     __syncwarp();
 
     CudaWarp w;
+    w.tmap = use_tmap ? &tmap : nullptr;
+    w.status = A.status;
     SweepTask<CudaWarp, GRAV, RIEMANN, SPH> T(w, A, S, 0u);
     for (;;) {
         int t = 0;
@@ -129,7 +146,50 @@ __global__ void fastmath_probe_kernel(int op, const double* a, const double* b, 
     }
 }
 
-static int g_last_ntasks = 0, g_last_resident = 0, g_last_seglen = 0;
+// The tensor map of one state buffer: a rank-3 fp64 tensor (columns, rows, 4 planes) with the planes' row pitch and plane
+// stride, box = 38 columns x 1 row x 4 planes, out-of-range columns filled with zeros.  cuTensorMapEncodeTiled comes from
+// the driver through the runtime (cudaGetDriverEntryPoint): libcuda is not a link-time dependency.  Encoding is host-only
+// arithmetic (~1 us), done per launch because the buffers alternate.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+#ifndef P2B_SWEEP_NO_TMAP
+        if (!getenv("P2B_SWEEP_NO_TMAP")) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = (EncodeTiledFn)p;
+            cudaGetLastError();
+        }
+#endif
+    }
+    return fn;
+}
+
+static bool make_tensor_map(CUtensorMap* tm, const SweepArgs& A)
+{
+    EncodeTiledFn enc = encode_tiled();
+    memset(tm, 0, sizeof *tm);
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)A.pitch, (cuuint64_t)(A.nx + 2 * A.ng), 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)A.pitch * 8, (cuuint64_t)A.plane_stride * 8};     // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {SW_QW, 1, 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (strides[0] % 16 || strides[1] % 16) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(A.Uin), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_last_ntasks = 0, g_last_tmap = 0, g_last_resident = 0, g_last_seglen = 0;
 
 // function attributes and SM counts are per device: cached per device ordinal
 static int resident_warps()
@@ -185,17 +245,20 @@ int p2b_compressible_sweep(const double* Uin, double* Uout, const p2b_grid* g, c
     const size_t smem = SWEEP_WARPS * sizeof(SweepSmem);
     unsigned long long* counter = (unsigned long long*)(scratch + 2);
     const bool grav = sweep_has_sources(prm);
+    alignas(64) CUtensorMap tm;
+    const int tmap = make_tensor_map(&tm, A) ? 1 : 0;
+    g_last_tmap = tmap;
     if (prm->geo_i) {
-        sweep_kernel<true, 1, true><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        sweep_kernel<true, 1, true><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
     } else if (prm->riemann == 2) {
-        if (grav) sweep_kernel<true, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
-        else sweep_kernel<false, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        if (grav) sweep_kernel<true, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
+        else sweep_kernel<false, 2><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
     } else if (prm->riemann == 1) {
-        if (grav) sweep_kernel<true, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
-        else sweep_kernel<false, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        if (grav) sweep_kernel<true, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
+        else sweep_kernel<false, 1><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
     } else {
-        if (grav) sweep_kernel<true, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
-        else sweep_kernel<false, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks);
+        if (grav) sweep_kernel<true, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
+        else sweep_kernel<false, 0><<<blocks, SWEEP_THREADS, smem, st>>>(A, counter, ntasks, tm, tmap);
     }
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
@@ -209,6 +272,9 @@ int p2b_test_fastmath(int op, const double* a, const double* b, double* out, int
     P2B_CUDA_CHECK(cudaGetLastError());
     return P2B_OK;
 }
+
+// 1: the last sweep staged its rows with 3-d tensor-map copies (UTMALDG), 0: with 1-d bulk copies (UBLKCP)
+int p2b_sweep_uses_tensor_map(void) { return g_last_tmap; }
 
 int p2b_sweep_info(int* ntasks, int* resident_warps_out, int* seglen)
 {

@@ -81,8 +81,14 @@ struct SweepArgs {
     int src_flip_xlo, src_flip_xhi;   // 1: that x boundary is "reflect" -> the ghost-row SOURCES change sign
 };
 
-struct alignas(16) SweepSmem {
-    double q[4][SW_RING][SW_QW];      // raw U on arrival, primitives after ready()
+// One ring slot = one staged row: the four variables' 38 columns back to back -- the box of ONE 3-d TMA tensor copy
+// (columns x 1 row x 4 planes, 1216 bytes) -- padded to the 128-byte alignment the tensor engine wants for its destination.
+struct alignas(128) SweepSlot {
+    double p[4][SW_QW];               // raw U on arrival, primitives after ready()
+    double pad[8];
+};
+struct alignas(128) SweepSmem {
+    SweepSlot q[SW_RING];
     double xch[5][SW_XW];             // [0] xi_y, [1..4] limit2_y of the 4 primitives
     unsigned long long mbar[SW_RING];
 };
@@ -112,7 +118,7 @@ struct SweepTask {
 
     HD SweepTask(W& w_, const SweepArgs& a, SweepSmem& s, unsigned ph) : w(w_), A(a), S(s), phase_base(ph), row_base(0) {}
 
-    HD double& Q(int n, int r, int c) { return S.q[n][r & (SW_RING - 1)][c]; }
+    HD double& Q(int n, int r, int c) { return S.q[r & (SW_RING - 1)].p[n][c]; }
 
     // the Riemann problem at a face; `wall`: the face lies on a solid lower boundary (CGF only)
     HD Flux riemann(double rho_l, double E_l, double mn_l, double mt_l, double rho_r, double E_r, double mn_r,
@@ -140,12 +146,12 @@ struct SweepTask {
 #pragma unroll 1
         for (int c = w.lane(); c < SW_QW; c += 32) {
             Cons U;
-            U.dens = S.q[IDENS][slot][c]; U.ener = S.q[IENER][slot][c];
-            U.xmom = S.q[IXMOM][slot][c]; U.ymom = S.q[IYMOM][slot][c];
+            U.dens = S.q[slot].p[IDENS][c]; U.ener = S.q[slot].p[IENER][c];
+            U.xmom = S.q[slot].p[IXMOM][c]; U.ymom = S.q[slot].p[IYMOM][c];
             bool bad;
             Prim p = cons_to_prim(U, A.gamma, &bad);
-            S.q[IRHO][slot][c] = p.rho; S.q[IU][slot][c] = p.u;
-            S.q[IV][slot][c] = p.v;     S.q[IP][slot][c] = p.p;
+            S.q[slot].p[IRHO][c] = p.rho; S.q[slot].p[IU][c] = p.u;
+            S.q[slot].p[IV][c] = p.v;     S.q[slot].p[IP][c] = p.p;
             int j = col0 + c;
             if (bad && row_valid && j >= jvalid_lo && j < jvalid_hi) anybad = true;
         }
@@ -156,9 +162,8 @@ struct SweepTask {
     HD void issue(int r, int col0, int ncols)
     {
         const int slot = r & (SW_RING - 1);
-        const double* src = A.Uin + (long long)r * A.pitch + col0;
-        w.load_issue(S.mbar[slot], &S.q[0][slot][0], &S.q[1][slot][0], &S.q[2][slot][0],
-                     &S.q[3][slot][0], src, A.plane_stride, ncols);
+        // row r, columns col0 .. col0 + 37 of the four planes -> the slot (columns past the end of the row: not read)
+        w.load_issue(S.mbar[slot], &S.q[slot].p[0][0], A.Uin, A.plane_stride, A.pitch, r, col0, ncols);
     }
 
     HD double flat_x(int r, int c, const FlatPar& fp)

@@ -124,7 +124,8 @@ def compressible_sweep(Uin, Uout, nx, ny, ng, dx, dy, dt, params, scratch):
 def sweep_info():
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     _lib.lib().p2b_sweep_info(C.byref(a), C.byref(b), C.byref(c))
-    return {"ntasks": a.value, "resident_warps": b.value, "seglen": c.value}
+    return {"ntasks": a.value, "resident_warps": b.value, "seglen": c.value,
+            "tensor_map_tma": bool(_lib.lib().p2b_sweep_uses_tensor_map())}
 
 
 class _RawDeviceMemory:

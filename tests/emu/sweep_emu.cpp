@@ -42,12 +42,16 @@ struct EmuWarp {
     double up(double v) const { return exchange(v, lane_ - 1); }
     double down(double v) const { return exchange(v, lane_ + 1); }
 
-    void load_issue(unsigned long long&, double* d0, double* d1, double* d2, double* d3, const double* src,
-                    long long plane_stride, int ncols) const
+    void load_issue(unsigned long long&, double* dst, const double* U, long long plane_stride, int pitch, int r, int col0,
+                    int ncols) const
     {
         if (lane_ == 0) {
-            double* dst[4] = {d0, d1, d2, d3};
-            for (int n = 0; n < 4; ++n) memcpy(dst[n], src + n * plane_stride, (size_t)ncols * 8);
+            const double* src = U + (long long)r * pitch + col0;
+            for (int n = 0; n < 4; ++n) {
+                memcpy(dst + n * pyro::SW_QW, src + n * plane_stride, (size_t)ncols * 8);
+                // the tensor copy of the device fills what lies past the end of the row with zeros
+                for (int c = ncols; c < pyro::SW_QW; ++c) dst[n * pyro::SW_QW + c] = 0.0;
+            }
         }
     }
     void load_wait(unsigned long long&, unsigned) const { pthread_barrier_wait(&ws->bar); }

@@ -60,6 +60,8 @@ class EmuLibrary:
             return self._counted(name, self._sweep)
         if name == "p2b_sweep_info":
             return self._sweep_info
+        if name == "p2b_sweep_uses_tensor_map":
+            return lambda: 0
         if name == "p2b_test_fastmath":
             lib = emu_util.load_sweep_emu()
             return lambda op, a, b, out, n, stream: lib.emu_test_fastmath(op, a, b, out, n)
