@@ -224,6 +224,20 @@ int p2b_mg_exchange(p2b_mg* m, int level, int which, int depth, void* stream);  
 int p2b_mg_set_stop(p2b_mg* m, int enable, double source_norm, double rtol, int max_cycles, void* stream);
 int p2b_mg_result(p2b_mg* m, double* out4, long long* comm_error, void* stream);   /* (relsq, rsq, residual_error, cycles); syncs */
 void* p2b_mg_control_ptr(p2b_mg* m);
+/* halo rows of the STATE planes of a decomposed run (HP-1 and the explicit solvers) through peer memory, and the maximum
+ * of four 64-bit words over the ranks (wave speeds + status for the next dt): csrc/slab_comm.cu.  The control block and the
+ * registered plane buffers are p2b_shared_alloc'd and mapped into every rank; ctl_peers / peer_bases list them as mapped
+ * here ([rank] = the local one).  Replaces one grid's interior copy in ArrayIndexer.fill_ghost
+ * (pyro/mesh/array_indexer.py:157-274) across slab boundaries. */
+typedef struct p2b_slab p2b_slab;
+long long p2b_slab_ctl_bytes(void);
+p2b_slab* p2b_slab_create(int rank, int size, int periodic, void* const* ctl_peers);
+int p2b_slab_destroy(p2b_slab* s);
+int p2b_slab_register(p2b_slab* s, int k, void* local_base, long long bytes, void* const* peer_bases);
+int p2b_slab_owns(p2b_slab* s, const void* planes);
+int p2b_slab_exchange(p2b_slab* s, double* planes, int nvar, long long plane_stride, int pitch, int nx, int ng, void* stream);
+int p2b_slab_allreduce_max4(p2b_slab* s, uint64_t* words, void* stream);
+int p2b_slab_error(p2b_slab* s, void* stream);
 void* p2b_shared_alloc(long long bytes);                  /* cudaMalloc'd + zeroed; mappable by other processes */
 int p2b_shared_free(void* p);
 int p2b_shared_handle(void* p, unsigned char* out64);     /* 64 opaque bytes (cudaIpcMemHandle_t) */

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # P2B_SO overrides the library path (A/B timing of kernel variants during development)
 SO_PATH = os.environ.get("P2B_SO") or os.path.join(CSRC, "libpyro2b200.so")
-SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu", "lm.cu"]
-HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "sweep_args.cuh", "mg_kernels.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "lm_kernels.cuh", "../../include/pyro2b200.h"]
+SOURCES = ["ghost_cfl.cu", "sweep.cu", "mg.cu", "flow.cu", "bc_user.cu", "lm.cu", "slab_comm.cu"]
+HEADERS = ["common.cuh", "hydro_core.cuh", "sweep_task.cuh", "sweep_args.cuh", "mg_kernels.cuh", "peer_comm.cuh", "flow_kernels.cuh", "bc_user_kernels.cuh", "lm_kernels.cuh", "../../include/pyro2b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 
@@ -153,6 +153,14 @@ SIGNATURES = {
     "p2b_mg_set_stop": (_i, [_vp, _i, _d, _d, _i, _vp]),
     "p2b_mg_result": (_i, [_vp, C.POINTER(_d), C.POINTER(_ll), _vp]),
     "p2b_mg_control_ptr": (_vp, [_vp]),
+    "p2b_slab_ctl_bytes": (_ll, []),
+    "p2b_slab_create": (_vp, [_i, _i, _i, C.POINTER(_vp)]),
+    "p2b_slab_destroy": (_i, [_vp]),
+    "p2b_slab_register": (_i, [_vp, _i, _vp, _ll, C.POINTER(_vp)]),
+    "p2b_slab_owns": (_i, [_vp, _vp]),
+    "p2b_slab_exchange": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _vp]),
+    "p2b_slab_allreduce_max4": (_i, [_vp, _vp, _vp]),
+    "p2b_slab_error": (_i, [_vp, _vp]),
     "p2b_shared_alloc": (_vp, [_ll]),
     "p2b_shared_free": (_i, [_vp]),
     "p2b_shared_handle": (_i, [_vp, C.c_char_p]),

@@ -124,7 +124,16 @@ class Simulation(NullSimulation):
         my_data.register_var("y-momentum", bc_yodd)
         my_data.set_aux("gamma", rp.get_param("eos.gamma"))
         my_data.set_aux("grav", rp.get_param("compressible.grav"))
-        my_data.create()
+        dec = self.decomposition
+        from .. import _lib as _libmod
+        on_device = my_grid.device.type == "cuda" or getattr(_libmod.lib(), "is_emulated", False)
+        peer = dec is not None and dec.size > 1 and on_device and hasattr(dec, "shared_planes")
+        if peer:
+            # decomposed: both state buffers live in memory the neighbours can write -- halo rows and the wave-speed
+            # reduction then go through peer memory (csrc/slab_comm.cu) instead of NCCL
+            my_data.create(planes=dec.shared_planes(my_data.nvar, my_grid.qx, my_grid.qy, bc.xlb == "periodic"))
+        else:
+            my_data.create()
         my_data.decomposition = self.decomposition
         self.cc_data = my_data
         # artificial viscosity is left unset on the GLOBAL +x face only
@@ -135,7 +144,8 @@ class Simulation(NullSimulation):
         self.cc_data.add_derived(derives.derive_primitives)
 
         # second state buffer (the sweep is out of place) and the device scratch words
-        self._alt_planes = torch.zeros_like(my_data.planes)
+        self._alt_planes = (dec.shared_planes(my_data.nvar, my_grid.qx, my_grid.qy, bc.xlb == "periodic") if peer
+                            else torch.zeros_like(my_data.planes))
         self._scratch = ops.new_scratch()
         self._wave_version = None     # cc_data.version for which the cached wave speeds are valid
         self._pending_status = False

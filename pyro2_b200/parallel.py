@@ -47,10 +47,58 @@ class SlabDecomposition:
             lo = hi = None   # single slab: periodic wrap is the ordinary local ghost fill
         return lo, hi
 
+    # ---- peer-memory transport (csrc/slab_comm.cu): planes allocated through shared_planes() are exchanged by kernels
+    # that store straight into the neighbours' ghost rows; everything else goes over torch.distributed as before ----
+    _peer = None
+
+    def shared_planes(self, nvar, qx, qy, periodic):
+        """collective: (nvar, qx, pitch) float64 planes in device memory every rank can write, registered with this
+        decomposition's peer communicator (created on first use; `periodic`: the x direction wraps)"""
+        import ctypes as C
+        from . import _lib, ops
+        L = _lib.lib()
+        if self._peer is None:
+            nbytes = L.p2b_slab_ctl_bytes()
+            ctl = L.p2b_shared_alloc(nbytes)
+            if not ctl:
+                raise RuntimeError(L.p2b_last_error().decode())
+            ptrs = self.map_peer_workspaces(ctl)
+            h = L.p2b_slab_create(self.rank, self.size, int(bool(periodic)), (C.c_void_p * self.size)(*ptrs))
+            if not h:
+                raise RuntimeError(L.p2b_last_error().decode())
+            self._peer = {"handle": h, "periodic": bool(periodic), "nbuf": 0, "keep": [ctl]}
+        if self._peer["periodic"] != bool(periodic) or self._peer["nbuf"] >= 4:
+            raise ValueError("peer communicator: one periodicity and at most four buffers per decomposition")
+        pitch = ops.row_pitch(qy)
+        nelem = nvar * qx * pitch
+        ptr = L.p2b_shared_alloc(nelem * 8)
+        if not ptr:
+            raise RuntimeError(L.p2b_last_error().decode())
+        peers = self.map_peer_workspaces(ptr)
+        _lib.check(L.p2b_slab_register(self._peer["handle"], self._peer["nbuf"], C.c_void_p(ptr), nelem * 8,
+                                       (C.c_void_p * self.size)(*peers)))
+        self._peer["nbuf"] += 1
+        self._peer["keep"].append(ptr)
+        return ops.tensor_from_pointer(ptr, nelem).view(nvar, qx, pitch)
+
+    def _peer_owns(self, t, periodic):
+        if self._peer is None or self._peer["periodic"] != bool(periodic) or not t.is_cuda:
+            return False
+        from . import _lib
+        import ctypes as C
+        return bool(_lib.lib().p2b_slab_owns(self._peer["handle"], C.c_void_p(t.data_ptr())))
+
     def exchange(self, planes, nx, ng, periodic=False):
         """fill the x ghost rows that face another slab with that slab's boundary rows.
         planes: (nvar, qx, pitch); rows of a plane are contiguous, so each plane's ng-row block is
-        sent / received in place."""
+        sent / received in place (torch.distributed) or stored by a kernel into the neighbour's ghost rows (planes
+        from shared_planes())."""
+        if self._peer_owns(planes, periodic):
+            import ctypes as C
+            from . import _lib
+            _lib.check(_lib.lib().p2b_slab_exchange(self._peer["handle"], C.c_void_p(planes.data_ptr()), planes.shape[0],
+                                                    planes.stride(0), planes.stride(1), nx, ng, _lib.stream_ptr()))
+            return
         lo, hi = self.neighbours(periodic)
         ops = []
         # Posting order matters when both neighbours are the same rank (2 slabs, periodic): messages
@@ -95,8 +143,22 @@ class SlabDecomposition:
 
     def allreduce_max_(self, t):
         if self.size > 1:
+            if self._peer is not None and t.is_cuda and t.dtype == torch.int64 and t.numel() == 4 and t.is_contiguous():
+                # the sweep's scratch words (wave-speed maxima as bit patterns, status): reduced through peer slots
+                import ctypes as C
+                from . import _lib
+                _lib.check(_lib.lib().p2b_slab_allreduce_max4(self._peer["handle"], C.c_void_p(t.data_ptr()), _lib.stream_ptr()))
+                return t
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
+
+    def check_peer(self):
+        """raise if a wait of the peer-memory transport timed out (synchronises)"""
+        if self._peer is not None:
+            from . import _lib
+            e = _lib.lib().p2b_slab_error(self._peer["handle"], _lib.stream_ptr())
+            if e:
+                raise RuntimeError(f"slab communicator: a wait on a neighbouring rank timed out (control word {e - 1})")
 
     def interior_sides(self, periodic):
         """(low_is_interior, high_is_interior)"""
@@ -139,7 +201,11 @@ class _LocalSlab(SlabDecomposition):
         self._g._barrier.wait()
 
     def exchange(self, planes, nx, ng, periodic=False):
-        raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")
+        if not self._peer_owns(planes, periodic):
+            raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")
+        super().exchange(planes, nx, ng, periodic)
 
     def allreduce_max_(self, t):
-        raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")
+        if self._peer is None or t.dtype != torch.int64 or t.numel() != 4:
+            raise NotImplementedError("ranks that share a process exchange through the library's peer-memory kernels only")
+        return super().allreduce_max_(t)

@@ -5,6 +5,7 @@
 #include "cuda_emu_runtime.inc"
 
 #include "../../pyro2_b200/csrc/ghost_cfl.cu"
+#include "../../pyro2_b200/csrc/slab_comm.cu"
 
 namespace {
 struct RegisterThreaded {

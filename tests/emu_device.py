@@ -36,7 +36,9 @@ class EmuLibrary:
     ROUTES = (("p2b_mg_", emu_util.load_mg_emu), ("p2b_shared_", emu_util.load_mg_emu), ("p2b_flow_", emu_util.load_flow_emu), ("p2b_lm_", emu_util.load_lm_emu),
               ("p2b_fill_hse", emu_util.load_bc_emu), ("p2b_fill_ambient", emu_util.load_bc_emu),
               ("p2b_fill_ghost", emu_util.load_ghost_emu), ("p2b_cfl_wavemax", emu_util.load_ghost_emu),
-              ("p2b_device_sms", emu_util.load_ghost_emu))
+              ("p2b_device_sms", emu_util.load_ghost_emu), ("p2b_slab_", emu_util.load_ghost_emu))
+
+    is_emulated = True
 
     def __init__(self):
         self.calls = {}          # symbol -> number of calls, for the tests to see what really ran

@@ -69,7 +69,7 @@ def load_bc_emu():
 
 def load_ghost_emu():
     """pyro2_b200/csrc/ghost_cfl.cu compiled for the host: ghost fill and CFL wave speeds over numpy memory"""
-    return _load("ghost", ["ghost_cfl.cu"], ("p2b_fill_ghost", "p2b_cfl_wavemax", "p2b_device_sms"))
+    return _load("ghost", ["ghost_cfl.cu", "slab_comm.cu", "peer_comm.cuh"], ("p2b_fill_ghost", "p2b_cfl_wavemax", "p2b_device_sms", "p2b_slab_"))
 
 
 def load_sweep_emu():

@@ -121,6 +121,9 @@ def _emulated_run_worker(rank, size, port, problem, nx, ny, nsteps, q):
             p.sim.check_state()
             g = p.sim.cc_data.grid
             assert g.nx == nx // size and dev.calls["p2b_compressible_sweep"] == nsteps
+            # the state's halo rows and the wave-speed reduction went through peer memory (csrc/slab_comm.cu), not gloo
+            assert dev.calls.get("p2b_slab_exchange", 0) >= nsteps and dev.calls.get("p2b_slab_allreduce_max4", 0) >= nsteps - 1
+            p.sim.decomposition.check_peer()
             mine = p.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].contiguous()
             parts = [torch.empty_like(mine) for _ in range(size)] if rank == 0 else None
             dist.gather(mine, parts, dst=0)
