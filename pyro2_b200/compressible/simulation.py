@@ -261,9 +261,11 @@ class Simulation(NullSimulation):
             wx, wy = ops.cfl_wavemax(self.cc_data.planes, g.nx, g.ny, g.ng, self.rp.get_param("eos.gamma"),
                                      self._scratch)
             if self.decomposition is not None and self.decomposition.size > 1:
-                w = self.decomposition.allreduce_max_(torch.tensor([wx, wy], dtype=torch.float64,
-                                                                   device=self.cc_data.planes.device))
-                wx, wy = w.tolist()
+                # as four 64-bit words (positive doubles order like their bit patterns): the form the peer-memory
+                # reduction of the sweep's scratch words takes, so this path needs no other transport
+                w = torch.tensor([wx, wy, 0.0, 0.0], dtype=torch.float64, device=self.cc_data.planes.device).view(torch.int64)
+                self.decomposition.allreduce_max_(w)
+                wx, wy = w.view(torch.float64)[:2].tolist()
         self.dt = cfl * float(min(g.dx / wx, g.dy / wy))
 
     def evolve(self):

@@ -331,3 +331,63 @@ def test_streamed_steps_are_bit_identical_to_resident_steps(nx, ny, nchunks, pro
     torch.cuda.synchronize()
     assert p.sim.dt == ref.sim.dt
     assert torch.equal(bufs[1][:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1], ref.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].cpu())
+
+
+def compressible_slabs_in_one_process(size, problem, nx, ny, nsteps):
+    """a decomposed Pyro("compressible") run whose slabs live in ONE process (a host thread and a stream each; halo rows
+    and the wave-speed reduction through the peer-memory transport of csrc/slab_comm.cu over plain pointers) against the
+    single-domain run.  Shared by the GPU test below and the emulated-device CPU test."""
+    import contextlib
+    import threading
+
+    import torch
+    from pyro2_b200.parallel import LocalSlabGroup
+    from pyro2_b200.pyro_sim import Pyro
+    inputs = {"mesh.nx": nx, "mesh.ny": ny, "driver.max_steps": 10 ** 6, "driver.tmax": 1e9}
+    # the single-domain run first: it also loads every kernel (a lazily loaded kernel must not meet a spinning one)
+    s = Pyro("compressible")
+    s.initialize_problem(problem, inputs_dict=inputs)
+    dts1 = []
+    for _ in range(nsteps):
+        s.single_step()
+        dts1.append(s.sim.dt)
+    s.sim.check_state()
+    g1 = s.sim.cc_data.grid
+    one = s.sim.cc_data.planes[:, g1.ilo:g1.ihi + 1, g1.jlo:g1.jhi + 1].cpu().numpy().copy()
+    group = LocalSlabGroup(size)
+    out, errs = [None] * size, []
+
+    def run(rank):
+        try:
+            stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+            with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+                p = Pyro("compressible")
+                p.initialize_problem(problem, inputs_dict=inputs, decomposition=group.member(rank))
+                dts = []
+                for _ in range(nsteps):
+                    p.single_step()
+                    dts.append(p.sim.dt)
+                p.sim.check_state()
+                p.sim.decomposition.check_peer()
+                g = p.sim.cc_data.grid
+                out[rank] = (p.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].cpu().numpy().copy(), dts)
+        except Exception as exc:   # pylint: disable=broad-except
+            import traceback
+            errs.append(traceback.format_exc() + repr(exc))
+            group._barrier.abort()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(size)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(600)
+    assert not errs, errs
+    assert all(o[1] == dts1 for o in out)
+    return np.concatenate([o[0] for o in out], axis=1), one
+
+
+@pytest.mark.parametrize("size,problem,nx,ny,nsteps", [(2, "sedov", 128, 64, 12), (2, "kh", 64, 48, 8), (4, "quad", 128, 32, 8)])
+def test_compressible_slabs_sharing_one_gpu_are_bit_identical(size, problem, nx, ny, nsteps):
+    """HP-1 on x-slabs with the peer-memory transport, on ONE device (the driver's GPU-test box has one): each slab a host
+    thread + stream; state and every dt identical to the single-domain run (kh: periodic x, both neighbours the same slab)"""
+    full, one = compressible_slabs_in_one_process(size, problem, nx, ny, nsteps)
+    assert np.array_equal(full, one)

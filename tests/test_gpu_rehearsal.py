@@ -171,3 +171,15 @@ def test_scale_tests_rehearsed_small():
     with emu_device.emulated_device():
         ts.test_sedov_through_the_driver_at_scale(64, (1, 6))
         ts.test_multigrid_2048_cycle_by_cycle(128)
+
+
+def test_compressible_slabs_as_threads_on_the_emulated_device():
+    """the hardware test of the same name minus the hardware: two compressible slabs as host threads of one process,
+    halo rows and the wave-speed reduction through the emulated peer memory"""
+    import numpy as np
+
+    import emu_device
+    from test_gpu_api import compressible_slabs_in_one_process
+    with emu_device.emulated_device():
+        full, one = compressible_slabs_in_one_process(2, "sedov", 32, 16, 4)
+    assert np.array_equal(full, one)
