@@ -525,6 +525,14 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
         for (int a = 0; a < 2; ++a) { col_lo[a] = (gj0 + a == 1); col_hi[a] = (gj0 + a == n); }
     }
 
+    // warp-uniform: does this warp hold a boundary row / does any of its lanes hold a boundary column?
+    const bool row_edge = EDGE && (row_lo | row_hi) != 0u;
+#ifdef P2B_EMU_HEADER
+    const bool col_edge = EDGE;                    // (the emulator has no warp vote: always take the guarded selects)
+#else
+    const bool col_edge = EDGE && __any_sync(0xffffffffu, col_lo[0] || col_lo[1] || col_hi[0] || col_hi[1]);
+#endif
+
     if (VC) tile_copy_wait();                      // the coefficient tiles requested above have landed
 
     double uph[2] = {0.0, 0.0}, dnh[2] = {0.0, 0.0};   // rows just above / below this thread's strip
@@ -572,10 +580,16 @@ __device__ __forceinline__ void smooth_tb_body(const MgLevel& L, const double* _
                     grow = L.ioff + gi;
                     grow = grow < 1 ? grow + n : (grow > n ? grow - n : grow);
                 }
-                if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
-                if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
-                if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, grow, L.dy);
-                if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, grow, L.dy);
+                // (warp-uniform guards: a warp's rows are the same for all lanes, and whether any lane holds a boundary
+                // column was voted once -- most warps of a boundary tile touch no boundary and skip the selects)
+                if (row_edge) {
+                    if ((row_lo >> r) & 1u) up = ghost_lo(self, b.xl, b.xlv, gj, L.dx);
+                    if ((row_hi >> r) & 1u) dn = ghost_hi(self, b.xr, b.xrv, gj, L.dx);
+                }
+                if (col_edge) {
+                    if (col_lo[a]) lf = ghost_lo(self, b.yl, b.ylv, grow, L.dy);
+                    if (col_hi[a]) rt = ghost_hi(self, b.yr, b.yrv, grow, L.dy);
+                }
             }
             if (VC) {
                 const int rr = w * TB_R + r;

@@ -21,6 +21,7 @@
 namespace pyro {
 
 constexpr int SLAB_MAX_RANKS = 16;
+constexpr int SLAB_MAX_BUFFERS = 64;    // plane buffers one communicator can hold (two per compressible simulation)
 enum { SW_EPOCH = 0, SW_ERR = COMM_ERR_WORD, SW_FROM_LO = 2, SW_FROM_HI = 3, SW_CNT = 4, SW_GFLAG = 8 /* [16] */,
        SW_SLOTS = 24 /* u64 [2][16][4] */, SW_WORDS = 24 + 2 * 16 * 4 };
 
@@ -113,9 +114,9 @@ struct p2b_slab {
     unsigned long long* peer_ctl[SLAB_MAX_RANKS];
     long long* peer_off_dev;                        // device copy of the control-word offsets (inside the ctl block's tail)
     int nbuf;
-    double* base[4];
-    long long bytes[4];
-    double* peer_base[4][SLAB_MAX_RANKS];
+    double* base[SLAB_MAX_BUFFERS];
+    long long bytes[SLAB_MAX_BUFFERS];
+    double* peer_base[SLAB_MAX_BUFFERS][SLAB_MAX_RANKS];
 };
 
 static SlabComm slab_comm(const p2b_slab* s)
@@ -164,7 +165,7 @@ int p2b_slab_destroy(p2b_slab* s) { delete s; return P2B_OK; }
 // it can then be exchanged
 int p2b_slab_register(p2b_slab* s, int k, void* local_base, long long bytes, void* const* peer_bases)
 {
-    P2B_REQUIRE(s && k >= 0 && k < 4 && local_base && peer_bases && bytes > 0, "bad buffer registration");
+    P2B_REQUIRE(s && k >= 0 && k < SLAB_MAX_BUFFERS && local_base && peer_bases && bytes > 0, "bad buffer registration");
     P2B_REQUIRE(peer_bases[s->rank] == local_base, "peer_bases[rank] must be the local buffer");
     s->base[k] = (double*)local_base; s->bytes[k] = bytes;
     for (int r = 0; r < s->size; ++r) s->peer_base[k][r] = (double*)peer_bases[r];

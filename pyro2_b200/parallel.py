@@ -67,8 +67,9 @@ class SlabDecomposition:
             if not h:
                 raise RuntimeError(L.p2b_last_error().decode())
             self._peer = {"handle": h, "periodic": bool(periodic), "nbuf": 0, "keep": [ctl]}
-        if self._peer["periodic"] != bool(periodic) or self._peer["nbuf"] >= 4:
-            raise ValueError("peer communicator: one periodicity and at most four buffers per decomposition")
+        if self._peer["periodic"] != bool(periodic) or self._peer["nbuf"] >= 64:
+            raise ValueError("peer communicator: one periodicity and at most 64 plane buffers per decomposition "
+                             "(use a fresh SlabDecomposition for a problem with another x boundary type)")
         pitch = ops.row_pitch(qy)
         nelem = nvar * qx * pitch
         ptr = L.p2b_shared_alloc(nelem * 8)
