@@ -183,3 +183,15 @@ def test_compressible_slabs_as_threads_on_the_emulated_device():
     with emu_device.emulated_device():
         full, one = compressible_slabs_in_one_process(2, "sedov", 32, 16, 4)
     assert np.array_equal(full, one)
+
+
+def test_stored_reference_goldens_rehearsed():
+    """tests/test_gpu_zzz_reference_h5.py on the emulated device: the product against the regression files the reference
+    itself stores (Sod 128 x 10 after 76 steps; the 256^2 Dirichlet multigrid solve, bit for bit)"""
+    import emu_device
+    import test_gpu_zzz_reference_h5 as t
+    import os
+    with emu_device.emulated_device():
+        t.test_pyro_sod_matches_the_stored_reference_golden()
+        if os.environ.get("P2B_FULL_TESTS"):          # ~100 s of emulated 256^2 V-cycles
+            t.test_multigrid_matches_the_stored_reference_golden()

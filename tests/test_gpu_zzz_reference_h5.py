@@ -1,0 +1,44 @@
+"""GPU: the public API against the regression files the REFERENCE ITSELF STORES (tests/golden/refh5_*.npz, re-packed from
+pyro's .h5 goldens by tests/golden/make_h5_golden.py with the pure-Python reader tests/h5lite.py):
+
+  pyro/compressible/tests/sod_x_0076.h5         Pyro("compressible"), problem sod, 128 x 10, 76 steps   (1e-12 of scale)
+  pyro/multigrid/tests/mg_poisson_dirichlet.h5  CellCenterMG2d(256, 256).solve(rtol=1e-11)             (solution bit for bit)
+
+(The file sorts last on purpose: these cases were added after the round's last GPU run and are rehearsed on the emulated
+device, tests/test_gpu_rehearsal.py.)"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_pyro_sod_matches_the_stored_reference_golden():
+    from golden_util import load_comp
+    from pyro2_b200.pyro_sim import Pyro
+    stored = np.load(os.path.join(GOLDEN, "refh5_sod_x_0076.npz"))
+    z, rp, inputs = load_comp("sod_x")
+    p = Pyro("compressible")
+    p.initialize_problem("sod", inputs_dict=dict(inputs, **{"driver.max_steps": 100000}))
+    for _ in range(76):
+        p.single_step()
+    p.sim.check_state()
+    g = p.sim.cc_data.grid
+    assert p.sim.n == 76 and p.sim.cc_data.t == pytest.approx(0.2, rel=1e-12)
+    U = p.sim.cc_data.data.numpy()[g.ilo:g.ihi + 1, g.jlo:g.jhi + 1]
+    for k, name in enumerate(("density", "energy", "x_momentum", "y_momentum")):
+        scale = max(np.abs(stored[name]).max(), 1.0)
+        assert np.abs(U[..., k] - stored[name]).max() <= 1e-12 * scale, name
+
+
+def test_multigrid_matches_the_stored_reference_golden():
+    from pyro2_b200.multigrid import MG
+    stored = np.load(os.path.join(GOLDEN, "refh5_mg_poisson_dirichlet.npz"))
+    a = MG.CellCenterMG2d(256, 256)
+    x, y = a.x2d.t(), a.y2d.t()
+    a.init_zeros()
+    a.init_RHS(-2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2)))
+    a.solve(rtol=1.e-11)
+    assert np.array_equal(a.get_solution().numpy()[1:-1, 1:-1], stored["v"])

@@ -2,6 +2,8 @@
 reference (tests/golden/make_golden.py) -- this is what pins the oracle.  Tolerances: the
 compressible step matches the reference to ~1e-15 per step (np.dot / pow ordering), 1e-12 after
 tens of steps; multigrid solutions are bit-identical; dt is bit-identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -259,3 +261,63 @@ def test_lm_atm_run_matches_reference(fname):
         assert raw >= float(dt) * (1 - 1e-15)          # the driver only ever shrinks the method's dt
         oracle.lm_evolve(S, base, prm, float(dt))
     assert np.array_equal(S, z["P"])
+
+
+# ---- the regression files the reference itself stores (read with tests/h5lite.py, tests/golden/make_h5_golden.py) -------
+def _refh5(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"refh5_{name}.npz"))
+    meta = dict(s.split("=", 1) for s in z["meta"])
+    return z, meta
+
+
+def mg_test_simple_rhs(n):
+    """right-hand side of pyro/multigrid/examples/mg_test_simple.py on the (n + 2)^2 cell centres"""
+    x = (np.arange(n + 2) - 0.5) / n
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    return -2.0 * ((1.0 - 6.0 * X ** 2) * Y ** 2 * (1.0 - Y ** 2) + (1.0 - 6.0 * Y ** 2) * X ** 2 * (1.0 - X ** 2))
+
+
+def test_h5_reader_against_the_reference_files():
+    """tests/h5lite.py on the reference's own snapshots: groups, attributes (incl. variable-length strings), contiguous
+    datasets; the committed fixtures hold exactly these bytes"""
+    ref = "/root/reference/pyro"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference tree is not on this box")
+    import h5lite
+    f = h5lite.File(os.path.join(ref, "compressible/tests/sod_x_0076.h5"))
+    assert f.keys() == ["BC", "aux", "grid", "runtime parameters", "state"]
+    assert f.attrs()["nsteps"] == 76 and f.attrs()["problem"] == "sod" and f.attrs("grid")["nx"] == 128
+    assert f.attrs("runtime parameters")["compressible.riemann"] == "HLLC"
+    assert f.attrs("state/y-momentum")["ylb"] == "reflect-odd"
+    z, _ = _refh5("sod_x_0076")
+    for name in ("density", "energy", "x-momentum", "y-momentum"):
+        assert np.array_equal(f[f"state/{name}/data"], z[name.replace("-", "_")])
+    g = h5lite.File(os.path.join(ref, "multigrid/tests/mg_poisson_dirichlet.h5"))
+    zm, _ = _refh5("mg_poisson_dirichlet")
+    assert np.array_equal(g["state/v/data"], zm["v"]) and g["state/v/data"].shape == (256, 256)
+
+
+def test_oracle_reproduces_the_stored_sod_golden():
+    """pyro/compressible/tests/sod_x_0076.h5 -- the file the reference's own regression test compares against"""
+    z, rp, inputs = load_comp("sod_x")
+    stored, meta = _refh5("sod_x_0076")
+    assert int(meta["nsteps"]) == int(z["n"]) == 76 and float(meta["time"]) == pytest.approx(float(z["t"]), rel=1e-14)
+    U, dts, ng = _run_oracle(z, rp, fix_dt=inputs.get("driver.fix_dt", -1.0))
+    v = (slice(ng, -ng), slice(ng, -ng))
+    for k, name in enumerate(("density", "energy", "x_momentum", "y_momentum")):
+        assert np.abs(U[v][..., k] - stored[name]).max() <= 2e-14, name       # another machine's libm / numba: round-off
+
+
+def test_oracle_reproduces_the_stored_multigrid_golden():
+    """pyro/multigrid/tests/mg_poisson_dirichlet.h5: the right-hand side bit for bit, then the solution bit for bit"""
+    import hashlib
+    stored, meta = _refh5("mg_poisson_dirichlet")
+    n = int(meta["grid.nx"])
+    f = mg_test_simple_rhs(n)
+    assert hashlib.sha256(np.ascontiguousarray(f[1:-1, 1:-1]).tobytes()).hexdigest() == str(stored["f_sha256"])
+    o = oracle.MG(n)
+    o.init_zeros()
+    o.init_RHS(f)
+    o.solve(rtol=1.e-11)
+    assert np.array_equal(o.get_solution()[1:-1, 1:-1], stored["v"])
+    assert np.abs(o.plane(o.nlevels - 1, "r")[1:-1, 1:-1] - stored["r"]).max() <= 1e-18 + 1e-12 * np.abs(stored["r"]).max()
