@@ -14,7 +14,7 @@ sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), ROOT]
 import oracle  # noqa: E402
 from emu_util import EmuLm, load_lm_emu, load_mg_emu  # noqa: E402
 from golden_util import load_flow  # noqa: E402
-from test_oracle_golden import _lm_setup  # noqa: E402
+from oracle_runs import lm_setup as _lm_setup  # noqa: E402
 
 if __name__ == "__main__":
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 30

@@ -1,5 +1,5 @@
 """Randomised end-to-end comparison: Pyro("compressible") runs on the emulated device (the product's Python layer over
-the host-compiled kernels, tests/emu_device.py) against the oracle's driver loop (tests/test_oracle_golden._run_oracle)
+the host-compiled kernels, tests/emu_device.py) against the oracle's driver loop (tests/oracle_runs.run_compressible)
 started from the same initial state -- random problems, boundary overrides, Riemann solvers, limiters, gravity.  This
 exercises the host-side plumbing (parameter structs, boundary hooks, source flags, time-step control).
 Development tool (CPU only):
@@ -16,7 +16,7 @@ sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), ROOT]
 import emu_device  # noqa: E402
 import oracle  # noqa: E402
 from conftest import state_errors  # noqa: E402
-from test_oracle_golden import _run_oracle  # noqa: E402
+from oracle_runs import run_compressible as _run_oracle  # noqa: E402
 
 PROBLEMS = {  # problem -> (base inputs, allowed y boundaries, allowed x boundaries)
     "sedov": ({"mesh.nx": 24, "mesh.ny": 20, "sedov.r_init": 0.12}, ["outflow", "reflect", "periodic"], ["outflow", "reflect", "periodic"]),

@@ -8,7 +8,7 @@ import pytest
 import oracle
 from emu_util import EmuLm, load_lm_emu, load_mg_emu
 from golden_util import load_flow
-from test_oracle_golden import _lm_setup
+from oracle_runs import lm_setup as _lm_setup
 
 
 @pytest.mark.parametrize("fname,nsteps", [("lm_bubble32.npz", 3), ("lm_bubble64_lim1.npz", 2)])
