@@ -109,6 +109,8 @@ class File:
             return np.dtype(f"S{size}"), size
         if cls == 9:                           # variable length (h5py's str attributes): a global-heap reference
             return "vlen", size
+        if cls == 8:                           # enumeration (h5py's bool): the base integer type follows the 8-byte header
+            return self._dtype(d + 8)[0], size
         raise ValueError(f"datatype class {cls} is not handled")
 
     def _global_heap_object(self, addr, index):
@@ -181,3 +183,56 @@ class File:
                 val = val[0].item()
             out[name] = val
         return out
+
+
+# ---- an h5py-shaped, read-only view (what pyro2_b200.util.io_pyro.read touches: File as a context manager, groups that
+#      index / iterate / test membership, .attrs mappings, datasets through np.asarray / [...]) ------------------------------
+class Node:
+    def __init__(self, f, path):
+        self._f, self._path = f, path
+
+    @property
+    def attrs(self):
+        return self._f.attrs(self._path)
+
+    def _is_group(self):
+        try:
+            self._f.keys(self._path)
+            return True
+        except Exception:          # noqa: BLE001  (a dataset has no symbol-table message)
+            return False
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            if key not in self._f.keys(self._path):
+                raise KeyError(key)
+            return Node(self._f, f"{self._path}/{key}")
+        return self._f[self._path][key]
+
+    def __contains__(self, key):
+        return key in self._f.keys(self._path)
+
+    def __iter__(self):
+        return iter(self._f.keys(self._path))
+
+    def __len__(self):
+        return len(self._f.keys(self._path))
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._f[self._path]
+        return a if dtype is None else a.astype(dtype)
+
+
+class H5pyFile(Node):
+    """`with h5lite.H5pyFile(name, "r") as f:` -- stands in for h5py.File when READING the reference's files"""
+
+    def __init__(self, filename, mode="r"):
+        if mode != "r":
+            raise ValueError("h5lite only reads")
+        super().__init__(File(filename), "")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
