@@ -293,7 +293,7 @@ def test_user_defined_bc_callback_runs_after_standard_fill():
 
 
 @pytest.mark.parametrize("nx,ny,nchunks,problem", [(256, 128, 7, "sedov"), (96, 200, 16, "sedov"), (128, 64, 1, "quad")])
-def test_streamed_steps_are_bit_identical_to_resident_steps(nx, ny, nchunks, problem):
+def test_streamed_steps_are_bit_identical_to_resident_steps(nx, ny, nchunks, problem, nsteps=12):
     """Pyro.single_step_streamed(): the state lives in pinned host memory, blocks of rows travel host -> device -> host
     while the neighbouring blocks are swept.  Every dt and the final state must equal the resident run's bit for bit
     (blocks are x-slabs: interior block faces get the artificial viscosity, the global +x face does not)."""
@@ -310,7 +310,7 @@ def test_streamed_steps_are_bit_identical_to_resident_steps(nx, ny, nchunks, pro
     bufs = [torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True) for _ in range(2)]
     bufs[0].copy_(planes)
     dts_ref, dts = [], []
-    for step in range(12):
+    for step in range(nsteps):
         ref.single_step()
         dts_ref.append(ref.sim.dt)
         p.single_step_streamed(bufs[step % 2], bufs[(step + 1) % 2], nchunks=nchunks)
@@ -320,12 +320,12 @@ def test_streamed_steps_are_bit_identical_to_resident_steps(nx, ny, nchunks, pro
     torch.cuda.synchronize()
     g = p.sim.cc_data.grid
     assert dts == dts_ref
-    host = bufs[12 % 2][:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1]
+    host = bufs[nsteps % 2][:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1]
     want = ref.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1].cpu()
     assert torch.equal(host, want)
     # and a step fed from a buffer the previous step did not write takes the reduction path, same bits
     other = torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True)
-    other.copy_(bufs[12 % 2])
+    other.copy_(bufs[nsteps % 2])
     ref.single_step()
     p.single_step_streamed(other, bufs[1], nchunks=nchunks)
     torch.cuda.synchronize()

@@ -159,8 +159,8 @@ def test_streamed_step_on_emulated_device(monkeypatch):
         return real_empty(*a, **k)
     monkeypatch.setattr(torch, "empty", empty)
     with emu_device.emulated_device():
-        body(64, 48, 4, "sedov")
-        body(48, 40, 1, "quad")
+        body(64, 48, 4, "sedov", nsteps=5)
+        body(48, 40, 1, "quad", nsteps=3)
 
 
 def test_scale_tests_rehearsed_small():
@@ -191,7 +191,8 @@ def test_stored_reference_goldens_rehearsed():
     import emu_device
     import test_gpu_zzz_reference_h5 as t
     import os
+    if not os.environ.get("P2B_FULL_TESTS"):          # ~100 s of emulated Sod steps + ~100 s of emulated 256^2 V-cycles
+        pytest.skip("set P2B_FULL_TESTS=1 (last full run: passed, see profiles/README.md)")
     with emu_device.emulated_device():
         t.test_pyro_sod_matches_the_stored_reference_golden()
-        if os.environ.get("P2B_FULL_TESTS"):          # ~100 s of emulated 256^2 V-cycles
-            t.test_multigrid_matches_the_stored_reference_golden()
+        t.test_multigrid_matches_the_stored_reference_golden()
