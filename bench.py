@@ -213,8 +213,18 @@ def cpu_incompressible(n):
     return time.perf_counter() - t0, cyc
 
 
+_HOST_THREADS = None
+
+
 def host_threads():
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    """threads the CPU legs can use -- taken once, BEFORE an OpenMP runtime binds the calling thread to its first place
+    (with OMP_PROC_BIND the main thread's affinity mask shrinks to one core and would be reported as `cores: 1`)"""
+    global _HOST_THREADS
+    if _HOST_THREADS is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        env = os.environ.get("OMP_NUM_THREADS", "")
+        _HOST_THREADS = min(n, int(env)) if env.isdigit() and int(env) > 0 else n
+    return _HOST_THREADS
 
 
 def run_reference(args, rank):
@@ -340,8 +350,13 @@ def main():
     # OpenMP pinning is for the CPU legs only (reference arm; cpu_baseline at N = 1).  Under torchrun every rank would bind
     # its threads -- the main thread included -- to the SAME first cores: eight GPU ranks sharing one core made every
     # launch-bound leg 10x slower in an N = 8 run of this round.
+    if args.impl == "reference" and world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun exports OMP_NUM_THREADS=1 to its workers when the variable is unset; the reference arm is ONE process
+        # (rank 0) and is meant to use every host thread it can, exactly as at N = 1
+        os.environ.pop("OMP_NUM_THREADS")
     if args.impl == "reference" or world == 1:
         pin_host_threads()
+    host_threads()
     if args.impl == "reference":
         run_reference(args, rank)
         return
