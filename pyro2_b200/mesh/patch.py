@@ -343,7 +343,26 @@ class CellCenterData2d:
         g = self.grid
         planes = self.planes if planes is None else planes
         periodic = bcs[0].xlb == "periodic"
+        has_ext = any(t in bnd.ext_bcs for b in bcs for t in b.names())
+        # The halo rows of an inter-slab boundary stand for ordinary interior cells of the single domain.  Those across the
+        # PERIODIC SEAM (low side of the first slab, high side of the last) stand for its x ghost rows, and there the
+        # reference's variable-by-variable fill matters when a user hook reads other variables: the hse energy takes the
+        # momenta of the base row over the full x range, x ghost rows included, and the momenta are refilled only AFTER the
+        # energy (patch.py:575-624, compressible/BC.py:62-76) -- so it sees their ghost rows as the previous fill left
+        # them.  Reproduced here: the seam rows are kept as they were, and each variable's fresh rows are put in place
+        # when its turn comes.  (Without this a decomposed periodic-x / hse-y run differs from the single-domain run in the
+        # corner ghost energies: found by scripts/fuzz_compressible_slabs_gloo.py.)
+        seam = []
+        if has_ext and periodic and len(bcs) > 1:
+            if self.decomposition.rank == 0:
+                seam.append(slice(0, g.ng))
+            if self.decomposition.rank == self.decomposition.size - 1:
+                seam.append(slice(g.ng + g.nx, g.ng + g.nx + g.ng))
+        kept = [planes[:, rows, :].clone() for rows in seam]
         self.decomposition.exchange(planes, g.nx, g.ng, periodic=periodic)
+        fresh = [planes[:, rows, :].clone() for rows in seam]
+        for rows, old in zip(seam, kept):
+            planes[:, rows, :] = old
         lo_int, hi_int = self.decomposition.interior_sides(periodic)
         names = []
         for b in bcs:
@@ -353,7 +372,7 @@ class CellCenterData2d:
             if hi_int:
                 n[1] = None
             names.append(tuple(n))
-        if not any(t in bnd.ext_bcs for b in bcs for t in b.names()):
+        if not has_ext:
             ops.fill_ghost(planes, g.nx, g.ny, g.ng, names)
             return
         # user-defined boundaries: variable by variable like the single-domain fill (standard types, then the hooks in
@@ -363,6 +382,8 @@ class CellCenterData2d:
         # (fill_BC(name) exchanges that variable's planes alone: a hook that reads OTHER variables then sees their halo
         # rows as of the last full fill -- the solvers here only ever fill all variables together.)
         for k, b in enumerate(bcs):
+            for rows, new in zip(seam, fresh):
+                planes[k, rows, :] = new[k]
             ops.fill_ghost(planes[k:k + 1], g.nx, g.ny, g.ng, [names[k]])
             name = self.names[first + k]
             for side, btype, interior in zip(("xlb", "xrb", "ylb", "yrb"), b.names(), (lo_int, hi_int, False, False)):

@@ -196,3 +196,29 @@ def test_stored_reference_goldens_rehearsed():
     with emu_device.emulated_device():
         t.test_pyro_sod_matches_the_stored_reference_golden()
         t.test_multigrid_matches_the_stored_reference_golden()
+
+
+
+@pytest.mark.parametrize("case,solver,problem", [("advection", "advection", "smooth"), ("burgers", "burgers", "test"),
+                                                 ("diffusion", "diffusion", "gaussian")])
+def test_stored_flow_goldens_rehearsed(case, solver, problem):
+    """tests/test_gpu_zzz_reference_h5.py's flow runs on the emulated device: this build's problem setups, time-step
+    control and kernels reproduce the reference's stored advection / Burgers / diffusion files bit for bit"""
+    import os
+    import emu_device
+    import test_gpu_zzz_reference_h5 as t
+    if case == "diffusion" and not os.environ.get("P2B_FULL_TESTS"):          # 164 emulated 128^2 multigrid solves: ~9 min
+        pytest.skip("set P2B_FULL_TESTS=1 (last full run: passed, see profiles/README.md)")
+    with emu_device.emulated_device():
+        t.test_pyro_flow_run_matches_the_stored_reference_golden(case, solver, problem)
+
+
+def test_stored_incompressible_golden_rehearsed():
+    """the 216-step shear run against pyro/incompressible/tests/shear_128_0216.h5 on the emulated device (~25 min)"""
+    import os
+    import emu_device
+    import test_gpu_zzz_reference_h5 as t
+    if not os.environ.get("P2B_FULL_TESTS"):
+        pytest.skip("set P2B_FULL_TESTS=1 (last full run: passed, see profiles/README.md)")
+    with emu_device.emulated_device():
+        t.test_pyro_incompressible_run_matches_the_stored_reference_golden()

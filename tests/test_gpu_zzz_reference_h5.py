@@ -3,6 +3,14 @@ pyro's .h5 goldens by tests/golden/make_h5_golden.py with the pure-Python reader
 
   pyro/compressible/tests/sod_x_0076.h5         Pyro("compressible"), problem sod, 128 x 10, 76 steps   (1e-11 of scale)
   pyro/multigrid/tests/mg_poisson_dirichlet.h5  CellCenterMG2d(256, 256).solve(rtol=1e-11)             (solution bit for bit)
+  pyro/advection/tests/smooth_0040.h5           Pyro("advection"), smooth, 32^2, 40 steps               (bit for bit)
+  pyro/burgers/tests/test_0051.h5               Pyro("burgers"), test, 128^2, 51 steps                  (bit for bit)
+  pyro/diffusion/tests/gaussian_0164.h5         Pyro("diffusion"), gaussian, 128^2, 164 multigrid solves (bit for bit)
+  pyro/incompressible/tests/shear_128_0216.h5   Pyro("incompressible"), shear, 128^2, 216 steps         (2e-12 of each variable's
+                                                maximum: the unmodified reference run on this image is itself 6e-13 away)
+
+The flow runs start from the runtime parameters recorded INSIDE the stored file (tests/golden/pin_stored_goldens.py), set
+up the problem with this build's own problem modules and compute their own time steps.
 
 (The file sorts last on purpose: these cases were added after the round's last GPU run and are rehearsed on the emulated
 device, tests/test_gpu_rehearsal.py.)"""
@@ -42,3 +50,39 @@ def test_multigrid_matches_the_stored_reference_golden():
     a.init_RHS(-2.0 * ((1.0 - 6.0 * x ** 2) * y ** 2 * (1.0 - y ** 2) + (1.0 - 6.0 * y ** 2) * x ** 2 * (1.0 - x ** 2)))
     a.solve(rtol=1.e-11)
     assert np.array_equal(a.get_solution().numpy()[1:-1, 1:-1], stored["v"])
+
+
+@pytest.mark.parametrize("case,solver,problem", [("advection", "advection", "smooth"), ("burgers", "burgers", "test"),
+                                                 ("diffusion", "diffusion", "gaussian")])
+def test_pyro_flow_run_matches_the_stored_reference_golden(case, solver, problem):
+    from golden_util import _parse
+    from pyro2_b200.pyro_sim import Pyro
+    z = np.load(os.path.join(GOLDEN, f"refh5_{case}.npz"))
+    inputs = {s.split("=", 1)[0]: _parse(s.split("=", 1)[1]) for s in z["inputs"]}
+    inputs = {k: v for k, v in inputs.items() if not k.startswith("particles.")}       # not part of this build (and off)
+    p = Pyro(solver)
+    p.initialize_problem(problem, inputs_dict=dict(inputs, **{"driver.max_steps": 100000, "driver.verbose": 0}))
+    while not p.sim.finished():
+        p.single_step()
+    assert p.sim.n == int(z["n"]) and p.sim.cc_data.t == pytest.approx(float(z["t"]), rel=1e-12)
+    for name, stored in zip(z["names"], z["stored"]):
+        assert np.array_equal(p.sim.cc_data.get_var(str(name)).v().numpy(), stored), name
+
+
+def test_pyro_incompressible_run_matches_the_stored_reference_golden():
+    from golden_util import _parse
+    from pyro2_b200.pyro_sim import Pyro
+    z = np.load(os.path.join(GOLDEN, "refh5_incomp.npz"))
+    inputs = {s.split("=", 1)[0]: _parse(s.split("=", 1)[1]) for s in z["inputs"]}
+    inputs = {k: v for k, v in inputs.items() if not k.startswith("particles.")}
+    p = Pyro("incompressible")
+    p.initialize_problem("shear", inputs_dict=dict(inputs, **{"driver.max_steps": 100000, "driver.verbose": 0}))
+    dts = []
+    while not p.sim.finished():
+        p.single_step()
+        dts.append(p.sim.dt)
+    assert p.sim.n == int(z["n"]) == 216 and p.sim.cc_data.t == pytest.approx(float(z["t"]), rel=1e-12)
+    assert dts == [float(d) for d in z["dts"]]                  # the reference's own time steps (run on this image), bit for bit
+    for name, stored in zip(z["names"], z["stored"]):
+        got = p.sim.cc_data.get_var(str(name)).v().numpy()
+        assert np.abs(got - stored).max() <= 2e-12 * np.abs(stored).max(), name
