@@ -195,13 +195,6 @@ class Node:
     def attrs(self):
         return self._f.attrs(self._path)
 
-    def _is_group(self):
-        try:
-            self._f.keys(self._path)
-            return True
-        except Exception:          # noqa: BLE001  (a dataset has no symbol-table message)
-            return False
-
     def __getitem__(self, key):
         if isinstance(key, str):
             if key not in self._f.keys(self._path):
