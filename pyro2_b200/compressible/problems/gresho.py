@@ -26,7 +26,12 @@ def init_data(my_data, rp):
     gamma = rp.get_param("eos.gamma")
     rho0, mach = rp.get_param("gresho.rho0"), rp.get_param("gresho.mach")
     rr, t_r = rp.get_param("gresho.r"), rp.get_param("gresho.t_r")
-    x_center = 0.5 * (g.x[0] + g.x[-1])
+    # the reference takes the midpoint of the cell-centre array, ghost cells included (gresho.py:37); on an x-slab of a
+    # decomposed run that array covers the slab only, so the first and last centre of the WHOLE domain are rebuilt with
+    # the grid's own expressions (mesh/patch.py) -- same bits as g.x[0], g.x[-1] of the single domain
+    ends = np.array([0, g.nx_global + 2 * g.ng - 1])
+    x_ends = 0.5 * (((ends - g.ng) * g.dx + g.xmin) + ((ends + 1.0 - g.ng) * g.dx + g.xmin))
+    x_center = 0.5 * (x_ends[0] + x_ends[1])
     y_center = 0.5 * (g.y[0] + g.y[-1])
     q_r = 0.4 * np.pi * (g.xmax - g.xmin) / t_r
     # p0 from the requested Mach number at the velocity peak u_phi = 5 rr, where p = p0 + 12.5 rr^2

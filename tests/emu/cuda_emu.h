@@ -63,6 +63,8 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 // cudaMalloc is only used for allocations that other ranks map (p2b_shared_alloc): POSIX shared memory, so that the
 // ranks may be threads of one process or separate processes (the gloo tests).  The "IPC handle" is the segment's name.
+#include <cerrno>
+#include <cstdint>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -73,14 +75,28 @@ namespace emu {
 struct Shm { std::string name; size_t bytes; bool owner; };
 inline std::map<void*, Shm>& shm_table() { static std::map<void*, Shm> t; return t; }
 inline std::mutex& shm_mutex() { static std::mutex m; return m; }
+// segments still allocated when the process ends are unlinked (a test that fails, or a Python exit that never freed its
+// handles, used to leave them in /dev/shm -- and a later process with the same recycled pid then failed to allocate)
+struct ShmJanitor {
+    ~ShmJanitor() { for (auto& kv : shm_table()) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); }
+};
+inline ShmJanitor& shm_janitor() { static ShmJanitor j; return j; }
 }  // namespace emu
 inline cudaError_t cudaMalloc(void** p, size_t n)
 {
     static int counter = 0;
     std::lock_guard<std::mutex> lk(emu::shm_mutex());
+    emu::shm_table();
+    emu::shm_janitor();               // constructed after the table: destroyed before it
     char name[64];
-    snprintf(name, sizeof name, "/p2b_emu_%d_%d", (int)getpid(), counter++);
+    // pid + this library's own counter address + counter: unique among live segments, so a segment that already has
+    // the name was left behind by a dead process whose pid has been recycled -- remove it and retry
+    snprintf(name, sizeof name, "/p2b_emu_%d_%lx_%d", (int)getpid(), (unsigned long)(reinterpret_cast<uintptr_t>(&counter) >> 4 & 0xffffff), counter++);
     int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 && errno == EEXIST) {
+        shm_unlink(name);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    }
     if (fd < 0) return 1;
     if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); return 1; }
     void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);

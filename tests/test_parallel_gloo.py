@@ -293,6 +293,8 @@ def _emulated_flow_worker(rank, size, port, solver, problem, inputs, nsteps, q):
     # domain's x GHOST rows, which the hse energy sees as the previous fill left them (regression: differed by 2e-21)
     ("compressible", "bubble", {"mesh.nx": 24, "mesh.ny": 36, "mesh.ymax": 4.0, "mesh.xlboundary": "periodic", "mesh.xrboundary": "periodic",
                                 "mesh.ylboundary": "hse", "mesh.yrboundary": "hse"}, 6, 3),
+    # a setup that places its feature relative to the DOMAIN (regression: the vortex was centred on each slab)
+    ("compressible", "gresho", {"mesh.nx": 20, "mesh.ny": 20}, 3, 2),
     pytest.param("compressible", "convection", {"mesh.nx": 16, "mesh.ny": 72}, 3, 4, marks=_FULL),    # ambient top, heating, sponge
     # lm_atm: explicit stages on slabs, the two variable-coefficient projections replicated after all-gathers
     ("lm_atm", "bubble", {"mesh.nx": 32, "mesh.ny": 32}, 1, 2),
