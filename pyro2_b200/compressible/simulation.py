@@ -339,6 +339,7 @@ class Simulation(NullSimulation):
             myd.fill_BC_all()
         self.compute_timestep()
         prm = self._comp_params()
+        xl_solid = prm.xl_solid
         out = self._alt_planes
         self.clean_state(None)
 
@@ -363,6 +364,7 @@ class Simulation(NullSimulation):
             if known and c + 1 < nchunks:
                 fill_block(c + 1)                   # block c reads 4 rows of block c + 1
             prm.no_avisc_xhi = 1 if c == nchunks - 1 else 0
+            prm.xl_solid = xl_solid if c == 0 else 0           # the solid-wall rule of the CGF solver: the domain's -x face only
             ops.compressible_sweep(dev[:, a - ng:b + ng], out[:, a - ng:b + ng], b - a, ny, ng, g.dx, g.dy, float(self.dt),
                                    prm, self._chunk_scratch[c])
             swept[c].record()

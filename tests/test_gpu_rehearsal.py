@@ -223,3 +223,33 @@ def test_stored_incompressible_golden_rehearsed():
         pytest.skip("set P2B_FULL_TESTS=1 (last full run: passed, see profiles/README.md)")
     with emu_device.emulated_device():
         t.test_pyro_incompressible_run_matches_the_stored_reference_golden()
+
+
+def test_streamed_step_keeps_the_solid_wall_rule_on_the_first_block(monkeypatch):
+    """regression (scripts/fuzz_streamed_emulated.py): with a reflecting -x boundary the CGF solver zeroes the normal
+    velocity on the domain's -x face; the streamed step applied that on the low face of every row block"""
+    import torch
+
+    import emu_device
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "pin_memory"}))
+    inputs = {"mesh.nx": 62, "mesh.ny": 25, "driver.max_steps": 10 ** 6, "driver.tmax": 1e9, "driver.verbose": 0,
+              "mesh.xlboundary": "reflect", "mesh.xrboundary": "outflow", "mesh.ylboundary": "outflow", "mesh.yrboundary": "outflow",
+              "compressible.riemann": "CGF"}
+    with emu_device.emulated_device():
+        from pyro2_b200.pyro_sim import Pyro
+
+        def make():
+            p = Pyro("compressible")
+            p.initialize_problem("kh", inputs_dict=inputs)
+            return p
+        ref, p = make(), make()
+        planes = p.sim.cc_data.planes
+        bufs = [torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True) for _ in range(2)]
+        bufs[0].copy_(planes)
+        for step in range(2):
+            ref.single_step()
+            p.single_step_streamed(bufs[step % 2], bufs[(step + 1) % 2], nchunks=3)
+            assert p.sim.dt == ref.sim.dt
+        g = p.sim.cc_data.grid
+        assert torch.equal(bufs[0][:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1], ref.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1])
