@@ -76,7 +76,12 @@ PROBLEMS = {"sedov": ({"sedov.r_init": 0.15}, ["outflow", "reflect", "periodic"]
             "rt2": ({}, ["periodic"], None),
             "rt_multimode": ({}, ["periodic"], None),
             "heating": ({}, None, None),
-            "ramp": ({"mesh.ny": 16, "nx_per_ny": 4}, None, None)}
+            "ramp": ({"mesh.ny": 16, "nx_per_ny": 4}, None, None),
+            # SphericalPolar grids (slabs along r; CGF only, no user boundaries)
+            "advect@sph": ({"mesh.grid_type": "SphericalPolar", "mesh.xmin": 1.0, "mesh.xmax": 2.0, "mesh.ymin": 0.523, "mesh.ymax": 2.617,
+                            "driver.fix_dt": -1.0}, ["reflect", "outflow"], ["outflow"]),
+            "sedov@sph": ({"mesh.grid_type": "SphericalPolar", "mesh.xmin": 0.2, "mesh.xmax": 1.0, "mesh.ymin": 0.785, "mesh.ymax": 2.355,
+                           "sedov.r_init": 0.3}, ["reflect", "outflow"], ["outflow", "reflect"])}
 
 if __name__ == "__main__":
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 10
@@ -109,6 +114,10 @@ if __name__ == "__main__":
             inputs["mesh.ny"] = 36
         if problem == "rt":
             inputs["compressible.grav"] = -1.0
+        if problem.endswith("@sph"):
+            problem = problem[:-4]
+            inputs["compressible.riemann"] = "CGF"
+            inputs["compressible.grav"] = float(rng.choice([0.0, -0.5]))
         if problem in ("sedov", "quad") and inputs["compressible.limiter"] == 0:
             inputs["compressible.limiter"] = 1          # unlimited slopes at the blast / the contacts go negative
                                                         # (in the single-domain run and in the reference too)
