@@ -365,6 +365,8 @@ class Simulation(NullSimulation):
                 fill_block(c + 1)                   # block c reads 4 rows of block c + 1
             prm.no_avisc_xhi = 1 if c == nchunks - 1 else 0
             prm.xl_solid = xl_solid if c == 0 else 0           # the solid-wall rule of the CGF solver: the domain's -x face only
+            if self._heat_plane is not None:                   # the heating profile is a plane like the state's: same rows
+                prm.heat_profile = self._heat_plane[0, a - ng:].data_ptr()
             ops.compressible_sweep(dev[:, a - ng:b + ng], out[:, a - ng:b + ng], b - a, ny, ng, g.dx, g.dy, float(self.dt),
                                    prm, self._chunk_scratch[c])
             swept[c].record()

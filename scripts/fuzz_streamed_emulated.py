@@ -1,7 +1,7 @@
 """Randomised check of Pyro.single_step_streamed() (host-resident state, row blocks host -> device -> host) against resident
 steps on the emulated device: random grid shapes, block counts, problems, boundary types, Riemann solvers; every dt and the
 final state bit for bit.  Found that the CGF solver's solid-wall rule (xl_solid) was applied at the low-x face of EVERY block
-when the domain's -x boundary reflects.  Development tool (CPU only):
+when the domain's -x boundary reflects, and that every block read the heating profile's FIRST rows.  Development tool (CPU only):
 
     python scripts/fuzz_streamed_emulated.py [ncases] [seed]
 """
@@ -26,13 +26,18 @@ with emu_device.emulated_device():
     for c in range(N):
         nx, ny = int(rng.integers(16, 90)), int(rng.integers(8, 40))
         nchunks = int(rng.integers(1, 24))
-        problem = str(rng.choice(["sedov", "quad", "sod", "advect", "kh"]))
+        problem = str(rng.choice(["sedov", "quad", "sod", "advect", "kh", "heating", "rt", "bubble", "gresho", "acoustic_pulse"]))
         xb = str(rng.choice(["outflow", "reflect"]))
         yb = str(rng.choice(["outflow", "reflect", "periodic"]))
         inputs = {"mesh.nx": nx, "mesh.ny": ny, "driver.max_steps": 10**6, "driver.tmax": 1e9, "driver.verbose": 0,
                   "mesh.xlboundary": xb, "mesh.xrboundary": str(rng.choice([xb, "outflow"])), "mesh.ylboundary": yb, "mesh.yrboundary": yb,
                   "compressible.riemann": str(rng.choice(["HLLC", "CGF", "HLLC_lm"])), "compressible.limiter": int(rng.integers(1, 3))}
-        if problem == "sedov": inputs["sedov.r_init"] = 0.2
+        if problem == "sedov":
+            inputs["sedov.r_init"] = 0.2
+        if problem in ("rt", "bubble"):                 # gravity; their stock hse boundaries are user hooks (refused here)
+            inputs.update({"compressible.grav": -1.0, "mesh.ymax": 3.0})
+            if yb == "periodic":
+                inputs.update({"mesh.ylboundary": "reflect", "mesh.yrboundary": "reflect"})
         def make():
             p = Pyro("compressible"); p.initialize_problem(problem, inputs_dict=inputs); return p
         try:

@@ -225,7 +225,7 @@ def test_stored_incompressible_golden_rehearsed():
         t.test_pyro_incompressible_run_matches_the_stored_reference_golden()
 
 
-def test_streamed_step_keeps_the_solid_wall_rule_on_the_first_block(monkeypatch):
+def test_streamed_step_block_parameters(monkeypatch):
     """regression (scripts/fuzz_streamed_emulated.py): with a reflecting -x boundary the CGF solver zeroes the normal
     velocity on the domain's -x face; the streamed step applied that on the low face of every row block"""
     import torch
@@ -244,6 +244,23 @@ def test_streamed_step_keeps_the_solid_wall_rule_on_the_first_block(monkeypatch)
             p.initialize_problem("kh", inputs_dict=inputs)
             return p
         ref, p = make(), make()
+        planes = p.sim.cc_data.planes
+        bufs = [torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True) for _ in range(2)]
+        bufs[0].copy_(planes)
+        for step in range(2):
+            ref.single_step()
+            p.single_step_streamed(bufs[step % 2], bufs[(step + 1) % 2], nchunks=3)
+            assert p.sim.dt == ref.sim.dt
+        g = p.sim.cc_data.grid
+        assert torch.equal(bufs[0][:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1], ref.sim.cc_data.planes[:, g.ilo:g.ihi + 1, g.jlo:g.jhi + 1])
+        # second regression of the same fuzzer: every block read the FIRST rows of the heating profile plane
+        inputs = {"mesh.nx": 48, "mesh.ny": 32, "driver.max_steps": 10 ** 6, "driver.tmax": 1e9, "driver.verbose": 0}
+
+        def make_heating():
+            q = Pyro("compressible")
+            q.initialize_problem("heating", inputs_dict=inputs)
+            return q
+        ref, p = make_heating(), make_heating()
         planes = p.sim.cc_data.planes
         bufs = [torch.empty(planes.shape, dtype=planes.dtype, pin_memory=True) for _ in range(2)]
         bufs[0].copy_(planes)
