@@ -341,7 +341,11 @@ class Simulation(NullSimulation):
         prm = self._comp_params()
         xl_solid = prm.xl_solid
         out = self._alt_planes
-        self.clean_state(None)
+        small = self.rp.get_param("compressible.small_dens")
+        if not known:
+            self.clean_state(None)                  # the state is resident already
+        # (otherwise the density floor is applied block by block as the rows arrive: after the block's ghost fill, like
+        # clean_state() after fill_BC_all() in the resident step)
 
         def block_bcs(c):
             # an x side of a block that faces another block is left alone (its rows arrive with that block)
@@ -356,6 +360,8 @@ class Simulation(NullSimulation):
             lo = 0 if c == 0 else a
             hi = g.qx if c == nchunks - 1 else b
             ops.fill_ghost(dev[:, lo:hi], hi - lo - 2 * ng, ny, ng, block_bcs(c))
+            if small > -1.e100:
+                dev[0, a:b, g.jlo:g.jhi + 1].clamp_(min=small)
 
         if known:
             fill_block(0)

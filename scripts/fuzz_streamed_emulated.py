@@ -32,6 +32,8 @@ with emu_device.emulated_device():
         inputs = {"mesh.nx": nx, "mesh.ny": ny, "driver.max_steps": 10**6, "driver.tmax": 1e9, "driver.verbose": 0,
                   "mesh.xlboundary": xb, "mesh.xrboundary": str(rng.choice([xb, "outflow"])), "mesh.ylboundary": yb, "mesh.yrboundary": yb,
                   "compressible.riemann": str(rng.choice(["HLLC", "CGF", "HLLC_lm"])), "compressible.limiter": int(rng.integers(1, 3))}
+        if rng.integers(4) == 0:                        # an active density floor (clean_state), applied block by block
+            inputs["compressible.small_dens"] = {"sedov": 0.95, "quad": 0.6, "sod": 0.2}.get(problem, 0.99)
         if problem == "sedov":
             inputs["sedov.r_init"] = 0.2
         if problem in ("rt", "bubble"):                 # gravity; their stock hse boundaries are user hooks (refused here)
