@@ -74,8 +74,10 @@ def one_case(lib, rng):
         ref = oracle.compressible_step(U, ng, dx, dy, dt, prm)
     except AssertionError:
         return None, desc           # the random state went invalid in the oracle as well: not a parity question
-    got, scratch = _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips, heat=heat, src_copy_yhi=int(bc[3] == "ambient"))
     vv = (slice(ng, ng + nx), slice(ng, ng + ny))
+    if not np.isfinite(ref[vv]).all():
+        return None, desc           # e.g. hse ghost cells with a negative pressure (one row, large dy): NaN in the oracle too
+    got, scratch = _emu_step(lib, U, ng, dx, dy, dt, prm, seglen, flips, heat=heat, src_copy_yhi=int(bc[3] == "ambient"))
     errs = [rel_l2(got[vv][..., n], ref[vv][..., n]) for n in range(4)]
     ok = not np.isnan(got[vv]).any() and max(errs) < 1e-12 and scratch[3] == 0
     return ok, dict(desc, errs=[float(f"{e:.2e}") for e in errs], status=int(scratch[3]))
