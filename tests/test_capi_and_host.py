@@ -478,6 +478,51 @@ def test_reader_reads_the_files_the_reference_stores(monkeypatch):
         io_pyro.read(os.path.join(ref, "advection/tests/smooth_0040.h5"), device="cpu")
 
 
+def test_snapshot_layout_matches_a_file_written_by_the_reference(monkeypatch, tmp_path):
+    """Simulation.write against the STRUCTURE of a real file of the reference (pyro/compressible/tests/rt_0945.h5, read
+    with tests/h5lite.py): same root attributes, groups, grid / aux records, per-variable boundary records, dataset names,
+    shapes and types.  The writer's tree comes through the in-memory h5py stand-in (h5py itself is not in this image);
+    this is the writer-side half of the interchange (the reader-side half reads the reference's bytes, test above).
+    Differences, all from the stored file's age: newer reference versions (and this build) also record grid.coord_type,
+    the `ambient` boundary and the sponge / floor parameters; particle parameters are not part of this build."""
+    import sys
+    ref_root = "/root/reference/pyro"
+    if not os.path.isdir(ref_root):
+        pytest.skip("the reference tree is not on this box")
+    import emu_device
+    import fake_h5py
+    import h5lite
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    ref = h5lite.File(os.path.join(ref_root, "compressible/tests/rt_0945.h5"))
+    rp = {k: v for k, v in ref.attrs("runtime parameters").items() if not k.startswith(("vis.", "io.", "particles."))}
+    with emu_device.emulated_device():
+        from pyro2_b200.pyro_sim import Pyro
+        p = Pyro("compressible")
+        p.initialize_problem("rt", inputs_dict=rp)
+        p.sim.write(str(tmp_path / "ours"))
+    f = fake_h5py.File(str(tmp_path / "ours.h5"), "r")
+    assert sorted(f.attrs) == sorted(ref.attrs("")) == ["nsteps", "problem", "solver", "time"]
+    assert (f.attrs["solver"], f.attrs["problem"]) == (ref.attrs("")["solver"], ref.attrs("")["problem"])
+    assert sorted(f) == ref.keys("") == ["BC", "aux", "grid", "runtime parameters", "state"]
+    ours = {k: type(v) for k, v in f["grid"].attrs.items()}
+    assert ours.pop("coord_type") is int
+    assert ours == {k: type(v) for k, v in ref.attrs("grid").items()}
+    assert {k: f["grid"].attrs[k] for k in ours} == ref.attrs("grid")
+    assert dict(f["aux"].attrs) == ref.attrs("aux")
+    assert sorted(f["state"]) == ref.keys("state")
+    for v in ref.keys("state"):
+        assert sorted(f["state"][v]) == ref.keys(f"state/{v}") == ["data"]
+        assert dict(f["state"][v].attrs) == ref.attrs(f"state/{v}")
+        mine, theirs = np.asarray(f["state"][v]["data"]), ref[f"state/{v}/data"]
+        assert mine.shape == theirs.shape and mine.dtype == theirs.dtype == np.float64
+    assert set(ref.keys("BC")) <= set(f["BC"]) and not bool(np.asarray(f["BC"]["hse"])[()]) and not bool(ref["BC/hse"])
+    ours_rp, ref_rp = dict(f["runtime parameters"].attrs), ref.attrs("runtime parameters")
+    assert {k for k in ref_rp if k not in ours_rp} == {"particles.n_particles", "particles.particle_generator"}
+    assert all(k.startswith(("compressible.small_", "sponge.", "io.force_final_output")) for k in ours_rp if k not in ref_rp)
+    for k in ("compressible.grav", "mesh.ylboundary", "rt.amp", "driver.cfl", "eos.gamma", "mesh.nx"):
+        assert ours_rp[k] == ref_rp[k]
+
+
 def test_burgers_verify_shock_speed():
     """burgers/problems/verify.py: the front tracker on two states of the `test` problem (advanced here by the
     oracle) recovers the Rankine-Hugoniot speed sqrt(8) of the 3 -> 1 jump to within the half-cell resolution of
