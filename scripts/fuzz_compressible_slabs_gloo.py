@@ -116,6 +116,9 @@ if __name__ == "__main__":
             inputs["compressible.grav"] = -1.0
         if problem.endswith("@sph"):
             problem = problem[:-4]
+            # the ghost rows must keep r > 0 (the grid refuses otherwise, like the reference's): xmin > ng dx
+            need = int(4 * (inputs["mesh.xmax"] - inputs["mesh.xmin"]) / inputs["mesh.xmin"]) + 1
+            inputs["mesh.nx"] = size * max(inputs["mesh.nx"] // size, -(-need // size))
             inputs["compressible.riemann"] = "CGF"
             inputs["compressible.grav"] = float(rng.choice([0.0, -0.5]))
         if problem in ("sedov", "quad") and inputs["compressible.limiter"] == 0:
