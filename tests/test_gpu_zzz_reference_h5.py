@@ -9,6 +9,10 @@ pyro's .h5 goldens by tests/golden/make_h5_golden.py with the pure-Python reader
   pyro/incompressible/tests/shear_128_0216.h5   Pyro("incompressible"), shear, 128^2, 216 steps         (2e-12 of each variable's
                                                 maximum: the unmodified reference run on this image is itself 6e-13 away)
 
+  pyro/compressible/tests/quad_unsplit_0606.h5  Pyro("compressible"), quad, 256^2, 606 steps            (1e-10 of each variable's
+  pyro/compressible/tests/rt_0945.h5            Pyro("compressible"), rt, 64 x 192, gravity, hse, 945   maximum = north_star's bar; the
+                                                steps through the instability's growth                 oracle: 1e-13 / 4e-13)
+
 The flow runs start from the runtime parameters recorded INSIDE the stored file (tests/golden/pin_stored_goldens.py), set
 up the problem with this build's own problem modules and compute their own time steps.
 
@@ -86,3 +90,25 @@ def test_pyro_incompressible_run_matches_the_stored_reference_golden():
     for name, stored in zip(z["names"], z["stored"]):
         got = p.sim.cc_data.get_var(str(name)).v().numpy()
         assert np.abs(got - stored).max() <= 2e-12 * np.abs(stored).max(), name
+
+
+@pytest.mark.parametrize("case,problem", [("quad", "quad"), ("rt", "rt")])
+def test_pyro_compressible_run_matches_the_stored_reference_golden(case, problem):
+    """the reference's two long compressible regression runs from the parameters inside the stored files, with this build's
+    problem setups and time-step control: same number of steps to tmax, the state within north_star's 1e-10 of each
+    variable's maximum (every second cell of the 256^2 file is kept in the fixture)"""
+    from golden_util import _parse
+    from pyro2_b200.pyro_sim import Pyro
+    z = np.load(os.path.join(GOLDEN, f"refh5_{case}.npz"))
+    inputs = {s.split("=", 1)[0]: _parse(s.split("=", 1)[1]) for s in z["inputs"]}
+    inputs = {k: v for k, v in inputs.items() if not k.startswith("particles.")}
+    p = Pyro("compressible")
+    p.initialize_problem(problem, inputs_dict=dict(inputs, **{"driver.max_steps": 100000, "driver.verbose": 0}))
+    while not p.sim.finished():
+        p.single_step()
+    p.sim.check_state()
+    assert p.sim.n == int(z["n"]) and p.sim.cc_data.t == pytest.approx(float(z["t"]), rel=1e-12)
+    stride = int(z["stride"])
+    for name, stored in zip(z["names"], z["stored"]):
+        got = p.sim.cc_data.get_var(str(name)).v().numpy()[::stride, ::stride]
+        assert np.abs(got - stored).max() <= 1e-10 * np.abs(stored).max(), name
