@@ -92,7 +92,7 @@ def test_pyro_incompressible_run_matches_the_stored_reference_golden():
         assert np.abs(got - stored).max() <= 2e-12 * np.abs(stored).max(), name
 
 
-@pytest.mark.parametrize("case,problem", [("quad", "quad"), ("rt", "rt")])
+@pytest.mark.parametrize("case,problem", [("rt", "rt"), ("quad", "quad")])      # the one case never rehearsed end to end runs last
 def test_pyro_compressible_run_matches_the_stored_reference_golden(case, problem):
     """the reference's two long compressible regression runs from the parameters inside the stored files, with this build's
     problem setups and time-step control: same number of steps to tmax, the state within north_star's 1e-10 of each
